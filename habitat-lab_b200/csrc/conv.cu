@@ -1,0 +1,762 @@
+// hb200 -- implicit-GEMM convolution (forward, data gradient, weight gradient) on tcgen05.
+//
+// One CTA = one 128-row accumulator tile held in TMEM.  The im2col A tile is gathered from the
+// NHWC bf16 activation tensor straight into shared memory with zero-filling cp.async (padding
+// and stride handled by predication, never materialised), the weight tile is a pre-packed
+// shared-memory image copied verbatim, one elected thread issues tcgen05.mma (kind::f16,
+// bf16 x bf16 -> f32) and the epilogue drains TMEM with tcgen05.ld, fusing the GroupNorm
+// statistics (sum / sum of squares per frame x group) or the residual-gradient add.
+//
+//   forward : D[pixel, co]    = sum_{r,s,ci} X[pixel@(r,s), ci] * W[co, r,s,ci]     (K-major)
+//   dgrad   : D[pixel, ci]    = sum_{r,s,co} dY[pixel@(r,s), co] * W[co, r,s,ci]    (K-major)
+//   wgrad   : D[(r,s,ci), co] = sum_{pixel}  X[pixel@(r,s), ci] * dY[pixel, co]     (MN-major,
+//             split over pixel slabs, fp32 atomics into the accumulator)
+//
+// Shared-memory operand layouts (selected at runtime, pinned by hb200_umma_gemm_probe):
+//   layout 0: no-swizzle "interleaved" core matrices: 16-byte vector (row, k8) at
+//             k8 * rows*16 + row*16               (LBO = rows*16, SBO = 128)
+//   layout 1: 128-byte swizzle: (row>>3)*1024 + (row&7)*128 + ((k8 ^ (row&7)) << 4)
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace hb200 {
+void count_launch(int n);
+static int g_umma_layout = 0;
+
+using namespace umma;
+
+constexpr int kStages = 3;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;  // bf16 elements per K chunk (8 x 16-byte vectors)
+
+template <int LAYOUT>
+__device__ __forceinline__ uint32_t tile_off(int row, int k8, int rows_total) {
+  if (LAYOUT == 0) return (uint32_t)(k8 * rows_total + row) << 4;
+  return (uint32_t)((row >> 3) << 10) + (uint32_t)((row & 7) << 7) + (uint32_t)((k8 ^ (row & 7)) << 4);
+}
+template <int LAYOUT>
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t base, int kk, int rows_total) {
+  if (LAYOUT == 0)
+    return make_smem_desc(base + (uint32_t)(kk * 2 * rows_total * 16), (uint32_t)rows_total * 16, 128, kNoSwizzle);
+  return make_smem_desc(base + (uint32_t)(kk * 32), 16, 1024, kSwizzle128B);
+}
+
+struct ConvArgs {
+  const __nv_bfloat16* src;   // gathered activation tensor (x for fwd, dy for dgrad)
+  const __nv_bfloat16* wimg;  // packed weight tile images
+  __nv_bfloat16* out;
+  const __nv_bfloat16* addend;
+  float* stats;
+  int B, SH, SW, SC;  // gathered tensor dims (H, W, C), C power of two
+  int OH, OW, OC;     // output grid and channels
+  int kh, kw, stride, pad;
+  int M, nchunks, cshift, gn_groups;
+};
+
+template <int BN, int MODE, int LAYOUT>
+__global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[kStages];
+  __shared__ uint32_t tmem_slot;
+  constexpr uint32_t kABytes = kTileM * kChunkK * 2;
+  constexpr uint32_t kBBytes = BN * kChunkK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m = blockIdx.x * kTileM + tid;
+  const int n0 = blockIdx.y * BN;
+  const bool row_ok = m < a.M;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&mma_bar[s], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  // output-grid coordinates of this thread's row
+  int ob, op, oq;
+  {
+    const int hw = a.OH * a.OW;
+    const int mm = row_ok ? m : 0;
+    ob = mm / hw;
+    const int rem = mm - ob * hw;
+    op = rem / a.OW;
+    oq = rem - op * a.OW;
+  }
+  const int taps = a.kh * a.kw;
+  const __nv_bfloat16* wtile = a.wimg + (size_t)blockIdx.y * a.nchunks * (BN * kChunkK);
+
+  auto load_chunk = [&](int chunk, int stage) {
+    const uint32_t sa = smem_base + stage * kStageBytes;
+    const uint32_t sb = sa + kABytes;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k0 = (chunk * 8 + j) << 3;
+      const int tap = k0 >> a.cshift;
+      const int c0 = k0 & (a.SC - 1);
+      const int r = tap / a.kw, s = tap - r * a.kw;
+      bool ok = row_ok && tap < taps;
+      int ih, iw;
+      if (MODE == 0) {
+        ih = op * a.stride - a.pad + r;
+        iw = oq * a.stride - a.pad + s;
+        ok = ok && ih >= 0 && ih < a.SH && iw >= 0 && iw < a.SW;
+      } else {
+        const int th = op + a.pad - r, tw = oq + a.pad - s;
+        ih = th / a.stride;
+        iw = tw / a.stride;
+        ok = ok && th >= 0 && tw >= 0 && (ih * a.stride == th) && (iw * a.stride == tw) &&
+             ih < a.SH && iw < a.SW;
+      }
+      const __nv_bfloat16* g =
+          ok ? a.src + ((((size_t)ob * a.SH + ih) * a.SW + iw) << a.cshift) + c0 : a.src;
+      cp_async16(sa + tile_off<LAYOUT>(tid, j, kTileM), g, ok);
+    }
+    const uint4* wsrc = reinterpret_cast<const uint4*>(wtile + (size_t)chunk * (BN * kChunkK));
+#pragma unroll
+    for (int i = 0; i < BN / 16; ++i) {
+      const int v = tid + i * 128;
+      cp_async16(sb + ((uint32_t)v << 4), wsrc + v, true);
+    }
+  };
+
+  constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
+  // ---- software pipeline: cp.async runs kStages-1 chunks ahead of the tensor core ----
+#pragma unroll
+  for (int c = 0; c < kStages - 1; ++c) {
+    if (c < a.nchunks) load_chunk(c, c);
+    cp_async_commit();
+  }
+  for (int c = 0; c < a.nchunks; ++c) {
+    const int stage = c % kStages;
+    cp_async_wait<kStages - 2>();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t sa = smem_base + stage * kStageBytes;
+      const uint32_t sb = sa + kABytes;
+#pragma unroll
+      for (int kk = 0; kk < kChunkK / 16; ++kk)
+        mma_bf16_ss(tmem_base, kmajor_desc<LAYOUT>(sa, kk, kTileM), kmajor_desc<LAYOUT>(sb, kk, BN),
+                    idesc, (c > 0 || kk > 0) ? 1u : 0u);
+      mma_commit(&mma_bar[stage]);
+    }
+    const int nc = c + kStages - 1;
+    if (nc < a.nchunks) {
+      if (c >= 1) mbar_wait(&mma_bar[(c - 1) % kStages], ((c - 1) / kStages) & 1);
+      load_chunk(nc, nc % kStages);
+    }
+    cp_async_commit();
+  }
+  {
+    const int last = a.nchunks - 1;
+    mbar_wait(&mma_bar[last % kStages], (last / kStages) & 1);
+  }
+  fence_after_sync();
+
+  // ---- epilogue: TMEM -> registers -> (stats | + addend) -> bf16 NHWC ----
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int hw = a.OH * a.OW;
+  int seg = 1;  // lanes of a warp that share a frame (power of two), else 1
+  if ((hw & (hw - 1)) == 0) seg = hw < 32 ? hw : 32;
+#pragma unroll 1
+  for (int col0 = 0; col0 < BN; col0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + col0, r);
+    tmem_ld_wait();
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+
+    if (MODE == 0 && a.stats != nullptr) {
+      const int cpg = a.OC / a.gn_groups;  // channels per group (power of two >= 2)
+      float s2[16], q2[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        s2[i] = acc[2 * i] + acc[2 * i + 1];
+        q2[i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
+      }
+      int lg = 0;  // log2(min(cpg,32)) - 1
+      while ((2 << lg) < cpg && lg < 4) ++lg;
+#pragma unroll
+      for (int lvl = 0; lvl < 4; ++lvl) {
+        if (lvl < lg) {
+#pragma unroll
+          for (int i = 0; i < (8 >> lvl); ++i) {
+            s2[i] = s2[2 * i] + s2[2 * i + 1];
+            q2[i] = q2[2 * i] + q2[2 * i + 1];
+          }
+        }
+      }
+      const int ng = 16 >> lg;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        if (off < seg) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < ng) {
+              s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+              q2[i] += __shfl_xor_sync(0xffffffffu, q2[i], off);
+            }
+          }
+        }
+      }
+      if (row_ok && (lane & (seg - 1)) == 0) {
+        const int g0 = (n0 + col0) / cpg;
+        float* dst = a.stats + ((size_t)ob * a.gn_groups + g0) * 2;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (i < ng) {
+            atomicAdd(dst + 2 * i, s2[i]);
+            atomicAdd(dst + 2 * i + 1, q2[i]);
+          }
+        }
+      }
+    }
+    if (row_ok) {
+      const size_t o = (size_t)m * a.OC + n0 + col0;
+      if (MODE == 1 && a.addend != nullptr) {
+        const uint4* ad = reinterpret_cast<const uint4*>(a.addend + o);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float f[8];
+          unpack8(ad[v], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[v * 8 + e] += f[e];
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(a.out + o);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        uint4 u;
+        u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+        u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+        u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+        u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+        dst[v] = u;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient: rows = (tap, ci) (128 per CTA), cols = co, reduction over output pixels
+// ------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* dy;
+  float* dw;  // [(tap, ci)][Co]
+  int B, Hi, Wi, Ci, Ho, Wo, Co, kh, kw, stride, pad;
+  int P;       // output pixels B*Ho*Wo
+  int KW;      // taps * Ci (valid rows)
+  int chunks_per_split;
+  int cshift;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(128) conv_wgrad_kernel(const WgradArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[kStages];
+  __shared__ uint32_t tmem_slot;
+  constexpr uint32_t kABytes = kTileM * kChunkK * 2;
+  constexpr uint32_t kBBytes = BN * kChunkK * 2;
+  constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kLboA = (kTileM / 8) * 128, kLboB = (BN / 8) * 128;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row_base = blockIdx.x * kTileM;
+  const int n0 = blockIdx.y * BN;
+  const long long total_chunks = ((long long)a.P + kChunkK - 1) / kChunkK;
+  const long long c_begin = (long long)blockIdx.z * a.chunks_per_split;
+  long long c_end = c_begin + a.chunks_per_split;
+  if (c_end > total_chunks) c_end = total_chunks;
+  const int nchunks = (int)(c_end - c_begin);
+  if (nchunks <= 0) return;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&mma_bar[s], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  const int kpix = tid & 63;    // pixel within the chunk handled by this thread
+  const int half = tid >> 6;    // 0/1
+  const int taps = a.kh * a.kw;
+  const int hw = a.Ho * a.Wo;
+
+  auto load_chunk = [&](int chunk, int stage) {
+    const uint32_t sa = smem_base + stage * kStageBytes;
+    const uint32_t sb = sa + kABytes;
+    const long long pg = (c_begin + chunk) * kChunkK + kpix;
+    const bool pix_ok = pg < a.P;
+    int b = 0, oh = 0, ow = 0;
+    if (pix_ok) {
+      b = (int)(pg / hw);
+      const int rem = (int)(pg - (long long)b * hw);
+      oh = rem / a.Wo;
+      ow = rem - oh * a.Wo;
+    }
+    const uint32_t koff = (uint32_t)(kpix >> 3) * 0 + (uint32_t)((kpix & 7) << 4);
+    // A: rows (tap, ci) gathered from x
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mb = half * 8 + i;
+      const int row0 = row_base + mb * 8;
+      const int tap = row0 >> a.cshift;
+      const int c0 = row0 & (a.Ci - 1);
+      const int r = tap / a.kw, s = tap - r * a.kw;
+      const int ih = oh * a.stride - a.pad + r, iw = ow * a.stride - a.pad + s;
+      const bool ok = pix_ok && tap < taps && ih >= 0 && ih < a.Hi && iw >= 0 && iw < a.Wi;
+      const __nv_bfloat16* g = ok ? a.x + ((((size_t)b * a.Hi + ih) * a.Wi + iw) << a.cshift) + c0 : a.x;
+      cp_async16(sa + (uint32_t)(kpix >> 3) * kLboA + (uint32_t)mb * 128 + koff, g, ok);
+    }
+    // B: cols co from dy
+#pragma unroll
+    for (int i = 0; i < BN / 16; ++i) {
+      const int nb = half + 2 * i;
+      const __nv_bfloat16* g = pix_ok ? a.dy + (size_t)pg * a.Co + n0 + nb * 8 : a.dy;
+      cp_async16(sb + (uint32_t)(kpix >> 3) * kLboB + (uint32_t)nb * 128 + koff, g, pix_ok);
+    }
+  };
+
+  constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 1, 1);
+#pragma unroll
+  for (int c = 0; c < kStages - 1; ++c) {
+    if (c < nchunks) load_chunk(c, c);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    const int stage = c % kStages;
+    cp_async_wait<kStages - 2>();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t sa = smem_base + stage * kStageBytes;
+      const uint32_t sb = sa + kABytes;
+#pragma unroll
+      for (int kk = 0; kk < kChunkK / 16; ++kk) {
+        // MN-major, no swizzle: SBO = stride between 8-element MN blocks, LBO = between 8-k blocks
+        const uint64_t da = make_smem_desc(sa + kk * 2 * kLboA, kLboA, 128, kNoSwizzle);
+        const uint64_t db = make_smem_desc(sb + kk * 2 * kLboB, kLboB, 128, kNoSwizzle);
+        mma_bf16_ss(tmem_base, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+      }
+      mma_commit(&mma_bar[stage]);
+    }
+    const int nc = c + kStages - 1;
+    if (nc < nchunks) {
+      if (c >= 1) mbar_wait(&mma_bar[(c - 1) % kStages], ((c - 1) / kStages) & 1);
+      load_chunk(nc, nc % kStages);
+    }
+    cp_async_commit();
+  }
+  {
+    const int last = nchunks - 1;
+    mbar_wait(&mma_bar[last % kStages], (last / kStages) & 1);
+  }
+  fence_after_sync();
+
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int row = row_base + tid;
+#pragma unroll 1
+  for (int col0 = 0; col0 < BN; col0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + col0, r);
+    tmem_ld_wait();
+    if (row < a.KW) {
+      float* dst = a.dw + (size_t)row * a.Co + n0 + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// minimal synchronous GEMM used to pin the descriptor encodings on hardware
+// ------------------------------------------------------------------------------------------
+template <int LAYOUT, int MNMAJOR>
+__global__ void __launch_bounds__(128)
+umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Bm,
+                  float* __restrict__ D, int M, int N, int K) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sa = smem_base, sb = smem_base + kTileM * kChunkK * 2;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.x * kTileM;
+  uint32_t ncols = 32;
+  while ((int)ncols < N) ncols <<= 1;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(&tmem_slot, ncols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t idesc = make_idesc_bf16(kTileM, N, MNMAJOR, MNMAJOR);
+  const int nchunks = K / kChunkK;
+  for (int c = 0; c < nchunks; ++c) {
+    if (!MNMAJOR) {
+      // A [M,K] row-major, B [N,K] row-major
+      for (int v = tid; v < kTileM * 8; v += 128) {
+        const int row = v >> 3, j = v & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(A + (size_t)(m0 + row) * K + c * kChunkK + j * 8);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa + tile_off<LAYOUT>(row, j, kTileM)),
+                     "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+      }
+      for (int v = tid; v < N * 8; v += 128) {
+        const int row = v >> 3, j = v & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(Bm + (size_t)row * K + c * kChunkK + j * 8);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb + tile_off<LAYOUT>(row, j, N)),
+                     "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+      }
+    } else {
+      // A given as [K,M] (M contiguous), B as [K,N]
+      const uint32_t lboA = (kTileM / 8) * 128, lboB = (uint32_t)(N / 8) * 128;
+      for (int v = tid; v < kChunkK * (kTileM / 8); v += 128) {
+        const int k = v / (kTileM / 8), mb = v % (kTileM / 8);
+        const uint4 val = *reinterpret_cast<const uint4*>(A + (size_t)(c * kChunkK + k) * M + m0 + mb * 8);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sa + (k >> 3) * lboA + mb * 128 + ((k & 7) << 4)),
+                     "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+      }
+      for (int v = tid; v < kChunkK * (N / 8); v += 128) {
+        const int k = v / (N / 8), nb = v % (N / 8);
+        const uint4 val = *reinterpret_cast<const uint4*>(Bm + (size_t)(c * kChunkK + k) * N + nb * 8);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sb + (k >> 3) * lboB + nb * 128 + ((k & 7) << 4)),
+                     "r"(val.x), "r"(val.y), "r"(val.z), "r"(val.w) : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      for (int kk = 0; kk < kChunkK / 16; ++kk) {
+        uint64_t da, db;
+        if (!MNMAJOR) {
+          da = kmajor_desc<LAYOUT>(sa, kk, kTileM);
+          db = kmajor_desc<LAYOUT>(sb, kk, N);
+        } else {
+          const uint32_t lboA = (kTileM / 8) * 128, lboB = (uint32_t)(N / 8) * 128;
+          da = make_smem_desc(sa + kk * 2 * lboA, lboA, 128, kNoSwizzle);
+          db = make_smem_desc(sb + kk * 2 * lboB, lboB, 128, kNoSwizzle);
+        }
+        mma_bf16_ss(tmem_base, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+      }
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, c & 1);  // fully synchronous: smem is reused next iteration
+    fence_after_sync();
+    __syncthreads();
+  }
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  for (int col0 = 0; col0 < N; col0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(taddr + col0, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(size_t)(m0 + tid) * N + col0 + j] = __uint_as_float(r[j]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------
+// tile images [ntile][chunk][BN x 64 in the smem operand layout]
+__global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img,
+                                   int rows /*N dim*/, int BN, int kc /*channels per tap*/,
+                                   int kc_real, int taps, int kw, int nchunks, int transposed,
+                                   int co, int ci_real, int layout) {
+  // one thread per 16-byte vector of the image
+  const long long nvec = (long long)(rows / BN) * nchunks * BN * 8;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < nvec;
+       v += (long long)gridDim.x * blockDim.x) {
+    const int per_tile = BN * 8;
+    const long long t = v / per_tile;
+    const int within = (int)(v - t * per_tile);
+    const int ntile = (int)(t / nchunks), chunk = (int)(t - (long long)ntile * nchunks);
+    // invert the layout: find (row, k8) stored at vector slot `within`
+    int row, k8;
+    if (layout == 0) {
+      k8 = within / BN;
+      row = within - k8 * BN;
+    } else {
+      const int g = within >> 6, rr = (within >> 3) & 7, pos = within & 7;
+      row = g * 8 + rr;
+      k8 = pos ^ rr;
+    }
+    const int n = ntile * BN + row;
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = chunk * kChunkK + k8 * 8 + e;
+      const int tap = k / kc, c = k - tap * kc;
+      float val = 0.f;
+      if (tap < taps && c < kc_real) {
+        const int r = tap / kw, s = tap - r * kw;
+        const int kh = taps / kw;
+        // forward:    n = co, c = ci : W[co][ci][r][s]
+        // transposed: n = ci, c = co : W[co][ci][r][s]
+        const int o = transposed ? c : n, i = transposed ? n : c;
+        if (o < co && i < ci_real) val = w[(((size_t)o * ci_real + i) * kh + r) * kw + s];
+      }
+      f[e] = val;
+    }
+    reinterpret_cast<uint4*>(img)[v] = pack8(f);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ acc, float* __restrict__ dw, int co,
+                                    int ci_real, int ci_pad, int kh, int kw) {
+  const long long n = (long long)co * ci_real * kh * kw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(i % kw);
+    long long t = i / kw;
+    const int r = (int)(t % kh);
+    t /= kh;
+    const int ci = (int)(t % ci_real);
+    const int o = (int)(t / ci_real);
+    dw[i] = acc[((size_t)(r * kw + s) * ci_pad + ci) * co + o];
+  }
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+static int pick_bn(int n) { return n >= 256 ? 256 : n; }
+
+template <int MODE>
+static int launch_igemm(const ConvArgs& a, int BN, cudaStream_t st) {
+  dim3 grid(cdiv(a.M, kTileM), a.OC / BN);
+  const size_t smem = (size_t)kStages * (kTileM * kChunkK * 2 + BN * kChunkK * 2) + 1024;
+#define HB_CONV_CASE(bn, L)                                                                     \
+  {                                                                                             \
+    auto kern = conv_igemm_kernel<bn, MODE, L>;                                                 \
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, 128, smem, st>>>(a);                                                           \
+  }
+#define HB_CONV_BN(bn)                      \
+  if (g_umma_layout == 0) HB_CONV_CASE(bn, 0) else HB_CONV_CASE(bn, 1)
+  switch (BN) {
+    case 32: HB_CONV_BN(32); break;
+    case 64: HB_CONV_BN(64); break;
+    case 128: HB_CONV_BN(128); break;
+    case 256: HB_CONV_BN(256); break;
+    default:
+      set_last_error("conv: unsupported N tile %d", BN);
+      return HB200_ERR_UNSUPPORTED;
+  }
+#undef HB_CONV_BN
+#undef HB_CONV_CASE
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+static int check_shape(const hb200_conv_shape* s) {
+  HB_CHECK_ARG(s, "conv: null shape");
+  HB_CHECK_ARG(s->batch > 0 && s->hi > 0 && s->wi > 0 && s->kh > 0 && s->kw > 0 && s->stride > 0,
+               "conv: bad shape");
+  HB_CHECK_ARG(is_pow2(s->ci) && s->ci >= 8, "conv: Ci=%d must be a power of two >= 8", s->ci);
+  HB_CHECK_ARG(is_pow2(s->co) && s->co >= 32, "conv: Co=%d must be a power of two >= 32", s->co);
+  HB_CHECK_ARG(s->ho == (s->hi + 2 * s->pad - s->kh) / s->stride + 1 &&
+                   s->wo == (s->wi + 2 * s->pad - s->kw) / s->stride + 1,
+               "conv: output dims inconsistent");
+  return HB200_OK;
+}
+
+}  // namespace hb200
+
+using namespace hb200;
+
+extern "C" int hb200_set_umma_layout(int layout) {
+  HB_CHECK_ARG(layout == 0 || layout == 1, "umma layout must be 0 or 1");
+  g_umma_layout = layout;
+  return HB200_OK;
+}
+extern "C" int hb200_get_umma_layout(void) { return g_umma_layout; }
+
+extern "C" int hb200_conv_fwd(const hb200_bf16* x, const hb200_bf16* w_packed, hb200_bf16* y,
+                              float* gn_stats, int gn_groups, const hb200_conv_shape* s,
+                              hb200_stream_t stream) {
+  int rc = check_shape(s);
+  if (rc) return rc;
+  HB_CHECK_ARG(x && w_packed && y, "conv_fwd: null pointer");
+  if (gn_stats) {
+    HB_CHECK_ARG(gn_groups > 0 && s->co % gn_groups == 0 && is_pow2(s->co / gn_groups) && s->co / gn_groups >= 2,
+                 "conv_fwd: channels per GroupNorm group must be a power of two >= 2");
+  }
+  ConvArgs a;
+  a.src = (const __nv_bfloat16*)x; a.wimg = (const __nv_bfloat16*)w_packed; a.out = (__nv_bfloat16*)y;
+  a.addend = nullptr; a.stats = gn_stats;
+  a.B = s->batch; a.SH = s->hi; a.SW = s->wi; a.SC = s->ci;
+  a.OH = s->ho; a.OW = s->wo; a.OC = s->co;
+  a.kh = s->kh; a.kw = s->kw; a.stride = s->stride; a.pad = s->pad;
+  a.M = s->batch * s->ho * s->wo;
+  a.nchunks = cdiv((long long)s->kh * s->kw * s->ci, kChunkK);
+  a.cshift = ilog2(s->ci);
+  a.gn_groups = gn_groups > 0 ? gn_groups : 1;
+  return launch_igemm<0>(a, pick_bn(s->co), (cudaStream_t)stream);
+}
+
+extern "C" int hb200_conv_dgrad(const hb200_bf16* dy, const hb200_bf16* w_packed_t,
+                                const hb200_bf16* addend, hb200_bf16* dx, const hb200_conv_shape* s,
+                                hb200_stream_t stream) {
+  int rc = check_shape(s);
+  if (rc) return rc;
+  HB_CHECK_ARG(dy && w_packed_t && dx, "conv_dgrad: null pointer");
+  HB_CHECK_ARG(s->ci >= 32, "conv_dgrad: Ci=%d must be >= 32", s->ci);
+  ConvArgs a;
+  a.src = (const __nv_bfloat16*)dy; a.wimg = (const __nv_bfloat16*)w_packed_t; a.out = (__nv_bfloat16*)dx;
+  a.addend = (const __nv_bfloat16*)addend; a.stats = nullptr;
+  a.B = s->batch; a.SH = s->ho; a.SW = s->wo; a.SC = s->co;
+  a.OH = s->hi; a.OW = s->wi; a.OC = s->ci;
+  a.kh = s->kh; a.kw = s->kw; a.stride = s->stride; a.pad = s->pad;
+  a.M = s->batch * s->hi * s->wi;
+  a.nchunks = cdiv((long long)s->kh * s->kw * s->co, kChunkK);
+  a.cshift = ilog2(s->co);
+  a.gn_groups = 1;
+  return launch_igemm<1>(a, pick_bn(s->ci), (cudaStream_t)stream);
+}
+
+extern "C" int hb200_conv_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc,
+                                const hb200_conv_shape* s, hb200_stream_t stream) {
+  int rc = check_shape(s);
+  if (rc) return rc;
+  HB_CHECK_ARG(x && dy && dw_acc, "conv_wgrad: null pointer");
+  WgradArgs a;
+  a.x = (const __nv_bfloat16*)x; a.dy = (const __nv_bfloat16*)dy; a.dw = dw_acc;
+  a.B = s->batch; a.Hi = s->hi; a.Wi = s->wi; a.Ci = s->ci; a.Ho = s->ho; a.Wo = s->wo; a.Co = s->co;
+  a.kh = s->kh; a.kw = s->kw; a.stride = s->stride; a.pad = s->pad;
+  a.P = s->batch * s->ho * s->wo;
+  a.KW = s->kh * s->kw * s->ci;
+  a.cshift = ilog2(s->ci);
+  const int BN = pick_bn(s->co);
+  const int mtiles = cdiv(a.KW, kTileM), ntiles = s->co / BN;
+  const long long total_chunks = cdiv(a.P, kChunkK);
+  int nsplit = (kNumSMs * 4) / (mtiles * ntiles);
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > total_chunks) nsplit = (int)total_chunks;
+  a.chunks_per_split = (int)((total_chunks + nsplit - 1) / nsplit);
+  nsplit = (int)((total_chunks + a.chunks_per_split - 1) / a.chunks_per_split);
+  dim3 grid(mtiles, ntiles, nsplit);
+  const size_t smem = (size_t)kStages * (kTileM * kChunkK * 2 + BN * kChunkK * 2) + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+#define HB_WG_CASE(bn)                                                                          \
+  {                                                                                             \
+    auto kern = conv_wgrad_kernel<bn>;                                                          \
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, 128, smem, st>>>(a);                                                           \
+  }
+  switch (BN) {
+    case 32: HB_WG_CASE(32); break;
+    case 64: HB_WG_CASE(64); break;
+    case 128: HB_WG_CASE(128); break;
+    case 256: HB_WG_CASE(256); break;
+    default:
+      set_last_error("conv_wgrad: unsupported N tile %d", BN);
+      return HB200_ERR_UNSUPPORTED;
+  }
+#undef HB_WG_CASE
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_pack_conv_weight(const float* w_oihw, hb200_bf16* w_packed,
+                                      hb200_bf16* w_packed_t, int co, int ci_real, int ci_pad, int kh,
+                                      int kw, hb200_stream_t stream) {
+  HB_CHECK_ARG(w_oihw && (w_packed || w_packed_t), "pack: null pointer");
+  HB_CHECK_ARG(is_pow2(ci_pad) && ci_pad >= 8 && ci_pad >= ci_real && is_pow2(co) && co >= 32, "pack: bad dims");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = kh * kw;
+  if (w_packed) {
+    const int BN = pick_bn(co), nchunks = cdiv((long long)taps * ci_pad, kChunkK);
+    const long long nvec = (long long)(co / BN) * nchunks * BN * 8;
+    pack_weight_kernel<<<(int)min((nvec + 255) / 256, (long long)kNumSMs * 8), 256, 0, st>>>(
+        w_oihw, (__nv_bfloat16*)w_packed, co, BN, ci_pad, ci_real, taps, kw, nchunks, 0, co, ci_real,
+        g_umma_layout);
+    HB_LAUNCH_OK();
+    count_launch(1);
+  }
+  if (w_packed_t) {
+    HB_CHECK_ARG(ci_pad >= 32, "pack: transposed pack needs Ci >= 32");
+    const int BN = pick_bn(ci_pad), nchunks = cdiv((long long)taps * co, kChunkK);
+    const long long nvec = (long long)(ci_pad / BN) * nchunks * BN * 8;
+    pack_weight_kernel<<<(int)min((nvec + 255) / 256, (long long)kNumSMs * 8), 256, 0, st>>>(
+        w_oihw, (__nv_bfloat16*)w_packed_t, ci_pad, BN, co, co, taps, kw, nchunks, 1, co, ci_real,
+        g_umma_layout);
+    HB_LAUNCH_OK();
+    count_launch(1);
+  }
+  return HB200_OK;
+}
+
+extern "C" size_t hb200_packed_weight_elems(int n_rows, int k_channels, int kh, int kw) {
+  const int nchunks = cdiv((long long)kh * kw * k_channels, kChunkK);
+  return (size_t)n_rows * nchunks * kChunkK;
+}
+
+extern "C" int hb200_unpack_conv_wgrad(const float* dw_acc, float* dw_oihw, int co, int ci_real,
+                                       int ci_pad, int kh, int kw, hb200_stream_t stream) {
+  HB_CHECK_ARG(dw_acc && dw_oihw, "unpack: null pointer");
+  const long long n = (long long)co * ci_real * kh * kw;
+  unpack_wgrad_kernel<<<(int)min((n + 255) / 256, (long long)kNumSMs * 8), 256, 0, (cudaStream_t)stream>>>(
+      dw_acc, dw_oihw, co, ci_real, ci_pad, kh, kw);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_umma_gemm_probe(const hb200_bf16* a, const hb200_bf16* b, float* d, int m, int n,
+                                     int k, int layout, hb200_stream_t stream) {
+  HB_CHECK_ARG(a && b && d, "probe: null pointer");
+  HB_CHECK_ARG(m % 128 == 0 && n % 16 == 0 && n >= 16 && n <= 256 && k % 64 == 0, "probe: bad dims");
+  HB_CHECK_ARG(layout >= 0 && layout <= 2, "probe: layout 0 (K-major no swizzle), 1 (K-major 128B), 2 (MN-major)");
+  const size_t smem = (size_t)(kTileM + n) * kChunkK * 2 + 1024;
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* A = (const __nv_bfloat16*)a;
+  const __nv_bfloat16* B = (const __nv_bfloat16*)b;
+  if (layout == 0) {
+    auto kern = umma_probe_kernel<0, 0>;
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<m / 128, 128, smem, st>>>(A, B, d, m, n, k);
+  } else if (layout == 1) {
+    auto kern = umma_probe_kernel<1, 0>;
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<m / 128, 128, smem, st>>>(A, B, d, m, n, k);
+  } else {
+    auto kern = umma_probe_kernel<0, 1>;
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<m / 128, 128, smem, st>>>(A, B, d, m, n, k);
+  }
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}

@@ -1,0 +1,818 @@
+// hb200 -- HBM-bound passes around the conv stack (all bf16 NHWC, 16-byte vectors):
+// input prep (u8/f32 gather + 2x2 mean + running mean/var), GroupNorm apply / residual / maxpool,
+// GroupNorm backward (reduce + apply), maxpool backward, dtype converts, goal/action embeddings.
+#include "common.cuh"
+
+namespace hb200 {
+void count_launch(int n);
+
+static inline int grid_for(long long n, int bs) {
+  long long g = (n + bs - 1) / bs;
+  const long long cap = (long long)kNumSMs * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+// ======================================================================================
+// input prep  (HB/rl/ddppo/policy/resnet_policy.py:255-271, running_mean_and_var.py:24-78)
+// ======================================================================================
+// one thread = 4 horizontally adjacent pooled pixels (8 input pixels x 2 rows)
+template <bool HAS_RGB, bool HAS_DEPTH>
+__device__ __forceinline__ void pooled4(const uint8_t* __restrict__ rgb, const float* __restrict__ depth,
+                                        size_t row, int H, int W, int py, int px4, float rgb_scale,
+                                        float (&out)[4][4]) {
+  // out[pixel][channel]; channel order rgb(3) then depth(1)
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) out[p][c] = 0.f;
+  if (HAS_RGB) {
+    const uint8_t* base = rgb + (row * H + 2 * py) * (size_t)W * 3 + (size_t)px4 * 8 * 3;
+    uint8_t v[2][24];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint2* src = reinterpret_cast<const uint2*>(base + (size_t)r * W * 3);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const uint2 u = __ldg(src + q);
+        *reinterpret_cast<uint2*>(&v[r][q * 8]) = u;
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        // avg_pool2d sums the window row-major then divides (ATen); u8 is scaled first
+        float s = __fmul_rn((float)v[0][(2 * p) * 3 + c], rgb_scale);
+        s = __fadd_rn(s, __fmul_rn((float)v[0][(2 * p + 1) * 3 + c], rgb_scale));
+        s = __fadd_rn(s, __fmul_rn((float)v[1][(2 * p) * 3 + c], rgb_scale));
+        s = __fadd_rn(s, __fmul_rn((float)v[1][(2 * p + 1) * 3 + c], rgb_scale));
+        out[p][c] = s * 0.25f;
+      }
+  }
+  if (HAS_DEPTH) {
+    const int dc = HAS_RGB ? 3 : 0;
+    const float* base = depth + (row * H + 2 * py) * (size_t)W + (size_t)px4 * 8;
+    float d[2][8];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float4* src = reinterpret_cast<const float4*>(base + (size_t)r * W);
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      d[r][0] = a.x; d[r][1] = a.y; d[r][2] = a.z; d[r][3] = a.w;
+      d[r][4] = b.x; d[r][5] = b.y; d[r][6] = b.z; d[r][7] = b.w;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float s = __fadd_rn(d[0][2 * p], d[0][2 * p + 1]);
+      s = __fadd_rn(s, d[1][2 * p]);
+      s = __fadd_rn(s, d[1][2 * p + 1]);
+      out[p][dc] = s * 0.25f;
+    }
+  }
+}
+
+template <bool HAS_RGB, bool HAS_DEPTH>
+__global__ void __launch_bounds__(256)
+prep_stats_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ depth,
+                  const int32_t* __restrict__ frame_rows, int B, int H, int W, float rgb_scale,
+                  double* __restrict__ stats) {
+  __shared__ double red[32];
+  const int Hp = H / 2, Wq = W / 8;
+  const long long total = (long long)B * Hp * Wq;
+  float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px4 = (int)(i % Wq);
+    const long long t = i / Wq;
+    const int py = (int)(t % Hp);
+    const int f = (int)(t / Hp);
+    float o[4][4];
+    pooled4<HAS_RGB, HAS_DEPTH>(rgb, depth, (size_t)frame_rows[f], H, W, py, px4, rgb_scale, o);
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { s[c] += o[p][c]; q[c] = fmaf(o[p][c], o[p][c], q[c]); }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double a = block_sum((double)s[c], red);
+    const double b = block_sum((double)q[c], red);
+    if (threadIdx.x == 0) { atomicAdd(&stats[c], a); atomicAdd(&stats[8 + c], b); }
+  }
+}
+
+template <bool HAS_RGB, bool HAS_DEPTH>
+__global__ void __launch_bounds__(256)
+prep_apply_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ depth,
+                  const int32_t* __restrict__ frame_rows, int B, int H, int W, float rgb_scale,
+                  const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ out) {
+  const int Hp = H / 2, Wq = W / 8;
+  const long long total = (long long)B * Hp * Wq;
+  float sc[4] = {1, 1, 1, 1}, sh[4] = {0, 0, 0, 0};
+  if (scale_shift) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { sc[c] = scale_shift[c]; sh[c] = scale_shift[8 + c]; }
+  }
+  const int C = (HAS_RGB ? 3 : 0) + (HAS_DEPTH ? 1 : 0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px4 = (int)(i % Wq);
+    const long long t = i / Wq;
+    const int py = (int)(t % Hp);
+    const int f = (int)(t / Hp);
+    float o[4][4];
+    pooled4<HAS_RGB, HAS_DEPTH>(rgb, depth, (size_t)frame_rows[f], H, W, py, px4, rgb_scale, o);
+    uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)f * Hp + py) * (W / 2) + (size_t)px4 * 4) * 8);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) v[c] = fmaf(o[p][c], sc[c], sh[c]);
+      dst[p] = pack8(v);
+    }
+  }
+}
+
+__global__ void prep_finalize_kernel(const double* __restrict__ stats, float* __restrict__ run_mean,
+                                     float* __restrict__ run_var, float* __restrict__ run_count,
+                                     float* __restrict__ scale_shift, int C, long long pix_per_frame,
+                                     int update) {
+  const int c = threadIdx.x;
+  __shared__ float s_count;
+  if (c == 0) s_count = run_count[0];
+  __syncthreads();
+  if (c < C) {
+    float mean = run_mean[c], var = run_var[c];
+    if (update) {
+      const double frames = stats[16];
+      const double n_el = frames * (double)pix_per_frame;
+      const double nm = stats[c] / n_el;
+      double nv = stats[8 + c] / n_el - nm * nm;
+      if (nv < 0) nv = 0;
+      const float count = s_count, new_count = (float)frames;
+      const float new_mean = (float)nm, new_var = (float)nv;
+      // parallel-variance merge, running_mean_and_var.py:50-66
+      const float m_a = var * count, m_b = new_var * new_count;
+      const float d = new_mean - mean;
+      const float M2 = m_a + m_b + d * d * count * new_count / (count + new_count);
+      var = M2 / (count + new_count);
+      mean = (count * mean + new_count * new_mean) / (count + new_count);
+      run_mean[c] = mean;
+      run_var[c] = var;
+    }
+    const float inv = 1.0f / sqrtf(fmaxf(var, 1e-2f));
+    scale_shift[c] = inv;
+    scale_shift[8 + c] = -mean * inv;
+  } else if (c < 8) {
+    scale_shift[c] = 0.f;
+    scale_shift[8 + c] = 0.f;
+  }
+  __syncthreads();
+  if (c == 0 && update) run_count[0] = s_count + (float)stats[16];
+}
+
+// ======================================================================================
+// GroupNorm helpers
+// ======================================================================================
+struct GnP {
+  const float* stats;  // [B,G,2] sum, sumsq
+  const float* gamma;
+  const float* beta;
+  int C, G, lcpg;  // lcpg = log2(channels per group)
+  float inv_m, eps;
+};
+
+// mean/rstd for the 8 channels starting at c0 of frame b
+__device__ __forceinline__ void gn_coeffs(const GnP& p, int b, int c0, float (&mu)[8], float (&rs)[8]) {
+  int prev = -1;
+  float m = 0.f, r = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int g = (c0 + e) >> p.lcpg;
+    if (g != prev) {
+      const float2 st = *reinterpret_cast<const float2*>(p.stats + ((size_t)b * p.G + g) * 2);
+      m = st.x * p.inv_m;
+      const float var = fmaxf(st.y * p.inv_m - m * m, 0.f);
+      r = rsqrtf(var + p.eps);
+      prev = g;
+    }
+    mu[e] = m;
+    rs[e] = r;
+  }
+}
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ out, int B, int hw, int relu) {
+  const int cv = p.C >> 3;
+  const long long total = (long long)B * hw * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) << 3;
+    const int b = (int)(i / ((long long)hw * cv));
+    float mu[8], rs[8], x[8], ga[8], be[8];
+    gn_coeffs(p, b, c0, mu, rs);
+    unpack8(reinterpret_cast<const uint4*>(y)[i], x);
+    load8f(p.gamma + c0, ga);
+    load8f(p.beta + c0, be);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float z = fmaf((x[e] - mu[e]) * rs[e], ga[e], be[e]);
+      x[e] = relu ? fmaxf(z, 0.f) : z;
+    }
+    if (OUT_F32) {
+      float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+      o[0] = make_float4(x[0], x[1], x[2], x[3]);
+      o[1] = make_float4(x[4], x[5], x[6], x[7]);
+    } else {
+      reinterpret_cast<uint4*>(out)[i] = pack8(x);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_residual_relu_kernel(const __nv_bfloat16* __restrict__ y, GnP p, const __nv_bfloat16* __restrict__ res,
+                        GnP rp, int res_is_prenorm, __nv_bfloat16* __restrict__ out, int B, int hw) {
+  const int cv = p.C >> 3;
+  const long long total = (long long)B * hw * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) << 3;
+    const int b = (int)(i / ((long long)hw * cv));
+    float mu[8], rs[8], x[8], ga[8], be[8], r[8];
+    gn_coeffs(p, b, c0, mu, rs);
+    unpack8(reinterpret_cast<const uint4*>(y)[i], x);
+    unpack8(reinterpret_cast<const uint4*>(res)[i], r);
+    load8f(p.gamma + c0, ga);
+    load8f(p.beta + c0, be);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = fmaf((x[e] - mu[e]) * rs[e], ga[e], be[e]);
+    if (res_is_prenorm) {
+      gn_coeffs(rp, b, c0, mu, rs);
+      load8f(rp.gamma + c0, ga);
+      load8f(rp.beta + c0, be);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) r[e] = fmaf((r[e] - mu[e]) * rs[e], ga[e], be[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e] + r[e], 0.f);
+    reinterpret_cast<uint4*>(out)[i] = pack8(x);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfloat16* __restrict__ out,
+                       uint8_t* __restrict__ argmax, int B, int H, int W) {
+  const int cv = p.C >> 3, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) << 3;
+    long long t = i / cv;
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float mu[8], rs[8], ga[8], be[8], best[8];
+    int arg[8];
+    gn_coeffs(p, b, c0, mu, rs);
+    load8f(p.gamma + c0, ga);
+    load8f(p.beta + c0, be);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = 2 * oy - 1 + r;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = 2 * ox - 1 + s;
+        if (ix < 0 || ix >= W) continue;
+        float x[8];
+        unpack8(*reinterpret_cast<const uint4*>(y + (((size_t)b * H + iy) * W + ix) * p.C + c0), x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float z = fmaxf(fmaf((x[e] - mu[e]) * rs[e], ga[e], be[e]), 0.f);
+          if (z > best[e]) { best[e] = z; arg[e] = r * 3 + s; }
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8(best);
+    uint2 a;
+    a.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
+    a.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
+    reinterpret_cast<uint2*>(argmax)[i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax,
+                   __nv_bfloat16* __restrict__ dz, int B, int H, int W, int C) {
+  const int cv = C >> 3, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) << 3;
+    long long t = i / cv;
+    const int ix = (int)(t % W);
+    t /= W;
+    const int iy = (int)(t % H);
+    const int b = (int)(t / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // windows (oy,ox) with 2*o-1 <= i <= 2*o+1
+    const int oy_lo = iy >> 1, oy_hi = (iy + 1) >> 1;
+    const int ox_lo = ix >> 1, ox_hi = (ix + 1) >> 1;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      if (oy >= Ho) continue;
+      const int r = iy - (2 * oy - 1);
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        if (ox >= Wo) continue;
+        const int s = ix - (2 * ox - 1);
+        const int code = r * 3 + s;
+        const size_t o = (((size_t)b * Ho + oy) * Wo + ox) * C + c0;
+        const uint2 a = *reinterpret_cast<const uint2*>(argmax + o);
+        float g[8];
+        unpack8(*reinterpret_cast<const uint4*>(dout + o), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int am = (int)(((e < 4 ? a.x : a.y) >> ((e & 3) * 8)) & 0xff);
+          if (am == code) acc[e] += g[e];
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(dz)[i] = pack8(acc);
+  }
+}
+
+// ---- GroupNorm backward ----------------------------------------------------------------
+// gz = g * mask;  per (frame, channel): a = sum gz, bb = sum gz*xhat
+//   dbeta += a, dgamma += bb, sums[b,g] += (gamma*a, gamma*bb)
+// dy = rstd * (gamma*gz - (S1 + xhat*S2)/m)
+__device__ __forceinline__ void gn_masked_grad(int mask_mode, const float (&g)[8], const float (&z)[8],
+                                               const float (&act)[8], float (&gz)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float m = 1.f;
+    if (mask_mode == 1) m = z[e] > 0.f ? 1.f : 0.f;
+    if (mask_mode == 2) m = act[e] > 0.f ? 1.f : 0.f;
+    gz[e] = g[e] * m;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act,
+                     const __nv_bfloat16* __restrict__ y, GnP p, float* __restrict__ sums,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int hw,
+                     int pix_per_block, int mask_mode) {
+  // block = (frame b, pixel slab); thread = (pixel lane, channel vector)
+  __shared__ float sa[256][9], sb[256][9];
+  const int cv = p.C >> 3;
+  const int slabs = (hw + pix_per_block - 1) / pix_per_block;
+  const int b = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+  const int vec = threadIdx.x % cv, pl = threadIdx.x / cv, npl = blockDim.x / cv;
+  const int c0 = vec << 3;
+  float mu[8], rs[8], ga[8], be[8], a[8], bb[8];
+  gn_coeffs(p, b, c0, mu, rs);
+  load8f(p.gamma + c0, ga);
+  load8f(p.beta + c0, be);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = 0.f; bb[e] = 0.f; }
+  const int p1 = min(hw, (slab + 1) * pix_per_block);
+  for (int pix = slab * pix_per_block + pl; pix < p1; pix += npl) {
+    const size_t o = ((size_t)b * hw + pix) * cv + vec;
+    float gg[8], x[8], z[8], ac[8], gz[8];
+    unpack8(reinterpret_cast<const uint4*>(g)[o], gg);
+    unpack8(reinterpret_cast<const uint4*>(y)[o], x);
+    if (mask_mode == 2) unpack8(reinterpret_cast<const uint4*>(act)[o], ac);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      x[e] = (x[e] - mu[e]) * rs[e];
+      z[e] = fmaf(x[e], ga[e], be[e]);
+      if (mask_mode != 2) ac[e] = 0.f;
+    }
+    gn_masked_grad(mask_mode, gg, z, ac, gz);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] += gz[e]; bb[e] = fmaf(gz[e], x[e], bb[e]); }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sa[threadIdx.x][e] = a[e]; sb[threadIdx.x][e] = bb[e]; }
+  __syncthreads();
+  // thread c (< C) finishes channel c
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const int v = c >> 3, e = c & 7;
+    float ta = 0.f, tb = 0.f;
+    for (int q = 0; q < npl; ++q) { ta += sa[q * cv + v][e]; tb += sb[q * cv + v][e]; }
+    atomicAdd(&dbeta[c], ta);
+    atomicAdd(&dgamma[c], tb);
+    const float gm = p.gamma[c];
+    float* s = sums + ((size_t)b * p.G + (c >> p.lcpg)) * 2;
+    atomicAdd(s, gm * ta);
+    atomicAdd(s + 1, gm * tb);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act,
+                    const __nv_bfloat16* __restrict__ y, GnP p, const float* __restrict__ sums,
+                    __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ gz_out, int B, int hw,
+                    int mask_mode) {
+  const int cv = p.C >> 3;
+  const long long total = (long long)B * hw * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) << 3;
+    const int b = (int)(i / ((long long)hw * cv));
+    float mu[8], rs[8], ga[8], be[8], gg[8], x[8], z[8], ac[8], gz[8], o[8];
+    gn_coeffs(p, b, c0, mu, rs);
+    load8f(p.gamma + c0, ga);
+    load8f(p.beta + c0, be);
+    unpack8(reinterpret_cast<const uint4*>(g)[i], gg);
+    unpack8(reinterpret_cast<const uint4*>(y)[i], x);
+    if (mask_mode == 2) unpack8(reinterpret_cast<const uint4*>(act)[i], ac);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      x[e] = (x[e] - mu[e]) * rs[e];
+      z[e] = fmaf(x[e], ga[e], be[e]);
+      if (mask_mode != 2) ac[e] = 0.f;
+    }
+    gn_masked_grad(mask_mode, gg, z, ac, gz);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float2 s = *reinterpret_cast<const float2*>(sums + ((size_t)b * p.G + ((c0 + e) >> p.lcpg)) * 2);
+      o[e] = rs[e] * (ga[e] * gz[e] - (s.x + x[e] * s.y) * p.inv_m);
+    }
+    reinterpret_cast<uint4*>(dy)[i] = pack8(o);
+    if (gz_out) reinterpret_cast<uint4*>(gz_out)[i] = pack8(gz);
+  }
+}
+
+// ---- converts ------------------------------------------------------------------------------
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ o, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[i], f);
+    reinterpret_cast<float4*>(o)[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(o)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ o, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    load8f(x + 8 * i, f);
+    reinterpret_cast<uint4*>(o)[i] = pack8(f);
+  }
+}
+
+// ---- embeddings (HB/rl/ddppo/policy/resnet_policy.py:658-692, 747-761) ------------------
+__global__ void embed_fwd_kernel(const float* __restrict__ goal, const int64_t* __restrict__ prev_actions,
+                                 const uint8_t* __restrict__ masks, const int32_t* __restrict__ rows,
+                                 const float* __restrict__ w_tgt, const float* __restrict__ b_tgt,
+                                 const float* __restrict__ emb, float* __restrict__ out, int ld, int col0,
+                                 int B) {
+  const long long total = (long long)B * 64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i >> 6), j = (int)(i & 63);
+    const size_t row = (size_t)rows[f];
+    float v;
+    if (j < 32) {
+      const float r = goal[row * 2], th = goal[row * 2 + 1];
+      v = b_tgt[j] + w_tgt[j * 3] * r + w_tgt[j * 3 + 1] * cosf(-th) + w_tgt[j * 3 + 2] * sinf(-th);
+    } else {
+      const int idx = masks[row] ? (int)prev_actions[row] + 1 : 0;
+      v = emb[idx * 32 + (j - 32)];
+    }
+    out[(size_t)f * ld + col0 + j] = v;
+  }
+}
+__global__ void embed_bwd_kernel(const float* __restrict__ goal, const int64_t* __restrict__ prev_actions,
+                                 const uint8_t* __restrict__ masks, const int32_t* __restrict__ rows,
+                                 const float* __restrict__ d_out, int ld, int col0, int B, int n_emb,
+                                 float* __restrict__ d_w, float* __restrict__ d_b, float* __restrict__ d_emb) {
+  // block-local accumulation in smem, one atomic flush per block
+  extern __shared__ float acc[];  // [32*3 + 32 + n_emb*32]
+  const int nacc = 128 + n_emb * 32;
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const long long total = (long long)B * 64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i >> 6), j = (int)(i & 63);
+    const size_t row = (size_t)rows[f];
+    const float d = d_out[(size_t)f * ld + col0 + j];
+    if (j < 32) {
+      const float r = goal[row * 2], th = goal[row * 2 + 1];
+      atomicAdd(&acc[j * 3], d * r);
+      atomicAdd(&acc[j * 3 + 1], d * cosf(-th));
+      atomicAdd(&acc[j * 3 + 2], d * sinf(-th));
+      atomicAdd(&acc[96 + j], d);
+    } else {
+      const int idx = masks[row] ? (int)prev_actions[row] + 1 : 0;
+      atomicAdd(&acc[128 + idx * 32 + (j - 32)], d);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+    const float v = acc[i];
+    if (v == 0.f) continue;
+    if (i < 96) atomicAdd(&d_w[i], v);
+    else if (i < 128) atomicAdd(&d_b[i - 96], v);
+    else atomicAdd(&d_emb[i - 128], v);
+  }
+}
+
+// mask / shift helpers for the recurrent encoder
+__global__ void rnn_shift_mask_kernel(const float* __restrict__ h_seq, const float* __restrict__ h0,
+                                      long long h0_stride, const uint8_t* __restrict__ masks,
+                                      float* __restrict__ h_in, int T, int n, int H) {
+  const long long total = (long long)T * n * H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % H);
+    const long long tn = i / H;
+    const int s = (int)(tn % n);
+    const int t = (int)(tn / n);
+    const float prev = (t == 0) ? h0[(size_t)s * h0_stride + k] : h_seq[i - (long long)n * H];
+    h_in[i] = masks[tn] ? prev : 0.f;
+  }
+}
+__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int N,
+                              int accumulate) {
+  // block handles 32 columns; threads (32 x 8) stride rows
+  __shared__ float red[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (col < N)
+    for (long long r = ry; r < M; r += 8) acc += x[r * N + col];
+  red[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && col < N) {
+    float s = 0.f;
+    for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x & 31];
+    out[col] = accumulate ? out[col] + s : s;
+  }
+}
+
+static int ilog2i(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+static int make_gn(GnP& p, const float* stats, const float* gamma, const float* beta, int C, int G, int hw,
+                   float eps) {
+  HB_CHECK_ARG(stats && gamma && beta, "gn: null pointer");
+  HB_CHECK_ARG(C % 8 == 0 && G > 0 && C % G == 0, "gn: C=%d G=%d unsupported", C, G);
+  const int cpg = C / G;
+  HB_CHECK_ARG((cpg & (cpg - 1)) == 0, "gn: channels per group (%d) must be a power of two", cpg);
+  p.stats = stats; p.gamma = gamma; p.beta = beta; p.C = C; p.G = G; p.lcpg = ilog2i(cpg);
+  p.inv_m = 1.0f / ((float)cpg * (float)hw);
+  p.eps = eps;
+  return HB200_OK;
+}
+}  // namespace hb200
+
+using namespace hb200;
+
+// ---- C ABI ---------------------------------------------------------------------------------
+static int prep_check(const uint8_t* rgb, const float* depth, const int32_t* rows, int B, int H, int W,
+                      int c_rgb, int c_depth) {
+  HB_CHECK_ARG(rows && B > 0, "prep: bad args");
+  HB_CHECK_ARG((c_rgb == 3 && rgb) || (c_rgb == 0), "prep: c_rgb must be 0 or 3");
+  HB_CHECK_ARG((c_depth == 1 && depth) || (c_depth == 0), "prep: c_depth must be 0 or 1");
+  HB_CHECK_ARG(c_rgb + c_depth > 0, "prep: no visual channels");
+  HB_CHECK_ARG(H % 2 == 0 && W % 8 == 0, "prep: H must be even and W a multiple of 8 (got %dx%d)", H, W);
+  return HB200_OK;
+}
+
+extern "C" int hb200_prep_stats(const uint8_t* rgb, const float* depth, const int32_t* frame_rows,
+                                int batch, int height, int width, int c_rgb, int c_depth,
+                                float rgb_scale, double* stats_acc, hb200_stream_t stream) {
+  int rc = prep_check(rgb, depth, frame_rows, batch, height, width, c_rgb, c_depth);
+  if (rc) return rc;
+  HB_CHECK_ARG(stats_acc, "prep_stats: null stats");
+  cudaStream_t st = (cudaStream_t)stream;
+  HB_CUDA(cudaMemsetAsync(stats_acc, 0, 17 * sizeof(double), st));
+  const long long total = (long long)batch * (height / 2) * (width / 8);
+  const int grid = grid_for(total, 256);
+  if (c_rgb && c_depth) prep_stats_kernel<true, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, stats_acc);
+  else if (c_rgb) prep_stats_kernel<true, false><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, stats_acc);
+  else prep_stats_kernel<false, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, stats_acc);
+  HB_LAUNCH_OK();
+  // frame count (the reference's new_count = x.size(0), running_mean_and_var.py:27,36)
+  const double frames = (double)batch;
+  HB_CUDA(cudaMemcpyAsync(stats_acc + 16, &frames, sizeof(double), cudaMemcpyHostToDevice, st));
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_prep_finalize(const double* stats_acc, float* run_mean, float* run_var,
+                                   float* run_count, float* scale_shift, int channels,
+                                   long long pixels_per_frame, int update, hb200_stream_t stream) {
+  HB_CHECK_ARG(stats_acc && run_mean && run_var && run_count && scale_shift, "prep_finalize: null pointer");
+  HB_CHECK_ARG(channels > 0 && channels <= 8, "prep_finalize: channels must be 1..8");
+  prep_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(stats_acc, run_mean, run_var, run_count,
+                                                            scale_shift, channels, pixels_per_frame, update);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_prep_apply(const uint8_t* rgb, const float* depth, const int32_t* frame_rows,
+                                int batch, int height, int width, int c_rgb, int c_depth,
+                                float rgb_scale, const float* scale_shift, hb200_bf16* out,
+                                hb200_stream_t stream) {
+  int rc = prep_check(rgb, depth, frame_rows, batch, height, width, c_rgb, c_depth);
+  if (rc) return rc;
+  HB_CHECK_ARG(out, "prep_apply: null out");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)batch * (height / 2) * (width / 8);
+  const int grid = grid_for(total, 256);
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  if (c_rgb && c_depth) prep_apply_kernel<true, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o);
+  else if (c_rgb) prep_apply_kernel<true, false><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o);
+  else prep_apply_kernel<false, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_gn_apply(const hb200_bf16* y, const float* stats, const float* gamma,
+                              const float* beta, void* out, int out_f32, int batch, int hw,
+                              int channels, int groups, float eps, int relu, hb200_stream_t stream) {
+  GnP p;
+  int rc = make_gn(p, stats, gamma, beta, channels, groups, hw, eps);
+  if (rc) return rc;
+  HB_CHECK_ARG(y && out, "gn_apply: null pointer");
+  const long long total = (long long)batch * hw * (channels / 8);
+  if (out_f32)
+    gn_apply_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
+  else
+    gn_apply_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_gn_residual_relu(const hb200_bf16* y, const float* stats, const float* gamma,
+                                      const float* beta, const hb200_bf16* res, const float* res_stats,
+                                      const float* res_gamma, const float* res_beta, hb200_bf16* out,
+                                      int batch, int hw, int channels, int groups, float eps,
+                                      hb200_stream_t stream) {
+  GnP p, rp;
+  int rc = make_gn(p, stats, gamma, beta, channels, groups, hw, eps);
+  if (rc) return rc;
+  HB_CHECK_ARG(y && res && out, "gn_residual_relu: null pointer");
+  rp = p;
+  if (res_stats) {
+    rc = make_gn(rp, res_stats, res_gamma, res_beta, channels, groups, hw, eps);
+    if (rc) return rc;
+  }
+  const long long total = (long long)batch * hw * (channels / 8);
+  gn_residual_relu_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y, p, (const __nv_bfloat16*)res, rp, res_stats ? 1 : 0, (__nv_bfloat16*)out, batch, hw);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_gn_relu_maxpool(const hb200_bf16* y, const float* stats, const float* gamma,
+                                     const float* beta, hb200_bf16* out, uint8_t* argmax, int batch,
+                                     int h, int w, int channels, int groups, float eps,
+                                     hb200_stream_t stream) {
+  GnP p;
+  int rc = make_gn(p, stats, gamma, beta, channels, groups, h * w, eps);
+  if (rc) return rc;
+  HB_CHECK_ARG(y && out && argmax && h % 2 == 0 && w % 2 == 0, "gn_relu_maxpool: bad args");
+  const long long total = (long long)batch * (h / 2) * (w / 2) * (channels / 8);
+  gn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y, p, (__nv_bfloat16*)out, argmax, batch, h, w);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_maxpool_bwd(const hb200_bf16* dout, const uint8_t* argmax, hb200_bf16* dz,
+                                 int batch, int h, int w, int channels, hb200_stream_t stream) {
+  HB_CHECK_ARG(dout && argmax && dz && channels % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_bwd: bad args");
+  const long long total = (long long)batch * h * w * (channels / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dout, argmax, (__nv_bfloat16*)dz, batch, h, w, channels);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_gn_bwd_reduce(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
+                                   const float* stats, const float* gamma, const float* beta,
+                                   float* sums, float* dgamma, float* dbeta, int batch, int hw,
+                                   int channels, int groups, float eps, int mask_mode,
+                                   hb200_stream_t stream) {
+  GnP p;
+  int rc = make_gn(p, stats, gamma, beta, channels, groups, hw, eps);
+  if (rc) return rc;
+  HB_CHECK_ARG(g && y && sums && dgamma && dbeta, "gn_bwd_reduce: null pointer");
+  HB_CHECK_ARG(mask_mode >= 0 && mask_mode <= 2 && (mask_mode != 2 || act), "gn_bwd_reduce: bad mask_mode");
+  HB_CHECK_ARG(channels <= 2048 && 256 % (channels / 8) == 0, "gn_bwd_reduce: C/8 must divide 256");
+  cudaStream_t st = (cudaStream_t)stream;
+  HB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)batch * groups, st));
+  const int npl = 256 / (channels / 8);
+  int ppb = npl * 16;  // 16 pixels per thread
+  if (ppb > hw) ppb = hw;
+  const int slabs = (hw + ppb - 1) / ppb;
+  gn_bwd_reduce_kernel<<<batch * slabs, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)act,
+                                                      (const __nv_bfloat16*)y, p, sums, dgamma, dbeta,
+                                                      batch, hw, ppb, mask_mode);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_gn_bwd_apply(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
+                                  const float* stats, const float* gamma, const float* beta,
+                                  const float* sums, hb200_bf16* dy, hb200_bf16* gz_out, int batch,
+                                  int hw, int channels, int groups, float eps, int mask_mode,
+                                  hb200_stream_t stream) {
+  GnP p;
+  int rc = make_gn(p, stats, gamma, beta, channels, groups, hw, eps);
+  if (rc) return rc;
+  HB_CHECK_ARG(g && y && sums && dy, "gn_bwd_apply: null pointer");
+  HB_CHECK_ARG(mask_mode >= 0 && mask_mode <= 2 && (mask_mode != 2 || act), "gn_bwd_apply: bad mask_mode");
+  const long long total = (long long)batch * hw * (channels / 8);
+  gn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)g, (const __nv_bfloat16*)act, (const __nv_bfloat16*)y, p, sums,
+      (__nv_bfloat16*)dy, (__nv_bfloat16*)gz_out, batch, hw, mask_mode);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_bf16_to_f32(const hb200_bf16* x, float* out, long long n, hb200_stream_t stream) {
+  HB_CHECK_ARG(x && out && n > 0 && n % 8 == 0, "bf16_to_f32: n must be a positive multiple of 8");
+  bf16_to_f32_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, n / 8);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+extern "C" int hb200_f32_to_bf16(const float* x, hb200_bf16* out, long long n, hb200_stream_t stream) {
+  HB_CHECK_ARG(x && out && n > 0 && n % 8 == 0, "f32_to_bf16: n must be a positive multiple of 8");
+  f32_to_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, n / 8);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_embed_fwd(const float* goal, const int64_t* prev_actions, const uint8_t* masks,
+                               const int32_t* frame_rows, const float* w_tgt, const float* b_tgt,
+                               const float* emb_table, float* out, int ld, int col0, int batch,
+                               hb200_stream_t stream) {
+  HB_CHECK_ARG(goal && prev_actions && masks && frame_rows && w_tgt && b_tgt && emb_table && out && batch > 0,
+               "embed_fwd: bad args");
+  embed_fwd_kernel<<<grid_for((long long)batch * 64, 256), 256, 0, (cudaStream_t)stream>>>(
+      goal, prev_actions, masks, frame_rows, w_tgt, b_tgt, emb_table, out, ld, col0, batch);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+extern "C" int hb200_embed_bwd(const float* goal, const int64_t* prev_actions, const uint8_t* masks,
+                               const int32_t* frame_rows, const float* d_out, int ld, int col0,
+                               int batch, int n_emb, float* d_w_tgt, float* d_b_tgt, float* d_emb,
+                               hb200_stream_t stream) {
+  HB_CHECK_ARG(goal && prev_actions && masks && frame_rows && d_out && d_w_tgt && d_b_tgt && d_emb && batch > 0,
+               "embed_bwd: bad args");
+  HB_CHECK_ARG(n_emb > 0 && n_emb <= 64, "embed_bwd: n_emb out of range");
+  const size_t smem = sizeof(float) * (128 + n_emb * 32);
+  int grid = grid_for((long long)batch * 64, 256);
+  if (grid > kNumSMs) grid = kNumSMs;
+  embed_bwd_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(goal, prev_actions, masks, frame_rows, d_out,
+                                                              ld, col0, batch, n_emb, d_w_tgt, d_b_tgt, d_emb);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_rnn_shift_mask(const float* h_seq, const float* h0, long long h0_row_stride,
+                                    const uint8_t* masks, float* h_in, int t_steps, int n, int hidden,
+                                    hb200_stream_t stream) {
+  HB_CHECK_ARG(h_seq && h0 && masks && h_in && t_steps > 0 && n > 0 && hidden > 0, "rnn_shift_mask: bad args");
+  const long long total = (long long)t_steps * n * hidden;
+  rnn_shift_mask_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(h_seq, h0, h0_row_stride, masks,
+                                                                                 h_in, t_steps, n, hidden);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+extern "C" int hb200_colsum(const float* x, float* out, long long m, int n, int accumulate,
+                            hb200_stream_t stream) {
+  HB_CHECK_ARG(x && out && m > 0 && n > 0, "colsum: bad args");
+  colsum_kernel<<<(n + 31) / 32, 256, 0, (cudaStream_t)stream>>>(x, out, m, n, accumulate);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}

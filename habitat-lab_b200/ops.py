@@ -1,0 +1,245 @@
+"""Thin typed wrappers over the C ABI (include/hb200.h): torch tensors in, device pointers
+out.  torch is plumbing only (allocation, streams); every computation happens in libhb200.so."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvShape, call, load, ptr
+
+BF16 = torch.bfloat16
+N_METRICS = 12
+METRIC_KEYS = ("value_loss", "action_loss", "dist_entropy", "value_pred_min", "value_pred_mean",
+               "value_pred_max", "prob_ratio_min", "prob_ratio_mean", "prob_ratio_max",
+               "ppo_fraction_clipped", "total_loss")
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise _lib.Hb200Error(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.Hb200Error(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.Hb200Error(f"{name}: expected a contiguous tensor")
+
+
+def as_u8(masks: torch.Tensor) -> torch.Tensor:
+    return masks.view(torch.uint8) if masks.dtype == torch.bool else masks
+
+
+# ---- GAE / advantages ---------------------------------------------------------------------
+def gae_adv(rewards, value_preds, masks, next_value, returns, advantages, stats, t_cur, gamma, tau,
+            use_gae=True, variant=0):
+    t_alloc, n = rewards.shape[0], rewards.shape[1]
+    for t, nm in ((rewards, "rewards"), (value_preds, "value_preds"), (returns, "returns"), (next_value, "next_value")):
+        _chk(t, torch.float32, nm)
+    call("hb200_gae_adv", ptr(rewards), ptr(value_preds), ptr(as_u8(masks)), ptr(next_value), ptr(returns),
+         ptr(advantages), ptr(stats), int(t_cur), int(t_alloc), int(n), float(gamma), float(tau),
+         int(bool(use_gae)), int(variant))
+
+
+def adv_normalize(advantages, stats=None, mean_var=None):
+    mode = 0 if mean_var is None else 1
+    call("hb200_adv_normalize", ptr(advantages), advantages.numel(), ptr(stats), ptr(mean_var), mode)
+
+
+# ---- heads + loss ---------------------------------------------------------------------------
+def ppo_loss_workspace(batch, hidden, n_actions, device):
+    nbytes = load().hb200_ppo_loss_workspace_bytes(batch, hidden, n_actions)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def ppo_loss(features, w_act, b_act, w_val, b_val, actions, old_lp, adv, old_v, returns, clip, c_v, c_e,
+             use_clipped_value_loss, compute_grads, out, workspace, is_coeffs=None):
+    """out: dict with optional tensors values/log_probs/entropy, d_features, d_w_act, d_b_act,
+    d_w_val, d_b_val, metrics."""
+    B, H = features.shape
+    A = w_act.shape[0]
+    _chk(features, torch.float32, "features")
+    _chk(actions, torch.int64, "actions")
+    call("hb200_ppo_loss", ptr(features), ptr(w_act), ptr(b_act), ptr(w_val), ptr(b_val), ptr(actions),
+         ptr(old_lp), ptr(adv), ptr(old_v), ptr(returns), ptr(is_coeffs), B, H, A, float(clip), float(c_v),
+         float(c_e), int(bool(use_clipped_value_loss)), int(bool(compute_grads)),
+         ptr(out.get("values")), ptr(out.get("log_probs")), ptr(out.get("entropy")),
+         ptr(out.get("d_features")), ptr(out.get("d_w_act")), ptr(out.get("d_b_act")),
+         ptr(out.get("d_w_val")), ptr(out.get("d_b_val")), ptr(out["metrics"]), ptr(workspace))
+
+
+# ---- optimizer ----------------------------------------------------------------------------------
+def clip_adam_workspace(n, device):
+    return torch.empty(load().hb200_clip_adam_workspace_bytes(n), dtype=torch.uint8, device=device)
+
+
+def clip_adam(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, max_grad_norm, grad_scale,
+              step, grad_norm_out, workspace, hyper=None):
+    for t, nm in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _chk(t, torch.float32, nm)
+    call("hb200_clip_adam", ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), float(lr),
+         float(betas[0]), float(betas[1]), float(eps), float(weight_decay),
+         float(max_grad_norm if max_grad_norm is not None else 0.0), float(grad_scale), int(step), ptr(hyper),
+         ptr(grad_norm_out), ptr(workspace))
+
+
+# ---- visual prep ------------------------------------------------------------------------------------
+def prep_stats(rgb, depth, frame_rows, H, W, stats_acc, rgb_scale=1.0 / 255.0):
+    call("hb200_prep_stats", ptr(rgb), ptr(depth), ptr(frame_rows), frame_rows.numel(), H, W,
+         3 if rgb is not None else 0, 1 if depth is not None else 0, float(rgb_scale), ptr(stats_acc))
+
+
+def prep_finalize(stats_acc, run_mean, run_var, run_count, scale_shift, channels, pixels_per_frame, update):
+    call("hb200_prep_finalize", ptr(stats_acc), ptr(run_mean), ptr(run_var), ptr(run_count), ptr(scale_shift),
+         channels, int(pixels_per_frame), int(bool(update)))
+
+
+def prep_apply(rgb, depth, frame_rows, H, W, scale_shift, out, rgb_scale=1.0 / 255.0):
+    call("hb200_prep_apply", ptr(rgb), ptr(depth), ptr(frame_rows), frame_rows.numel(), H, W,
+         3 if rgb is not None else 0, 1 if depth is not None else 0, float(rgb_scale), ptr(scale_shift), ptr(out))
+
+
+# ---- conv ----------------------------------------------------------------------------------------------
+def conv_shape(batch, hi, wi, ci, co, kh, kw, stride, pad) -> ConvShape:
+    ho = (hi + 2 * pad - kh) // stride + 1
+    wo = (wi + 2 * pad - kw) // stride + 1
+    return ConvShape(batch, hi, wi, ci, ho, wo, co, kh, kw, stride, pad)
+
+
+def packed_weight_elems(n_rows, k_channels, kh, kw) -> int:
+    return load().hb200_packed_weight_elems(n_rows, k_channels, kh, kw)
+
+
+def pack_conv_weight(w_oihw: torch.Tensor, ci_pad: int, want_t: bool = True):
+    co, ci_real, kh, kw = w_oihw.shape
+    _chk(w_oihw, torch.float32, "w_oihw")
+    dev = w_oihw.device
+    wp = torch.empty(packed_weight_elems(co, ci_pad, kh, kw), dtype=BF16, device=dev)
+    wt = torch.empty(packed_weight_elems(ci_pad, co, kh, kw), dtype=BF16, device=dev) if want_t else None
+    call("hb200_pack_conv_weight", ptr(w_oihw), ptr(wp), ptr(wt), co, ci_real, ci_pad, kh, kw)
+    return wp, wt
+
+
+def pack_conv_weight_into(w_oihw, wp, wt, ci_pad):
+    co, ci_real, kh, kw = w_oihw.shape
+    call("hb200_pack_conv_weight", ptr(w_oihw), ptr(wp), ptr(wt), co, ci_real, ci_pad, kh, kw)
+
+
+def conv_fwd(x, wp, y, s: ConvShape, gn_stats=None, gn_groups=0):
+    call("hb200_conv_fwd", ptr(x), ptr(wp), ptr(y), ptr(gn_stats), int(gn_groups), ctypes.addressof(s))
+
+
+def conv_dgrad(dy, wt, dx, s: ConvShape, addend=None):
+    call("hb200_conv_dgrad", ptr(dy), ptr(wt), ptr(addend), ptr(dx), ctypes.addressof(s))
+
+
+def conv_wgrad(x, dy, dw_acc, s: ConvShape):
+    call("hb200_conv_wgrad", ptr(x), ptr(dy), ptr(dw_acc), ctypes.addressof(s))
+
+
+def unpack_conv_wgrad(dw_acc, dw_oihw, ci_pad):
+    co, ci_real, kh, kw = dw_oihw.shape
+    call("hb200_unpack_conv_wgrad", ptr(dw_acc), ptr(dw_oihw), co, ci_real, ci_pad, kh, kw)
+
+
+def umma_gemm_probe(a, b, d, m, n, k, layout):
+    call("hb200_umma_gemm_probe", ptr(a), ptr(b), ptr(d), m, n, k, layout)
+
+
+# ---- GroupNorm & friends -----------------------------------------------------------------------------
+def gn_apply(y, stats, gamma, beta, out, batch, hw, channels, groups, relu, eps=1e-5):
+    call("hb200_gn_apply", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(out),
+         int(out.dtype == torch.float32), batch, hw, channels, groups, float(eps), int(bool(relu)))
+
+
+def gn_residual_relu(y, stats, gamma, beta, res, out, batch, hw, channels, groups, res_stats=None,
+                     res_gamma=None, res_beta=None, eps=1e-5):
+    call("hb200_gn_residual_relu", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(res), ptr(res_stats),
+         ptr(res_gamma), ptr(res_beta), ptr(out), batch, hw, channels, groups, float(eps))
+
+
+def gn_relu_maxpool(y, stats, gamma, beta, out, argmax, batch, h, w, channels, groups, eps=1e-5):
+    call("hb200_gn_relu_maxpool", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(out), ptr(argmax), batch, h, w,
+         channels, groups, float(eps))
+
+
+def maxpool_bwd(dout, argmax, dz, batch, h, w, channels):
+    call("hb200_maxpool_bwd", ptr(dout), ptr(argmax), ptr(dz), batch, h, w, channels)
+
+
+def gn_bwd_reduce(g, act, y, stats, gamma, beta, sums, dgamma, dbeta, batch, hw, channels, groups, mask_mode,
+                  eps=1e-5):
+    call("hb200_gn_bwd_reduce", ptr(g), ptr(act), ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(sums),
+         ptr(dgamma), ptr(dbeta), batch, hw, channels, groups, float(eps), mask_mode)
+
+
+def gn_bwd_apply(g, act, y, stats, gamma, beta, sums, dy, gz_out, batch, hw, channels, groups, mask_mode,
+                 eps=1e-5):
+    call("hb200_gn_bwd_apply", ptr(g), ptr(act), ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(sums), ptr(dy),
+         ptr(gz_out), batch, hw, channels, groups, float(eps), mask_mode)
+
+
+# ---- dense / rnn / misc -----------------------------------------------------------------------------------
+def sgemm(a, a_ms, a_ks, b, b_ks, b_ns, c, ldc, m, n, k, bias=None, alpha=1.0, accumulate=False, relu=False):
+    call("hb200_sgemm", ptr(a), int(a_ms), int(a_ks), ptr(b), int(b_ks), int(b_ns), ptr(c), int(ldc), ptr(bias),
+         m, n, k, float(alpha), int(bool(accumulate)), int(bool(relu)))
+
+
+def linear_fwd(x, w, bias, out, relu=False, ldc=None):
+    """out[M,N] = x[M,K] @ w[N,K]^T + bias"""
+    M, K = x.shape
+    N = w.shape[0]
+    sgemm(x, x.stride(0), 1, w, 1, w.stride(0), out, ldc if ldc is not None else out.stride(0), M, N, K,
+          bias=bias, relu=relu)
+
+
+def linear_bwd_input(dy, w, dx, ld_dy=None, accumulate=False):
+    """dx[M,K] = dy[M,N] @ w[N,K]"""
+    M, N = dy.shape
+    K = w.shape[1]
+    sgemm(dy, ld_dy if ld_dy is not None else dy.stride(0), 1, w, w.stride(0), 1, dx, dx.stride(0), M, K, N,
+          accumulate=accumulate)
+
+
+def linear_bwd_weight(dy, x, dw, accumulate=False):
+    """dw[N,K] = dy[M,N]^T @ x[M,K]"""
+    M, N = dy.shape
+    K = x.shape[1]
+    sgemm(dy, 1, dy.stride(0), x, x.stride(0), 1, dw, dw.stride(0), N, K, M, accumulate=accumulate)
+
+
+def bf16_to_f32(x, out):
+    call("hb200_bf16_to_f32", ptr(x), ptr(out), x.numel())
+
+
+def f32_to_bf16(x, out):
+    call("hb200_f32_to_bf16", ptr(x), ptr(out), x.numel())
+
+
+def lstm_step_fwd(xproj, w_hh, masks, h_prev, c_prev, h, c, gates_out, n, hidden):
+    call("hb200_lstm_step_fwd", ptr(xproj), ptr(w_hh), ptr(masks), ptr(h_prev), h_prev.stride(0), ptr(c_prev),
+         c_prev.stride(0), ptr(h), ptr(c), ptr(gates_out), n, hidden)
+
+
+def lstm_step_bwd(dh_out, dh_rec, dc_rec, gates, c, c_prev, w_hh, masks, dgates, dh_prev, dc_prev, n, hidden):
+    call("hb200_lstm_step_bwd", ptr(dh_out), ptr(dh_rec), ptr(dc_rec), ptr(gates), ptr(c), ptr(c_prev),
+         c_prev.stride(0), ptr(w_hh), ptr(masks), ptr(dgates), ptr(dh_prev), ptr(dc_prev), n, hidden)
+
+
+def rnn_shift_mask(h_seq, h0, masks, h_in, T, n, hidden):
+    call("hb200_rnn_shift_mask", ptr(h_seq), ptr(h0), h0.stride(0), ptr(masks), ptr(h_in), T, n, hidden)
+
+
+def colsum(x, out, accumulate=False):
+    M, N = x.shape
+    call("hb200_colsum", ptr(x), ptr(out), M, N, int(bool(accumulate)))
+
+
+def embed_fwd(goal, prev_actions, masks, frame_rows, w_tgt, b_tgt, emb, out, col0):
+    call("hb200_embed_fwd", ptr(goal), ptr(prev_actions), ptr(as_u8(masks)), ptr(frame_rows), ptr(w_tgt),
+         ptr(b_tgt), ptr(emb), ptr(out), out.stride(0), col0, frame_rows.numel())
+
+
+def embed_bwd(goal, prev_actions, masks, frame_rows, d_out, col0, d_w_tgt, d_b_tgt, d_emb):
+    call("hb200_embed_bwd", ptr(goal), ptr(prev_actions), ptr(as_u8(masks)), ptr(frame_rows), ptr(d_out),
+         d_out.stride(0), col0, frame_rows.numel(), d_emb.shape[0], ptr(d_w_tgt), ptr(d_b_tgt), ptr(d_emb))

@@ -1,0 +1,298 @@
+/* hb200.h -- C ABI of libhb200.so: the B200 (sm_100a) DD-PPO learner hot path that
+ * sits below habitat-baselines' Python registry classes.
+ *
+ * The reference (facebookresearch/habitat-lab) has NO native boundary: every hot-path
+ * op is a PyTorch library call made from Python.  This header is the boundary a
+ * maintainer would bind with ctypes from the reference's own classes; each entry point
+ * cites the reference Python code it replaces (paths relative to the habitat-lab tree,
+ * HB = habitat-baselines/habitat_baselines).
+ *
+ * Conventions
+ *  - plain pointers + sizes only; all pointers are DEVICE pointers unless named h_*.
+ *  - every function takes the cudaStream_t (as void*) to launch on and returns an int
+ *    status: 0 ok, <0 error (message via hb200_last_error()).
+ *  - the library never allocates or frees caller memory; scratch is passed in and sized
+ *    by the *_workspace_bytes twin.
+ *  - activations are NHWC; "bf16" pointers are raw uint16 bfloat16 storage.
+ */
+#ifndef HB200_H_
+#define HB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB200_OK 0
+#define HB200_ERR_INVALID_ARG (-1)
+#define HB200_ERR_CUDA (-2)
+#define HB200_ERR_UNSUPPORTED (-3)
+
+typedef void* hb200_stream_t; /* cudaStream_t */
+typedef uint16_t hb200_bf16;
+
+/* ---- library ---------------------------------------------------------------- */
+const char* hb200_last_error(void);
+int hb200_version(void);
+/* number of kernel launches issued through this library since load (bench's gpu_launches) */
+long long hb200_launch_count(void);
+
+/* ---- GAE return scan + advantages ---------------------------------------------
+ * replaces RolloutStorage.compute_returns (HB/common/rollout_storage.py:174-205)
+ * fused with PPO.get_advantages / _compute_var_mean (HB/rl/ppo/ppo.py:139-157).
+ *
+ * rewards, value_preds, returns, advantages: f32 [t_alloc, n_envs] (row pitch = n_envs)
+ * masks: u8/bool [t_alloc, n_envs]; next_value: f32 [n_envs] written to value_preds[t_cur]
+ * (use_gae) or returns[t_cur] (!use_gae) exactly like the reference.
+ * t_cur = current_rollout_step_idx; t_alloc = numsteps+1 (advantages cover ALL t_alloc rows,
+ * including the bootstrap row and stale rows -- reference quirk, ppo.py:140-149).
+ * advantages may be NULL (returns only).  stats (f64[4], may be NULL): sum, sum of squares,
+ * count over FINITE advantages, spare -- the raw material of the (distributed) var/mean.
+ * variant: 0 auto, 1 thread-per-env serial scan (reference summation order), 2 warp-per-env
+ * shuffle scan (affine-map composition; differs from the serial order by fp32 rounding only).
+ */
+int hb200_gae_adv(const float* rewards, float* value_preds, const uint8_t* masks,
+                  const float* next_value, float* returns, float* advantages, double* stats,
+                  int t_cur, int t_alloc, int n_envs, float gamma, float tau, int use_gae,
+                  int variant, hb200_stream_t stream);
+
+/* advantages <- (advantages - mean) * rsqrt(var + 1e-5) in place (ppo.py:151-153).
+ * mode 0: single process, unbiased torch.var_mean over finite entries computed from stats
+ * (ppo.py:155-157).  mode 1: mean/var given in mean_var[2] on device (distributed path,
+ * HB/rl/ddppo/algo/ddppo.py:59-84, after the caller's all-reduce). */
+int hb200_adv_normalize(float* advantages, long long n, const double* stats,
+                        const float* mean_var, int mode, hb200_stream_t stream);
+
+/* ---- action/value heads + PPO loss, forward and backward in one pass -------------
+ * replaces CategoricalNet + CriticHead (HB/utils/common.py:64-96, HB/rl/ppo/policy.py:416-424)
+ * and the loss section of PPO._update_from_batch (HB/rl/ppo/ppo.py:195-250, 260-275).
+ *
+ * features f32 [B,H]; w_act f32 [A,H], b_act [A]; w_val f32 [1,H], b_val [1]; actions i64 [B];
+ * old_log_probs, advantages, old_values, returns f32 [B]; is_coeffs f32 [B] or NULL (VER).
+ * Outputs: values, log_probs, entropy f32 [B] (any may be NULL); d_features f32 [B,H];
+ * d_w_act [A,H], d_b_act [A], d_w_val [H], d_b_val [1] (OVERWRITTEN, not accumulated);
+ * metrics f32 [HB200_LOSS_NMETRICS].  compute_grads=0 -> forward/metrics only.
+ * workspace: hb200_ppo_loss_workspace_bytes(B,H,A).  A <= 8, H % 32 == 0, H <= 1024.
+ */
+#define HB200_LOSS_NMETRICS 12
+enum {
+  HB200_M_VALUE_LOSS = 0, HB200_M_ACTION_LOSS = 1, HB200_M_DIST_ENTROPY = 2,
+  HB200_M_VALUE_MIN = 3, HB200_M_VALUE_MEAN = 4, HB200_M_VALUE_MAX = 5,
+  HB200_M_RATIO_MIN = 6, HB200_M_RATIO_MEAN = 7, HB200_M_RATIO_MAX = 8,
+  HB200_M_FRAC_CLIPPED = 9, HB200_M_TOTAL_LOSS = 10, HB200_M_SPARE = 11
+};
+size_t hb200_ppo_loss_workspace_bytes(int batch, int hidden, int n_actions);
+int hb200_ppo_loss(const float* features, const float* w_act, const float* b_act,
+                   const float* w_val, const float* b_val, const int64_t* actions,
+                   const float* old_log_probs, const float* advantages, const float* old_values,
+                   const float* returns, const float* is_coeffs, int batch, int hidden,
+                   int n_actions, float clip_param, float value_loss_coef, float entropy_coef,
+                   int use_clipped_value_loss, int compute_grads, float* values, float* log_probs,
+                   float* entropy, float* d_features, float* d_w_act, float* d_b_act,
+                   float* d_w_val, float* d_b_val, float* metrics, void* workspace,
+                   hb200_stream_t stream);
+
+/* ---- clip_grad_norm_ + Adam on flat buffers ---------------------------------------
+ * replaces nn.utils.clip_grad_norm_ + torch.optim.Adam(foreach=True).step()
+ * (HB/rl/ppo/ppo.py:112-137, 257, 347-371).
+ * params/grads/exp_avg/exp_avg_sq: f32 [n].  grad_norm_out: f32[1] device (the pre-clip total
+ * L2 norm, what clip_grad_norm_ returns).  hyper: f32[8] DEVICE or NULL -> if non-NULL, lr is
+ * read from hyper[0] (LambdaLR mutates lr every update; keeps the launch graph-capturable).
+ * step = 1-based Adam step count for bias correction.  max_grad_norm <= 0 disables clipping.
+ * grad_scale multiplies grads first (1/world_size when the all-reduce was a SUM).
+ * workspace: hb200_clip_adam_workspace_bytes(n).
+ */
+size_t hb200_clip_adam_workspace_bytes(long long n);
+int hb200_grad_sqnorm(const float* grads, long long n, float grad_scale, float* sqnorm_out,
+                      void* workspace, hb200_stream_t stream);
+int hb200_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                    long long n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float max_grad_norm, float grad_scale, long long step, const float* hyper,
+                    float* grad_norm_out, void* workspace, hb200_stream_t stream);
+
+/* ---- visual input prep ----------------------------------------------------------------
+ * replaces ResNetEncoder.forward's permute/float/scale/cat/avg_pool2d
+ * (HB/rl/ddppo/policy/resnet_policy.py:255-271) and RunningMeanAndVar
+ * (HB/rl/ddppo/policy/running_mean_and_var.py:24-78).
+ *
+ * Sources are the rollout buffers in place (no minibatch gather copy,
+ * HB/common/rollout_storage.py:236-246): rgb u8 [rows,H,W,c_rgb] (may be NULL, c_rgb=0),
+ * depth f32 [rows,H,W,c_depth] (may be NULL).  frame_rows i32 [B]: buffer row of each frame.
+ * Channel order = rgb then depth (observation-space order).  C = c_rgb + c_depth <= 8.
+ * stats_acc f64 [17]: [0,8) per-channel sum, [8,16) sum of squares of the 2x2-pooled input,
+ * [16] number of frames (the reference's new_count = x.size(0)); with >1 ranks the caller
+ * all-reduces (SUM) these 17 doubles -- one packed collective instead of the reference's three.
+ */
+int hb200_prep_stats(const uint8_t* rgb, const float* depth, const int32_t* frame_rows, int batch,
+                     int height, int width, int c_rgb, int c_depth, float rgb_scale,
+                     double* stats_acc, hb200_stream_t stream);
+/* Welford merge of the batch stats into (_mean,_var,_count) f32 buffers [C],[C],[1]
+ * (running_mean_and_var.py:50-68) and scale/shift f32 [2*8] for the normalise pass (:70-78).
+ * world_size > 1: stats_acc must already hold the all-reduced SUM over ranks. update=0 skips
+ * the merge (eval mode) and only refreshes scale_shift. */
+int hb200_prep_finalize(const double* stats_acc, float* run_mean, float* run_var, float* run_count,
+                        float* scale_shift, int channels, long long pixels_per_frame, int update,
+                        hb200_stream_t stream);
+/* pooled + normalised NHWC bf16 [B,H/2,W/2,8] (channels >= C zero padded).
+ * scale_shift NULL -> no normalisation (normalize_visual_inputs=False). */
+int hb200_prep_apply(const uint8_t* rgb, const float* depth, const int32_t* frame_rows, int batch,
+                     int height, int width, int c_rgb, int c_depth, float rgb_scale,
+                     const float* scale_shift, hb200_bf16* out, hb200_stream_t stream);
+
+/* ---- implicit-GEMM convolution on tcgen05 tensor cores -----------------------------------
+ * replaces nn.Conv2d forward / backward-data / backward-weight as dispatched by
+ * HB/rl/ddppo/policy/resnet.py:15-34,207-219 and resnet_policy.py:224-234 (cuDNN today).
+ *
+ * x bf16 NHWC [B,Hi,Wi,Ci]; w_packed bf16 [Co][kh*kw*Ci padded to 64] (hb200_pack_conv_weight);
+ * y bf16 NHWC [B,Ho,Wo,Co].  Ci % 8 == 0, Co % 16 == 0, Co <= 256 or Co % 256 == 0.
+ * gn_stats f32 [B, gn_groups, 2] or NULL: per-(frame,group) sum / sum-of-squares of the fp32
+ * accumulators are atomically added (GroupNorm statistics fused into the conv epilogue).
+ * addend (dgrad only) bf16 [B,Hi,Wi,Ci] or NULL: dx = conv_dgrad + addend (residual grad).
+ */
+typedef struct {
+  int batch, hi, wi, ci, ho, wo, co, kh, kw, stride, pad;
+} hb200_conv_shape;
+
+int hb200_conv_fwd(const hb200_bf16* x, const hb200_bf16* w_packed, hb200_bf16* y,
+                   float* gn_stats, int gn_groups, const hb200_conv_shape* s,
+                   hb200_stream_t stream);
+/* dy [B,Ho,Wo,Co] -> dx [B,Hi,Wi,Ci]; w_packed_t bf16 [Ci][kh*kw*Co padded] (transposed pack) */
+int hb200_conv_dgrad(const hb200_bf16* dy, const hb200_bf16* w_packed_t, const hb200_bf16* addend,
+                     hb200_bf16* dx, const hb200_conv_shape* s, hb200_stream_t stream);
+/* dw_acc f32 [kh*kw*Ci][Co], ACCUMULATED with atomics (caller zeroes) */
+int hb200_conv_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc,
+                     const hb200_conv_shape* s, hb200_stream_t stream);
+/* f32 OIHW [Co,Ci_real,kh,kw] -> bf16 [Co][(r,s,ci) padded] (ci_pad >= ci_real, zero filled),
+ * and the transposed pack [Ci_pad][(r,s,co) padded] used by dgrad.  Both are stored as
+ * ready-to-copy shared-memory tile images (see hb200_set_umma_layout). */
+int hb200_pack_conv_weight(const float* w_oihw, hb200_bf16* w_packed, hb200_bf16* w_packed_t,
+                           int co, int ci_real, int ci_pad, int kh, int kw, hb200_stream_t stream);
+/* dw_acc f32 [(r,s,ci_pad)][Co] -> f32 OIHW grad [Co,Ci_real,kh,kw] (overwrite) */
+int hb200_unpack_conv_wgrad(const float* dw_acc, float* dw_oihw, int co, int ci_real, int ci_pad,
+                            int kh, int kw, hb200_stream_t stream);
+
+/* number of bf16 elements of a packed weight image with n_rows GEMM rows and
+ * kh*kw*k_channels reduction length (padded to the 64-element K chunk) */
+size_t hb200_packed_weight_elems(int n_rows, int k_channels, int kh, int kw);
+/* shared-memory operand layout used by the conv kernels AND the weight images
+ * (0 = no-swizzle interleaved core matrices, 1 = 128-byte swizzle); set before packing. */
+int hb200_set_umma_layout(int layout);
+int hb200_get_umma_layout(void);
+
+/* raw tcgen05 GEMM probe: D[M,N] f32 = A[M,K] * B[N,K]^T (bf16, K-major both), M%128==0,
+ * N%16==0 && N<=256, K%64==0.  layout: 0 = K-major no-swizzle interleaved core matrices,
+ * 1 = K-major 128B swizzle, 2 = MN-major no-swizzle (then A is given as [K,M], B as [K,N]).
+ * Used by the tests to pin the smem/instruction descriptor encodings on hardware. */
+int hb200_umma_gemm_probe(const hb200_bf16* a, const hb200_bf16* b, float* d, int m, int n, int k,
+                          int layout, hb200_stream_t stream);
+
+/* ---- GroupNorm / ReLU / pooling / residual elementwise passes (bf16 NHWC) ---------------
+ * replace nn.GroupNorm, nn.ReLU, nn.MaxPool2d and the residual add of BasicBlock
+ * (HB/rl/ddppo/policy/resnet.py:37-69, 207-219, 272-281).
+ * stats f32 [B,G,2] = (sum, sumsq) over the (C/G)*H*W elements of each group (conv epilogue).
+ */
+/* out = act(gamma * (y - mu) * rstd + beta);  relu: 0/1;  out is bf16, or f32 when out_f32 */
+int hb200_gn_apply(const hb200_bf16* y, const float* stats, const float* gamma, const float* beta,
+                   void* out, int out_f32, int batch, int hw, int channels, int groups, float eps,
+                   int relu, hb200_stream_t stream);
+/* out = relu(GN(y) + res)  with res either an activation tensor (res_stats NULL) or a second
+ * pre-norm tensor normalised with (res_stats, res_gamma, res_beta) (downsample branch). */
+int hb200_gn_residual_relu(const hb200_bf16* y, const float* stats, const float* gamma,
+                           const float* beta, const hb200_bf16* res, const float* res_stats,
+                           const float* res_gamma, const float* res_beta, hb200_bf16* out,
+                           int batch, int hw, int channels, int groups, float eps,
+                           hb200_stream_t stream);
+/* out[B,H/2,W/2,C] = maxpool3x3s2p1(relu(GN(y[B,H,W,C]))); argmax u8 (0..8) saved for bwd */
+int hb200_gn_relu_maxpool(const hb200_bf16* y, const float* stats, const float* gamma,
+                          const float* beta, hb200_bf16* out, uint8_t* argmax, int batch, int h,
+                          int w, int channels, int groups, float eps, hb200_stream_t stream);
+/* dz[B,H,W,C] (grad wrt the GN output BEFORE relu masking is applied by the GN backward)
+ * scattered from dout[B,H/2,W/2,C] through argmax */
+int hb200_maxpool_bwd(const hb200_bf16* dout, const uint8_t* argmax, hb200_bf16* dz, int batch,
+                      int h, int w, int channels, hb200_stream_t stream);
+/* GroupNorm backward, two passes.  g = upstream grad wrt the activation that follows GN.
+ * mask_mode 0: no ReLU (g is grad wrt z);  1: ReLU directly after GN (mask = z > 0, z recomputed);
+ * 2: mask from `act` tensor (mask = act > 0; block output relu(GN(y)+res)).
+ * pass 1 accumulates sums f32 [B,G,2] = (sum gamma*gz, sum gamma*gz*xhat) and dgamma/dbeta f32 [C]
+ * (atomics, caller zeroes); pass 2 writes dy (grad wrt the conv output y) and, if gz_out != NULL,
+ * the masked upstream grad gz (the residual-branch gradient). */
+int hb200_gn_bwd_reduce(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
+                        const float* stats, const float* gamma, const float* beta, float* sums,
+                        float* dgamma, float* dbeta, int batch, int hw, int channels, int groups,
+                        float eps, int mask_mode, hb200_stream_t stream);
+int hb200_gn_bwd_apply(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
+                       const float* stats, const float* gamma, const float* beta,
+                       const float* sums, hb200_bf16* dy, hb200_bf16* gz_out, int batch, int hw,
+                       int channels, int groups, float eps, int mask_mode, hb200_stream_t stream);
+
+/* ---- fp32 SIMT GEMM (linears, LSTM projections) ---------------------------------------------
+ * C[M,N] = alpha * op(A)[M,K] * op(B)[K,N] (+ bias[N]) (+ C if accumulate), optional ReLU.
+ * A(m,k) = a[m*a_ms + k*a_ks], B(k,n) = b[k*b_ks + n*b_ns], C row pitch ldc.
+ * replaces nn.Linear forward/backward (cuBLAS sgemm): visual_fc (resnet_policy.py:587-594),
+ * LSTM/GRU input projections and weight gradients (rnn_state_encoder.py:380-422).
+ */
+int hb200_sgemm(const float* a, long long a_ms, long long a_ks, const float* b, long long b_ks,
+                long long b_ns, float* c, long long ldc, const float* bias, int m, int n, int k,
+                float alpha, int accumulate, int relu, hb200_stream_t stream);
+/* bf16 activations [M,K] (optionally GN+ReLU applied on load: stats/gamma/beta non-NULL with
+ * per-row frame = m, K laid out NHWC (hw, C)) -> f32 [M,K].  Feeds visual_fc. */
+int hb200_bf16_to_f32(const hb200_bf16* x, float* out, long long n, hb200_stream_t stream);
+int hb200_f32_to_bf16(const float* x, hb200_bf16* out, long long n, hb200_stream_t stream);
+
+/* ---- recurrent state encoder ------------------------------------------------------------------
+ * replaces RNNStateEncoder.seq_forward/single_forward with nn.LSTM / nn.GRU and the whole
+ * packed-sequence machinery build_pack_info_from_dones/build_rnn_inputs/build_rnn_out_from_seq
+ * (HB/rl/models/rnn_state_encoder.py:35-277, 301-371): the masked recurrence
+ *   h_in = h_{t-1} * m_t ; (h_t, c_t) = cell(x_t, h_in, c_in)
+ * is exactly what that machinery computes (pinned by test/test_rnn_state_encoder.py:72-94).
+ *
+ * One call = one time step of one layer (frames of step t are rows [t*n, (t+1)*n)).
+ * xproj f32 [n, G*H] = x_t W_ih^T + b_ih + b_hh precomputed by hb200_sgemm (G=4 LSTM, 3 GRU;
+ * for GRU b_hh of the n-gate must NOT be folded: pass b_hn separately).
+ * w_hh f32 [G*H, H] (PyTorch gate order i,f,g,o / r,z,n).  masks u8 [n] (1 = not done).
+ * h_prev/c_prev f32 [n,H] (row pitch H); outputs h,c [n,H]; gates_out f32 [n,G*H] saved
+ * activations for backward (i,f,g,o post-nonlinearity).  GRU (config #3) is a "next" row.
+ */
+int hb200_lstm_step_fwd(const float* xproj, const float* w_hh, const uint8_t* masks,
+                        const float* h_prev, long long h_prev_stride, const float* c_prev,
+                        long long c_prev_stride, float* h, float* c, float* gates_out, int n,
+                        int hidden, hb200_stream_t stream);
+/* backward of one step: dh_out f32 [n,H] = grad wrt h_t from above (layer output, may be NULL);
+ * dh_rec/dc_rec f32 [n,H] = recurrent grads from step t+1 (already masked; NULL at the last
+ * step).  Writes dgates f32 [n,4H] (pre-activation grads = d xproj), dh_prev, dc_prev [n,H]
+ * (masked by m_t, i.e. grads wrt h_{t-1}, c_{t-1}). */
+int hb200_lstm_step_bwd(const float* dh_out, const float* dh_rec, const float* dc_rec,
+                        const float* gates, const float* c, const float* c_prev,
+                        long long c_prev_stride, const float* w_hh, const uint8_t* masks,
+                        float* dgates, float* dh_prev, float* dc_prev, int n, int hidden,
+                        hb200_stream_t stream);
+/* h_in[t] = (t == 0 ? h0 : h_seq[t-1]) * m_t for the whole sequence (input of dW_hh = dG^T h_in) */
+int hb200_rnn_shift_mask(const float* h_seq, const float* h0, long long h0_row_stride,
+                         const uint8_t* masks, float* h_in, int t_steps, int n, int hidden,
+                         hb200_stream_t stream);
+/* out[N] (+)= column sums of x[M,N] (bias gradients) */
+int hb200_colsum(const float* x, float* out, long long m, int n, int accumulate,
+                 hb200_stream_t stream);
+
+/* ---- goal / previous-action embeddings --------------------------------------------------------
+ * replaces tgt_embeding + prev_action_embedding + torch.cat of PointNavResNetNet.forward
+ * (HB/rl/ddppo/policy/resnet_policy.py:658-692, 747-763).
+ * goal f32 [rows,2] gathered through frame_rows; prev_actions i64 [rows]; masks u8 [rows].
+ * Writes columns [col0, col0+32) (goal) and [col0+32, col0+64) (prev action) of out f32 [B,ld].
+ */
+int hb200_embed_fwd(const float* goal, const int64_t* prev_actions, const uint8_t* masks,
+                    const int32_t* frame_rows, const float* w_tgt, const float* b_tgt,
+                    const float* emb_table, float* out, int ld, int col0, int batch,
+                    hb200_stream_t stream);
+/* d_out f32 [B,ld]; d_w_tgt [32,3], d_b_tgt [32], d_emb [A+1,32] accumulated with atomics */
+int hb200_embed_bwd(const float* goal, const int64_t* prev_actions, const uint8_t* masks,
+                    const int32_t* frame_rows, const float* d_out, int ld, int col0, int batch,
+                    int n_emb, float* d_w_tgt, float* d_b_tgt, float* d_emb,
+                    hb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HB200_H_ */

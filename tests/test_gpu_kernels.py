@@ -1,0 +1,551 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (libhb200.so) against the CPU oracle
+(oracle/torch_oracle.py) or a plain fp32 torch restatement of the same op.
+
+Tolerances (stated per test): GAE variant 1 is bit-exact; fp32 kernels 1e-5..1e-4; bf16
+tensor-core convolutions are compared against an fp32 convolution of the SAME bf16-rounded
+operands, so only accumulation order + the final bf16 rounding of the output differ (2^-8 rel).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+from oracle import torch_oracle as O  # noqa: E402  (checker only)
+
+DEV = "cuda"
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# GAE / advantages
+# ---------------------------------------------------------------------------------------------
+def _rollout_scalars(T, N, seed, p_done=1 / 25):
+    g = torch.Generator().manual_seed(seed)
+    rewards = torch.randn(T + 1, N, 1, generator=g) * 0.1
+    masks = torch.rand(T + 1, N, 1, generator=g) > p_done
+    rewards = rewards + 2.5 * (~masks).float()
+    values = torch.randn(T + 1, N, 1, generator=g)
+    returns_stale = torch.randn(T + 1, N, 1, generator=g)
+    next_value = torch.randn(N, 1, generator=g)
+    return rewards, values, masks, returns_stale, next_value
+
+
+@pytest.mark.parametrize("T,N,t_cur", [(128, 64, 128), (16, 8, 16), (128, 64, 37), (5, 3, 5), (1, 1, 1),
+                                       (33, 129, 33), (128, 2048, 128)])
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("use_gae", [True, False])
+def test_gae_adv(hb, T, N, t_cur, variant, use_gae):
+    from habitat_lab_b200 import ops
+
+    rewards, values, masks, stale, next_value = _rollout_scalars(T, N, 7 * T + N)
+    v_ref = values.clone()
+    ret_ref = O.compute_returns(rewards, v_ref, masks, next_value, t_cur, use_gae, 0.99, 0.95)
+    # rows the reference does not write keep whatever the buffer held
+    keep = torch.ones(T + 1, dtype=torch.bool)
+    keep[: t_cur + (0 if use_gae else 1)] = False
+    ret_full = torch.where(keep.view(-1, 1, 1), stale, ret_ref)
+    adv_ref = O.get_advantages(ret_full, v_ref, normalize=False)
+
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    r, v, m, nv = d(rewards), d(values), d(masks), d(next_value)
+    ret = d(stale)
+    adv = torch.empty_like(ret)
+    stats = torch.zeros(4, dtype=torch.float64, device=DEV)
+    ops.gae_adv(r, v, m, nv, ret, adv, stats, t_cur, 0.99, 0.95, use_gae, variant)
+    torch.cuda.synchronize()
+    if variant == 1 or not use_gae:
+        assert torch.equal(ret.cpu(), ret_full), "serial GAE must be bit-exact with the reference order"
+        assert torch.equal(adv.cpu(), adv_ref)
+    else:
+        torch.testing.assert_close(ret.cpu(), ret_full, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(adv.cpu(), adv_ref, rtol=1e-5, atol=2e-5)
+    assert torch.equal(v.cpu(), v_ref)  # bootstrap row written like the reference
+    # normalisation (single-process unbiased var_mean, ppo.py:151-157)
+    adv_n_ref = O.get_advantages(ret_full, v_ref, normalize=True)
+    ops.adv_normalize(adv, stats=stats)
+    torch.testing.assert_close(adv.cpu(), adv_n_ref, rtol=1e-4, atol=1e-5)
+    # distributed statistics path (ddppo.py:59-84) with explicit mean/var
+    adv2 = d(adv_ref)
+    var, mean = O.distributed_var_mean([adv_ref, adv_ref * 0.5 + 0.1])
+    ops.adv_normalize(adv2, mean_var=torch.tensor([mean, var], device=DEV))
+    torch.testing.assert_close(adv2.cpu(), O.get_advantages(ret_full, v_ref, True, (var, mean)), rtol=1e-5, atol=1e-6)
+
+
+def test_gae_nonfinite_excluded_from_stats(hb):
+    from habitat_lab_b200 import ops
+
+    T, N = 8, 4
+    rewards, values, masks, stale, next_value = _rollout_scalars(T, N, 3)
+    stale[T, 1, 0] = float("inf")  # stale/bootstrap rows can be non-finite; ppo.py:146 filters them
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    ret, adv = d(stale), torch.empty(T + 1, N, 1, device=DEV)
+    stats = torch.zeros(4, dtype=torch.float64, device=DEV)
+    ops.gae_adv(d(rewards), d(values), d(masks), d(next_value), ret, adv, stats, T, 0.99, 0.95, True, 1)
+    assert stats[2].item() == (T + 1) * N - 1
+
+
+# ---------------------------------------------------------------------------------------------
+# heads + PPO loss
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,A", [(4096, 512, 4), (257, 512, 4), (64, 128, 6), (7, 32, 2)])
+@pytest.mark.parametrize("use_clip_v", [True, False])
+@pytest.mark.parametrize("perturb", [0.0, 0.5])
+def test_ppo_loss(hb, B, H, A, use_clip_v, perturb):
+    from habitat_lab_b200 import ops
+
+    g = torch.Generator().manual_seed(B + H + A)
+    feats = torch.randn(B, H, generator=g)
+    w_act = torch.randn(A, H, generator=g) * (0.01 + perturb * 0.1)
+    b_act = torch.randn(A, generator=g) * 0.1
+    w_val = torch.randn(1, H, generator=g) * 0.05
+    b_val = torch.randn(1, generator=g)
+    actions = torch.randint(0, A, (B, 1), generator=g)
+    with torch.no_grad():
+        v0, lp0, _ = O.heads(feats, w_act, b_act, w_val, b_val, actions)
+    batch = dict(
+        action_log_probs=lp0 + perturb * torch.randn(B, 1, generator=g) * 0.3,
+        advantages=torch.randn(B, 1, generator=g),
+        value_preds=v0 + perturb * torch.randn(B, 1, generator=g),
+        returns=v0 + torch.randn(B, 1, generator=g),
+    )
+    clip, c_v, c_e = 0.2, 0.5, 0.01
+    req = [t.clone().requires_grad_(True) for t in (feats, w_act, b_act, w_val, b_val)]
+    v, lp, ent = O.heads(*req, actions)
+    ref = O.ppo_loss(v, lp, ent, batch, clip, c_v, c_e, use_clip_v)
+    ref["total_loss"].backward()
+
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    out = dict(values=torch.empty(B, device=DEV), log_probs=torch.empty(B, device=DEV),
+               entropy=torch.empty(B, device=DEV), d_features=torch.empty(B, H, device=DEV),
+               d_w_act=torch.empty(A, H, device=DEV), d_b_act=torch.empty(A, device=DEV),
+               d_w_val=torch.empty(H, device=DEV), d_b_val=torch.empty(1, device=DEV),
+               metrics=torch.empty(ops.N_METRICS, device=DEV))
+    ws = ops.ppo_loss_workspace(B, H, A, DEV)
+    ops.ppo_loss(d(feats), d(w_act), d(b_act), d(w_val), d(b_val), d(actions.view(-1)),
+                 d(batch["action_log_probs"].view(-1)), d(batch["advantages"].view(-1)),
+                 d(batch["value_preds"].view(-1)), d(batch["returns"].view(-1)), clip, c_v, c_e, use_clip_v, True,
+                 out, ws)
+    torch.cuda.synchronize()
+    mt = out["metrics"].cpu()
+    for i, k in enumerate(ops.METRIC_KEYS):
+        torch.testing.assert_close(mt[i], ref[k].detach().float().reshape(()), rtol=2e-4, atol=2e-6, msg=lambda s, k=k: f"{k}: {s}")
+    torch.testing.assert_close(out["values"].cpu(), v.detach().view(-1), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out["log_probs"].cpu(), lp.detach().view(-1), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out["entropy"].cpu(), ent.detach().view(-1), rtol=1e-4, atol=1e-5)
+    gscale = max(1.0 / B, 1e-6)
+    torch.testing.assert_close(out["d_features"].cpu(), req[0].grad, rtol=1e-3, atol=1e-3 * gscale)
+    torch.testing.assert_close(out["d_w_act"].cpu(), req[1].grad, rtol=1e-3, atol=2e-5)
+    torch.testing.assert_close(out["d_b_act"].cpu(), req[2].grad, rtol=1e-3, atol=2e-5)
+    torch.testing.assert_close(out["d_w_val"].cpu(), req[3].grad.view(-1), rtol=1e-3, atol=2e-5)
+    torch.testing.assert_close(out["d_b_val"].cpu(), req[4].grad, rtol=1e-3, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# clip + Adam
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [8_481_125, 1003, 4])
+@pytest.mark.parametrize("max_norm", [0.2, 1e9])
+def test_clip_adam(hb, n, max_norm):
+    from habitat_lab_b200 import ops
+
+    g = torch.Generator().manual_seed(n)
+    n_pad = (n + 3) // 4 * 4
+    p0 = torch.randn(n, generator=g)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=2.5e-4, eps=1e-5)
+    flat = torch.zeros(4, n_pad, device=DEV)  # params, grads, m, v share one allocation (16B aligned rows)
+    flat[0, :n] = p0.to(DEV)
+    ws = ops.clip_adam_workspace(n, DEV)
+    gn = torch.zeros(1, device=DEV)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g) * (0.01 * step)
+        ref_p.grad = grad.clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_([ref_p], max_norm)
+        opt.step()
+        flat[1, :n] = grad.to(DEV)
+        ops.clip_adam(flat[0, :n], flat[1, :n], flat[2, :n], flat[3, :n], 2.5e-4, (0.9, 0.999), 1e-5, 0.0,
+                      max_norm, 1.0, step, gn, ws)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(gn.cpu()[0], ref_norm, rtol=1e-5, atol=1e-7)
+        torch.testing.assert_close(flat[0, :n].cpu(), ref_p.detach(), rtol=1e-5, atol=2e-7)
+    st = opt.state[ref_p]
+    torch.testing.assert_close(flat[2, :n].cpu(), st["exp_avg"], rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(flat[3, :n].cpu(), st["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 descriptor probe + convolutions
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", [0, 2])
+def test_umma_probe(hb, layout):
+    from habitat_lab_b200 import ops
+
+    m, n, k = 256, 64, 192
+    a = bf(torch.randn(m, k, device=DEV))
+    b = bf(torch.randn(n, k, device=DEV))
+    d = torch.zeros(m, n, device=DEV)
+    if layout == 2:
+        ops.umma_gemm_probe(a.t().contiguous(), b.t().contiguous(), d, m, n, k, 2)
+    else:
+        ops.umma_gemm_probe(a, b, d, m, n, k, layout)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(d, a.float() @ b.float().t(), rtol=1e-4, atol=1e-3)
+
+
+CONV_CASES = [
+    # B, H, W, Ci_real, Ci_pad, Co, k, stride, pad
+    (2, 32, 32, 32, 32, 32, 3, 1, 1),     # layer1
+    (3, 32, 32, 32, 32, 64, 3, 2, 1),     # layer2.0 conv a
+    (3, 32, 32, 32, 32, 64, 1, 2, 0),     # layer2.0 downsample
+    (2, 16, 16, 64, 64, 64, 3, 1, 1),
+    (2, 8, 8, 128, 128, 128, 3, 1, 1),
+    (4, 4, 4, 256, 256, 256, 3, 1, 1),    # layer4 (two frames per warp in the stats epilogue)
+    (4, 4, 4, 256, 256, 128, 3, 1, 1),    # compression
+    (2, 64, 64, 4, 8, 32, 7, 2, 3),       # stem, 4 real channels padded to 8
+    (1, 31, 17, 32, 32, 32, 3, 1, 1),     # odd sizes, ragged tile tail
+    (9, 8, 8, 64, 64, 128, 3, 2, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(hb, case):
+    from habitat_lab_b200 import ops
+
+    B, H, W, ci_real, ci, co, k, stride, pad = case
+    torch.manual_seed(sum(case))
+    x = torch.randn(B, ci_real, H, W, device=DEV)
+    w = torch.randn(co, ci_real, k, k, device=DEV) * (1.0 / math.sqrt(ci_real * k * k))
+    xb, wb = bf(x).float(), bf(w).float()
+    y_ref = F.conv2d(xb, wb, stride=stride, padding=pad)
+    s = ops.conv_shape(B, H, W, ci, co, k, k, stride, pad)
+    x_nhwc = torch.zeros(B, H, W, ci, device=DEV, dtype=torch.bfloat16)
+    x_nhwc[..., :ci_real] = bf(nhwc(x))
+    wp, wt = ops.pack_conv_weight(w, ci, want_t=ci >= 32)
+    y = torch.empty(B, s.ho, s.wo, co, device=DEV, dtype=torch.bfloat16)
+    groups = 16 if co % 16 == 0 and co // 16 >= 2 else 1
+    stats = torch.zeros(B, groups, 2, device=DEV)
+    ops.conv_fwd(x_nhwc, wp, y, s, stats, groups)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(nchw(y.float()), y_ref, rtol=1e-2, atol=1e-2)
+    # fused GroupNorm statistics: sum / sum of squares per (frame, group) of the fp32 accumulators
+    yg = y_ref.view(B, groups, -1)
+    torch.testing.assert_close(stats[..., 0], yg.sum(-1), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(stats[..., 1], (yg * yg).sum(-1), rtol=1e-3, atol=2e-2)
+
+    dy = torch.randn_like(y_ref)
+    dyb = bf(dy).float()
+    dy_nhwc = bf(nhwc(dy))
+    # weight gradient
+    dw_ref = torch.nn.grad.conv2d_weight(xb, w.shape, dyb, stride=stride, padding=pad)
+    acc = torch.zeros(k * k * ci, co, device=DEV)
+    ops.conv_wgrad(x_nhwc, dy_nhwc, acc, s)
+    dw = torch.empty_like(w)
+    ops.unpack_conv_wgrad(acc, dw, ci)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dw, dw_ref, rtol=2e-3, atol=2e-3 * dw_ref.abs().max().item())
+    # data gradient (+ fused residual-gradient add)
+    if ci >= 32:
+        dx_ref = torch.nn.grad.conv2d_input(xb.shape, wb, dyb, stride=stride, padding=pad)
+        addend = bf(torch.randn(B, H, W, ci, device=DEV))
+        dx = torch.empty(B, H, W, ci, device=DEV, dtype=torch.bfloat16)
+        ops.conv_dgrad(dy_nhwc, wt, dx, s, addend=None)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(nchw(dx.float()), dx_ref, rtol=1e-2, atol=1e-2 * max(1.0, dx_ref.abs().max().item()))
+        ops.conv_dgrad(dy_nhwc, wt, dx, s, addend=addend)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(nchw(dx.float()), dx_ref + nchw(addend.float()), rtol=1e-2,
+                                   atol=2e-2 * max(1.0, dx_ref.abs().max().item()))
+
+
+# ---------------------------------------------------------------------------------------------
+# input prep + running mean/var
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("has_rgb,has_depth", [(True, True), (False, True), (True, False)])
+def test_prep(hb, has_rgb, has_depth):
+    from habitat_lab_b200 import ops
+
+    rows, B, H, W = 12, 5, 32, 48
+    g = torch.Generator().manual_seed(11)
+    rgb = torch.randint(0, 256, (rows, H, W, 3), generator=g, dtype=torch.uint8)
+    depth = torch.rand(rows, H, W, 1, generator=g)
+    frame_rows = torch.tensor([3, 0, 11, 7, 7], dtype=torch.int32)
+    C = (3 if has_rgb else 0) + (1 if has_depth else 0)
+    obs, keys = {}, []
+    if has_rgb:
+        obs["rgb"] = rgb[frame_rows.long()]
+        keys.append("rgb")
+    if has_depth:
+        obs["depth"] = depth[frame_rows.long()]
+        keys.append("depth")
+    xs = []
+    for kname in keys:
+        o = obs[kname].permute(0, 3, 1, 2)
+        xs.append(o.float() * (1.0 / 255.0) if o.dtype == torch.uint8 else o)
+    x = F.avg_pool2d(torch.cat(xs, 1), 2)
+    mean, var, count = torch.rand(1, C, 1, 1), torch.rand(1, C, 1, 1) + 0.01, torch.tensor(7.0)
+    m2, v2, c2 = O.running_mean_var_update(x, mean, var, count)
+    ref = O.running_mean_var_apply(x, m2, v2)
+
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    drgb = d(rgb) if has_rgb else None
+    ddepth = d(depth) if has_depth else None
+    stats = torch.zeros(17, dtype=torch.float64, device=DEV)
+    rm, rv, rc = d(mean.view(-1)), d(var.view(-1)), d(count.view(1))
+    ss = torch.zeros(16, device=DEV)
+    out = torch.empty(B, H // 2, W // 2, 8, device=DEV, dtype=torch.bfloat16)
+    fr = d(frame_rows)
+    ops.prep_stats(drgb, ddepth, fr, H, W, stats)
+    ops.prep_finalize(stats, rm, rv, rc, ss, C, (H // 2) * (W // 2), True)
+    ops.prep_apply(drgb, ddepth, fr, H, W, ss, out)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(rm.cpu(), m2.view(-1), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(rv.cpu(), v2.view(-1), rtol=1e-4, atol=1e-6)
+    assert rc.item() == c2.item()
+    got = nchw(out.float().cpu())
+    torch.testing.assert_close(got[:, :C], ref, rtol=1e-2, atol=1e-2)  # bf16 output
+    assert (got[:, C:] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------
+# GroupNorm passes
+# ---------------------------------------------------------------------------------------------
+def _stats_of(y_nchw, groups):
+    B = y_nchw.shape[0]
+    yg = y_nchw.reshape(B, groups, -1)
+    return torch.stack([yg.sum(-1), (yg * yg).sum(-1)], -1).contiguous()
+
+
+@pytest.mark.parametrize("B,C,H,W,G", [(3, 32, 16, 16, 16), (2, 64, 8, 8, 16), (2, 128, 4, 4, 1), (5, 256, 4, 4, 16)])
+def test_groupnorm_passes(hb, B, C, H, W, G):
+    from habitat_lab_b200 import ops
+
+    torch.manual_seed(C + H)
+    y = bf(torch.randn(B, C, H, W, device=DEV) * 1.5 + 0.3).float()
+    res = bf(torch.randn(B, C, H, W, device=DEV)).float()
+    gamma = torch.rand(C, device=DEV) + 0.5
+    beta = torch.randn(C, device=DEV) * 0.2
+    stats = _stats_of(y, G)
+    yb, resb = bf(nhwc(y)), bf(nhwc(res))
+    hw = H * W
+    # --- forward: GN + ReLU
+    out = torch.empty_like(yb)
+    ops.gn_apply(yb, stats, gamma, beta, out, B, hw, C, G, relu=True)
+    yr = y.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = F.group_norm(yr, G, gr, br, eps=1e-5)
+    a = F.relu(z)
+    torch.testing.assert_close(nchw(out.float()), a.detach(), rtol=1e-2, atol=1e-2)
+    outf = torch.empty(B, H, W, C, device=DEV)
+    ops.gn_apply(yb, stats, gamma, beta, outf, B, hw, C, G, relu=True)
+    torch.testing.assert_close(nchw(outf), a.detach(), rtol=1e-4, atol=1e-4)
+    # --- backward through GN + ReLU (mask_mode 1)
+    g = bf(torch.randn(B, C, H, W, device=DEV)).float()
+    a.backward(g)
+    sums = torch.zeros(B, G, 2, device=DEV)
+    dga, dbe = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    gb = bf(nhwc(g))
+    ops.gn_bwd_reduce(gb, None, yb, stats, gamma, beta, sums, dga, dbe, B, hw, C, G, 1)
+    dy = torch.empty_like(yb)
+    ops.gn_bwd_apply(gb, None, yb, stats, gamma, beta, sums, dy, None, B, hw, C, G, 1)
+    torch.cuda.synchronize()
+    sc = yr.grad.abs().max().item()
+    torch.testing.assert_close(nchw(dy.float()), yr.grad, rtol=2e-2, atol=1e-2 * sc)
+    torch.testing.assert_close(dga, gr.grad, rtol=1e-3, atol=1e-3 * gr.grad.abs().max().item())
+    torch.testing.assert_close(dbe, br.grad, rtol=1e-3, atol=1e-3 * br.grad.abs().max().item())
+    # --- residual block output: relu(GN(y) + res), backward with mask from the block output
+    blk = torch.empty_like(yb)
+    ops.gn_residual_relu(yb, stats, gamma, beta, resb, blk, B, hw, C, G)
+    yr2 = y.clone().requires_grad_(True)
+    rr2 = res.clone().requires_grad_(True)
+    o2 = F.relu(F.group_norm(yr2, G, gamma, beta, eps=1e-5) + rr2)
+    torch.testing.assert_close(nchw(blk.float()), o2.detach(), rtol=1e-2, atol=2e-2)
+    o2.backward(g)
+    sums.zero_(); dga.zero_(); dbe.zero_()
+    gz = torch.empty_like(yb)
+    # mask from the exact fp32 block output (bf16 copies of tiny positives could flip the mask)
+    act = bf(nhwc(o2.detach()))
+    ops.gn_bwd_reduce(gb, act, yb, stats, gamma, beta, sums, dga, dbe, B, hw, C, G, 2)
+    ops.gn_bwd_apply(gb, act, yb, stats, gamma, beta, sums, dy, gz, B, hw, C, G, 2)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(nchw(gz.float()), rr2.grad, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(nchw(dy.float()), yr2.grad, rtol=2e-2, atol=1e-2 * yr2.grad.abs().max().item())
+    # --- downsample variant: relu(GN(y) + GN_d(yd))
+    gd, bd = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
+    rstats = _stats_of(res, G)
+    ops.gn_residual_relu(yb, stats, gamma, beta, resb, blk, B, hw, C, G, rstats, gd, bd)
+    o3 = F.relu(F.group_norm(y, G, gamma, beta, eps=1e-5) + F.group_norm(res, G, gd, bd, eps=1e-5))
+    torch.testing.assert_close(nchw(blk.float()), o3, rtol=1e-2, atol=3e-2)
+
+
+def test_gn_relu_maxpool(hb):
+    from habitat_lab_b200 import ops
+
+    B, C, H, W, G = 3, 32, 16, 24, 16
+    torch.manual_seed(5)
+    y = bf(torch.randn(B, C, H, W, device=DEV)).float()
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
+    stats = _stats_of(y, G)
+    yb = bf(nhwc(y))
+    out = torch.empty(B, H // 2, W // 2, C, device=DEV, dtype=torch.bfloat16)
+    arg = torch.empty(B, H // 2, W // 2, C, device=DEV, dtype=torch.uint8)
+    ops.gn_relu_maxpool(yb, stats, gamma, beta, out, arg, B, H, W, C, G)
+    yr = y.clone().requires_grad_(True)
+    zr = F.relu(F.group_norm(yr, G, gamma, beta, eps=1e-5))
+    zr.retain_grad()
+    pr = F.max_pool2d(zr, 3, 2, 1)
+    torch.testing.assert_close(nchw(out.float()), pr.detach(), rtol=1e-2, atol=1e-2)
+    g = bf(torch.randn_like(pr)).float()
+    pr.backward(g)
+    dz = torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16)
+    ops.maxpool_bwd(bf(nhwc(g)), arg, dz, B, H, W, C)
+    torch.cuda.synchronize()
+    # compare only where the max is unique & positive (ties among zeros carry no gradient after ReLU)
+    ref = zr.grad
+    got = nchw(dz.float())
+    mask = zr.detach() > 1e-3
+    torch.testing.assert_close(got[mask], ref[mask], rtol=1e-2, atol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------
+# sgemm, LSTM recurrence, embeddings
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 2048), (300, 70, 50), (128, 2048, 576), (5, 7, 3)])
+def test_sgemm_linear(hb, M, N, K):
+    from habitat_lab_b200 import ops
+
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / math.sqrt(K)
+    b = torch.randn(N, device=DEV)
+    out = torch.empty(M, N + 8, device=DEV)  # ldc > N
+    ops.linear_fwd(x, w, b, out, relu=True)
+    ref = F.relu(F.linear(x.double(), w.double(), b.double())).float()
+    torch.testing.assert_close(out[:, :N], ref, rtol=1e-4, atol=1e-4)
+    dy = torch.randn(M, N, device=DEV)
+    dx = torch.empty(M, K, device=DEV)
+    ops.linear_bwd_input(dy, w, dx)
+    torch.testing.assert_close(dx, (dy.double() @ w.double()).float(), rtol=1e-4, atol=1e-4)
+    dw = torch.empty(N, K, device=DEV)
+    ops.linear_bwd_weight(dy, x, dw)
+    ref_dw = (dy.double().t() @ x.double()).float()
+    torch.testing.assert_close(dw, ref_dw, rtol=1e-4, atol=1e-4 * max(1.0, ref_dw.abs().max().item()))
+    db = torch.empty(N, device=DEV)
+    ops.colsum(dy, db)
+    torch.testing.assert_close(db, dy.sum(0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("T,n,H,D", [(16, 8, 512, 576), (7, 3, 32, 32), (33, 33, 128, 64)])
+def test_lstm_masked_recurrence(hb, T, n, H, D):
+    """The logic of test/test_rnn_state_encoder.py:72-94: flat (T*N) batch + masks must equal the
+    step-by-step loop h = where(mask, h, 0); rnn(x_t, h), norm of the difference < 1e-3."""
+    from habitat_lab_b200 import ops
+
+    torch.manual_seed(T * n + H)
+    lstm = torch.nn.LSTM(D, H, num_layers=1)
+    for name, p in lstm.named_parameters():
+        if "weight" in name:
+            torch.nn.init.orthogonal_(p)
+        else:
+            torch.nn.init.normal_(p, std=0.1)
+    sd = {"rnn." + k: v.detach() for k, v in lstm.state_dict().items()}
+    x = torch.randn(T * n, D)
+    masks = torch.rand(T * n, 1) > (1 / 25)
+    hidden = torch.randn(n, 2, H)
+    xr = x.clone().requires_grad_(True)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out_ref, hid_ref = O.rnn_seq_forward(xr, hidden, masks, sdr, "rnn.", "LSTM", 1, n)
+    gout = torch.randn(T * n, H)
+    (out_ref * gout).sum().backward()
+
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    w_ih, w_hh = d(sd["rnn.weight_ih_l0"]), d(sd["rnn.weight_hh_l0"])
+    bias = d(sd["rnn.bias_ih_l0"] + sd["rnn.bias_hh_l0"])
+    xd, md = d(x), d(masks.view(-1)).view(torch.uint8)
+    xproj = torch.empty(T * n, 4 * H, device=DEV)
+    ops.linear_fwd(xd, w_ih, bias, xproj)
+    h0, c0 = d(hidden[:, 0]), d(hidden[:, 1])
+    hs = torch.empty(T, n, H, device=DEV)
+    cs = torch.empty(T, n, H, device=DEV)
+    gates = torch.empty(T, n, 4 * H, device=DEV)
+    for t in range(T):
+        ops.lstm_step_fwd(xproj[t * n:(t + 1) * n], w_hh, md[t * n:(t + 1) * n], h0 if t == 0 else hs[t - 1],
+                          c0 if t == 0 else cs[t - 1], hs[t], cs[t], gates[t], n, H)
+    torch.cuda.synchronize()
+    diff = (hs.view(T * n, H).cpu() - out_ref.detach()).norm().item()
+    assert diff < 1e-3, diff
+    torch.testing.assert_close(hs[-1].cpu(), hid_ref[:, 0].detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(cs[-1].cpu(), hid_ref[:, 1].detach(), rtol=1e-4, atol=1e-5)
+    # backward through time
+    dg = torch.empty(T, n, 4 * H, device=DEV)
+    dh = [torch.zeros(n, H, device=DEV) for _ in range(2)]
+    dc = [torch.zeros(n, H, device=DEV) for _ in range(2)]
+    gd = d(gout).view(T, n, H)
+    for t in reversed(range(T)):
+        last = t == T - 1
+        ops.lstm_step_bwd(gd[t], None if last else dh[(t + 1) % 2], None if last else dc[(t + 1) % 2], gates[t],
+                          cs[t], c0 if t == 0 else cs[t - 1], w_hh, md[t * n:(t + 1) * n], dg[t], dh[t % 2],
+                          dc[t % 2], n, H)
+    dgf = dg.view(T * n, 4 * H)
+    dx = torch.empty(T * n, D, device=DEV)
+    ops.linear_bwd_input(dgf, w_ih, dx)
+    dw_ih = torch.empty_like(w_ih)
+    ops.linear_bwd_weight(dgf, xd, dw_ih)
+    hin = torch.empty(T, n, H, device=DEV)
+    ops.rnn_shift_mask(hs, h0, md, hin, T, n, H)
+    dw_hh = torch.empty_like(w_hh)
+    ops.linear_bwd_weight(dgf, hin.view(T * n, H), dw_hh)
+    db = torch.empty(4 * H, device=DEV)
+    ops.colsum(dgf, db)
+    torch.cuda.synchronize()
+    tol = dict(rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(dx.cpu(), xr.grad, **tol)
+    torch.testing.assert_close(dw_ih.cpu(), sdr["rnn.weight_ih_l0"].grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dw_hh.cpu(), sdr["rnn.weight_hh_l0"].grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(db.cpu(), sdr["rnn.bias_ih_l0"].grad, rtol=1e-3, atol=1e-3)
+
+
+def test_embeddings(hb):
+    from habitat_lab_b200 import ops
+
+    rows, B, A = 40, 17, 4
+    g = torch.Generator().manual_seed(2)
+    goal = torch.rand(rows, 2, generator=g) * torch.tensor([10.0, 6.28]) - torch.tensor([0.0, 3.14])
+    pa = torch.randint(0, A, (rows, 1), generator=g)
+    masks = torch.rand(rows, 1, generator=g) > 0.3
+    fr = torch.randint(0, rows, (B,), generator=g).int()
+    w = torch.randn(32, 3, generator=g, requires_grad=True)
+    b = torch.randn(32, generator=g, requires_grad=True)
+    emb = torch.randn(A + 1, 32, generator=g, requires_grad=True)
+    gsel = goal[fr.long()]
+    gi = torch.stack([gsel[:, 0], torch.cos(-gsel[:, 1]), torch.sin(-gsel[:, 1])], -1)
+    ref_t = F.linear(gi, w, b)
+    idx = torch.where(masks[fr.long()].view(-1), pa[fr.long()].view(-1) + 1, torch.zeros(B, dtype=torch.long))
+    ref_e = F.embedding(idx, emb)
+    d = lambda t: t.detach().to(DEV).contiguous()  # noqa: E731
+    out = torch.zeros(B, 576, device=DEV)
+    ops.embed_fwd(d(goal), d(pa.view(-1)), d(masks.view(-1)), d(fr), d(w), d(b), d(emb), out, 512)
+    torch.testing.assert_close(out[:, 512:544].cpu(), ref_t.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out[:, 544:576].cpu(), ref_e.detach(), rtol=0, atol=0)
+    dout = torch.randn(B, 576, generator=g)
+    (ref_t * dout[:, 512:544]).sum().backward()
+    (ref_e * dout[:, 544:576]).sum().backward()
+    dw, db, de = torch.zeros(32, 3, device=DEV), torch.zeros(32, device=DEV), torch.zeros(A + 1, 32, device=DEV)
+    ops.embed_bwd(d(goal), d(pa.view(-1)), d(masks.view(-1)), d(fr), d(dout), 512, dw, db, de)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dw.cpu(), w.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(db.cpu(), b.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(de.cpu(), emb.grad, rtol=1e-4, atol=1e-4)
