@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- DD-PPO learner frames/sec on BASELINE.json config #2:
+PointNav DD-PPO, ResNet18 (baseplanes 32, GroupNorm 16) RGB-D 256x256, LSTM-512 x 2,
+num_envs = 64 per rank, T = 128, ppo_epoch = 2, num_mini_batch = 2, synthetic observations.
+
+One "step" = one learner iteration on a full rollout: RolloutStorage.compute_returns (GAE) +
+PPO.update (2 epochs x 2 minibatches of 4096 frames: forward, backward, [all-reduce], clip,
+Adam).  value = world * T * N / t_step  (the reference's perf/fps definition,
+habitat-baselines/habitat_baselines/rl/ppo/ppo_trainer.py:595-598, learner part).
+
+    python bench.py --gpus 1 --steps K --warmup W           # this repo's sm_100a path
+    python bench.py --impl reference ...                     # the reference's CPU learner (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU, NCCL
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(T=128, N=64, H=256, W=256, hidden=512, layers=2, ppo_epoch=2, num_mini_batch=2, clip_param=0.2,
+           value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, gamma=0.99, tau=0.95)
+METRIC = "DD-PPO learner frames/sec (ResNet18 RGB-D 256x256)"
+# algorithmic work per frame of config #2 (SURVEY.md section 8d / DESIGN.md)
+CONV_FWD_GFLOP = 0.3376
+CONV_TRAIN_GFLOP = 0.9614  # fwd + dgrad + wgrad, no dgrad for conv1
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU learner (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------
+def _cpu_learner_sample(threads, updates, T=16, N=8):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from recipe import recipe_state_dict, synthetic_rollout
+    from oracle.cpu_learner import time_cpu_learner
+    import habitat_lab_b200 as hb
+    from habitat_lab_b200.synthetic import pointnav_spaces
+
+    obs_space, act_space = pointnav_spaces(CFG["H"], CFG["W"])
+    pol = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=CFG["hidden"], num_recurrent_layers=CFG["layers"],
+                                  rnn_type="LSTM", normalize_visual_inputs=True)  # shapes only (holders)
+    shapes = {k: tuple(v.shape) for k, v in pol.state_dict().items()}
+    sd = recipe_state_dict(shapes, 7)
+    cfg = dict(visual_keys=["rgb", "depth"], ngroups=16, rnn_type="LSTM", num_layers=CFG["layers"])
+    make = lambda: synthetic_rollout(T, N, CFG["H"], CFG["W"], 4, 2 * CFG["layers"], CFG["hidden"], 5)  # noqa: E731
+    fps, dt = time_cpu_learner(make, sd, cfg, T, N, updates, threads, ppo_epoch=CFG["ppo_epoch"],
+                               num_mini_batch=CFG["num_mini_batch"])
+    sample = (f"{updates} learner iterations of T={T} x N={N} frames (256x256 RGB-D, {CFG['ppo_epoch']} epochs x "
+              f"{CFG['num_mini_batch']} minibatches) after 1 warm-up, {dt:.1f} s")
+    return fps, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    ms, vals = [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        fps, sample = _cpu_learner_sample(cores, updates=1)
+        if i >= args.warmup:
+            vals.append(fps)
+            ms.append((time.perf_counter() - t0) * 1e3)
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": _config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def _config(n):
+    return {"workload": "BASELINE configs[1]: PointNav DD-PPO ResNet18 RGB-D 256x256, LSTM-512x2, 64 envs/rank, "
+                        "T=128, 2 epochs x 2 minibatches (4096 frames each), synthetic obs",
+            "num_envs_per_rank": CFG["N"], "rollout_steps": CFG["T"], "frames_per_step_per_rank": CFG["T"] * CFG["N"],
+            "parallelism": f"dp{n}", "l2_policy": "inputs (3.8 GB of observations per rank) far exceed the 126 MB L2"}
+
+
+# ---------------------------------------------------------------------------------------------
+# hb200 arm
+# ---------------------------------------------------------------------------------------------
+def run_hb200(args):
+    import habitat_lab_b200 as hb
+    from habitat_lab_b200 import ops
+    from habitat_lab_b200.synthetic import fill_rollout_, pointnav_spaces
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hb200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = hb.load()
+    T, N = CFG["T"], CFG["N"]
+    torch.manual_seed(100 + rank * N)  # habitat.seed=100, ppo_trainer.py:207-215
+    obs_space, act_space = pointnav_spaces(CFG["H"], CFG["W"])
+    policy = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=CFG["hidden"], num_recurrent_layers=CFG["layers"],
+                                     rnn_type="LSTM", resnet_baseplanes=32, backbone="resnet18",
+                                     normalize_visual_inputs=True).to(dev)
+    cls = hb.DDPPO if world > 1 else hb.PPO
+    ppo = cls(policy, clip_param=CFG["clip_param"], ppo_epoch=CFG["ppo_epoch"], num_mini_batch=CFG["num_mini_batch"],
+              value_loss_coef=CFG["value_loss_coef"], entropy_coef=CFG["entropy_coef"], lr=CFG["lr"], eps=CFG["eps"],
+              max_grad_norm=CFG["max_grad_norm"], use_clipped_value_loss=True, use_normalized_advantage=False)
+    if world > 1:
+        ppo.init_distributed(find_unused_params=False)
+    policy.train()
+    st = hb.RolloutStorage(T, N, obs_space, act_space, policy)
+    st.to(dev)
+    next_value = fill_rollout_(st, seed=100 + rank * N)
+
+    def learner_step():
+        st.current_rollout_step_idxs = [T]
+        st.compute_returns(next_value, True, CFG["gamma"], CFG["tau"])
+        return ppo.update(st)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item(), out
+
+    for _ in range(max(args.warmup, 3)):
+        learner_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.hb200_launch_count()
+    ms, metrics = timed(learner_step, args.steps)
+    launches = lib.hb200_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    frames = world * T * N * args.steps
+    value = frames / (ms * 1e-3)
+
+    # ---- e2e: same iteration through the public API with HOST inputs: the rollout's observations
+    # and scalars come from pinned host memory every step, the metrics dict goes back to the host.
+    host = {}
+    h2d = 0
+    for k, v in list(st.buffers["observations"].items()) + [(k, st.buffers[k]) for k in
+                                                             ("rewards", "masks", "actions", "prev_actions",
+                                                              "action_log_probs", "value_preds", "recurrent_hidden_states")]:
+        host[k] = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+        host[k].copy_(v)
+        h2d += v.numel() * v.element_size()
+    nv_host = next_value.cpu().pin_memory()
+    h2d += nv_host.numel() * 4
+
+    def e2e_step():
+        for k in st.buffers["observations"]:
+            st.buffers["observations"][k].copy_(host[k], non_blocking=True)
+        for k in ("rewards", "masks", "actions", "prev_actions", "action_log_probs", "value_preds",
+                  "recurrent_hidden_states"):
+            st.buffers[k].copy_(host[k], non_blocking=True)
+        nv = nv_host.to(dev, non_blocking=True)
+        st.current_rollout_step_idxs = [T]
+        st.compute_returns(nv, True, CFG["gamma"], CFG["tau"])
+        return ppo.update(st)  # returns python floats: one D2H read of the metric vector
+
+    e2e_step()
+    e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e, _ = timed(e2e_step, e2e_steps)
+    e2e_value = world * T * N * e2e_steps / (ms_e2e * 1e-3)
+
+    line = None
+    if rank == 0:
+        peaks = _peaks()
+        roof = kernel_roofline(hb, ops, policy, st, dev, peaks)
+        cores = len(os.sched_getaffinity(0))
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            fps, sample = _cpu_learner_sample(cores, updates=3)
+            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _config(world),
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": 14 * 4, "ms_per_step": ms_e2e / e2e_steps},
+                "roofline": roof, "cpu_baseline": cpu,
+                "conv_tensor_frac_of_step": (world * T * N * CFG["ppo_epoch"] * CONV_TRAIN_GFLOP * 1e-3 * args.steps)
+                / (ms * 1e-3) / (peaks["bf16_sustained"] * world),
+                "learner_metrics": {k: round(float(v), 6) for k, v in metrics.items()}}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def kernel_roofline(hb, ops, policy, st, dev, peaks):
+    """Live CUDA-event timing of the dominant kernel family (the tcgen05 implicit-GEMM convolutions)
+    on the real config-#2 minibatch buffers: algorithmic FLOPs of every conv launch of one
+    minibatch pass (forward + dgrad + wgrad) / the summed launch durations."""
+    eng = policy._engine_()
+    B = CFG["T"] * CFG["N"] // CFG["num_mini_batch"]
+    ws = eng._ws.get((B, True))
+    if ws is None:
+        return None
+    idx = {id(c): i for i, c in enumerate(eng.convs)}
+
+    def t_ms(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    inputs = {id(eng.stem): ws["x0"]}
+    x = ws["x1"]
+    for j, (ca, cb, cd) in enumerate(eng.blocks):
+        inputs[id(ca)] = x
+        inputs[id(cb)] = ws[f"a{j}"]
+        if cd is not None:
+            inputs[id(cd)] = x
+        x = ws[f"o{j}"]
+    inputs[id(eng.comp)] = x
+    per = {"fwd": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
+    detail = []
+    for c in eng.convs:
+        i = idx[id(c)]
+        s = c.shape(B)
+        flop = 2.0 * B * c.out_hw[0] * c.out_hw[1] * c.co * c.ci_real * c.k * c.k
+        xin, y = inputs[id(c)], ws[f"y{i}"]
+        stats = ws[f"st{i}"]
+        tf = t_ms(lambda: ops.conv_fwd(xin, c.wp, y, s, stats, c.groups))
+        tw = t_ms(lambda: ops.conv_wgrad(xin, y, c.dw_acc, s))
+        per["fwd"][0] += flop; per["fwd"][1] += tf
+        per["wgrad"][0] += flop; per["wgrad"][1] += tw
+        td = None
+        if c.wt is not None:
+            dx = ws["g0"][: xin.numel()].view_as(xin)
+            td = t_ms(lambda: ops.conv_dgrad(y, c.wt, dx, s))
+            per["dgrad"][0] += flop; per["dgrad"][1] += td
+        detail.append({"conv": f"{c.ci_real}->{c.co} k{c.k}s{c.stride} @{c.in_hw[0]}", "gflop": flop * 1e-9,
+                       "fwd_ms": tf, "dgrad_ms": td, "wgrad_ms": tw})
+    flops = sum(v[0] for v in per.values())
+    ms = sum(v[1] for v in per.values())
+    achieved = flops / (ms * 1e-3) * 1e-12
+    return {"kernel": "conv_igemm_kernel / conv_wgrad_kernel (tcgen05, all 21 convs of one 4096-frame minibatch pass)",
+            "bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["bf16"], "peak_source": peaks["src"] + " (burst: kernels timed alone)",
+            "traffic": None,
+            "by_pass": {k: {"tflops": (v[0] / (v[1] * 1e-3) * 1e-12) if v[1] else None, "ms": v[1]} for k, v in per.items()},
+            "per_layer": detail}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hb200", choices=["hb200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_hb200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -9,7 +9,31 @@ from ._lib import Hb200Error, load  # noqa: F401
 
 __version__ = "0.1.0"
 
+_LAZY = {
+    "PointNavResNetPolicy": ("rl.resnet_policy", "PointNavResNetPolicy"),
+    "RolloutObservations": ("rl.resnet_policy", "RolloutObservations"),
+    "PPO": ("rl.ppo", "PPO"),
+    "DDPPO": ("rl.ppo", "DDPPO"),
+    "FusedAdam": ("rl.ppo", "FusedAdam"),
+    "RolloutStorage": ("common.rollout_storage", "RolloutStorage"),
+    "TensorDict": ("common.tensor_dict", "TensorDict"),
+    "baseline_registry": ("common.baseline_registry", "baseline_registry"),
+    "spaces": ("common.spaces", None),
+    "ops": ("ops", None),
+}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+
+        mod, attr = _LAZY[name]
+        m = importlib.import_module(f"{__name__}.{mod}")
+        return m if attr is None else getattr(m, attr)
+    raise AttributeError(name)
+
 
 def smoke() -> None:
     from .smoke import run
+
     run()

@@ -55,10 +55,13 @@ SIGNATURES = {
     "hb200_sgemm": ("i", "pll" + "pll" + "pl" + "p" + "iii" + "f" + "ii" + "p"),
     "hb200_bf16_to_f32": ("i", "pplp"),
     "hb200_f32_to_bf16": ("i", "pplp"),
-    "hb200_lstm_step_fwd": ("i", "pppplplppp" + "ii" + "p"),
+    "hb200_lstm_step_fwd": ("i", "ppppplplppp" + "ii" + "p"),
     "hb200_lstm_step_bwd": ("i", "ppppppl" + "ppppp" + "ii" + "p"),
     "hb200_rnn_shift_mask": ("i", "pplpp" + "iii" + "p"),
-    "hb200_colsum": ("i", "pplii" + "p"),
+    "hb200_colsum": ("i", "plplii" + "p"),
+    "hb200_relu_bwd": ("i", "pplll" + "i" + "p"),
+    "hb200_f32_chw_to_bf16_hwc": ("i", "pp" + "iii" + "p"),
+    "hb200_heads_fwd": ("i", "ppppp" + "iii" + "pp" + "p"),
     "hb200_embed_fwd": ("i", "pppppppp" + "iii" + "p"),
     "hb200_embed_bwd": ("i", "ppppp" + "iiii" + "ppp" + "p"),
 }

@@ -206,7 +206,7 @@ __device__ __forceinline__ void load8f(const float* __restrict__ p, float (&f)[8
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-template <bool OUT_F32>
+template <int OUT_F32>  // 0: bf16 NHWC, 1: f32 NHWC, 2: f32 flattened in (c, h, w) order (nn.Flatten of NCHW)
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ out, int B, int hw, int relu) {
   const int cv = p.C >> 3;
@@ -225,10 +225,15 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ o
       float z = fmaf((x[e] - mu[e]) * rs[e], ga[e], be[e]);
       x[e] = relu ? fmaxf(z, 0.f) : z;
     }
-    if (OUT_F32) {
+    if (OUT_F32 == 1) {
       float4* o = reinterpret_cast<float4*>(out) + 2 * i;
       o[0] = make_float4(x[0], x[1], x[2], x[3]);
       o[1] = make_float4(x[4], x[5], x[6], x[7]);
+    } else if (OUT_F32 == 2) {
+      const int pix = (int)((i / cv) % hw);
+      float* o = reinterpret_cast<float*>(out) + (size_t)b * p.C * hw;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[(size_t)(c0 + e) * hw + pix] = x[e];
     } else {
       reinterpret_cast<uint4*>(out)[i] = pack8(x);
     }
@@ -486,7 +491,7 @@ __global__ void embed_fwd_kernel(const float* __restrict__ goal, const int64_t* 
       const float r = goal[row * 2], th = goal[row * 2 + 1];
       v = b_tgt[j] + w_tgt[j * 3] * r + w_tgt[j * 3 + 1] * cosf(-th) + w_tgt[j * 3 + 2] * sinf(-th);
     } else {
-      const int idx = masks[row] ? (int)prev_actions[row] + 1 : 0;
+      const int idx = masks[f] ? (int)prev_actions[f] + 1 : 0;
       v = emb[idx * 32 + (j - 32)];
     }
     out[(size_t)f * ld + col0 + j] = v;
@@ -514,7 +519,7 @@ __global__ void embed_bwd_kernel(const float* __restrict__ goal, const int64_t* 
       atomicAdd(&acc[j * 3 + 2], d * sinf(-th));
       atomicAdd(&acc[96 + j], d);
     } else {
-      const int idx = masks[row] ? (int)prev_actions[row] + 1 : 0;
+      const int idx = masks[f] ? (int)prev_actions[f] + 1 : 0;
       atomicAdd(&acc[128 + idx * 32 + (j - 32)], d);
     }
   }
@@ -543,20 +548,68 @@ __global__ void rnn_shift_mask_kernel(const float* __restrict__ h_seq, const flo
     h_in[i] = masks[tn] ? prev : 0.f;
   }
 }
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int N,
-                              int accumulate) {
+__global__ void colsum_kernel(const float* __restrict__ x, long long ld, float* __restrict__ out,
+                              long long M, int N, int accumulate) {
   // block handles 32 columns; threads (32 x 8) stride rows
   __shared__ float red[8][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31), ry = threadIdx.x >> 5;
   float acc = 0.f;
   if (col < N)
-    for (long long r = ry; r < M; r += 8) acc += x[r * N + col];
+    for (long long r = ry; r < M; r += 8) acc += x[r * ld + col];
   red[ry][threadIdx.x & 31] = acc;
   __syncthreads();
   if (ry == 0 && col < N) {
     float s = 0.f;
     for (int q = 0; q < 8; ++q) s += red[q][threadIdx.x & 31];
     out[col] = accumulate ? out[col] + s : s;
+  }
+}
+
+// d[r, c] *= (y[r, c] > 0) for c < cols (ReLU backward on a column block of a wider matrix)
+__global__ void relu_bwd_kernel(float* __restrict__ d, const float* __restrict__ y, long long ld_d,
+                                long long ld_y, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    if (!(y[r * ld_y + c] > 0.f)) d[r * ld_d + c] = 0.f;
+  }
+}
+// x f32 [B, C*hw] in (c, h, w) order  ->  bf16 NHWC [B, hw, C]
+__global__ void f32_chw_to_bf16_hwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                           int B, int hw, int C) {
+  const int cv = C >> 3;
+  const long long total = (long long)B * hw * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) << 3;
+    const long long t = i / cv;
+    const int p = (int)(t % hw);
+    const int b = (int)(t / hw);
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = x[((size_t)b * C + c0 + e) * hw + p];
+    reinterpret_cast<uint4*>(out)[i] = pack8(f);
+  }
+}
+// logits/value heads only (actor path): logits [B,A], values [B]
+__global__ void heads_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ w_act,
+                                 const float* __restrict__ b_act, const float* __restrict__ w_val,
+                                 const float* __restrict__ b_val, int B, int H, int A,
+                                 float* __restrict__ logits, float* __restrict__ values) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= B) return;
+  for (int a = 0; a <= A; ++a) {
+    const float* w = (a < A) ? w_act + (size_t)a * H : w_val;
+    float acc = 0.f;
+    for (int k = lane; k < H; k += 32) acc = fmaf(feat[(size_t)f * H + k], w[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (a < A) logits[(size_t)f * A + a] = acc + b_act[a];
+      else values[f] = acc + b_val[0];
+    }
   }
 }
 
@@ -651,10 +704,12 @@ extern "C" int hb200_gn_apply(const hb200_bf16* y, const float* stats, const flo
   if (rc) return rc;
   HB_CHECK_ARG(y && out, "gn_apply: null pointer");
   const long long total = (long long)batch * hw * (channels / 8);
-  if (out_f32)
-    gn_apply_kernel<true><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
+  if (out_f32 == 1)
+    gn_apply_kernel<1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
+  else if (out_f32 == 2)
+    gn_apply_kernel<2><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
   else
-    gn_apply_kernel<false><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
+    gn_apply_kernel<0><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -808,10 +863,38 @@ extern "C" int hb200_rnn_shift_mask(const float* h_seq, const float* h0, long lo
   count_launch(1);
   return HB200_OK;
 }
-extern "C" int hb200_colsum(const float* x, float* out, long long m, int n, int accumulate,
+extern "C" int hb200_colsum(const float* x, long long ld, float* out, long long m, int n, int accumulate,
                             hb200_stream_t stream) {
-  HB_CHECK_ARG(x && out && m > 0 && n > 0, "colsum: bad args");
-  colsum_kernel<<<(n + 31) / 32, 256, 0, (cudaStream_t)stream>>>(x, out, m, n, accumulate);
+  HB_CHECK_ARG(x && out && m > 0 && n > 0 && ld >= n, "colsum: bad args");
+  colsum_kernel<<<(n + 31) / 32, 256, 0, (cudaStream_t)stream>>>(x, ld, out, m, n, accumulate);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_relu_bwd(float* d, const float* y, long long ld_d, long long ld_y, long long rows,
+                              int cols, hb200_stream_t stream) {
+  HB_CHECK_ARG(d && y && rows > 0 && cols > 0, "relu_bwd: bad args");
+  relu_bwd_kernel<<<grid_for(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(d, y, ld_d, ld_y, rows, cols);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+extern "C" int hb200_f32_chw_to_bf16_hwc(const float* x, hb200_bf16* out, int batch, int hw, int channels,
+                                         hb200_stream_t stream) {
+  HB_CHECK_ARG(x && out && batch > 0 && hw > 0 && channels % 8 == 0, "f32_chw_to_bf16_hwc: bad args");
+  const long long total = (long long)batch * hw * (channels / 8);
+  f32_chw_to_bf16_hwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, batch, hw, channels);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+extern "C" int hb200_heads_fwd(const float* features, const float* w_act, const float* b_act,
+                               const float* w_val, const float* b_val, int batch, int hidden, int n_actions,
+                               float* logits, float* values, hb200_stream_t stream) {
+  HB_CHECK_ARG(features && w_act && b_act && w_val && b_val && logits && values && batch > 0, "heads_fwd: bad args");
+  heads_fwd_kernel<<<cdiv(batch, 8), 256, 0, (cudaStream_t)stream>>>(features, w_act, b_act, w_val, b_val, batch,
+                                                                      hidden, n_actions, logits, values);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;

@@ -18,7 +18,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 template <int NJ>  // H = 32 * NJ
 __global__ void __launch_bounds__(256)
 lstm_step_fwd_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh,
-                     const uint8_t* __restrict__ masks, const float* __restrict__ h_prev,
+                     const float* __restrict__ b_hh, const uint8_t* __restrict__ masks, const float* __restrict__ h_prev,
                      long long hp_stride, const float* __restrict__ c_prev, long long cp_stride,
                      float* __restrict__ h, float* __restrict__ c, float* __restrict__ gates_out, int n) {
   constexpr int H = NJ * 32;
@@ -52,6 +52,7 @@ lstm_step_fwd_kernel(const float* __restrict__ xproj, const float* __restrict__ 
     if (lane < kUnits) {
       const int col = u0 + lane;
       const float* xp = xproj + (size_t)s * 4 * H;
+      if (b_hh) { gi += b_hh[col]; gf += b_hh[H + col]; gg += b_hh[2 * H + col]; go += b_hh[3 * H + col]; }
       const float i_ = sigmoidf_(gi + xp[col]);
       const float f_ = sigmoidf_(gf + xp[H + col]);
       const float g_ = tanhf(gg + xp[2 * H + col]);
@@ -131,7 +132,7 @@ lstm_step_bwd_matmul_kernel(const float* __restrict__ dgates, const float* __res
 
 using namespace hb200;
 
-extern "C" int hb200_lstm_step_fwd(const float* xproj, const float* w_hh, const uint8_t* masks,
+extern "C" int hb200_lstm_step_fwd(const float* xproj, const float* w_hh, const float* b_hh, const uint8_t* masks,
                                    const float* h_prev, long long h_prev_stride, const float* c_prev,
                                    long long c_prev_stride, float* h, float* c, float* gates_out, int n,
                                    int hidden, hb200_stream_t stream) {
@@ -145,7 +146,7 @@ extern "C" int hb200_lstm_step_fwd(const float* xproj, const float* w_hh, const 
   {                                                                                                       \
     auto kern = lstm_step_fwd_kernel<NJ>;                                                                 \
     if (smem > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, 256, smem, st>>>(xproj, w_hh, masks, h_prev, h_prev_stride, c_prev, c_prev_stride, h, c,  \
+    kern<<<grid, 256, smem, st>>>(xproj, w_hh, b_hh, masks, h_prev, h_prev_stride, c_prev, c_prev_stride, h, c,  \
                                   gates_out, n);                                                          \
   }
   switch (hidden / 32) {

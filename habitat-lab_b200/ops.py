@@ -147,9 +147,10 @@ def umma_gemm_probe(a, b, d, m, n, k, layout):
 
 
 # ---- GroupNorm & friends -----------------------------------------------------------------------------
-def gn_apply(y, stats, gamma, beta, out, batch, hw, channels, groups, relu, eps=1e-5):
-    call("hb200_gn_apply", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(out),
-         int(out.dtype == torch.float32), batch, hw, channels, groups, float(eps), int(bool(relu)))
+def gn_apply(y, stats, gamma, beta, out, batch, hw, channels, groups, relu, eps=1e-5, chw_flat=False):
+    mode = 0 if out.dtype != torch.float32 else (2 if chw_flat else 1)
+    call("hb200_gn_apply", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(out), mode, batch, hw, channels, groups,
+         float(eps), int(bool(relu)))
 
 
 def gn_residual_relu(y, stats, gamma, beta, res, out, batch, hw, channels, groups, res_stats=None,
@@ -216,8 +217,8 @@ def f32_to_bf16(x, out):
     call("hb200_f32_to_bf16", ptr(x), ptr(out), x.numel())
 
 
-def lstm_step_fwd(xproj, w_hh, masks, h_prev, c_prev, h, c, gates_out, n, hidden):
-    call("hb200_lstm_step_fwd", ptr(xproj), ptr(w_hh), ptr(masks), ptr(h_prev), h_prev.stride(0), ptr(c_prev),
+def lstm_step_fwd(xproj, w_hh, masks, h_prev, c_prev, h, c, gates_out, n, hidden, b_hh=None):
+    call("hb200_lstm_step_fwd", ptr(xproj), ptr(w_hh), ptr(b_hh), ptr(masks), ptr(h_prev), h_prev.stride(0), ptr(c_prev),
          c_prev.stride(0), ptr(h), ptr(c), ptr(gates_out), n, hidden)
 
 
@@ -230,9 +231,24 @@ def rnn_shift_mask(h_seq, h0, masks, h_in, T, n, hidden):
     call("hb200_rnn_shift_mask", ptr(h_seq), ptr(h0), h0.stride(0), ptr(masks), ptr(h_in), T, n, hidden)
 
 
-def colsum(x, out, accumulate=False):
-    M, N = x.shape
-    call("hb200_colsum", ptr(x), ptr(out), M, N, int(bool(accumulate)))
+def colsum(x, out, accumulate=False, n_cols=None):
+    M = x.shape[0]
+    N = x.shape[1] if n_cols is None else n_cols
+    call("hb200_colsum", ptr(x), x.stride(0), ptr(out), M, N, int(bool(accumulate)))
+
+
+def relu_bwd(d, y, cols):
+    call("hb200_relu_bwd", ptr(d), ptr(y), d.stride(0), y.stride(0), d.shape[0], cols)
+
+
+def f32_chw_to_bf16_hwc(x, out, batch, hw, channels):
+    call("hb200_f32_chw_to_bf16_hwc", ptr(x), ptr(out), batch, hw, channels)
+
+
+def heads_fwd(features, w_act, b_act, w_val, b_val, logits, values):
+    B, H = features.shape
+    call("hb200_heads_fwd", ptr(features), ptr(w_act), ptr(b_act), ptr(w_val), ptr(b_val), B, H, w_act.shape[0],
+         ptr(logits), ptr(values))
 
 
 def embed_fwd(goal, prev_actions, masks, frame_rows, w_tgt, b_tgt, emb, out, col0):

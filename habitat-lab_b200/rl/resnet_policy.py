@@ -1,0 +1,757 @@
+"""PointNavResNetPolicy on the hb200 kernels.
+
+Mirrors the reference policy's interface and checkpoint layout
+(habitat-baselines/habitat_baselines/rl/ddppo/policy/resnet_policy.py:50-162, 165-276, 394-767;
+rl/ppo/policy.py:252-424): `from_config`, `act`, `get_value`, `evaluate_actions`, the properties the
+trainer / agent-access-manager read, and a state_dict with the reference's exact key names and
+shapes (the torch.nn modules below are parameter holders + initialisers only; their forward is
+never called).  All arithmetic runs in libhb200.so:
+
+  forward  : prep (u8/f32 rollout rows -> pooled, normalised bf16 NHWC) -> tcgen05 conv stack with
+             GroupNorm statistics fused in the epilogue -> fp32 linears / masked LSTM -> heads
+  backward : hand-written, layer by layer, into one flat fp32 gradient buffer (no autograd)
+
+There is no CPU / PyTorch fallback: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import Hb200Error
+from ..common import spaces
+from ..common.baseline_registry import baseline_registry
+
+BF16 = torch.bfloat16
+POINTGOAL_UUID = "pointgoal_with_gps_compass"  # IntegratedPointGoalGPSAndCompassSensor.cls_uuid
+IMAGEGOAL_UUID = "imagegoal"
+
+
+@dataclass
+class PolicyActionData:
+    """Subset of rl/ppo/policy.py:47-96 used by the trainer's rollout loop."""
+    rnn_hidden_states: Optional[torch.Tensor] = None
+    actions: Optional[torch.Tensor] = None
+    values: Optional[torch.Tensor] = None
+    action_log_probs: Optional[torch.Tensor] = None
+    take_actions: Optional[torch.Tensor] = None
+    policy_info: Optional[list] = None
+    should_inserts: Optional[torch.Tensor] = None
+
+    @property
+    def env_actions(self):
+        return self.actions if self.take_actions is None else self.take_actions
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter holders (same module tree / names as the reference)
+# ---------------------------------------------------------------------------------------------
+class RunningMeanAndVar(nn.Module):
+    def __init__(self, n_channels: int):
+        super().__init__()
+        self.register_buffer("_mean", torch.zeros(1, n_channels, 1, 1))
+        self.register_buffer("_var", torch.zeros(1, n_channels, 1, 1))
+        self.register_buffer("_count", torch.zeros(()))
+
+
+class _BasicBlock(nn.Module):
+    def __init__(self, inplanes, planes, ngroups, stride=1, downsample=None):
+        super().__init__()
+        self.convs = nn.Sequential(
+            nn.Conv2d(inplanes, planes, 3, stride, 1, bias=False), nn.GroupNorm(ngroups, planes), nn.ReLU(True),
+            nn.Conv2d(planes, planes, 3, 1, 1, bias=False), nn.GroupNorm(ngroups, planes))
+        self.downsample = downsample
+        self.stride = stride
+
+
+class _ResNet18(nn.Module):
+    def __init__(self, in_channels, base_planes, ngroups):
+        super().__init__()
+        self.conv1 = nn.Sequential(nn.Conv2d(in_channels, base_planes, 7, 2, 3, bias=False),
+                                   nn.GroupNorm(ngroups, base_planes), nn.ReLU(True))
+        inplanes = base_planes
+        for li, mult in enumerate((1, 2, 4, 8), start=1):
+            planes, stride = base_planes * mult, (1 if li == 1 else 2)
+            blocks = []
+            for b in range(2):
+                ds = None
+                s = stride if b == 0 else 1
+                if b == 0 and (s != 1 or inplanes != planes):
+                    ds = nn.Sequential(nn.Conv2d(inplanes, planes, 1, s, bias=False), nn.GroupNorm(ngroups, planes))
+                blocks.append(_BasicBlock(inplanes, planes, ngroups, s, ds))
+                inplanes = planes
+            setattr(self, f"layer{li}", nn.Sequential(*blocks))
+        self.final_channels = inplanes
+        self.final_spatial_compress = 1.0 / 32
+
+
+class ResNetEncoder(nn.Module):
+    def __init__(self, observation_space, baseplanes=32, ngroups=16, normalize_visual_inputs=False,
+                 backbone="resnet18"):
+        super().__init__()
+        self.visual_keys = [k for k, v in observation_space.spaces.items()
+                            if len(v.shape) > 1 and k != IMAGEGOAL_UUID]
+        self.key_needs_rescaling = {k: None for k in self.visual_keys}
+        for k, v in observation_space.spaces.items():
+            if v.dtype == np.uint8:
+                self.key_needs_rescaling[k] = 1.0 / float(np.max(v.high))
+        self._n_input_channels = sum(observation_space.spaces[k].shape[2] for k in self.visual_keys)
+        self.running_mean_and_var = (RunningMeanAndVar(self._n_input_channels)
+                                     if normalize_visual_inputs else nn.Sequential())
+        self.ngroups = ngroups
+        if not self.is_blind:
+            if backbone != "resnet18":
+                raise NotImplementedError(f"backbone {backbone!r}: only resnet18 has sm_100a kernels so far "
+                                          "(resnet50 / resneXt50 are 'next' rows, SURVEY.md section 8f)")
+            h, w = observation_space.spaces[self.visual_keys[0]].shape[:2]
+            self.in_hw = (h, w)
+            self.backbone = _ResNet18(self._n_input_channels, baseplanes, ngroups)
+            fh = int(np.ceil((h // 2) * self.backbone.final_spatial_compress))
+            fw = int(np.ceil((w // 2) * self.backbone.final_spatial_compress))
+            ncomp = int(round(2048 / (fh * fw)))
+            self.compression = nn.Sequential(nn.Conv2d(self.backbone.final_channels, ncomp, 3, padding=1, bias=False),
+                                             nn.GroupNorm(1, ncomp), nn.ReLU(True))
+            self.output_shape = (ncomp, fh, fw)
+
+    @property
+    def is_blind(self):
+        return self._n_input_channels == 0
+
+
+class _LSTMStateEncoder(nn.Module):
+    def __init__(self, input_size, hidden_size, num_layers):
+        super().__init__()
+        self.num_recurrent_layers = num_layers * 2
+        self.rnn = nn.LSTM(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
+        for name, p in self.rnn.named_parameters():  # rnn_state_encoder.py:288-293
+            if "weight" in name:
+                nn.init.orthogonal_(p)
+            elif "bias" in name:
+                nn.init.constant_(p, 0)
+
+
+class PointNavResNetNet(nn.Module):
+    def __init__(self, observation_space, action_space, hidden_size, num_recurrent_layers, rnn_type, backbone,
+                 resnet_baseplanes, normalize_visual_inputs):
+        super().__init__()
+        self.prev_action_embedding = nn.Embedding(action_space.n + 1, 32)
+        rnn_input_size = 32
+        if POINTGOAL_UUID not in observation_space.spaces:
+            raise NotImplementedError("hb200 policy needs the pointgoal_with_gps_compass sensor (PointNav); "
+                                      "other goal sensors are 'next' rows")
+        n_goal = observation_space.spaces[POINTGOAL_UUID].shape[0]
+        if n_goal != 2:
+            raise NotImplementedError("only the 2-D polar pointgoal is implemented")
+        self.tgt_embeding = nn.Linear(n_goal + 1, 32)  # sic: the reference's spelling
+        rnn_input_size += 32
+        self._hidden_size = hidden_size
+        self.visual_encoder = ResNetEncoder(observation_space, baseplanes=resnet_baseplanes,
+                                            ngroups=resnet_baseplanes // 2,
+                                            normalize_visual_inputs=normalize_visual_inputs, backbone=backbone)
+        if self.visual_encoder.is_blind:
+            raise NotImplementedError("blind policies are not implemented")
+        self.visual_fc = nn.Sequential(nn.Flatten(), nn.Linear(int(np.prod(self.visual_encoder.output_shape)),
+                                                               hidden_size), nn.ReLU(True))
+        if rnn_type.lower() != "lstm":
+            raise NotImplementedError("rnn_type GRU is a 'next' row (config #3); LSTM is implemented")
+        self.state_encoder = _LSTMStateEncoder(hidden_size + rnn_input_size, hidden_size, num_recurrent_layers)
+        self.train()
+
+    @property
+    def output_size(self):
+        return self._hidden_size
+
+    @property
+    def is_blind(self):
+        return False
+
+    @property
+    def num_recurrent_layers(self):
+        return self.state_encoder.num_recurrent_layers
+
+    @property
+    def recurrent_hidden_size(self):
+        return self._hidden_size
+
+    @property
+    def perception_embedding_size(self):
+        return self._hidden_size
+
+
+class CategoricalNet(nn.Module):
+    def __init__(self, num_inputs, num_outputs):
+        super().__init__()
+        self.linear = nn.Linear(num_inputs, num_outputs)
+        nn.init.orthogonal_(self.linear.weight, gain=0.01)
+        nn.init.constant_(self.linear.bias, 0)
+
+
+class CriticHead(nn.Module):
+    def __init__(self, input_size):
+        super().__init__()
+        self.fc = nn.Linear(input_size, 1)
+        nn.init.orthogonal_(self.fc.weight)
+        nn.init.constant_(self.fc.bias, 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# observation handle: lets the updater hand the policy the rollout buffers IN PLACE
+# ---------------------------------------------------------------------------------------------
+class RolloutObservations(dict):
+    """dict of full rollout tensors [(T+1)*N, ...] plus `frame_rows` (int32 [B]): the buffer row
+    of each minibatch frame.  Replaces the advanced-index gather copy of data_generator
+    (common/rollout_storage.py:236-246), 1.9 GB per minibatch at config #2."""
+
+    def __init__(self, tensors: Dict[str, torch.Tensor], frame_rows: torch.Tensor):
+        super().__init__(tensors)
+        self.frame_rows = frame_rows
+
+
+def _as_rows(observations, device):
+    if isinstance(observations, RolloutObservations):
+        return observations, observations.frame_rows
+    any_t = next(iter(observations.values()))
+    rows = torch.arange(any_t.shape[0], dtype=torch.int32, device=device)
+    return observations, rows
+
+
+# ---------------------------------------------------------------------------------------------
+# conv stack engine
+# ---------------------------------------------------------------------------------------------
+class _Conv:
+    def __init__(self, conv: nn.Conv2d, gn: nn.GroupNorm, in_hw, ci_pad=None):
+        self.w, self.gamma, self.beta = conv.weight, gn.weight, gn.bias
+        self.groups = gn.num_groups
+        self.co, self.ci_real, self.k, _ = conv.weight.shape
+        self.ci = ci_pad or self.ci_real
+        self.stride, self.pad = conv.stride[0], conv.padding[0]
+        self.in_hw = in_hw
+        self.out_hw = tuple((d + 2 * self.pad - self.k) // self.stride + 1 for d in in_hw)
+        self.wp = self.wt = self.dw_acc = None
+
+    def alloc_weights(self, dev, need_dgrad):
+        self.wp = torch.empty(ops.packed_weight_elems(self.co, self.ci, self.k, self.k), dtype=BF16, device=dev)
+        self.wt = (torch.empty(ops.packed_weight_elems(self.ci, self.co, self.k, self.k), dtype=BF16, device=dev)
+                   if need_dgrad else None)
+        self.dw_acc = torch.empty(self.k * self.k * self.ci, self.co, device=dev)
+
+    def shape(self, B):
+        return ops.conv_shape(B, self.in_hw[0], self.in_hw[1], self.ci, self.co, self.k, self.k, self.stride, self.pad)
+
+
+class EncoderEngine:
+    """ResNet18 (BasicBlock) + compression forward/backward on NHWC bf16 activations."""
+
+    def __init__(self, enc: ResNetEncoder):
+        self.enc = enc
+        h, w = enc.in_hw
+        if h % 64 or w % 64:
+            raise NotImplementedError(f"visual input {h}x{w}: the sm_100a conv stack needs H, W multiples of 64")
+        self.hp, self.wp_ = h // 2, w // 2
+        bb = enc.backbone
+        self.stem = _Conv(bb.conv1[0], bb.conv1[1], (self.hp, self.wp_), ci_pad=8)
+        hw = tuple(d // 2 for d in self.stem.out_hw)  # maxpool 3x3 s2 p1
+        self.pool_hw = hw
+        self.blocks = []
+        for li in (1, 2, 3, 4):
+            for blk in getattr(bb, f"layer{li}"):
+                ca = _Conv(blk.convs[0], blk.convs[1], hw)
+                cb = _Conv(blk.convs[3], blk.convs[4], ca.out_hw)
+                cd = _Conv(blk.downsample[0], blk.downsample[1], hw) if blk.downsample is not None else None
+                self.blocks.append((ca, cb, cd))
+                hw = ca.out_hw
+        self.comp = _Conv(enc.compression[0], enc.compression[1], hw)
+        assert self.comp.out_hw == tuple(enc.output_shape[1:]), (self.comp.out_hw, enc.output_shape)
+        self.convs: List[_Conv] = [self.stem] + [c for blk in self.blocks for c in blk if c is not None] + [self.comp]
+        self._ws = {}
+        self._dev = None
+
+    # ---- buffers -----------------------------------------------------------------------------
+    def _ensure(self, B, dev, train):
+        if self._dev != dev:
+            for c in self.convs:
+                c.alloc_weights(dev, need_dgrad=c is not self.stem)
+            self._dev, self._ws = dev, {}
+        key = (B, train)
+        if key in self._ws:
+            return self._ws[key]
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
+        ws = {"x0": e(B, self.hp, self.wp_, 8)}
+        for i, c in enumerate(self.convs):
+            ws[f"y{i}"] = e(B, *c.out_hw, c.co)
+            ws[f"st{i}"] = torch.empty(B, c.groups, 2, device=dev)
+            if train:
+                ws[f"sums{i}"] = torch.empty(B, c.groups, 2, device=dev)
+        ws["x1"] = e(B, *self.pool_hw, self.stem.co)
+        ws["argmax"] = torch.empty(B, *self.pool_hw, self.stem.co, dtype=torch.uint8, device=dev)
+        for j, (ca, cb, cd) in enumerate(self.blocks):
+            ws[f"a{j}"] = e(B, *ca.out_hw, ca.co)
+            ws[f"o{j}"] = e(B, *cb.out_hw, cb.co)
+        ncomp, fh, fw = self.enc.output_shape
+        ws["feat"] = torch.empty(B, ncomp * fh * fw, device=dev)
+        if train:
+            big = max(int(np.prod(c.out_hw)) * c.co for c in self.convs)
+            for nm in ("g0", "g1", "dy", "gz"):
+                ws[nm] = torch.empty(B * big, dtype=BF16, device=dev)
+        self._ws[key] = ws
+        return ws
+
+    def pack_weights(self):
+        for c in self.convs:
+            ops.pack_conv_weight_into(c.w.data, c.wp, c.wt, c.ci)
+
+    # ---- forward -----------------------------------------------------------------------------
+    def forward(self, x0_writer, B, dev, train):
+        """x0_writer(x0) fills the pooled/normalised input.  Returns feat f32 [B, C*h*w] in the
+        reference's (c,h,w) flatten order."""
+        ws = self._ensure(B, dev, train)
+        self.pack_weights()
+        x0_writer(ws["x0"])
+        idx = {id(c): i for i, c in enumerate(self.convs)}
+
+        def conv(c, x):
+            i = idx[id(c)]
+            ws[f"st{i}"].zero_()
+            ops.conv_fwd(x, c.wp, ws[f"y{i}"], c.shape(B), ws[f"st{i}"], c.groups)
+            return ws[f"y{i}"], ws[f"st{i}"]
+
+        y, st = conv(self.stem, ws["x0"])
+        sh, sw = self.stem.out_hw
+        ops.gn_relu_maxpool(y, st, self.stem.gamma, self.stem.beta, ws["x1"], ws["argmax"], B, sh, sw,
+                            self.stem.co, self.stem.groups)
+        x = ws["x1"]
+        for j, (ca, cb, cd) in enumerate(self.blocks):
+            ya, sa = conv(ca, x)
+            hw = ca.out_hw[0] * ca.out_hw[1]
+            ops.gn_apply(ya, sa, ca.gamma, ca.beta, ws[f"a{j}"], B, hw, ca.co, ca.groups, relu=True)
+            yb, sb = conv(cb, ws[f"a{j}"])
+            if cd is not None:
+                yd, sd = conv(cd, x)
+                ops.gn_residual_relu(yb, sb, cb.gamma, cb.beta, yd, ws[f"o{j}"], B, hw, cb.co, cb.groups, sd,
+                                     cd.gamma, cd.beta)
+            else:
+                ops.gn_residual_relu(yb, sb, cb.gamma, cb.beta, x, ws[f"o{j}"], B, hw, cb.co, cb.groups)
+            x = ws[f"o{j}"]
+        yc, sc = conv(self.comp, x)
+        fhw = self.comp.out_hw[0] * self.comp.out_hw[1]
+        ops.gn_apply(yc, sc, self.comp.gamma, self.comp.beta, ws["feat"], B, fhw, self.comp.co, self.comp.groups,
+                     relu=True, chw_flat=True)
+        return ws["feat"]
+
+    # ---- backward ----------------------------------------------------------------------------
+    def backward(self, d_feat, B, dev):
+        """d_feat f32 [B, C*h*w] (c,h,w order): gradient wrt the compression output (after ReLU).
+        Writes every conv / GroupNorm parameter gradient into the parameters' .grad views."""
+        ws = self._ws[(B, True)]
+        idx = {id(c): i for i, c in enumerate(self.convs)}
+        Y = lambda c: ws[f"y{idx[id(c)]}"]  # noqa: E731
+        ST = lambda c: ws[f"st{idx[id(c)]}"]  # noqa: E731
+
+        def view(buf, c_or_shape):
+            shp = (B, *c_or_shape.out_hw, c_or_shape.co) if isinstance(c_or_shape, _Conv) else c_or_shape
+            n = int(np.prod(shp))
+            return buf[:n].view(*shp)
+
+        def gn_bwd(c, g, act, mode, want_gz):
+            hw = c.out_hw[0] * c.out_hw[1]
+            sums = ws[f"sums{idx[id(c)]}"]
+            dy = view(ws["dy"], c)
+            gz = view(ws["gz"], c) if want_gz else None
+            ops.gn_bwd_reduce(g, act, Y(c), ST(c), c.gamma, c.beta, sums, c.gamma.grad, c.beta.grad, B, hw, c.co,
+                              c.groups, mode)
+            ops.gn_bwd_apply(g, act, Y(c), ST(c), c.gamma, c.beta, sums, dy, gz, B, hw, c.co, c.groups, mode)
+            return dy, gz
+
+        def wgrad(c, x, dy):
+            c.dw_acc.zero_()
+            ops.conv_wgrad(x, dy, c.dw_acc, c.shape(B))
+            ops.unpack_conv_wgrad(c.dw_acc, c.w.grad, c.ci)
+
+        g_bufs = [ws["g0"], ws["g1"]]
+        cur = 0
+        # compression: relu(GN(yc)) -> visual_fc
+        comp = self.comp
+        fhw = comp.out_hw[0] * comp.out_hw[1]
+        g = view(g_bufs[cur], comp)
+        ops.f32_chw_to_bf16_hwc(d_feat, g, B, fhw, comp.co)
+        dy, _ = gn_bwd(comp, g, None, 1, False)
+        x_last = ws[f"o{len(self.blocks) - 1}"]
+        wgrad(comp, x_last, dy)
+        cur ^= 1
+        g = g_bufs[cur][: x_last.numel()].view_as(x_last)
+        ops.conv_dgrad(dy, comp.wt, g, comp.shape(B))
+        # residual blocks, last to first
+        for j in reversed(range(len(self.blocks))):
+            ca, cb, cd = self.blocks[j]
+            xin = ws[f"o{j - 1}"] if j > 0 else ws["x1"]
+            out = ws[f"o{j}"]
+            dyb, gz = gn_bwd(cb, g, out, 2, True)                 # g: grad wrt block output
+            wgrad(cb, ws[f"a{j}"], dyb)
+            cur ^= 1
+            ga = g_bufs[cur][: ws[f"a{j}"].numel()].view_as(ws[f"a{j}"])
+            ops.conv_dgrad(dyb, cb.wt, ga, cb.shape(B))           # grad wrt a = relu(GN(ya))
+            gz_keep = gz  # ws["gz"] is only rewritten by the next block's GN_b backward
+            dya, _ = gn_bwd(ca, ga, None, 1, False)
+            wgrad(ca, xin, dya)
+            gx = g_bufs[cur][: xin.numel()].view_as(xin)          # ga is consumed; reuse its buffer
+            if cd is not None:
+                ops.conv_dgrad(dya, ca.wt, gx, ca.shape(B))
+                dyd, _ = gn_bwd(cd, gz_keep, None, 0, False)
+                wgrad(cd, xin, dyd)
+                ops.conv_dgrad(dyd, cd.wt, gx, cd.shape(B), addend=gx)
+            else:
+                ops.conv_dgrad(dya, ca.wt, gx, ca.shape(B), addend=gz_keep)
+            g = gx
+        # stem: maxpool -> relu(GN(y0)) -> conv1 (input needs no gradient)
+        stem = self.stem
+        sh, sw = stem.out_hw
+        cur ^= 1
+        gzs = g_bufs[cur][: Y(stem).numel()].view_as(Y(stem))
+        ops.maxpool_bwd(g, ws["argmax"], gzs, B, sh, sw, stem.co)
+        dy0, _ = gn_bwd(stem, gzs, None, 1, False)
+        wgrad(stem, ws["x0"], dy0)
+
+
+# ---------------------------------------------------------------------------------------------
+# the policy
+# ---------------------------------------------------------------------------------------------
+@baseline_registry.register_policy
+class PointNavResNetPolicy(nn.Module):
+    def __init__(self, observation_space, action_space, hidden_size: int = 512, num_recurrent_layers: int = 1,
+                 rnn_type: str = "GRU", resnet_baseplanes: int = 32, backbone: str = "resnet18",
+                 normalize_visual_inputs: bool = False, force_blind_policy: bool = False, policy_config=None,
+                 aux_loss_config=None, fuse_keys=None, **kwargs):
+        super().__init__()
+        if force_blind_policy:
+            raise NotImplementedError("force_blind_policy is not implemented")
+        if policy_config is not None and getattr(policy_config, "action_distribution_type", "categorical") != "categorical":
+            raise NotImplementedError("only categorical action distributions are implemented")
+        self.action_distribution_type = "categorical"
+        self._action_space = action_space
+        self.net = PointNavResNetNet(observation_space, action_space, hidden_size, num_recurrent_layers, rnn_type,
+                                     backbone, resnet_baseplanes, normalize_visual_inputs)
+        self.dim_actions = action_space.n
+        self.action_distribution = CategoricalNet(self.net.output_size, self.dim_actions)
+        self.critic = CriticHead(self.net.output_size)
+        self.aux_loss_modules = nn.ModuleDict()
+        self.observation_space = observation_space
+        self._engine: Optional[EncoderEngine] = None
+        self._flat = None
+        self._buf = {}
+        self.world_size = 1  # set by the distributed updater
+        self.dist_group = None
+
+    # ---- reference API surface ----------------------------------------------------------------
+    @classmethod
+    def from_config(cls, config, observation_space, action_space, **kwargs):
+        hb = config.habitat_baselines
+        ignore = []
+        try:
+            ignore = [s.uuid for s in hb.eval.extra_sim_sensors.values()]
+        except Exception:
+            pass
+        filtered = spaces.Dict(OrderedDict((k, v) for k, v in observation_space.spaces.items() if k not in ignore))
+        agent_name = kwargs.get("agent_name")
+        policy_cfg = None
+        try:
+            if agent_name is None:
+                agent_name = config.habitat.simulator.agents_order[0]
+            policy_cfg = hb.rl.policy[agent_name]
+        except Exception:
+            pass
+        return cls(observation_space=filtered, action_space=action_space, hidden_size=hb.rl.ppo.hidden_size,
+                   rnn_type=hb.rl.ddppo.rnn_type, num_recurrent_layers=hb.rl.ddppo.num_recurrent_layers,
+                   backbone=hb.rl.ddppo.backbone, normalize_visual_inputs="rgb" in observation_space.spaces,
+                   force_blind_policy=getattr(hb, "force_blind_policy", False), policy_config=policy_cfg)
+
+    @property
+    def should_load_agent_state(self):
+        return True
+
+    @property
+    def num_recurrent_layers(self) -> int:
+        return self.net.num_recurrent_layers
+
+    @property
+    def recurrent_hidden_size(self) -> int:
+        return self.net.recurrent_hidden_size
+
+    @property
+    def hidden_state_shape(self):
+        return (self.num_recurrent_layers, self.recurrent_hidden_size)
+
+    @property
+    def visual_encoder(self):
+        return self.net.visual_encoder
+
+    @property
+    def policy_action_space(self):
+        return self._action_space
+
+    def _get_policy_components(self):
+        return [self.net, self.critic, self.action_distribution]
+
+    def policy_parameters(self):
+        for c in self._get_policy_components():
+            yield from c.parameters()
+
+    def all_policy_tensors(self):
+        yield from self.policy_parameters()
+        for c in self._get_policy_components():
+            yield from c.buffers()
+
+    def aux_loss_parameters(self):
+        return {}
+
+    # ---- flat parameter / gradient storage ---------------------------------------------------------
+    def flatten_parameters_(self):
+        """Re-home every parameter in one flat fp32 buffer (and .grad in a second one) so the
+        gradient all-reduce, the norm and Adam are single kernels.  Idempotent; re-run
+        automatically after .to()/load_state_dict replaced the storage."""
+        params = list(self.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise Hb200Error("hb200 policy must live on a CUDA device (no CPU fallback)")
+        n = sum(p.numel() for p in params)
+        f = self._flat
+        if f is not None and f["params"].device == dev and all(
+                p.data_ptr() == f["params"].data_ptr() + 4 * o and p.grad is not None and
+                p.grad.data_ptr() == f["grads"].data_ptr() + 4 * o for p, o in zip(params, f["offsets"])):
+            return f
+        n_pad = (n + 3) // 4 * 4
+        flat_p = torch.zeros(n_pad, device=dev)
+        flat_g = torch.zeros(n_pad, device=dev)
+        offs, o = [], 0
+        for p in params:
+            k = p.numel()
+            flat_p[o:o + k].copy_(p.data.reshape(-1))
+            p.data = flat_p[o:o + k].view(p.shape)
+            p.grad = flat_g[o:o + k].view(p.shape)
+            offs.append(o)
+            o += k
+        self._flat = dict(params=flat_p, grads=flat_g, offsets=offs, n=n, plist=params)
+        return self._flat
+
+    # ---- shared forward pieces -----------------------------------------------------------------------
+    def _engine_(self):
+        if self._engine is None:
+            self._engine = EncoderEngine(self.net.visual_encoder)
+        return self._engine
+
+    def _tmp(self, name, shape, dev, dtype=torch.float32):
+        key = (name, tuple(shape), dtype)
+        t = self._buf.get(key)
+        if t is None or t.device != dev:
+            t = torch.empty(*shape, device=dev, dtype=dtype)
+            self._buf[key] = t
+        return t
+
+    def _visual_prep(self, observations, rows, B, dev, update_stats):
+        enc = self.net.visual_encoder
+        H, W = enc.in_hw
+        rgb = observations.get("rgb") if "rgb" in enc.visual_keys else None
+        depth = observations.get("depth") if "depth" in enc.visual_keys else None
+        for k in enc.visual_keys:
+            if k not in ("rgb", "depth"):
+                raise NotImplementedError(f"visual sensor {k!r}: only rgb (u8x3) and depth (f32x1) are implemented")
+        rmv = enc.running_mean_and_var
+        scale_shift = None
+        if isinstance(rmv, RunningMeanAndVar):
+            C = enc._n_input_channels
+            scale_shift = self._tmp("scale_shift", (16,), dev)
+            stats = self._tmp("prep_stats", (17,), dev, torch.float64)
+            if update_stats:
+                ops.prep_stats(rgb, depth, rows, H, W, stats)
+                if self.world_size > 1:  # one packed collective instead of the reference's three
+                    torch.distributed.all_reduce(stats, group=self.dist_group)
+            ops.prep_finalize(stats, rmv._mean, rmv._var, rmv._count, scale_shift, C, (H // 2) * (W // 2),
+                              update_stats)
+
+        def write(x0):
+            ops.prep_apply(rgb, depth, rows, H, W, scale_shift, x0)
+
+        return write
+
+    def _trunk(self, observations, rnn_hidden_states, prev_actions, masks, train: bool):
+        """Everything up to the recurrent features.  Returns a dict of saved tensors."""
+        obs, rows = _as_rows(observations, rnn_hidden_states.device)
+        dev = rnn_hidden_states.device
+        if dev.type != "cuda":
+            raise Hb200Error("hb200 policy: inputs must be CUDA tensors (no CPU fallback)")
+        self.flatten_parameters_()
+        B = rows.numel()
+        n = rnn_hidden_states.shape[0]
+        T = B // n
+        assert T * n == B, "frames must be (t, env)-ordered with T*n rows"
+        H = self.net._hidden_size
+        L = self.net.state_encoder.rnn.num_layers
+        eng = self._engine_()
+        write_x0 = self._visual_prep(obs, rows, B, dev, update_stats=train and self.training)
+        feat = eng.forward(write_x0, B, dev, train)
+        # rnn input = [visual_fc | goal embedding | prev-action embedding]
+        fc = self.net.visual_fc[1]
+        D = H + 64
+        rnn_in = self._tmp("rnn_in", (B, D), dev)
+        ops.linear_fwd(feat, fc.weight, fc.bias, rnn_in, relu=True, ldc=D)
+        goal = obs[POINTGOAL_UUID]
+        pa = prev_actions.reshape(-1)
+        mk = ops.as_u8(masks.reshape(-1))
+        ops.embed_fwd(goal.reshape(-1, 2), pa, mk, rows, self.net.tgt_embeding.weight, self.net.tgt_embeding.bias,
+                      self.net.prev_action_embedding.weight, rnn_in, H)
+        rnn = self.net.state_encoder.rnn
+        hid = rnn_hidden_states.contiguous()
+        saved = dict(B=B, n=n, T=T, rows=rows, obs=obs, feat=feat, rnn_in=rnn_in, masks=mk, pa=pa, hid=hid, layers=[])
+        x = rnn_in
+        for l in range(L):
+            w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
+            b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
+            xproj = self._tmp(f"xproj{l}", (B, 4 * H), dev)
+            ops.linear_fwd(x, w_ih, b_ih, xproj)
+            hs = self._tmp(f"hs{l}", (T, n, H), dev)
+            cs = self._tmp(f"cs{l}", (T, n, H), dev)
+            gates = self._tmp(f"gates{l}", (T, n, 4 * H), dev) if train else None
+            h0, c0 = hid[:, l], hid[:, L + l]
+            for t in range(T):
+                ops.lstm_step_fwd(xproj[t * n:(t + 1) * n], w_hh, mk[t * n:(t + 1) * n], h0 if t == 0 else hs[t - 1],
+                                  c0 if t == 0 else cs[t - 1], hs[t], cs[t], gates[t] if train else None, n, H, b_hh)
+            saved["layers"].append(dict(x=x, xproj=xproj, hs=hs, cs=cs, gates=gates, h0=h0, c0=c0))
+            x = hs.view(B, H)
+        saved["features"] = x
+        saved["hidden_out"] = torch.stack([ly["hs"][T - 1] for ly in saved["layers"]] +
+                                          [ly["cs"][T - 1] for ly in saved["layers"]], dim=1)
+        return saved
+
+    # ---- inference paths ---------------------------------------------------------------------------------
+    @torch.no_grad()
+    def act(self, observations, rnn_hidden_states, prev_actions, masks, deterministic=False):
+        s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=False)
+        feats, B = s["features"], s["B"]
+        dev = feats.device
+        logits = self._tmp("logits", (B, self.dim_actions), dev)
+        values = self._tmp("values_act", (B,), dev)
+        ad, cr = self.action_distribution.linear, self.critic.fc
+        ops.heads_fwd(feats, ad.weight, ad.bias, cr.weight, cr.bias, logits, values)
+        logp = torch.log_softmax(logits, dim=-1)
+        if deterministic:
+            action = logp.argmax(dim=-1, keepdim=True)
+        else:  # sampling is not bit-reproducible across implementations (torch.multinomial, Philox)
+            action = torch.multinomial(logp.exp(), 1)
+        return PolicyActionData(values=values.view(B, 1).clone(), actions=action,
+                                action_log_probs=logp.gather(1, action), rnn_hidden_states=s["hidden_out"])
+
+    @torch.no_grad()
+    def get_value(self, observations, rnn_hidden_states, prev_actions, masks):
+        s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=False)
+        feats, B = s["features"], s["B"]
+        dev = feats.device
+        logits = self._tmp("logits", (B, self.dim_actions), dev)
+        values = self._tmp("values_act", (B,), dev)
+        ad, cr = self.action_distribution.linear, self.critic.fc
+        ops.heads_fwd(feats, ad.weight, ad.bias, cr.weight, cr.bias, logits, values)
+        return values.view(B, 1).clone()
+
+    # ---- training path --------------------------------------------------------------------------------------
+    def evaluate_actions(self, observations, rnn_hidden_states, prev_actions, masks, action,
+                         rnn_build_seq_info=None):
+        """Forward only (values, log-probs, entropy, hidden, aux) like the reference
+        (rl/ppo/policy.py:361-402).  The saved activations are kept for `loss_and_backward`;
+        `rnn_build_seq_info` is accepted and ignored: the masked recurrence needs only `masks`."""
+        s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=True)
+        self._saved = s
+        feats, B = s["features"], s["B"]
+        dev = feats.device
+        out = dict(values=self._tmp("ea_values", (B,), dev), log_probs=self._tmp("ea_lp", (B,), dev),
+                   entropy=self._tmp("ea_ent", (B,), dev), metrics=self._tmp("ea_metrics", (ops.N_METRICS,), dev))
+        ad, cr = self.action_distribution.linear, self.critic.fc
+        zero = self._tmp("zeros_B", (B,), dev)
+        zero.zero_()
+        ws = self._loss_ws(B, dev)
+        ops.ppo_loss(feats, ad.weight, ad.bias, cr.weight, cr.bias, action.reshape(-1), zero, zero, zero, zero, 0.2,
+                     0.5, 0.0, False, False, out, ws)
+        return (out["values"].view(B, 1), out["log_probs"].view(B, 1), out["entropy"].view(B, 1),
+                s["hidden_out"], {})
+
+    def _loss_ws(self, B, dev):
+        key = ("loss_ws", B)
+        if key not in self._buf or self._buf[key].device != dev:
+            self._buf[key] = ops.ppo_loss_workspace(B, self.net._hidden_size, self.dim_actions, dev)
+        return self._buf[key]
+
+    def loss_and_backward(self, batch, clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss,
+                          observations=None):
+        """Fused replacement of evaluate_actions + the loss section of PPO._update_from_batch +
+        total_loss.backward() (rl/ppo/ppo.py:180-254).  Leaves every parameter's gradient in the flat
+        gradient buffer (p.grad views) and returns the 12 metrics as a device tensor."""
+        obs = observations if observations is not None else batch["observations"]
+        s = self._trunk(obs, batch["recurrent_hidden_states"], batch["prev_actions"], batch["masks"], train=True)
+        feats, B, n, T = s["features"], s["B"], s["n"], s["T"]
+        dev = feats.device
+        H = self.net._hidden_size
+        flat = self._flat
+        flat["grads"].zero_()
+        ad, cr = self.action_distribution.linear, self.critic.fc
+        out = dict(values=self._tmp("ea_values", (B,), dev), log_probs=self._tmp("ea_lp", (B,), dev),
+                   entropy=self._tmp("ea_ent", (B,), dev), metrics=self._tmp("ea_metrics", (ops.N_METRICS,), dev),
+                   d_features=self._tmp("d_features", (B, H), dev), d_w_act=ad.weight.grad, d_b_act=ad.bias.grad,
+                   d_w_val=cr.weight.grad, d_b_val=cr.bias.grad)
+        f32 = lambda t: t.reshape(-1).contiguous()  # noqa: E731
+        ops.ppo_loss(feats, ad.weight, ad.bias, cr.weight, cr.bias, f32(batch["actions"]),
+                     f32(batch["action_log_probs"]), f32(batch["advantages"]), f32(batch["value_preds"]),
+                     f32(batch["returns"]), clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss, True,
+                     out, self._loss_ws(B, dev), is_coeffs=f32(batch["is_coeffs"]) if "is_coeffs" in batch else None)
+        # ---- LSTM backward through time, top layer first
+        rnn = self.net.state_encoder.rnn
+        L = rnn.num_layers
+        d_out = out["d_features"]
+        mk = s["masks"]
+        for l in reversed(range(L)):
+            ly = s["layers"][l]
+            w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
+            b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
+            dg = self._tmp(f"dgates{l}", (T, n, 4 * H), dev)
+            dh = [self._tmp(f"dh{i}", (n, H), dev) for i in range(2)]
+            dc = [self._tmp(f"dc{i}", (n, H), dev) for i in range(2)]
+            dov = d_out.view(T, n, H)
+            for t in reversed(range(T)):
+                last = t == T - 1
+                ops.lstm_step_bwd(dov[t], None if last else dh[(t + 1) % 2], None if last else dc[(t + 1) % 2],
+                                  ly["gates"][t], ly["cs"][t], ly["c0"] if t == 0 else ly["cs"][t - 1], w_hh,
+                                  mk[t * n:(t + 1) * n], dg[t], dh[t % 2], dc[t % 2], n, H)
+            dgf = dg.view(B, 4 * H)
+            x = ly["x"]
+            ops.linear_bwd_weight(dgf, x, w_ih.grad)
+            hin = self._tmp("hin", (T, n, H), dev)
+            ops.rnn_shift_mask(ly["hs"], ly["h0"], mk, hin, T, n, H)
+            ops.linear_bwd_weight(dgf, hin.view(B, H), w_hh.grad)
+            ops.colsum(dgf, b_ih.grad)
+            b_hh.grad.copy_(b_ih.grad)
+            dx = self._tmp(f"dx{l}", (B, x.shape[1]), dev)
+            ops.linear_bwd_input(dgf, w_ih, dx)
+            d_out = dx
+        d_rnn_in = d_out  # [B, H + 64]
+        # ---- embeddings
+        tg, emb = self.net.tgt_embeding, self.net.prev_action_embedding
+        ops.embed_bwd(s["obs"][POINTGOAL_UUID].reshape(-1, 2), s["pa"], mk, s["rows"], d_rnn_in, H, tg.weight.grad,
+                      tg.bias.grad, emb.weight.grad)
+        # ---- visual_fc (ReLU -> Linear)
+        fc = self.net.visual_fc[1]
+        ops.relu_bwd(d_rnn_in, s["rnn_in"], H)
+        dvis = d_rnn_in[:, :H]
+        ops.sgemm(dvis, 1, dvis.stride(0), s["feat"], s["feat"].stride(0), 1, fc.weight.grad, fc.weight.grad.stride(0),
+                  H, s["feat"].shape[1], B)
+        ops.colsum(dvis, fc.bias.grad, n_cols=H)
+        d_feat = self._tmp("d_feat", tuple(s["feat"].shape), dev)
+        ops.sgemm(dvis, dvis.stride(0), 1, fc.weight, fc.weight.stride(0), 1, d_feat, d_feat.stride(0), B,
+                  s["feat"].shape[1], H)
+        # ---- conv stack
+        self._engine_().backward(d_feat, B, dev)
+        self._last = dict(values=out["values"], log_probs=out["log_probs"], entropy=out["entropy"],
+                          hidden_out=s["hidden_out"])
+        return out["metrics"]

@@ -193,7 +193,8 @@ int hb200_umma_gemm_probe(const hb200_bf16* a, const hb200_bf16* b, float* d, in
  * (HB/rl/ddppo/policy/resnet.py:37-69, 207-219, 272-281).
  * stats f32 [B,G,2] = (sum, sumsq) over the (C/G)*H*W elements of each group (conv epilogue).
  */
-/* out = act(gamma * (y - mu) * rstd + beta);  relu: 0/1;  out is bf16, or f32 when out_f32 */
+/* out = act(gamma * (y - mu) * rstd + beta);  relu: 0/1;  out_f32: 0 -> bf16 NHWC, 1 -> f32 NHWC,
+ * 2 -> f32 [B, C*hw] flattened in (c,h,w) order (what nn.Flatten of the NCHW map feeds visual_fc) */
 int hb200_gn_apply(const hb200_bf16* y, const float* stats, const float* gamma, const float* beta,
                    void* out, int out_f32, int batch, int hw, int channels, int groups, float eps,
                    int relu, hb200_stream_t stream);
@@ -249,13 +250,13 @@ int hb200_f32_to_bf16(const float* x, hb200_bf16* out, long long n, hb200_stream
  * is exactly what that machinery computes (pinned by test/test_rnn_state_encoder.py:72-94).
  *
  * One call = one time step of one layer (frames of step t are rows [t*n, (t+1)*n)).
- * xproj f32 [n, G*H] = x_t W_ih^T + b_ih + b_hh precomputed by hb200_sgemm (G=4 LSTM, 3 GRU;
- * for GRU b_hh of the n-gate must NOT be folded: pass b_hn separately).
+ * xproj f32 [n, 4H] = x_t W_ih^T + b_ih precomputed for all frames by hb200_sgemm; b_hh f32 [4H]
+ * (may be NULL) is added in the step kernel.
  * w_hh f32 [G*H, H] (PyTorch gate order i,f,g,o / r,z,n).  masks u8 [n] (1 = not done).
  * h_prev/c_prev f32 [n,H] (row pitch H); outputs h,c [n,H]; gates_out f32 [n,G*H] saved
  * activations for backward (i,f,g,o post-nonlinearity).  GRU (config #3) is a "next" row.
  */
-int hb200_lstm_step_fwd(const float* xproj, const float* w_hh, const uint8_t* masks,
+int hb200_lstm_step_fwd(const float* xproj, const float* w_hh, const float* b_hh, const uint8_t* masks,
                         const float* h_prev, long long h_prev_stride, const float* c_prev,
                         long long c_prev_stride, float* h, float* c, float* gates_out, int n,
                         int hidden, hb200_stream_t stream);
@@ -273,13 +274,24 @@ int hb200_rnn_shift_mask(const float* h_seq, const float* h0, long long h0_row_s
                          const uint8_t* masks, float* h_in, int t_steps, int n, int hidden,
                          hb200_stream_t stream);
 /* out[N] (+)= column sums of x[M,N] (bias gradients) */
-int hb200_colsum(const float* x, float* out, long long m, int n, int accumulate,
+int hb200_colsum(const float* x, long long ld, float* out, long long m, int n, int accumulate,
                  hb200_stream_t stream);
+/* d[r,c] = 0 where y[r,c] <= 0, c < cols (ReLU backward on a column block; row pitches ld_*) */
+int hb200_relu_bwd(float* d, const float* y, long long ld_d, long long ld_y, long long rows, int cols,
+                   hb200_stream_t stream);
+/* f32 [B, C*hw] flattened in (c,h,w) order (nn.Flatten of NCHW, resnet_policy.py:587-594)
+ * -> bf16 NHWC [B,hw,C]: the gradient of visual_fc's input re-enters the NHWC conv stack */
+int hb200_f32_chw_to_bf16_hwc(const float* x, hb200_bf16* out, int batch, int hw, int channels,
+                              hb200_stream_t stream);
+/* actor path: logits f32 [B,A] and values f32 [B] only (HB/rl/ppo/policy.py:300-359) */
+int hb200_heads_fwd(const float* features, const float* w_act, const float* b_act, const float* w_val,
+                    const float* b_val, int batch, int hidden, int n_actions, float* logits,
+                    float* values, hb200_stream_t stream);
 
 /* ---- goal / previous-action embeddings --------------------------------------------------------
  * replaces tgt_embeding + prev_action_embedding + torch.cat of PointNavResNetNet.forward
  * (HB/rl/ddppo/policy/resnet_policy.py:658-692, 747-763).
- * goal f32 [rows,2] gathered through frame_rows; prev_actions i64 [rows]; masks u8 [rows].
+ * goal f32 [rows,2] gathered through frame_rows; prev_actions i64 [B]; masks u8 [B] (per frame).
  * Writes columns [col0, col0+32) (goal) and [col0+32, col0+64) (prev action) of out f32 [B,ld].
  */
 int hb200_embed_fwd(const float* goal, const int64_t* prev_actions, const uint8_t* masks,

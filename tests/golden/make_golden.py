@@ -1,0 +1,142 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference classes (imported from
+/root/reference through oracle/ref_shim.py) on recipe inputs.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The fixtures hold only small outputs (losses, per-frame values, per-tensor gradient norms ...);
+inputs and weights are regenerated from seeds by tests/golden/recipe.py.
+"""
+from __future__ import annotations
+
+import collections
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from oracle import ref_shim  # noqa: E402
+from recipe import recipe_state_dict, synthetic_rollout  # noqa: E402
+
+CASES = {
+    # name: (T, N, H, W, rnn_type, layers, ppo_epoch, num_mini_batch, use_normalized_advantage)
+    "small128": dict(T=8, N=4, H=128, W=128, rnn="LSTM", layers=2, epochs=2, mb=2, norm_adv=False, seed=11),
+    "full256": dict(T=4, N=2, H=256, W=256, rnn="LSTM", layers=2, epochs=1, mb=1, norm_adv=True, seed=12),
+}
+PPO_KW = dict(clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2,
+              use_clipped_value_loss=True)
+
+
+def build_reference(R, c):
+    sp = R.spaces
+    obs_space = sp.Dict({
+        "rgb": sp.Box(0, 255, (c["H"], c["W"], 3), np.uint8),
+        "depth": sp.Box(0, 1, (c["H"], c["W"], 1), np.float32),
+        "pointgoal_with_gps_compass": sp.Box(-1e9, 1e9, (2,), np.float32),
+    })
+    act_space = sp.Discrete(4)
+    pol = R.PointNavResNetPolicy(obs_space, act_space, hidden_size=512, num_recurrent_layers=c["layers"],
+                                 rnn_type=c["rnn"], resnet_baseplanes=32, backbone="resnet18",
+                                 normalize_visual_inputs=True)
+    shapes = {k: tuple(v.shape) for k, v in pol.state_dict().items()}
+    pol.load_state_dict(recipe_state_dict(shapes, c["seed"]))
+    return pol, obs_space, act_space, shapes
+
+
+def fill_storage(R, pol, obs_space, act_space, c):
+    st = R.RolloutStorage(c["T"], c["N"], obs_space, act_space, pol)
+    bufs, next_value = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, pol.num_recurrent_layers, 512, c["seed"])
+    for k, v in bufs["observations"].items():
+        st.buffers["observations"][k].copy_(v)
+    for k in ("recurrent_hidden_states", "masks", "rewards", "value_preds", "returns", "action_log_probs",
+              "actions", "prev_actions"):
+        st.buffers[k].copy_(bufs[k])
+    st.current_rollout_step_idxs = [c["T"]]
+    return st, next_value
+
+
+def main():
+    R = ref_shim.ref()
+    torch.set_num_threads(8)
+    for name, c in CASES.items():
+        torch.manual_seed(c["seed"])
+        pol, obs_space, act_space, shapes = build_reference(R, c)
+        st, next_value = fill_storage(R, pol, obs_space, act_space, c)
+        out = {"case": c, "shapes": shapes}
+        # --- compute_returns + advantages (rollout_storage.py:174-205, ppo.py:139-157)
+        st.compute_returns(next_value, True, 0.99, 0.95)
+        out["returns"] = st.buffers["returns"].clone()
+        out["value_preds_after"] = st.buffers["value_preds"].clone()
+        ppo = R.PPO(pol, ppo_epoch=c["epochs"], num_mini_batch=c["mb"], use_normalized_advantage=c["norm_adv"], **PPO_KW)
+        out["advantages"] = ppo.get_advantages(st).clone()
+        ppo_nn = R.PPO(pol, ppo_epoch=1, num_mini_batch=1, use_normalized_advantage=not c["norm_adv"], **PPO_KW)
+        out["advantages_other_mode"] = ppo_nn.get_advantages(st).clone()
+
+        # --- one minibatch: evaluate_actions + loss + backward (no optimizer step)
+        pol.train()
+        torch.manual_seed(1000 + c["seed"])  # randperm of data_generator
+        adv = ppo.get_advantages(st)
+        batch = next(iter(st.data_generator(adv, c["mb"])))
+        out["mb_env_inds_seed"] = 1000 + c["seed"]
+        stats_before = {k: v.clone() for k, v in pol.state_dict().items() if "running_mean_and_var" in k}
+        values, lp, ent, hid, _ = pol.evaluate_actions(batch["observations"], batch["recurrent_hidden_states"],
+                                                       batch["prev_actions"], batch["masks"], batch["actions"],
+                                                       batch["rnn_build_seq_info"])
+        out["eval_values"], out["eval_log_probs"], out["eval_entropy"] = values.detach(), lp.detach(), ent.detach()
+        out["eval_hidden"] = hid.detach()
+        out["running_stats_after_one_forward"] = {k: v.clone() for k, v in pol.state_dict().items()
+                                                  if "running_mean_and_var" in k}
+        ratio = torch.exp(lp - batch["action_log_probs"])
+        s1 = batch["advantages"] * ratio
+        s2 = batch["advantages"] * torch.clamp(ratio, 0.8, 1.2)
+        action_loss = -torch.min(s1, s2)
+        delta = values.detach() - batch["value_preds"]
+        vclip = batch["value_preds"] + delta.clamp(-0.2, 0.2)
+        vv = torch.where(delta.abs() < 0.2, values, vclip)
+        value_loss = 0.5 * (vv - batch["returns"]) ** 2
+        total = 0.5 * value_loss.mean() + action_loss.mean() - 0.01 * ent.mean()
+        pol.zero_grad()
+        total.backward()
+        out["mb_losses"] = dict(value_loss=value_loss.mean().item(), action_loss=action_loss.mean().item(),
+                                dist_entropy=ent.mean().item(), total=total.item())
+        out["grad_norms"] = {k: p.grad.norm().item() for k, p in pol.named_parameters()}
+        out["grad_samples"] = {k: p.grad.flatten()[:: max(1, p.numel() // 16)][:16].clone()
+                               for k, p in pol.named_parameters()}
+        # restore running stats so update() starts from the recipe state
+        pol.load_state_dict({**pol.state_dict(), **stats_before})
+        pol.zero_grad()
+
+        # --- full PPO.update (ppo.py:301-332)
+        torch.manual_seed(2000 + c["seed"])
+        metrics = ppo.update(st)
+        out["update_metrics"] = metrics
+        out["param_norms_after_update"] = {k: v.float().norm().item() for k, v in pol.state_dict().items()}
+        out["param_samples_after_update"] = {k: v.flatten()[:: max(1, v.numel() // 16)][:16].clone()
+                                             for k, v in pol.state_dict().items()}
+        torch.save(out, os.path.join(HERE, f"{name}.pt"))
+        print(name, "losses", out["mb_losses"], "update", {k: round(v, 6) for k, v in metrics.items()})
+
+    # --- RNN packed-sequence semantics (test/test_rnn_state_encoder.py) golden
+    torch.manual_seed(3)
+    enc = R.build_rnn_state_encoder(32, 32, rnn_type="LSTM", num_layers=2)
+    T, N = 13, 5
+    masks = torch.rand(T * N, 1) > (1 / 25)
+    x = torch.randn(T * N, 32)
+    hidden = torch.randn(N, 4, 32)
+    info = R.build_rnn_build_seq_info(device=torch.device("cpu"),
+                                      build_fn_result=R.build_pack_info_from_dones(
+                                          torch.logical_not(masks).view(T, N).numpy()))
+    with torch.no_grad():
+        y, h = enc(x, hidden, masks, info)
+    torch.save(dict(state_dict=enc.state_dict(), x=x, masks=masks, hidden=hidden, out=y, hidden_out=h, T=T, N=N),
+               os.path.join(HERE, "rnn_lstm.pt"))
+    print("rnn golden saved")
+
+
+if __name__ == "__main__":
+    main()

@@ -174,17 +174,22 @@ def test_clip_adam(hb, n, max_norm):
     for step in range(1, 4):
         grad = torch.randn(n, generator=g) * (0.01 * step)
         ref_p.grad = grad.clone()
+        true_norm = grad.double().norm().item()
         ref_norm = torch.nn.utils.clip_grad_norm_([ref_p], max_norm)
         opt.step()
         flat[1, :n] = grad.to(DEV)
         ops.clip_adam(flat[0, :n], flat[1, :n], flat[2, :n], flat[3, :n], 2.5e-4, (0.9, 0.999), 1e-5, 0.0,
                       max_norm, 1.0, step, gn, ws)
         torch.cuda.synchronize()
-        torch.testing.assert_close(gn.cpu()[0], ref_norm, rtol=1e-5, atol=1e-7)
+        # torch's fp32 CPU norm of 8.5M elements is itself off by ~3e-4 relative; the kernel
+        # accumulates in fp64 and must match the exact norm tightly, the reference loosely
+        assert gn.item() == pytest.approx(true_norm, rel=1e-5)
+        torch.testing.assert_close(gn.cpu()[0], ref_norm, rtol=1e-3, atol=1e-7)
         torch.testing.assert_close(flat[0, :n].cpu(), ref_p.detach(), rtol=1e-5, atol=2e-7)
     st = opt.state[ref_p]
-    torch.testing.assert_close(flat[2, :n].cpu(), st["exp_avg"], rtol=1e-5, atol=1e-8)
-    torch.testing.assert_close(flat[3, :n].cpu(), st["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+    # with clipping active the moments inherit the reference's ~3e-4 fp32 norm error (see above)
+    torch.testing.assert_close(flat[2, :n].cpu(), st["exp_avg"], rtol=1e-3, atol=1e-8)
+    torch.testing.assert_close(flat[3, :n].cpu(), st["exp_avg_sq"], rtol=2e-3, atol=1e-10)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -537,14 +542,15 @@ def test_embeddings(hb):
     ref_e = F.embedding(idx, emb)
     d = lambda t: t.detach().to(DEV).contiguous()  # noqa: E731
     out = torch.zeros(B, 576, device=DEV)
-    ops.embed_fwd(d(goal), d(pa.view(-1)), d(masks.view(-1)), d(fr), d(w), d(b), d(emb), out, 512)
+    pa_f, m_f = pa[fr.long()].view(-1), masks[fr.long()].view(-1)  # per-frame (gathered) like the minibatch
+    ops.embed_fwd(d(goal), d(pa_f), d(m_f), d(fr), d(w), d(b), d(emb), out, 512)
     torch.testing.assert_close(out[:, 512:544].cpu(), ref_t.detach(), rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(out[:, 544:576].cpu(), ref_e.detach(), rtol=0, atol=0)
     dout = torch.randn(B, 576, generator=g)
     (ref_t * dout[:, 512:544]).sum().backward()
     (ref_e * dout[:, 544:576]).sum().backward()
     dw, db, de = torch.zeros(32, 3, device=DEV), torch.zeros(32, device=DEV), torch.zeros(A + 1, 32, device=DEV)
-    ops.embed_bwd(d(goal), d(pa.view(-1)), d(masks.view(-1)), d(fr), d(dout), 512, dw, db, de)
+    ops.embed_bwd(d(goal), d(pa_f), d(m_f), d(fr), d(dout), 512, dw, db, de)
     torch.cuda.synchronize()
     torch.testing.assert_close(dw.cpu(), w.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(db.cpu(), b.grad, rtol=1e-4, atol=1e-4)

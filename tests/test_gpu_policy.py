@@ -1,0 +1,140 @@
+"""GPU: the whole native learner path (policy forward/backward, PPO.update) against the outputs of
+the REAL reference recorded in tests/golden/*.pt and against the CPU oracle on the same inputs.
+
+Tolerances: the conv stack computes in bf16 x bf16 -> fp32 (tensor cores) with bf16 activation
+storage; the reference's CUDA path is TF32.  Losses are means over frames and hold rtol 1e-3
+(north_star); per-frame values / log-probs and gradients carry the bf16 error of a 21-conv stack
+and are checked at the tolerance stated in each assert."""
+import math
+
+import pytest
+import torch
+
+from helpers import POLICY_CFG, gather_minibatch, load_golden, minibatch_env_inds, recipe_state_dict, synthetic_rollout
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+DEV = "cuda"
+
+
+def _make(hb, G):
+    from habitat_lab_b200.synthetic import pointnav_spaces
+
+    c = G["case"]
+    obs_space, act_space = pointnav_spaces(c["H"], c["W"])
+    pol = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=512, num_recurrent_layers=c["layers"],
+                                  rnn_type=c["rnn"], resnet_baseplanes=32, backbone="resnet18",
+                                  normalize_visual_inputs=True)
+    shapes = {k: tuple(v.shape) for k, v in pol.state_dict().items()}
+    assert shapes == {k: tuple(v) for k, v in G["shapes"].items()}, "state_dict layout differs from the reference"
+    pol.load_state_dict(recipe_state_dict(G["shapes"], c["seed"]))
+    pol.to(DEV)
+    st = hb.RolloutStorage(c["T"], c["N"], obs_space, act_space, pol)
+    bufs, next_value = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, 2 * c["layers"], 512, c["seed"])
+    for k, v in bufs["observations"].items():
+        st.buffers["observations"][k].copy_(v)
+    for k in ("recurrent_hidden_states", "masks", "rewards", "value_preds", "returns", "action_log_probs", "actions",
+              "prev_actions"):
+        st.buffers[k].copy_(bufs[k])
+    st.current_rollout_step_idxs = [c["T"]]
+    st.to(DEV)
+    return pol, st, next_value.to(DEV), c
+
+
+@pytest.mark.parametrize("name", ["small128", "full256"])
+def test_returns_advantages_vs_reference(hb, name):
+    G = load_golden(name)
+    pol, st, next_value, c = _make(hb, G)
+    st.compute_returns(next_value, True, 0.99, 0.95)
+    torch.testing.assert_close(st.buffers["returns"][: c["T"]].cpu(), G["returns"][: c["T"]], rtol=1e-5, atol=1e-5)
+    assert torch.equal(st.buffers["value_preds"].cpu(), G["value_preds_after"])
+    ppo = hb.PPO(pol, clip_param=0.2, ppo_epoch=1, num_mini_batch=1, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4,
+                 eps=1e-5, max_grad_norm=0.2, use_clipped_value_loss=True, use_normalized_advantage=c["norm_adv"])
+    adv = ppo.get_advantages(st)
+    torch.testing.assert_close(adv.cpu(), G["advantages"], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["small128", "full256"])
+def test_minibatch_forward_backward_vs_reference(hb, name):
+    G = load_golden(name)
+    pol, st, next_value, c = _make(hb, G)
+    pol.train()
+    st.buffers["value_preds"].copy_(G["value_preds_after"])
+    st.buffers["returns"].copy_(G["returns"])
+    torch.manual_seed(G["mb_env_inds_seed"])
+    batch = next(iter(st.data_generator(G["advantages"].to(DEV), c["mb"])))
+    assert torch.equal(batch["env_inds"], minibatch_env_inds(G["mb_env_inds_seed"], c["N"], c["mb"])[0])
+    metrics = pol.loss_and_backward(batch, 0.2, 0.5, 0.01, True).cpu()
+    torch.cuda.synchronize()
+    last = pol._last
+    # per-frame outputs (bf16 conv stack): absolute tolerance relative to the spread of the values
+    v_ref = G["eval_values"].view(-1)
+    assert (last["values"].cpu() - v_ref).abs().max().item() < 0.02 * max(1.0, v_ref.abs().max().item())
+    assert (last["log_probs"].cpu() - G["eval_log_probs"].view(-1)).abs().max().item() < 2e-2
+    assert (last["entropy"].cpu() - G["eval_entropy"].view(-1)).abs().max().item() < 2e-3
+    assert (last["hidden_out"].cpu() - G["eval_hidden"]).abs().max().item() < 3e-2
+    # running mean/var after one training forward
+    rs = G["running_stats_after_one_forward"]
+    p = "net.visual_encoder.running_mean_and_var."
+    sd = pol.state_dict()
+    torch.testing.assert_close(sd[p + "_mean"].cpu(), rs[p + "_mean"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(sd[p + "_var"].cpu(), rs[p + "_var"], rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(sd[p + "_count"].cpu(), rs[p + "_count"])
+    # losses: north_star tolerance rtol 1e-3 (abs floor for the near-zero action loss)
+    L = G["mb_losses"]
+    got = dict(value_loss=metrics[0].item(), action_loss=metrics[1].item(), dist_entropy=metrics[2].item(),
+               total=metrics[10].item())
+    print(name, "losses got", got, "ref", L)
+    for k in got:
+        assert got[k] == pytest.approx(L[k], rel=1e-3, abs=2e-4), (k, got[k], L[k])
+    # gradients of all 83 tensors: norm within 3% (bf16 tensor-core backward), sampled entries too
+    bad = []
+    for k, prm in pol.named_parameters():
+        gn_ref = G["grad_norms"][k]
+        gn = prm.grad.norm().item()
+        if abs(gn - gn_ref) > 0.03 * gn_ref + 1e-7:
+            bad.append((k, gn, gn_ref))
+    assert not bad, bad
+    worst = 0.0
+    for k, prm in pol.named_parameters():
+        g = prm.grad.flatten()[:: max(1, prm.numel() // 16)][:16].cpu()
+        ref = G["grad_samples"][k]
+        scale = max(G["grad_norms"][k] / math.sqrt(prm.numel()), 1e-9)
+        worst = max(worst, ((g - ref).abs().max() / scale).item())
+    print(name, "worst sampled-gradient error / rms gradient:", worst)
+    assert worst < 0.5
+
+
+@pytest.mark.parametrize("name", ["small128", "full256"])
+def test_ppo_update_vs_reference(hb, name):
+    G = load_golden(name)
+    pol, st, next_value, c = _make(hb, G)
+    pol.train()
+    ppo = hb.PPO(pol, clip_param=0.2, ppo_epoch=c["epochs"], num_mini_batch=c["mb"], value_loss_coef=0.5,
+                 entropy_coef=0.01, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, use_clipped_value_loss=True,
+                 use_normalized_advantage=c["norm_adv"])
+    st.compute_returns(next_value, True, 0.99, 0.95)
+    torch.manual_seed(2000 + c["seed"])
+    metrics = ppo.update(st)
+    ref = G["update_metrics"]
+    print(name, "update got", metrics, "ref", ref)
+    assert set(ref) <= set(metrics) | {"ppo_fraction_clipped"}
+    for k in ("value_loss", "action_loss", "dist_entropy"):
+        assert metrics[k] == pytest.approx(ref[k], rel=2e-3, abs=3e-4), k
+    for k in ("value_pred_mean", "prob_ratio_mean", "value_pred_min", "value_pred_max", "prob_ratio_min", "prob_ratio_max"):
+        assert metrics[k] == pytest.approx(ref[k], rel=2e-2, abs=2e-2), k
+    assert metrics["grad_norm"] == pytest.approx(ref["grad_norm"], rel=3e-2), "grad_norm"
+    assert metrics["ppo_fraction_clipped"] == pytest.approx(ref["ppo_fraction_clipped"], abs=0.07)
+    # parameters after the Adam steps: every tensor's norm within 1e-3 relative
+    sd = pol.state_dict()
+    for k, n_ref in G["param_norms_after_update"].items():
+        assert sd[k].float().norm().item() == pytest.approx(n_ref, rel=1e-3, abs=1e-5), k
+    # optimizer state round-trips through torch.optim.Adam's state_dict format
+    osd = ppo.get_resume_state()["optim_state"]
+    ref_opt = torch.optim.Adam([torch.nn.Parameter(torch.zeros_like(p, device="cpu")) for p in pol.parameters()], lr=2.5e-4, eps=1e-5)
+    cpu_sd = dict(state={i: {kk: vv.cpu() for kk, vv in s.items()} for i, s in osd["state"].items()},
+                  param_groups=osd["param_groups"])
+    ref_opt.load_state_dict(cpu_sd)
+
+
+def test_smoke_runs(hb):
+    hb.smoke()
