@@ -57,6 +57,8 @@ SIGNATURES = {
     "hb200_f32_to_bf16": ("i", "pplp"),
     "hb200_lstm_step_fwd": ("i", "ppppplplppp" + "ii" + "p"),
     "hb200_lstm_step_bwd": ("i", "ppppppl" + "ppppp" + "ii" + "p"),
+    "hb200_lstm_seq_fwd": ("i", "ppppplplppp" + "iii" + "pp"),
+    "hb200_lstm_seq_bwd": ("i", "pppplppp" + "iii" + "pp"),
     "hb200_rnn_shift_mask": ("i", "pplpp" + "iii" + "p"),
     "hb200_colsum": ("i", "plplii" + "p"),
     "hb200_relu_bwd": ("i", "pplll" + "i" + "p"),

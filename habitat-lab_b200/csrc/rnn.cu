@@ -188,3 +188,226 @@ extern "C" int hb200_lstm_step_bwd(const float* dh_out, const float* dh_rec, con
   count_launch(2);
   return HB200_OK;
 }
+
+// =====================================================================================
+// Persistent whole-sequence kernels: one cooperative launch per layer instead of T (forward)
+// / 2T (backward) launches.  Each CTA keeps its slice of W_hh in shared memory for all T steps
+// and the CTAs exchange h_t (forward) / dgates_t (backward) through L2 with one grid barrier per
+// step.  Launched with cudaLaunchCooperativeKernel so all CTAs are co-resident.
+// =====================================================================================
+namespace hb200 {
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(counter) < target) {
+      if (clock64() - t0 > 4000000000ll) __trap();  // bounded: a lost CTA errors out instead of hanging
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(256)
+lstm_seq_fwd_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh,
+                    const float* __restrict__ b_hh, const uint8_t* __restrict__ masks,
+                    const float* __restrict__ h0, long long h0_stride, const float* __restrict__ c0,
+                    long long c0_stride, float* __restrict__ hs, float* __restrict__ cs,
+                    float* __restrict__ gates_out, int T, int n, unsigned* counter) {
+  constexpr int H = NJ * 32;
+  extern __shared__ float sw[];  // [16][H]
+  const int u0 = blockIdx.x * kUnits;
+  for (int i = threadIdx.x; i < 16 * H; i += blockDim.x) {
+    const int r = i / H, k = i - r * H;
+    sw[i] = w_hh[((size_t)(r >> 2) * H + u0 + (r & 3)) * H + k];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float bi = 0, bf_ = 0, bg = 0, bo = 0;
+  if (b_hh && lane < kUnits) {
+    const int col = u0 + lane;
+    bi = b_hh[col]; bf_ = b_hh[H + col]; bg = b_hh[2 * H + col]; bo = b_hh[3 * H + col];
+  }
+  for (int t = 0; t < T; ++t) {
+    const float* hp = t == 0 ? h0 : hs + (size_t)(t - 1) * n * H;
+    const long long hps = t == 0 ? h0_stride : H;
+    const float* cp = t == 0 ? c0 : cs + (size_t)(t - 1) * n * H;
+    const long long cps = t == 0 ? c0_stride : H;
+    for (int s = warp; s < n; s += 8) {
+      const float m = masks[(size_t)t * n + s] ? 1.f : 0.f;
+      float hv[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) hv[j] = __ldcg(hp + (size_t)s * hps + lane + 32 * j) * m;
+      float dot[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc = fmaf(hv[j], sw[r * H + lane + 32 * j], acc);
+        dot[r] = warp_sum(acc);
+      }
+      float gi = 0, gf = 0, gg = 0, go = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (lane == u) { gi = dot[u]; gf = dot[4 + u]; gg = dot[8 + u]; go = dot[12 + u]; }
+      if (lane < kUnits) {
+        const int col = u0 + lane;
+        const float* xp = xproj + ((size_t)t * n + s) * 4 * H;
+        const float i_ = sigmoidf_(gi + bi + xp[col]);
+        const float f_ = sigmoidf_(gf + bf_ + xp[H + col]);
+        const float g_ = tanhf(gg + bg + xp[2 * H + col]);
+        const float o_ = sigmoidf_(go + bo + xp[3 * H + col]);
+        const float cin = __ldcg(cp + (size_t)s * cps + col) * m;
+        const float cn = f_ * cin + i_ * g_;
+        const size_t o = ((size_t)t * n + s) * H + col;
+        cs[o] = cn;
+        hs[o] = o_ * tanhf(cn);
+        if (gates_out) {
+          float* gp = gates_out + ((size_t)t * n + s) * 4 * H;
+          gp[col] = i_; gp[H + col] = f_; gp[2 * H + col] = g_; gp[3 * H + col] = o_;
+        }
+      }
+    }
+    if (t + 1 < T) grid_barrier(counter, (unsigned)(t + 1) * gridDim.x);
+  }
+}
+
+// backward through time for one layer.  CTA = 4 hidden units: pointwise for its units (dh_rec /
+// dc_rec of those units never leave the CTA), publishes its 16 dgates columns, barrier, then its 4
+// columns of dh_{t-1} = m_t * dgates_t W_hh  with W_hh^T[:, 4 cols] resident in shared memory.
+__global__ void __launch_bounds__(256)
+lstm_seq_bwd_kernel(const float* __restrict__ dh_out, const float* __restrict__ gates,
+                    const float* __restrict__ cs, const float* __restrict__ c0, long long c0_stride,
+                    const float* __restrict__ w_hh, const uint8_t* __restrict__ masks,
+                    float* __restrict__ dgates, int T, int n, int H, unsigned* counter) {
+  extern __shared__ float smem[];
+  const int R = 4 * H;
+  float* wt = smem;                 // [R][4]
+  float* dh_rec = smem + 4 * R;     // [n][4]
+  float* dc_rec = dh_rec + 4 * n;   // [n][4]
+  const int u0 = blockIdx.x * kUnits;
+  for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) {
+    const int r = i >> 2, u = i & 3;
+    wt[i] = w_hh[(size_t)r * H + u0 + u];
+  }
+  for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) { dh_rec[i] = 0.f; dc_rec[i] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = T - 1; t >= 0; --t) {
+    // ---- pointwise for own units
+    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) {
+      const int s = i >> 2, col = u0 + (i & 3);
+      const size_t row = (size_t)t * n + s;
+      const float m = masks[row] ? 1.f : 0.f;
+      const float* gt = gates + row * R;
+      const float i_ = gt[col], f_ = gt[H + col], g_ = gt[2 * H + col], o_ = gt[3 * H + col];
+      const float dh = dh_out[row * H + col] + dh_rec[i];
+      const float tc = tanhf(cs[row * H + col]);
+      const float dc = dh * o_ * (1.f - tc * tc) + dc_rec[i];
+      const float cin = (t == 0 ? c0[(size_t)s * c0_stride + col] : cs[(row - n) * H + col]) * m;
+      float* dg = dgates + row * R;
+      dg[col] = dc * g_ * i_ * (1.f - i_);
+      dg[H + col] = dc * cin * f_ * (1.f - f_);
+      dg[2 * H + col] = dc * i_ * (1.f - g_ * g_);
+      dg[3 * H + col] = dh * tc * o_ * (1.f - o_);
+      dc_rec[i] = dc * f_ * m;
+    }
+    if (t == 0) break;
+    grid_barrier(counter, (unsigned)(T - t) * gridDim.x);
+    // ---- dh_{t-1}[s, own 4 cols] = m_t[s] * sum_r dgates_t[s, r] * W_hh[r, col]
+    for (int s = warp; s < n; s += 8) {
+      const float* dg = dgates + ((size_t)t * n + s) * R;
+      float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int r = lane; r < R; r += 32) {
+        const float d = __ldcg(dg + r);
+        const float4 w = *reinterpret_cast<const float4*>(wt + 4 * r);
+        a0 = fmaf(d, w.x, a0); a1 = fmaf(d, w.y, a1); a2 = fmaf(d, w.z, a2); a3 = fmaf(d, w.w, a3);
+      }
+      a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+      if (lane == 0) {
+        const float m = masks[(size_t)t * n + s] ? 1.f : 0.f;
+        dh_rec[4 * s] = a0 * m; dh_rec[4 * s + 1] = a1 * m; dh_rec[4 * s + 2] = a2 * m; dh_rec[4 * s + 3] = a3 * m;
+      }
+    }
+    __syncthreads();
+  }
+}
+}  // namespace hb200
+
+static int coop_check(const void* kern, int block, size_t smem, int grid) {
+  int per_sm = 0;
+  HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
+  int dev = 0, sms = 0;
+  HB_CUDA(cudaGetDevice(&dev));
+  HB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (per_sm * sms < grid) {
+    set_last_error("lstm_seq: %d CTAs cannot be co-resident (%d per SM x %d SMs)", grid, per_sm, sms);
+    return HB200_ERR_UNSUPPORTED;
+  }
+  return HB200_OK;
+}
+
+extern "C" int hb200_lstm_seq_fwd(const float* xproj, const float* w_hh, const float* b_hh,
+                                  const uint8_t* masks, const float* h0, long long h0_stride,
+                                  const float* c0, long long c0_stride, float* hs, float* cs,
+                                  float* gates_out, int t_steps, int n, int hidden, void* workspace,
+                                  hb200_stream_t stream) {
+  HB_CHECK_ARG(xproj && w_hh && masks && h0 && c0 && hs && cs && workspace && t_steps > 0 && n > 0,
+               "lstm_seq_fwd: bad args");
+  HB_CHECK_ARG(hidden == 32 || hidden == 64 || hidden == 128 || hidden == 256 || hidden == 512,
+               "lstm_seq_fwd: hidden=%d unsupported (32,64,128,256,512)", hidden);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* counter = (unsigned*)workspace;
+  HB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+  const size_t smem = sizeof(float) * 16 * hidden;
+  const int grid = hidden / kUnits;
+  void* args[] = {(void*)&xproj, (void*)&w_hh, (void*)&b_hh, (void*)&masks, (void*)&h0, (void*)&h0_stride,
+                  (void*)&c0, (void*)&c0_stride, (void*)&hs, (void*)&cs, (void*)&gates_out, (void*)&t_steps,
+                  (void*)&n, (void*)&counter};
+  const void* kern = nullptr;
+  switch (hidden / 32) {
+    case 1: kern = (const void*)lstm_seq_fwd_kernel<1>; break;
+    case 2: kern = (const void*)lstm_seq_fwd_kernel<2>; break;
+    case 4: kern = (const void*)lstm_seq_fwd_kernel<4>; break;
+    case 8: kern = (const void*)lstm_seq_fwd_kernel<8>; break;
+    default: kern = (const void*)lstm_seq_fwd_kernel<16>; break;
+  }
+  if (smem > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc = coop_check(kern, 256, smem, grid);
+  if (rc) return rc;
+  HB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, smem, st));
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const float* cs, const float* c0,
+                                  long long c0_stride, const float* w_hh, const uint8_t* masks, float* dgates,
+                                  int t_steps, int n, int hidden, void* workspace, hb200_stream_t stream) {
+  HB_CHECK_ARG(dh_out && gates && cs && c0 && w_hh && masks && dgates && workspace && t_steps > 0 && n > 0,
+               "lstm_seq_bwd: bad args");
+  HB_CHECK_ARG(hidden % kUnits == 0 && hidden % 32 == 0, "lstm_seq_bwd: hidden must be a multiple of 32");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* counter = (unsigned*)workspace;
+  HB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+  const size_t smem = sizeof(float) * (16 * (size_t)hidden + 8 * (size_t)n);
+  HB_CHECK_ARG(smem <= 200 * 1024, "lstm_seq_bwd: n=%d too large for one CTA's shared memory", n);
+  const int grid = hidden / kUnits;
+  const void* kern = (const void*)lstm_seq_bwd_kernel;
+  if (smem > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc = coop_check(kern, 256, smem, grid);
+  if (rc) return rc;
+  void* args[] = {(void*)&dh_out, (void*)&gates, (void*)&cs, (void*)&c0, (void*)&c0_stride, (void*)&w_hh,
+                  (void*)&masks, (void*)&dgates, (void*)&t_steps, (void*)&n, (void*)&hidden, (void*)&counter};
+  HB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, smem, st));
+  count_launch(1);
+  return HB200_OK;
+}

@@ -227,6 +227,16 @@ def lstm_step_bwd(dh_out, dh_rec, dc_rec, gates, c, c_prev, w_hh, masks, dgates,
          c_prev.stride(0), ptr(w_hh), ptr(masks), ptr(dgates), ptr(dh_prev), ptr(dc_prev), n, hidden)
 
 
+def lstm_seq_fwd(xproj, w_hh, b_hh, masks, h0, c0, hs, cs, gates, T, n, hidden, workspace):
+    call("hb200_lstm_seq_fwd", ptr(xproj), ptr(w_hh), ptr(b_hh), ptr(masks), ptr(h0), h0.stride(0), ptr(c0),
+         c0.stride(0), ptr(hs), ptr(cs), ptr(gates), T, n, hidden, ptr(workspace))
+
+
+def lstm_seq_bwd(dh_out, gates, cs, c0, w_hh, masks, dgates, T, n, hidden, workspace):
+    call("hb200_lstm_seq_bwd", ptr(dh_out), ptr(gates), ptr(cs), ptr(c0), c0.stride(0), ptr(w_hh), ptr(masks),
+         ptr(dgates), T, n, hidden, ptr(workspace))
+
+
 def rnn_shift_mask(h_seq, h0, masks, h_in, T, n, hidden):
     call("hb200_rnn_shift_mask", ptr(h_seq), ptr(h0), h0.stride(0), ptr(masks), ptr(h_in), T, n, hidden)
 

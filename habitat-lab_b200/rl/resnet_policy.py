@@ -618,9 +618,7 @@ class PointNavResNetPolicy(nn.Module):
             cs = self._tmp(f"cs{l}", (T, n, H), dev)
             gates = self._tmp(f"gates{l}", (T, n, 4 * H), dev) if train else None
             h0, c0 = hid[:, l], hid[:, L + l]
-            for t in range(T):
-                ops.lstm_step_fwd(xproj[t * n:(t + 1) * n], w_hh, mk[t * n:(t + 1) * n], h0 if t == 0 else hs[t - 1],
-                                  c0 if t == 0 else cs[t - 1], hs[t], cs[t], gates[t] if train else None, n, H, b_hh)
+            ops.lstm_seq_fwd(xproj, w_hh, b_hh, mk, h0, c0, hs, cs, gates, T, n, H, self._tmp("rnn_ws", (64,), dev, torch.uint8))
             saved["layers"].append(dict(x=x, xproj=xproj, hs=hs, cs=cs, gates=gates, h0=h0, c0=c0))
             x = hs.view(B, H)
         saved["features"] = x
@@ -716,14 +714,8 @@ class PointNavResNetPolicy(nn.Module):
             w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
             b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
             dg = self._tmp(f"dgates{l}", (T, n, 4 * H), dev)
-            dh = [self._tmp(f"dh{i}", (n, H), dev) for i in range(2)]
-            dc = [self._tmp(f"dc{i}", (n, H), dev) for i in range(2)]
-            dov = d_out.view(T, n, H)
-            for t in reversed(range(T)):
-                last = t == T - 1
-                ops.lstm_step_bwd(dov[t], None if last else dh[(t + 1) % 2], None if last else dc[(t + 1) % 2],
-                                  ly["gates"][t], ly["cs"][t], ly["c0"] if t == 0 else ly["cs"][t - 1], w_hh,
-                                  mk[t * n:(t + 1) * n], dg[t], dh[t % 2], dc[t % 2], n, H)
+            ops.lstm_seq_bwd(d_out.view(T, n, H), ly["gates"], ly["cs"], ly["c0"], w_hh, mk, dg, T, n, H,
+                             self._tmp("rnn_ws", (64,), dev, torch.uint8))
             dgf = dg.view(B, 4 * H)
             x = ly["x"]
             ops.linear_bwd_weight(dgf, x, w_ih.grad)

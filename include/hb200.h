@@ -269,6 +269,18 @@ int hb200_lstm_step_bwd(const float* dh_out, const float* dh_rec, const float* d
                         long long c_prev_stride, const float* w_hh, const uint8_t* masks,
                         float* dgates, float* dh_prev, float* dc_prev, int n, int hidden,
                         hb200_stream_t stream);
+/* Whole-sequence persistent versions (ONE cooperative launch per layer; W_hh slices stay in shared
+ * memory for all T steps, CTAs exchange h_t / dgates_t through L2 with one grid barrier per step).
+ * xproj [T*n,4H], masks u8 [T*n], hs/cs [T,n,H], gates [T,n,4H] (NULL in inference), h0/c0 [n,H]
+ * with row strides.  workspace: >= 64 bytes of device memory (barrier counter). */
+int hb200_lstm_seq_fwd(const float* xproj, const float* w_hh, const float* b_hh, const uint8_t* masks,
+                       const float* h0, long long h0_stride, const float* c0, long long c0_stride,
+                       float* hs, float* cs, float* gates_out, int t_steps, int n, int hidden,
+                       void* workspace, hb200_stream_t stream);
+/* dh_out [T,n,H] = gradient wrt the layer output; writes dgates [T,n,4H] (= d xproj). */
+int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const float* cs, const float* c0,
+                       long long c0_stride, const float* w_hh, const uint8_t* masks, float* dgates,
+                       int t_steps, int n, int hidden, void* workspace, hb200_stream_t stream);
 /* h_in[t] = (t == 0 ? h0 : h_seq[t-1]) * m_t for the whole sequence (input of dW_hh = dG^T h_in) */
 int hb200_rnn_shift_mask(const float* h_seq, const float* h0, long long h0_row_stride,
                          const uint8_t* masks, float* h_in, int t_steps, int n, int hidden,

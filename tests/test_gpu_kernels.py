@@ -494,6 +494,14 @@ def test_lstm_masked_recurrence(hb, T, n, H, D):
     assert diff < 1e-3, diff
     torch.testing.assert_close(hs[-1].cpu(), hid_ref[:, 0].detach(), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(cs[-1].cpu(), hid_ref[:, 1].detach(), rtol=1e-4, atol=1e-5)
+    # persistent whole-sequence kernel must reproduce the per-step kernel bit for bit
+    ws = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    hs2, cs2, gates2 = torch.empty_like(hs), torch.empty_like(cs), torch.empty_like(gates)
+    ops.lstm_seq_fwd(xproj, w_hh, None, md, h0, c0, hs2, cs2, gates2, T, n, H, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(hs2, hs) and torch.equal(cs2, cs) and torch.equal(gates2, gates)
+    dg2 = torch.empty(T, n, 4 * H, device=DEV)
+    ops.lstm_seq_bwd(d(gout).view(T, n, H), gates, cs, c0, w_hh, md, dg2, T, n, H, ws)
     # backward through time
     dg = torch.empty(T, n, 4 * H, device=DEV)
     dh = [torch.zeros(n, H, device=DEV) for _ in range(2)]
@@ -504,6 +512,8 @@ def test_lstm_masked_recurrence(hb, T, n, H, D):
         ops.lstm_step_bwd(gd[t], None if last else dh[(t + 1) % 2], None if last else dc[(t + 1) % 2], gates[t],
                           cs[t], c0 if t == 0 else cs[t - 1], w_hh, md[t * n:(t + 1) * n], dg[t], dh[t % 2],
                           dc[t % 2], n, H)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dg2, dg, rtol=1e-4, atol=1e-6)
     dgf = dg.view(T * n, 4 * H)
     dx = torch.empty(T * n, D, device=DEV)
     ops.linear_bwd_input(dgf, w_ih, dx)
