@@ -28,6 +28,22 @@ using namespace umma;
 
 constexpr int TH = 16, TW = 8;  // output tile: 16 rows x 8 cols = 128 pixels = UMMA M
 
+// transpose-reduce: each lane holds 16 partial sums v[i]; afterwards lane l holds the warp-wide sum of
+// v[l >> 1] (16 shuffles).  Lanes 2i and 2i+1 hold the same value.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (b4 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, b4 ? v[i] : v[i + 8], 16);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b[i] = (b3 ? a[i + 4] : a[i]) + __shfl_xor_sync(0xffffffffu, b3 ? a[i] : a[i + 4], 8);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) c[i] = (b2 ? b[i + 2] : b[i]) + __shfl_xor_sync(0xffffffffu, b2 ? b[i] : b[i + 2], 4);
+  float d = (b1 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, b1 ? c[0] : c[1], 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+
 struct HaloArgs {
   const __nv_bfloat16* x;      // [B,H,W,C] input of the conv (x for fwd, dy for dgrad)
   const __nv_bfloat16* wimg;   // [taps][C/8][N][8] weight image (K-major no-swizzle per tap)
@@ -162,6 +178,8 @@ __global__ void __launch_bounds__(128) conv_halo_kernel(const HaloArgs a) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rr[j]);
         if (MODE == 0 && a.stats != nullptr) {
+          // per (frame, group) sum / sum-of-squares of this 32-column slab over the warp's 32 pixels:
+          // pairwise channel sums, then a transpose-reduce (16 + 16 shuffles instead of 2 x 16 x 5)
           const int cpg = N / a.gn_groups;
           float s2[16], q2[16];
 #pragma unroll
@@ -169,38 +187,12 @@ __global__ void __launch_bounds__(128) conv_halo_kernel(const HaloArgs a) {
             s2[i] = acc[2 * i] + acc[2 * i + 1];
             q2[i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
           }
-          int lg = 0;
-          while ((2 << lg) < cpg && lg < 4) ++lg;
-#pragma unroll
-          for (int lvl = 0; lvl < 4; ++lvl) {
-            if (lvl < lg) {
-#pragma unroll
-              for (int i = 0; i < (8 >> lvl); ++i) {
-                s2[i] = s2[2 * i] + s2[2 * i + 1];
-                q2[i] = q2[2 * i] + q2[2 * i + 1];
-              }
-            }
-          }
-          const int ng = 16 >> lg;
-#pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (i < ng) {
-                s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
-                q2[i] += __shfl_xor_sync(0xffffffffu, q2[i], off);
-              }
-            }
-          }
-          if (lane == 0) {
-            float* dst = a.stats + ((size_t)b * a.gn_groups + col0 / cpg) * 2;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (i < ng) {
-                atomicAdd(dst + 2 * i, s2[i]);
-                atomicAdd(dst + 2 * i + 1, q2[i]);
-              }
-            }
+          const float ts = warp_reduce16(s2, lane), tq = warp_reduce16(q2, lane);  // lane l: channel pair l >> 1
+          if ((lane & 1) == 0) {
+            const int ch = col0 + lane;  // first channel of the pair
+            float* dst = a.stats + ((size_t)b * a.gn_groups + ch / cpg) * 2;
+            atomicAdd(dst, ts);
+            atomicAdd(dst + 1, tq);
           }
         }
         const size_t o = pix * N + col0;
@@ -403,17 +395,31 @@ __global__ void unpack_stem_wgrad_kernel(const float* __restrict__ acc, float* _
   }
 }
 
+// resident CTAs per SM from static limits (registers, shared memory, TMEM columns); cached per kernel
+static int blocks_per_sm(const void* kern, size_t smem, int tmem_cols, int* cache) {
+  if (*cache > 0) return *cache;
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) return 1;
+  const int regs = fa.numRegs > 0 ? fa.numRegs : 128;
+  int by_regs = 65536 / (((regs + 7) / 8 * 8) * 128);
+  int by_smem = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+  int by_tmem = 512 / tmem_cols;
+  int n = by_regs < by_smem ? by_regs : by_smem;
+  if (by_tmem < n) n = by_tmem;
+  if (n > 16) n = 16;
+  if (n < 1) n = 1;
+  *cache = n;
+  return n;
+}
+
 template <int C, int N, int KH, int KW, int PAD, int MODE>
 static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   using Cfg = HaloCfg<C, N, KH, KW, PAD>;
   const size_t smem = Cfg::W_BYTES + 2 * Cfg::HALO_BYTES + 256;
   auto kern = conv_halo_kernel<C, N, KH, KW, PAD, MODE>;
-  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 1;
-  HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
-  if (per_sm < 1) per_sm = 1;
-  const int tmem_limit = 512 / Cfg::TMEM_COLS;
-  if (per_sm > tmem_limit) per_sm = tmem_limit;
+  static int cache = 0;
+  if (cache == 0) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = blocks_per_sm((const void*)kern, smem, Cfg::TMEM_COLS, &cache);
   int grid = kNumSMs * per_sm;
   if (grid > a.ntiles) grid = a.ntiles;
   kern<<<grid, 128, smem, st>>>(a);
@@ -428,13 +434,11 @@ static int launch_halo_wgrad(const HaloWgradArgs& a, cudaStream_t st) {
   constexpr int MT = (KH * CJ + 15) / 16, RMAX = (MT * 16 + CJ - 1) / CJ, HROWS = TH - 1 + RMAX;
   const size_t smem = 2 * (size_t)(HROWS * RP + 128 * N * 2) + 256;
   auto kern = conv_halo_wgrad_kernel<C, N, KH, KW, PAD>;
-  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 1;
-  HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
-  if (per_sm < 1) per_sm = 1;
+  static int cache = 0;
+  if (cache == 0) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   constexpr int raw = KW * MT * N;
   constexpr int tcols = raw <= 32 ? 32 : raw <= 64 ? 64 : raw <= 128 ? 128 : raw <= 256 ? 256 : 512;
-  if (per_sm > 512 / tcols) per_sm = 512 / tcols;
+  const int per_sm = blocks_per_sm((const void*)kern, smem, tcols, &cache);
   int grid = kNumSMs * per_sm;
   if (grid > a.ntiles) grid = a.ntiles;
   kern<<<grid, 128, smem, st>>>(a);

@@ -223,23 +223,45 @@ __device__ __forceinline__ void load8f(const float* __restrict__ p, float (&f)[8
   f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
+// The three per-layer GroupNorm passes below share one mapping: block = (frame, pixel slab),
+// thread = (8-channel vector, pixel lane).  All per-channel / per-group coefficients are hoisted
+// out of the pixel loop, so the inner loop is load - 8 FMAs - store: HBM-bound.
+struct GnSlab {
+  int b, vec, c0, pix0, pix1, npl, pl;
+};
+__device__ __forceinline__ GnSlab gn_slab(int C, int hw, int ppb) {
+  GnSlab s;
+  const int cv = C >> 3;
+  const int slabs = (hw + ppb - 1) / ppb;
+  s.b = blockIdx.x / slabs;
+  const int slab = blockIdx.x - s.b * slabs;
+  s.vec = threadIdx.x % cv;
+  s.pl = threadIdx.x / cv;
+  s.npl = blockDim.x / cv;
+  s.c0 = s.vec << 3;
+  s.pix0 = slab * ppb;
+  s.pix1 = min(hw, s.pix0 + ppb);
+  return s;
+}
+
 template <int OUT_F32>  // 0: bf16 NHWC, 1: f32 NHWC, 2: f32 flattened in (c, h, w) order (nn.Flatten of NCHW)
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ out, int B, int hw, int relu) {
+gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ out, int B, int hw, int relu, int ppb) {
+  const GnSlab t = gn_slab(p.C, hw, ppb);
   const int cv = p.C >> 3;
-  const long long total = (long long)B * hw * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cv) << 3;
-    const int b = (int)(i / ((long long)hw * cv));
-    float mu[8], rs[8], x[8], ga[8], be[8];
-    gn_coeffs(p, b, c0, mu, rs);
+  float mu[8], rs[8], ga[8], be[8], sc[8], sh[8];
+  gn_coeffs(p, t.b, t.c0, mu, rs);
+  load8f(p.gamma + t.c0, ga);
+  load8f(p.beta + t.c0, be);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = rs[e] * ga[e]; sh[e] = fmaf(-mu[e], sc[e], be[e]); }
+  for (int pix = t.pix0 + t.pl; pix < t.pix1; pix += t.npl) {
+    const size_t i = ((size_t)t.b * hw + pix) * cv + t.vec;
+    float x[8];
     unpack8(reinterpret_cast<const uint4*>(y)[i], x);
-    load8f(p.gamma + c0, ga);
-    load8f(p.beta + c0, be);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float z = fmaf((x[e] - mu[e]) * rs[e], ga[e], be[e]);
+      const float z = fmaf(x[e], sc[e], sh[e]);
       x[e] = relu ? fmaxf(z, 0.f) : z;
     }
     if (OUT_F32 == 1) {
@@ -247,10 +269,9 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ o
       o[0] = make_float4(x[0], x[1], x[2], x[3]);
       o[1] = make_float4(x[4], x[5], x[6], x[7]);
     } else if (OUT_F32 == 2) {
-      const int pix = (int)((i / cv) % hw);
-      float* o = reinterpret_cast<float*>(out) + (size_t)b * p.C * hw;
+      float* o = reinterpret_cast<float*>(out) + (size_t)t.b * p.C * hw;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[(size_t)(c0 + e) * hw + pix] = x[e];
+      for (int e = 0; e < 8; ++e) o[(size_t)(t.c0 + e) * hw + pix] = x[e];
     } else {
       reinterpret_cast<uint4*>(out)[i] = pack8(x);
     }
@@ -259,30 +280,29 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ o
 
 __global__ void __launch_bounds__(256)
 gn_residual_relu_kernel(const __nv_bfloat16* __restrict__ y, GnP p, const __nv_bfloat16* __restrict__ res,
-                        GnP rp, int res_is_prenorm, __nv_bfloat16* __restrict__ out, int B, int hw) {
+                        GnP rp, int res_is_prenorm, __nv_bfloat16* __restrict__ out, int B, int hw, int ppb) {
+  const GnSlab t = gn_slab(p.C, hw, ppb);
   const int cv = p.C >> 3;
-  const long long total = (long long)B * hw * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cv) << 3;
-    const int b = (int)(i / ((long long)hw * cv));
-    float mu[8], rs[8], x[8], ga[8], be[8], r[8];
-    gn_coeffs(p, b, c0, mu, rs);
+  float mu[8], rs[8], ga[8], be[8], sc[8], sh[8], rsc[8], rsh[8];
+  gn_coeffs(p, t.b, t.c0, mu, rs);
+  load8f(p.gamma + t.c0, ga);
+  load8f(p.beta + t.c0, be);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sc[e] = rs[e] * ga[e]; sh[e] = fmaf(-mu[e], sc[e], be[e]); rsc[e] = 1.f; rsh[e] = 0.f; }
+  if (res_is_prenorm) {
+    gn_coeffs(rp, t.b, t.c0, mu, rs);
+    load8f(rp.gamma + t.c0, ga);
+    load8f(rp.beta + t.c0, be);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { rsc[e] = rs[e] * ga[e]; rsh[e] = fmaf(-mu[e], rsc[e], be[e]); }
+  }
+  for (int pix = t.pix0 + t.pl; pix < t.pix1; pix += t.npl) {
+    const size_t i = ((size_t)t.b * hw + pix) * cv + t.vec;
+    float x[8], r[8];
     unpack8(reinterpret_cast<const uint4*>(y)[i], x);
     unpack8(reinterpret_cast<const uint4*>(res)[i], r);
-    load8f(p.gamma + c0, ga);
-    load8f(p.beta + c0, be);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] = fmaf((x[e] - mu[e]) * rs[e], ga[e], be[e]);
-    if (res_is_prenorm) {
-      gn_coeffs(rp, b, c0, mu, rs);
-      load8f(rp.gamma + c0, ga);
-      load8f(rp.beta + c0, be);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) r[e] = fmaf((r[e] - mu[e]) * rs[e], ga[e], be[e]);
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e] + r[e], 0.f);
+    for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], sc[e], sh[e]) + fmaf(r[e], rsc[e], rsh[e]), 0.f);
     reinterpret_cast<uint4*>(out)[i] = pack8(x);
   }
 }
@@ -442,17 +462,24 @@ __global__ void __launch_bounds__(256)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act,
                     const __nv_bfloat16* __restrict__ y, GnP p, const float* __restrict__ sums,
                     __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ gz_out, int B, int hw,
-                    int mask_mode) {
+                    int mask_mode, int ppb) {
+  const GnSlab t = gn_slab(p.C, hw, ppb);
   const int cv = p.C >> 3;
-  const long long total = (long long)B * hw * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % cv) << 3;
-    const int b = (int)(i / ((long long)hw * cv));
-    float mu[8], rs[8], ga[8], be[8], gg[8], x[8], z[8], ac[8], gz[8], o[8];
-    gn_coeffs(p, b, c0, mu, rs);
-    load8f(p.gamma + c0, ga);
-    load8f(p.beta + c0, be);
+  float mu[8], rs[8], ga[8], be[8], k1[8], k2[8], k3[8];
+  gn_coeffs(p, t.b, t.c0, mu, rs);
+  load8f(p.gamma + t.c0, ga);
+  load8f(p.beta + t.c0, be);
+  // dy = rs*ga*gz - rs*inv_m*S1 - xhat * rs*inv_m*S2
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float2 sm = *reinterpret_cast<const float2*>(sums + ((size_t)t.b * p.G + ((t.c0 + e) >> p.lcpg)) * 2);
+    k1[e] = rs[e] * ga[e];
+    k2[e] = rs[e] * p.inv_m * sm.x;
+    k3[e] = rs[e] * p.inv_m * sm.y;
+  }
+  for (int pix = t.pix0 + t.pl; pix < t.pix1; pix += t.npl) {
+    const size_t i = ((size_t)t.b * hw + pix) * cv + t.vec;
+    float gg[8], x[8], z[8], ac[8], gz[8], o[8];
     unpack8(reinterpret_cast<const uint4*>(g)[i], gg);
     unpack8(reinterpret_cast<const uint4*>(y)[i], x);
     if (mask_mode == 2) unpack8(reinterpret_cast<const uint4*>(act)[i], ac);
@@ -464,10 +491,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
     }
     gn_masked_grad(mask_mode, gg, z, ac, gz);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float2 s = *reinterpret_cast<const float2*>(sums + ((size_t)b * p.G + ((c0 + e) >> p.lcpg)) * 2);
-      o[e] = rs[e] * (ga[e] * gz[e] - (s.x + x[e] * s.y) * p.inv_m);
-    }
+    for (int e = 0; e < 8; ++e) o[e] = fmaf(k1[e], gz[e], -fmaf(x[e], k3[e], k2[e]));
     reinterpret_cast<uint4*>(dy)[i] = pack8(o);
     if (gz_out) reinterpret_cast<uint4*>(gz_out)[i] = pack8(gz);
   }
@@ -630,6 +654,18 @@ __global__ void heads_fwd_kernel(const float* __restrict__ feat, const float* __
   }
 }
 
+// block = (frame, slab of ppb pixels); 256 threads = (C/8 vectors) x (pixel lanes)
+static int gn_slab_launch(int C, int hw, int B, int* ppb, int* grid) {
+  const int cv = C / 8;
+  HB_CHECK_ARG(cv >= 1 && cv <= 256 && 256 % cv == 0, "gn: C/8 = %d must divide 256", cv);
+  const int npl = 256 / cv;
+  int p = npl * 8;  // ~8 pixels per thread
+  if (p > hw) p = hw;
+  *ppb = p;
+  *grid = B * ((hw + p - 1) / p);
+  return HB200_OK;
+}
+
 static int ilog2i(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -725,13 +761,15 @@ extern "C" int hb200_gn_apply(const hb200_bf16* y, const float* stats, const flo
   int rc = make_gn(p, stats, gamma, beta, channels, groups, hw, eps);
   if (rc) return rc;
   HB_CHECK_ARG(y && out, "gn_apply: null pointer");
-  const long long total = (long long)batch * hw * (channels / 8);
+  int ppb = 0, grid = 0;
+  rc = gn_slab_launch(channels, hw, batch, &ppb, &grid);
+  if (rc) return rc;
   if (out_f32 == 1)
-    gn_apply_kernel<1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
+    gn_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu, ppb);
   else if (out_f32 == 2)
-    gn_apply_kernel<2><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
+    gn_apply_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu, ppb);
   else
-    gn_apply_kernel<0><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu);
+    gn_apply_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu, ppb);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -751,9 +789,11 @@ extern "C" int hb200_gn_residual_relu(const hb200_bf16* y, const float* stats, c
     rc = make_gn(rp, res_stats, res_gamma, res_beta, channels, groups, hw, eps);
     if (rc) return rc;
   }
-  const long long total = (long long)batch * hw * (channels / 8);
-  gn_residual_relu_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)y, p, (const __nv_bfloat16*)res, rp, res_stats ? 1 : 0, (__nv_bfloat16*)out, batch, hw);
+  int ppb = 0, grid = 0;
+  rc = gn_slab_launch(channels, hw, batch, &ppb, &grid);
+  if (rc) return rc;
+  gn_residual_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)y, p, (const __nv_bfloat16*)res, rp, res_stats ? 1 : 0, (__nv_bfloat16*)out, batch, hw, ppb);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -821,10 +861,12 @@ extern "C" int hb200_gn_bwd_apply(const hb200_bf16* g, const hb200_bf16* act, co
   if (rc) return rc;
   HB_CHECK_ARG(g && y && sums && dy, "gn_bwd_apply: null pointer");
   HB_CHECK_ARG(mask_mode >= 0 && mask_mode <= 2 && (mask_mode != 2 || act), "gn_bwd_apply: bad mask_mode");
-  const long long total = (long long)batch * hw * (channels / 8);
-  gn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  int ppb = 0, grid = 0;
+  rc = gn_slab_launch(channels, hw, batch, &ppb, &grid);
+  if (rc) return rc;
+  gn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)g, (const __nv_bfloat16*)act, (const __nv_bfloat16*)y, p, sums,
-      (__nv_bfloat16*)dy, (__nv_bfloat16*)gz_out, batch, hw, mask_mode);
+      (__nv_bfloat16*)dy, (__nv_bfloat16*)gz_out, batch, hw, mask_mode, ppb);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;

@@ -216,8 +216,45 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
   __syncthreads();
 }
 
+// transpose-reduce: every lane holds 16 partial sums v[r]; returns in lane l the full warp sum of
+// row (l >> 1)  (16 shuffles instead of 16 x 5)
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+  float a[8];
+  const bool b4 = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? v[i] : v[i + 8];
+    const float keep = b4 ? v[i + 8] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float b[4];
+  const bool b3 = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? a[i] : a[i + 4];
+    const float keep = b3 ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float c[2];
+  const bool b2 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? b[i] : b[i + 2];
+    const float keep = b2 ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const bool b1 = lane & 2;
+  const float send = b1 ? c[0] : c[1];
+  const float keep = b1 ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+
+constexpr int kSeqThreads = 1024;  // one warp per sequence (n <= 32 in one pass)
+
 template <int NJ>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSeqThreads)
 lstm_seq_fwd_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh,
                     const float* __restrict__ b_hh, const uint8_t* __restrict__ masks,
                     const float* __restrict__ h0, long long h0_stride, const float* __restrict__ c0,
@@ -231,43 +268,39 @@ lstm_seq_fwd_kernel(const float* __restrict__ xproj, const float* __restrict__ w
     sw[i] = w_hh[((size_t)(r >> 2) * H + u0 + (r & 3)) * H + k];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float bi = 0, bf_ = 0, bg = 0, bo = 0;
-  if (b_hh && lane < kUnits) {
-    const int col = u0 + lane;
-    bi = b_hh[col]; bf_ = b_hh[H + col]; bg = b_hh[2 * H + col]; bo = b_hh[3 * H + col];
-  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // lane l finishes gate row (l >> 1): row = gate * 4 + unit
+  const int row = lane >> 1, gate = row >> 2, unit = row & 3, col = u0 + unit;
+  const float bias = b_hh ? b_hh[(size_t)gate * H + col] : 0.f;
   for (int t = 0; t < T; ++t) {
     const float* hp = t == 0 ? h0 : hs + (size_t)(t - 1) * n * H;
     const long long hps = t == 0 ? h0_stride : H;
     const float* cp = t == 0 ? c0 : cs + (size_t)(t - 1) * n * H;
     const long long cps = t == 0 ? c0_stride : H;
-    for (int s = warp; s < n; s += 8) {
+    for (int s = warp; s < n; s += nwarps) {
       const float m = masks[(size_t)t * n + s] ? 1.f : 0.f;
       float hv[NJ];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) hv[j] = __ldcg(hp + (size_t)s * hps + lane + 32 * j) * m;
-      float dot[16];
+      for (int j = 0; j < NJ; ++j) hv[j] = __ldcg(hp + (size_t)s * hps + lane + 32 * j);
+      const float xp = xproj[((size_t)t * n + s) * 4 * H + (size_t)gate * H + col];
+      const float cprev = __ldcg(cp + (size_t)s * cps + col);
+      float part[16];
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         float acc = 0.f;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc = fmaf(hv[j], sw[r * H + lane + 32 * j], acc);
-        dot[r] = warp_sum(acc);
+        part[r] = acc;
       }
-      float gi = 0, gf = 0, gg = 0, go = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (lane == u) { gi = dot[u]; gf = dot[4 + u]; gg = dot[8 + u]; go = dot[12 + u]; }
-      if (lane < kUnits) {
-        const int col = u0 + lane;
-        const float* xp = xproj + ((size_t)t * n + s) * 4 * H;
-        const float i_ = sigmoidf_(gi + bi + xp[col]);
-        const float f_ = sigmoidf_(gf + bf_ + xp[H + col]);
-        const float g_ = tanhf(gg + bg + xp[2 * H + col]);
-        const float o_ = sigmoidf_(go + bo + xp[3 * H + col]);
-        const float cin = __ldcg(cp + (size_t)s * cps + col) * m;
-        const float cn = f_ * cin + i_ * g_;
+      const float pre = warp_reduce16(part, lane) * m + bias + xp;  // (h*m) . w == m * (h . w)
+      const float act = (gate == 2) ? tanhf(pre) : sigmoidf_(pre);
+      // gather the four gates of this lane's unit: rows unit, 4+unit, 8+unit, 12+unit -> lanes 2*row
+      const float i_ = __shfl_sync(0xffffffffu, act, 2 * unit);
+      const float f_ = __shfl_sync(0xffffffffu, act, 2 * (4 + unit));
+      const float g_ = __shfl_sync(0xffffffffu, act, 2 * (8 + unit));
+      const float o_ = __shfl_sync(0xffffffffu, act, 2 * (12 + unit));
+      if (lane < 8 && (lane & 1) == 0) {  // lanes 0,2,4,6 own units 0..3
+        const float cn = f_ * (cprev * m) + i_ * g_;
         const size_t o = ((size_t)t * n + s) * H + col;
         cs[o] = cn;
         hs[o] = o_ * tanhf(cn);
@@ -284,24 +317,24 @@ lstm_seq_fwd_kernel(const float* __restrict__ xproj, const float* __restrict__ w
 // backward through time for one layer.  CTA = 4 hidden units: pointwise for its units (dh_rec /
 // dc_rec of those units never leave the CTA), publishes its 16 dgates columns, barrier, then its 4
 // columns of dh_{t-1} = m_t * dgates_t W_hh  with W_hh^T[:, 4 cols] resident in shared memory.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kSeqThreads)
 lstm_seq_bwd_kernel(const float* __restrict__ dh_out, const float* __restrict__ gates,
                     const float* __restrict__ cs, const float* __restrict__ c0, long long c0_stride,
                     const float* __restrict__ w_hh, const uint8_t* __restrict__ masks,
                     float* __restrict__ dgates, int T, int n, int H, unsigned* counter) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int R = 4 * H;
-  float* wt = smem;                 // [R][4]
+  float* wt = smem;                 // [4][R]  (unit-major: conflict-free float4 reads along r)
   float* dh_rec = smem + 4 * R;     // [n][4]
   float* dc_rec = dh_rec + 4 * n;   // [n][4]
   const int u0 = blockIdx.x * kUnits;
   for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) {
-    const int r = i >> 2, u = i & 3;
+    const int u = i / R, r = i - u * R;
     wt[i] = w_hh[(size_t)r * H + u0 + u];
   }
   for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) { dh_rec[i] = 0.f; dc_rec[i] = 0.f; }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int t = T - 1; t >= 0; --t) {
     // ---- pointwise for own units
     for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) {
@@ -323,14 +356,31 @@ lstm_seq_bwd_kernel(const float* __restrict__ dh_out, const float* __restrict__ 
     }
     if (t == 0) break;
     grid_barrier(counter, (unsigned)(T - t) * gridDim.x);
-    // ---- dh_{t-1}[s, own 4 cols] = m_t[s] * sum_r dgates_t[s, r] * W_hh[r, col]
-    for (int s = warp; s < n; s += 8) {
-      const float* dg = dgates + ((size_t)t * n + s) * R;
+    // ---- dh_{t-1}[s, own 4 cols] = m_t[s] * sum_r dgates_t[s, r] * W_hh[r, col]; one warp per sequence
+    for (int s = warp; s < n; s += nwarps) {
+      const float4* dg4 = reinterpret_cast<const float4*>(dgates + ((size_t)t * n + s) * R);
       float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      for (int r = lane; r < R; r += 32) {
-        const float d = __ldcg(dg + r);
-        const float4 w = *reinterpret_cast<const float4*>(wt + 4 * r);
-        a0 = fmaf(d, w.x, a0); a1 = fmaf(d, w.y, a1); a2 = fmaf(d, w.z, a2); a3 = fmaf(d, w.w, a3);
+      for (int g0 = 0; g0 < R / 4; g0 += 32 * 4) {  // 4 independent 16-byte loads in flight per lane
+        float4 d[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int g = g0 + q * 32 + lane;
+          d[q] = (g < R / 4) ? __ldcg(dg4 + g) : make_float4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int g = g0 + q * 32 + lane;
+          if (g < R / 4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wt + 0 * R + 4 * g);
+            const float4 w1 = *reinterpret_cast<const float4*>(wt + 1 * R + 4 * g);
+            const float4 w2 = *reinterpret_cast<const float4*>(wt + 2 * R + 4 * g);
+            const float4 w3 = *reinterpret_cast<const float4*>(wt + 3 * R + 4 * g);
+            a0 += d[q].x * w0.x + d[q].y * w0.y + d[q].z * w0.z + d[q].w * w0.w;
+            a1 += d[q].x * w1.x + d[q].y * w1.y + d[q].z * w1.z + d[q].w * w1.w;
+            a2 += d[q].x * w2.x + d[q].y * w2.y + d[q].z * w2.z + d[q].w * w2.w;
+            a3 += d[q].x * w3.x + d[q].y * w3.y + d[q].z * w3.z + d[q].w * w3.w;
+          }
+        }
       }
       a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
       if (lane == 0) {
@@ -382,9 +432,9 @@ extern "C" int hb200_lstm_seq_fwd(const float* xproj, const float* w_hh, const f
     default: kern = (const void*)lstm_seq_fwd_kernel<16>; break;
   }
   if (smem > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int rc = coop_check(kern, 256, smem, grid);
+  int rc = coop_check(kern, kSeqThreads, smem, grid);
   if (rc) return rc;
-  HB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, smem, st));
+  HB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kSeqThreads), args, smem, st));
   count_launch(1);
   return HB200_OK;
 }
@@ -403,11 +453,11 @@ extern "C" int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const
   const int grid = hidden / kUnits;
   const void* kern = (const void*)lstm_seq_bwd_kernel;
   if (smem > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int rc = coop_check(kern, 256, smem, grid);
+  int rc = coop_check(kern, kSeqThreads, smem, grid);
   if (rc) return rc;
   void* args[] = {(void*)&dh_out, (void*)&gates, (void*)&cs, (void*)&c0, (void*)&c0_stride, (void*)&w_hh,
                   (void*)&masks, (void*)&dgates, (void*)&t_steps, (void*)&n, (void*)&hidden, (void*)&counter};
-  HB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, smem, st));
+  HB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kSeqThreads), args, smem, st));
   count_launch(1);
   return HB200_OK;
 }

@@ -65,7 +65,8 @@ template <int AMODE, int BMODE>
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ a, long long a_ms, long long a_ks, const float* __restrict__ b,
              long long b_ks, long long b_ns, float* __restrict__ c, long long ldc,
-             const float* __restrict__ bias, int M, int N, int K, float alpha, int accumulate, int relu) {
+             const float* __restrict__ bias, int M, int N, int K, float alpha, int accumulate, int relu,
+             int k_per_split) {
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -76,9 +77,11 @@ sgemm_kernel(const float* __restrict__ a, long long a_ms, long long a_ks, const 
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    load_tile<AMODE>(a, a_ms, a_ks, m0, k0, M, K, As);
-    load_tile<BMODE>(b, b_ns, b_ks, n0, k0, N, K, Bs);
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+    load_tile<AMODE>(a, a_ms, a_ks, m0, k0, M, k_end, As);
+    load_tile<BMODE>(b, b_ns, b_ks, n0, k0, N, k_end, Bs);
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
@@ -105,8 +108,13 @@ sgemm_kernel(const float* __restrict__ a, long long a_ms, long long a_ks, const 
       const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
       if (n >= N) continue;
       float v = alpha * acc[i][j];
-      if (bias) v += bias[n];
       float* dst = c + (long long)m * ldc + n;
+      if (gridDim.z > 1) {  // split-K: partial sums meet in a pre-zeroed (or accumulated-into) C
+        if (bias && blockIdx.z == 0) v += bias[n];
+        atomicAdd(dst, v);
+        continue;
+      }
+      if (bias) v += bias[n];
       if (accumulate) v += *dst;
       if (relu) v = fmaxf(v, 0.f);
       *dst = v;
@@ -121,12 +129,25 @@ extern "C" int hb200_sgemm(const float* a, long long a_ms, long long a_ks, const
                            long long b_ns, float* c, long long ldc, const float* bias, int m, int n, int k,
                            float alpha, int accumulate, int relu, hb200_stream_t stream) {
   HB_CHECK_ARG(a && b && c && m > 0 && n > 0 && k > 0, "sgemm: bad args");
+  // split-K when the output tile grid cannot fill the GPU and the reduction is long (weight gradients:
+  // K = frames).  Needs C to hold the value to accumulate into -> only in accumulate mode without ReLU.
+  int splits = 1;
+  {
+    const long long tiles = (long long)cdiv(n, BN) * cdiv(m, BM);
+    if (accumulate && !relu && tiles < kNumSMs && k >= 1024) {
+      splits = (int)((2 * kNumSMs + tiles - 1) / tiles);
+      if (splits > k / 256) splits = k / 256;
+      if (splits < 1) splits = 1;
+    }
+  }
+  int k_per_split = ((cdiv(k, splits) + BK - 1) / BK) * BK;
+  splits = cdiv(k, k_per_split);
   const int am = (a_ms == 1) ? 0 : (a_ks == 1 ? 1 : 2);
   const int bm = (b_ns == 1) ? 0 : (b_ks == 1 ? 1 : 2);
-  dim3 grid(cdiv(n, BN), cdiv(m, BM));
+  dim3 grid(cdiv(n, BN), cdiv(m, BM), splits);
   cudaStream_t st = (cudaStream_t)stream;
 #define HB_SG(AM, BMO) \
-  sgemm_kernel<AM, BMO><<<grid, 256, 0, st>>>(a, a_ms, a_ks, b, b_ks, b_ns, c, ldc, bias, m, n, k, alpha, accumulate, relu)
+  sgemm_kernel<AM, BMO><<<grid, 256, 0, st>>>(a, a_ms, a_ks, b, b_ks, b_ns, c, ldc, bias, m, n, k, alpha, accumulate, relu, k_per_split)
   switch (am * 3 + bm) {
     case 0: HB_SG(0, 0); break;
     case 1: HB_SG(0, 1); break;

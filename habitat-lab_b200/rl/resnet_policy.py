@@ -766,10 +766,10 @@ class PointNavResNetPolicy(nn.Module):
                              self._tmp("rnn_ws", (64,), dev, torch.uint8))
             dgf = dg.view(B, 4 * H)
             x = ly["x"]
-            ops.linear_bwd_weight(dgf, x, w_ih.grad)
+            ops.linear_bwd_weight(dgf, x, w_ih.grad, accumulate=True)  # grads are pre-zeroed: enables split-K
             hin = self._tmp("hin", (T, n, H), dev)
             ops.rnn_shift_mask(ly["hs"], ly["h0"], mk, hin, T, n, H)
-            ops.linear_bwd_weight(dgf, hin.view(B, H), w_hh.grad)
+            ops.linear_bwd_weight(dgf, hin.view(B, H), w_hh.grad, accumulate=True)
             ops.colsum(dgf, b_ih.grad)
             b_hh.grad.copy_(b_ih.grad)
             dx = self._tmp(f"dx{l}", (B, x.shape[1]), dev)
@@ -785,7 +785,7 @@ class PointNavResNetPolicy(nn.Module):
         ops.relu_bwd(d_rnn_in, s["rnn_in"], H)
         dvis = d_rnn_in[:, :H]
         ops.sgemm(dvis, 1, dvis.stride(0), s["feat"], s["feat"].stride(0), 1, fc.weight.grad, fc.weight.grad.stride(0),
-                  H, s["feat"].shape[1], B)
+                  H, s["feat"].shape[1], B, accumulate=True)
         ops.colsum(dvis, fc.bias.grad, n_cols=H)
         d_feat = self._tmp("d_feat", tuple(s["feat"].shape), dev)
         ops.sgemm(dvis, dvis.stride(0), 1, fc.weight, fc.weight.stride(0), 1, d_feat, d_feat.stride(0), B,

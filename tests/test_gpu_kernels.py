@@ -575,12 +575,13 @@ def test_lstm_masked_recurrence(hb, T, n, H, D):
     assert diff < 1e-3, diff
     torch.testing.assert_close(hs[-1].cpu(), hid_ref[:, 0].detach(), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(cs[-1].cpu(), hid_ref[:, 1].detach(), rtol=1e-4, atol=1e-5)
-    # persistent whole-sequence kernel must reproduce the per-step kernel bit for bit
+    # persistent whole-sequence kernel (different reduction tree) must agree with the per-step kernel
     ws = torch.zeros(64, dtype=torch.uint8, device=DEV)
     hs2, cs2, gates2 = torch.empty_like(hs), torch.empty_like(cs), torch.empty_like(gates)
     ops.lstm_seq_fwd(xproj, w_hh, None, md, h0, c0, hs2, cs2, gates2, T, n, H, ws)
     torch.cuda.synchronize()
-    assert torch.equal(hs2, hs) and torch.equal(cs2, cs) and torch.equal(gates2, gates)
+    for a_, b_ in ((hs2, hs), (cs2, cs), (gates2, gates)):
+        torch.testing.assert_close(a_, b_, rtol=1e-5, atol=1e-6)
     dg2 = torch.empty(T, n, 4 * H, device=DEV)
     ops.lstm_seq_bwd(d(gout).view(T, n, H), gates, cs, c0, w_hh, md, dg2, T, n, H, ws)
     # backward through time
