@@ -51,6 +51,7 @@ struct ConvArgs {
   int OH, OW, OC;     // output grid and channels
   int kh, kw, stride, pad;
   int M, nchunks, cshift, gn_groups;
+  int s2_classes;  // dgrad of a stride-2 conv: rows are grouped by output-pixel parity class (4 x M/4)
 };
 
 template <int BN, int MODE, int LAYOUT>
@@ -65,9 +66,52 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m = blockIdx.x * kTileM + tid;
   const int n0 = blockIdx.y * BN;
-  const bool row_ok = m < a.M;
+  __shared__ int chunk_ids[64];
+  __shared__ int n_valid_s;
+  // ---- row -> output pixel.  Stride-2 dgrad: tiles are grouped by the parity class (ph, pw) of the
+  // output pixel, because a class only ever touches the filter taps with r = ph+pad (mod 2),
+  // s = pw+pad (mod 2): the other ~3/4 of the K chunks are skipped instead of multiplied by zeros.
+  int m, ob, op, oq, ph = 0, pw = 0;
+  bool row_ok;
+  if (MODE == 1 && a.s2_classes) {
+    const int mq = a.M >> 2;                                   // rows per class
+    const int tiles_per_class = (mq + kTileM - 1) / kTileM;
+    const int cls = blockIdx.x / tiles_per_class;
+    const int idx = (blockIdx.x - cls * tiles_per_class) * kTileM + tid;
+    ph = cls >> 1; pw = cls & 1;
+    row_ok = idx < mq;
+    const int h2 = a.OH >> 1, w2 = a.OW >> 1;
+    const int ii = row_ok ? idx : 0;
+    ob = ii / (h2 * w2);
+    const int rem = ii - ob * (h2 * w2);
+    op = 2 * (rem / w2) + ph;
+    oq = 2 * (rem % w2) + pw;
+    m = (ob * a.OH + op) * a.OW + oq;
+  } else {
+    m = blockIdx.x * kTileM + tid;
+    row_ok = m < a.M;
+    const int hw = a.OH * a.OW;
+    const int mm = row_ok ? m : 0;
+    ob = mm / hw;
+    const int rem = mm - ob * hw;
+    op = rem / a.OW;
+    oq = rem - op * a.OW;
+  }
+  if (tid == 0) {
+    int nv = 0;
+    const int cpt = a.SC >> 6;  // 64-channel chunks per tap (>= 1 in class mode)
+    for (int c = 0; c < a.nchunks && nv < 64; ++c) {
+      bool ok = true;
+      if (MODE == 1 && a.s2_classes) {
+        const int tap = c / cpt;
+        const int r = tap / a.kw, sx = tap - r * a.kw;
+        ok = tap < a.kh * a.kw && (((ph + a.pad - r) & 1) == 0) && (((pw + a.pad - sx) & 1) == 0);
+      }
+      if (ok) chunk_ids[nv++] = c;
+    }
+    n_valid_s = nv;
+  }
 
   if (tid == 0) {
 #pragma unroll
@@ -79,17 +123,7 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-
-  // output-grid coordinates of this thread's row
-  int ob, op, oq;
-  {
-    const int hw = a.OH * a.OW;
-    const int mm = row_ok ? m : 0;
-    ob = mm / hw;
-    const int rem = mm - ob * hw;
-    op = rem / a.OW;
-    oq = rem - op * a.OW;
-  }
+  const int n_valid = n_valid_s;
   const int taps = a.kh * a.kw;
   const __nv_bfloat16* wtile = a.wimg + (size_t)blockIdx.y * a.nchunks * (BN * kChunkK);
 
@@ -131,10 +165,10 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
   // ---- software pipeline: cp.async runs kStages-1 chunks ahead of the tensor core ----
 #pragma unroll
   for (int c = 0; c < kStages - 1; ++c) {
-    if (c < a.nchunks) load_chunk(c, c);
+    if (c < n_valid) load_chunk(chunk_ids[c], c);
     cp_async_commit();
   }
-  for (int c = 0; c < a.nchunks; ++c) {
+  for (int c = 0; c < n_valid; ++c) {
     const int stage = c % kStages;
     cp_async_wait<kStages - 2>();
     fence_proxy_async_smem();
@@ -150,14 +184,14 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
       mma_commit(&mma_bar[stage]);
     }
     const int nc = c + kStages - 1;
-    if (nc < a.nchunks) {
+    if (nc < n_valid) {
       if (c >= 1) mbar_wait(&mma_bar[(c - 1) % kStages], ((c - 1) / kStages) & 1);
-      load_chunk(nc, nc % kStages);
+      load_chunk(chunk_ids[nc], nc % kStages);
     }
     cp_async_commit();
   }
-  {
-    const int last = a.nchunks - 1;
+  if (n_valid > 0) {
+    const int last = n_valid - 1;
     mbar_wait(&mma_bar[last % kStages], (last / kStages) & 1);
   }
   fence_after_sync();
@@ -169,12 +203,17 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
   if ((hw & (hw - 1)) == 0) seg = hw < 32 ? hw : 32;
 #pragma unroll 1
   for (int col0 = 0; col0 < BN; col0 += 32) {
-    uint32_t r[32];
-    tmem_ld32(taddr + col0, r);
-    tmem_ld_wait();
     float acc[32];
+    if (n_valid > 0) {
+      uint32_t r[32];
+      tmem_ld32(taddr + col0, r);
+      tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    }
 
     if (MODE == 0 && a.stats != nullptr) {
       const int cpg = a.OC / a.gn_groups;  // channels per group (power of two >= 2)
@@ -553,7 +592,7 @@ static int pick_bn(int n) { return n >= 256 ? 256 : n; }
 
 template <int MODE>
 static int launch_igemm(const ConvArgs& a, int BN, cudaStream_t st) {
-  dim3 grid(cdiv(a.M, kTileM), a.OC / BN);
+  dim3 grid(a.s2_classes ? 4 * cdiv(a.M / 4, kTileM) : cdiv(a.M, kTileM), a.OC / BN);
   const size_t smem = (size_t)kStages * (kTileM * kChunkK * 2 + BN * kChunkK * 2) + 1024;
 #define HB_CONV_CASE(bn, L)                                                                     \
   {                                                                                             \
@@ -622,6 +661,7 @@ extern "C" int hb200_conv_fwd(const hb200_bf16* x, const hb200_bf16* w_packed, h
   a.nchunks = cdiv((long long)s->kh * s->kw * s->ci, kChunkK);
   a.cshift = ilog2(s->ci);
   a.gn_groups = gn_groups > 0 ? gn_groups : 1;
+  a.s2_classes = 0;
   return launch_igemm<0>(a, pick_bn(s->co), (cudaStream_t)stream);
 }
 
@@ -642,6 +682,7 @@ extern "C" int hb200_conv_dgrad(const hb200_bf16* dy, const hb200_bf16* w_packed
   a.nchunks = cdiv((long long)s->kh * s->kw * s->co, kChunkK);
   a.cshift = ilog2(s->co);
   a.gn_groups = 1;
+  a.s2_classes = (s->stride == 2 && s->co >= 64 && (s->hi % 2 == 0) && (s->wi % 2 == 0)) ? 1 : 0;
   return launch_igemm<1>(a, pick_bn(s->ci), (cudaStream_t)stream);
 }
 

@@ -1,0 +1,300 @@
+"""PPOTrainer ("ppo" / "ddppo") on the hb200 classes: the rollout loop, DD-PPO's preemption rule,
+`_update_agent` and the post-update coalescing of habitat-baselines' trainer
+(habitat-baselines/habitat_baselines/rl/ppo/ppo_trainer.py:172-292, 343-557, 641-801), with the
+simulator replaced by an in-process synthetic VectorEnv that hands back DEVICE-resident observations
+(the drop-in seam is `vector_env_factory._target_`).
+
+The config is attribute-style (OmegaConf / SimpleNamespace / the dataclasses below) with the
+reference's field names, so a Hydra-composed `habitat_baselines` config is accepted unchanged.
+"""
+from __future__ import annotations
+
+import collections
+import math
+import time
+from dataclasses import dataclass, field
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from ..common.baseline_registry import baseline_registry
+from ..common.rollout_storage import RolloutStorage
+from ..common.tensor_dict import TensorDict
+from ..synthetic import pointnav_spaces
+from .ppo import DDPPO, PPO
+from .resnet_policy import PointNavResNetPolicy
+
+
+# ---- config (field names and defaults: habitat_baselines/config/default_structured_configs.py:288-363) ----
+@dataclass
+class PPOConfig:
+    clip_param: float = 0.2
+    ppo_epoch: int = 4
+    num_mini_batch: int = 2
+    value_loss_coef: float = 0.5
+    entropy_coef: float = 0.01
+    lr: float = 2.5e-4
+    eps: float = 1e-5
+    max_grad_norm: float = 0.5
+    num_steps: int = 5
+    use_gae: bool = True
+    use_linear_lr_decay: bool = False
+    use_linear_clip_decay: bool = False
+    gamma: float = 0.99
+    tau: float = 0.95
+    reward_window_size: int = 50
+    use_normalized_advantage: bool = False
+    hidden_size: int = 512
+    entropy_target_factor: float = 0.0
+    use_adaptive_entropy_pen: bool = False
+    use_clipped_value_loss: bool = True
+    use_double_buffered_sampler: bool = False
+
+
+@dataclass
+class DDPPOConfig:
+    sync_frac: float = 0.6
+    distrib_backend: str = "NCCL"
+    rnn_type: str = "LSTM"
+    num_recurrent_layers: int = 2
+    backbone: str = "resnet18"
+    force_distributed: bool = False
+
+
+def make_config(num_environments=4, total_num_steps=-1.0, num_updates=2, height=256, width=256, seed=100, **ppo_kw):
+    """A habitat_baselines-shaped config for the synthetic PointNav DD-PPO run (ddppo_pointnav.yaml values)."""
+    ppo = PPOConfig(**{**dict(ppo_epoch=2, num_mini_batch=2, num_steps=128, max_grad_norm=0.2), **ppo_kw})
+    hb = SimpleNamespace(
+        trainer_name="ddppo", updater_name="PPO", distrib_updater_name="DDPPO", rollout_storage_name="RolloutStorage",
+        num_environments=num_environments, total_num_steps=total_num_steps, num_updates=num_updates,
+        log_interval=10, force_blind_policy=False,
+        rl=SimpleNamespace(ppo=ppo, ddppo=DDPPOConfig(), policy={"main_agent": SimpleNamespace(
+            name="PointNavResNetPolicy", action_distribution_type="categorical")}),
+        eval=SimpleNamespace(extra_sim_sensors={}),
+    )
+    habitat = SimpleNamespace(seed=seed, simulator=SimpleNamespace(agents_order=["main_agent"]),
+                              synthetic=SimpleNamespace(height=height, width=width, p_done=1.0 / 250.0))
+    return SimpleNamespace(habitat_baselines=hb, habitat=habitat)
+
+
+# ---- synthetic VectorEnv ------------------------------------------------------------------------------
+class SyntheticVectorEnv:
+    """VectorEnv-shaped source of synthetic RGB-D PointNav observations born on the device
+    (method surface: habitat/core/vector_env.py as used by ppo_trainer.py:136-157, 266-267, 388, 409-419)."""
+
+    def __init__(self, num_envs, obs_space, act_space, device, seed, p_done):
+        self.num_envs = num_envs
+        self.observation_spaces = [obs_space] * num_envs
+        self.action_spaces = [act_space] * num_envs
+        self.orig_action_spaces = self.action_spaces
+        self.device = device
+        self.gen = torch.Generator(device=device).manual_seed(seed)
+        self.p_done = p_done
+        self._pending = None
+
+    def _obs(self):
+        sp = self.observation_spaces[0].spaces
+        out = {}
+        n, d, g = self.num_envs, self.device, self.gen
+        if "rgb" in sp:
+            out["rgb"] = torch.randint(0, 256, (n, *sp["rgb"].shape), generator=g, device=d, dtype=torch.uint8)
+        if "depth" in sp:
+            out["depth"] = torch.rand((n, *sp["depth"].shape), generator=g, device=d)
+        goal = torch.rand(n, 2, generator=g, device=d)
+        goal[:, 0] *= 10.0
+        goal[:, 1] = goal[:, 1] * 2 * math.pi - math.pi
+        out["pointgoal_with_gps_compass"] = goal
+        return out
+
+    def reset(self):
+        return self._obs()
+
+    def step(self, actions):
+        """Batched step: (obs dict, rewards [N,1], dones [N] bool, infos)."""
+        n, d, g = self.num_envs, self.device, self.gen
+        dones = torch.rand(n, generator=g, device=d) < self.p_done
+        rewards = torch.randn(n, 1, generator=g, device=d) * 0.1 + 2.5 * dones.float().view(n, 1)
+        return self._obs(), rewards, dones, [{} for _ in range(n)]
+
+    def close(self):
+        pass
+
+
+class SyntheticVectorEnvFactory:
+    """Drop-in for `habitat_baselines.vector_env_factory._target_` (common/env_factory.py contract)."""
+
+    def construct_envs(self, config, workers_ignore_signals=False, enforce_scenes_greater_eq_environments=False,
+                       is_first_rank=True, device=None, rank=0):
+        syn = config.habitat.synthetic
+        obs_space, act_space = pointnav_spaces(syn.height, syn.width)
+        n = config.habitat_baselines.num_environments
+        return SyntheticVectorEnv(n, obs_space, act_space, device, config.habitat.seed + rank * n, syn.p_done)
+
+
+# ---- the trainer -------------------------------------------------------------------------------------------
+@baseline_registry.register_trainer(name="ddppo")
+@baseline_registry.register_trainer(name="ppo")
+class PPOTrainer:
+    SHORT_ROLLOUT_THRESHOLD: float = 0.25  # ppo_trainer.py:78
+
+    def __init__(self, config=None):
+        self.config = config
+        self.num_updates_done = 0
+        self.num_steps_done = 0
+        self._is_distributed = torch.distributed.is_available() and torch.distributed.is_initialized()
+        self._last_fps = 0.0
+        self.timings = collections.defaultdict(float)
+
+    # -- helpers mirroring BaseRLTrainer (common/base_trainer.py:226-267)
+    def percent_done(self) -> float:
+        hb = self.config.habitat_baselines
+        if hb.num_updates != -1:
+            return self.num_updates_done / hb.num_updates
+        return self.num_steps_done / hb.total_num_steps
+
+    def is_done(self) -> bool:
+        return self.percent_done() >= 1.0
+
+    def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        if not self._is_distributed:
+            return t
+        orig = t.device
+        t = t.to(self.device)
+        torch.distributed.all_reduce(t)
+        return t.to(orig)
+
+    def _init_train(self):
+        cfg = self.config
+        hb = cfg.habitat_baselines
+        ppo_cfg = hb.rl.ppo
+        self._is_distributed = (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
+            getattr(hb.rl.ddppo, "force_distributed", False)
+        rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        # seed offset per rank (ppo_trainer.py:207-215)
+        seed = cfg.habitat.seed + rank * hb.num_environments
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        if torch.distributed.is_initialized():
+            # the same TCPStore doubles as the preemption counter (ppo_trainer.py:216-219, 553, 776)
+            store = torch.distributed.distributed_c10d._get_default_store()
+            self.num_rollouts_done_store = torch.distributed.PrefixStore("rollout_tracker", store)
+            if rank == 0:
+                self.num_rollouts_done_store.set("num_done", "0")
+            torch.distributed.barrier()
+        self.envs = SyntheticVectorEnvFactory().construct_envs(cfg, device=self.device, rank=rank)
+        obs_space, act_space = self.envs.observation_spaces[0], self.envs.action_spaces[0]
+        policy_cls = baseline_registry.get_policy(hb.rl.policy["main_agent"].name) or PointNavResNetPolicy
+        self.actor_critic = policy_cls.from_config(cfg, obs_space, act_space).to(self.device)
+        upd_name = hb.distrib_updater_name if torch.distributed.is_initialized() else hb.updater_name
+        upd_cls = baseline_registry.get_updater(upd_name) or (DDPPO if torch.distributed.is_initialized() else PPO)
+        self.updater = upd_cls.from_config(self.actor_critic, ppo_cfg)
+        if torch.distributed.is_initialized():
+            self.updater.init_distributed(find_unused_params=False)
+        storage_cls = baseline_registry.get_storage(hb.rollout_storage_name) or RolloutStorage
+        self.rollouts = storage_cls(ppo_cfg.num_steps, self.envs.num_envs, obs_space, act_space, self.actor_critic,
+                                    is_double_buffered=False)
+        self.rollouts.to(self.device)
+        obs = self.envs.reset()
+        self.rollouts.insert_first_observations(TensorDict.from_tree(obs))
+        n = self.envs.num_envs
+        self.current_episode_reward = torch.zeros(n, 1, device=self.device)
+        self.running_episode_stats = dict(count=torch.zeros(n, 1, device=self.device),
+                                          reward=torch.zeros(n, 1, device=self.device))
+        self.window_episode_stats = collections.defaultdict(lambda: collections.deque(maxlen=ppo_cfg.reward_window_size))
+        self._lr0 = ppo_cfg.lr
+        self._clip0 = ppo_cfg.clip_param
+        self.t_start = time.time()
+
+    # -- one environment step for all envs (ppo_trainer.py:343-482, batched: observations never leave the GPU)
+    def _rollout_step(self):
+        r = self.rollouts
+        step = r.get_current_step(slice(0, self.envs.num_envs), 0)
+        t0 = time.perf_counter()
+        ad = self.actor_critic.act(step["observations"], step["recurrent_hidden_states"], step["prev_actions"],
+                                   step["masks"])
+        self.timings["act"] += time.perf_counter() - t0
+        obs, rewards, dones, _ = self.envs.step(ad.actions)
+        not_done = (~dones).view(-1, 1)
+        self.current_episode_reward += rewards
+        self.running_episode_stats["reward"] += torch.where(not_done, torch.zeros_like(rewards), self.current_episode_reward)
+        self.running_episode_stats["count"] += (~not_done).float()
+        self.current_episode_reward.masked_fill_(~not_done, 0.0)
+        r.insert(next_observations=TensorDict.from_tree(obs), next_recurrent_hidden_states=ad.rnn_hidden_states,
+                 actions=ad.actions, action_log_probs=ad.action_log_probs, value_preds=ad.values, rewards=rewards,
+                 next_masks=not_done)
+        r.advance_rollout()
+        return self.envs.num_envs
+
+    def should_end_early(self, rollout_step) -> bool:
+        """DD-PPO straggler preemption (ppo_trainer.py:641-653)."""
+        if not (self._is_distributed and torch.distributed.is_initialized()):
+            return False
+        hb = self.config.habitat_baselines
+        return rollout_step >= hb.rl.ppo.num_steps * self.SHORT_ROLLOUT_THRESHOLD and \
+            int(self.num_rollouts_done_store.get("num_done")) >= hb.rl.ddppo.sync_frac * torch.distributed.get_world_size()
+
+    def _update_agent(self) -> Dict[str, float]:
+        """get_value -> compute_returns -> update -> after_update (ppo_trainer.py:489-522)."""
+        ppo_cfg = self.config.habitat_baselines.rl.ppo
+        r = self.rollouts
+        t0 = time.perf_counter()
+        last = r.get_last_step()
+        next_value = self.actor_critic.get_value(last["observations"], last["recurrent_hidden_states"],
+                                                 last["prev_actions"], last["masks"])
+        r.compute_returns(next_value, ppo_cfg.use_gae, ppo_cfg.gamma, ppo_cfg.tau)
+        self.actor_critic.train()
+        losses = self.updater.update(r)
+        r.after_update()
+        # LambdaLR(1 - percent_done) / clip decay (single_agent_access_mgr.py:285-297)
+        if ppo_cfg.use_linear_lr_decay:
+            for g in self.updater.optimizer.param_groups:
+                g["lr"] = self._lr0 * (1 - self.percent_done())
+        if ppo_cfg.use_linear_clip_decay:
+            self.updater.clip_param = self._clip0 * (1 - self.percent_done())
+        self.timings["learn"] += time.perf_counter() - t0
+        return losses
+
+    def _coalesce_post_step(self, losses: Dict[str, float], count_steps_delta: int) -> Dict[str, float]:
+        """ppo_trainer.py:524-557: two packed all-reduces; rank 0 resets the preemption counter."""
+        order = sorted(self.running_episode_stats.keys())
+        stats = self._all_reduce(torch.stack([self.running_episode_stats[k] for k in order], 0))
+        for i, k in enumerate(order):
+            self.window_episode_stats[k].append(stats[i].clone())
+        if self._is_distributed and torch.distributed.is_initialized():
+            names = sorted(losses.keys())
+            vec = torch.tensor([losses[k] for k in names] + [count_steps_delta], dtype=torch.float32)
+            vec = self._all_reduce(vec)
+            count_steps_delta = int(vec[-1].item())
+            vec /= torch.distributed.get_world_size()
+            losses = {k: vec[i].item() for i, k in enumerate(names)}
+            if torch.distributed.get_rank() == 0:
+                self.num_rollouts_done_store.set("num_done", "0")
+        self.num_steps_done += count_steps_delta
+        return losses
+
+    def train(self) -> Dict[str, float]:
+        self._init_train()
+        ppo_cfg = self.config.habitat_baselines.rl.ppo
+        losses = {}
+        while not self.is_done():
+            self.actor_critic.eval()
+            count_steps_delta = 0
+            t0 = time.perf_counter()
+            for step in range(ppo_cfg.num_steps):
+                count_steps_delta += self._rollout_step()
+                if self.should_end_early(step + 1):
+                    break
+            torch.cuda.synchronize()
+            self.timings["rollout"] += time.perf_counter() - t0
+            if self._is_distributed and torch.distributed.is_initialized():
+                self.num_rollouts_done_store.add("num_done", 1)
+            losses = self._update_agent()
+            torch.cuda.synchronize()
+            self.num_updates_done += 1
+            losses = self._coalesce_post_step(losses, count_steps_delta)
+            self._last_fps = self.num_steps_done / max(time.time() - self.t_start, 1e-9)
+        self.envs.close()
+        return losses

@@ -48,6 +48,22 @@ def _worker(rank, world, port, q):
         packed[8:12] = (x.double() ** 2).sum((0, 2, 3))
         packed[16] = x.shape[0]
         dist.all_reduce(packed)
+        # DD-PPO preemption rule (ppo_trainer.py:641-653) over the shared store
+        from habitat_lab_b200.rl.ppo_trainer import PPOTrainer, make_config
+
+        tr = PPOTrainer(make_config(num_steps=128))
+        tr._is_distributed = True
+        store = dist.distributed_c10d._get_default_store()
+        tr.num_rollouts_done_store = dist.PrefixStore("rollout_tracker", store)
+        if rank == 0:
+            tr.num_rollouts_done_store.set("num_done", "0")
+        dist.barrier()
+        early0 = (tr.should_end_early(31), tr.should_end_early(64))      # nobody done yet
+        dist.barrier()
+        tr.num_rollouts_done_store.add("num_done", 1)                     # both ranks finish their rollout
+        dist.barrier()
+        early1 = (tr.should_end_early(31), tr.should_end_early(32))      # 2 >= 0.6*2 but step must be >= 0.25*T
+        packed = torch.cat([packed, torch.tensor([float(x) for x in early0 + early1], dtype=torch.float64)])
         q.put((rank, adv.numpy(), mean_var.numpy(), g.numpy(), flat.numpy(), x.numpy(), packed.numpy()))
     finally:
         dist.destroy_process_group()
@@ -76,6 +92,8 @@ def test_world2_host_logic():
     xs = [r[5] for r in res]
     n_el = sum(x.shape[0] * 64 for x in xs)
     packed = res[0][6]
+    for r in res:
+        assert r[6][17:].tolist() == [0.0, 0.0, 0.0, 1.0], r[6][17:]
     mean = packed[:4] / n_el
     var = packed[8:12] / n_el - mean * mean
     cat = torch.cat(xs).transpose(1, 0).reshape(4, -1).double()

@@ -154,3 +154,18 @@ def test_ppo_update_vs_reference(hb, name):
 
 def test_smoke_runs(hb):
     hb.smoke()
+
+
+def test_trainer_loop_synthetic_env(hb):
+    """PPOTrainer.train with the synthetic VectorEnv: rollout (act -> insert) + _update_agent, 2 updates."""
+    from habitat_lab_b200.rl.ppo_trainer import PPOTrainer, make_config
+
+    cfg = make_config(num_environments=4, num_updates=2, height=128, width=128, num_steps=8, use_linear_lr_decay=True)
+    tr = PPOTrainer(cfg)
+    losses = tr.train()
+    assert tr.num_updates_done == 2 and tr.num_steps_done == 2 * 8 * 4
+    for k in ("value_loss", "action_loss", "dist_entropy", "grad_norm"):
+        assert math.isfinite(losses[k]), (k, losses)
+    assert 1.2 < losses["dist_entropy"] <= math.log(4) + 1e-4
+    assert tr.updater.optimizer.param_groups[0]["lr"] == pytest.approx(2.5e-4 * 0.0, abs=1e-12)  # decayed to 0 at 100 %
+    assert len(tr.window_episode_stats["count"]) == 2
