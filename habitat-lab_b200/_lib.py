@@ -57,7 +57,10 @@ SIGNATURES = {
     "hb200_maxpool_bwd": ("i", "ppp" + "iiii" + "p"),
     "hb200_gn_bwd_reduce": ("i", "ppppppppp" + "iiii" + "f" + "i" + "p"),
     "hb200_gn_bwd_apply": ("i", "ppppppppp" + "iiii" + "f" + "i" + "p"),
+    "hb200_gn_bwd": ("i", "pppppppppp" + "iiii" + "f" + "i" + "p"),
     "hb200_sgemm": ("i", "pll" + "pll" + "pl" + "p" + "iii" + "f" + "ii" + "p"),
+    "hb200_tgemm": ("i", "pll" + "pll" + "pl" + "p" + "iii" + "ii" + "p"),
+    "hb200_transpose_f32": ("i", "plpl" + "ii" + "p"),
     "hb200_bf16_to_f32": ("i", "pplp"),
     "hb200_f32_to_bf16": ("i", "pplp"),
     "hb200_lstm_step_fwd": ("i", "ppppplplppp" + "ii" + "p"),

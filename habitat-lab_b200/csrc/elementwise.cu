@@ -497,6 +497,97 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
   }
 }
 
+// One block per frame: phase 1 reduces (dgamma/dbeta atomics + per-group sums kept in shared memory),
+// phase 2 re-reads the frame's g / y / act -- which phase 1 just pulled into L2 -- and writes dy (and
+// gz).  Compared with gn_bwd_reduce + gn_bwd_apply this removes one full HBM read of every operand, the
+// per-(frame,group) atomics and a launch + memset per layer.
+__global__ void __launch_bounds__(256)
+gn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act,
+                    const __nv_bfloat16* __restrict__ y, GnP p, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dy,
+                    __nv_bfloat16* __restrict__ gz_out, int B, int hw, int mask_mode) {
+  __shared__ float sa[256][9], sb[256][9];
+  extern __shared__ float dyn[];  // [C] gamma*a, [C] gamma*b, [G] S1, [G] S2
+  float* ch_a = dyn;
+  float* ch_b = dyn + p.C;
+  float* gS1 = dyn + 2 * p.C;
+  float* gS2 = gS1 + p.G;
+  const int cv = p.C >> 3;
+  const int b = blockIdx.x;
+  const int vec = threadIdx.x % cv, pl = threadIdx.x / cv, npl = blockDim.x / cv;
+  const int c0 = vec << 3;
+  float mu[8], rs[8], ga[8], be[8], a[8], bb[8];
+  gn_coeffs(p, b, c0, mu, rs);
+  load8f(p.gamma + c0, ga);
+  load8f(p.beta + c0, be);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = 0.f; bb[e] = 0.f; }
+  for (int pix = pl; pix < hw; pix += npl) {
+    const size_t o = ((size_t)b * hw + pix) * cv + vec;
+    float gg[8], x[8], z[8], ac[8], gz[8];
+    unpack8(reinterpret_cast<const uint4*>(g)[o], gg);
+    unpack8(reinterpret_cast<const uint4*>(y)[o], x);
+    if (mask_mode == 2) unpack8(reinterpret_cast<const uint4*>(act)[o], ac);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      x[e] = (x[e] - mu[e]) * rs[e];
+      z[e] = fmaf(x[e], ga[e], be[e]);
+      if (mask_mode != 2) ac[e] = 0.f;
+    }
+    gn_masked_grad(mask_mode, gg, z, ac, gz);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a[e] += gz[e]; bb[e] = fmaf(gz[e], x[e], bb[e]); }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sa[threadIdx.x][e] = a[e]; sb[threadIdx.x][e] = bb[e]; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const int v = c >> 3, e = c & 7;
+    float ta = 0.f, tb = 0.f;
+    for (int q = 0; q < npl; ++q) { ta += sa[q * cv + v][e]; tb += sb[q * cv + v][e]; }
+    atomicAdd(&dbeta[c], ta);
+    atomicAdd(&dgamma[c], tb);
+    const float gm = p.gamma[c];
+    ch_a[c] = gm * ta;
+    ch_b[c] = gm * tb;
+  }
+  __syncthreads();
+  const int cpg = 1 << p.lcpg;
+  for (int gi = threadIdx.x; gi < p.G; gi += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) { s1 += ch_a[c]; s2 += ch_b[c]; }
+    gS1[gi] = s1;
+    gS2[gi] = s2;
+  }
+  __syncthreads();
+  float k1[8], k2[8], k3[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int gi = (c0 + e) >> p.lcpg;
+    k1[e] = rs[e] * ga[e];
+    k2[e] = rs[e] * p.inv_m * gS1[gi];
+    k3[e] = rs[e] * p.inv_m * gS2[gi];
+  }
+  for (int pix = pl; pix < hw; pix += npl) {
+    const size_t o = ((size_t)b * hw + pix) * cv + vec;
+    float gg[8], x[8], z[8], ac[8], gz[8], out[8];
+    unpack8(reinterpret_cast<const uint4*>(g)[o], gg);
+    unpack8(reinterpret_cast<const uint4*>(y)[o], x);
+    if (mask_mode == 2) unpack8(reinterpret_cast<const uint4*>(act)[o], ac);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      x[e] = (x[e] - mu[e]) * rs[e];
+      z[e] = fmaf(x[e], ga[e], be[e]);
+      if (mask_mode != 2) ac[e] = 0.f;
+    }
+    gn_masked_grad(mask_mode, gg, z, ac, gz);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = fmaf(k1[e], gz[e], -fmaf(x[e], k3[e], k2[e]));
+    reinterpret_cast<uint4*>(dy)[o] = pack8(out);
+    if (gz_out) reinterpret_cast<uint4*>(gz_out)[o] = pack8(gz);
+  }
+}
+
 // ---- converts ------------------------------------------------------------------------------
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ o, long long n8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
@@ -664,6 +755,23 @@ static int gn_slab_launch(int C, int hw, int B, int* ppb, int* grid) {
   *ppb = p;
   *grid = B * ((hw + p - 1) / p);
   return HB200_OK;
+}
+
+// dst[c, r] = src[r, c]  (32x32 tiles through padded shared memory; both sides coalesced)
+__global__ void transpose_f32_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst,
+                                     long long ld_dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < rows && c < cols) ? src[(long long)r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < cols && r < rows) dst[(long long)c * ld_dst + r] = tile[tx][i];
+  }
 }
 
 static int ilog2i(int v) {
@@ -959,6 +1067,36 @@ extern "C" int hb200_heads_fwd(const float* features, const float* w_act, const 
   HB_CHECK_ARG(features && w_act && b_act && w_val && b_val && logits && values && batch > 0, "heads_fwd: bad args");
   heads_fwd_kernel<<<cdiv(batch, 8), 256, 0, (cudaStream_t)stream>>>(features, w_act, b_act, w_val, b_val, batch,
                                                                       hidden, n_actions, logits, values);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y, const float* stats,
+                            const float* gamma, const float* beta, float* dgamma, float* dbeta, hb200_bf16* dy,
+                            hb200_bf16* gz_out, int batch, int hw, int channels, int groups, float eps,
+                            int mask_mode, hb200_stream_t stream) {
+  GnP p;
+  int rc = make_gn(p, stats, gamma, beta, channels, groups, hw, eps);
+  if (rc) return rc;
+  HB_CHECK_ARG(g && y && dgamma && dbeta && dy, "gn_bwd: null pointer");
+  HB_CHECK_ARG(mask_mode >= 0 && mask_mode <= 2 && (mask_mode != 2 || act), "gn_bwd: bad mask_mode");
+  const int cv = channels / 8;
+  HB_CHECK_ARG(cv >= 1 && cv <= 256 && 256 % cv == 0, "gn_bwd: C/8 = %d must divide 256", cv);
+  const size_t smem = sizeof(float) * (2 * (size_t)channels + 2 * (size_t)groups);
+  gn_bwd_fused_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)g, (const __nv_bfloat16*)act, (const __nv_bfloat16*)y, p, dgamma, dbeta,
+      (__nv_bfloat16*)dy, (__nv_bfloat16*)gz_out, batch, hw, mask_mode);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_transpose_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int rows,
+                                   int cols, hb200_stream_t stream) {
+  HB_CHECK_ARG(src && dst && rows > 0 && cols > 0 && ld_src >= cols && ld_dst >= rows, "transpose_f32: bad args");
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+  transpose_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst, ld_dst, rows, cols);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;

@@ -1,0 +1,232 @@
+// hb200 -- TF32 tensor-core GEMM (tcgen05 kind::tf32) on fp32 operands for the dense layers:
+// visual_fc, the LSTM input projections and their data / weight gradients.
+//
+//   C[M,N] (f32) (+)= A[M,K] * B[K,N] (+ bias[N]) (ReLU)
+//   A(m,k) = a[m*a_ms + k*a_ks],  B(k,n) = b[k*b_ks + n*b_ns]   (one of the two strides of each == 1)
+//
+// Precision: operands are fp32 in memory; the tensor core reads them as TF32 (10-bit mantissa,
+// the reference's own cuDNN-RNN precision on CUDA), accumulation is fp32 in TMEM.
+//
+// Operand tiles are copied with 16-byte cp.async (4 floats) straight into the no-swizzle UMMA
+// layouts (descriptor encodings pinned by hb200_umma_gemm_probe):
+//   K-major  (k contiguous):  vector (row, k4) at k4*rows*16 + row*16          LBO = rows*16, SBO = 128
+//   MN-major (mn contiguous): vector (mn4, k)  at (k>>3)*LBO + mn4*128 + (k&7)*16,  SBO = 128 (next 4 mn),
+//                             LBO = (rows/4)*128 (next 8 k)
+// One MMA covers K = 8 (32 bytes); a chunk is K = 32 (4 MMAs); 3-stage cp.async ring as in conv.cu.
+// Weight gradients (K = frames, tiny M x N tile grid) are split over K with fp32 atomics.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace hb200 {
+void count_launch(int n);
+using namespace umma;
+
+constexpr int GT_M = 128, GT_K = 32, GT_STAGES = 3;
+
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+struct TgemmArgs {
+  const float* a; long long a_ms, a_ks;
+  const float* b; long long b_ks, b_ns;
+  float* c; long long ldc;
+  const float* bias;
+  int M, N, K, k_per_split, accumulate, relu;
+};
+
+// load one [ROWS x 32] operand tile (rows = m or n, zero-filled out of range)
+template <int MNMAJOR>
+__device__ __forceinline__ void tg_load(const float* __restrict__ p, long long s_mn, long long s_k, int mn0, int MN,
+                                        int k0, int k_end, uint32_t sdst, int rows) {
+  if (!MNMAJOR) {
+    // K-major: vector = 4 consecutive k of one row; 8 vectors per row per chunk
+    for (int v = threadIdx.x; v < rows * 8; v += 128) {
+      const int row = v % rows, k4 = v / rows;          // consecutive threads: consecutive rows = consecutive
+                                                        // 16-byte smem slots (bank-conflict free)
+      const int gm = mn0 + row, gk = k0 + k4 * 4;
+      const bool ok = gm < MN && gk + 3 < k_end;
+      const float* g = ok ? p + (long long)gm * s_mn + gk : p;
+      cp_async16(sdst + (uint32_t)(k4 * rows + row) * 16, g, ok);
+    }
+  } else {
+    // MN-major: vector = 4 consecutive mn at one k; rows/4 vectors per k
+    const int r4 = rows >> 2;
+    for (int v = threadIdx.x; v < r4 * GT_K; v += 128) {
+      // 8 consecutive threads = the 8 k rows of one core matrix (128 contiguous smem bytes), the next
+      // 8 threads the next 4 mn (adjacent 16 B in global memory)
+      const int kl = v & 7, mb = (v >> 3) % r4, k = (v / (8 * r4)) * 8 + kl;
+      const int gm = mn0 + mb * 4, gk = k0 + k;
+      const bool ok = gm + 3 < MN && gk < k_end;
+      const float* g = ok ? p + (long long)gk * s_k + gm : p;
+      cp_async16(sdst + (uint32_t)(k >> 3) * (r4 * 128) + (uint32_t)mb * 128 + (uint32_t)(k & 7) * 16, g, ok);
+    }
+  }
+}
+
+template <int BN, int A_MN, int B_MN>
+__global__ void __launch_bounds__(128) tgemm_kernel(const TgemmArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[GT_STAGES];
+  __shared__ uint32_t tmem_slot;
+  constexpr uint32_t kABytes = GT_M * GT_K * 4, kBBytes = BN * GT_K * 4, kStage = kABytes + kBBytes;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int m0 = blockIdx.y * GT_M, n0 = blockIdx.x * BN;
+  const int k_begin = blockIdx.z * a.k_per_split;
+  const int k_end = min(a.K, k_begin + a.k_per_split);
+  const int nchunks = (k_end - k_begin + GT_K - 1) / GT_K;
+  if (nchunks <= 0) return;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GT_STAGES; ++s) mbar_init(&mma_bar[s], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  constexpr uint32_t idesc = make_idesc_tf32(GT_M, BN, A_MN, B_MN);
+
+  auto load_chunk = [&](int c, int st) {
+    const uint32_t sa = sbase + st * kStage, sb = sa + kABytes;
+    const int k0 = k_begin + c * GT_K;
+    tg_load<A_MN>(a.a, a.a_ms, a.a_ks, m0, a.M, k0, k_end, sa, GT_M);
+    tg_load<B_MN>(a.b, a.b_ns, a.b_ks, n0, a.N, k0, k_end, sb, BN);
+  };
+#pragma unroll
+  for (int c = 0; c < GT_STAGES - 1; ++c) {
+    if (c < nchunks) load_chunk(c, c);
+    cp_async_commit();
+  }
+  for (int c = 0; c < nchunks; ++c) {
+    const int st = c % GT_STAGES;
+    cp_async_wait<GT_STAGES - 2>();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t sa = sbase + st * kStage, sb = sa + kABytes;
+#pragma unroll
+      for (int kk = 0; kk < GT_K / 8; ++kk) {
+        // K-major: the two 16-byte k4 vectors of this K=8 step are LBO = rows*16 apart
+        // MN-major: one 8-k block per step, blocks LBO' = (rows/4)*128 apart; SBO = 128 between 4-mn vectors
+        const uint64_t da = A_MN ? make_smem_desc(sa + kk * (GT_M / 4) * 128, (GT_M / 4) * 128, 128, kNoSwizzle)
+                                 : make_smem_desc(sa + kk * 2 * GT_M * 16, GT_M * 16, 128, kNoSwizzle);
+        const uint64_t db = B_MN ? make_smem_desc(sb + kk * (BN / 4) * 128, (BN / 4) * 128, 128, kNoSwizzle)
+                                 : make_smem_desc(sb + kk * 2 * BN * 16, BN * 16, 128, kNoSwizzle);
+        mma_tf32_ss(tmem_base, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+      }
+      mma_commit(&mma_bar[st]);
+    }
+    const int nc = c + GT_STAGES - 1;
+    if (nc < nchunks) {
+      if (c >= 1) mbar_wait(&mma_bar[(c - 1) % GT_STAGES], ((c - 1) / GT_STAGES) & 1);
+      load_chunk(nc, nc % GT_STAGES);
+    }
+    cp_async_commit();
+  }
+  mbar_wait(&mma_bar[(nchunks - 1) % GT_STAGES], ((nchunks - 1) / GT_STAGES) & 1);
+  fence_after_sync();
+
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const int m = m0 + tid;
+#pragma unroll 1
+  for (int col0 = 0; col0 < BN; col0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + col0, r);
+    tmem_ld_wait();
+    if (m < a.M) {
+      float* dst = a.c + (long long)m * a.ldc + n0 + col0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = n0 + col0 + j;
+        if (n >= a.N) continue;
+        float v = __uint_as_float(r[j]);
+        if (gridDim.z > 1) {
+          if (a.bias && blockIdx.z == 0) v += a.bias[n];
+          atomicAdd(dst + j, v);
+        } else {
+          if (a.bias) v += a.bias[n];
+          if (a.accumulate) v += dst[j];
+          if (a.relu) v = fmaxf(v, 0.f);
+          dst[j] = v;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+}  // namespace hb200
+
+using namespace hb200;
+
+extern "C" int hb200_tgemm(const float* a, long long a_ms, long long a_ks, const float* b, long long b_ks,
+                           long long b_ns, float* c, long long ldc, const float* bias, int m, int n, int k,
+                           int accumulate, int relu, hb200_stream_t stream) {
+  HB_CHECK_ARG(a && b && c && m > 0 && n > 0 && k > 0, "tgemm: bad args");
+  // MN-major fp32 operands would need the SWIZZLE_128B_BASE32B layouts (the plain interleaved MN-major
+  // descriptor is 16-bit only: verified wrong on hardware) -> K-major only, callers transpose
+  HB_CHECK_ARG(a_ks == 1 && b_ks == 1, "tgemm: both operands must be K-major (a_ks == 1, b_ks == 1)");
+  const int a_mn = (a_ks == 1) ? 0 : 1;   // k contiguous -> K-major
+  const int b_mn = (b_ks == 1) ? 0 : 1;
+  // 16-byte vector loads: leading dimensions / pointers must be multiples of 4 floats
+  const long long lda = a_mn ? a_ks : a_ms, ldb = b_mn ? b_ks : b_ns;
+  HB_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0,
+               "tgemm: operands must be 16-byte aligned with leading dimensions that are multiples of 4");
+  HB_CHECK_ARG(k % 4 == 0 && (!a_mn || m % 4 == 0) && (!b_mn || n % 4 == 0), "tgemm: k (and mn-major extents) must be multiples of 4");
+  const int BN = n >= 256 ? 256 : (n >= 128 ? 128 : (n >= 64 ? 64 : 32));
+  HB_CHECK_ARG(n % 4 == 0, "tgemm: n must be a multiple of 4");
+  TgemmArgs g;
+  g.a = a; g.a_ms = a_ms; g.a_ks = a_ks; g.b = b; g.b_ks = b_ks; g.b_ns = b_ns; g.c = c; g.ldc = ldc; g.bias = bias;
+  g.M = m; g.N = n; g.K = k; g.accumulate = accumulate; g.relu = relu;
+  const long long tiles = (long long)cdiv(n, BN) * cdiv(m, GT_M);
+  int splits = 1;
+  if (accumulate && !relu && tiles < kNumSMs && k >= 1024) {
+    splits = (int)((2 * kNumSMs + tiles - 1) / tiles);
+    if (splits > k / 256) splits = k / 256;
+    if (splits < 1) splits = 1;
+  }
+  g.k_per_split = ((cdiv(k, splits) + GT_K - 1) / GT_K) * GT_K;
+  splits = cdiv(k, g.k_per_split);
+  dim3 grid(cdiv(n, BN), cdiv(m, GT_M), splits);
+  cudaStream_t st = (cudaStream_t)stream;
+#define HB_TG(bn, AM, BM)                                                                          \
+  {                                                                                                \
+    const size_t smem = (size_t)GT_STAGES * (GT_M * GT_K * 4 + bn * GT_K * 4) + 256;               \
+    auto kern = tgemm_kernel<bn, AM, BM>;                                                          \
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    kern<<<grid, 128, smem, st>>>(g);                                                              \
+  }
+#define HB_TG_BN(AM, BM)                 \
+  switch (BN) {                          \
+    case 32: HB_TG(32, AM, BM); break;   \
+    case 64: HB_TG(64, AM, BM); break;   \
+    case 128: HB_TG(128, AM, BM); break; \
+    default: HB_TG(256, AM, BM); break;  \
+  }
+  if (!a_mn && !b_mn) { HB_TG_BN(0, 0) }
+  else if (!a_mn && b_mn) { HB_TG_BN(0, 1) }
+  else if (a_mn && !b_mn) { HB_TG_BN(1, 0) }
+  else { HB_TG_BN(1, 1) }
+#undef HB_TG_BN
+#undef HB_TG
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}

@@ -203,32 +203,80 @@ def gn_bwd_apply(g, act, y, stats, gamma, beta, sums, dy, gz_out, batch, hw, cha
          ptr(gz_out), batch, hw, channels, groups, float(eps), mask_mode)
 
 
+def gn_bwd(g, act, y, stats, gamma, beta, dgamma, dbeta, dy, gz_out, batch, hw, channels, groups, mask_mode, eps=1e-5):
+    call("hb200_gn_bwd", ptr(g), ptr(act), ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(dgamma), ptr(dbeta),
+         ptr(dy), ptr(gz_out), batch, hw, channels, groups, float(eps), mask_mode)
+
+
 # ---- dense / rnn / misc -----------------------------------------------------------------------------------
-def sgemm(a, a_ms, a_ks, b, b_ks, b_ns, c, ldc, m, n, k, bias=None, alpha=1.0, accumulate=False, relu=False):
+DENSE_TF32 = True  # dense layers on tcgen05 kind::tf32 (the reference's cuDNN-RNN precision); False -> fp32 SIMT
+
+
+def _tf32_ok(a, a_ms, a_ks, b, b_ks, b_ns, m, n, k):
+    return (a_ks == 1 and b_ks == 1 and a_ms % 4 == 0 and b_ns % 4 == 0 and a.data_ptr() % 16 == 0
+            and b.data_ptr() % 16 == 0 and k % 4 == 0 and n % 4 == 0)
+
+
+_scratch = {}
+
+
+def _scratch_f32(tag, shape, device):
+    key = (tag, tuple(shape), device)
+    t = _scratch.get(key)
+    if t is None:
+        t = torch.empty(*shape, device=device)
+        _scratch[key] = t
+    return t
+
+
+def transpose_f32(src, dst):
+    """dst[c, r] = src[r, c] for 2-D fp32 tensors (row strides honoured)"""
+    rows, cols = src.shape
+    call("hb200_transpose_f32", ptr(src), src.stride(0), ptr(dst), dst.stride(0), rows, cols)
+
+
+def sgemm(a, a_ms, a_ks, b, b_ks, b_ns, c, ldc, m, n, k, bias=None, alpha=1.0, accumulate=False, relu=False,
+          tf32=False):
+    if tf32 and DENSE_TF32 and alpha == 1.0 and _tf32_ok(a, a_ms, a_ks, b, b_ks, b_ns, m, n, k):
+        call("hb200_tgemm", ptr(a), int(a_ms), int(a_ks), ptr(b), int(b_ks), int(b_ns), ptr(c), int(ldc), ptr(bias),
+             m, n, k, int(bool(accumulate)), int(bool(relu)))
+        return
     call("hb200_sgemm", ptr(a), int(a_ms), int(a_ks), ptr(b), int(b_ks), int(b_ns), ptr(c), int(ldc), ptr(bias),
          m, n, k, float(alpha), int(bool(accumulate)), int(bool(relu)))
 
 
-def linear_fwd(x, w, bias, out, relu=False, ldc=None):
+def linear_fwd(x, w, bias, out, relu=False, ldc=None, tf32=False):
     """out[M,N] = x[M,K] @ w[N,K]^T + bias"""
     M, K = x.shape
     N = w.shape[0]
     sgemm(x, x.stride(0), 1, w, 1, w.stride(0), out, ldc if ldc is not None else out.stride(0), M, N, K,
-          bias=bias, relu=relu)
+          bias=bias, relu=relu, tf32=tf32)
 
 
-def linear_bwd_input(dy, w, dx, ld_dy=None, accumulate=False):
+def linear_bwd_input(dy, w, dx, ld_dy=None, accumulate=False, tf32=False):
     """dx[M,K] = dy[M,N] @ w[N,K]"""
     M, N = dy.shape
     K = w.shape[1]
+    if tf32 and DENSE_TF32 and N % 4 == 0 and K % 4 == 0 and dy.stride(0) % 4 == 0:
+        wt = _scratch_f32("wt", (K, N), w.device)       # W^T so that both operands are K-major
+        transpose_f32(w, wt)
+        sgemm(dy, dy.stride(0), 1, wt, 1, wt.stride(0), dx, dx.stride(0), M, K, N, accumulate=accumulate, tf32=True)
+        return
     sgemm(dy, ld_dy if ld_dy is not None else dy.stride(0), 1, w, w.stride(0), 1, dx, dx.stride(0), M, K, N,
           accumulate=accumulate)
 
 
-def linear_bwd_weight(dy, x, dw, accumulate=False):
+def linear_bwd_weight(dy, x, dw, accumulate=False, tf32=False):
     """dw[N,K] = dy[M,N]^T @ x[M,K]"""
     M, N = dy.shape
     K = x.shape[1]
+    if tf32 and DENSE_TF32 and M % 4 == 0 and K % 4 == 0:
+        dyt = _scratch_f32("dyt", (N, M), dy.device)    # dy^T [N, frames], x^T [K, frames]: K-major operands
+        xt = _scratch_f32("xt", (K, M), x.device)
+        transpose_f32(dy, dyt)
+        transpose_f32(x, xt)
+        sgemm(dyt, M, 1, xt, 1, M, dw, dw.stride(0), N, K, M, accumulate=accumulate, tf32=True)
+        return
     sgemm(dy, 1, dy.stride(0), x, x.stride(0), 1, dw, dw.stride(0), N, K, M, accumulate=accumulate)
 
 

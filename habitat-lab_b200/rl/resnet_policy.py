@@ -403,9 +403,7 @@ class EncoderEngine:
             sums = ws[f"sums{idx[id(c)]}"]
             dy = view(ws["dy"], c)
             gz = view(ws["gz"], c) if want_gz else None
-            ops.gn_bwd_reduce(g, act, Y(c), ST(c), c.gamma, c.beta, sums, c.gamma.grad, c.beta.grad, B, hw, c.co,
-                              c.groups, mode)
-            ops.gn_bwd_apply(g, act, Y(c), ST(c), c.gamma, c.beta, sums, dy, gz, B, hw, c.co, c.groups, mode)
+            ops.gn_bwd(g, act, Y(c), ST(c), c.gamma, c.beta, c.gamma.grad, c.beta.grad, dy, gz, B, hw, c.co, c.groups, mode)
             return dy, gz
 
         def wgrad(c, x, dy):
@@ -647,7 +645,7 @@ class PointNavResNetPolicy(nn.Module):
         fc = self.net.visual_fc[1]
         D = H + 64
         rnn_in = self._tmp("rnn_in", (B, D), dev)
-        ops.linear_fwd(feat, fc.weight, fc.bias, rnn_in, relu=True, ldc=D)
+        ops.linear_fwd(feat, fc.weight, fc.bias, rnn_in, relu=True, ldc=D, tf32=True)
         goal = obs[POINTGOAL_UUID]
         pa = prev_actions.reshape(-1)
         mk = ops.as_u8(masks.reshape(-1))
@@ -661,7 +659,7 @@ class PointNavResNetPolicy(nn.Module):
             w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
             b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
             xproj = self._tmp(f"xproj{l}", (B, 4 * H), dev)
-            ops.linear_fwd(x, w_ih, b_ih, xproj)
+            ops.linear_fwd(x, w_ih, b_ih, xproj, tf32=True)
             hs = self._tmp(f"hs{l}", (T, n, H), dev)
             cs = self._tmp(f"cs{l}", (T, n, H), dev)
             gates = self._tmp(f"gates{l}", (T, n, 4 * H), dev) if train else None
@@ -766,14 +764,14 @@ class PointNavResNetPolicy(nn.Module):
                              self._tmp("rnn_ws", (64,), dev, torch.uint8))
             dgf = dg.view(B, 4 * H)
             x = ly["x"]
-            ops.linear_bwd_weight(dgf, x, w_ih.grad, accumulate=True)  # grads are pre-zeroed: enables split-K
+            ops.linear_bwd_weight(dgf, x, w_ih.grad, accumulate=True, tf32=True)  # grads pre-zeroed: split-K
             hin = self._tmp("hin", (T, n, H), dev)
             ops.rnn_shift_mask(ly["hs"], ly["h0"], mk, hin, T, n, H)
-            ops.linear_bwd_weight(dgf, hin.view(B, H), w_hh.grad, accumulate=True)
+            ops.linear_bwd_weight(dgf, hin.view(B, H), w_hh.grad, accumulate=True, tf32=True)
             ops.colsum(dgf, b_ih.grad)
             b_hh.grad.copy_(b_ih.grad)
             dx = self._tmp(f"dx{l}", (B, x.shape[1]), dev)
-            ops.linear_bwd_input(dgf, w_ih, dx)
+            ops.linear_bwd_input(dgf, w_ih, dx, tf32=True)
             d_out = dx
         d_rnn_in = d_out  # [B, H + 64]
         # ---- embeddings
@@ -784,12 +782,10 @@ class PointNavResNetPolicy(nn.Module):
         fc = self.net.visual_fc[1]
         ops.relu_bwd(d_rnn_in, s["rnn_in"], H)
         dvis = d_rnn_in[:, :H]
-        ops.sgemm(dvis, 1, dvis.stride(0), s["feat"], s["feat"].stride(0), 1, fc.weight.grad, fc.weight.grad.stride(0),
-                  H, s["feat"].shape[1], B, accumulate=True)
+        ops.linear_bwd_weight(dvis, s["feat"], fc.weight.grad, accumulate=True, tf32=True)
         ops.colsum(dvis, fc.bias.grad, n_cols=H)
         d_feat = self._tmp("d_feat", tuple(s["feat"].shape), dev)
-        ops.sgemm(dvis, dvis.stride(0), 1, fc.weight, fc.weight.stride(0), 1, d_feat, d_feat.stride(0), B,
-                  s["feat"].shape[1], H)
+        ops.linear_bwd_input(dvis, fc.weight, d_feat, tf32=True)
         # ---- conv stack
         self._engine_().backward(d_feat, B, dev)
         self._last = dict(values=out["values"], log_probs=out["log_probs"], entropy=out["entropy"],

@@ -242,6 +242,12 @@ int hb200_gn_bwd_reduce(const hb200_bf16* g, const hb200_bf16* act, const hb200_
                         const float* stats, const float* gamma, const float* beta, float* sums,
                         float* dgamma, float* dbeta, int batch, int hw, int channels, int groups,
                         float eps, int mask_mode, hb200_stream_t stream);
+/* both passes in one launch (one block per frame; the second pass re-reads from L2): dgamma/dbeta are
+ * accumulated (caller zeroes), dy / gz_out written */
+int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y, const float* stats,
+                 const float* gamma, const float* beta, float* dgamma, float* dbeta, hb200_bf16* dy,
+                 hb200_bf16* gz_out, int batch, int hw, int channels, int groups, float eps, int mask_mode,
+                 hb200_stream_t stream);
 int hb200_gn_bwd_apply(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
                        const float* stats, const float* gamma, const float* beta,
                        const float* sums, hb200_bf16* dy, hb200_bf16* gz_out, int batch, int hw,
@@ -256,6 +262,17 @@ int hb200_gn_bwd_apply(const hb200_bf16* g, const hb200_bf16* act, const hb200_b
 int hb200_sgemm(const float* a, long long a_ms, long long a_ks, const float* b, long long b_ks,
                 long long b_ns, float* c, long long ldc, const float* bias, int m, int n, int k,
                 float alpha, int accumulate, int relu, hb200_stream_t stream);
+/* Same contract on the tensor cores: tcgen05 kind::tf32 (operands stay fp32 in memory, read as TF32 --
+ * the precision of the reference's cuDNN RNN path on CUDA -- fp32 accumulation).  Both operands must be
+ * K-major (a_ks == 1 and b_ks == 1; transposed operands go through hb200_transpose_f32) with 16-byte
+ * aligned rows (leading dimensions multiples of 4 floats).  Weight gradients
+ * (accumulate != 0, long K) are split over K with fp32 atomics. */
+int hb200_tgemm(const float* a, long long a_ms, long long a_ks, const float* b, long long b_ks, long long b_ns,
+                float* c, long long ldc, const float* bias, int m, int n, int k, int accumulate, int relu,
+                hb200_stream_t stream);
+/* dst[c,r] = src[r,c] (fp32): feeds hb200_tgemm K-major operands for the data / weight gradient GEMMs */
+int hb200_transpose_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int rows, int cols,
+                        hb200_stream_t stream);
 /* bf16 activations [M,K] (optionally GN+ReLU applied on load: stats/gamma/beta non-NULL with
  * per-row frame = m, K laid out NHWC (hw, C)) -> f32 [M,K].  Feeds visual_fc. */
 int hb200_bf16_to_f32(const hb200_bf16* x, float* out, long long n, hb200_stream_t stream);

@@ -450,6 +450,13 @@ def test_groupnorm_passes(hb, B, C, H, W, G):
     torch.cuda.synchronize()
     sc = yr.grad.abs().max().item()
     torch.testing.assert_close(nchw(dy.float()), yr.grad, rtol=2e-2, atol=1e-2 * sc)
+    # fused single-launch variant must reproduce the two-pass result
+    dga2, dbe2, dy2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.empty_like(yb)
+    ops.gn_bwd(gb, None, yb, stats, gamma, beta, dga2, dbe2, dy2, None, B, hw, C, G, 1)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dy2.float(), dy.float(), rtol=1e-2, atol=1e-2 * sc)
+    torch.testing.assert_close(dga2, dga, rtol=1e-4, atol=1e-4 * dga.abs().max().item())
+    torch.testing.assert_close(dbe2, dbe, rtol=1e-4, atol=1e-4 * dbe.abs().max().item())
     torch.testing.assert_close(dga, gr.grad, rtol=1e-3, atol=1e-3 * gr.grad.abs().max().item())
     torch.testing.assert_close(dbe, br.grad, rtol=1e-3, atol=1e-3 * br.grad.abs().max().item())
     # --- residual block output: relu(GN(y) + res), backward with mask from the block output
@@ -532,6 +539,31 @@ def test_sgemm_linear(hb, M, N, K):
     db = torch.empty(N, device=DEV)
     ops.colsum(dy, db)
     torch.testing.assert_close(db, dy.sum(0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 2048), (4096, 2048, 576), (128, 64, 64), (260, 36, 100)])
+def test_tgemm_tf32(hb, M, N, K):
+    """tcgen05 kind::tf32 dense layers: forward (K-major x K-major), data gradient (K-major x N-major) and
+    split-K weight gradient (M-major x N-major) vs fp64; tolerance = TF32 operand rounding (2^-11 relative)."""
+    from habitat_lab_b200 import ops
+
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / math.sqrt(K)
+    b = torch.randn(N, device=DEV)
+    out = torch.empty(M, N + 8, device=DEV)
+    ops.linear_fwd(x, w, b, out, relu=True, tf32=True)
+    ref = F.relu(F.linear(x.double(), w.double(), b.double())).float()
+    torch.testing.assert_close(out[:, :N], ref, rtol=2e-3, atol=4e-3)
+    dy = torch.randn(M, N, device=DEV)
+    dx = torch.empty(M, K, device=DEV)
+    ops.linear_bwd_input(dy, w, dx, tf32=True)
+    ref_dx = (dy.double() @ w.double()).float()
+    torch.testing.assert_close(dx, ref_dx, rtol=2e-3, atol=4e-3 * ref_dx.abs().max().item())
+    dw = torch.zeros(N, K, device=DEV)
+    ops.linear_bwd_weight(dy, x, dw, accumulate=True, tf32=True)
+    ref_dw = (dy.double().t() @ x.double()).float()
+    torch.testing.assert_close(dw, ref_dw, rtol=2e-3, atol=2e-3 * ref_dw.abs().max().item())
 
 
 @pytest.mark.parametrize("T,n,H,D", [(16, 8, 512, 576), (7, 3, 32, 32), (33, 33, 128, 64)])
