@@ -268,6 +268,7 @@ def run_hb200(args):
     if rank == 0:
         peaks = _peaks()
         roof = kernel_roofline(hb, ops, policy, st, dev, peaks)
+        hbm_roofs = hbm_kernel_rooflines(hb, ops, dev, peaks) if world == 1 else None
         cores = _cpu_threads()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -279,7 +280,7 @@ def run_hb200(args):
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 14 * 4, "ms_per_step": ms_e2e / e2e_steps},
-                "roofline": roof, "cpu_baseline": cpu,
+                "roofline": roof, "hbm_kernel_rooflines": hbm_roofs, "cpu_baseline": cpu,
                 "conv_tensor_frac_of_step": (world * T * N * CFG["ppo_epoch"] * CONV_TRAIN_GFLOP * 1e-3 * args.steps)
                 / (ms * 1e-3) / (peaks["bf16_sustained"] * world),
                 "learner_metrics": {k: round(float(v), 6) for k, v in metrics.items()}}
@@ -354,6 +355,68 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
             "traffic": None,
             "by_pass": {k: {"tflops": (v[0] / (v[1] * 1e-3) * 1e-12) if v[1] else None, "ms": v[1]} for k, v in per.items()},
             "per_layer": detail}
+
+
+def hbm_kernel_rooflines(hb, ops, dev, peaks):
+    """HBM-bound kernels timed alone on batched instances >> L2 (the config-#2 sizes of GAE / loss / Adam are
+    launch-latency bound: 8192 x 17 B), CUDA events, an L2-sized scratch write between repetitions."""
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def t_ms(fn, reps=5):
+        fn()
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sorted(ts)[len(ts) // 2]
+
+    # GAE + advantages: T = 128, N = 655,360 envs -> 17 B x (T+1) x N = 1.44 GB
+    T, N = 128, 655360
+    g = torch.Generator(device=dev).manual_seed(1)
+    rewards = torch.randn(T + 1, N, 1, device=dev, generator=g)
+    values = torch.randn(T + 1, N, 1, device=dev, generator=g)
+    masks = torch.rand(T + 1, N, 1, device=dev, generator=g) > 0.004
+    nv = torch.randn(N, device=dev, generator=g)
+    returns, adv = torch.empty_like(rewards), torch.empty_like(rewards)
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    ms = t_ms(lambda: ops.gae_adv(rewards, values, masks, nv, returns, adv, stats, T, 0.99, 0.95, True, 1))
+    by = 17.0 * (T + 1) * N
+    out["gae_adv"] = {"workload": f"T={T} x N={N} (batched: cfg #2 is 8192 elements = launch bound)", "bytes": by,
+                      "ms": ms, "achieved": by / ms * 1e-6, "peak": peaks["hbm"], "unit": "GB/s",
+                      "frac": by / ms * 1e-6 / peaks["hbm"]}
+    del rewards, values, masks, returns, adv
+    # clip + Adam on 64 x the policy's parameter count: 32 B/param
+    n = 8481125 * 16
+    bufs = [torch.randn(n, device=dev) * 0.01 for _ in range(2)] + [torch.zeros(n, device=dev) for _ in range(2)]
+    ws, gn = ops.clip_adam_workspace(n, dev), torch.zeros(1, device=dev)
+    ms = t_ms(lambda: ops.clip_adam(bufs[0], bufs[1], bufs[2], bufs[3], 2.5e-4, (0.9, 0.999), 1e-5, 0.0, 0.2, 1.0, 1, gn, ws))
+    by = 32.0 * n
+    out["clip_adam"] = {"workload": f"{n} params (16 x cfg #2)", "bytes": by, "ms": ms, "achieved": by / ms * 1e-6,
+                        "peak": peaks["hbm"], "unit": "GB/s", "frac": by / ms * 1e-6 / peaks["hbm"]}
+    del bufs
+    # heads + PPO loss fwd+bwd: B = 1M frames, H = 512: features in + d_features out = 4096 B/frame
+    B, H, A = 1 << 20, 512, 4
+    feats = torch.randn(B, H, device=dev)
+    o = dict(values=torch.empty(B, device=dev), log_probs=torch.empty(B, device=dev), entropy=torch.empty(B, device=dev),
+             d_features=torch.empty(B, H, device=dev), d_w_act=torch.empty(A, H, device=dev), d_b_act=torch.empty(A, device=dev),
+             d_w_val=torch.empty(H, device=dev), d_b_val=torch.empty(1, device=dev), metrics=torch.empty(12, device=dev))
+    small = [torch.randn(B, device=dev) for _ in range(4)]
+    acts = torch.randint(0, A, (B,), device=dev)
+    w_a, b_a, w_v, b_v = torch.randn(A, H, device=dev) * 0.01, torch.zeros(A, device=dev), torch.randn(1, H, device=dev) * 0.05, torch.zeros(1, device=dev)
+    wsl = ops.ppo_loss_workspace(B, H, A, dev)
+    ms = t_ms(lambda: ops.ppo_loss(feats, w_a, b_a, w_v, b_v, acts, small[0], small[1], small[2], small[3], 0.2, 0.5, 0.01,
+                                   True, True, o, wsl))
+    by = (2 * H * 4 + 64 + 2 * H * 4) * float(B)  # features read twice (loss + head-weight gradient) + d_features + scalars
+    out["ppo_loss_fwd_bwd"] = {"workload": f"B={B} frames, H=512, A=4", "bytes": by, "ms": ms, "achieved": by / ms * 1e-6,
+                               "peak": peaks["hbm"], "unit": "GB/s", "frac": by / ms * 1e-6 / peaks["hbm"]}
+    return out
 
 
 def main():

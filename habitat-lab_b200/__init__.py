@@ -16,6 +16,9 @@ _LAZY = {
     "DDPPO": ("rl.ppo", "DDPPO"),
     "FusedAdam": ("rl.ppo", "FusedAdam"),
     "RolloutStorage": ("common.rollout_storage", "RolloutStorage"),
+    "PPOTrainer": ("rl.ppo_trainer", "PPOTrainer"),
+    "SingleAgentAccessMgr": ("rl.single_agent_access_mgr", "SingleAgentAccessMgr"),
+    "ddp_utils": ("rl.ddp_utils", None),
     "TensorDict": ("common.tensor_dict", "TensorDict"),
     "baseline_registry": ("common.baseline_registry", "baseline_registry"),
     "spaces": ("common.spaces", None),

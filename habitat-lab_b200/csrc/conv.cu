@@ -423,7 +423,9 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const WgradArgs a) {
     if (row < a.KW) {
       float* dst = a.dw + (size_t)row * a.Co + n0 + col0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+      for (int j = 0; j < 32; j += 4)
+        red_add_v4(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                   __uint_as_float(r[j + 3]));
     }
   }
   fence_before_sync();
@@ -701,7 +703,8 @@ extern "C" int hb200_conv_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float
   const int BN = pick_bn(s->co);
   const int mtiles = cdiv(a.KW, kTileM), ntiles = s->co / BN;
   const long long total_chunks = cdiv(a.P, kChunkK);
-  int nsplit = (kNumSMs * 4) / (mtiles * ntiles);
+  // ~1.5 waves of CTAs: every extra split costs a full 128 x N tile of fp32 reductions into L2
+  int nsplit = (kNumSMs * 3 / 2) / (mtiles * ntiles);
   if (nsplit < 1) nsplit = 1;
   if (nsplit > total_chunks) nsplit = (int)total_chunks;
   a.chunks_per_split = (int)((total_chunks + nsplit - 1) / nsplit);

@@ -343,7 +343,9 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
         if (ok) {
           float* dst = a.dw + row * N + col0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rr[j]));
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(dst + j, __uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
+                       __uint_as_float(rr[j + 3]));
         }
       }
     }

@@ -522,21 +522,36 @@ gn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
   load8f(p.beta + c0, be);
 #pragma unroll
   for (int e = 0; e < 8; ++e) { a[e] = 0.f; bb[e] = 0.f; }
-  for (int pix = pl; pix < hw; pix += npl) {
-    const size_t o = ((size_t)b * hw + pix) * cv + vec;
-    float gg[8], x[8], z[8], ac[8], gz[8];
-    unpack8(reinterpret_cast<const uint4*>(g)[o], gg);
-    unpack8(reinterpret_cast<const uint4*>(y)[o], x);
-    if (mask_mode == 2) unpack8(reinterpret_cast<const uint4*>(act)[o], ac);
+  constexpr int UN = 4;  // pixels in flight per thread: 4 x (2..3) 16-byte loads issued before any use
+  for (int pix = pl; pix < hw; pix += UN * npl) {
+    uint4 G[UN], Y[UN], A[UN];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      x[e] = (x[e] - mu[e]) * rs[e];
-      z[e] = fmaf(x[e], ga[e], be[e]);
-      if (mask_mode != 2) ac[e] = 0.f;
+    for (int u = 0; u < UN; ++u) {
+      const int pp = pix + u * npl;
+      if (pp < hw) {
+        const size_t o = ((size_t)b * hw + pp) * cv + vec;
+        G[u] = reinterpret_cast<const uint4*>(g)[o];
+        Y[u] = reinterpret_cast<const uint4*>(y)[o];
+        if (mask_mode == 2) A[u] = reinterpret_cast<const uint4*>(act)[o];
+      }
     }
-    gn_masked_grad(mask_mode, gg, z, ac, gz);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { a[e] += gz[e]; bb[e] = fmaf(gz[e], x[e], bb[e]); }
+    for (int u = 0; u < UN; ++u) {
+      if (pix + u * npl >= hw) continue;
+      float gg[8], x[8], z[8], ac[8], gz[8];
+      unpack8(G[u], gg);
+      unpack8(Y[u], x);
+      if (mask_mode == 2) unpack8(A[u], ac);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        x[e] = (x[e] - mu[e]) * rs[e];
+        z[e] = fmaf(x[e], ga[e], be[e]);
+        if (mask_mode != 2) ac[e] = 0.f;
+      }
+      gn_masked_grad(mask_mode, gg, z, ac, gz);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a[e] += gz[e]; bb[e] = fmaf(gz[e], x[e], bb[e]); }
+    }
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sa[threadIdx.x][e] = a[e]; sb[threadIdx.x][e] = bb[e]; }
@@ -568,23 +583,39 @@ gn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
     k2[e] = rs[e] * p.inv_m * gS1[gi];
     k3[e] = rs[e] * p.inv_m * gS2[gi];
   }
-  for (int pix = pl; pix < hw; pix += npl) {
-    const size_t o = ((size_t)b * hw + pix) * cv + vec;
-    float gg[8], x[8], z[8], ac[8], gz[8], out[8];
-    unpack8(reinterpret_cast<const uint4*>(g)[o], gg);
-    unpack8(reinterpret_cast<const uint4*>(y)[o], x);
-    if (mask_mode == 2) unpack8(reinterpret_cast<const uint4*>(act)[o], ac);
+  for (int pix = pl; pix < hw; pix += UN * npl) {
+    uint4 G[UN], Y[UN], A[UN];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      x[e] = (x[e] - mu[e]) * rs[e];
-      z[e] = fmaf(x[e], ga[e], be[e]);
-      if (mask_mode != 2) ac[e] = 0.f;
+    for (int u = 0; u < UN; ++u) {
+      const int pp = pix + u * npl;
+      if (pp < hw) {
+        const size_t o = ((size_t)b * hw + pp) * cv + vec;
+        G[u] = reinterpret_cast<const uint4*>(g)[o];
+        Y[u] = reinterpret_cast<const uint4*>(y)[o];
+        if (mask_mode == 2) A[u] = reinterpret_cast<const uint4*>(act)[o];
+      }
     }
-    gn_masked_grad(mask_mode, gg, z, ac, gz);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) out[e] = fmaf(k1[e], gz[e], -fmaf(x[e], k3[e], k2[e]));
-    reinterpret_cast<uint4*>(dy)[o] = pack8(out);
-    if (gz_out) reinterpret_cast<uint4*>(gz_out)[o] = pack8(gz);
+    for (int u = 0; u < UN; ++u) {
+      const int pp = pix + u * npl;
+      if (pp >= hw) continue;
+      const size_t o = ((size_t)b * hw + pp) * cv + vec;
+      float gg[8], x[8], z[8], ac[8], gz[8], out[8];
+      unpack8(G[u], gg);
+      unpack8(Y[u], x);
+      if (mask_mode == 2) unpack8(A[u], ac);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        x[e] = (x[e] - mu[e]) * rs[e];
+        z[e] = fmaf(x[e], ga[e], be[e]);
+        if (mask_mode != 2) ac[e] = 0.f;
+      }
+      gn_masked_grad(mask_mode, gg, z, ac, gz);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) out[e] = fmaf(k1[e], gz[e], -fmaf(x[e], k3[e], k2[e]));
+      reinterpret_cast<uint4*>(dy)[o] = pack8(out);
+      if (gz_out) reinterpret_cast<uint4*>(gz_out)[o] = pack8(gz);
+    }
   }
 }
 
