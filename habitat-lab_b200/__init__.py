@@ -11,6 +11,7 @@ __version__ = "0.1.0"
 
 _LAZY = {
     "PointNavResNetPolicy": ("rl.resnet_policy", "PointNavResNetPolicy"),
+    "PointNavBaselinePolicy": ("rl.policy", "PointNavBaselinePolicy"),
     "RolloutObservations": ("rl.resnet_policy", "RolloutObservations"),
     "PPO": ("rl.ppo", "PPO"),
     "DDPPO": ("rl.ppo", "DDPPO"),

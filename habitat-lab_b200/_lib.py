@@ -38,6 +38,10 @@ SIGNATURES = {
     "hb200_prep_finalize": ("i", "ppppp" + "ili" + "p"),
     "hb200_prep_apply": ("i", "ppp" + "iiiii" + "f" + "pp" + "i" + "p"),
     "hb200_conv_fwd": ("i", "pppp" + "i" + "pp"),
+    "hb200_conv_bias_act_fwd": ("i", "pppp" + "i" + "pp"),
+    "hb200_prep_plain": ("i", "ppp" + "iiiii" + "pp"),
+    "hb200_relu_bias_bwd": ("i", "pppp" + "li" + "p"),
+    "hb200_bf16_hwc_to_f32_chw": ("i", "pp" + "iii" + "p"),
     "hb200_conv_dgrad": ("i", "pppppp"),
     "hb200_conv_wgrad": ("i", "ppppp"),
     "hb200_pack_conv_weight": ("i", "ppp" + "iiiii" + "p"),
@@ -58,6 +62,8 @@ SIGNATURES = {
     "hb200_gn_bwd_reduce": ("i", "ppppppppp" + "iiii" + "f" + "i" + "p"),
     "hb200_gn_bwd_apply": ("i", "ppppppppp" + "iiii" + "f" + "i" + "p"),
     "hb200_gn_bwd": ("i", "pppppppppp" + "iiii" + "f" + "i" + "p"),
+    "hb200_gn_relu_maxpool_bwd_supported": ("i", "iiii"),
+    "hb200_gn_relu_maxpool_bwd": ("i", "ppppppppp" + "iiiii" + "f" + "p"),
     "hb200_sgemm": ("i", "pll" + "pll" + "pl" + "p" + "iii" + "f" + "ii" + "p"),
     "hb200_tgemm": ("i", "pll" + "pll" + "pl" + "p" + "iii" + "ii" + "p"),
     "hb200_transpose_f32": ("i", "plpl" + "ii" + "p"),
@@ -67,6 +73,8 @@ SIGNATURES = {
     "hb200_lstm_step_bwd": ("i", "ppppppl" + "ppppp" + "ii" + "p"),
     "hb200_lstm_seq_fwd": ("i", "ppppplplppp" + "iii" + "pp"),
     "hb200_lstm_seq_bwd": ("i", "pppplppp" + "iii" + "pp"),
+    "hb200_gru_seq_fwd": ("i", "ppppplpp" + "iii" + "pp"),
+    "hb200_gru_seq_bwd": ("i", "pppplpppp" + "iii" + "pp"),
     "hb200_rnn_shift_mask": ("i", "pplpp" + "iii" + "p"),
     "hb200_colsum": ("i", "plplii" + "p"),
     "hb200_relu_bwd": ("i", "pplll" + "i" + "p"),

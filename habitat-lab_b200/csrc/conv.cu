@@ -51,6 +51,8 @@ struct ConvArgs {
   int OH, OW, OC;     // output grid and channels
   int kh, kw, stride, pad;
   int M, nchunks, cshift, gn_groups;
+  const float* bias;  // forward only: per-output-channel bias (SimpleCNN), or nullptr
+  int relu;           // forward only: ReLU in the epilogue
   int s2_classes;  // dgrad of a stride-2 conv: rows are grouped by output-pixel parity class (4 x M/4)
 };
 
@@ -259,6 +261,14 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
           }
         }
       }
+    }
+    if (MODE == 0 && a.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] += __ldg(a.bias + n0 + col0 + j);
+    }
+    if (MODE == 0 && a.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = fmaxf(acc[j], 0.f);
     }
     if (row_ok) {
       const size_t o = (size_t)m * a.OC + n0 + col0;
@@ -664,6 +674,29 @@ extern "C" int hb200_conv_fwd(const hb200_bf16* x, const hb200_bf16* w_packed, h
   a.cshift = ilog2(s->ci);
   a.gn_groups = gn_groups > 0 ? gn_groups : 1;
   a.s2_classes = 0;
+  a.bias = nullptr;
+  a.relu = 0;
+  return launch_igemm<0>(a, pick_bn(s->co), (cudaStream_t)stream);
+}
+
+/* forward with a per-channel bias and optional ReLU fused in the epilogue (SimpleCNN,
+ * habitat-baselines/habitat_baselines/rl/models/simple_cnn.py:68-93); output dims may use pad 0 */
+extern "C" int hb200_conv_bias_act_fwd(const hb200_bf16* x, const hb200_bf16* w_packed, const float* bias,
+                                       hb200_bf16* y, int relu, const hb200_conv_shape* s, hb200_stream_t stream) {
+  int rc = check_shape(s);
+  if (rc) return rc;
+  HB_CHECK_ARG(x && w_packed && y, "conv_bias_act_fwd: null pointer");
+  ConvArgs a;
+  a.src = (const __nv_bfloat16*)x; a.wimg = (const __nv_bfloat16*)w_packed; a.out = (__nv_bfloat16*)y;
+  a.addend = nullptr; a.stats = nullptr; a.bias = bias; a.relu = relu;
+  a.B = s->batch; a.SH = s->hi; a.SW = s->wi; a.SC = s->ci;
+  a.OH = s->ho; a.OW = s->wo; a.OC = s->co;
+  a.kh = s->kh; a.kw = s->kw; a.stride = s->stride; a.pad = s->pad;
+  a.M = s->batch * s->ho * s->wo;
+  a.nchunks = cdiv((long long)s->kh * s->kw * s->ci, kChunkK);
+  a.cshift = ilog2(s->ci);
+  a.gn_groups = 1;
+  a.s2_classes = 0;
   return launch_igemm<0>(a, pick_bn(s->co), (cudaStream_t)stream);
 }
 
@@ -684,6 +717,8 @@ extern "C" int hb200_conv_dgrad(const hb200_bf16* dy, const hb200_bf16* w_packed
   a.nchunks = cdiv((long long)s->kh * s->kw * s->co, kChunkK);
   a.cshift = ilog2(s->co);
   a.gn_groups = 1;
+  a.bias = nullptr;
+  a.relu = 0;
   a.s2_classes = (s->stride == 2 && s->co >= 64 && (s->hi % 2 == 0) && (s->wi % 2 == 0)) ? 1 : 0;
   return launch_igemm<1>(a, pick_bn(s->ci), (cudaStream_t)stream);
 }

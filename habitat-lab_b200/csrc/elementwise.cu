@@ -2,8 +2,15 @@
 // input prep (u8/f32 gather + 2x2 mean + running mean/var), GroupNorm apply / residual / maxpool,
 // GroupNorm backward (reduce + apply), maxpool backward, dtype converts, goal/action embeddings.
 #include "common.cuh"
+#include "umma.cuh"
+#include <cooperative_groups.h>
 
 namespace hb200 {
+namespace cg = cooperative_groups;
+using umma::cp_async16;
+using umma::cp_async_commit;
+using umma::cp_async_wait;
+using umma::smem_u32;
 void count_launch(int n);
 
 static inline int grid_for(long long n, int bs) {
@@ -352,6 +359,81 @@ gn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfloat16
   }
 }
 
+// Row-slab variant: a CTA stages rows+1 input rows (one halo row above) in shared memory with cp.async and pools
+// from there, so y crosses HBM once (plus 1/rows re-read of the halo row) in fully coalesced 16-byte copies.  The
+// window maximum is taken on x * sign(rstd*gamma) (the affine map is monotonic per channel) and the affine + ReLU
+// applied once per output.
+__global__ void __launch_bounds__(256)
+gn_relu_maxpool_slab_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfloat16* __restrict__ out,
+                            uint8_t* __restrict__ argmax, int H, int W, int rows) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  uint4* sy = reinterpret_cast<uint4*>(gsm);
+  const int cv = p.C >> 3, Ho = H >> 1, Wo = W >> 1, nslab = H / rows;
+  const int b = blockIdx.x / nslab, slab = blockIdx.x - b * nslab;
+  const int iy0 = slab * rows, yrow = W * cv;
+  const int tid = threadIdx.x;
+  {
+    const int lr0 = iy0 == 0 ? 1 : 0;  // local row 0 is input row iy0-1 (absent for the first slab)
+    const uint4* gy = reinterpret_cast<const uint4*>(y) + ((size_t)b * H + iy0 - 1 + lr0) * yrow;
+    const uint32_t ay = smem_u32(sy) + lr0 * yrow * 16;
+    const int n = (rows + 1 - lr0) * yrow;
+    for (int i = tid; i < n; i += 256) cp_async16(ay + i * 16, gy + i, true);
+    cp_async_commit();
+  }
+  const int vec = tid % cv, c0 = vec << 3;
+  float sg[8], za[8], zd[8];
+  {
+    float mu[8], rs[8], ga[8], be[8];
+    gn_coeffs(p, b, c0, mu, rs);
+    load8f(p.gamma + c0, ga);
+    load8f(p.beta + c0, be);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float zc = rs[e] * ga[e];
+      sg[e] = zc < 0.f ? -1.f : 1.f;
+      za[e] = fabsf(zc);
+      zd[e] = fmaf(-mu[e], zc, be[e]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  const int nout = (rows >> 1) * Wo * cv;
+  uint4* o4 = reinterpret_cast<uint4*>(out) + ((size_t)b * Ho + (iy0 >> 1)) * Wo * cv;
+  uint2* a2 = reinterpret_cast<uint2*>(argmax) + ((size_t)b * Ho + (iy0 >> 1)) * Wo * cv;
+  for (int it = tid; it < nout; it += 256) {
+    const int pos = it / cv, ol = pos / Wo, ox = pos - ol * Wo;
+    float best[8];
+    int arg[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int lr = 2 * ol + r;  // local row; input row iy0 - 1 + lr
+      if (iy0 + lr < 1) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = 2 * ox - 1 + s;
+        if (ix < 0) continue;
+        float x[8];
+        unpack8(sy[(lr * W + ix) * cv + vec], x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xs = x[e] * sg[e];
+          if (xs > best[e]) { best[e] = xs; arg[e] = r * 3 + s; }
+        }
+      }
+    }
+    float z[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) z[e] = fmaxf(fmaf(best[e], za[e], zd[e]), 0.f);
+    o4[it] = pack8(z);
+    uint2 a;
+    a.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
+    a.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
+    a2[it] = a;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax,
                    __nv_bfloat16* __restrict__ dz, int B, int H, int W, int C) {
@@ -495,6 +577,311 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
     reinterpret_cast<uint4*>(dy)[i] = pack8(o);
     if (gz_out) reinterpret_cast<uint4*>(gz_out)[i] = pack8(gz);
   }
+}
+
+// GroupNorm (+ReLU) backward, frame held ON CHIP: a thread-block cluster owns one frame, each CTA of the cluster
+// stages its pixel slice of g / y (/ act) in shared memory with cp.async (every thread later consumes exactly the
+// 16-byte vectors it copied, so no block barrier is needed between copy and use), reduces the per-channel sums,
+// exchanges them with its peers through distributed shared memory, then writes dy (/ gz) from the staged copy.
+// HBM traffic is the algorithmic minimum (every operand read once, every result written once); slices are sized
+// to <= 48 KB so 4+ CTAs are resident per SM and the copy / reduce / write phases of different frames overlap.
+
+// Shared tail of the cluster GroupNorm-backward kernels: per-thread partial sums (a = sum gz, bx = sum gz*x over
+// the thread's elements of channel vector `vec`) -> warp shuffle -> CTA -> cluster (DSMEM) -> dgamma/dbeta atomics
+// (cluster rank 0) -> per-group S1/S2 -> the per-channel dy coefficients c2, c3.  Ends with a cluster
+// barrier ARRIVE; the caller must execute the matching WAIT before it exits.
+__device__ __forceinline__ void gn_bwd_cluster_sums(cg::cluster_group& cluster, const GnP& p, int b, int CS, int rank,
+                                                    int c0, float (&a)[8], float (&bx)[8], float* part, float* tot,
+                                                    float* wred, float* gS, float* __restrict__ dgamma,
+                                                    float* __restrict__ dbeta, float (&c2)[8], float (&c3)[8]) {
+  const int C = p.C, G = p.G, cv = C >> 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // lanes l, l+cv, l+2cv, ... of a warp own the same channel vector
+  for (int o = cv; o < 32; o <<= 1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      a[e] += __shfl_xor_sync(0xffffffffu, a[e], o);
+      bx[e] += __shfl_xor_sync(0xffffffffu, bx[e], o);
+    }
+  }
+  if (lane < cv) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      wred[warp * 2 * C + c0 + e] = a[e];
+      wred[warp * 2 * C + C + c0 + e] = bx[e];
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < 2 * C; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += wred[w * 2 * C + c];
+    part[c] = t;
+  }
+  cluster.sync();
+  for (int c = tid; c < C; c += 256) {
+    float ta = 0.f, tx = 0.f;
+    for (int r = 0; r < CS; ++r) {
+      const float* pr = cluster.map_shared_rank(part, r);
+      ta += pr[c];
+      tx += pr[C + c];
+    }
+    const float2 st = *reinterpret_cast<const float2*>(p.stats + ((size_t)b * G + (c >> p.lcpg)) * 2);
+    const float m = st.x * p.inv_m;
+    const float r = rsqrtf(fmaxf(st.y * p.inv_m - m * m, 0.f) + p.eps);
+    const float tb = r * (tx - m * ta);  // sum gz * xhat
+    tot[c] = ta;
+    tot[C + c] = tb;
+    if (rank == 0) {
+      atomicAdd(&dbeta[c], ta);
+      atomicAdd(&dgamma[c], tb);
+    }
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");  // peers may exit once all have read
+  __syncthreads();
+  const int cpg = 1 << p.lcpg;
+  for (int gi = tid; gi < G; gi += 256) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+      const float gm = p.gamma[c];
+      s1 = fmaf(gm, tot[c], s1);
+      s2 = fmaf(gm, tot[C + c], s2);
+    }
+    gS[gi] = s1;
+    gS[G + gi] = s2;
+  }
+  __syncthreads();
+  // dy = zc*gz - xhat*k3 - k2  with xhat = (x - mu)*rs, k2 = rs*S1/m, k3 = rs*S2/m   ==  zc*gz + (x*c3 + c2)
+  {
+    float mu[8], rs[8];
+    gn_coeffs(p, b, c0, mu, rs);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int gi = (c0 + e) >> p.lcpg;
+      const float k2 = rs[e] * p.inv_m * gS[gi], k3 = rs[e] * p.inv_m * gS[G + gi];
+      c3[e] = -rs[e] * k3;
+      c2[e] = fmaf(mu[e] * rs[e], k3, -k2);
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 4)
+gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act,
+                      const __nv_bfloat16* __restrict__ y, GnP p, float* __restrict__ dgamma,
+                      float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dy,
+                      __nv_bfloat16* __restrict__ gz_out, int hw, int ppc) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / CS;
+  const int cv = p.C >> 3, C = p.C, G = p.G;
+  const int pix0 = rank * ppc, pix1 = min(hw, pix0 + ppc);
+  const int n = max(pix1 - pix0, 0) * cv, ncap = ppc * cv;
+  uint4* sg = reinterpret_cast<uint4*>(gsm);
+  uint4* sy = sg + ncap;
+  uint4* sact = sy + ncap;
+  float* part = reinterpret_cast<float*>(sy + (MODE == 2 ? 2 : 1) * ncap);  // [2C] this CTA's channel sums
+  float* tot = part + 2 * C;                                                  // [2C] cluster totals
+  float* wred = tot + 2 * C;                                                  // [8][2C]
+  float* gS = wred + 16 * C;                                                  // [2G]
+  const size_t base = ((size_t)b * hw + pix0) * cv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const uint4* gg = reinterpret_cast<const uint4*>(g) + base;
+    const uint4* gy = reinterpret_cast<const uint4*>(y) + base;
+    const uint4* ga = reinterpret_cast<const uint4*>(act) + base;
+    const uint32_t ag = smem_u32(sg), ay = smem_u32(sy), aa = smem_u32(sact);
+    for (int i = tid; i < n; i += 256) {
+      cp_async16(ag + i * 16, gg + i, true);
+      cp_async16(ay + i * 16, gy + i, true);
+      if (MODE == 2) cp_async16(aa + i * 16, ga + i, true);
+    }
+    cp_async_commit();
+  }
+  const int vec = tid % cv, c0 = vec << 3;
+  // z = x*zc + zd (only its sign is needed: the ReLU mask); zc = rstd*gamma is also the dy coefficient of gz
+  float zc[8], zd[8];
+  {
+    float mu[8], rs[8], ga[8], be[8];
+    gn_coeffs(p, b, c0, mu, rs);
+    load8f(p.gamma + c0, ga);
+    load8f(p.beta + c0, be);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { zc[e] = rs[e] * ga[e]; zd[e] = fmaf(-mu[e], zc[e], be[e]); }
+  }
+  cp_async_wait<0>();
+  float a[8], bx[8];  // sum gz, sum gz*x (raw x; converted to sum gz*xhat per channel below)
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = 0.f; bx[e] = 0.f; }
+  for (int i = tid; i < n; i += 256) {
+    float gg[8], x[8], ac[8];
+    unpack8(sg[i], gg);
+    unpack8(sy[i], x);
+    if (MODE == 2) unpack8(sact[i], ac);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float gz = gg[e];
+      if (MODE == 1) gz = fmaf(x[e], zc[e], zd[e]) > 0.f ? gz : 0.f;
+      if (MODE == 2) gz = ac[e] > 0.f ? gz : 0.f;
+      a[e] += gz;
+      bx[e] = fmaf(gz, x[e], bx[e]);
+    }
+  }
+  float c2[8], c3[8];
+  gn_bwd_cluster_sums(cluster, p, b, CS, rank, c0, a, bx, part, tot, wred, gS, dgamma, dbeta, c2, c3);
+  uint4* od = reinterpret_cast<uint4*>(dy) + base;
+  uint4* oz = reinterpret_cast<uint4*>(gz_out) + base;
+  for (int i = tid; i < n; i += 256) {
+    float gg[8], x[8], ac[8], gz[8], o[8];
+    unpack8(sg[i], gg);
+    unpack8(sy[i], x);
+    if (MODE == 2) unpack8(sact[i], ac);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gz[e] = gg[e];
+      if (MODE == 1) gz[e] = fmaf(x[e], zc[e], zd[e]) > 0.f ? gz[e] : 0.f;
+      if (MODE == 2) gz[e] = ac[e] > 0.f ? gz[e] : 0.f;
+      o[e] = fmaf(zc[e], gz[e], fmaf(x[e], c3[e], c2[e]));
+    }
+    od[i] = pack8(o);
+    if (gz_out) oz[i] = pack8(gz);
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Stem backward: MaxPool(3,2,1) backward + ReLU backward + GroupNorm backward in one pass.  The full-resolution
+// gradient of the pooled activation is never materialised: every CTA stages its rows of y plus the pooled-gradient /
+// argmax rows that can route into them (R/2+1 pooled rows for R input rows), and evaluates
+//   gz(iy,ix,c) = [z > 0] * sum over the <= 4 windows (oy,ox) containing (iy,ix) of [argmax(oy,ox,c) == tap] * dpool
+// from shared memory in both phases.  Reference: resnet.py:244-252 (conv1 / GroupNorm / ReLU / MaxPool2d).
+// gz += [argmax == code] * dpool for the 8 channels of one pooled window (o = its vector index in the staged rows)
+__device__ __forceinline__ void pool_take(const uint4* __restrict__ sdp, const uint2* __restrict__ sarg, int o,
+                                          uint32_t code, float (&gz)[8]) {
+  const uint2 am = sarg[o];
+  const uint4 dp = sdp[o];
+  const uint32_t c4 = code * 0x01010101u;
+  const uint32_t m0 = __vcmpeq4(am.x, c4), m1 = __vcmpeq4(am.y, c4);  // 0xff per matching channel
+  const float2 f0 = unpack_bf16x2(dp.x & __byte_perm(m0, 0, 0x1100));
+  const float2 f1 = unpack_bf16x2(dp.y & __byte_perm(m0, 0, 0x3322));
+  const float2 f2 = unpack_bf16x2(dp.z & __byte_perm(m1, 0, 0x1100));
+  const float2 f3 = unpack_bf16x2(dp.w & __byte_perm(m1, 0, 0x3322));
+  gz[0] += f0.x; gz[1] += f0.y; gz[2] += f1.x; gz[3] += f1.y;
+  gz[4] += f2.x; gz[5] += f2.y; gz[6] += f3.x; gz[7] += f3.y;
+}
+
+// Pooled gradient routed to input pixel (2k+DY, 2j+DX): the windows containing it and the tap it is in each are
+// compile-time constants (row 2k: window k tap r=1; row 2k+1: window k tap 2 and window k+1 tap 0; same for columns).
+// o00 = vector index of window (k, j) in the staged pooled rows; row_ok / col_ok: windows k+1 / j+1 exist.
+template <int DY, int DX>
+__device__ __forceinline__ void pool_route_px(const uint4* __restrict__ sdp, const uint2* __restrict__ sarg, int o00,
+                                              int wrow, int cv, bool row_ok, bool col_ok, float (&gz)[8]) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) gz[e] = 0.f;
+  constexpr int r0 = DY == 0 ? 1 : 2, s0 = DX == 0 ? 1 : 2;
+  pool_take(sdp, sarg, o00, r0 * 3 + s0, gz);
+  if (DX == 1 && col_ok) pool_take(sdp, sarg, o00 + cv, r0 * 3 + 0, gz);
+  if (DY == 1 && row_ok) {
+    pool_take(sdp, sarg, o00 + wrow, 0 * 3 + s0, gz);
+    if (DX == 1 && col_ok) pool_take(sdp, sarg, o00 + wrow + cv, 0, gz);
+  }
+}
+
+__global__ void __launch_bounds__(256, 3)
+gn_pool_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ argmax,
+                           const __nv_bfloat16* __restrict__ y, GnP p, float* __restrict__ dgamma,
+                           float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dy, int H, int W, int rows) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / CS;
+  const int cv = p.C >> 3, C = p.C, G = p.G, Ho = H >> 1, Wo = W >> 1;
+  const int iy0 = rank * rows, oy0 = iy0 >> 1;           // rows is even
+  const int prow = min(rows / 2 + 1, Ho - oy0);          // pooled rows that can route into this slice
+  const int n = rows * W * cv, npool = prow * Wo * cv, pcap = (rows / 2 + 1) * Wo * cv;
+  uint4* sy = reinterpret_cast<uint4*>(gsm);
+  uint4* sdp = sy + n;
+  uint2* sarg = reinterpret_cast<uint2*>(sdp + pcap);
+  float* part = reinterpret_cast<float*>(sarg + pcap);
+  float* tot = part + 2 * C;
+  float* wred = tot + 2 * C;
+  float* gS = wred + 16 * C;
+  const size_t base = ((size_t)b * H + iy0) * W * cv;
+  const int tid = threadIdx.x;
+  {
+    const uint4* gy = reinterpret_cast<const uint4*>(y) + base;
+    const size_t pbase = ((size_t)b * Ho + oy0) * Wo * cv;
+    const uint4* gd = reinterpret_cast<const uint4*>(dpool) + pbase;
+    const uint4* gm = reinterpret_cast<const uint4*>(argmax + pbase * 8);
+    const uint32_t ay = smem_u32(sy), ad = smem_u32(sdp), am = smem_u32(sarg);
+    for (int i = tid; i < n; i += 256) cp_async16(ay + i * 16, gy + i, true);
+    for (int i = tid; i < npool; i += 256) cp_async16(ad + i * 16, gd + i, true);
+    for (int i = tid; i < npool / 2; i += 256) cp_async16(am + i * 16, gm + i, true);
+    cp_async_commit();
+  }
+  const int vec = tid % cv, c0 = vec << 3;
+  float zc[8], zd[8];
+  {
+    float mu[8], rs[8], ga[8], be[8];
+    gn_coeffs(p, b, c0, mu, rs);
+    load8f(p.gamma + c0, ga);
+    load8f(p.beta + c0, be);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { zc[e] = rs[e] * ga[e]; zd[e] = fmaf(-mu[e], zc[e], be[e]); }
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // staged rows are consumed by other threads than the ones that copied them
+  const int nblk = (rows >> 1) * Wo * cv;  // 2x2 input blocks x channel vectors; thread = (block, vec)
+  const int wrow = Wo * cv, yrow = W * cv;
+  float a[8], bx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = 0.f; bx[e] = 0.f; }
+#define HB_POOL_PIXEL(DY, DX, BODY)                                                    \
+  {                                                                                    \
+    float gz[8], x[8];                                                                 \
+    pool_route_px<DY, DX>(sdp, sarg, o00, wrow, cv, row_ok, col_ok, gz);               \
+    const int yi = ((2 * kb + DY) * W + 2 * j + DX) * cv + vec;                        \
+    unpack8(sy[yi], x);                                                                \
+    BODY                                                                               \
+  }
+  for (int it = tid; it < nblk; it += 256) {
+    const int pos = it / cv, kb = pos / Wo, j = pos - kb * Wo;
+    const int o00 = (kb * Wo + j) * cv + vec;
+    const bool row_ok = oy0 + kb + 1 < Ho, col_ok = j + 1 < Wo;
+#define HB_BODY1                                                                       \
+  _Pragma("unroll") for (int e = 0; e < 8; ++e) {                                      \
+    const float gm = fmaf(x[e], zc[e], zd[e]) > 0.f ? gz[e] : 0.f;                     \
+    a[e] += gm;                                                                        \
+    bx[e] = fmaf(gm, x[e], bx[e]);                                                     \
+  }
+    HB_POOL_PIXEL(0, 0, HB_BODY1)
+    HB_POOL_PIXEL(0, 1, HB_BODY1)
+    HB_POOL_PIXEL(1, 0, HB_BODY1)
+    HB_POOL_PIXEL(1, 1, HB_BODY1)
+#undef HB_BODY1
+  }
+  float c2[8], c3[8];
+  gn_bwd_cluster_sums(cluster, p, b, CS, rank, c0, a, bx, part, tot, wred, gS, dgamma, dbeta, c2, c3);
+  uint4* od = reinterpret_cast<uint4*>(dy) + base;
+  for (int it = tid; it < nblk; it += 256) {
+    const int pos = it / cv, kb = pos / Wo, j = pos - kb * Wo;
+    const int o00 = (kb * Wo + j) * cv + vec;
+    const bool row_ok = oy0 + kb + 1 < Ho, col_ok = j + 1 < Wo;
+#define HB_BODY2                                                                       \
+  float o[8];                                                                          \
+  _Pragma("unroll") for (int e = 0; e < 8; ++e) {                                      \
+    const float gm = fmaf(x[e], zc[e], zd[e]) > 0.f ? gz[e] : 0.f;                     \
+    o[e] = fmaf(zc[e], gm, fmaf(x[e], c3[e], c2[e]));                                  \
+  }                                                                                    \
+  od[yi] = pack8(o);
+    HB_POOL_PIXEL(0, 0, HB_BODY2)
+    HB_POOL_PIXEL(0, 1, HB_BODY2)
+    HB_POOL_PIXEL(1, 0, HB_BODY2)
+    HB_POOL_PIXEL(1, 1, HB_BODY2)
+#undef HB_BODY2
+  }
+#undef HB_POOL_PIXEL
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // One block per frame: phase 1 reduces (dgamma/dbeta atomics + per-group sums kept in shared memory),
@@ -805,6 +1192,71 @@ __global__ void transpose_f32_kernel(const float* __restrict__ src, long long ld
   }
 }
 
+// SimpleCNN input: rgb/255 and raw depth concatenated, NHWC bf16 padded to 8 channels, no pooling
+// (simple_cnn.py:139-157).  One thread per pixel.
+__global__ void prep_plain_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ depth,
+                                  const int32_t* __restrict__ rows, long long npix_per_frame, int B, int c_rgb,
+                                  int c_depth, __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)B * npix_per_frame;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / npix_per_frame);
+    const long long p = i - (long long)f * npix_per_frame;
+    const size_t src = (size_t)rows[f] * npix_per_frame + p;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < c_rgb; ++c) v[c] = (float)rgb[src * c_rgb + c] / 255.0f;
+    for (int c = 0; c < c_depth; ++c) v[c_rgb + c] = depth[src * c_depth + c];
+    reinterpret_cast<uint4*>(out)[i] = pack8(v);
+  }
+}
+// backward of (conv + bias) -> ReLU: dy = g * (out > 0); dbias[c] += sum dy   (out = post-ReLU activation)
+__global__ void __launch_bounds__(256)
+relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out, int use_mask,
+                     __nv_bfloat16* __restrict__ dy, float* __restrict__ dbias, long long npix, int C) {
+  __shared__ float sacc[256][9];
+  const int cv = C >> 3;
+  const int vec = threadIdx.x % cv, pl = threadIdx.x / cv, npl = blockDim.x / cv;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long pix = (long long)blockIdx.x * npl + pl; pix < npix; pix += (long long)gridDim.x * npl) {
+    const size_t o = (size_t)pix * cv + vec;
+    float gg[8], oo[8];
+    unpack8(reinterpret_cast<const uint4*>(g)[o], gg);
+    if (use_mask) {
+      unpack8(reinterpret_cast<const uint4*>(out)[o], oo);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gg[e] = oo[e] > 0.f ? gg[e] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += gg[e];
+    if (dy) reinterpret_cast<uint4*>(dy)[o] = pack8(gg);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sacc[threadIdx.x][e] = acc[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < npl; ++q) t += sacc[q * cv + (c >> 3)][c & 7];
+    atomicAdd(&dbias[c], t);
+  }
+}
+// bf16 NHWC [B,hw,C] -> f32 [B, C*hw] flattened in (c,h,w) order (nn.Flatten of the NCHW map)
+__global__ void bf16_hwc_to_f32_chw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int B,
+                                           int hw, int C) {
+  const int cv = C >> 3;
+  const long long total = (long long)B * hw * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) << 3;
+    const long long t = i / cv;
+    const int p = (int)(t % hw);
+    const int b = (int)(t / hw);
+    float f[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[i], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[((size_t)b * C + c0 + e) * hw + p] = f[e];
+  }
+}
+
 static int ilog2i(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;
@@ -946,6 +1398,23 @@ extern "C" int hb200_gn_relu_maxpool(const hb200_bf16* y, const float* stats, co
   int rc = make_gn(p, stats, gamma, beta, channels, groups, h * w, eps);
   if (rc) return rc;
   HB_CHECK_ARG(y && out && argmax && h % 2 == 0 && w % 2 == 0, "gn_relu_maxpool: bad args");
+  {
+    // slab path: largest even row count <= 8 dividing h whose rows+1 staged rows fit in 64 KB
+    const int cv = channels / 8;
+    int rows = 0;
+    for (int r = 8; r >= 2; r -= 2)
+      if (h % r == 0 && (size_t)(r + 1) * w * channels * 2 <= 64 * 1024) { rows = r; break; }
+    if (rows && cv <= 32 && 256 % cv == 0) {
+      const size_t smem = (size_t)(rows + 1) * w * channels * 2;
+      auto kern = gn_relu_maxpool_slab_kernel;
+      HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<batch * (h / rows), 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, (__nv_bfloat16*)out,
+                                                                    argmax, h, w, rows);
+      HB_LAUNCH_OK();
+      count_launch(1);
+      return HB200_OK;
+    }
+  }
   const long long total = (long long)batch * (h / 2) * (w / 2) * (channels / 8);
   gn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)y, p, (__nv_bfloat16*)out, argmax, batch, h, w);
@@ -1114,6 +1583,42 @@ extern "C" int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb
   HB_CHECK_ARG(mask_mode >= 0 && mask_mode <= 2 && (mask_mode != 2 || act), "gn_bwd: bad mask_mode");
   const int cv = channels / 8;
   HB_CHECK_ARG(cv >= 1 && cv <= 256 && 256 % cv == 0, "gn_bwd: C/8 = %d must divide 256", cv);
+  if (cv <= 32) {
+    // cluster path: smallest cluster whose per-CTA slice is <= 48 KB (<= 200 KB at the portable maximum of 8)
+    const int ntens = mask_mode == 2 ? 3 : 2;
+    int cs = 1, ppc = hw;
+    size_t slice = 0;
+    for (;; cs *= 2) {
+      ppc = (hw + cs - 1) / cs;
+      slice = (size_t)ntens * ppc * channels * 2;
+      if (slice <= 48 * 1024 || cs == 8) break;
+    }
+    const size_t smem = slice + sizeof(float) * (20 * (size_t)channels + 2 * (size_t)groups);
+    if (smem <= 200 * 1024) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)batch * cs);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = (cudaStream_t)stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      const __nv_bfloat16 *G_ = (const __nv_bfloat16*)g, *A_ = (const __nv_bfloat16*)act, *Y_ = (const __nv_bfloat16*)y;
+      __nv_bfloat16 *D_ = (__nv_bfloat16*)dy, *Z_ = (__nv_bfloat16*)gz_out;
+#define HB_GNB_CASE(m)                                                                                       \
+  {                                                                                                          \
+    auto kern = gn_bwd_cluster_kernel<m>;                                                                    \
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+    HB_CUDA(cudaLaunchKernelEx(&cfg, kern, G_, A_, Y_, p, dgamma, dbeta, D_, Z_, hw, ppc));                  \
+  }
+      if (mask_mode == 0) HB_GNB_CASE(0) else if (mask_mode == 1) HB_GNB_CASE(1) else HB_GNB_CASE(2)
+#undef HB_GNB_CASE
+      count_launch(1);
+      return HB200_OK;
+    }
+  }
   const size_t smem = sizeof(float) * (2 * (size_t)channels + 2 * (size_t)groups);
   gn_bwd_fused_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)g, (const __nv_bfloat16*)act, (const __nv_bfloat16*)y, p, dgamma, dbeta,
@@ -1123,11 +1628,103 @@ extern "C" int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb
   return HB200_OK;
 }
 
+// rows per CTA for the fused stem backward: smallest cluster (1..8 CTAs per frame) whose slice fits; 0 = unsupported
+static int gn_pool_bwd_plan(int h, int w, int channels, int groups, int* cs_out, size_t* smem_out) {
+  const int cv = channels / 8;
+  if (channels % 8 || cv < 1 || cv > 32 || 256 % cv || h % 2 || w % 2) return 0;
+  for (int cs = 1; cs <= 8; cs *= 2) {
+    if (h % (2 * cs)) continue;
+    const int rows = h / cs;
+    const size_t bytes = (size_t)rows * w * channels * 2 + (size_t)(rows / 2 + 1) * (w / 2) * channels * 3 +
+                         sizeof(float) * (20 * (size_t)channels + 2 * (size_t)groups);
+    if (bytes <= 50 * 1024 || (cs == 8 && bytes <= 200 * 1024)) {
+      *cs_out = cs;
+      *smem_out = bytes;
+      return rows;
+    }
+  }
+  return 0;
+}
+
+extern "C" int hb200_gn_relu_maxpool_bwd_supported(int h, int w, int channels, int groups) {
+  int cs = 0;
+  size_t smem = 0;
+  return gn_pool_bwd_plan(h, w, channels, groups, &cs, &smem) > 0;
+}
+
+extern "C" int hb200_gn_relu_maxpool_bwd(const hb200_bf16* dpool, const uint8_t* argmax, const hb200_bf16* y,
+                                         const float* stats, const float* gamma, const float* beta, float* dgamma,
+                                         float* dbeta, hb200_bf16* dy, int batch, int h, int w, int channels,
+                                         int groups, float eps, hb200_stream_t stream) {
+  GnP p;
+  int rc = make_gn(p, stats, gamma, beta, channels, groups, h * w, eps);
+  if (rc) return rc;
+  HB_CHECK_ARG(dpool && argmax && y && dgamma && dbeta && dy && batch > 0, "gn_relu_maxpool_bwd: null pointer");
+  int cs = 0;
+  size_t smem = 0;
+  const int rows = gn_pool_bwd_plan(h, w, channels, groups, &cs, &smem);
+  if (rows <= 0) {
+    set_last_error("gn_relu_maxpool_bwd: unsupported shape %dx%dx%d (use maxpool_bwd + gn_bwd)", h, w, channels);
+    return HB200_ERR_UNSUPPORTED;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)batch * cs);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  auto kern = gn_pool_bwd_cluster_kernel;
+  HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HB_CUDA(cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16*)dpool, argmax, (const __nv_bfloat16*)y, p, dgamma, dbeta,
+                             (__nv_bfloat16*)dy, h, w, rows));
+  count_launch(1);
+  return HB200_OK;
+}
+
 extern "C" int hb200_transpose_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int rows,
                                    int cols, hb200_stream_t stream) {
   HB_CHECK_ARG(src && dst && rows > 0 && cols > 0 && ld_src >= cols && ld_dst >= rows, "transpose_f32: bad args");
   dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
   transpose_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst, ld_dst, rows, cols);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_prep_plain(const uint8_t* rgb, const float* depth, const int32_t* frame_rows, int batch,
+                                int height, int width, int c_rgb, int c_depth, hb200_bf16* out,
+                                hb200_stream_t stream) {
+  HB_CHECK_ARG(frame_rows && out && batch > 0 && c_rgb + c_depth > 0 && c_rgb + c_depth <= 8, "prep_plain: bad args");
+  HB_CHECK_ARG((c_rgb == 0 || rgb) && (c_depth == 0 || depth), "prep_plain: missing sensor buffer");
+  const long long total = (long long)batch * height * width;
+  prep_plain_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(rgb, depth, frame_rows,
+                                                                            (long long)height * width, batch, c_rgb,
+                                                                            c_depth, (__nv_bfloat16*)out);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+extern "C" int hb200_relu_bias_bwd(const hb200_bf16* g, const hb200_bf16* out, hb200_bf16* dy, float* dbias,
+                                   long long npix, int channels, hb200_stream_t stream) {
+  HB_CHECK_ARG(g && dbias && npix > 0 && channels % 8 == 0 && 256 % (channels / 8) == 0, "relu_bias_bwd: bad args");
+  int grid = (int)((npix + 255) / 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (grid < 1) grid = 1;
+  relu_bias_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)out,
+                                                               out != nullptr, (__nv_bfloat16*)dy, dbias, npix, channels);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+extern "C" int hb200_bf16_hwc_to_f32_chw(const hb200_bf16* x, float* out, int batch, int hw, int channels,
+                                         hb200_stream_t stream) {
+  HB_CHECK_ARG(x && out && batch > 0 && hw > 0 && channels % 8 == 0, "bf16_hwc_to_f32_chw: bad args");
+  const long long total = (long long)batch * hw * (channels / 8);
+  bf16_hwc_to_f32_chw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, batch, hw, channels);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;

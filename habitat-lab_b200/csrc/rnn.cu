@@ -461,3 +461,195 @@ extern "C" int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const
   count_launch(1);
   return HB200_OK;
 }
+
+// =====================================================================================
+// GRU (rnn_type GRU: PointNavBaselinePolicy / config #1, ObjectNav config #3), PyTorch gate order r,z,n:
+//   r = sig(xr + Whr h + bhr)   z = sig(xz + Whz h + bhz)   n = tanh(xn + r * (Whn h + bhn))
+//   h' = (1 - z) * n + z * h          with h = h_{t-1} * m_t  (mask resets before the step)
+// xproj [T*n, 3H] = x W_ih^T + b_ih (one GEMM for all frames); same persistent cooperative structure as
+// the LSTM kernels: one CTA = 4 hidden units (12 gate rows of W_hh in shared memory).
+// saved [T,n,4H] = (r, z, n, hn_pre = Whn h + bhn) for the backward pass.
+// =====================================================================================
+namespace hb200 {
+
+template <int NJ>
+__global__ void __launch_bounds__(kSeqThreads)
+gru_seq_fwd_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh,
+                   const float* __restrict__ b_hh, const uint8_t* __restrict__ masks,
+                   const float* __restrict__ h0, long long h0_stride, float* __restrict__ hs,
+                   float* __restrict__ saved, int T, int n, unsigned* counter) {
+  constexpr int H = NJ * 32;
+  extern __shared__ float sw[];  // [16][H]: rows 0..11 = (gate, unit), rows 12..15 zero padding
+  const int u0 = blockIdx.x * kUnits;
+  for (int i = threadIdx.x; i < 16 * H; i += blockDim.x) {
+    const int r = i / H, k = i - r * H;
+    sw[i] = (r < 12) ? w_hh[((size_t)(r >> 2) * H + u0 + (r & 3)) * H + k] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int row = lane >> 1, gate = row >> 2, unit = row & 3, col = u0 + unit;
+  const float bias = (b_hh && gate < 3) ? b_hh[(size_t)gate * H + col] : 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float* hp = t == 0 ? h0 : hs + (size_t)(t - 1) * n * H;
+    const long long hps = t == 0 ? h0_stride : H;
+    for (int s = warp; s < n; s += nwarps) {
+      const float m = masks[(size_t)t * n + s] ? 1.f : 0.f;
+      float hv[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) hv[j] = __ldcg(hp + (size_t)s * hps + lane + 32 * j);
+      const float xp = gate < 3 ? xproj[((size_t)t * n + s) * 3 * H + (size_t)gate * H + col] : 0.f;
+      const float hprev = __ldcg(hp + (size_t)s * hps + col) * m;
+      float part[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc = fmaf(hv[j], sw[r * H + lane + 32 * j], acc);
+        part[r] = acc;
+      }
+      const float hdot = warp_reduce16(part, lane) * m + bias;  // W_h* (h*m) + b_h*   for this lane's row
+      // lanes 2*unit hold r-row, 2*(4+unit) z-row, 2*(8+unit) n-row
+      const float hr = __shfl_sync(0xffffffffu, hdot, 2 * unit), xr = __shfl_sync(0xffffffffu, xp, 2 * unit);
+      const float hz = __shfl_sync(0xffffffffu, hdot, 2 * (4 + unit)), xz = __shfl_sync(0xffffffffu, xp, 2 * (4 + unit));
+      const float hn = __shfl_sync(0xffffffffu, hdot, 2 * (8 + unit)), xn = __shfl_sync(0xffffffffu, xp, 2 * (8 + unit));
+      if (lane < 8 && (lane & 1) == 0) {
+        const float r_ = sigmoidf_(xr + hr), z_ = sigmoidf_(xz + hz);
+        const float n_ = tanhf(xn + r_ * hn);
+        const size_t o = ((size_t)t * n + s) * H + col;
+        hs[o] = (1.f - z_) * n_ + z_ * hprev;
+        if (saved) {
+          float* sp = saved + ((size_t)t * n + s) * 4 * H;
+          sp[col] = r_; sp[H + col] = z_; sp[2 * H + col] = n_; sp[3 * H + col] = hn;
+        }
+      }
+    }
+    if (t + 1 < T) grid_barrier(counter, (unsigned)(t + 1) * gridDim.x);
+  }
+}
+
+// dgx [T,n,3H] = d(xproj) = (dr_pre, dz_pre, dn_pre);  dgh [T,n,3H] = d(h-side pre-activations) =
+// (dr_pre, dz_pre, dn_pre * r).  dh_{t-1} = m_t * (dh * z + dgh W_hh).
+__global__ void __launch_bounds__(kSeqThreads)
+gru_seq_bwd_kernel(const float* __restrict__ dh_out, const float* __restrict__ saved,
+                   const float* __restrict__ hs, const float* __restrict__ h0, long long h0_stride,
+                   const float* __restrict__ w_hh, const uint8_t* __restrict__ masks,
+                   float* __restrict__ dgx, float* __restrict__ dgh, int T, int n, int H, unsigned* counter) {
+  extern __shared__ __align__(16) float smem[];
+  const int R = 3 * H;
+  float* wt = smem;               // [4][R]
+  float* dh_rec = smem + 4 * R;   // [n][4]
+  const int u0 = blockIdx.x * kUnits;
+  for (int i = threadIdx.x; i < 4 * R; i += blockDim.x) {
+    const int u = i / R, r = i - u * R;
+    wt[i] = w_hh[(size_t)r * H + u0 + u];
+  }
+  for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) dh_rec[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int t = T - 1; t >= 0; --t) {
+    for (int i = threadIdx.x; i < 4 * n; i += blockDim.x) {
+      const int s = i >> 2, col = u0 + (i & 3);
+      const size_t row = (size_t)t * n + s;
+      const float m = masks[row] ? 1.f : 0.f;
+      const float* sp = saved + row * 4 * H;
+      const float r_ = sp[col], z_ = sp[H + col], n_ = sp[2 * H + col], hn = sp[3 * H + col];
+      const float hin = (t == 0 ? h0[(size_t)s * h0_stride + col] : hs[(row - n) * H + col]) * m;
+      const float dh = dh_out[row * H + col] + dh_rec[i];
+      const float dn_pre = dh * (1.f - z_) * (1.f - n_ * n_);
+      const float dz_pre = dh * (hin - n_) * z_ * (1.f - z_);
+      const float dr_pre = dn_pre * hn * r_ * (1.f - r_);
+      float* gx = dgx + row * R;
+      float* gh = dgh + row * R;
+      gx[col] = dr_pre; gx[H + col] = dz_pre; gx[2 * H + col] = dn_pre;
+      gh[col] = dr_pre; gh[H + col] = dz_pre; gh[2 * H + col] = dn_pre * r_;
+      dh_rec[i] = dh * z_ * m;  // direct path; the W_hh path is added below
+    }
+    if (t == 0) break;
+    grid_barrier(counter, (unsigned)(T - t) * gridDim.x);
+    for (int s = warp; s < n; s += nwarps) {
+      const float4* g4 = reinterpret_cast<const float4*>(dgh + ((size_t)t * n + s) * R);
+      float a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      for (int g0 = 0; g0 < R / 4; g0 += 32 * 4) {
+        float4 d[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int g = g0 + q * 32 + lane;
+          d[q] = (g < R / 4) ? __ldcg(g4 + g) : make_float4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int g = g0 + q * 32 + lane;
+          if (g < R / 4) {
+            const float4 w0 = *reinterpret_cast<const float4*>(wt + 0 * R + 4 * g);
+            const float4 w1 = *reinterpret_cast<const float4*>(wt + 1 * R + 4 * g);
+            const float4 w2 = *reinterpret_cast<const float4*>(wt + 2 * R + 4 * g);
+            const float4 w3 = *reinterpret_cast<const float4*>(wt + 3 * R + 4 * g);
+            a0 += d[q].x * w0.x + d[q].y * w0.y + d[q].z * w0.z + d[q].w * w0.w;
+            a1 += d[q].x * w1.x + d[q].y * w1.y + d[q].z * w1.z + d[q].w * w1.w;
+            a2 += d[q].x * w2.x + d[q].y * w2.y + d[q].z * w2.z + d[q].w * w2.w;
+            a3 += d[q].x * w3.x + d[q].y * w3.y + d[q].z * w3.z + d[q].w * w3.w;
+          }
+        }
+      }
+      a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+      if (lane == 0) {
+        const float m = masks[(size_t)t * n + s] ? 1.f : 0.f;
+        dh_rec[4 * s] += a0 * m; dh_rec[4 * s + 1] += a1 * m; dh_rec[4 * s + 2] += a2 * m; dh_rec[4 * s + 3] += a3 * m;
+      }
+    }
+    __syncthreads();
+  }
+}
+}  // namespace hb200
+
+extern "C" int hb200_gru_seq_fwd(const float* xproj, const float* w_hh, const float* b_hh, const uint8_t* masks,
+                                 const float* h0, long long h0_stride, float* hs, float* saved, int t_steps, int n,
+                                 int hidden, void* workspace, hb200_stream_t stream) {
+  HB_CHECK_ARG(xproj && w_hh && masks && h0 && hs && workspace && t_steps > 0 && n > 0, "gru_seq_fwd: bad args");
+  HB_CHECK_ARG(hidden == 32 || hidden == 64 || hidden == 128 || hidden == 256 || hidden == 512,
+               "gru_seq_fwd: hidden=%d unsupported (32,64,128,256,512)", hidden);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* counter = (unsigned*)workspace;
+  HB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+  const size_t smem = sizeof(float) * 16 * hidden;
+  const int grid = hidden / kUnits;
+  void* args[] = {(void*)&xproj, (void*)&w_hh, (void*)&b_hh, (void*)&masks, (void*)&h0, (void*)&h0_stride,
+                  (void*)&hs, (void*)&saved, (void*)&t_steps, (void*)&n, (void*)&counter};
+  const void* kern = nullptr;
+  switch (hidden / 32) {
+    case 1: kern = (const void*)gru_seq_fwd_kernel<1>; break;
+    case 2: kern = (const void*)gru_seq_fwd_kernel<2>; break;
+    case 4: kern = (const void*)gru_seq_fwd_kernel<4>; break;
+    case 8: kern = (const void*)gru_seq_fwd_kernel<8>; break;
+    default: kern = (const void*)gru_seq_fwd_kernel<16>; break;
+  }
+  if (smem > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc = coop_check(kern, kSeqThreads, smem, grid);
+  if (rc) return rc;
+  HB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kSeqThreads), args, smem, st));
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_gru_seq_bwd(const float* dh_out, const float* saved, const float* hs, const float* h0,
+                                 long long h0_stride, const float* w_hh, const uint8_t* masks, float* dgx, float* dgh,
+                                 int t_steps, int n, int hidden, void* workspace, hb200_stream_t stream) {
+  HB_CHECK_ARG(dh_out && saved && hs && h0 && w_hh && masks && dgx && dgh && workspace && t_steps > 0 && n > 0,
+               "gru_seq_bwd: bad args");
+  HB_CHECK_ARG(hidden % 32 == 0 && hidden % kUnits == 0, "gru_seq_bwd: hidden must be a multiple of 32");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* counter = (unsigned*)workspace;
+  HB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
+  const size_t smem = sizeof(float) * (12 * (size_t)hidden + 4 * (size_t)n);
+  HB_CHECK_ARG(smem <= 200 * 1024, "gru_seq_bwd: n=%d too large for one CTA's shared memory", n);
+  const int grid = hidden / kUnits;
+  const void* kern = (const void*)gru_seq_bwd_kernel;
+  if (smem > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int rc = coop_check(kern, kSeqThreads, smem, grid);
+  if (rc) return rc;
+  void* args[] = {(void*)&dh_out, (void*)&saved, (void*)&hs, (void*)&h0, (void*)&h0_stride, (void*)&w_hh,
+                  (void*)&masks, (void*)&dgx, (void*)&dgh, (void*)&t_steps, (void*)&n, (void*)&hidden, (void*)&counter};
+  HB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kSeqThreads), args, smem, st));
+  count_launch(1);
+  return HB200_OK;
+}

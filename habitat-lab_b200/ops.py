@@ -130,6 +130,22 @@ def conv_fwd(x, wp, y, s: ConvShape, gn_stats=None, gn_groups=0):
     call("hb200_conv_fwd", ptr(x), ptr(wp), ptr(y), ptr(gn_stats), int(gn_groups), ctypes.addressof(s))
 
 
+def conv_bias_act_fwd(x, wp, bias, y, s: ConvShape, relu):
+    call("hb200_conv_bias_act_fwd", ptr(x), ptr(wp), ptr(bias), ptr(y), int(bool(relu)), ctypes.addressof(s))
+
+
+def prep_plain(rgb, depth, frame_rows, H, W, c_rgb, c_depth, out):
+    call("hb200_prep_plain", ptr(rgb), ptr(depth), ptr(frame_rows), frame_rows.numel(), H, W, c_rgb, c_depth, ptr(out))
+
+
+def relu_bias_bwd(g, out, dy, dbias, npix, channels):
+    call("hb200_relu_bias_bwd", ptr(g), ptr(out), ptr(dy), ptr(dbias), int(npix), channels)
+
+
+def bf16_hwc_to_f32_chw(x, out, batch, hw, channels):
+    call("hb200_bf16_hwc_to_f32_chw", ptr(x), ptr(out), batch, hw, channels)
+
+
 def conv_dgrad(dy, wt, dx, s: ConvShape, addend=None):
     call("hb200_conv_dgrad", ptr(dy), ptr(wt), ptr(addend), ptr(dx), ctypes.addressof(s))
 
@@ -185,6 +201,16 @@ def gn_residual_relu(y, stats, gamma, beta, res, out, batch, hw, channels, group
 def gn_relu_maxpool(y, stats, gamma, beta, out, argmax, batch, h, w, channels, groups, eps=1e-5):
     call("hb200_gn_relu_maxpool", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(out), ptr(argmax), batch, h, w,
          channels, groups, float(eps))
+
+
+def gn_relu_maxpool_bwd_supported(h, w, channels, groups) -> bool:
+    return bool(load().hb200_gn_relu_maxpool_bwd_supported(h, w, channels, groups))
+
+
+def gn_relu_maxpool_bwd(dpool, argmax, y, stats, gamma, beta, dgamma, dbeta, dy, batch, h, w, channels, groups,
+                        eps=1e-5):
+    call("hb200_gn_relu_maxpool_bwd", ptr(dpool), ptr(argmax), ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(dgamma),
+         ptr(dbeta), ptr(dy), batch, h, w, channels, groups, float(eps))
 
 
 def maxpool_bwd(dout, argmax, dz, batch, h, w, channels):
@@ -306,6 +332,16 @@ def lstm_seq_fwd(xproj, w_hh, b_hh, masks, h0, c0, hs, cs, gates, T, n, hidden, 
 def lstm_seq_bwd(dh_out, gates, cs, c0, w_hh, masks, dgates, T, n, hidden, workspace):
     call("hb200_lstm_seq_bwd", ptr(dh_out), ptr(gates), ptr(cs), ptr(c0), c0.stride(0), ptr(w_hh), ptr(masks),
          ptr(dgates), T, n, hidden, ptr(workspace))
+
+
+def gru_seq_fwd(xproj, w_hh, b_hh, masks, h0, hs, saved, T, n, hidden, workspace):
+    call("hb200_gru_seq_fwd", ptr(xproj), ptr(w_hh), ptr(b_hh), ptr(masks), ptr(h0), h0.stride(0), ptr(hs), ptr(saved),
+         T, n, hidden, ptr(workspace))
+
+
+def gru_seq_bwd(dh_out, saved, hs, h0, w_hh, masks, dgx, dgh, T, n, hidden, workspace):
+    call("hb200_gru_seq_bwd", ptr(dh_out), ptr(saved), ptr(hs), ptr(h0), h0.stride(0), ptr(w_hh), ptr(masks), ptr(dgx),
+         ptr(dgh), T, n, hidden, ptr(workspace))
 
 
 def rnn_shift_mask(h_seq, h0, masks, h_in, T, n, hidden):

@@ -24,6 +24,7 @@ from ..common.rollout_storage import RolloutStorage
 from ..common.tensor_dict import TensorDict
 from ..synthetic import pointnav_spaces
 from .ppo import DDPPO, PPO
+from . import policy as _policy  # noqa: F401  (registers PointNavBaselinePolicy)
 from .resnet_policy import PointNavResNetPolicy
 
 

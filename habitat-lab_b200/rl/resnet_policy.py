@@ -457,64 +457,43 @@ class EncoderEngine:
         stem = self.stem
         sh, sw = stem.out_hw
         cur ^= 1
-        gzs = g_bufs[cur][: Y(stem).numel()].view_as(Y(stem))
-        ops.maxpool_bwd(g, ws["argmax"], gzs, B, sh, sw, stem.co)
-        dy0, _ = gn_bwd(stem, gzs, None, 1, False)
+        if ops.gn_relu_maxpool_bwd_supported(sh, sw, stem.co, stem.groups):
+            # pooled gradient -> dy of the stem conv in one pass (the 64x64 pooled gradient is never materialised)
+            dy0 = g_bufs[cur][: Y(stem).numel()].view_as(Y(stem))
+            ops.gn_relu_maxpool_bwd(g, ws["argmax"], Y(stem), ST(stem), stem.gamma, stem.beta, stem.gamma.grad,
+                                    stem.beta.grad, dy0, B, sh, sw, stem.co, stem.groups)
+        else:
+            gzs = g_bufs[cur][: Y(stem).numel()].view_as(Y(stem))
+            ops.maxpool_bwd(g, ws["argmax"], gzs, B, sh, sw, stem.co)
+            dy0, _ = gn_bwd(stem, gzs, None, 1, False)
         wgrad(stem, ws["x0"], dy0)
 
 
 # ---------------------------------------------------------------------------------------------
-# the policy
+# generic policy machinery: flat parameters, recurrent encoder, heads, loss + backward
 # ---------------------------------------------------------------------------------------------
-@baseline_registry.register_policy
-class PointNavResNetPolicy(nn.Module):
-    def __init__(self, observation_space, action_space, hidden_size: int = 512, num_recurrent_layers: int = 1,
-                 rnn_type: str = "GRU", resnet_baseplanes: int = 32, backbone: str = "resnet18",
-                 normalize_visual_inputs: bool = False, force_blind_policy: bool = False, policy_config=None,
-                 aux_loss_config=None, fuse_keys=None, **kwargs):
+class NativeNetPolicy(nn.Module):
+    """NetPolicy (rl/ppo/policy.py:252-413) whose forward AND backward are libhb200 kernels.
+    Subclasses provide the perception part through two hooks:
+      _visual_forward(obs, rows, prev_actions, masks_u8, B, dev, train) -> (rnn_in f32 [B, D], saved)
+      _visual_backward(d_rnn_in f32 [B, D], saved, B, dev)   (writes parameter gradients in place)
+    """
+
+    def __init__(self, net: nn.Module, action_space):
         super().__init__()
-        if force_blind_policy:
-            raise NotImplementedError("force_blind_policy is not implemented")
-        if policy_config is not None and getattr(policy_config, "action_distribution_type", "categorical") != "categorical":
-            raise NotImplementedError("only categorical action distributions are implemented")
         self.action_distribution_type = "categorical"
         self._action_space = action_space
-        self.net = PointNavResNetNet(observation_space, action_space, hidden_size, num_recurrent_layers, rnn_type,
-                                     backbone, resnet_baseplanes, normalize_visual_inputs)
+        self.net = net
         self.dim_actions = action_space.n
         self.action_distribution = CategoricalNet(self.net.output_size, self.dim_actions)
         self.critic = CriticHead(self.net.output_size)
         self.aux_loss_modules = nn.ModuleDict()
-        self.observation_space = observation_space
-        self._engine: Optional[EncoderEngine] = None
         self._flat = None
         self._buf = {}
         self.world_size = 1  # set by the distributed updater
         self.dist_group = None
 
     # ---- reference API surface ----------------------------------------------------------------
-    @classmethod
-    def from_config(cls, config, observation_space, action_space, **kwargs):
-        hb = config.habitat_baselines
-        ignore = []
-        try:
-            ignore = [s.uuid for s in hb.eval.extra_sim_sensors.values()]
-        except Exception:
-            pass
-        filtered = spaces.Dict(OrderedDict((k, v) for k, v in observation_space.spaces.items() if k not in ignore))
-        agent_name = kwargs.get("agent_name")
-        policy_cfg = None
-        try:
-            if agent_name is None:
-                agent_name = config.habitat.simulator.agents_order[0]
-            policy_cfg = hb.rl.policy[agent_name]
-        except Exception:
-            pass
-        return cls(observation_space=filtered, action_space=action_space, hidden_size=hb.rl.ppo.hidden_size,
-                   rnn_type=hb.rl.ddppo.rnn_type, num_recurrent_layers=hb.rl.ddppo.num_recurrent_layers,
-                   backbone=hb.rl.ddppo.backbone, normalize_visual_inputs="rgb" in observation_space.spaces,
-                   force_blind_policy=getattr(hb, "force_blind_policy", False), policy_config=policy_cfg)
-
     @property
     def should_load_agent_state(self):
         return True
@@ -569,25 +548,20 @@ class PointNavResNetPolicy(nn.Module):
                 p.data_ptr() == f["params"].data_ptr() + 4 * o and p.grad is not None and
                 p.grad.data_ptr() == f["grads"].data_ptr() + 4 * o for p, o in zip(params, f["offsets"])):
             return f
-        n_pad = (n + 3) // 4 * 4
-        flat_p = torch.zeros(n_pad, device=dev)
-        flat_g = torch.zeros(n_pad, device=dev)
+        # every tensor starts on a 16-byte boundary (TF32 / vector kernels read rows as float4)
         offs, o = [], 0
         for p in params:
-            k = p.numel()
-            flat_p[o:o + k].copy_(p.data.reshape(-1))
-            p.data = flat_p[o:o + k].view(p.shape)
-            p.grad = flat_g[o:o + k].view(p.shape)
             offs.append(o)
-            o += k
-        self._flat = dict(params=flat_p, grads=flat_g, offsets=offs, n=n, plist=params)
+            o += (p.numel() + 3) // 4 * 4
+        flat_p = torch.zeros(o, device=dev)
+        flat_g = torch.zeros(o, device=dev)
+        for p, off in zip(params, offs):
+            k = p.numel()
+            flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = flat_p[off:off + k].view(p.shape)
+            p.grad = flat_g[off:off + k].view(p.shape)
+        self._flat = dict(params=flat_p, grads=flat_g, offsets=offs, n=o, n_real=n, plist=params)
         return self._flat
-
-    # ---- shared forward pieces -----------------------------------------------------------------------
-    def _engine_(self):
-        if self._engine is None:
-            self._engine = EncoderEngine(self.net.visual_encoder)
-        return self._engine
 
     def _tmp(self, name, shape, dev, dtype=torch.float32):
         key = (name, tuple(shape), dtype)
@@ -596,6 +570,211 @@ class PointNavResNetPolicy(nn.Module):
             t = torch.empty(*shape, device=dev, dtype=dtype)
             self._buf[key] = t
         return t
+
+    def _loss_ws(self, B, dev):
+        key = ("loss_ws", B)
+        if key not in self._buf or self._buf[key].device != dev:
+            self._buf[key] = ops.ppo_loss_workspace(B, self.net.output_size, self.dim_actions, dev)
+        return self._buf[key]
+
+    # ---- recurrent state encoder -----------------------------------------------------------------------
+    def _rnn_forward(self, rnn_in, hid, mk, T, n, B, dev, train):
+        rnn = self.net.state_encoder.rnn
+        H, L = rnn.hidden_size, rnn.num_layers
+        lstm = isinstance(rnn, nn.LSTM)
+        ws = self._tmp("rnn_ws", (64,), dev, torch.uint8)
+        layers, x = [], rnn_in
+        for l in range(L):
+            w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
+            b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
+            G = 4 if lstm else 3
+            xproj = self._tmp(f"xproj{l}", (B, G * H), dev)
+            ops.linear_fwd(x, w_ih, b_ih, xproj, tf32=True)
+            hs = self._tmp(f"hs{l}", (T, n, H), dev)
+            if lstm:
+                cs = self._tmp(f"cs{l}", (T, n, H), dev)
+                gates = self._tmp(f"gates{l}", (T, n, 4 * H), dev) if train else None
+                h0, c0 = hid[:, l], hid[:, L + l]
+                ops.lstm_seq_fwd(xproj, w_hh, b_hh, mk, h0, c0, hs, cs, gates, T, n, H, ws)
+                layers.append(dict(x=x, hs=hs, cs=cs, gates=gates, h0=h0, c0=c0))
+            else:
+                saved = self._tmp(f"gates{l}", (T, n, 4 * H), dev) if train else None
+                h0 = hid[:, l]
+                ops.gru_seq_fwd(xproj, w_hh, b_hh, mk, h0, hs, saved, T, n, H, ws)
+                layers.append(dict(x=x, hs=hs, gates=saved, h0=h0))
+            x = hs.view(B, H)
+        parts = [ly["hs"][T - 1] for ly in layers] + ([ly["cs"][T - 1] for ly in layers] if lstm else [])
+        return x, layers, torch.stack(parts, dim=1)
+
+    def _rnn_backward(self, d_out, layers, mk, T, n, B, dev):
+        rnn = self.net.state_encoder.rnn
+        H, L = rnn.hidden_size, rnn.num_layers
+        lstm = isinstance(rnn, nn.LSTM)
+        ws = self._tmp("rnn_ws", (64,), dev, torch.uint8)
+        for l in reversed(range(L)):
+            ly = layers[l]
+            w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
+            b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
+            G = 4 if lstm else 3
+            dgx = self._tmp(f"dgates{l}", (T, n, G * H), dev)
+            if lstm:
+                ops.lstm_seq_bwd(d_out.view(T, n, H), ly["gates"], ly["cs"], ly["c0"], w_hh, mk, dgx, T, n, H, ws)
+                dgh = dgx
+            else:
+                dgh = self._tmp(f"dgh{l}", (T, n, G * H), dev)
+                ops.gru_seq_bwd(d_out.view(T, n, H), ly["gates"], ly["hs"], ly["h0"], w_hh, mk, dgx, dgh, T, n, H, ws)
+            dgxf, dghf = dgx.view(B, G * H), dgh.view(B, G * H)
+            x = ly["x"]
+            ops.linear_bwd_weight(dgxf, x, w_ih.grad, accumulate=True, tf32=True)  # grads pre-zeroed: split-K
+            hin = self._tmp("hin", (T, n, H), dev)
+            ops.rnn_shift_mask(ly["hs"], ly["h0"], mk, hin, T, n, H)
+            ops.linear_bwd_weight(dghf, hin.view(B, H), w_hh.grad, accumulate=True, tf32=True)
+            ops.colsum(dgxf, b_ih.grad)
+            if lstm:
+                b_hh.grad.copy_(b_ih.grad)
+            else:
+                ops.colsum(dghf, b_hh.grad)
+            dx = self._tmp(f"dx{l}", (B, x.stride(0)), dev)[:, : x.shape[1]]   # same (16-byte) row pitch as x
+            ops.linear_bwd_input(dgxf, w_ih, dx, tf32=True)
+            d_out = dx
+        return d_out
+
+    # ---- shared forward ----------------------------------------------------------------------------------
+    def _trunk(self, observations, rnn_hidden_states, prev_actions, masks, train: bool):
+        obs, rows = _as_rows(observations, rnn_hidden_states.device)
+        dev = rnn_hidden_states.device
+        if dev.type != "cuda":
+            raise Hb200Error("hb200 policy: inputs must be CUDA tensors (no CPU fallback)")
+        self.flatten_parameters_()
+        B = rows.numel()
+        n = rnn_hidden_states.shape[0]
+        T = B // n
+        assert T * n == B, "frames must be (t, env)-ordered with T*n rows"
+        pa = prev_actions.reshape(-1)
+        mk = ops.as_u8(masks.reshape(-1))
+        rnn_in, vsaved = self._visual_forward(obs, rows, pa, mk, B, dev, train)
+        hid = rnn_hidden_states.contiguous()
+        feats, layers, hidden_out = self._rnn_forward(rnn_in, hid, mk, T, n, B, dev, train)
+        return dict(B=B, n=n, T=T, rows=rows, obs=obs, masks=mk, pa=pa, layers=layers, features=feats,
+                    hidden_out=hidden_out, visual=vsaved)
+
+    def _heads(self, feats, B, dev):
+        logits = self._tmp("logits", (B, self.dim_actions), dev)
+        values = self._tmp("values_act", (B,), dev)
+        ad, cr = self.action_distribution.linear, self.critic.fc
+        ops.heads_fwd(feats, ad.weight, ad.bias, cr.weight, cr.bias, logits, values)
+        return logits, values
+
+    @torch.no_grad()
+    def act(self, observations, rnn_hidden_states, prev_actions, masks, deterministic=False):
+        s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=False)
+        B = s["B"]
+        logits, values = self._heads(s["features"], B, s["features"].device)
+        logp = torch.log_softmax(logits, dim=-1)
+        if deterministic:
+            action = logp.argmax(dim=-1, keepdim=True)
+        else:  # sampling is not bit-reproducible across implementations (torch.multinomial, Philox)
+            action = torch.multinomial(logp.exp(), 1)
+        return PolicyActionData(values=values.view(B, 1).clone(), actions=action,
+                                action_log_probs=logp.gather(1, action), rnn_hidden_states=s["hidden_out"])
+
+    @torch.no_grad()
+    def get_value(self, observations, rnn_hidden_states, prev_actions, masks):
+        s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=False)
+        _, values = self._heads(s["features"], s["B"], s["features"].device)
+        return values.view(s["B"], 1).clone()
+
+    def evaluate_actions(self, observations, rnn_hidden_states, prev_actions, masks, action,
+                         rnn_build_seq_info=None):
+        """Forward only (values, log-probs, entropy, hidden, aux) like the reference
+        (rl/ppo/policy.py:361-402); `rnn_build_seq_info` is accepted and ignored: the masked
+        recurrence needs only `masks`."""
+        s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=True)
+        feats, B = s["features"], s["B"]
+        dev = feats.device
+        out = dict(values=self._tmp("ea_values", (B,), dev), log_probs=self._tmp("ea_lp", (B,), dev),
+                   entropy=self._tmp("ea_ent", (B,), dev), metrics=self._tmp("ea_metrics", (ops.N_METRICS,), dev))
+        ad, cr = self.action_distribution.linear, self.critic.fc
+        zero = self._tmp("zeros_B", (B,), dev)
+        zero.zero_()
+        ops.ppo_loss(feats, ad.weight, ad.bias, cr.weight, cr.bias, action.reshape(-1), zero, zero, zero, zero, 0.2,
+                     0.5, 0.0, False, False, out, self._loss_ws(B, dev))
+        return (out["values"].view(B, 1), out["log_probs"].view(B, 1), out["entropy"].view(B, 1),
+                s["hidden_out"], {})
+
+    def loss_and_backward(self, batch, clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss,
+                          observations=None):
+        """Fused replacement of evaluate_actions + the loss section of PPO._update_from_batch +
+        total_loss.backward() (rl/ppo/ppo.py:180-254).  Leaves every parameter's gradient in the flat
+        gradient buffer (p.grad views) and returns the 12 metrics as a device tensor."""
+        obs = observations if observations is not None else batch["observations"]
+        s = self._trunk(obs, batch["recurrent_hidden_states"], batch["prev_actions"], batch["masks"], train=True)
+        feats, B, n, T = s["features"], s["B"], s["n"], s["T"]
+        dev = feats.device
+        H = self.net.output_size
+        self._flat["grads"].zero_()
+        ad, cr = self.action_distribution.linear, self.critic.fc
+        out = dict(values=self._tmp("ea_values", (B,), dev), log_probs=self._tmp("ea_lp", (B,), dev),
+                   entropy=self._tmp("ea_ent", (B,), dev), metrics=self._tmp("ea_metrics", (ops.N_METRICS,), dev),
+                   d_features=self._tmp("d_features", (B, H), dev), d_w_act=ad.weight.grad, d_b_act=ad.bias.grad,
+                   d_w_val=cr.weight.grad, d_b_val=cr.bias.grad)
+        f32 = lambda t: t.reshape(-1).contiguous()  # noqa: E731
+        ops.ppo_loss(feats, ad.weight, ad.bias, cr.weight, cr.bias, f32(batch["actions"]),
+                     f32(batch["action_log_probs"]), f32(batch["advantages"]), f32(batch["value_preds"]),
+                     f32(batch["returns"]), clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss, True,
+                     out, self._loss_ws(B, dev), is_coeffs=f32(batch["is_coeffs"]) if "is_coeffs" in batch else None)
+        d_rnn_in = self._rnn_backward(out["d_features"], s["layers"], s["masks"], T, n, B, dev)
+        self._visual_backward(d_rnn_in, s, B, dev)
+        self._last = dict(values=out["values"], log_probs=out["log_probs"], entropy=out["entropy"],
+                          hidden_out=s["hidden_out"])
+        return out["metrics"]
+
+
+# ---------------------------------------------------------------------------------------------
+# PointNavResNetPolicy
+# ---------------------------------------------------------------------------------------------
+@baseline_registry.register_policy
+class PointNavResNetPolicy(NativeNetPolicy):
+    def __init__(self, observation_space, action_space, hidden_size: int = 512, num_recurrent_layers: int = 1,
+                 rnn_type: str = "GRU", resnet_baseplanes: int = 32, backbone: str = "resnet18",
+                 normalize_visual_inputs: bool = False, force_blind_policy: bool = False, policy_config=None,
+                 aux_loss_config=None, fuse_keys=None, **kwargs):
+        if force_blind_policy:
+            raise NotImplementedError("force_blind_policy is not implemented")
+        if policy_config is not None and getattr(policy_config, "action_distribution_type", "categorical") != "categorical":
+            raise NotImplementedError("only categorical action distributions are implemented")
+        super().__init__(PointNavResNetNet(observation_space, action_space, hidden_size, num_recurrent_layers,
+                                           rnn_type, backbone, resnet_baseplanes, normalize_visual_inputs),
+                         action_space)
+        self.observation_space = observation_space
+        self._engine: Optional[EncoderEngine] = None
+
+    @classmethod
+    def from_config(cls, config, observation_space, action_space, **kwargs):
+        hb = config.habitat_baselines
+        ignore = []
+        try:
+            ignore = [s.uuid for s in hb.eval.extra_sim_sensors.values()]
+        except Exception:
+            pass
+        filtered = spaces.Dict(OrderedDict((k, v) for k, v in observation_space.spaces.items() if k not in ignore))
+        agent_name = kwargs.get("agent_name")
+        policy_cfg = None
+        try:
+            if agent_name is None:
+                agent_name = config.habitat.simulator.agents_order[0]
+            policy_cfg = hb.rl.policy[agent_name]
+        except Exception:
+            pass
+        return cls(observation_space=filtered, action_space=action_space, hidden_size=hb.rl.ppo.hidden_size,
+                   rnn_type=hb.rl.ddppo.rnn_type, num_recurrent_layers=hb.rl.ddppo.num_recurrent_layers,
+                   backbone=hb.rl.ddppo.backbone, normalize_visual_inputs="rgb" in observation_space.spaces,
+                   force_blind_policy=getattr(hb, "force_blind_policy", False), policy_config=policy_cfg)
+
+    def _engine_(self):
+        if self._engine is None:
+            self._engine = EncoderEngine(self.net.visual_encoder)
+        return self._engine
 
     def _visual_prep(self, observations, rows, B, dev, update_stats):
         enc = self.net.visual_encoder
@@ -617,7 +796,6 @@ class PointNavResNetPolicy(nn.Module):
                     torch.distributed.all_reduce(stats, group=self.dist_group)
             ops.prep_finalize(stats, rmv._mean, rmv._var, rmv._count, scale_shift, C, (H // 2) * (W // 2),
                               update_stats)
-
         s2d = self._engine_().stem.stem_s2d
 
         def write(x0):
@@ -625,19 +803,8 @@ class PointNavResNetPolicy(nn.Module):
 
         return write
 
-    def _trunk(self, observations, rnn_hidden_states, prev_actions, masks, train: bool):
-        """Everything up to the recurrent features.  Returns a dict of saved tensors."""
-        obs, rows = _as_rows(observations, rnn_hidden_states.device)
-        dev = rnn_hidden_states.device
-        if dev.type != "cuda":
-            raise Hb200Error("hb200 policy: inputs must be CUDA tensors (no CPU fallback)")
-        self.flatten_parameters_()
-        B = rows.numel()
-        n = rnn_hidden_states.shape[0]
-        T = B // n
-        assert T * n == B, "frames must be (t, env)-ordered with T*n rows"
+    def _visual_forward(self, obs, rows, pa, mk, B, dev, train):
         H = self.net._hidden_size
-        L = self.net.state_encoder.rnn.num_layers
         eng = self._engine_()
         write_x0 = self._visual_prep(obs, rows, B, dev, update_stats=train and self.training)
         feat = eng.forward(write_x0, B, dev, train)
@@ -646,148 +813,21 @@ class PointNavResNetPolicy(nn.Module):
         D = H + 64
         rnn_in = self._tmp("rnn_in", (B, D), dev)
         ops.linear_fwd(feat, fc.weight, fc.bias, rnn_in, relu=True, ldc=D, tf32=True)
-        goal = obs[POINTGOAL_UUID]
-        pa = prev_actions.reshape(-1)
-        mk = ops.as_u8(masks.reshape(-1))
-        ops.embed_fwd(goal.reshape(-1, 2), pa, mk, rows, self.net.tgt_embeding.weight, self.net.tgt_embeding.bias,
-                      self.net.prev_action_embedding.weight, rnn_in, H)
-        rnn = self.net.state_encoder.rnn
-        hid = rnn_hidden_states.contiguous()
-        saved = dict(B=B, n=n, T=T, rows=rows, obs=obs, feat=feat, rnn_in=rnn_in, masks=mk, pa=pa, hid=hid, layers=[])
-        x = rnn_in
-        for l in range(L):
-            w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
-            b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
-            xproj = self._tmp(f"xproj{l}", (B, 4 * H), dev)
-            ops.linear_fwd(x, w_ih, b_ih, xproj, tf32=True)
-            hs = self._tmp(f"hs{l}", (T, n, H), dev)
-            cs = self._tmp(f"cs{l}", (T, n, H), dev)
-            gates = self._tmp(f"gates{l}", (T, n, 4 * H), dev) if train else None
-            h0, c0 = hid[:, l], hid[:, L + l]
-            ops.lstm_seq_fwd(xproj, w_hh, b_hh, mk, h0, c0, hs, cs, gates, T, n, H, self._tmp("rnn_ws", (64,), dev, torch.uint8))
-            saved["layers"].append(dict(x=x, xproj=xproj, hs=hs, cs=cs, gates=gates, h0=h0, c0=c0))
-            x = hs.view(B, H)
-        saved["features"] = x
-        saved["hidden_out"] = torch.stack([ly["hs"][T - 1] for ly in saved["layers"]] +
-                                          [ly["cs"][T - 1] for ly in saved["layers"]], dim=1)
-        return saved
+        ops.embed_fwd(obs[POINTGOAL_UUID].reshape(-1, 2), pa, mk, rows, self.net.tgt_embeding.weight,
+                      self.net.tgt_embeding.bias, self.net.prev_action_embedding.weight, rnn_in, H)
+        return rnn_in, dict(feat=feat, rnn_in=rnn_in)
 
-    # ---- inference paths ---------------------------------------------------------------------------------
-    @torch.no_grad()
-    def act(self, observations, rnn_hidden_states, prev_actions, masks, deterministic=False):
-        s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=False)
-        feats, B = s["features"], s["B"]
-        dev = feats.device
-        logits = self._tmp("logits", (B, self.dim_actions), dev)
-        values = self._tmp("values_act", (B,), dev)
-        ad, cr = self.action_distribution.linear, self.critic.fc
-        ops.heads_fwd(feats, ad.weight, ad.bias, cr.weight, cr.bias, logits, values)
-        logp = torch.log_softmax(logits, dim=-1)
-        if deterministic:
-            action = logp.argmax(dim=-1, keepdim=True)
-        else:  # sampling is not bit-reproducible across implementations (torch.multinomial, Philox)
-            action = torch.multinomial(logp.exp(), 1)
-        return PolicyActionData(values=values.view(B, 1).clone(), actions=action,
-                                action_log_probs=logp.gather(1, action), rnn_hidden_states=s["hidden_out"])
-
-    @torch.no_grad()
-    def get_value(self, observations, rnn_hidden_states, prev_actions, masks):
-        s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=False)
-        feats, B = s["features"], s["B"]
-        dev = feats.device
-        logits = self._tmp("logits", (B, self.dim_actions), dev)
-        values = self._tmp("values_act", (B,), dev)
-        ad, cr = self.action_distribution.linear, self.critic.fc
-        ops.heads_fwd(feats, ad.weight, ad.bias, cr.weight, cr.bias, logits, values)
-        return values.view(B, 1).clone()
-
-    # ---- training path --------------------------------------------------------------------------------------
-    def evaluate_actions(self, observations, rnn_hidden_states, prev_actions, masks, action,
-                         rnn_build_seq_info=None):
-        """Forward only (values, log-probs, entropy, hidden, aux) like the reference
-        (rl/ppo/policy.py:361-402).  The saved activations are kept for `loss_and_backward`;
-        `rnn_build_seq_info` is accepted and ignored: the masked recurrence needs only `masks`."""
-        s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=True)
-        self._saved = s
-        feats, B = s["features"], s["B"]
-        dev = feats.device
-        out = dict(values=self._tmp("ea_values", (B,), dev), log_probs=self._tmp("ea_lp", (B,), dev),
-                   entropy=self._tmp("ea_ent", (B,), dev), metrics=self._tmp("ea_metrics", (ops.N_METRICS,), dev))
-        ad, cr = self.action_distribution.linear, self.critic.fc
-        zero = self._tmp("zeros_B", (B,), dev)
-        zero.zero_()
-        ws = self._loss_ws(B, dev)
-        ops.ppo_loss(feats, ad.weight, ad.bias, cr.weight, cr.bias, action.reshape(-1), zero, zero, zero, zero, 0.2,
-                     0.5, 0.0, False, False, out, ws)
-        return (out["values"].view(B, 1), out["log_probs"].view(B, 1), out["entropy"].view(B, 1),
-                s["hidden_out"], {})
-
-    def _loss_ws(self, B, dev):
-        key = ("loss_ws", B)
-        if key not in self._buf or self._buf[key].device != dev:
-            self._buf[key] = ops.ppo_loss_workspace(B, self.net._hidden_size, self.dim_actions, dev)
-        return self._buf[key]
-
-    def loss_and_backward(self, batch, clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss,
-                          observations=None):
-        """Fused replacement of evaluate_actions + the loss section of PPO._update_from_batch +
-        total_loss.backward() (rl/ppo/ppo.py:180-254).  Leaves every parameter's gradient in the flat
-        gradient buffer (p.grad views) and returns the 12 metrics as a device tensor."""
-        obs = observations if observations is not None else batch["observations"]
-        s = self._trunk(obs, batch["recurrent_hidden_states"], batch["prev_actions"], batch["masks"], train=True)
-        feats, B, n, T = s["features"], s["B"], s["n"], s["T"]
-        dev = feats.device
+    def _visual_backward(self, d_rnn_in, s, B, dev):
         H = self.net._hidden_size
-        flat = self._flat
-        flat["grads"].zero_()
-        ad, cr = self.action_distribution.linear, self.critic.fc
-        out = dict(values=self._tmp("ea_values", (B,), dev), log_probs=self._tmp("ea_lp", (B,), dev),
-                   entropy=self._tmp("ea_ent", (B,), dev), metrics=self._tmp("ea_metrics", (ops.N_METRICS,), dev),
-                   d_features=self._tmp("d_features", (B, H), dev), d_w_act=ad.weight.grad, d_b_act=ad.bias.grad,
-                   d_w_val=cr.weight.grad, d_b_val=cr.bias.grad)
-        f32 = lambda t: t.reshape(-1).contiguous()  # noqa: E731
-        ops.ppo_loss(feats, ad.weight, ad.bias, cr.weight, cr.bias, f32(batch["actions"]),
-                     f32(batch["action_log_probs"]), f32(batch["advantages"]), f32(batch["value_preds"]),
-                     f32(batch["returns"]), clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss, True,
-                     out, self._loss_ws(B, dev), is_coeffs=f32(batch["is_coeffs"]) if "is_coeffs" in batch else None)
-        # ---- LSTM backward through time, top layer first
-        rnn = self.net.state_encoder.rnn
-        L = rnn.num_layers
-        d_out = out["d_features"]
-        mk = s["masks"]
-        for l in reversed(range(L)):
-            ly = s["layers"][l]
-            w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
-            b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
-            dg = self._tmp(f"dgates{l}", (T, n, 4 * H), dev)
-            ops.lstm_seq_bwd(d_out.view(T, n, H), ly["gates"], ly["cs"], ly["c0"], w_hh, mk, dg, T, n, H,
-                             self._tmp("rnn_ws", (64,), dev, torch.uint8))
-            dgf = dg.view(B, 4 * H)
-            x = ly["x"]
-            ops.linear_bwd_weight(dgf, x, w_ih.grad, accumulate=True, tf32=True)  # grads pre-zeroed: split-K
-            hin = self._tmp("hin", (T, n, H), dev)
-            ops.rnn_shift_mask(ly["hs"], ly["h0"], mk, hin, T, n, H)
-            ops.linear_bwd_weight(dgf, hin.view(B, H), w_hh.grad, accumulate=True, tf32=True)
-            ops.colsum(dgf, b_ih.grad)
-            b_hh.grad.copy_(b_ih.grad)
-            dx = self._tmp(f"dx{l}", (B, x.shape[1]), dev)
-            ops.linear_bwd_input(dgf, w_ih, dx, tf32=True)
-            d_out = dx
-        d_rnn_in = d_out  # [B, H + 64]
-        # ---- embeddings
+        v = s["visual"]
         tg, emb = self.net.tgt_embeding, self.net.prev_action_embedding
-        ops.embed_bwd(s["obs"][POINTGOAL_UUID].reshape(-1, 2), s["pa"], mk, s["rows"], d_rnn_in, H, tg.weight.grad,
-                      tg.bias.grad, emb.weight.grad)
-        # ---- visual_fc (ReLU -> Linear)
+        ops.embed_bwd(s["obs"][POINTGOAL_UUID].reshape(-1, 2), s["pa"], s["masks"], s["rows"], d_rnn_in, H,
+                      tg.weight.grad, tg.bias.grad, emb.weight.grad)
         fc = self.net.visual_fc[1]
-        ops.relu_bwd(d_rnn_in, s["rnn_in"], H)
+        ops.relu_bwd(d_rnn_in, v["rnn_in"], H)
         dvis = d_rnn_in[:, :H]
-        ops.linear_bwd_weight(dvis, s["feat"], fc.weight.grad, accumulate=True, tf32=True)
+        ops.linear_bwd_weight(dvis, v["feat"], fc.weight.grad, accumulate=True, tf32=True)
         ops.colsum(dvis, fc.bias.grad, n_cols=H)
-        d_feat = self._tmp("d_feat", tuple(s["feat"].shape), dev)
+        d_feat = self._tmp("d_feat", tuple(v["feat"].shape), dev)
         ops.linear_bwd_input(dvis, fc.weight, d_feat, tf32=True)
-        # ---- conv stack
         self._engine_().backward(d_feat, B, dev)
-        self._last = dict(values=out["values"], log_probs=out["log_probs"], entropy=out["entropy"],
-                          hidden_out=s["hidden_out"])
-        return out["metrics"]

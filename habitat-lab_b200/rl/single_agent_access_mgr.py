@@ -11,6 +11,7 @@ from torch.optim.lr_scheduler import LambdaLR
 from ..common.baseline_registry import baseline_registry
 from ..common.rollout_storage import RolloutStorage
 from .ppo import DDPPO, PPO
+from . import policy as _policy  # noqa: F401  (registers PointNavBaselinePolicy)
 from .resnet_policy import PointNavResNetPolicy
 
 

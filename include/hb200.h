@@ -142,6 +142,18 @@ int hb200_prep_apply(const uint8_t* rgb, const float* depth, const int32_t* fram
                      int height, int width, int c_rgb, int c_depth, float rgb_scale,
                      const float* scale_shift, hb200_bf16* out, int s2d, hb200_stream_t stream);
 
+/* SimpleCNN input (HB/rl/models/simple_cnn.py:139-157): rgb/255 and raw depth concatenated, bf16 NHWC
+ * [B,H,W,8] (zero padded channels), no pooling; rows gathered through frame_rows */
+int hb200_prep_plain(const uint8_t* rgb, const float* depth, const int32_t* frame_rows, int batch, int height,
+                     int width, int c_rgb, int c_depth, hb200_bf16* out, hb200_stream_t stream);
+/* backward of conv+bias -> ReLU: dy = g * (out > 0) (out = post-ReLU activation; NULL -> no mask),
+ * dbias[C] += per-channel sums of dy (caller zeroes); dy may be NULL (bias gradient only) */
+int hb200_relu_bias_bwd(const hb200_bf16* g, const hb200_bf16* out, hb200_bf16* dy, float* dbias, long long npix,
+                        int channels, hb200_stream_t stream);
+/* bf16 NHWC [B,hw,C] -> f32 [B, C*hw] in (c,h,w) order (nn.Flatten of the NCHW map) */
+int hb200_bf16_hwc_to_f32_chw(const hb200_bf16* x, float* out, int batch, int hw, int channels,
+                              hb200_stream_t stream);
+
 /* ---- implicit-GEMM convolution on tcgen05 tensor cores -----------------------------------
  * replaces nn.Conv2d forward / backward-data / backward-weight as dispatched by
  * HB/rl/ddppo/policy/resnet.py:15-34,207-219 and resnet_policy.py:224-234 (cuDNN today).
@@ -159,6 +171,10 @@ typedef struct {
 int hb200_conv_fwd(const hb200_bf16* x, const hb200_bf16* w_packed, hb200_bf16* y,
                    float* gn_stats, int gn_groups, const hb200_conv_shape* s,
                    hb200_stream_t stream);
+/* forward with per-channel bias (+ReLU) fused in the epilogue: SimpleCNN's biased convs
+ * (HB/rl/models/simple_cnn.py:68-93) */
+int hb200_conv_bias_act_fwd(const hb200_bf16* x, const hb200_bf16* w_packed, const float* bias, hb200_bf16* y,
+                            int relu, const hb200_conv_shape* s, hb200_stream_t stream);
 /* dy [B,Ho,Wo,Co] -> dx [B,Hi,Wi,Ci]; w_packed_t bf16 [Ci][kh*kw*Co padded] (transposed pack) */
 int hb200_conv_dgrad(const hb200_bf16* dy, const hb200_bf16* w_packed_t, const hb200_bf16* addend,
                      hb200_bf16* dx, const hb200_conv_shape* s, hb200_stream_t stream);
@@ -242,12 +258,23 @@ int hb200_gn_bwd_reduce(const hb200_bf16* g, const hb200_bf16* act, const hb200_
                         const float* stats, const float* gamma, const float* beta, float* sums,
                         float* dgamma, float* dbeta, int batch, int hw, int channels, int groups,
                         float eps, int mask_mode, hb200_stream_t stream);
-/* both passes in one launch (one block per frame; the second pass re-reads from L2): dgamma/dbeta are
- * accumulated (caller zeroes), dy / gz_out written */
+/* both passes in one launch: a thread-block cluster owns a frame, stages it in shared memory (cp.async), reduces
+ * through distributed shared memory and writes dy / gz_out from the staged copy, so every operand crosses HBM once.
+ * dgamma/dbeta are accumulated (caller zeroes). */
 int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y, const float* stats,
                  const float* gamma, const float* beta, float* dgamma, float* dbeta, hb200_bf16* dy,
                  hb200_bf16* gz_out, int batch, int hw, int channels, int groups, float eps, int mask_mode,
                  hb200_stream_t stream);
+
+/* Stem backward in one pass: MaxPool2d(3,2,1) backward (argmax codes from hb200_gn_relu_maxpool) + ReLU backward +
+ * GroupNorm backward (resnet.py:244-252).  dpool bf16 [B,H/2,W/2,C] is the gradient of the pooled activation, y / dy
+ * bf16 [B,H,W,C] the stem conv output and its gradient; the full-resolution pooled gradient is never written.
+ * _supported() tells whether a (h, w, channels) shape can be tiled (else: hb200_maxpool_bwd + hb200_gn_bwd). */
+int hb200_gn_relu_maxpool_bwd_supported(int h, int w, int channels, int groups);
+int hb200_gn_relu_maxpool_bwd(const hb200_bf16* dpool, const uint8_t* argmax, const hb200_bf16* y,
+                              const float* stats, const float* gamma, const float* beta, float* dgamma,
+                              float* dbeta, hb200_bf16* dy, int batch, int h, int w, int channels, int groups,
+                              float eps, hb200_stream_t stream);
 int hb200_gn_bwd_apply(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
                        const float* stats, const float* gamma, const float* beta,
                        const float* sums, hb200_bf16* dy, hb200_bf16* gz_out, int batch, int hw,
@@ -317,6 +344,15 @@ int hb200_lstm_seq_fwd(const float* xproj, const float* w_hh, const float* b_hh,
 int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const float* cs, const float* c0,
                        long long c0_stride, const float* w_hh, const uint8_t* masks, float* dgates,
                        int t_steps, int n, int hidden, void* workspace, hb200_stream_t stream);
+/* GRU (gate order r,z,n), same persistent cooperative structure.  xproj [T*n,3H] = x W_ih^T + b_ih;
+ * saved [T,n,4H] = (r, z, n, W_hn h + b_hn) for backward (NULL in inference).  Backward writes
+ * dgx [T,n,3H] = d xproj (-> dW_ih, db_ih, dx) and dgh [T,n,3H] = d(h-side pre-activations) (-> dW_hh, db_hh). */
+int hb200_gru_seq_fwd(const float* xproj, const float* w_hh, const float* b_hh, const uint8_t* masks,
+                      const float* h0, long long h0_stride, float* hs, float* saved, int t_steps, int n, int hidden,
+                      void* workspace, hb200_stream_t stream);
+int hb200_gru_seq_bwd(const float* dh_out, const float* saved, const float* hs, const float* h0, long long h0_stride,
+                      const float* w_hh, const uint8_t* masks, float* dgx, float* dgh, int t_steps, int n, int hidden,
+                      void* workspace, hb200_stream_t stream);
 /* h_in[t] = (t == 0 ? h0 : h_seq[t-1]) * m_t for the whole sequence (input of dW_hh = dG^T h_in) */
 int hb200_rnn_shift_mask(const float* h_seq, const float* h0, long long h0_row_stride,
                          const uint8_t* masks, float* h_in, int t_steps, int n, int hidden,

@@ -63,7 +63,10 @@ def fill_storage(R, pol, obs_space, act_space, c):
 def main():
     R = ref_shim.ref()
     torch.set_num_threads(8)
+    only = sys.argv[1:]
     for name, c in CASES.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(c["seed"])
         pol, obs_space, act_space, shapes = build_reference(R, c)
         st, next_value = fill_storage(R, pol, obs_space, act_space, c)
@@ -120,6 +123,50 @@ def main():
                                              for k, v in pol.state_dict().items()}
         torch.save(out, os.path.join(HERE, f"{name}.pt"))
         print(name, "losses", out["mb_losses"], "update", {k: round(v, 6) for k, v in metrics.items()})
+
+    # --- BASELINE config #1: PointNavBaselinePolicy (SimpleCNN depth-only 128x128 + GRU), num_envs = 2
+    c = dict(T=8, N=2, H=128, W=128, seed=21, mb=1)
+    sp = R.spaces
+    obs_space = sp.Dict({"depth": sp.Box(0, 1, (c["H"], c["W"], 1), np.float32),
+                         "pointgoal_with_gps_compass": sp.Box(-1e9, 1e9, (2,), np.float32)})
+    pol = R.PointNavBaselinePolicy(obs_space, sp.Discrete(4), hidden_size=512)
+    shapes = {k: tuple(v.shape) for k, v in pol.state_dict().items()}
+    pol.load_state_dict(recipe_state_dict(shapes, c["seed"]))
+    st = R.RolloutStorage(c["T"], c["N"], obs_space, sp.Discrete(4), pol)
+    bufs, next_value = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, 1, 512, c["seed"], rgb=False)
+    for k, v in bufs["observations"].items():
+        st.buffers["observations"][k].copy_(v)
+    for k in ("recurrent_hidden_states", "masks", "rewards", "value_preds", "returns", "action_log_probs", "actions",
+              "prev_actions"):
+        st.buffers[k].copy_(bufs[k])
+    st.current_rollout_step_idxs = [c["T"]]
+    st.compute_returns(next_value, True, 0.99, 0.95)
+    ppo = R.PPO(pol, ppo_epoch=1, num_mini_batch=1, use_normalized_advantage=False, **PPO_KW)
+    adv = ppo.get_advantages(st)
+    torch.manual_seed(1000 + c["seed"])
+    batch = next(iter(st.data_generator(adv, 1)))
+    values, lp, ent, hid, _ = pol.evaluate_actions(batch["observations"], batch["recurrent_hidden_states"],
+                                                   batch["prev_actions"], batch["masks"], batch["actions"],
+                                                   batch["rnn_build_seq_info"])
+    ratio = torch.exp(lp - batch["action_log_probs"])
+    action_loss = -torch.min(batch["advantages"] * ratio, batch["advantages"] * torch.clamp(ratio, 0.8, 1.2))
+    delta = values.detach() - batch["value_preds"]
+    vv = torch.where(delta.abs() < 0.2, values, batch["value_preds"] + delta.clamp(-0.2, 0.2))
+    value_loss = 0.5 * (vv - batch["returns"]) ** 2
+    total = 0.5 * value_loss.mean() + action_loss.mean() - 0.01 * ent.mean()
+    pol.zero_grad()
+    total.backward()
+    out = dict(case=c, shapes=shapes, returns=st.buffers["returns"].clone(), advantages=adv.clone(),
+               value_preds_after=st.buffers["value_preds"].clone(), mb_env_inds_seed=1000 + c["seed"],
+               eval_values=values.detach(), eval_log_probs=lp.detach(), eval_entropy=ent.detach(), eval_hidden=hid.detach(),
+               mb_losses=dict(value_loss=value_loss.mean().item(), action_loss=action_loss.mean().item(),
+                              dist_entropy=ent.mean().item(), total=total.item()),
+               grad_norms={k: p.grad.norm().item() for k, p in pol.named_parameters()})
+    pol.zero_grad()
+    torch.manual_seed(2000 + c["seed"])
+    out["update_metrics"] = ppo.update(st)
+    torch.save(out, os.path.join(HERE, "baseline_cnn.pt"))
+    print("baseline_cnn", out["mb_losses"], {k: round(v, 6) for k, v in out["update_metrics"].items()})
 
     # --- RNN packed-sequence semantics (test/test_rnn_state_encoder.py) golden
     torch.manual_seed(3)

@@ -223,6 +223,9 @@ CONV_CASES = [
     (2, 64, 64, 4, 8, 32, 7, 2, 3),       # stem, 4 real channels padded to 8
     (1, 31, 17, 32, 32, 32, 3, 1, 1),     # odd sizes, ragged tile tail
     (9, 8, 8, 64, 64, 128, 3, 2, 1),
+    (2, 128, 128, 1, 8, 32, 8, 4, 0),     # SimpleCNN conv 1 (depth only), simple_cnn.py:84-96
+    (2, 31, 31, 32, 32, 64, 4, 2, 0),     # SimpleCNN conv 2 (odd input, last row/col unused)
+    (2, 14, 14, 64, 64, 32, 3, 1, 0),     # SimpleCNN conv 3 (no padding)
 ]
 
 
@@ -415,7 +418,9 @@ def _stats_of(y_nchw, groups):
     return torch.stack([yg.sum(-1), (yg * yg).sum(-1)], -1).contiguous()
 
 
-@pytest.mark.parametrize("B,C,H,W,G", [(3, 32, 16, 16, 16), (2, 64, 8, 8, 16), (2, 128, 4, 4, 1), (5, 256, 4, 4, 16)])
+@pytest.mark.parametrize("B,C,H,W,G", [(3, 32, 16, 16, 16), (2, 64, 8, 8, 16), (2, 128, 4, 4, 1), (5, 256, 4, 4, 16),
+                                       (2, 32, 64, 64, 16), (3, 32, 32, 32, 16), (3, 64, 16, 16, 16),
+                                       (2, 32, 31, 17, 16)])  # clusters of 8 / 4 / 2 CTAs per frame, ragged slice
 def test_groupnorm_passes(hb, B, C, H, W, G):
     from habitat_lab_b200 import ops
 
@@ -476,6 +481,22 @@ def test_groupnorm_passes(hb, B, C, H, W, G):
     torch.cuda.synchronize()
     torch.testing.assert_close(nchw(gz.float()), rr2.grad, rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(nchw(dy.float()), yr2.grad, rtol=2e-2, atol=1e-2 * yr2.grad.abs().max().item())
+    dga2.zero_(); dbe2.zero_()
+    gz2 = torch.empty_like(yb)
+    ops.gn_bwd(gb, act, yb, stats, gamma, beta, dga2, dbe2, dy2, gz2, B, hw, C, G, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(gz2, gz)
+    torch.testing.assert_close(dy2.float(), dy.float(), rtol=1e-2, atol=1e-2 * yr2.grad.abs().max().item())
+    torch.testing.assert_close(dga2, dga, rtol=1e-4, atol=1e-4 * dga.abs().max().item())
+    torch.testing.assert_close(dbe2, dbe, rtol=1e-4, atol=1e-4 * dbe.abs().max().item())
+    # mask_mode 0 (downsample branch: GroupNorm without ReLU)
+    sums.zero_(); dga.zero_(); dbe.zero_(); dga2.zero_(); dbe2.zero_()
+    ops.gn_bwd_reduce(gb, None, yb, stats, gamma, beta, sums, dga, dbe, B, hw, C, G, 0)
+    ops.gn_bwd_apply(gb, None, yb, stats, gamma, beta, sums, dy, None, B, hw, C, G, 0)
+    ops.gn_bwd(gb, None, yb, stats, gamma, beta, dga2, dbe2, dy2, None, B, hw, C, G, 0)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dy2.float(), dy.float(), rtol=1e-2, atol=1e-2 * dy.float().abs().max().item())
+    torch.testing.assert_close(dga2, dga, rtol=1e-4, atol=1e-4 * dga.abs().max().item())
     # --- downsample variant: relu(GN(y) + GN_d(yd))
     gd, bd = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
     rstats = _stats_of(res, G)
@@ -484,10 +505,10 @@ def test_groupnorm_passes(hb, B, C, H, W, G):
     torch.testing.assert_close(nchw(blk.float()), o3, rtol=1e-2, atol=3e-2)
 
 
-def test_gn_relu_maxpool(hb):
+@pytest.mark.parametrize("B,C,H,W,G", [(3, 32, 16, 24, 16), (2, 32, 64, 64, 16), (2, 64, 32, 32, 16)])
+def test_gn_relu_maxpool(hb, B, C, H, W, G):
     from habitat_lab_b200 import ops
 
-    B, C, H, W, G = 3, 32, 16, 24, 16
     torch.manual_seed(5)
     y = bf(torch.randn(B, C, H, W, device=DEV)).float()
     gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
@@ -511,6 +532,19 @@ def test_gn_relu_maxpool(hb):
     got = nchw(dz.float())
     mask = zr.detach() > 1e-3
     torch.testing.assert_close(got[mask], ref[mask], rtol=1e-2, atol=1e-2)
+    # fused stem backward (pool + ReLU + GroupNorm backward in one cluster kernel) vs the two-kernel path and autograd
+    hw = H * W
+    dga, dbe, dy = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.empty_like(dz)
+    ops.gn_bwd(dz, None, yb, stats, gamma, beta, dga, dbe, dy, None, B, hw, C, G, 1)
+    assert ops.gn_relu_maxpool_bwd_supported(H, W, C, G)
+    dga2, dbe2, dy2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.empty_like(dz)
+    ops.gn_relu_maxpool_bwd(bf(nhwc(g)), arg, yb, stats, gamma, beta, dga2, dbe2, dy2, B, H, W, C, G)
+    torch.cuda.synchronize()
+    sc = dy.float().abs().max().item()
+    torch.testing.assert_close(dy2.float(), dy.float(), rtol=2e-2, atol=1e-2 * sc)
+    torch.testing.assert_close(dga2, dga, rtol=1e-2, atol=1e-2 * dga.abs().max().item())
+    torch.testing.assert_close(dbe2, dbe, rtol=1e-2, atol=1e-2 * dbe.abs().max().item())
+    assert (nchw(dy2.float()) - yr.grad).norm().item() < 2e-2 * yr.grad.norm().item()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -645,6 +679,56 @@ def test_lstm_masked_recurrence(hb, T, n, H, D):
     torch.testing.assert_close(dw_ih.cpu(), sdr["rnn.weight_ih_l0"].grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(dw_hh.cpu(), sdr["rnn.weight_hh_l0"].grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(db.cpu(), sdr["rnn.bias_ih_l0"].grad, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("T,n,H,D", [(16, 8, 512, 514), (9, 3, 32, 16)])
+def test_gru_masked_recurrence(hb, T, n, H, D):
+    """persistent GRU kernels vs the masked step loop of the oracle (same contract as the LSTM test)"""
+    from habitat_lab_b200 import ops
+
+    torch.manual_seed(T + H)
+    gru = torch.nn.GRU(D, H, num_layers=1)
+    for name, p in gru.named_parameters():
+        torch.nn.init.orthogonal_(p) if "weight" in name else torch.nn.init.normal_(p, std=0.1)
+    sd = {"rnn." + k: v.detach() for k, v in gru.state_dict().items()}
+    x = torch.randn(T * n, D)
+    masks = torch.rand(T * n, 1) > (1 / 25)
+    hidden = torch.randn(n, 1, H)
+    xr = x.clone().requires_grad_(True)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out_ref, hid_ref = O.rnn_seq_forward(xr, hidden, masks, sdr, "rnn.", "GRU", 1, n)
+    gout = torch.randn(T * n, H)
+    (out_ref * gout).sum().backward()
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    w_ih, w_hh, b_ih, b_hh = (d(sd["rnn." + k]) for k in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0"))
+    xd, md = d(x), d(masks.view(-1)).view(torch.uint8)
+    xproj = torch.empty(T * n, 3 * H, device=DEV)
+    ops.linear_fwd(xd, w_ih, b_ih, xproj)
+    h0 = d(hidden[:, 0])
+    hs, saved = torch.empty(T, n, H, device=DEV), torch.empty(T, n, 4 * H, device=DEV)
+    ws = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    ops.gru_seq_fwd(xproj, w_hh, b_hh, md, h0, hs, saved, T, n, H, ws)
+    torch.cuda.synchronize()
+    assert (hs.view(T * n, H).cpu() - out_ref.detach()).norm().item() < 1e-3
+    dgx, dgh = torch.empty(T, n, 3 * H, device=DEV), torch.empty(T, n, 3 * H, device=DEV)
+    ops.gru_seq_bwd(d(gout).view(T, n, H), saved, hs, h0, w_hh, md, dgx, dgh, T, n, H, ws)
+    dgxf, dghf = dgx.view(T * n, 3 * H), dgh.view(T * n, 3 * H)
+    dx = torch.empty(T * n, D, device=DEV)
+    ops.linear_bwd_input(dgxf, w_ih, dx)
+    dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
+    ops.linear_bwd_weight(dgxf, xd, dw_ih)
+    hin = torch.empty(T, n, H, device=DEV)
+    ops.rnn_shift_mask(hs, h0, md, hin, T, n, H)
+    ops.linear_bwd_weight(dghf, hin.view(T * n, H), dw_hh)
+    db_ih, db_hh = torch.empty(3 * H, device=DEV), torch.empty(3 * H, device=DEV)
+    ops.colsum(dgxf, db_ih)
+    ops.colsum(dghf, db_hh)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dx.cpu(), xr.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(dw_ih.cpu(), sdr["rnn.weight_ih_l0"].grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dw_hh.cpu(), sdr["rnn.weight_hh_l0"].grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(db_ih.cpu(), sdr["rnn.bias_ih_l0"].grad, rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(db_hh.cpu(), sdr["rnn.bias_hh_l0"].grad, rtol=1e-3, atol=1e-3)
 
 
 def test_embeddings(hb):

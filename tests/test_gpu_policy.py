@@ -179,3 +179,55 @@ def test_trainer_loop_synthetic_env(hb):
     # (ppo_trainer.py:519-521, 778): after the 2nd of 2 updates the factor is 1 - 1/2
     assert tr.updater.optimizer.param_groups[0]["lr"] == pytest.approx(2.5e-4 * 0.5, rel=1e-6)
     assert len(tr.window_episode_stats["count"]) == 2
+
+
+def test_baseline_cnn_policy_vs_reference(hb):
+    """BASELINE config #1: PointNavBaselinePolicy (SimpleCNN depth-only 128x128, GRU-512, num_envs = 2) --
+    minibatch losses / gradients and PPO.update metrics vs the real reference's recorded outputs."""
+    from habitat_lab_b200.common import spaces
+    from habitat_lab_b200.rl.policy import PointNavBaselinePolicy
+    import numpy as np
+
+    G = load_golden("baseline_cnn")
+    c = G["case"]
+    obs_space = spaces.Dict({"depth": spaces.Box(0.0, 1.0, (c["H"], c["W"], 1), np.float32),
+                             "pointgoal_with_gps_compass": spaces.Box(-1e9, 1e9, (2,), np.float32)})
+    act_space = spaces.Discrete(4)
+    pol = PointNavBaselinePolicy(obs_space, act_space, hidden_size=512)
+    assert {k: tuple(v.shape) for k, v in pol.state_dict().items()} == {k: tuple(v) for k, v in G["shapes"].items()}
+    pol.load_state_dict(recipe_state_dict(G["shapes"], c["seed"]))
+    pol.to(DEV).train()
+    st = hb.RolloutStorage(c["T"], c["N"], obs_space, act_space, pol)
+    bufs, next_value = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, 1, 512, c["seed"], rgb=False)
+    for k, v in bufs["observations"].items():
+        st.buffers["observations"][k].copy_(v)
+    for k in ("recurrent_hidden_states", "masks", "rewards", "value_preds", "returns", "action_log_probs", "actions",
+              "prev_actions"):
+        st.buffers[k].copy_(bufs[k])
+    st.current_rollout_step_idxs = [c["T"]]
+    st.to(DEV)
+    st.compute_returns(next_value.to(DEV), True, 0.99, 0.95)
+    torch.testing.assert_close(st.buffers["returns"][: c["T"]].cpu(), G["returns"][: c["T"]], rtol=1e-5, atol=1e-5)
+    ppo = hb.PPO(pol, clip_param=0.2, ppo_epoch=1, num_mini_batch=1, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4,
+                 eps=1e-5, max_grad_norm=0.2, use_clipped_value_loss=True, use_normalized_advantage=False)
+    adv = ppo.get_advantages(st)
+    torch.manual_seed(G["mb_env_inds_seed"])
+    batch = next(iter(st.data_generator(adv, 1)))
+    metrics = pol.loss_and_backward(batch, 0.2, 0.5, 0.01, True).cpu()
+    torch.cuda.synchronize()
+    got = dict(value_loss=metrics[0].item(), action_loss=metrics[1].item(), dist_entropy=metrics[2].item())
+    print("baseline_cnn losses got", got, "ref", G["mb_losses"])
+    for k in got:
+        assert got[k] == pytest.approx(G["mb_losses"][k], rel=1e-3, abs=2e-4), (k, got[k], G["mb_losses"][k])
+    assert (pol._last["values"].cpu() - G["eval_values"].view(-1)).abs().max().item() < 2e-2
+    assert (pol._last["hidden_out"].cpu() - G["eval_hidden"]).abs().max().item() < 2e-2
+    bad = [(k, p.grad.norm().item(), G["grad_norms"][k]) for k, p in pol.named_parameters()
+           if abs(p.grad.norm().item() - G["grad_norms"][k]) > 0.05 * G["grad_norms"][k] + 1e-6]
+    assert not bad, bad
+    torch.manual_seed(2000 + c["seed"])
+    m = ppo.update(st)
+    ref = G["update_metrics"]
+    print("baseline_cnn update got", m, "ref", ref)
+    for k in ("value_loss", "action_loss", "dist_entropy"):
+        assert m[k] == pytest.approx(ref[k], rel=5e-3, abs=5e-4), k
+    assert m["grad_norm"] == pytest.approx(ref["grad_norm"], rel=3e-2)

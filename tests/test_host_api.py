@@ -32,6 +32,7 @@ def test_registry_names_match_the_reference_yaml_keys():
 
     reg = hb.baseline_registry
     assert reg.get_policy("PointNavResNetPolicy") is hb.PointNavResNetPolicy
+    assert reg.get_policy("PointNavBaselinePolicy") is hb.PointNavBaselinePolicy
     assert reg.get_updater("PPO") is hb.PPO and reg.get_updater("DDPPO") is hb.DDPPO
     assert reg.get_storage("RolloutStorage") is hb.RolloutStorage
     assert reg.get_trainer("ddppo") is hb.PPOTrainer and reg.get_trainer("ppo") is hb.PPOTrainer
