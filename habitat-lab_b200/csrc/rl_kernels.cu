@@ -50,17 +50,63 @@ __global__ void gae_serial_kernel(const float* __restrict__ rewards, float* __re
   double s = 0, ss = 0, cnt = 0;
   if (n < N) {
     const float nv = next_value[n];
+    const bool want_adv = adv != nullptr;
     if (use_gae) {
       values[(size_t)T * N + n] = nv;
       float gae = 0.f, v_next = nv;
-      for (int t = T - 1; t >= 0; --t) {
+      // U time steps of loads are issued before the (serial, order-preserving) recurrence consumes them: the
+      // chain is 4 dependent FP ops per step, the loads are what must be in flight.  Advantages come out of the
+      // same pass: adv = fl(fl(gae + v) - v), exactly what `returns - value_preds` gives the reference.
+      constexpr int U = 8;
+      int t = T - 1;
+      for (; t >= U - 1; t -= U) {
+        float r[U], v[U];
+        uint8_t mk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = (size_t)(t - u) * N + n;
+          r[u] = rewards[i];
+          v[u] = values[i];
+          mk[u] = masks[i + N];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const size_t i = (size_t)(t - u) * N + n;
+          const float m = mk[u] ? 1.f : 0.f;
+          const float delta = __fsub_rn(__fadd_rn(r[u], __fmul_rn(__fmul_rn(gamma, v_next), m)), v[u]);
+          gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gt, gae), m));
+          const float ret = __fadd_rn(gae, v[u]);
+          returns[i] = ret;
+          if (want_adv) {
+            const float a = __fsub_rn(ret, v[u]);
+            adv[i] = a;
+            acc_stats(a, s, ss, cnt);
+          }
+          v_next = v[u];
+        }
+      }
+      for (; t >= 0; --t) {
         const size_t i = (size_t)t * N + n;
         const float m = masks[i + N] ? 1.f : 0.f;
         const float r = rewards[i], v = values[i];
         const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, v_next), m)), v);
         gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gt, gae), m));
-        returns[i] = __fadd_rn(gae, v);
+        const float ret = __fadd_rn(gae, v);
+        returns[i] = ret;
+        if (want_adv) {
+          const float a = __fsub_rn(ret, v);
+          adv[i] = a;
+          acc_stats(a, s, ss, cnt);
+        }
         v_next = v;
+      }
+      if (want_adv) {
+        for (int t2 = T; t2 < Talloc; ++t2) {  // bootstrap row + stale rows of an early-ended rollout
+          const size_t i = (size_t)t2 * N + n;
+          const float a = __fsub_rn(returns[i], t2 == T ? nv : values[i]);
+          adv[i] = a;
+          acc_stats(a, s, ss, cnt);
+        }
       }
     } else {
       returns[(size_t)T * N + n] = nv;
@@ -71,13 +117,13 @@ __global__ void gae_serial_kernel(const float* __restrict__ rewards, float* __re
         ret = __fadd_rn(__fmul_rn(__fmul_rn(gamma, ret), m), rewards[i]);
         returns[i] = ret;
       }
-    }
-    if (adv != nullptr) {
-      for (int t = 0; t < Talloc; ++t) {
-        const size_t i = (size_t)t * N + n;
-        const float a = __fsub_rn(returns[i], values[i]);
-        adv[i] = a;
-        acc_stats(a, s, ss, cnt);
+      if (want_adv) {
+        for (int t = 0; t < Talloc; ++t) {
+          const size_t i = (size_t)t * N + n;
+          const float a = __fsub_rn(returns[i], values[i]);
+          adv[i] = a;
+          acc_stats(a, s, ss, cnt);
+        }
       }
     }
   }

@@ -258,6 +258,57 @@ class _Conv:
         return ops.conv_shape(B, self.in_hw[0], self.in_hw[1], self.ci, self.co, self.k, self.k, self.stride, self.pad)
 
 
+class SideStream:
+    """Second CUDA stream for work nothing on the critical path consumes (weight gradients): the backward pass
+    keeps the data-gradient chain on the main stream and lets the weight-gradient kernels of layer k overlap
+    the GroupNorm-backward / dgrad kernels of layer k-1.  HB200_NO_SIDE_STREAM=1 runs everything in order."""
+
+    def __init__(self):
+        import os
+        self.enabled = not os.environ.get("HB200_NO_SIDE_STREAM")
+        self.stream = None
+
+    class _Ctx:
+        def __init__(self, side):
+            self.side, self.cm = side, None
+
+        def __enter__(self):
+            sd = self.side
+            if not sd.enabled:
+                return self
+            if sd.stream is None:
+                sd.stream = torch.cuda.Stream()
+            sd.stream.wait_stream(torch.cuda.current_stream())   # everything enqueued on main so far
+            self.cm = torch.cuda.stream(sd.stream)
+            self.cm.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            if self.cm is not None:
+                self.cm.__exit__(*exc)
+            return False
+
+    def after_main(self):
+        return SideStream._Ctx(self)
+
+    def mark(self):
+        """event after the side work enqueued so far (None when disabled: program order already covers it)"""
+        if not self.enabled or self.stream is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return ev
+
+    @staticmethod
+    def wait(ev):
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def join(self):
+        if self.enabled and self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+
 class EncoderEngine:
     """ResNet18 (BasicBlock) + compression forward/backward on NHWC bf16 activations."""
 
@@ -292,6 +343,7 @@ class EncoderEngine:
                     c.halo = ops.conv_halo_supported(c.ci, c.co, 3, c.in_hw[0], c.in_hw[1])
         self._ws = {}
         self._dev = None
+        self.side = SideStream()
 
     # ---- buffers -----------------------------------------------------------------------------
     def _ensure(self, B, dev, train):
@@ -318,7 +370,7 @@ class EncoderEngine:
         ws["feat"] = torch.empty(B, ncomp * fh * fw, device=dev)
         if train:
             big = max(int(np.prod(c.out_hw)) * c.co for c in self.convs)
-            for nm in ("g0", "g1", "dy", "gz"):
+            for nm in ("g0", "g1", "dy", "dy2", "gz"):
                 ws[nm] = torch.empty(B * big, dtype=BF16, device=dev)
         self._ws[key] = ws
         return ws
@@ -398,25 +450,37 @@ class EncoderEngine:
             n = int(np.prod(shp))
             return buf[:n].view(*shp)
 
+        # dy buffers alternate so that the weight-gradient kernel of layer k (side stream) can still read its dy
+        # while GroupNorm backward of layer k-1 writes the other one; dy_busy[i] = side-stream event of the last reader
+        side = self.side
+        dy_bufs, dy_busy, dy_turn = [ws["dy"], ws["dy2"]], [None, None], [0]
+
         def gn_bwd(c, g, act, mode, want_gz):
             hw = c.out_hw[0] * c.out_hw[1]
-            sums = ws[f"sums{idx[id(c)]}"]
-            dy = view(ws["dy"], c)
+            slot = dy_turn[0]
+            dy_turn[0] ^= 1
+            side.wait(dy_busy[slot])
+            dy = view(dy_bufs[slot], c)
             gz = view(ws["gz"], c) if want_gz else None
             ops.gn_bwd(g, act, Y(c), ST(c), c.gamma, c.beta, c.gamma.grad, c.beta.grad, dy, gz, B, hw, c.co, c.groups, mode)
             return dy, gz
 
         def wgrad(c, x, dy):
-            c.dw_acc.zero_()
-            if c.stem_s2d:
-                ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.out_hw[0], c.out_hw[1], 16, c.co, 4)
-                ops.unpack_stem_wgrad(c.dw_acc, c.w.grad)
-                return
-            if c.halo:
-                ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, 3)
-            else:
-                ops.conv_wgrad(x, dy, c.dw_acc, c.shape(B))
-            ops.unpack_conv_wgrad(c.dw_acc, c.w.grad, c.ci)
+            with side.after_main():
+                c.dw_acc.zero_()
+                if c.stem_s2d:
+                    ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.out_hw[0], c.out_hw[1], 16, c.co, 4)
+                    ops.unpack_stem_wgrad(c.dw_acc, c.w.grad)
+                else:
+                    if c.halo:
+                        ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, 3)
+                    else:
+                        ops.conv_wgrad(x, dy, c.dw_acc, c.shape(B))
+                    ops.unpack_conv_wgrad(c.dw_acc, c.w.grad, c.ci)
+                ev = side.mark()
+            for i in (0, 1):
+                if dy.data_ptr() == dy_bufs[i].data_ptr():
+                    dy_busy[i] = ev
 
         g_bufs = [ws["g0"], ws["g1"]]
         cur = 0
@@ -467,6 +531,7 @@ class EncoderEngine:
             ops.maxpool_bwd(g, ws["argmax"], gzs, B, sh, sw, stem.co)
             dy0, _ = gn_bwd(stem, gzs, None, 1, False)
         wgrad(stem, ws["x0"], dy0)
+        side.join()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -490,6 +555,7 @@ class NativeNetPolicy(nn.Module):
         self.aux_loss_modules = nn.ModuleDict()
         self._flat = None
         self._buf = {}
+        self._side = SideStream()
         self.world_size = 1  # set by the distributed updater
         self.dist_group = None
 
@@ -625,15 +691,16 @@ class NativeNetPolicy(nn.Module):
                 ops.gru_seq_bwd(d_out.view(T, n, H), ly["gates"], ly["hs"], ly["h0"], w_hh, mk, dgx, dgh, T, n, H, ws)
             dgxf, dghf = dgx.view(B, G * H), dgh.view(B, G * H)
             x = ly["x"]
-            ops.linear_bwd_weight(dgxf, x, w_ih.grad, accumulate=True, tf32=True)  # grads pre-zeroed: split-K
-            hin = self._tmp("hin", (T, n, H), dev)
-            ops.rnn_shift_mask(ly["hs"], ly["h0"], mk, hin, T, n, H)
-            ops.linear_bwd_weight(dghf, hin.view(B, H), w_hh.grad, accumulate=True, tf32=True)
-            ops.colsum(dgxf, b_ih.grad)
-            if lstm:
-                b_hh.grad.copy_(b_ih.grad)
-            else:
-                ops.colsum(dghf, b_hh.grad)
+            with self._side.after_main():   # weight gradients: off the critical path (SideStream)
+                ops.linear_bwd_weight(dgxf, x, w_ih.grad, accumulate=True, tf32=True)  # grads pre-zeroed: split-K
+                hin = self._tmp("hin", (T, n, H), dev)
+                ops.rnn_shift_mask(ly["hs"], ly["h0"], mk, hin, T, n, H)
+                ops.linear_bwd_weight(dghf, hin.view(B, H), w_hh.grad, accumulate=True, tf32=True)
+                ops.colsum(dgxf, b_ih.grad)
+                if lstm:
+                    b_hh.grad.copy_(b_ih.grad)
+                else:
+                    ops.colsum(dghf, b_hh.grad)
             dx = self._tmp(f"dx{l}", (B, x.stride(0)), dev)[:, : x.shape[1]]   # same (16-byte) row pitch as x
             ops.linear_bwd_input(dgxf, w_ih, dx, tf32=True)
             d_out = dx
@@ -725,6 +792,7 @@ class NativeNetPolicy(nn.Module):
                      out, self._loss_ws(B, dev), is_coeffs=f32(batch["is_coeffs"]) if "is_coeffs" in batch else None)
         d_rnn_in = self._rnn_backward(out["d_features"], s["layers"], s["masks"], T, n, B, dev)
         self._visual_backward(d_rnn_in, s, B, dev)
+        self._side.join()
         self._last = dict(values=out["values"], log_probs=out["log_probs"], entropy=out["entropy"],
                           hidden_out=s["hidden_out"])
         return out["metrics"]
@@ -774,6 +842,7 @@ class PointNavResNetPolicy(NativeNetPolicy):
     def _engine_(self):
         if self._engine is None:
             self._engine = EncoderEngine(self.net.visual_encoder)
+            self._engine.side = self._side   # one side stream for the whole backward pass
         return self._engine
 
     def _visual_prep(self, observations, rows, B, dev, update_stats):
@@ -826,8 +895,9 @@ class PointNavResNetPolicy(NativeNetPolicy):
         fc = self.net.visual_fc[1]
         ops.relu_bwd(d_rnn_in, v["rnn_in"], H)
         dvis = d_rnn_in[:, :H]
-        ops.linear_bwd_weight(dvis, v["feat"], fc.weight.grad, accumulate=True, tf32=True)
-        ops.colsum(dvis, fc.bias.grad, n_cols=H)
+        with self._side.after_main():
+            ops.linear_bwd_weight(dvis, v["feat"], fc.weight.grad, accumulate=True, tf32=True)
+            ops.colsum(dvis, fc.bias.grad, n_cols=H)
         d_feat = self._tmp("d_feat", tuple(v["feat"].shape), dev)
         ops.linear_bwd_input(dvis, fc.weight, d_feat, tf32=True)
         self._engine_().backward(d_feat, B, dev)
