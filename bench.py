@@ -345,6 +345,7 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
     inputs[id(eng.comp)] = x
     per = {"fwd": [0.0, 0.0], "dgrad": [0.0, 0.0], "wgrad": [0.0, 0.0]}
     detail = []
+    sol = [0.0, 0.0]
     for c in eng.convs:
         i = idx[id(c)]
         s = c.shape(B)
@@ -367,7 +368,14 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
             dx = ws["g0"][: xin.numel()].view_as(xin)
             td = t_ms(lambda: eng._dgrad(c, y, dx, B))
             per["dgrad"][0] += flop; per["dgrad"][1] += td
+        # speed of light of each launch: max(tensor time, HBM time of reading both operands / writing the result once)
+        nbytes = 2.0 * (xin.numel() + y.numel())
+        t_sol = max(flop / (peaks["bf16"] * 1e12), nbytes / (peaks["hbm"] * 1e9)) * 1e3
+        bound = "tensor" if flop / (peaks["bf16"] * 1e12) > nbytes / (peaks["hbm"] * 1e9) else "hbm"
+        sol[0] += t_sol * (2 if td is None else 3)
+        sol[1] += tf + tw + (td or 0.0)
         detail.append({"conv": f"{c.ci_real}->{c.co} k{c.k}s{c.stride} @{c.in_hw[0]}", "gflop": flop * 1e-9,
+                       "mbytes": nbytes * 1e-6, "bound": bound, "sol_ms": t_sol,
                        "fwd_ms": tf, "dgrad_ms": td, "wgrad_ms": tw})
     flops = sum(v[0] for v in per.values())
     ms = sum(v[1] for v in per.values())
@@ -376,6 +384,9 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
             "bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16"], "peak_source": peaks["src"] + " (burst: kernels timed alone)",
             "traffic": None,
+            "speed_of_light": {"note": "per launch max(FLOPs / bf16 peak, (input + output bytes) / HBM peak): the 32- and "
+                                       "64-channel layers are HBM-bound, not tensor-bound", "sol_ms": sol[0],
+                               "measured_ms": sol[1], "frac": sol[0] / sol[1] if sol[1] else None},
             "by_pass": {k: {"tflops": (v[0] / (v[1] * 1e-3) * 1e-12) if v[1] else None, "ms": v[1]} for k, v in per.items()},
             "per_layer": detail}
 

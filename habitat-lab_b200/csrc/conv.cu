@@ -21,7 +21,7 @@
 
 namespace hb200 {
 void count_launch(int n);
-static int g_umma_layout = 0;
+static int g_umma_layout = 1;  // 128-byte swizzle (coalesced gathers); 0 = no-swizzle interleave
 
 using namespace umma;
 
@@ -100,6 +100,11 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
     op = rem / a.OW;
     oq = rem - op * a.OW;
   }
+  // LAYOUT 1 (128-byte swizzle) gathers with a coalesced mapping -- 8 consecutive lanes fetch the 8 x 16 B of ONE
+  // pixel's 64-channel run (one full 128-byte line) and write one swizzled smem row -- so every thread needs the
+  // pixel coordinates of 8 other rows: publish them once per tile.
+  __shared__ int4 row_info[kTileM];
+  if (LAYOUT == 1) row_info[tid] = make_int4(ob, op, oq, row_ok ? 1 : 0);
   if (tid == 0) {
     int nv = 0;
     const int cpt = a.SC >> 6;  // 64-channel chunks per tap (>= 1 in class mode)
@@ -132,6 +137,35 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
   auto load_chunk = [&](int chunk, int stage) {
     const uint32_t sa = smem_base + stage * kStageBytes;
     const uint32_t sb = sa + kABytes;
+    if (LAYOUT == 1) {
+      const int j = tid & 7;
+      const int k0 = (chunk * 8 + j) << 3;
+      const int tap = k0 >> a.cshift;
+      const int c0 = k0 & (a.SC - 1);
+      const int r = tap / a.kw, s = tap - r * a.kw;
+      const bool tap_ok = tap < taps;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = (tid >> 3) + 16 * i;
+        const int4 ri = row_info[row];
+        bool ok = ri.w && tap_ok;
+        int ih, iw;
+        if (MODE == 0) {
+          ih = ri.y * a.stride - a.pad + r;
+          iw = ri.z * a.stride - a.pad + s;
+          ok = ok && ih >= 0 && ih < a.SH && iw >= 0 && iw < a.SW;
+        } else {
+          const int th = ri.y + a.pad - r, tw = ri.z + a.pad - s;
+          ih = th / a.stride;
+          iw = tw / a.stride;
+          ok = ok && th >= 0 && tw >= 0 && (ih * a.stride == th) && (iw * a.stride == tw) &&
+               ih < a.SH && iw < a.SW;
+        }
+        const __nv_bfloat16* g =
+            ok ? a.src + ((((size_t)ri.x * a.SH + ih) * a.SW + iw) << a.cshift) + c0 : a.src;
+        cp_async16(sa + tile_off<1>(row, j, kTileM), g, ok);
+      }
+    } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k0 = (chunk * 8 + j) << 3;
@@ -154,6 +188,7 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
       const __nv_bfloat16* g =
           ok ? a.src + ((((size_t)ob * a.SH + ih) * a.SW + iw) << a.cshift) + c0 : a.src;
       cp_async16(sa + tile_off<LAYOUT>(tid, j, kTileM), g, ok);
+    }
     }
     const uint4* wsrc = reinterpret_cast<const uint4*>(wtile + (size_t)chunk * (BN * kChunkK));
 #pragma unroll

@@ -6,6 +6,7 @@
 // the truly sequential h W_hh^T part lives here.  This replaces the PackedSequence index
 // machinery (rnn_state_encoder.py:35-277): a masked recurrence needs nothing but `masks`.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace hb200 {
 void count_launch(int n);
@@ -393,6 +394,250 @@ lstm_seq_bwd_kernel(const float* __restrict__ dh_out, const float* __restrict__ 
 }
 }  // namespace hb200
 
+// =====================================================================================
+// v2 of the persistent LSTM kernels (hidden = 512): register-tiled recurrent mat-vecs.
+// v1 gives every sequence its own warp, so each W_hh element is re-read from shared memory once per sequence and
+// the step is bound by shared-memory bandwidth (1 LDS per FMA: ~4.3 us of the ~7.7 us step).  Here a warp owns an
+// 8-sequence x 8-gate-row (forward) / 8-sequence x 4-column (backward) tile: one 16-byte LDS feeds 8 x 4 FMAs, the
+// staged h_{t-1} block / the streamed dgates rows are shared by the whole tile, and the 64 (32) per-lane partial
+// sums are finished with one transpose-reduce.
+// =====================================================================================
+namespace hb200 {
+
+// lane l ends with the warp sums of v[2l], v[2l+1]
+__device__ __forceinline__ void warp_reduce64(float (&v)[64], int lane, float& o0, float& o1) {
+  float a[32], b[16], c[8], d[4], e[2];
+  { const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const float send = hi ? v[i] : v[i + 32], keep = hi ? v[i + 32] : v[i];
+                                   a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); } }
+  { const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float send = hi ? a[i] : a[i + 16], keep = hi ? a[i + 16] : a[i];
+                                   b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); } }
+  { const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float send = hi ? b[i] : b[i + 8], keep = hi ? b[i + 8] : b[i];
+                                  c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); } }
+  { const bool hi = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float send = hi ? c[i] : c[i + 4], keep = hi ? c[i + 4] : c[i];
+                                  d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); } }
+  { const bool hi = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const float send = hi ? d[i] : d[i + 2], keep = hi ? d[i + 2] : d[i];
+                                  e[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1); } }
+  o0 = e[0];
+  o1 = e[1];
+}
+// lane l ends with the warp sum of v[l]
+__device__ __forceinline__ float warp_reduce32(float (&v)[32], int lane) {
+  float a[16], b[8], c[4], d[2];
+  { const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float send = hi ? v[i] : v[i + 16], keep = hi ? v[i + 16] : v[i];
+                                   a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); } }
+  { const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float send = hi ? a[i] : a[i + 8], keep = hi ? a[i + 8] : a[i];
+                                  b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); } }
+  { const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float send = hi ? b[i] : b[i + 4], keep = hi ? b[i + 4] : b[i];
+                                  c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); } }
+  { const bool hi = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const float send = hi ? c[i] : c[i + 2], keep = hi ? c[i + 2] : c[i];
+                                  d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); } }
+  const bool hi = lane & 1;
+  const float send = hi ? d[0] : d[1], keep = hi ? d[1] : d[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+constexpr int kV2Threads = 256;
+
+template <int H>
+__global__ void __launch_bounds__(kV2Threads)
+lstm_seq_fwd_v2_kernel(const float* __restrict__ xproj, const float* __restrict__ w_hh,
+                       const float* __restrict__ b_hh, const uint8_t* __restrict__ masks,
+                       const float* __restrict__ h0, long long h0_stride, const float* __restrict__ c0,
+                       long long c0_stride, float* __restrict__ hs, float* __restrict__ cs,
+                       float* __restrict__ gates_out, int T, int n, unsigned* counter) {
+  extern __shared__ __align__(16) float sm2[];
+  float* sw = sm2;             // [16][H]   row = gate * 4 + unit
+  float* sh = sw + 16 * H;     // [32][H]   h_{t-1} of the current block of 32 sequences
+  float* spre = sh + 32 * H;   // [32][16]  recurrent pre-activation sums
+  const int u0 = blockIdx.x * kUnits;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 16 * H; i += kV2Threads) {
+    const int r = i / H, k = i - r * H;
+    sw[i] = w_hh[((size_t)(r >> 2) * H + u0 + (r & 3)) * H + k];
+  }
+  const int sg = warp & 3, rg = warp >> 2;           // 8-sequence group, 8-row group of this warp's tile
+  const int ps = tid >> 2, pu = tid & 3, col = u0 + pu;  // pointwise role (threads 0..127)
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (b_hh && tid < 128) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) bias[g] = b_hh[(size_t)g * H + col];
+  }
+  __syncthreads();
+  for (int t = 0; t < T; ++t) {
+    const float* hp = t == 0 ? h0 : hs + (size_t)(t - 1) * n * H;
+    const long long hps = t == 0 ? h0_stride : H;
+    const float* cp = t == 0 ? c0 : cs + (size_t)(t - 1) * n * H;
+    const long long cps = t == 0 ? c0_stride : H;
+    for (int s0 = 0; s0 < n; s0 += 32) {
+      const int ns = min(32, n - s0);
+      // pointwise operands do not depend on the mat-vec: fetch them first
+      float xp[4] = {0.f, 0.f, 0.f, 0.f}, cprev = 0.f, m = 0.f;
+      const bool pw = tid < 128 && ps < ns;
+      if (pw) {
+        const size_t row = (size_t)t * n + s0 + ps;
+        m = masks[row] ? 1.f : 0.f;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xp[g] = xproj[row * 4 * H + (size_t)g * H + col];
+        cprev = __ldcg(cp + (size_t)(s0 + ps) * cps + col);
+      }
+      // stage h_{t-1} of the block (written by all CTAs in the previous step: L2 loads)
+      float4* sh4 = reinterpret_cast<float4*>(sh);
+      for (int i = tid; i < 32 * (H / 4); i += kV2Threads) {
+        const int row = i / (H / 4), c4 = i - row * (H / 4);
+        sh4[i] = row < ns ? __ldcg(reinterpret_cast<const float4*>(hp + (size_t)(s0 + row) * hps) + c4)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncthreads();
+      float acc[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+#pragma unroll 1
+      for (int jj = 0; jj < H / 128; ++jj) {
+        const int k = 4 * lane + 128 * jj;
+        float4 wv[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) wv[r] = *reinterpret_cast<const float4*>(sw + (rg * 8 + r) * H + k);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 hv = *reinterpret_cast<const float4*>(sh + (sg * 8 + i) * H + k);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            float a = acc[i * 8 + r];
+            a = fmaf(hv.x, wv[r].x, a);
+            a = fmaf(hv.y, wv[r].y, a);
+            a = fmaf(hv.z, wv[r].z, a);
+            a = fmaf(hv.w, wv[r].w, a);
+            acc[i * 8 + r] = a;
+          }
+        }
+      }
+      float o0, o1;
+      warp_reduce64(acc, lane, o0, o1);  // lane -> sequence (lane >> 2), rows 2 * (lane & 3) + {0, 1} of the tile
+      *reinterpret_cast<float2*>(spre + (sg * 8 + (lane >> 2)) * 16 + rg * 8 + 2 * (lane & 3)) = make_float2(o0, o1);
+      __syncthreads();
+      if (pw) {
+        const float* pr = spre + ps * 16 + pu;
+        const float i_ = sigmoidf_(pr[0] * m + bias[0] + xp[0]);   // (h*m) . w == m * (h . w)
+        const float f_ = sigmoidf_(pr[4] * m + bias[1] + xp[1]);
+        const float g_ = tanhf(pr[8] * m + bias[2] + xp[2]);
+        const float o_ = sigmoidf_(pr[12] * m + bias[3] + xp[3]);
+        const float cn = f_ * (cprev * m) + i_ * g_;
+        const size_t o = ((size_t)t * n + s0 + ps) * H + col;
+        cs[o] = cn;
+        hs[o] = o_ * tanhf(cn);
+        if (gates_out) {
+          float* gp = gates_out + ((size_t)t * n + s0 + ps) * 4 * H;
+          gp[col] = i_; gp[H + col] = f_; gp[2 * H + col] = g_; gp[3 * H + col] = o_;
+        }
+      }
+    }
+    if (t + 1 < T) grid_barrier(counter, (unsigned)(t + 1) * gridDim.x);
+  }
+}
+
+template <int H>
+__global__ void __launch_bounds__(kV2Threads)
+lstm_seq_bwd_v2_kernel(const float* __restrict__ dh_out, const float* __restrict__ gates,
+                       const float* __restrict__ cs, const float* __restrict__ c0, long long c0_stride,
+                       const float* __restrict__ w_hh, const uint8_t* __restrict__ masks,
+                       float* __restrict__ dgates, int T, int n, unsigned* counter) {
+  extern __shared__ __align__(16) float sm2[];
+  constexpr int R = 4 * H;
+  float* wt = sm2;                 // [4][R]  W_hh^T columns of this CTA's 4 units
+  float* spart = wt + 4 * R;       // [2][32][4]  partial dh_rec of the two r-halves
+  float* dh_rec = spart + 256;     // [n][4]
+  float* dc_rec = dh_rec + 4 * n;  // [n][4]
+  const int u0 = blockIdx.x * kUnits;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 4 * R; i += kV2Threads) {
+    const int u = i / R, r = i - u * R;
+    wt[i] = w_hh[(size_t)r * H + u0 + u];
+  }
+  for (int i = tid; i < 4 * n; i += kV2Threads) { dh_rec[i] = 0.f; dc_rec[i] = 0.f; }
+  __syncthreads();
+  const int sg = warp & 3, rh = warp >> 2;  // 8-sequence group, half of the 4H gate rows
+  for (int t = T - 1; t >= 0; --t) {
+    // ---- pointwise for own units (identical to v1)
+    for (int i = tid; i < 4 * n; i += kV2Threads) {
+      const int s = i >> 2, col = u0 + (i & 3);
+      const size_t row = (size_t)t * n + s;
+      const float m = masks[row] ? 1.f : 0.f;
+      const float* gt = gates + row * R;
+      const float i_ = gt[col], f_ = gt[H + col], g_ = gt[2 * H + col], o_ = gt[3 * H + col];
+      const float dh = dh_out[row * H + col] + dh_rec[i];
+      const float tc = tanhf(cs[row * H + col]);
+      const float dc = dh * o_ * (1.f - tc * tc) + dc_rec[i];
+      const float cin = (t == 0 ? c0[(size_t)s * c0_stride + col] : cs[(row - n) * H + col]) * m;
+      float* dg = dgates + row * R;
+      dg[col] = dc * g_ * i_ * (1.f - i_);
+      dg[H + col] = dc * cin * f_ * (1.f - f_);
+      dg[2 * H + col] = dc * i_ * (1.f - g_ * g_);
+      dg[3 * H + col] = dh * tc * o_ * (1.f - o_);
+      dc_rec[i] = dc * f_ * m;
+    }
+    if (t == 0) break;
+    grid_barrier(counter, (unsigned)(T - t) * gridDim.x);
+    // ---- dh_{t-1}[s, own 4 cols] = m_t[s] * sum_r dgates_t[s, r] * W_hh[r, col]
+    for (int s0 = 0; s0 < n; s0 += 32) {
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      const float* dgt = dgates + ((size_t)t * n + s0 + sg * 8) * R + rh * (R / 2) + 4 * lane;
+      const int nrows = min(8, n - s0 - sg * 8);  // sequences of this tile that exist (<= 0: none)
+#pragma unroll 2
+      for (int jj = 0; jj < R / 2 / 128; ++jj) {
+        float4 d[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          d[i] = i < nrows ? __ldcg(reinterpret_cast<const float4*>(dgt + (size_t)i * R + jj * 128))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int r = rh * (R / 2) + jj * 128 + 4 * lane;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 w = *reinterpret_cast<const float4*>(wt + u * R + r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a = acc[i * 4 + u];
+            a = fmaf(d[i].x, w.x, a);
+            a = fmaf(d[i].y, w.y, a);
+            a = fmaf(d[i].z, w.z, a);
+            a = fmaf(d[i].w, w.w, a);
+            acc[i * 4 + u] = a;
+          }
+        }
+      }
+      const float v = warp_reduce32(acc, lane);  // lane -> sequence (lane >> 2), unit (lane & 3) of the tile
+      spart[rh * 128 + sg * 32 + lane] = v;
+      __syncthreads();
+      if (tid < 128 && s0 + (tid >> 2) < n) {
+        const int s = s0 + (tid >> 2);
+        const float m = masks[(size_t)t * n + s] ? 1.f : 0.f;
+        dh_rec[4 * s + (tid & 3)] = (spart[tid] + spart[128 + tid]) * m;
+      }
+      __syncthreads();
+    }
+  }
+}
+}  // namespace hb200
+
 static int coop_check(const void* kern, int block, size_t smem, int grid) {
   int per_sm = 0;
   HB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem));
@@ -418,11 +663,22 @@ extern "C" int hb200_lstm_seq_fwd(const float* xproj, const float* w_hh, const f
   cudaStream_t st = (cudaStream_t)stream;
   unsigned* counter = (unsigned*)workspace;
   HB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), st));
-  const size_t smem = sizeof(float) * 16 * hidden;
   const int grid = hidden / kUnits;
   void* args[] = {(void*)&xproj, (void*)&w_hh, (void*)&b_hh, (void*)&masks, (void*)&h0, (void*)&h0_stride,
                   (void*)&c0, (void*)&c0_stride, (void*)&hs, (void*)&cs, (void*)&gates_out, (void*)&t_steps,
                   (void*)&n, (void*)&counter};
+  static const bool use_v1 = getenv("HB200_LSTM_V1") != nullptr;
+  if (hidden == 512 && !use_v1 && h0_stride % 4 == 0 && ((uintptr_t)h0 & 15) == 0 && ((uintptr_t)hs & 15) == 0) {
+    const void* k2 = (const void*)lstm_seq_fwd_v2_kernel<512>;
+    const size_t smem2 = sizeof(float) * (16 * 512 + 32 * 512 + 32 * 16);
+    HB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    int rc2 = coop_check(k2, kV2Threads, smem2, grid);
+    if (rc2) return rc2;
+    HB_CUDA(cudaLaunchCooperativeKernel(k2, dim3(grid), dim3(kV2Threads), args, smem2, st));
+    count_launch(1);
+    return HB200_OK;
+  }
+  const size_t smem = sizeof(float) * 16 * hidden;
   const void* kern = nullptr;
   switch (hidden / 32) {
     case 1: kern = (const void*)lstm_seq_fwd_kernel<1>; break;
@@ -451,6 +707,19 @@ extern "C" int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const
   const size_t smem = sizeof(float) * (16 * (size_t)hidden + 8 * (size_t)n);
   HB_CHECK_ARG(smem <= 200 * 1024, "lstm_seq_bwd: n=%d too large for one CTA's shared memory", n);
   const int grid = hidden / kUnits;
+  static const bool use_v1 = getenv("HB200_LSTM_V1") != nullptr;
+  if (hidden == 512 && !use_v1 && ((uintptr_t)dgates & 15) == 0) {
+    const void* k2 = (const void*)lstm_seq_bwd_v2_kernel<512>;
+    const size_t smem2 = smem + sizeof(float) * 256;
+    void* args2[] = {(void*)&dh_out, (void*)&gates, (void*)&cs, (void*)&c0, (void*)&c0_stride, (void*)&w_hh,
+                     (void*)&masks, (void*)&dgates, (void*)&t_steps, (void*)&n, (void*)&counter};
+    if (smem2 > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    int rc2 = coop_check(k2, kV2Threads, smem2, grid);
+    if (rc2) return rc2;
+    HB_CUDA(cudaLaunchCooperativeKernel(k2, dim3(grid), dim3(kV2Threads), args2, smem2, st));
+    count_launch(1);
+    return HB200_OK;
+  }
   const void* kern = (const void*)lstm_seq_bwd_kernel;
   if (smem > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int rc = coop_check(kern, kSeqThreads, smem, grid);

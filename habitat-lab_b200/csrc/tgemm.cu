@@ -15,6 +15,7 @@
 // One MMA covers K = 8 (32 bytes); a chunk is K = 32 (4 MMAs); 3-stage cp.async ring as in conv.cu.
 // Weight gradients (K = frames, tiny M x N tile grid) are split over K with fp32 atomics.
 #include "common.cuh"
+#include <stdlib.h>
 #include "umma.cuh"
 
 namespace hb200 {
@@ -51,13 +52,16 @@ __device__ __forceinline__ void tg_load(const float* __restrict__ p, long long s
                                         int k0, int k_end, uint32_t sdst, int rows) {
   if (!MNMAJOR) {
     // K-major: vector = 4 consecutive k of one row; 8 vectors per row per chunk
+    // 128-byte swizzle: 8 consecutive threads fetch the 8 x 16 B of one row (a full 128-byte line) and write one
+    // swizzled shared-memory row (conflict free); the row-per-thread mapping of the no-swizzle layout touched 32
+    // different lines per request and used half of every 32-byte sector.
     for (int v = threadIdx.x; v < rows * 8; v += 128) {
-      const int row = v % rows, k4 = v / rows;          // consecutive threads: consecutive rows = consecutive
-                                                        // 16-byte smem slots (bank-conflict free)
+      const int row = v >> 3, k4 = v & 7;
       const int gm = mn0 + row, gk = k0 + k4 * 4;
       const bool ok = gm < MN && gk + 3 < k_end;
       const float* g = ok ? p + (long long)gm * s_mn + gk : p;
-      cp_async16(sdst + (uint32_t)(k4 * rows + row) * 16, g, ok);
+      cp_async16(sdst + (uint32_t)((row >> 3) << 10) + (uint32_t)((row & 7) << 7) + (uint32_t)((k4 ^ (row & 7)) << 4),
+                 g, ok);
     }
   } else {
     // MN-major: vector = 4 consecutive mn at one k; rows/4 vectors per k
@@ -81,7 +85,7 @@ __global__ void __launch_bounds__(128) tgemm_kernel(const TgemmArgs a) {
   __shared__ uint32_t tmem_slot;
   constexpr uint32_t kABytes = GT_M * GT_K * 4, kBBytes = BN * GT_K * 4, kStage = kABytes + kBBytes;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
-  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms are 1024-byte aligned
   const int tid = threadIdx.x, warp = tid >> 5;
   const int m0 = blockIdx.y * GT_M, n0 = blockIdx.x * BN;
   const int k_begin = blockIdx.z * a.k_per_split;
@@ -125,9 +129,9 @@ __global__ void __launch_bounds__(128) tgemm_kernel(const TgemmArgs a) {
         // K-major: the two 16-byte k4 vectors of this K=8 step are LBO = rows*16 apart
         // MN-major: one 8-k block per step, blocks LBO' = (rows/4)*128 apart; SBO = 128 between 4-mn vectors
         const uint64_t da = A_MN ? make_smem_desc(sa + kk * (GT_M / 4) * 128, (GT_M / 4) * 128, 128, kNoSwizzle)
-                                 : make_smem_desc(sa + kk * 2 * GT_M * 16, GT_M * 16, 128, kNoSwizzle);
+                                 : make_smem_desc(sa + kk * 32, 16, 1024, kSwizzle128B);
         const uint64_t db = B_MN ? make_smem_desc(sb + kk * (BN / 4) * 128, (BN / 4) * 128, 128, kNoSwizzle)
-                                 : make_smem_desc(sb + kk * 2 * BN * 16, BN * 16, 128, kNoSwizzle);
+                                 : make_smem_desc(sb + kk * 32, 16, 1024, kSwizzle128B);
         mma_tf32_ss(tmem_base, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
       }
       mma_commit(&mma_bar[st]);
@@ -190,7 +194,16 @@ extern "C" int hb200_tgemm(const float* a, long long a_ms, long long a_ks, const
   HB_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0,
                "tgemm: operands must be 16-byte aligned with leading dimensions that are multiples of 4");
   HB_CHECK_ARG(k % 4 == 0 && (!a_mn || m % 4 == 0) && (!b_mn || n % 4 == 0), "tgemm: k (and mn-major extents) must be multiples of 4");
-  const int BN = n >= 256 ? 256 : (n >= 128 ? 128 : (n >= 64 ? 64 : 32));
+  int BN = n >= 256 ? 256 : (n >= 128 ? 128 : (n >= 64 ? 64 : 32));
+  {
+    // N tile 128 instead of 256 when that is what fills the 148 SMs (2 CTAs per SM fit at 96 KB of stages)
+    static const int forced = getenv("HB200_TGEMM_BN") ? atoi(getenv("HB200_TGEMM_BN")) : 0;
+    if (forced == 32 || forced == 64 || forced == 128 || forced == 256) {
+      if (forced <= BN) BN = forced;
+    } else if (BN == 256 && (long long)cdiv(n, 256) * cdiv(m, GT_M) < 2 * kNumSMs) {
+      BN = 128;
+    }
+  }
   HB_CHECK_ARG(n % 4 == 0, "tgemm: n must be a multiple of 4");
   TgemmArgs g;
   g.a = a; g.a_ms = a_ms; g.a_ks = a_ks; g.b = b; g.b_ks = b_ks; g.b_ns = b_ns; g.c = c; g.ldc = ldc; g.bias = bias;
@@ -208,7 +221,7 @@ extern "C" int hb200_tgemm(const float* a, long long a_ms, long long a_ks, const
   cudaStream_t st = (cudaStream_t)stream;
 #define HB_TG(bn, AM, BM)                                                                          \
   {                                                                                                \
-    const size_t smem = (size_t)GT_STAGES * (GT_M * GT_K * 4 + bn * GT_K * 4) + 256;               \
+    const size_t smem = (size_t)GT_STAGES * (GT_M * GT_K * 4 + bn * GT_K * 4) + 1024;              \
     auto kern = tgemm_kernel<bn, AM, BM>;                                                          \
     HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     kern<<<grid, 128, smem, st>>>(g);                                                              \

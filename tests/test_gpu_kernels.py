@@ -600,7 +600,7 @@ def test_tgemm_tf32(hb, M, N, K):
     torch.testing.assert_close(dw, ref_dw, rtol=2e-3, atol=2e-3 * ref_dw.abs().max().item())
 
 
-@pytest.mark.parametrize("T,n,H,D", [(16, 8, 512, 576), (7, 3, 32, 32), (33, 33, 128, 64)])
+@pytest.mark.parametrize("T,n,H,D", [(16, 8, 512, 576), (7, 3, 32, 32), (33, 33, 128, 64), (9, 35, 512, 64)])
 def test_lstm_masked_recurrence(hb, T, n, H, D):
     """The logic of test/test_rnn_state_encoder.py:72-94: flat (T*N) batch + masks must equal the
     step-by-step loop h = where(mask, h, 0); rnn(x_t, h), norm of the difference < 1e-3."""
