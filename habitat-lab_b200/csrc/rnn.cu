@@ -482,6 +482,7 @@ lstm_seq_fwd_v2_kernel(const float* __restrict__ xproj, const float* __restrict_
   }
   __syncthreads();
   for (int t = 0; t < T; ++t) {
+    asm volatile("" ::: "memory");  // keep step t+1's operand loads (xproj / masks rows) below this step's exit test
     const float* hp = t == 0 ? h0 : hs + (size_t)(t - 1) * n * H;
     const long long hps = t == 0 ? h0_stride : H;
     const float* cp = t == 0 ? c0 : cs + (size_t)(t - 1) * n * H;
@@ -496,14 +497,21 @@ lstm_seq_fwd_v2_kernel(const float* __restrict__ xproj, const float* __restrict_
         m = masks[row] ? 1.f : 0.f;
 #pragma unroll
         for (int g = 0; g < 4; ++g) xp[g] = xproj[row * 4 * H + (size_t)g * H + col];
-        cprev = __ldcg(cp + (size_t)(s0 + ps) * cps + col);
+        cprev = __ldcg(cp + (size_t)(s0 + ps) * cps + col);   // written by this very thread one step ago
       }
       // stage h_{t-1} of the block (written by all CTAs in the previous step: L2 loads)
       float4* sh4 = reinterpret_cast<float4*>(sh);
-      for (int i = tid; i < 32 * (H / 4); i += kV2Threads) {
-        const int row = i / (H / 4), c4 = i - row * (H / 4);
-        sh4[i] = row < ns ? __ldcg(reinterpret_cast<const float4*>(hp + (size_t)(s0 + row) * hps) + c4)
+      {
+        constexpr int NV = 32 * (H / 4) / kV2Threads;  // 16 vectors per thread, all in flight at once
+        float4 v[NV];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          const int i = tid + q * kV2Threads, row = i / (H / 4), c4 = i - row * (H / 4);
+          v[q] = row < ns ? __ldcg(reinterpret_cast<const float4*>(hp + (size_t)(s0 + row) * hps) + c4)
                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) sh4[tid + q * kV2Threads] = v[q];
       }
       __syncthreads();
       float acc[64];
@@ -575,6 +583,9 @@ lstm_seq_bwd_v2_kernel(const float* __restrict__ dh_out, const float* __restrict
   __syncthreads();
   const int sg = warp & 3, rh = warp >> 2;  // 8-sequence group, half of the 4H gate rows
   for (int t = T - 1; t >= 0; --t) {
+    // compiler barrier: without a grid barrier in the loop nvcc software-pipelines the read-only (LDG.CONSTANT)
+    // operand loads of step t-1 above the exit test of step t and reads rows -n..-1 of gates / dh_out at t = 0
+    asm volatile("" ::: "memory");
     // ---- pointwise for own units (identical to v1)
     for (int i = tid; i < 4 * n; i += kV2Threads) {
       const int s = i >> 2, col = u0 + (i & 3);
@@ -595,6 +606,7 @@ lstm_seq_bwd_v2_kernel(const float* __restrict__ dh_out, const float* __restrict
     }
     if (t == 0) break;
     grid_barrier(counter, (unsigned)(T - t) * gridDim.x);
+    asm volatile("" ::: "memory");
     // ---- dh_{t-1}[s, own 4 cols] = m_t[s] * sum_r dgates_t[s, r] * W_hh[r, col]
     for (int s0 = 0; s0 < n; s0 += 32) {
       float acc[32];
