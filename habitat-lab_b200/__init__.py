@@ -20,6 +20,9 @@ _LAZY = {
     "PPOTrainer": ("rl.ppo_trainer", "PPOTrainer"),
     "SingleAgentAccessMgr": ("rl.single_agent_access_mgr", "SingleAgentAccessMgr"),
     "ddp_utils": ("rl.ddp_utils", None),
+    "batch_obs": ("utils.common", "batch_obs"),
+    "build_rnn_state_encoder": ("rl.models.rnn_state_encoder", "build_rnn_state_encoder"),
+    "RNNStateEncoder": ("rl.models.rnn_state_encoder", "RNNStateEncoder"),
     "TensorDict": ("common.tensor_dict", "TensorDict"),
     "baseline_registry": ("common.baseline_registry", "baseline_registry"),
     "spaces": ("common.spaces", None),

@@ -231,3 +231,20 @@ def test_baseline_cnn_policy_vs_reference(hb):
     for k in ("value_loss", "action_loss", "dist_entropy"):
         assert m[k] == pytest.approx(ref[k], rel=5e-3, abs=5e-4), k
     assert m["grad_norm"] == pytest.approx(ref["grad_norm"], rel=3e-2)
+
+
+def test_rnn_state_encoder_vs_reference_packed_sequences(hb):
+    """Stand-alone RNNStateEncoder (masked recurrence kernels) vs the outputs the reference's PackedSequence path
+    recorded in rnn_lstm.pt -- the reference's own criterion, test/test_rnn_state_encoder.py:94."""
+    from habitat_lab_b200.rl.models.rnn_state_encoder import build_rnn_state_encoder
+
+    G = load_golden("rnn_lstm")
+    enc = build_rnn_state_encoder(32, 32, rnn_type="LSTM", num_layers=2)
+    assert set(enc.state_dict().keys()) == set(G["state_dict"].keys())
+    enc.load_state_dict(G["state_dict"])
+    enc.to(DEV)
+    out, hid = enc(G["x"].to(DEV), G["hidden"].to(DEV), G["masks"].to(DEV), None)
+    torch.cuda.synchronize()
+    assert (out.cpu() - G["out"]).norm().item() < 1e-3
+    assert (hid.cpu() - G["hidden_out"]).norm().item() < 1e-3
+    assert enc.num_recurrent_layers == 4

@@ -112,3 +112,37 @@ def test_trainer_percent_done_and_config_defaults():
     tr.num_updates_done = 4
     assert tr.percent_done() == 0.4 and not tr.is_done()
     assert tr.should_end_early(100) is False  # not distributed
+
+
+def test_rnn_state_encoder_factory_surface():
+    from habitat_lab_b200.rl.models.rnn_state_encoder import build_rnn_state_encoder
+
+    gru = build_rnn_state_encoder(514, 512, rnn_type="GRU", num_layers=1)
+    assert gru.num_recurrent_layers == 1 and "rnn.weight_hh_l0" in gru.state_dict()
+    lstm = build_rnn_state_encoder(576, 512, rnn_type="lstm", num_layers=2)
+    assert lstm.num_recurrent_layers == 4
+    assert float(lstm.rnn.bias_ih_l0.detach().abs().sum()) == 0.0  # zero biases, orthogonal weights (:288-293)
+    w = lstm.rnn.weight_hh_l1.detach()          # [2048, 512]: orthonormal columns
+    torch.testing.assert_close(w.t() @ w, torch.eye(512), rtol=1e-4, atol=1e-4)
+    with pytest.raises(RuntimeError):
+        build_rnn_state_encoder(8, 8, rnn_type="transformer")
+    with pytest.raises(hb.Hb200Error):   # CPU tensors: the product path has no CPU fallback
+        lstm(torch.zeros(4, 576), torch.zeros(2, 4, 512), torch.ones(4, 1, dtype=torch.bool))
+
+
+def test_batch_obs_stacks_per_env_observations():
+    from habitat_lab_b200.utils.common import ObservationBatchingCache, batch_obs
+
+    rng = np.random.default_rng(0)
+    obs = [{"rgb": rng.integers(0, 255, (8, 8, 3), dtype=np.uint8), "depth": rng.random((8, 8, 1)),
+            "pointgoal_with_gps_compass": np.array([1.0 + i, -0.5], dtype=np.float32),
+            "nested": {"gps": np.array([i, i], dtype=np.float32)}} for i in range(3)]
+    cache = ObservationBatchingCache()
+    b = batch_obs(obs, device="cpu", cache=cache)
+    assert b["rgb"].shape == (3, 8, 8, 3) and b["rgb"].dtype == torch.uint8
+    assert b["depth"].dtype == torch.float32            # float64 sensors are narrowed, uint8 kept (common.py:262-330)
+    assert torch.equal(b["rgb"][1], torch.from_numpy(obs[1]["rgb"]))
+    assert torch.equal(b["nested"]["gps"][2], torch.tensor([2.0, 2.0]))
+    b2 = batch_obs(obs, device="cpu", cache=cache)      # staging buffers are reused, results are independent copies
+    assert torch.equal(b2["pointgoal_with_gps_compass"], b["pointgoal_with_gps_compass"])
+    assert len(cache._pool) == 4
