@@ -180,6 +180,9 @@ def run_hb200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO") and not os.environ.get("HB200_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     lib = hb.load()
     T, N = CFG["T"], CFG["N"]

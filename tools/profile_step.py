@@ -42,6 +42,8 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record()
 ppo._update_from_batch(b1, 0, st, lm)
 e1.record()
+t_enq = (time.perf_counter() - t0) * 1e3
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print(f"minibatch of {T * n_envs // 2} frames: {e0.elapsed_time(e1):.2f} ms device, {(time.perf_counter() - t0) * 1e3:.2f} ms wall")
+print(f"minibatch of {T * n_envs // 2} frames: {e0.elapsed_time(e1):.2f} ms device, {(time.perf_counter() - t0) * 1e3:.2f} ms wall, "
+      f"{t_enq:.2f} ms host enqueue")
