@@ -315,6 +315,19 @@ def run_hb200(args):
         torch.distributed.destroy_process_group()
 
 
+def _ncu_traffic():
+    """DRAM bytes per launch of the most frequent conv kernel, from the committed `ncu --set full` capture of this
+    round (profiles/*_ncu_traffic.json; offline measurement, not taken during the bench run)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        t = json.load(f)
+    return {"kernel": t["kernel"], "dram_bytes_per_launch": t["traffic_bytes_per_launch"],
+            "algorithmic_bytes_per_launch": 2.0 * 2 * 4096 * 32 * 32 * 32, "source": t["source"]}
+
+
 def kernel_roofline(hb, ops, policy, st, dev, peaks):
     """Live CUDA-event timing of the dominant kernel family (the tcgen05 implicit-GEMM convolutions)
     on the real config-#2 minibatch buffers: algorithmic FLOPs of every conv launch of one
@@ -386,7 +399,7 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
     return {"kernel": "conv_halo_kernel / conv_igemm_kernel / conv_*wgrad_kernel (tcgen05, all 21 convs of one 4096-frame minibatch pass)",
             "bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16"], "peak_source": peaks["src"] + " (burst: kernels timed alone)",
-            "traffic": None,
+            "traffic": _ncu_traffic(),
             "speed_of_light": {"note": "per launch max(FLOPs / bf16 peak, (input + output bytes) / HBM peak): the 32- and "
                                        "64-channel layers are HBM-bound, not tensor-bound", "sol_ms": sol[0],
                                "measured_ms": sol[1], "frac": sol[0] / sol[1] if sol[1] else None},
