@@ -62,6 +62,10 @@ struct HaloCfg {
   static constexpr int HALO_BYTES = HH * RP;
   static constexpr int W_BYTES = KH * KW * C * N * 2;
   static constexpr int TMEM_COLS = (2 * N) < 32 ? 32 : (2 * N);
+  // Halo stages per CTA.  Two stages let one CTA overlap the next tile's loads with the current MMAs, but for
+  // C = N = 64 (72 KB of resident weights) that footprint (120 KB) leaves a single 128-thread CTA per SM -- ncu:
+  // 6 % occupancy, latency-bound.  One stage (97 KB) fits two CTAs per SM, which overlap each other instead.
+  static constexpr int NBUF = (W_BYTES + 2 * HALO_BYTES > 110 * 1024) ? 1 : 2;
 };
 
 // issue the zero-filling loads of one halo tile (all 128 threads participate)
@@ -127,25 +131,28 @@ __global__ void __launch_bounds__(128) conv_halo_kernel(const HaloArgs a) {
 
   const int py = tid >> 3, px = tid & 7;  // this thread's output pixel within the tile (epilogue)
 
+  constexpr int NBUF = Cfg::NBUF;
   for (int it = 0; it <= my_n; ++it) {
-    // (1) MMAs of tile it-1 are complete (frees halo stage (it+1)&1 and fills TMEM stage (it-1)&1)
-    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-    // (2) prefetch the halo of tile it+1
-    if (it + 1 < my_n) {
-      int b, oh0, ow0;
-      tile_coords(first + (it + 1) * stride, b, oh0, ow0);
-      load_halo<C, KH, KW, PAD, Cfg::HH>(a.x, s_halo0 + ((it + 1) & 1) * Cfg::HALO_BYTES, b, oh0, ow0, a.H, a.W);
+    if (NBUF == 2) {
+      // (1) MMAs of tile it-1 are complete (frees halo stage (it+1)&1 and fills TMEM stage (it-1)&1)
+      if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+      // (2) prefetch the halo of tile it+1
+      if (it + 1 < my_n) {
+        int b, oh0, ow0;
+        tile_coords(first + (it + 1) * stride, b, oh0, ow0);
+        load_halo<C, KH, KW, PAD, Cfg::HH>(a.x, s_halo0 + ((it + 1) & 1) * Cfg::HALO_BYTES, b, oh0, ow0, a.H, a.W);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
     // (3) halo of tile it has landed -> issue its MMAs
     if (it < my_n) {
-      cp_async_wait<1>();
+      if (NBUF == 2) cp_async_wait<1>(); else cp_async_wait<0>();
       fence_proxy_async_smem();
       fence_before_sync();  // orders the previous iteration's tcgen05.ld (TMEM stage reuse) too
       __syncthreads();
       if (tid == 0) {
         fence_after_sync();
-        const uint32_t sh = s_halo0 + (it & 1) * Cfg::HALO_BYTES;
+        const uint32_t sh = s_halo0 + (NBUF == 2 ? (it & 1) : 0) * Cfg::HALO_BYTES;
         const uint32_t tacc = tmem_base + (uint32_t)((it & 1) * N);
         uint32_t accum = 0;
 #pragma unroll
@@ -217,6 +224,17 @@ __global__ void __launch_bounds__(128) conv_halo_kernel(const HaloArgs a) {
           dst[v] = u;
         }
       }
+    }
+    if (NBUF == 1 && it < my_n) {
+      // single halo stage: the MMAs of tile it must have consumed it before the next tile's loads overwrite it
+      // (the other CTA on this SM covers the gap); this is also the completion the next epilogue needs
+      mbar_wait(&mma_bar[it & 1], (it >> 1) & 1);
+      if (it + 1 < my_n) {
+        int b, oh0, ow0;
+        tile_coords(first + (it + 1) * stride, b, oh0, ow0);
+        load_halo<C, KH, KW, PAD, Cfg::HH>(a.x, s_halo0, b, oh0, ow0, a.H, a.W);
+      }
+      cp_async_commit();
     }
   }
   fence_before_sync();
@@ -417,7 +435,7 @@ static int blocks_per_sm(const void* kern, size_t smem, int tmem_cols, int* cach
 template <int C, int N, int KH, int KW, int PAD, int MODE>
 static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   using Cfg = HaloCfg<C, N, KH, KW, PAD>;
-  const size_t smem = Cfg::W_BYTES + 2 * Cfg::HALO_BYTES + 256;
+  const size_t smem = Cfg::W_BYTES + Cfg::NBUF * Cfg::HALO_BYTES + 256;
   auto kern = conv_halo_kernel<C, N, KH, KW, PAD, MODE>;
   static int cache = 0;
   if (cache == 0) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
