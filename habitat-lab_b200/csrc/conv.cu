@@ -46,7 +46,7 @@ struct ConvArgs {
   const __nv_bfloat16* wimg;  // packed weight tile images
   __nv_bfloat16* out;
   const __nv_bfloat16* addend;
-  float* stats;
+  double* stats;  // [B,G,2] sum / sum of squares, accumulated in double: order-independent after rounding
   int B, SH, SW, SC;  // gathered tensor dims (H, W, C), C power of two
   int OH, OW, OC;     // output grid and channels
   int kh, kw, stride, pad;
@@ -287,12 +287,12 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
       }
       if (row_ok && (lane & (seg - 1)) == 0) {
         const int g0 = (n0 + col0) / cpg;
-        float* dst = a.stats + ((size_t)ob * a.gn_groups + g0) * 2;
+        double* dst = a.stats + ((size_t)ob * a.gn_groups + g0) * 2;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           if (i < ng) {
-            atomicAdd(dst + 2 * i, s2[i]);
-            atomicAdd(dst + 2 * i + 1, q2[i]);
+            atomicAdd(dst + 2 * i, (double)s2[i]);
+            atomicAdd(dst + 2 * i + 1, (double)q2[i]);
           }
         }
       }
@@ -689,7 +689,7 @@ extern "C" int hb200_set_umma_layout(int layout) {
 extern "C" int hb200_get_umma_layout(void) { return g_umma_layout; }
 
 extern "C" int hb200_conv_fwd(const hb200_bf16* x, const hb200_bf16* w_packed, hb200_bf16* y,
-                              float* gn_stats, int gn_groups, const hb200_conv_shape* s,
+                              double* gn_stats, int gn_groups, const hb200_conv_shape* s,
                               hb200_stream_t stream) {
   int rc = check_shape(s);
   if (rc) return rc;

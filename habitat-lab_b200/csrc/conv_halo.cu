@@ -49,7 +49,7 @@ struct HaloArgs {
   const __nv_bfloat16* wimg;   // [taps][C/8][N][8] weight image (K-major no-swizzle per tap)
   __nv_bfloat16* y;            // [B,H,W,N]
   const __nv_bfloat16* addend; // dgrad residual add, or nullptr
-  float* stats;                // [B,G,2] or nullptr
+  double* stats;               // [B,G,2] or nullptr (double accumulators: run-to-run identical)
   int B, H, W, gn_groups, ntiles;
 };
 
@@ -197,9 +197,9 @@ __global__ void __launch_bounds__(128) conv_halo_kernel(const HaloArgs a) {
           const float ts = warp_reduce16(s2, lane), tq = warp_reduce16(q2, lane);  // lane l: channel pair l >> 1
           if ((lane & 1) == 0) {
             const int ch = col0 + lane;  // first channel of the pair
-            float* dst = a.stats + ((size_t)b * a.gn_groups + ch / cpg) * 2;
-            atomicAdd(dst, ts);
-            atomicAdd(dst + 1, tq);
+            double* dst = a.stats + ((size_t)b * a.gn_groups + ch / cpg) * 2;
+            atomicAdd(dst, (double)ts);
+            atomicAdd(dst + 1, (double)tq);
           }
         }
         const size_t o = pix * N + col0;
@@ -501,7 +501,7 @@ extern "C" int hb200_unpack_stem_wgrad(const float* dw_acc, float* dw_oihw, int 
 /* x [B,H,W,C] -> y [B,H,W,N], stride-1 "same" conv, k = 3 (pad 1) or k = 4 (pad 2 top/left, 1 bottom/right:
  * the space-to-depth stem).  mode 0 forward (gn_stats optional), mode 1 dgrad (addend optional). */
 extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb200_bf16* y, const hb200_bf16* addend,
-                               float* gn_stats, int gn_groups, int batch, int h, int w, int c, int n, int k,
+                               double* gn_stats, int gn_groups, int batch, int h, int w, int c, int n, int k,
                                int mode, hb200_stream_t stream) {
   HB_CHECK_ARG(x && wimg && y, "conv_halo: null pointer");
   HB_CHECK_ARG(hb200_conv_halo_supported(c, n, k, h, w), "conv_halo: unsupported shape C=%d N=%d k=%d %dx%d", c, n, k, h, w);

@@ -199,7 +199,7 @@ __global__ void prep_finalize_kernel(const double* __restrict__ stats, float* __
 // GroupNorm helpers
 // ======================================================================================
 struct GnP {
-  const float* stats;  // [B,G,2] sum, sumsq
+  const double* stats;  // [B,G,2] sum, sumsq (double accumulators)
   const float* gamma;
   const float* beta;
   int C, G, lcpg;  // lcpg = log2(channels per group)
@@ -214,9 +214,10 @@ __device__ __forceinline__ void gn_coeffs(const GnP& p, int b, int c0, float (&m
   for (int e = 0; e < 8; ++e) {
     const int g = (c0 + e) >> p.lcpg;
     if (g != prev) {
-      const float2 st = *reinterpret_cast<const float2*>(p.stats + ((size_t)b * p.G + g) * 2);
-      m = st.x * p.inv_m;
-      const float var = fmaxf(st.y * p.inv_m - m * m, 0.f);
+      const double2 st = *reinterpret_cast<const double2*>(p.stats + ((size_t)b * p.G + g) * 2);
+      const double md = st.x * (double)p.inv_m;
+      m = (float)md;
+      const float var = fmaxf((float)(st.y * (double)p.inv_m - md * md), 0.f);
       r = rsqrtf(var + p.eps);
       prev = g;
     }
@@ -626,9 +627,10 @@ __device__ __forceinline__ void gn_bwd_cluster_sums(cg::cluster_group& cluster, 
       ta += pr[c];
       tx += pr[C + c];
     }
-    const float2 st = *reinterpret_cast<const float2*>(p.stats + ((size_t)b * G + (c >> p.lcpg)) * 2);
-    const float m = st.x * p.inv_m;
-    const float r = rsqrtf(fmaxf(st.y * p.inv_m - m * m, 0.f) + p.eps);
+    const double2 st = *reinterpret_cast<const double2*>(p.stats + ((size_t)b * G + (c >> p.lcpg)) * 2);
+    const double md = st.x * (double)p.inv_m;
+    const float m = (float)md;
+    const float r = rsqrtf(fmaxf((float)(st.y * (double)p.inv_m - md * md), 0.f) + p.eps);
     const float tb = r * (tx - m * ta);  // sum gz * xhat
     tot[c] = ta;
     tot[C + c] = tb;
@@ -1262,7 +1264,7 @@ static int ilog2i(int v) {
   while ((1 << l) < v) ++l;
   return l;
 }
-static int make_gn(GnP& p, const float* stats, const float* gamma, const float* beta, int C, int G, int hw,
+static int make_gn(GnP& p, const double* stats, const float* gamma, const float* beta, int C, int G, int hw,
                    float eps) {
   HB_CHECK_ARG(stats && gamma && beta, "gn: null pointer");
   HB_CHECK_ARG(C % 8 == 0 && G > 0 && C % G == 0, "gn: C=%d G=%d unsupported", C, G);
@@ -1345,7 +1347,7 @@ extern "C" int hb200_prep_apply(const uint8_t* rgb, const float* depth, const in
   return HB200_OK;
 }
 
-extern "C" int hb200_gn_apply(const hb200_bf16* y, const float* stats, const float* gamma,
+extern "C" int hb200_gn_apply(const hb200_bf16* y, const double* stats, const float* gamma,
                               const float* beta, void* out, int out_f32, int batch, int hw,
                               int channels, int groups, float eps, int relu, hb200_stream_t stream) {
   GnP p;
@@ -1366,8 +1368,8 @@ extern "C" int hb200_gn_apply(const hb200_bf16* y, const float* stats, const flo
   return HB200_OK;
 }
 
-extern "C" int hb200_gn_residual_relu(const hb200_bf16* y, const float* stats, const float* gamma,
-                                      const float* beta, const hb200_bf16* res, const float* res_stats,
+extern "C" int hb200_gn_residual_relu(const hb200_bf16* y, const double* stats, const float* gamma,
+                                      const float* beta, const hb200_bf16* res, const double* res_stats,
                                       const float* res_gamma, const float* res_beta, hb200_bf16* out,
                                       int batch, int hw, int channels, int groups, float eps,
                                       hb200_stream_t stream) {
@@ -1390,7 +1392,7 @@ extern "C" int hb200_gn_residual_relu(const hb200_bf16* y, const float* stats, c
   return HB200_OK;
 }
 
-extern "C" int hb200_gn_relu_maxpool(const hb200_bf16* y, const float* stats, const float* gamma,
+extern "C" int hb200_gn_relu_maxpool(const hb200_bf16* y, const double* stats, const float* gamma,
                                      const float* beta, hb200_bf16* out, uint8_t* argmax, int batch,
                                      int h, int w, int channels, int groups, float eps,
                                      hb200_stream_t stream) {
@@ -1435,7 +1437,7 @@ extern "C" int hb200_maxpool_bwd(const hb200_bf16* dout, const uint8_t* argmax, 
 }
 
 extern "C" int hb200_gn_bwd_reduce(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
-                                   const float* stats, const float* gamma, const float* beta,
+                                   const double* stats, const float* gamma, const float* beta,
                                    float* sums, float* dgamma, float* dbeta, int batch, int hw,
                                    int channels, int groups, float eps, int mask_mode,
                                    hb200_stream_t stream) {
@@ -1460,7 +1462,7 @@ extern "C" int hb200_gn_bwd_reduce(const hb200_bf16* g, const hb200_bf16* act, c
 }
 
 extern "C" int hb200_gn_bwd_apply(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
-                                  const float* stats, const float* gamma, const float* beta,
+                                  const double* stats, const float* gamma, const float* beta,
                                   const float* sums, hb200_bf16* dy, hb200_bf16* gz_out, int batch,
                                   int hw, int channels, int groups, float eps, int mask_mode,
                                   hb200_stream_t stream) {
@@ -1572,7 +1574,7 @@ extern "C" int hb200_heads_fwd(const float* features, const float* w_act, const 
   return HB200_OK;
 }
 
-extern "C" int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y, const float* stats,
+extern "C" int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y, const double* stats,
                             const float* gamma, const float* beta, float* dgamma, float* dbeta, hb200_bf16* dy,
                             hb200_bf16* gz_out, int batch, int hw, int channels, int groups, float eps,
                             int mask_mode, hb200_stream_t stream) {
@@ -1653,7 +1655,7 @@ extern "C" int hb200_gn_relu_maxpool_bwd_supported(int h, int w, int channels, i
 }
 
 extern "C" int hb200_gn_relu_maxpool_bwd(const hb200_bf16* dpool, const uint8_t* argmax, const hb200_bf16* y,
-                                         const float* stats, const float* gamma, const float* beta, float* dgamma,
+                                         const double* stats, const float* gamma, const float* beta, float* dgamma,
                                          float* dbeta, hb200_bf16* dy, int batch, int h, int w, int channels,
                                          int groups, float eps, hb200_stream_t stream) {
   GnP p;

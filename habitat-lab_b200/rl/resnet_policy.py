@@ -358,7 +358,7 @@ class EncoderEngine:
         ws = {"x0": e(B, self.hp // 2, self.wp_ // 2, 16) if self.stem.stem_s2d else e(B, self.hp, self.wp_, 8)}
         for i, c in enumerate(self.convs):
             ws[f"y{i}"] = e(B, *c.out_hw, c.co)
-            ws[f"st{i}"] = torch.empty(B, c.groups, 2, device=dev)
+            ws[f"st{i}"] = torch.empty(B, c.groups, 2, device=dev, dtype=torch.float64)  # f64: reproducible atomics
             if train:
                 ws[f"sums{i}"] = torch.empty(B, c.groups, 2, device=dev)
         ws["x1"] = e(B, *self.pool_hw, self.stem.co)

@@ -160,7 +160,8 @@ int hb200_bf16_hwc_to_f32_chw(const hb200_bf16* x, float* out, int batch, int hw
  *
  * x bf16 NHWC [B,Hi,Wi,Ci]; w_packed bf16 [Co][kh*kw*Ci padded to 64] (hb200_pack_conv_weight);
  * y bf16 NHWC [B,Ho,Wo,Co].  Ci % 8 == 0, Co % 16 == 0, Co <= 256 or Co % 256 == 0.
- * gn_stats f32 [B, gn_groups, 2] or NULL: per-(frame,group) sum / sum-of-squares of the fp32
+ * gn_stats f64 [B, gn_groups, 2] or NULL (double accumulators: the atomics become order-independent
+ * after rounding, so the forward pass is run-to-run reproducible): per-(frame,group) sum / sum-of-squares of the fp32
  * accumulators are atomically added (GroupNorm statistics fused into the conv epilogue).
  * addend (dgrad only) bf16 [B,Hi,Wi,Ci] or NULL: dx = conv_dgrad + addend (residual grad).
  */
@@ -169,7 +170,7 @@ typedef struct {
 } hb200_conv_shape;
 
 int hb200_conv_fwd(const hb200_bf16* x, const hb200_bf16* w_packed, hb200_bf16* y,
-                   float* gn_stats, int gn_groups, const hb200_conv_shape* s,
+                   double* gn_stats, int gn_groups, const hb200_conv_shape* s,
                    hb200_stream_t stream);
 /* forward with per-channel bias (+ReLU) fused in the epilogue: SimpleCNN's biased convs
  * (HB/rl/models/simple_cnn.py:68-93) */
@@ -208,7 +209,7 @@ int hb200_conv_halo_supported(int c, int n, int k, int h, int w);
 int hb200_pack_halo_weight(const float* w_oihw, hb200_bf16* img, int co, int ci_real, int c, int n, int k,
                            int mode, hb200_stream_t stream);
 int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb200_bf16* y, const hb200_bf16* addend,
-                    float* gn_stats, int gn_groups, int batch, int h, int w, int c, int n, int k, int mode,
+                    double* gn_stats, int gn_groups, int batch, int h, int w, int c, int n, int k, int mode,
                     hb200_stream_t stream);
 /* dw_acc f32 [(r*k+s)*C + ci][N] accumulated with atomics (caller zeroes), like hb200_conv_wgrad */
 int hb200_conv_halo_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc, int batch, int h, int w,
@@ -226,22 +227,22 @@ int hb200_umma_gemm_probe(const hb200_bf16* a, const hb200_bf16* b, float* d, in
 /* ---- GroupNorm / ReLU / pooling / residual elementwise passes (bf16 NHWC) ---------------
  * replace nn.GroupNorm, nn.ReLU, nn.MaxPool2d and the residual add of BasicBlock
  * (HB/rl/ddppo/policy/resnet.py:37-69, 207-219, 272-281).
- * stats f32 [B,G,2] = (sum, sumsq) over the (C/G)*H*W elements of each group (conv epilogue).
+ * stats f64 [B,G,2] = (sum, sumsq) over the (C/G)*H*W elements of each group (conv epilogue).
  */
 /* out = act(gamma * (y - mu) * rstd + beta);  relu: 0/1;  out_f32: 0 -> bf16 NHWC, 1 -> f32 NHWC,
  * 2 -> f32 [B, C*hw] flattened in (c,h,w) order (what nn.Flatten of the NCHW map feeds visual_fc) */
-int hb200_gn_apply(const hb200_bf16* y, const float* stats, const float* gamma, const float* beta,
+int hb200_gn_apply(const hb200_bf16* y, const double* stats, const float* gamma, const float* beta,
                    void* out, int out_f32, int batch, int hw, int channels, int groups, float eps,
                    int relu, hb200_stream_t stream);
 /* out = relu(GN(y) + res)  with res either an activation tensor (res_stats NULL) or a second
  * pre-norm tensor normalised with (res_stats, res_gamma, res_beta) (downsample branch). */
-int hb200_gn_residual_relu(const hb200_bf16* y, const float* stats, const float* gamma,
-                           const float* beta, const hb200_bf16* res, const float* res_stats,
+int hb200_gn_residual_relu(const hb200_bf16* y, const double* stats, const float* gamma,
+                           const float* beta, const hb200_bf16* res, const double* res_stats,
                            const float* res_gamma, const float* res_beta, hb200_bf16* out,
                            int batch, int hw, int channels, int groups, float eps,
                            hb200_stream_t stream);
 /* out[B,H/2,W/2,C] = maxpool3x3s2p1(relu(GN(y[B,H,W,C]))); argmax u8 (0..8) saved for bwd */
-int hb200_gn_relu_maxpool(const hb200_bf16* y, const float* stats, const float* gamma,
+int hb200_gn_relu_maxpool(const hb200_bf16* y, const double* stats, const float* gamma,
                           const float* beta, hb200_bf16* out, uint8_t* argmax, int batch, int h,
                           int w, int channels, int groups, float eps, hb200_stream_t stream);
 /* dz[B,H,W,C] (grad wrt the GN output BEFORE relu masking is applied by the GN backward)
@@ -255,13 +256,13 @@ int hb200_maxpool_bwd(const hb200_bf16* dout, const uint8_t* argmax, hb200_bf16*
  * (atomics, caller zeroes); pass 2 writes dy (grad wrt the conv output y) and, if gz_out != NULL,
  * the masked upstream grad gz (the residual-branch gradient). */
 int hb200_gn_bwd_reduce(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
-                        const float* stats, const float* gamma, const float* beta, float* sums,
+                        const double* stats, const float* gamma, const float* beta, float* sums,
                         float* dgamma, float* dbeta, int batch, int hw, int channels, int groups,
                         float eps, int mask_mode, hb200_stream_t stream);
 /* both passes in one launch: a thread-block cluster owns a frame, stages it in shared memory (cp.async), reduces
  * through distributed shared memory and writes dy / gz_out from the staged copy, so every operand crosses HBM once.
  * dgamma/dbeta are accumulated (caller zeroes). */
-int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y, const float* stats,
+int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y, const double* stats,
                  const float* gamma, const float* beta, float* dgamma, float* dbeta, hb200_bf16* dy,
                  hb200_bf16* gz_out, int batch, int hw, int channels, int groups, float eps, int mask_mode,
                  hb200_stream_t stream);
@@ -272,11 +273,11 @@ int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y
  * _supported() tells whether a (h, w, channels) shape can be tiled (else: hb200_maxpool_bwd + hb200_gn_bwd). */
 int hb200_gn_relu_maxpool_bwd_supported(int h, int w, int channels, int groups);
 int hb200_gn_relu_maxpool_bwd(const hb200_bf16* dpool, const uint8_t* argmax, const hb200_bf16* y,
-                              const float* stats, const float* gamma, const float* beta, float* dgamma,
+                              const double* stats, const float* gamma, const float* beta, float* dgamma,
                               float* dbeta, hb200_bf16* dy, int batch, int h, int w, int channels, int groups,
                               float eps, hb200_stream_t stream);
 int hb200_gn_bwd_apply(const hb200_bf16* g, const hb200_bf16* act, const hb200_bf16* y,
-                       const float* stats, const float* gamma, const float* beta,
+                       const double* stats, const float* gamma, const float* beta,
                        const float* sums, hb200_bf16* dy, hb200_bf16* gz_out, int batch, int hw,
                        int channels, int groups, float eps, int mask_mode, hb200_stream_t stream);
 

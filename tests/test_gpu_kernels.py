@@ -245,14 +245,14 @@ def test_conv_fwd_dgrad_wgrad(hb, case):
     wp, wt = ops.pack_conv_weight(w, ci, want_t=ci >= 32)
     y = torch.empty(B, s.ho, s.wo, co, device=DEV, dtype=torch.bfloat16)
     groups = 16 if co % 16 == 0 and co // 16 >= 2 else 1
-    stats = torch.zeros(B, groups, 2, device=DEV)
+    stats = torch.zeros(B, groups, 2, device=DEV, dtype=torch.float64)
     ops.conv_fwd(x_nhwc, wp, y, s, stats, groups)
     torch.cuda.synchronize()
     torch.testing.assert_close(nchw(y.float()), y_ref, rtol=1e-2, atol=1e-2)
     # fused GroupNorm statistics: sum / sum of squares per (frame, group) of the fp32 accumulators
     yg = y_ref.view(B, groups, -1)
-    torch.testing.assert_close(stats[..., 0], yg.sum(-1), rtol=1e-3, atol=2e-2)
-    torch.testing.assert_close(stats[..., 1], (yg * yg).sum(-1), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(stats[..., 0].float(), yg.sum(-1), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(stats[..., 1].float(), (yg * yg).sum(-1), rtol=1e-3, atol=2e-2)
 
     dy = torch.randn_like(y_ref)
     dyb = bf(dy).float()
@@ -300,13 +300,13 @@ def test_conv_halo_3x3(hb, B, H, W, C, N):
     ops.pack_halo_weight(w, wht, N, C, 3, 1)
     y = torch.empty(B, H, W, N, device=DEV, dtype=torch.bfloat16)
     G = 16
-    stats = torch.zeros(B, G, 2, device=DEV)
+    stats = torch.zeros(B, G, 2, device=DEV, dtype=torch.float64)
     ops.conv_halo(x_nhwc, wh, y, B, H, W, C, N, 3, 0, gn_stats=stats, gn_groups=G)
     torch.cuda.synchronize()
     torch.testing.assert_close(nchw(y.float()), y_ref, rtol=1e-2, atol=1e-2)
     yg = y_ref.view(B, G, -1)
-    torch.testing.assert_close(stats[..., 0], yg.sum(-1), rtol=1e-3, atol=2e-2)
-    torch.testing.assert_close(stats[..., 1], (yg * yg).sum(-1), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(stats[..., 0].float(), yg.sum(-1), rtol=1e-3, atol=2e-2)
+    torch.testing.assert_close(stats[..., 1].float(), (yg * yg).sum(-1), rtol=1e-3, atol=2e-2)
     dy = torch.randn_like(y_ref)
     dyb, dy_nhwc = bf(dy).float(), bf(nhwc(dy))
     dx_ref = torch.nn.grad.conv2d_input(xb.shape, wb, dyb, padding=1)
@@ -341,7 +341,7 @@ def test_conv_halo_stem_s2d(hb, B, Hp, Wp):
     wh = torch.empty(16 * 16 * 32, device=DEV, dtype=torch.bfloat16)
     ops.pack_halo_weight(w, wh, 16, 32, 4, 2)
     y = torch.empty(B, Ho, Wo, 32, device=DEV, dtype=torch.bfloat16)
-    stats = torch.zeros(B, 16, 2, device=DEV)
+    stats = torch.zeros(B, 16, 2, device=DEV, dtype=torch.float64)
     ops.conv_halo(xs, wh, y, B, Ho, Wo, 16, 32, 4, 0, gn_stats=stats, gn_groups=16)
     torch.cuda.synchronize()
     torch.testing.assert_close(nchw(y.float()), y_ref, rtol=1e-2, atol=1e-2)
@@ -415,7 +415,8 @@ def test_prep(hb, has_rgb, has_depth):
 def _stats_of(y_nchw, groups):
     B = y_nchw.shape[0]
     yg = y_nchw.reshape(B, groups, -1)
-    return torch.stack([yg.sum(-1), (yg * yg).sum(-1)], -1).contiguous()
+    yg = yg.double()
+    return torch.stack([yg.sum(-1), (yg * yg).sum(-1)], -1).contiguous()   # f64 [B,G,2] like the conv epilogue
 
 
 @pytest.mark.parametrize("B,C,H,W,G", [(3, 32, 16, 16, 16), (2, 64, 8, 8, 16), (2, 128, 4, 4, 1), (5, 256, 4, 4, 16),

@@ -251,3 +251,51 @@ def test_rnn_state_encoder_vs_reference_packed_sequences(hb):
     assert (out.cpu() - G["out"]).norm().item() < 1e-3
     assert (hid.cpu() - G["hidden_out"]).norm().item() < 1e-3
     assert enc.num_recurrent_layers == 4
+
+
+def test_full_size_minibatch_is_additive_over_envs(hb):
+    """Size-independent property at BASELINE config #2's full minibatch (T = 128 x 32 envs = 4096 frames, 256x256
+    RGB-D, LSTM-512x2): with the input-normalisation statistics frozen (eval mode) every term of the loss is a mean over
+    frames and environments never interact, so losses and ALL 8.48 M gradients of the full minibatch must equal the
+    average of the two 16-env half minibatches.  Exercises every kernel of the path (halo / gather convs, split-K,
+    cluster GroupNorm backward, LSTM v2, fused loss) at the sizes the bench runs, without an oracle."""
+    from habitat_lab_b200.synthetic import fill_rollout_, pointnav_spaces
+
+    T, N = 128, 32
+    torch.manual_seed(3)
+    obs_space, act_space = pointnav_spaces(256, 256)
+    pol = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=512, num_recurrent_layers=2, rnn_type="LSTM",
+                                  normalize_visual_inputs=True).to(DEV)
+    pol.eval()
+    ppo = hb.PPO(pol, clip_param=0.2, ppo_epoch=1, num_mini_batch=1, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4,
+                 eps=1e-5, max_grad_norm=0.2, use_clipped_value_loss=True, use_normalized_advantage=False)
+    st = hb.RolloutStorage(T, N, obs_space, act_space, pol)
+    st.to(DEV)
+    nv = fill_rollout_(st, seed=9)
+    st.compute_returns(nv, True, 0.99, 0.95)
+    adv = ppo.get_advantages(st)
+
+    def run(num_mb):
+        torch.manual_seed(77)   # same randperm(N): the halves partition the envs of the full minibatch
+        outs = []
+        for batch in st.data_generator(adv, num_mb):
+            m = pol.loss_and_backward(batch, 0.2, 0.5, 0.01, True)
+            torch.cuda.synchronize()
+            outs.append((m[:3].double().cpu(), pol._flat["grads"].double().clone()))
+        return outs
+
+    (m_full, g_full), = run(1)
+    (m_again, g_again), = run(1)
+    rerun = (g_again - g_full).norm().item() / g_full.norm().item()
+    assert rerun < 1e-4, f"run-to-run gradient difference {rerun} (only fp32 atomic ordering may differ)"
+    (m_a, g_a), (m_b, g_b) = run(2)
+    assert torch.isfinite(g_full).all() and g_full.abs().max().item() > 0
+    torch.testing.assert_close((m_a + m_b) / 2, m_full, rtol=2e-4, atol=1e-6)
+    g_half = (g_a + g_b) / 2
+    rel = (g_half - g_full).norm().item() / g_full.norm().item()
+    worst = []
+    for (name, p_), off in zip(pol.named_parameters(), pol._flat["offsets"]):
+        a_, b_ = g_half[off: off + p_.numel()], g_full[off: off + p_.numel()]
+        worst.append(((a_ - b_).norm().item() / (b_.norm().item() + 1e-30), name))
+    worst.sort(reverse=True)
+    assert rel < 2e-3, (rel, worst[:8], worst[-3:])

@@ -36,7 +36,7 @@ def main():
         g = torch.randn(B, hw, C, device=DEV).to(BF)
         act = torch.randn(B, hw, C, device=DEV).to(BF)
         yf = y.float().view(B, hw, G, C // G)
-        stats = torch.stack([yf.sum((1, 3)), (yf * yf).sum((1, 3))], dim=-1).contiguous()
+        stats = torch.stack([yf.sum((1, 3)), (yf * yf).sum((1, 3))], dim=-1).double().contiguous()
         del yf
         gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
         dga, dbe = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
