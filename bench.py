@@ -289,6 +289,33 @@ def run_hb200(args):
     ms_e2e, _ = timed(lambda: e2e_run(e2e_steps), 1)
     e2e_value = world * T * N * e2e_steps / (ms_e2e * 1e-3)
 
+    # ---- informational: the actor half of the loop ("next"): T sequential act() calls at batch N on the
+    # same synthetic observations, so that learner-only and learner+actor frames/s can be read side by side.
+    actor = None
+    if rank == 0 and world == 1:
+        try:
+            with torch.no_grad():
+                ob = st.buffers["observations"]
+                hid = st.buffers["recurrent_hidden_states"][0].clone()
+
+                def rollout():
+                    h = hid
+                    for t in range(T):
+                        out = policy.act({k: v[t] for k, v in ob.items()}, h, st.buffers["prev_actions"][t],
+                                         st.buffers["masks"][t])
+                        h = out.rnn_hidden_states
+                    return h
+
+                rollout()
+                ms_act, _ = timed(rollout, 2)
+                ms_act /= 2
+            actor = {"ms_per_rollout": ms_act, "steps": T, "batch": N,
+                     "frames_per_s_learner_plus_actor": T * N / ((ms / args.steps + ms_act) * 1e-3),
+                     "note": "act() re-packs the weight images every call and is launch-bound at batch 64; not optimised "
+                             "this round (SURVEY 8f)"}
+        except Exception as e:  # informational only: never fail the bench line on it
+            actor = {"error": repr(e)[:200]}
+
     line = None
     if rank == 0:
         peaks = _peaks()
@@ -306,7 +333,7 @@ def run_hb200(args):
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 14 * 4, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                         "h2d": "pinned host -> device on a copy stream, double-buffered across steps; first copy exposed"},
-                "roofline": roof, "hbm_kernel_rooflines": hbm_roofs, "cpu_baseline": cpu,
+                "roofline": roof, "hbm_kernel_rooflines": hbm_roofs, "cpu_baseline": cpu, "actor": actor,
                 "conv_tensor_frac_of_step": (world * T * N * CFG["ppo_epoch"] * CONV_TRAIN_GFLOP * 1e-3 * args.steps)
                 / (ms * 1e-3) / (peaks["bf16_sustained"] * world),
                 "learner_metrics": {k: round(float(v), 6) for k, v in metrics.items()}}
