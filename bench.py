@@ -311,8 +311,8 @@ def run_hb200(args):
                 ms_act /= 2
             actor = {"ms_per_rollout": ms_act, "steps": T, "batch": N,
                      "frames_per_s_learner_plus_actor": T * N / ((ms / args.steps + ms_act) * 1e-3),
-                     "note": "act() re-packs the weight images every call and is launch-bound at batch 64; not optimised "
-                             "this round (SURVEY 8f)"}
+                     "note": "act() at batch 64 is launch-bound (~100 small kernels per step; weight images are cached across "
+                             "calls); CUDA-graph capture of the actor step is the next row (SURVEY 8f)"}
         except Exception as e:  # informational only: never fail the bench line on it
             actor = {"error": repr(e)[:200]}
 

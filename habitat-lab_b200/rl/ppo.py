@@ -75,6 +75,7 @@ class FusedAdam(torch.optim.Optimizer):
                       grad_scale, self._step, self._gn, self._ws)
         for st in self.state.values():
             st["step"].fill_(float(self._step))
+        self._policy.mark_weights_changed()   # the kernel wrote the parameters behind torch's version counter
         return self._gn
 
 
@@ -231,6 +232,7 @@ class DDPPO(PPO):
         dist.broadcast(flat["params"], src=0)
         for b in ac.buffers():
             dist.broadcast(b, src=0)
+        ac.mark_weights_changed()
 
     def _compute_var_mean(self, adv, stats):
         """distributed_var_mean (ddppo.py:59-84): mean of the rank means, mean of the rank BIASED

@@ -343,6 +343,7 @@ class EncoderEngine:
                     c.halo = ops.conv_halo_supported(c.ci, c.co, 3, c.in_hw[0], c.in_hw[1])
         self._ws = {}
         self._dev = None
+        self._packed_key = None
         self.side = SideStream()
 
     # ---- buffers -----------------------------------------------------------------------------
@@ -350,15 +351,20 @@ class EncoderEngine:
         if self._dev != dev:
             for c in self.convs:
                 c.alloc_weights(dev, need_dgrad=c is not self.stem)
-            self._dev, self._ws = dev, {}
+            self._dev, self._ws, self._packed_key = dev, {}, None
         key = (B, train)
         if key in self._ws:
             return self._ws[key]
         e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
         ws = {"x0": e(B, self.hp // 2, self.wp_ // 2, 16) if self.stem.stem_s2d else e(B, self.hp, self.wp_, 8)}
+        # GroupNorm statistics of all convs live in one f64 arena (f64: reproducible atomics) zeroed by ONE memset
+        tot = sum(B * c.groups * 2 for c in self.convs)
+        ws["st_all"] = torch.empty(tot, device=dev, dtype=torch.float64)
+        off = 0
         for i, c in enumerate(self.convs):
             ws[f"y{i}"] = e(B, *c.out_hw, c.co)
-            ws[f"st{i}"] = torch.empty(B, c.groups, 2, device=dev, dtype=torch.float64)  # f64: reproducible atomics
+            ws[f"st{i}"] = ws["st_all"][off: off + B * c.groups * 2].view(B, c.groups, 2)
+            off += B * c.groups * 2
             if train:
                 ws[f"sums{i}"] = torch.empty(B, c.groups, 2, device=dev)
         ws["x1"] = e(B, *self.pool_hw, self.stem.co)
@@ -392,17 +398,21 @@ class EncoderEngine:
             ops.conv_dgrad(dy, c.wt, dx, c.shape(B), addend=addend)
 
     # ---- forward -----------------------------------------------------------------------------
-    def forward(self, x0_writer, B, dev, train):
+    def forward(self, x0_writer, B, dev, train, wkey=None):
         """x0_writer(x0) fills the pooled/normalised input.  Returns feat f32 [B, C*h*w] in the
-        reference's (c,h,w) flatten order."""
+        reference's (c,h,w) flatten order.  `wkey` identifies the weight values: inference calls (act / get_value
+        during a rollout) with an unchanged key reuse the packed bf16 weight images instead of re-packing 41 tensors
+        per step; training forwards always re-pack."""
         ws = self._ensure(B, dev, train)
-        self.pack_weights()
+        if train or wkey is None or wkey != self._packed_key:
+            self.pack_weights()
+            self._packed_key = wkey
         x0_writer(ws["x0"])
         idx = {id(c): i for i, c in enumerate(self.convs)}
+        ws["st_all"].zero_()
 
         def conv(c, x):
             i = idx[id(c)]
-            ws[f"st{i}"].zero_()
             if c.stem_s2d:
                 ops.conv_halo(x, c.wh, ws[f"y{i}"], B, c.out_hw[0], c.out_hw[1], 16, c.co, 4, 0, gn_stats=ws[f"st{i}"],
                               gn_groups=c.groups)
@@ -555,6 +565,7 @@ class NativeNetPolicy(nn.Module):
         self.aux_loss_modules = nn.ModuleDict()
         self._flat = None
         self._buf = {}
+        self._wver = 0   # bumped whenever parameter VALUES change through a path torch's tensor version cannot see
         self._side = SideStream()
         self.world_size = 1  # set by the distributed updater
         self.dist_group = None
@@ -627,7 +638,25 @@ class NativeNetPolicy(nn.Module):
             p.data = flat_p[off:off + k].view(p.shape)
             p.grad = flat_g[off:off + k].view(p.shape)
         self._flat = dict(params=flat_p, grads=flat_g, offsets=offs, n=o, n_real=n, plist=params)
+        self.mark_weights_changed()
         return self._flat
+
+    def mark_weights_changed(self) -> None:
+        """Called by FusedAdam.step / load_state_dict / the DD-PPO broadcast: invalidates cached weight images."""
+        self._wver += 1
+
+    def weights_key(self):
+        """(explicit counter, storage, torch version counters): in-place torch ops on a parameter (nn.init, copy_,
+        optimizers) bump p._version; writes through p.data or raw pointers must call mark_weights_changed()."""
+        f = self._flat
+        if f is None:
+            return None
+        return (self._wver, f["params"].data_ptr(), f["params"]._version, sum(p._version for p in f["plist"]))
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self.mark_weights_changed()
+        return out
 
     def _tmp(self, name, shape, dev, dtype=torch.float32):
         key = (name, tuple(shape), dtype)
@@ -876,7 +905,7 @@ class PointNavResNetPolicy(NativeNetPolicy):
         H = self.net._hidden_size
         eng = self._engine_()
         write_x0 = self._visual_prep(obs, rows, B, dev, update_stats=train and self.training)
-        feat = eng.forward(write_x0, B, dev, train)
+        feat = eng.forward(write_x0, B, dev, train, wkey=self.weights_key())
         # rnn input = [visual_fc | goal embedding | prev-action embedding]
         fc = self.net.visual_fc[1]
         D = H + 64
