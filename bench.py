@@ -289,33 +289,6 @@ def run_hb200(args):
     ms_e2e, _ = timed(lambda: e2e_run(e2e_steps), 1)
     e2e_value = world * T * N * e2e_steps / (ms_e2e * 1e-3)
 
-    # ---- informational: the actor half of the loop ("next"): T sequential act() calls at batch N on the
-    # same synthetic observations, so that learner-only and learner+actor frames/s can be read side by side.
-    actor = None
-    if rank == 0 and world == 1:
-        try:
-            with torch.no_grad():
-                ob = st.buffers["observations"]
-                hid = st.buffers["recurrent_hidden_states"][0].clone()
-
-                def rollout():
-                    h = hid
-                    for t in range(T):
-                        out = policy.act({k: v[t] for k, v in ob.items()}, h, st.buffers["prev_actions"][t],
-                                         st.buffers["masks"][t])
-                        h = out.rnn_hidden_states
-                    return h
-
-                rollout()
-                ms_act, _ = timed(rollout, 2)
-                ms_act /= 2
-            actor = {"ms_per_rollout": ms_act, "steps": T, "batch": N,
-                     "frames_per_s_learner_plus_actor": T * N / ((ms / args.steps + ms_act) * 1e-3),
-                     "note": "act() at batch 64 is launch-bound (~100 small kernels per step; weight images are cached across "
-                             "calls); CUDA-graph capture of the actor step is the next row (SURVEY 8f)"}
-        except Exception as e:  # informational only: never fail the bench line on it
-            actor = {"error": repr(e)[:200]}
-
     line = None
     if rank == 0:
         peaks = _peaks()
@@ -326,6 +299,43 @@ def run_hb200(args):
         if world == 1 and not args.no_cpu_baseline:
             fps, sample = _cpu_learner_sample(cores, updates=16)   # ~15 s of host work
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+        # ---- informational: the actor half of the loop ("next"): T sequential act() calls at batch N
+        # on the same synthetic observations (eager and CUDA-graph replay), so that learner-only and learner+actor
+        # frames/s can be read side by side.  Measured last and fully guarded: it can never cost the bench line.
+        actor = None
+        if world == 1:
+            try:
+                ob = st.buffers["observations"]
+                hid0 = st.buffers["recurrent_hidden_states"][0].clone()
+
+                def rollout(step_fn):
+                    h = hid0
+                    for t in range(T):
+                        out = step_fn({k: v[t] for k, v in ob.items()}, h, st.buffers["prev_actions"][t],
+                                      st.buffers["masks"][t])
+                        h = out.rnn_hidden_states
+                    return h
+
+                with torch.no_grad():
+                    rollout(policy.act)
+                    ms_eager, _ = timed(lambda: rollout(policy.act), 2)
+                ms_eager /= 2
+                actor = {"ms_per_rollout_eager": ms_eager, "steps": T, "batch": N}
+                ms_best = ms_eager
+                try:
+                    ga = hb.GraphedActor(policy, {k: v[0] for k, v in ob.items()}, hid0, st.buffers["prev_actions"][0],
+                                         st.buffers["masks"][0])
+                    rollout(ga)
+                    ms_graph, _ = timed(lambda: rollout(ga), 2)
+                    actor["ms_per_rollout_cuda_graph"] = ms_graph / 2
+                    ms_best = min(ms_best, ms_graph / 2)
+                except Exception as e:
+                    actor["cuda_graph_error"] = repr(e)[:200]
+                actor["frames_per_s_learner_plus_actor"] = T * N / ((ms / args.steps + ms_best) * 1e-3)
+                actor["note"] = ("act() at batch 64 is launch-bound (~100 small kernels per step; weight images cached "
+                                 "across calls); GraphedActor replays the captured step")
+            except Exception as e:
+                actor = {"error": repr(e)[:200]}
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": _config(world),

@@ -20,6 +20,7 @@ _LAZY = {
     "PPOTrainer": ("rl.ppo_trainer", "PPOTrainer"),
     "SingleAgentAccessMgr": ("rl.single_agent_access_mgr", "SingleAgentAccessMgr"),
     "ddp_utils": ("rl.ddp_utils", None),
+    "GraphedActor": ("rl.graphed_actor", "GraphedActor"),
     "batch_obs": ("utils.common", "batch_obs"),
     "build_rnn_state_encoder": ("rl.models.rnn_state_encoder", "build_rnn_state_encoder"),
     "RNNStateEncoder": ("rl.models.rnn_state_encoder", "RNNStateEncoder"),

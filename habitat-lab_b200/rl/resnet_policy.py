@@ -874,6 +874,14 @@ class PointNavResNetPolicy(NativeNetPolicy):
             self._engine.side = self._side   # one side stream for the whole backward pass
         return self._engine
 
+    def refresh_inference_weights(self) -> None:
+        """Re-pack the bf16 weight images now (same buffers) and mark them current: used by GraphedActor, whose
+        captured act() step does not contain the packing kernels."""
+        self.flatten_parameters_()
+        eng = self._engine_()
+        eng.pack_weights()
+        eng._packed_key = self.weights_key()
+
     def _visual_prep(self, observations, rows, B, dev, update_stats):
         enc = self.net.visual_encoder
         H, W = enc.in_hw

@@ -299,3 +299,36 @@ def test_full_size_minibatch_is_additive_over_envs(hb):
         worst.append(((a_ - b_).norm().item() / (b_.norm().item() + 1e-30), name))
     worst.sort(reverse=True)
     assert rel < 2e-3, (rel, worst[:8], worst[-3:])
+
+
+def test_graphed_actor_replays_act(hb):
+    """CUDA-graph replay of the actor step must reproduce eager act() (deterministic mode: same logits -> same action),
+    also after the weights changed (the packed weight images are refreshed outside the graph)."""
+    from habitat_lab_b200.synthetic import fill_rollout_, pointnav_spaces
+
+    T, N = 4, 4
+    torch.manual_seed(5)
+    obs_space, act_space = pointnav_spaces(128, 128)
+    pol = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=512, num_recurrent_layers=2, rnn_type="LSTM",
+                                  normalize_visual_inputs=True).to(DEV)
+    st = hb.RolloutStorage(T, N, obs_space, act_space, pol)
+    st.to(DEV)
+    fill_rollout_(st, seed=2, p_done=0.2)
+    ob = st.buffers["observations"]
+    step = lambda t: ({k: v[t] for k, v in ob.items()}, st.buffers["recurrent_hidden_states"][t],  # noqa: E731
+                      st.buffers["prev_actions"][t], st.buffers["masks"][t])
+    ga = hb.GraphedActor(pol, *step(0), deterministic=True)
+    for t in (1, 2):
+        ref = pol.act(*step(t), deterministic=True)
+        got = ga(*step(t))
+        torch.cuda.synchronize()
+        assert torch.equal(got.actions, ref.actions)
+        torch.testing.assert_close(got.values, ref.values, rtol=0, atol=0)
+        torch.testing.assert_close(got.rnn_hidden_states, ref.rnn_hidden_states, rtol=0, atol=0)
+    with torch.no_grad():   # change the weights the way the optimizer does (behind torch's version counters)
+        pol._flat["params"].mul_(1.01)
+    pol.mark_weights_changed()
+    ref = pol.act(*step(3), deterministic=True)
+    got = ga(*step(3))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(got.values, ref.values, rtol=0, atol=0)
