@@ -153,7 +153,7 @@ def run_reference(args):
             "config": _config(args.gpus),
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def _config(n):
@@ -347,7 +347,7 @@ def run_hb200(args):
                 "conv_tensor_frac_of_step": (world * T * N * CFG["ppo_epoch"] * CONV_TRAIN_GFLOP * 1e-3 * args.steps)
                 / (ms * 1e-3) / (peaks["bf16_sustained"] * world),
                 "learner_metrics": {k: round(float(v), 6) for k, v in metrics.items()}}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -506,7 +506,26 @@ def hbm_kernel_rooflines(hb, ops, dev, peaks):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line) -> None:
+    """The one JSON line of the contract, written to the process's ORIGINAL stdout (see main)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout must carry exactly one JSON line, but libraries print there too (NCCL's "NCCL version ..." banner comes out
+    # on stdout whatever NCCL_DEBUG says): point fd 1 at stderr for the whole run and keep the real stdout for _emit.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
