@@ -28,6 +28,14 @@ CASES = {
     "small128": dict(T=8, N=4, H=128, W=128, rnn="LSTM", layers=2, epochs=2, mb=2, norm_adv=False, seed=11),
     "full256": dict(T=4, N=2, H=256, W=256, rnn="LSTM", layers=2, epochs=1, mb=1, norm_adv=True, seed=12),
 }
+NEXT_CASES = {
+    # BASELINE config #3: ObjectNav DD-PPO, ResNet50 RGB(-D) + semantic channel, GRU-512
+    "r50_objectnav": dict(T=4, N=2, H=128, W=128, backbone="resnet50", rnn="GRU", layers=1, n_actions=6, n_categories=21,
+                          imagegoal=False, seed=31),
+    # BASELINE config #4: ImageNav DD-PPO, ResNeXt50 dual encoder (observation + goal image), LSTM-512
+    "rx50_imagenav": dict(T=4, N=2, H=128, W=128, backbone="resneXt50", rnn="LSTM", layers=2, n_actions=4,
+                          n_categories=0, imagegoal=True, seed=41),
+}
 PPO_KW = dict(clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2,
               use_clipped_value_loss=True)
 
@@ -58,6 +66,71 @@ def fill_storage(R, pol, obs_space, act_space, c):
         st.buffers[k].copy_(bufs[k])
     st.current_rollout_step_idxs = [c["T"]]
     return st, next_value
+
+
+def _next_cases(R, only):
+    """BASELINE configs #3 / #4 ("next" rows): ResNet50 + GRU with the ObjectNav sensors, ResNeXt50 dual encoder + LSTM."""
+    from recipe import objectnav_rollout  # noqa: E402
+    for name, c in NEXT_CASES.items():
+        if only and name not in only and "next" not in only:
+            continue
+        sp = R.spaces
+        H, W = c["H"], c["W"]
+        od = collections.OrderedDict()
+        od["rgb"] = sp.Box(0, 255, (H, W, 3), np.uint8)
+        if c["imagegoal"]:
+            od["imagegoal"] = sp.Box(0, 255, (H, W, 3), np.uint8)
+        else:
+            od["depth"] = sp.Box(0, 1, (H, W, 1), np.float32)
+            od["semantic"] = sp.Box(0, 2 ** 30, (H, W, 1), np.int32)
+            od["objectgoal"] = sp.Box(0, c["n_categories"] - 1, (1,), np.int64)
+        od["compass"] = sp.Box(-np.pi, np.pi, (1,), np.float32)
+        od["gps"] = sp.Box(-1e9, 1e9, (2,), np.float32)
+        obs_space = sp.Dict(od)
+        act_space = sp.Discrete(c["n_actions"])
+        torch.manual_seed(c["seed"])
+        pol = R.PointNavResNetPolicy(obs_space, act_space, hidden_size=512, num_recurrent_layers=c["layers"],
+                                     rnn_type=c["rnn"], resnet_baseplanes=32, backbone=c["backbone"],
+                                     normalize_visual_inputs=True)
+        shapes = {k: tuple(v.shape) for k, v in pol.state_dict().items()}
+        pol.load_state_dict(recipe_state_dict(shapes, c["seed"]))
+        st = R.RolloutStorage(c["T"], c["N"], obs_space, act_space, pol)
+        bufs, next_value = objectnav_rollout(c["T"], c["N"], H, W, c["n_actions"], pol.num_recurrent_layers, 512,
+                                             c["seed"], c["n_categories"], c["imagegoal"])
+        for k, v in bufs["observations"].items():
+            st.buffers["observations"][k].copy_(v)
+        for k in ("recurrent_hidden_states", "masks", "rewards", "value_preds", "returns", "action_log_probs",
+                  "actions", "prev_actions"):
+            st.buffers[k].copy_(bufs[k])
+        st.current_rollout_step_idxs = [c["T"]]
+        st.compute_returns(next_value, True, 0.99, 0.95)
+        ppo = R.PPO(pol, ppo_epoch=1, num_mini_batch=1, use_normalized_advantage=False, **PPO_KW)
+        adv = ppo.get_advantages(st)
+        pol.train()
+        torch.manual_seed(1000 + c["seed"])
+        batch = next(iter(st.data_generator(adv, 1)))
+        values, lp, ent, hid, _ = pol.evaluate_actions(batch["observations"], batch["recurrent_hidden_states"],
+                                                       batch["prev_actions"], batch["masks"], batch["actions"],
+                                                       batch["rnn_build_seq_info"])
+        ratio = torch.exp(lp - batch["action_log_probs"])
+        action_loss = -torch.min(batch["advantages"] * ratio, batch["advantages"] * torch.clamp(ratio, 0.8, 1.2))
+        delta = values.detach() - batch["value_preds"]
+        vv = torch.where(delta.abs() < 0.2, values, batch["value_preds"] + delta.clamp(-0.2, 0.2))
+        value_loss = 0.5 * (vv - batch["returns"]) ** 2
+        total = 0.5 * value_loss.mean() + action_loss.mean() - 0.01 * ent.mean()
+        pol.zero_grad()
+        total.backward()
+        out = dict(case=c, shapes=shapes, visual_keys=list(pol.net.visual_encoder.visual_keys),
+                   returns=st.buffers["returns"].clone(), advantages=adv.clone(), mb_env_inds_seed=1000 + c["seed"],
+                   eval_values=values.detach(), eval_log_probs=lp.detach(), eval_entropy=ent.detach(),
+                   eval_hidden=hid.detach(),
+                   mb_losses=dict(value_loss=value_loss.mean().item(), action_loss=action_loss.mean().item(),
+                                  dist_entropy=ent.mean().item(), total=total.item()),
+                   grad_norms={k: p.grad.norm().item() for k, p in pol.named_parameters()},
+                   n_params=sum(p.numel() for p in pol.parameters()))
+        torch.save(out, os.path.join(HERE, f"{name}.pt"))
+        print(name, out["mb_losses"], "params", out["n_params"], "tensors", len(shapes))
+
 
 
 def main():
@@ -124,6 +197,8 @@ def main():
         torch.save(out, os.path.join(HERE, f"{name}.pt"))
         print(name, "losses", out["mb_losses"], "update", {k: round(v, 6) for k, v in metrics.items()})
 
+    if only and all(o == "next" or o in NEXT_CASES for o in only):
+        return _next_cases(R, only)
     # --- BASELINE config #1: PointNavBaselinePolicy (SimpleCNN depth-only 128x128 + GRU), num_envs = 2
     c = dict(T=8, N=2, H=128, W=128, seed=21, mb=1)
     sp = R.spaces
@@ -167,6 +242,8 @@ def main():
     out["update_metrics"] = ppo.update(st)
     torch.save(out, os.path.join(HERE, "baseline_cnn.pt"))
     print("baseline_cnn", out["mb_losses"], {k: round(v, 6) for k, v in out["update_metrics"].items()})
+
+    _next_cases(R, only)
 
     # --- RNN packed-sequence semantics (test/test_rnn_state_encoder.py) golden
     torch.manual_seed(3)

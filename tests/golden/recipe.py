@@ -69,3 +69,21 @@ def synthetic_rollout(T: int, N: int, H: int, W: int, n_actions: int, hidden_lay
     b["prev_actions"] = torch.randint(0, n_actions, (T + 1, N, 1), generator=g)
     next_value = torch.randn(N, 1, generator=g) * 0.5
     return b, next_value
+
+
+def objectnav_rollout(T: int, N: int, H: int, W: int, n_actions: int, hidden_layers: int, hidden: int, seed: int,
+                      n_categories: int = 21, imagegoal: bool = False):
+    """Config #3 / #4 sensor sets on top of synthetic_rollout: rgb (+ depth) + `semantic` (int32 class ids) +
+    objectgoal / compass / gps (ObjectNav), or rgb + imagegoal + compass / gps (ImageNav).  Same generator discipline."""
+    b, next_value = synthetic_rollout(T, N, H, W, n_actions, hidden_layers, hidden, seed, rgb=True, depth=not imagegoal)
+    g = torch.Generator().manual_seed(seed + 7919)
+    obs = b["observations"]
+    del obs["pointgoal_with_gps_compass"]
+    if imagegoal:
+        obs["imagegoal"] = torch.randint(0, 256, (T + 1, N, H, W, 3), generator=g, dtype=torch.uint8)
+    else:
+        obs["semantic"] = torch.randint(0, 40, (T + 1, N, H, W, 1), generator=g, dtype=torch.int32)
+        obs["objectgoal"] = torch.randint(0, n_categories, (T + 1, N, 1), generator=g)
+    obs["compass"] = torch.rand(T + 1, N, 1, generator=g) * 2 * math.pi - math.pi
+    obs["gps"] = torch.randn(T + 1, N, 2, generator=g) * 3.0
+    return b, next_value
