@@ -12,7 +12,7 @@ from torch import nn
 
 from .. import ops
 from ..common.baseline_registry import baseline_registry
-from .resnet_policy import BF16, POINTGOAL_UUID, NativeNetPolicy
+from .resnet_policy import BF16, POINTGOAL_UUID, NativeNetPolicy, _GRUStateEncoder
 
 
 class SimpleCNN(nn.Module):
@@ -43,18 +43,6 @@ class SimpleCNN(nn.Module):
     @property
     def is_blind(self):
         return self._n_input_rgb + self._n_input_depth == 0
-
-
-class _GRUStateEncoder(nn.Module):
-    def __init__(self, input_size, hidden_size, num_layers=1):
-        super().__init__()
-        self.num_recurrent_layers = num_layers
-        self.rnn = nn.GRU(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
-        for name, p in self.rnn.named_parameters():  # rnn_state_encoder.py:288-293
-            if "weight" in name:
-                nn.init.orthogonal_(p)
-            elif "bias" in name:
-                nn.init.constant_(p, 0)
 
 
 class PointNavBaselineNet(nn.Module):

@@ -137,6 +137,18 @@ class _LSTMStateEncoder(nn.Module):
                 nn.init.constant_(p, 0)
 
 
+class _GRUStateEncoder(nn.Module):
+    def __init__(self, input_size, hidden_size, num_layers=1):
+        super().__init__()
+        self.num_recurrent_layers = num_layers
+        self.rnn = nn.GRU(input_size=input_size, hidden_size=hidden_size, num_layers=num_layers)
+        for name, p in self.rnn.named_parameters():  # rnn_state_encoder.py:288-293
+            if "weight" in name:
+                nn.init.orthogonal_(p)
+            elif "bias" in name:
+                nn.init.constant_(p, 0)
+
+
 class PointNavResNetNet(nn.Module):
     def __init__(self, observation_space, action_space, hidden_size, num_recurrent_layers, rnn_type, backbone,
                  resnet_baseplanes, normalize_visual_inputs):
@@ -159,9 +171,12 @@ class PointNavResNetNet(nn.Module):
             raise NotImplementedError("blind policies are not implemented")
         self.visual_fc = nn.Sequential(nn.Flatten(), nn.Linear(int(np.prod(self.visual_encoder.output_shape)),
                                                                hidden_size), nn.ReLU(True))
-        if rnn_type.lower() != "lstm":
-            raise NotImplementedError("rnn_type GRU is a 'next' row (config #3); LSTM is implemented")
-        self.state_encoder = _LSTMStateEncoder(hidden_size + rnn_input_size, hidden_size, num_recurrent_layers)
+        if rnn_type.lower() == "lstm":
+            self.state_encoder = _LSTMStateEncoder(hidden_size + rnn_input_size, hidden_size, num_recurrent_layers)
+        elif rnn_type.lower() == "gru":
+            self.state_encoder = _GRUStateEncoder(hidden_size + rnn_input_size, hidden_size, num_recurrent_layers)
+        else:
+            raise RuntimeError(f"Did not recognize rnn type '{rnn_type}'")  # rnn_state_encoder.py:445
         self.train()
 
     @property

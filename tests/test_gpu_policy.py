@@ -332,3 +332,49 @@ def test_graphed_actor_replays_act(hb):
     got = ga(*step(3))
     torch.cuda.synchronize()
     torch.testing.assert_close(got.values, ref.values, rtol=0, atol=0)
+
+
+def test_resnet_policy_with_gru_vs_oracle(hb):
+    """PointNavResNetPolicy with rnn_type GRU (the reference default, resnet_policy.py:58): ResNet18 encoder + persistent
+    GRU kernels, minibatch losses and the GRU gradients against the CPU oracle on the same weights and rollout."""
+    from habitat_lab_b200.synthetic import fill_rollout_, pointnav_spaces
+    from oracle import torch_oracle as O
+
+    T, N = 8, 4
+    torch.manual_seed(11)
+    obs_space, act_space = pointnav_spaces(128, 128)
+    pol = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=512, num_recurrent_layers=1, rnn_type="GRU",
+                                  normalize_visual_inputs=True).to(DEV)
+    pol.train()
+    assert pol.net.num_recurrent_layers == 1
+    ppo = hb.PPO(pol, clip_param=0.2, ppo_epoch=1, num_mini_batch=1, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4,
+                 eps=1e-5, max_grad_norm=0.2, use_clipped_value_loss=True, use_normalized_advantage=False)
+    st = hb.RolloutStorage(T, N, obs_space, act_space, pol)
+    st.to(DEV)
+    nv = fill_rollout_(st, seed=4, p_done=0.1)
+    cpu = lambda t: t.detach().cpu().clone()  # noqa: E731
+    bufs = {k: cpu(v) for k, v in st.buffers.items() if k != "observations"}
+    obs = {k: cpu(v) for k, v in st.buffers["observations"].items()}
+    sd = {k: cpu(v) for k, v in pol.state_dict().items()}
+    st.compute_returns(nv, True, 0.99, 0.95)
+    adv = ppo.get_advantages(st)
+    batch = next(iter(st.data_generator(adv, 1)))
+    got = pol.loss_and_backward(batch, 0.2, 0.5, 0.01, True).cpu()
+    torch.cuda.synchronize()
+    ret = O.compute_returns(bufs["rewards"], bufs["value_preds"], bufs["masks"], cpu(nv), T, True, 0.99, 0.95)
+    sel = lambda v: v[0:T].flatten(0, 1)  # noqa: E731
+    rb = {k: sel(bufs[k]) for k in ("value_preds", "action_log_probs", "actions", "prev_actions", "masks")}
+    rb["returns"], rb["advantages"] = sel(ret), sel(O.get_advantages(ret, bufs["value_preds"], False))
+    sdr = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running_mean" not in k else v)
+           for k, v in sd.items()}
+    cfg = dict(visual_keys=["rgb", "depth"], ngroups=16, rnn_type="GRU", num_layers=1)
+    value, lp, ent, *_ = O.evaluate_actions({k: sel(v) for k, v in obs.items()}, bufs["recurrent_hidden_states"][0],
+                                            rb["prev_actions"], rb["masks"], rb["actions"], sdr, cfg, training=True)
+    ref = O.ppo_loss(value, lp, ent, rb, 0.2, 0.5, 0.01, True)
+    for i, k in enumerate(("value_loss", "action_loss", "dist_entropy")):
+        assert float(got[i]) == pytest.approx(float(ref[k]), rel=2e-2, abs=2e-3), k
+    ref["total_loss"].backward()
+    for name, p in pol.named_parameters():
+        if "state_encoder" in name or name.startswith(("critic", "action_distribution")):
+            r = sdr[name].grad
+            assert (p.grad.cpu() - r).norm().item() < 5e-2 * r.norm().item() + 1e-6, name
