@@ -677,7 +677,7 @@ gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* 
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int b = blockIdx.x / CS;
-  const int cv = p.C >> 3, C = p.C, G = p.G;
+  const int cv = p.C >> 3, C = p.C;
   const int pix0 = rank * ppc, pix1 = min(hw, pix0 + ppc);
   const int n = max(pix1 - pix0, 0) * cv, ncap = ppc * cv;
   uint4* sg = reinterpret_cast<uint4*>(gsm);
@@ -688,7 +688,7 @@ gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* 
   float* wred = tot + 2 * C;                                                  // [8][2C]
   float* gS = wred + 16 * C;                                                  // [2G]
   const size_t base = ((size_t)b * hw + pix0) * cv;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   {
     const uint4* gg = reinterpret_cast<const uint4*>(g) + base;
     const uint4* gy = reinterpret_cast<const uint4*>(y) + base;
@@ -797,7 +797,7 @@ gn_pool_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int b = blockIdx.x / CS;
-  const int cv = p.C >> 3, C = p.C, G = p.G, Ho = H >> 1, Wo = W >> 1;
+  const int cv = p.C >> 3, C = p.C, Ho = H >> 1, Wo = W >> 1;
   const int iy0 = rank * rows, oy0 = iy0 >> 1;           // rows is even
   const int prow = min(rows / 2 + 1, Ho - oy0);          // pooled rows that can route into this slice
   const int n = rows * W * cv, npool = prow * Wo * cv, pcap = (rows / 2 + 1) * Wo * cv;
@@ -834,7 +834,7 @@ gn_pool_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_
   cp_async_wait<0>();
   __syncthreads();  // staged rows are consumed by other threads than the ones that copied them
   const int nblk = (rows >> 1) * Wo * cv;  // 2x2 input blocks x channel vectors; thread = (block, vec)
-  const int wrow = Wo * cv, yrow = W * cv;
+  const int wrow = Wo * cv;
   float a[8], bx[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { a[e] = 0.f; bx[e] = 0.f; }
