@@ -146,3 +146,20 @@ def test_batch_obs_stacks_per_env_observations():
     b2 = batch_obs(obs, device="cpu", cache=cache)      # staging buffers are reused, results are independent copies
     assert torch.equal(b2["pointgoal_with_gps_compass"], b["pointgoal_with_gps_compass"])
     assert len(cache._pool) == 4
+
+
+@pytest.mark.parametrize("golden,backbone,cin", [("r50_objectnav", "resnet50", 5), ("rx50_imagenav", "resneXt50", 3)])
+def test_backbone_holders_match_reference_checkpoint_layout(golden, backbone, cin):
+    """Bottleneck / ResNeXt holders (no kernels yet: SURVEY 8f-2) expose exactly the reference's backbone state_dict --
+    including its quirk that only the first block of a ResNeXt stage is grouped."""
+    from habitat_lab_b200.rl.backbones import make_backbone
+
+    G = load_golden(golden)
+    pre = "net.visual_encoder.backbone."
+    ref = {k[len(pre):]: tuple(v) for k, v in G["shapes"].items() if k.startswith(pre)}
+    mine = {k: tuple(v.shape) for k, v in make_backbone(backbone, cin, 32, 16).state_dict().items()}
+    assert mine == ref
+    with pytest.raises(ValueError):
+        make_backbone("resnet1000", 3, 32, 16)
+    se = make_backbone("se_resneXt50", 3, 32, 16).state_dict()
+    assert tuple(se["layer1.0.se.excite.0.weight"].shape) == (8, 128)   # planes*expansion = 128, r = 16
