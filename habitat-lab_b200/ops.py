@@ -376,3 +376,10 @@ def embed_fwd(goal, prev_actions, masks, frame_rows, w_tgt, b_tgt, emb, out, col
 def embed_bwd(goal, prev_actions, masks, frame_rows, d_out, col0, d_w_tgt, d_b_tgt, d_emb):
     call("hb200_embed_bwd", ptr(goal), ptr(prev_actions), ptr(as_u8(masks)), ptr(frame_rows), ptr(d_out),
          d_out.stride(0), col0, frame_rows.numel(), d_emb.shape[0], ptr(d_w_tgt), ptr(d_b_tgt), ptr(d_emb))
+
+
+# ---- experimental probes (not on the product path) ------------------------------------------------------
+def tma_halo_probe(x, out, b, oh0, ow0, halo_h, halo_w, pad):
+    """x bf16 [B,H,W,C] -> out bf16 [C/8, halo_h, halo_w, 8]: one tile's input halo loaded by TMA (see hb200.h)."""
+    B, H, W, C = x.shape
+    call("hb200_tma_halo_probe", ptr(x), ptr(out), B, H, W, C, int(b), int(oh0), int(ow0), int(halo_h), int(halo_w), int(pad))

@@ -6,6 +6,7 @@ tensor-core convolutions are compared against an fp32 convolution of the SAME bf
 operands, so only accumulation order + the final bf16 rounding of the output differ (2^-8 rel).
 """
 import math
+import os
 
 import pytest
 import torch
@@ -764,3 +765,22 @@ def test_embeddings(hb):
     torch.testing.assert_close(dw.cpu(), w.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(db.cpu(), b.grad, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(de.cpu(), emb.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.skipif(not os.environ.get("HB200_EXPERIMENTAL"), reason="experimental probe, not on the product path "
+                    "(written without GPU time left in round 1; run with HB200_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("C,oh0,ow0", [(32, 0, 0), (32, 16, 24), (64, 0, 8), (32, 16, 0)])
+def test_tma_halo_probe(hb, C, oh0, ow0):
+    """TMA box copies with out-of-bounds zero fill reproduce the zero-padded halo of a 16x8 tile of a 3x3 conv."""
+    from habitat_lab_b200 import ops
+
+    B, H, W, pad, hh, hw_ = 3, 32, 32, 1, 18, 10
+    torch.manual_seed(C + oh0 + ow0)
+    x = bf(torch.randn(B, H, W, C, device=DEV))
+    out = torch.empty(C // 8, hh, hw_, 8, device=DEV, dtype=torch.bfloat16)
+    b = 1
+    ops.tma_halo_probe(x, out, b, oh0, ow0, hh, hw_, pad)
+    torch.cuda.synchronize()
+    xp = F.pad(x[b].float().permute(2, 0, 1), (pad, hw_, pad, hh))[:, oh0: oh0 + hh, ow0: ow0 + hw_]   # [C, hh, hw]
+    ref = xp.reshape(C // 8, 8, hh, hw_).permute(0, 2, 3, 1)
+    assert torch.equal(out.float(), ref)
