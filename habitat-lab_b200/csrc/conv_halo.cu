@@ -19,6 +19,9 @@
 // CTAs are persistent (weights / accumulators stay resident across tiles); halo loads for tile i+1
 // (zero-filling cp.async: padding by predication) overlap the MMAs of tile i and the epilogue of
 // tile i-1 (double-buffered halo + double-buffered TMEM accumulators).
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -416,6 +419,189 @@ __global__ void unpack_stem_wgrad_kernel(const float* __restrict__ acc, float* _
 }
 
 // resident CTAs per SM from static limits (registers, shared memory, TMEM columns); cached per kernel
+// ------------------------------------------------------------------------------------------
+// EXPERIMENTAL (HB200_HALO_TMA=1, off by default; written at the end of round 1 without GPU time left to run it):
+// the same persistent forward / dgrad kernel with the halo loaded by TMA.  One thread issues C/8
+// `cp.async.bulk.tensor.4d` box copies per tile (box = {8 channels, halo width, halo height, 1 frame}; the conv
+// padding is the TMA unit's out-of-bounds zero fill) that complete on an mbarrier, instead of ~6 predicated
+// cp.async per thread -- the address / predicate arithmetic that makes conv_halo_kernel<32,32> issue-bound
+// (profiles/r01f_ncu_top_kernels.md).  The box lands as [cj][hy][hx][8 ch], so the K-major descriptors become
+//   start = stage + 2kk*SLAB + r*HWD*16 + s*16,   LBO = SLAB (next 8 channels),   SBO = HWD*16 (next tile row).
+// Only the MMA-issuing thread waits for the load; the epilogue warps never touch the halo.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <int C, int N, int KH, int KW, int PAD, int MODE>
+__global__ void __launch_bounds__(128)
+conv_halo_tma_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
+  using Cfg = HaloCfg<C, N, KH, KW, PAD>;
+  constexpr int CJ = Cfg::CJ, HH = Cfg::HH, HWD = Cfg::HWD;
+  constexpr uint32_t SLAB = (uint32_t)((HH * HWD * 16 + 127) / 128 * 128);
+  constexpr uint32_t STAGE = CJ * SLAB;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ __align__(8) uint64_t ld_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t s_w = sbase;
+  const uint32_t s_halo0 = s_w + Cfg::W_BYTES;   // W_BYTES is a multiple of 128
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
+    mbar_init(&ld_bar[0], 1);
+    mbar_init(&ld_bar[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.wimg);
+    for (int v = tid; v < Cfg::W_BYTES / 16; v += 128) cp_async16(s_w + (uint32_t)v * 16, src + v, true);
+  }
+  cp_async_commit();
+  const int tiles_x = a.W / TW, tiles_y = a.H / TH;
+  const int tiles_per_img = tiles_x * tiles_y;
+  auto tile_coords = [&](int tile, int& b, int& oh0, int& ow0) {
+    b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    oh0 = (r / tiles_x) * TH;
+    ow0 = (r % tiles_x) * TW;
+  };
+  auto issue_halo = [&](int tile, int stage) {   // thread 0 only
+    int b, oh0, ow0;
+    tile_coords(tile, b, oh0, ow0);
+    mbar_expect_tx(&ld_bar[stage], (uint32_t)(CJ * HH * HWD * 16));
+#pragma unroll
+    for (int j = 0; j < CJ; ++j)
+      tma_load_4d(s_halo0 + (uint32_t)stage * STAGE + (uint32_t)j * SLAB, &tmap, &ld_bar[stage], j * 8, ow0 - PAD,
+                  oh0 - PAD, b);
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  if (tid == 0 && my_n > 0) issue_halo(first, 0);
+  cp_async_wait<0>();          // weights
+  fence_proxy_async_smem();    // cp.async (generic proxy) -> tcgen05 (async proxy)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+  const int py = tid >> 3, px = tid & 7;
+
+  for (int it = 0; it <= my_n; ++it) {
+    // (1) MMAs of tile it-1 are complete (frees halo stage (it+1)&1 and fills TMEM stage (it-1)&1)
+    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+    // (2) one thread starts the TMA load of tile it+1
+    if (tid == 0 && it + 1 < my_n) issue_halo(first + (it + 1) * stride, (it + 1) & 1);
+    // (3) MMAs of tile it as soon as its halo has landed
+    if (it < my_n) {
+      fence_before_sync();  // orders the previous iteration's tcgen05.ld (TMEM stage reuse)
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(&ld_bar[it & 1], (it >> 1) & 1);
+        fence_after_sync();
+        const uint32_t sh = s_halo0 + (uint32_t)(it & 1) * STAGE;
+        const uint32_t tacc = tmem_base + (uint32_t)((it & 1) * N);
+        uint32_t accum = 0;
+#pragma unroll
+        for (int r = 0; r < KH; ++r)
+#pragma unroll
+          for (int s = 0; s < KW; ++s)
+#pragma unroll
+            for (int kk = 0; kk < C / 16; ++kk) {
+              const uint64_t da = make_smem_desc(sh + 2 * kk * SLAB + r * (HWD * 16) + s * 16, SLAB, HWD * 16, kNoSwizzle);
+              const uint64_t db = make_smem_desc(s_w + (r * KW + s) * (C * N * 2) + 2 * kk * (N * 16), N * 16, 128, kNoSwizzle);
+              mma_bf16_ss(tacc, da, db, idesc, accum);
+              accum = 1;
+            }
+        mma_commit(&mma_bar[it & 1]);
+      }
+    }
+    // (4) epilogue of tile it-1 (same as conv_halo_kernel)
+    if (it >= 1) {
+      fence_after_sync();
+      int b, oh0, ow0;
+      tile_coords(first + (it - 1) * stride, b, oh0, ow0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(((it - 1) & 1) * N);
+      const size_t pix = ((size_t)b * a.H + oh0 + py) * a.W + ow0 + px;
+#pragma unroll 1
+      for (int col0 = 0; col0 < N; col0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + col0, rr);
+        tmem_ld_wait();
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rr[j]);
+        if (MODE == 0 && a.stats != nullptr) {
+          const int cpg = N / a.gn_groups;
+          float s2[16], q2[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            s2[i] = acc[2 * i] + acc[2 * i + 1];
+            q2[i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
+          }
+          const float ts = warp_reduce16(s2, lane), tq = warp_reduce16(q2, lane);
+          if ((lane & 1) == 0) {
+            const int ch = col0 + lane;
+            double* dst = a.stats + ((size_t)b * a.gn_groups + ch / cpg) * 2;
+            atomicAdd(dst, (double)ts);
+            atomicAdd(dst + 1, (double)tq);
+          }
+        }
+        const size_t o = pix * N + col0;
+        if (MODE == 1 && a.addend != nullptr) {
+          const uint4* ad = reinterpret_cast<const uint4*>(a.addend + o);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            float f[8];
+            unpack8(ad[v], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[v * 8 + e] += f[e];
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(a.y + o);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 u;
+          u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+          u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+          u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+          u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          dst[v] = u;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn halo_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
 static int blocks_per_sm(const void* kern, size_t smem, int tmem_cols, int* cache) {
   if (*cache > 0) return *cache;
   cudaFuncAttributes fa;
@@ -443,6 +629,40 @@ static int launch_halo(const HaloArgs& a, cudaStream_t st) {
   int grid = kNumSMs * per_sm;
   if (grid > a.ntiles) grid = a.ntiles;
   kern<<<grid, 128, smem, st>>>(a);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+template <int C, int N, int KH, int KW, int PAD, int MODE>
+static int launch_halo_tma(const HaloArgs& a, cudaStream_t st) {
+  using Cfg = HaloCfg<C, N, KH, KW, PAD>;
+  EncodeTiledFn enc = halo_encode_fn();
+  if (!enc) {
+    set_last_error("conv_halo (TMA): cuTensorMapEncodeTiled is not available from this driver");
+    return HB200_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)a.W * C * 2, (cuuint64_t)a.H * a.W * C * 2};
+  const cuuint32_t box[4] = {8u, (cuuint32_t)Cfg::HWD, (cuuint32_t)Cfg::HH, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.x, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("conv_halo (TMA): cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HB200_ERR_CUDA;
+  }
+  constexpr size_t slab = (size_t)((Cfg::HH * Cfg::HWD * 16 + 127) / 128 * 128);
+  const size_t smem = Cfg::W_BYTES + 2 * Cfg::CJ * slab + 256;
+  auto kern = conv_halo_tma_kernel<C, N, KH, KW, PAD, MODE>;
+  static int cache = 0;
+  if (cache == 0) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = blocks_per_sm((const void*)kern, smem, Cfg::TMEM_COLS, &cache);
+  int grid = kNumSMs * per_sm;
+  if (grid > a.ntiles) grid = a.ntiles;
+  kern<<<grid, 128, smem, st>>>(a, tmap);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -512,6 +732,10 @@ extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb20
   a.B = batch; a.H = h; a.W = w; a.gn_groups = gn_groups > 0 ? gn_groups : 1;
   a.ntiles = batch * (h / TH) * (w / TW);
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool use_tma = getenv("HB200_HALO_TMA") != nullptr;   // experimental TMA halo load (see above)
+  if (use_tma && k == 3 && c == 32)
+    return mode == 0 ? launch_halo_tma<32, 32, 3, 3, 1, 0>(a, st) : launch_halo_tma<32, 32, 3, 3, 1, 1>(a, st);
+  if (use_tma && k == 4 && mode == 0) return launch_halo_tma<16, 32, 4, 4, 2, 0>(a, st);
   if (k == 3 && c == 32) return mode == 0 ? launch_halo<32, 32, 3, 3, 1, 0>(a, st) : launch_halo<32, 32, 3, 3, 1, 1>(a, st);
   if (k == 3 && c == 64) return mode == 0 ? launch_halo<64, 64, 3, 3, 1, 0>(a, st) : launch_halo<64, 64, 3, 3, 1, 1>(a, st);
   HB_CHECK_ARG(mode == 0, "conv_halo: the stem has no data gradient");
