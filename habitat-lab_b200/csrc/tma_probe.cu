@@ -1,4 +1,4 @@
-// hb200 -- EXPERIMENTAL (not on the product path yet): TMA halo load probe.
+// hb200 -- TMA halo load probe (verified on a B200; not on the product path yet).
 //
 // Next step for the halo convolutions (NOTES_NEXT.md item 4): replace the per-thread zero-filling cp.async gather of the
 // (TH+KH-1) x (TW+KW-1) input halo -- ~6 copies per thread, each with its own address and bounds predicate, the reason

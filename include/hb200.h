@@ -389,7 +389,7 @@ int hb200_embed_bwd(const float* goal, const int64_t* prev_actions, const uint8_
                     int n_emb, float* d_w_tgt, float* d_b_tgt, float* d_emb,
                     hb200_stream_t stream);
 
-/* EXPERIMENTAL -- not on the product path.  Mechanism probe for the TMA halo load planned for the halo convolutions
+/* Not on the product path yet: mechanism probe (verified on hardware) for the TMA halo load of the halo convolutions
  * (NOTES_NEXT.md): loads the halo_h x halo_w halo of the tile whose first output pixel is (oh0, ow0) of frame b from the
  * NHWC bf16 tensor x [batch, h, w, channels] with channels/8 `cp.async.bulk.tensor.4d` box copies (out-of-bounds rows /
  * columns zero-filled = conv padding `pad`) and writes the staged slabs to out [channels/8][halo_h][halo_w][8]. */

@@ -767,8 +767,6 @@ def test_embeddings(hb):
     torch.testing.assert_close(de.cpu(), emb.grad, rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.skipif(not os.environ.get("HB200_EXPERIMENTAL"), reason="experimental probe, not on the product path "
-                    "(written without GPU time left in round 1; run with HB200_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("C,oh0,ow0", [(32, 0, 0), (32, 16, 24), (64, 0, 8), (32, 16, 0)])
 def test_tma_halo_probe(hb, C, oh0, ow0):
     """TMA box copies with out-of-bounds zero fill reproduce the zero-padded halo of a 16x8 tile of a 3x3 conv."""
