@@ -95,26 +95,34 @@ def _cpu_threads():
     return max(1, min(len(os.sched_getaffinity(0)), 32))
 
 
-def _make_cpu_learner(T=16, N=8):
+CPU_SAMPLE = dict(T=128, N=8)   # bounded CPU sample: the config's rollout length, 8 of the 64 envs per iteration
+if os.environ.get("HB200_CPU_SAMPLE"):   # "T,N": the contract test shrinks the sample, the wording below follows
+    CPU_SAMPLE = dict(zip(("T", "N"), (int(v) for v in os.environ["HB200_CPU_SAMPLE"].split(","))))
+
+
+def _recipe_rollout(T, N, seed=5):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-    from recipe import recipe_state_dict, synthetic_rollout
-    from oracle.cpu_learner import CpuLearner
-    import habitat_lab_b200 as hb
-    from habitat_lab_b200.synthetic import pointnav_spaces
+    from recipe import synthetic_rollout
+    return synthetic_rollout(T, N, CFG["H"], CFG["W"], 4, 2 * CFG["layers"], CFG["hidden"], seed, p_done=1.0 / 250.0)
 
-    obs_space, act_space = pointnav_spaces(CFG["H"], CFG["W"])
-    pol = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=CFG["hidden"], num_recurrent_layers=CFG["layers"],
-                                  rnn_type="LSTM", normalize_visual_inputs=True)  # shapes only (holders)
-    shapes = {k: tuple(v.shape) for k, v in pol.state_dict().items()}
-    sd = recipe_state_dict(shapes, 7)
-    cfg = dict(visual_keys=["rgb", "depth"], ngroups=16, rnn_type="LSTM", num_layers=CFG["layers"])
-    learner = CpuLearner(sd, cfg, ppo_epoch=CFG["ppo_epoch"], num_mini_batch=CFG["num_mini_batch"])
-    bufs, next_value = synthetic_rollout(T, N, CFG["H"], CFG["W"], 4, 2 * CFG["layers"], CFG["hidden"], 5)
 
-    def step():
-        learner.update({k: (dict(v) if isinstance(v, dict) else v.clone()) for k, v in bufs.items()}, next_value, T)
+def _make_cpu_learner(T=CPU_SAMPLE["T"], N=CPU_SAMPLE["N"]):
+    """The UNMODIFIED reference (baseline/_ref or /root/reference through the import shim): RolloutStorage.compute_returns
+    + PPO.update on device="cpu" -- the reference's own CPU PPO path."""
+    from oracle.ref_learner import ReferenceLearner
 
-    return step, T * N
+    learner = ReferenceLearner(T, N, CFG["H"], CFG["W"], "cpu", hidden=CFG["hidden"], layers=CFG["layers"],
+                               ppo_epoch=CFG["ppo_epoch"], num_mini_batch=CFG["num_mini_batch"])
+    bufs, next_value = _recipe_rollout(T, N)
+    learner.load_rollout(bufs, next_value)
+    return learner.step, T * N
+
+
+def _cpu_sample_text(threads):
+    return (f"learner iteration(s) of T={CPU_SAMPLE['T']} x N={CPU_SAMPLE['N']} frames (256x256 RGB-D; the config has T=128, "
+            f"N=64 envs per rank; {CFG['ppo_epoch']} epochs x {CFG['num_mini_batch']} minibatches of "
+            f"{CPU_SAMPLE['T'] * CPU_SAMPLE['N'] // CFG['num_mini_batch']} frames), unmodified reference classes on "
+            f"device=cpu, {threads} threads")
 
 
 def _cpu_learner_sample(threads, updates):
@@ -125,9 +133,7 @@ def _cpu_learner_sample(threads, updates):
     for _ in range(updates):
         step()
     dt = time.perf_counter() - t0
-    sample = (f"{updates} learner iterations of T=16 x N=8 frames (256x256 RGB-D, {CFG['ppo_epoch']} epochs x "
-              f"{CFG['num_mini_batch']} minibatches) after 1 warm-up, {threads} threads, {dt:.1f} s")
-    return updates * frames / dt, sample
+    return updates * frames / dt, f"{updates} " + _cpu_sample_text(threads) + f" after 1 warm-up, {dt:.1f} s"
 
 
 def run_reference(args):
@@ -145,15 +151,89 @@ def run_reference(args):
         step()
         ms.append((time.perf_counter() - t0) * 1e3)
     v = frames * len(ms) / (sum(ms) * 1e-3)
-    sample = (f"each step = 1 learner iteration of T=16 x N=8 frames (256x256 RGB-D, {CFG['ppo_epoch']} epochs x "
-              f"{CFG['num_mini_batch']} minibatches), {threads} threads")
+    sample = "each step = 1 " + _cpu_sample_text(threads)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": sum(ms) / len(ms),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": _config(args.gpus),
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
+
+
+# ---------------------------------------------------------------------------------------------
+# the competitor: the unmodified reference on CUDA (TF32 cuDNN, cudnn.benchmark, DDP + NCCL)
+# ---------------------------------------------------------------------------------------------
+def torch_cuda_measure(dev, world, rollout_buffers, next_value, steps, warmup, seed):
+    """frames/s of the reference's own PyTorch-CUDA DD-PPO learner on config #2 (same T, N, minibatching, same
+    synthetic rollout tensors as the hb200 arm), CUDA events, barrier both sides, max over ranks."""
+    from oracle.ref_learner import ReferenceLearner, cuda_settings
+
+    settings = cuda_settings()
+    T, N = CFG["T"], CFG["N"]
+    learner = ReferenceLearner(T, N, CFG["H"], CFG["W"], dev, hidden=CFG["hidden"], layers=CFG["layers"],
+                               ppo_epoch=CFG["ppo_epoch"], num_mini_batch=CFG["num_mini_batch"],
+                               distributed=world > 1, seed=seed)
+    learner.load_rollout(rollout_buffers, next_value)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, warmup)):
+        learner.step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = learner.step()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms = ms.item()
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del learner
+    torch.cuda.empty_cache()
+    return {"value": world * T * N * steps / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / steps, "steps": steps,
+            "warmup": max(3, warmup), "n_gpus": world, "kind": "reference (unmodified habitat_baselines classes, device=cuda)",
+            "settings": settings, "parallelism": "DistributedDataParallel + NCCL (DDPPO.init_distributed)" if world > 1 else "single process",
+            "peak_mem_gb": round(peak_gb, 1), "learner_metrics": {k: round(float(v), 6) for k, v in (out or {}).items()}}
+
+
+def run_torch_cuda(args):
+    """bench.py --impl torch_cuda: the competitor arm alone, launched like the hb200 arm (torchrun for N > 1)."""
+    import habitat_lab_b200 as hb
+    from habitat_lab_b200.synthetic import fill_rollout_, pointnav_spaces
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    T, N = CFG["T"], CFG["N"]
+    obs_space, act_space = pointnav_spaces(CFG["H"], CFG["W"])
+
+    class _Shape:   # RolloutStorage only reads these two attributes of the policy
+        num_recurrent_layers, recurrent_hidden_size = 2 * CFG["layers"], CFG["hidden"]
+
+    st = hb.RolloutStorage(T, N, obs_space, act_space, _Shape())
+    st.to(dev)
+    next_value = fill_rollout_(st, seed=100 + rank * N)
+    res = torch_cuda_measure(dev, world, st.buffers, next_value, args.steps, args.warmup, seed=100)
+    if rank == 0:
+        line = {"impl": "torch_cuda", "metric": METRIC, "value": res["value"], "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32 convs / fp32", "data": "synthetic",
+                "config": _config(world), "torch_cuda": res}
+        _emit(line)
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 def _config(n):
@@ -180,9 +260,8 @@ def run_hb200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO") and not os.environ.get("HB200_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG is left exactly as the launcher set it (the driver reads the communicator's rank count from the
+        # INFO log); main() points fd 1 at stderr, so whatever NCCL prints cannot reach the JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = hb.load()
     T, N = CFG["T"], CFG["N"]
@@ -237,6 +316,7 @@ def run_hb200(args):
     clocks = sampler.stop() if rank == 0 else None
     frames = world * T * N * args.steps
     value = frames / (ms * 1e-3)
+    cross_rank = cross_rank_equality(policy, dev, world) if world > 1 else None
 
     # ---- e2e: same iteration through the public API with HOST inputs: every step's rollout (observations and
     # scalars) is copied from pinned host memory and the metrics dict goes back to the host, all inside the timed
@@ -289,6 +369,18 @@ def run_hb200(args):
     ms_e2e, _ = timed(lambda: e2e_run(e2e_steps), 1)
     e2e_value = world * T * N * e2e_steps / (ms_e2e * 1e-3)
 
+    # ---- the competitor, in the same process group right after the hb200 measurement: the UNMODIFIED reference on
+    # CUDA (TF32 cuDNN convs, cudnn.benchmark, DDP + NCCL for world > 1) on the same synthetic rollout tensors
+    torch_cuda = None
+    if not args.no_torch_cuda:
+        del st_b, slots, host
+        torch.cuda.empty_cache()
+        try:
+            torch_cuda = torch_cuda_measure(dev, world, st.buffers, next_value, args.steps, args.warmup, seed=100)
+            torch_cuda["hb200_over_torch_cuda"] = value / torch_cuda["value"]
+            torch_cuda["hb200_e2e_over_torch_cuda"] = e2e_value / torch_cuda["value"]
+        except Exception as e:   # e.g. baseline/_ref missing on this box: report, never lose the hb200 line
+            torch_cuda = {"unavailable": repr(e)[:300]}
     line = None
     if rank == 0:
         peaks = _peaks()
@@ -297,8 +389,11 @@ def run_hb200(args):
         cores = _cpu_threads()
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            fps, sample = _cpu_learner_sample(cores, updates=16)   # ~15 s of host work
-            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+            try:
+                fps, sample = _cpu_learner_sample(cores, updates=2)   # ~15-30 s of host work
+                cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample}
+            except Exception as e:
+                cpu = {"unavailable": repr(e)[:300]}
         # ---- informational: the actor half of the loop ("next"): T sequential act() calls at batch N
         # on the same synthetic observations (eager and CUDA-graph replay), so that learner-only and learner+actor
         # frames/s can be read side by side.  Measured last and fully guarded: it can never cost the bench line.
@@ -344,12 +439,33 @@ def run_hb200(args):
                         "d2h_bytes_per_step": 14 * 4, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                         "h2d": "pinned host -> device on a copy stream, double-buffered across steps; first copy exposed"},
                 "roofline": roof, "hbm_kernel_rooflines": hbm_roofs, "cpu_baseline": cpu, "actor": actor,
+                "torch_cuda_baseline": torch_cuda, "cross_rank_equality": cross_rank,
                 "conv_tensor_frac_of_step": (world * T * N * CFG["ppo_epoch"] * CONV_TRAIN_GFLOP * 1e-3 * args.steps)
                 / (ms * 1e-3) / (peaks["bf16_sustained"] * world),
                 "learner_metrics": {k: round(float(v), 6) for k, v in metrics.items()}}
         _emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def cross_rank_equality(policy, dev, world):
+    """After the timed optimizer steps every rank must hold bit-identical parameters and RunningMeanAndVar buffers
+    (what DDP guarantees for the reference, test/test_ddppo_reduce.py:111-118): rank 0's copies are broadcast and
+    compared byte for byte on every rank, the verdict is reduced with MIN."""
+    import torch.distributed as dist
+
+    flat = policy.flatten_parameters_()
+    tensors = [("flat_params", flat["params"])] + [(n, b) for n, b in policy.named_buffers()]
+    out = {}
+    for name, t in tensors:
+        ref = t.detach().clone()
+        dist.broadcast(ref, src=0)
+        ok = torch.tensor([1 if torch.equal(ref, t.detach()) else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        out[name.split(".")[-1] if name != "flat_params" else name] = bool(ok.item())
+    out["all_equal"] = all(out.values())
+    out["world"] = world
+    return out
 
 
 def _ncu_traffic():
@@ -530,11 +646,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="hb200", choices=["hb200", "reference"])
+    ap.add_argument("--impl", default="hb200", choices=["hb200", "reference", "torch_cuda"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-cuda", action="store_true", help="skip the reference PyTorch-CUDA competitor leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_cuda":
+        run_torch_cuda(args)
     else:
         run_hb200(args)
 

@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const WgradArgs a) {
 template <int LAYOUT, int MNMAJOR>
 __global__ void __launch_bounds__(128)
 umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Bm,
-                  float* __restrict__ D, int M, int N, int K) {
+                  float* __restrict__ D, int M, int N, int K, int a_fmt, int b_fmt) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -500,7 +500,7 @@ umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  const uint32_t idesc = make_idesc_bf16(kTileM, N, MNMAJOR, MNMAJOR);
+  const uint32_t idesc = make_idesc_f16(kTileM, N, MNMAJOR, MNMAJOR, a_fmt, b_fmt);
   const int nchunks = K / kChunkK;
   for (int c = 0; c < nchunks; ++c) {
     if (!MNMAJOR) {
@@ -852,6 +852,9 @@ extern "C" int hb200_umma_gemm_probe(const hb200_bf16* a, const hb200_bf16* b, f
                                      int k, int layout, hb200_stream_t stream) {
   HB_CHECK_ARG(a && b && d, "probe: null pointer");
   HB_CHECK_ARG(m % 128 == 0 && n % 16 == 0 && n >= 16 && n <= 256 && k % 64 == 0, "probe: bad dims");
+  // bit 4 / bit 5 of `layout`: operand A / B holds IEEE fp16 instead of bf16 (pins the mixed-format encoding)
+  const int a_fmt = (layout & 16) ? kFmtF16 : kFmtBF16, b_fmt = (layout & 32) ? kFmtF16 : kFmtBF16;
+  layout &= 15;
   HB_CHECK_ARG(layout >= 0 && layout <= 2, "probe: layout 0 (K-major no swizzle), 1 (K-major 128B), 2 (MN-major)");
   const size_t smem = (size_t)(kTileM + n) * kChunkK * 2 + 1024;
   cudaStream_t st = (cudaStream_t)stream;
@@ -860,15 +863,15 @@ extern "C" int hb200_umma_gemm_probe(const hb200_bf16* a, const hb200_bf16* b, f
   if (layout == 0) {
     auto kern = umma_probe_kernel<0, 0>;
     HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<m / 128, 128, smem, st>>>(A, B, d, m, n, k);
+    kern<<<m / 128, 128, smem, st>>>(A, B, d, m, n, k, a_fmt, b_fmt);
   } else if (layout == 1) {
     auto kern = umma_probe_kernel<1, 0>;
     HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<m / 128, 128, smem, st>>>(A, B, d, m, n, k);
+    kern<<<m / 128, 128, smem, st>>>(A, B, d, m, n, k, a_fmt, b_fmt);
   } else {
     auto kern = umma_probe_kernel<0, 1>;
     HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<m / 128, 128, smem, st>>>(A, B, d, m, n, k);
+    kern<<<m / 128, 128, smem, st>>>(A, B, d, m, n, k, a_fmt, b_fmt);
   }
   HB_LAUNCH_OK();
   count_launch(1);

@@ -18,7 +18,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("HB200_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _pick_root() -> str:
+    """/root/reference in the build container; on the GPU box (where it does not exist) the verbatim copy that
+    baseline/install_reference.py placed under baseline/_ref/ (git-ignored, shipped with the snapshot)."""
+    env = os.environ.get("HB200_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "habitat-baselines", "habitat_baselines")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 HB = os.path.join(REFERENCE_ROOT, "habitat-baselines", "habitat_baselines")
 
 

@@ -27,6 +27,10 @@ CASES = {
     # name: (T, N, H, W, rnn_type, layers, ppo_epoch, num_mini_batch, use_normalized_advantage)
     "small128": dict(T=8, N=4, H=128, W=128, rnn="LSTM", layers=2, epochs=2, mb=2, norm_adv=False, seed=11),
     "full256": dict(T=4, N=2, H=256, W=256, rnn="LSTM", layers=2, epochs=1, mb=1, norm_adv=True, seed=12),
+    # BASELINE config #2 at the rollout length the bench runs (T = 128): 16 envs, minibatch = 8 envs x 128 steps = 1024
+    # frames of 256x256 RGB-D through the 2-layer LSTM (BPTT over 128 steps, ~1 reset per 100 steps)
+    "bench128": dict(T=128, N=16, H=256, W=256, rnn="LSTM", layers=2, epochs=1, mb=2, norm_adv=False, seed=13,
+                     p_done=0.01, grad_samples=64),
 }
 NEXT_CASES = {
     # BASELINE config #3: ObjectNav DD-PPO, ResNet50 RGB(-D) + semantic channel, GRU-512
@@ -58,7 +62,8 @@ def build_reference(R, c):
 
 def fill_storage(R, pol, obs_space, act_space, c):
     st = R.RolloutStorage(c["T"], c["N"], obs_space, act_space, pol)
-    bufs, next_value = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, pol.num_recurrent_layers, 512, c["seed"])
+    bufs, next_value = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, pol.num_recurrent_layers, 512, c["seed"],
+                                         p_done=c.get("p_done", 1 / 25))
     for k, v in bufs["observations"].items():
         st.buffers["observations"][k].copy_(v)
     for k in ("recurrent_hidden_states", "masks", "rewards", "value_preds", "returns", "action_log_probs",
@@ -153,6 +158,19 @@ def main():
         ppo_nn = R.PPO(pol, ppo_epoch=1, num_mini_batch=1, use_normalized_advantage=not c["norm_adv"], **PPO_KW)
         out["advantages_other_mode"] = ppo_nn.get_advantages(st).clone()
 
+        # --- actor path (rl/ppo/policy.py:322-357): eval-mode act(deterministic) / get_value on rollout step 1 (all envs)
+        pol.eval()
+        with torch.no_grad():
+            o1 = {k: v[1] for k, v in st.buffers["observations"].items()}
+            a = pol.act(o1, st.buffers["recurrent_hidden_states"][1], st.buffers["prev_actions"][1],
+                        st.buffers["masks"][1], deterministic=True)
+            feats, _, _ = pol.net(o1, st.buffers["recurrent_hidden_states"][1], st.buffers["prev_actions"][1],
+                                  st.buffers["masks"][1])
+            out["act"] = dict(values=a.values.clone(), actions=a.actions.clone(), action_log_probs=a.action_log_probs.clone(),
+                              rnn_hidden_states=a.rnn_hidden_states.clone(),
+                              logits=pol.action_distribution(feats).logits.clone(),
+                              get_value=pol.get_value(o1, st.buffers["recurrent_hidden_states"][1],
+                                                      st.buffers["prev_actions"][1], st.buffers["masks"][1]).clone())
         # --- one minibatch: evaluate_actions + loss + backward (no optimizer step)
         pol.train()
         torch.manual_seed(1000 + c["seed"])  # randperm of data_generator
@@ -181,7 +199,8 @@ def main():
         out["mb_losses"] = dict(value_loss=value_loss.mean().item(), action_loss=action_loss.mean().item(),
                                 dist_entropy=ent.mean().item(), total=total.item())
         out["grad_norms"] = {k: p.grad.norm().item() for k, p in pol.named_parameters()}
-        out["grad_samples"] = {k: p.grad.flatten()[:: max(1, p.numel() // 16)][:16].clone()
+        ns = c.get("grad_samples", 16)
+        out["grad_samples"] = {k: p.grad.flatten()[:: max(1, p.numel() // ns)][:ns].clone()
                                for k, p in pol.named_parameters()}
         # restore running stats so update() starts from the recipe state
         pol.load_state_dict({**pol.state_dict(), **stats_before})

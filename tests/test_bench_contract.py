@@ -1,4 +1,4 @@
-"""CPU: the reference arm of bench.py (`--impl reference`: the reference's CPU learner through the oracle port) prints exactly
+"""CPU: the reference arm of bench.py (`--impl reference`: the UNMODIFIED reference's CPU learner from baseline/_ref) prints exactly
 one JSON line on stdout with the keys the driver reads, whatever libraries print meanwhile."""
 import json
 import os
@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
-    env = dict(os.environ, OMP_NUM_THREADS="8")
+    env = dict(os.environ, OMP_NUM_THREADS="8", HB200_CPU_SAMPLE="16,4")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
@@ -20,7 +20,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["metric"].startswith("DD-PPO learner frames/sec")
     for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
     assert "workload" in d["config"]
 

@@ -212,6 +212,29 @@ def test_umma_probe(hb, layout):
     torch.testing.assert_close(d, a.float() @ b.float().t(), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("a_f16,b_f16", [(True, True), (True, False), (False, True)])
+def test_umma_probe_operand_formats(hb, layout, a_f16, b_f16):
+    """kind::f16 with per-operand formats: forward operands are IEEE fp16 (11-bit significand), gradients bf16; the
+    weight-gradient MMAs mix them (x fp16 x dy bf16).  Values carry > 8 significant bits so a wrong format field
+    (fp16 bits read as bf16 or vice versa) cannot pass."""
+    from habitat_lab_b200 import ops
+
+    m, n, k = 256, 64, 192
+    torch.manual_seed(layout * 4 + a_f16 * 2 + b_f16)
+    a32, b32 = torch.randn(m, k, device=DEV), torch.randn(n, k, device=DEV)
+    a = a32.half() if a_f16 else a32.bfloat16()
+    b = b32.half() if b_f16 else b32.bfloat16()
+    d = torch.zeros(m, n, device=DEV)
+    flags = layout | (16 if a_f16 else 0) | (32 if b_f16 else 0)
+    if layout == 2:
+        ops.umma_gemm_probe(a.t().contiguous(), b.t().contiguous(), d, m, n, k, flags)
+    else:
+        ops.umma_gemm_probe(a, b, d, m, n, k, flags)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(d, a.float() @ b.float().t(), rtol=1e-4, atol=1e-3)
+
+
 CONV_CASES = [
     # B, H, W, Ci_real, Ci_pad, Co, k, stride, pad
     (2, 32, 32, 32, 32, 32, 3, 1, 1),     # layer1

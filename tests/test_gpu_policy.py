@@ -29,7 +29,8 @@ def _make(hb, G):
     pol.load_state_dict(recipe_state_dict(G["shapes"], c["seed"]))
     pol.to(DEV)
     st = hb.RolloutStorage(c["T"], c["N"], obs_space, act_space, pol)
-    bufs, next_value = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, 2 * c["layers"], 512, c["seed"])
+    bufs, next_value = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, 2 * c["layers"], 512, c["seed"],
+                                         p_done=c.get("p_done", 1 / 25))
     for k, v in bufs["observations"].items():
         st.buffers["observations"][k].copy_(v)
     for k in ("recurrent_hidden_states", "masks", "rewards", "value_preds", "returns", "action_log_probs", "actions",
@@ -40,7 +41,7 @@ def _make(hb, G):
     return pol, st, next_value.to(DEV), c
 
 
-@pytest.mark.parametrize("name", ["small128", "full256"])
+@pytest.mark.parametrize("name", ["small128", "full256", "bench128"])
 def test_returns_advantages_vs_reference(hb, name):
     G = load_golden(name)
     pol, st, next_value, c = _make(hb, G)
@@ -53,7 +54,7 @@ def test_returns_advantages_vs_reference(hb, name):
     torch.testing.assert_close(adv.cpu(), G["advantages"], rtol=1e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize("name", ["small128", "full256"])
+@pytest.mark.parametrize("name", ["small128", "full256", "bench128"])
 def test_minibatch_forward_backward_vs_reference(hb, name):
     G = load_golden(name)
     pol, st, next_value, c = _make(hb, G)
@@ -102,7 +103,8 @@ def test_minibatch_forward_backward_vs_reference(hb, name):
     # full-gradient direction vs the CPU oracle on the same minibatch (cosine per tensor)
     from oracle import torch_oracle as O
 
-    bufs, _ = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, 2 * c["layers"], 512, c["seed"])
+    bufs, _ = synthetic_rollout(c["T"], c["N"], c["H"], c["W"], 4, 2 * c["layers"], 512, c["seed"],
+                                         p_done=c.get("p_done", 1 / 25))
     bufs["value_preds"], bufs["returns"] = G["value_preds_after"].clone(), G["returns"].clone()
     ob = gather_minibatch(bufs, G["advantages"], batch["env_inds"], c["T"])
     sd0 = recipe_state_dict(G["shapes"], c["seed"])
@@ -121,7 +123,35 @@ def test_minibatch_forward_backward_vs_reference(hb, name):
     print(name, "worst per-tensor gradient cosine vs fp32 oracle:", worst)
 
 
-@pytest.mark.parametrize("name", ["small128", "full256"])
+@pytest.mark.parametrize("name", ["small128", "full256", "bench128"])
+def test_act_and_get_value_vs_reference(hb, name):
+    """The actor path (eval-mode trunk, T = 1 single-step recurrence, heads): act(deterministic) / get_value on rollout
+    step 1 vs what the REAL reference recorded (rl/ppo/policy.py:322-357)."""
+    G = load_golden(name)
+    pol, st, _, c = _make(hb, G)
+    pol.eval()
+    A = G["act"]
+    b = st.buffers
+    step = ({k: v[1] for k, v in b["observations"].items()}, b["recurrent_hidden_states"][1], b["prev_actions"][1],
+            b["masks"][1])
+    out = pol.act(*step, deterministic=True)
+    val = pol.get_value(*step)
+    torch.cuda.synchronize()
+    assert (out.values.cpu() - A["values"]).abs().max().item() < 5e-3
+    assert (val.cpu() - A["get_value"]).abs().max().item() < 5e-3
+    assert (out.rnn_hidden_states.cpu() - A["rnn_hidden_states"]).abs().max().item() < 5e-3
+    # the greedy action may only differ where the reference's two best logits are closer than the logit tolerance
+    top2 = A["logits"].topk(2, dim=-1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 5e-3
+    assert torch.equal(out.actions.cpu()[decided], A["actions"][decided])
+    same = out.actions.cpu() == A["actions"]
+    assert (out.action_log_probs.cpu() - A["action_log_probs"])[same].abs().max().item() < 5e-3
+    # eval mode must not touch the running statistics
+    sd = pol.state_dict()
+    assert float(sd["net.visual_encoder.running_mean_and_var._count"]) == 5.0
+
+
+@pytest.mark.parametrize("name", ["small128", "full256", "bench128"])
 def test_ppo_update_vs_reference(hb, name):
     G = load_golden(name)
     pol, st, next_value, c = _make(hb, G)
