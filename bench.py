@@ -529,7 +529,10 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
             tw = t_ms(lambda: ops.conv_halo_wgrad(xin, y, c.dw_acc, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, 3))
         else:
             tf = t_ms(lambda: ops.conv_fwd(xin, c.wp, y, s, stats, c.groups))
-            tw = t_ms(lambda: ops.conv_wgrad(xin, y, c.dw_acc, s))
+            if getattr(c, "halo_w", False):
+                tw = t_ms(lambda: ops.conv_halo_wgrad(xin, y, c.dw_acc, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, 3))
+            else:
+                tw = t_ms(lambda: ops.conv_wgrad(xin, y, c.dw_acc, s))
         per["fwd"][0] += flop; per["fwd"][1] += tf
         per["wgrad"][0] += flop; per["wgrad"][1] += tw
         td = None

@@ -50,6 +50,7 @@ SIGNATURES = {
     "hb200_set_umma_layout": ("i", "i"),
     "hb200_get_umma_layout": ("i", ""),
     "hb200_conv_halo_supported": ("i", "iiiii"),
+    "hb200_conv_halo_wgrad_supported": ("i", "iiiii"),
     "hb200_pack_halo_weight": ("i", "pp" + "iiiiii" + "p"),
     "hb200_conv_halo": ("i", "ppppp" + "iiiiiiii" + "p"),
     "hb200_conv_halo_wgrad": ("i", "ppp" + "iiiiii" + "p"),

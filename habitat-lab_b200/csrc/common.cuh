@@ -1,6 +1,7 @@
 // hb200 -- shared device/host helpers for the sm_100a DD-PPO learner kernels.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -100,6 +101,36 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 u;
   u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
   u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+// ---- storage types -----------------------------------------------------------------
+// FORWARD values (pooled input, conv outputs y, normalised activations a / o, packed weight images of the forward
+// convs) are IEEE fp16: 11 significant bits -- the same significand as the TF32 operands the reference's cuDNN path
+// multiplies -- at bf16's cost.  GRADIENTS (g, dy, gz) are bf16: they need fp32's exponent range (per-element
+// magnitudes of 1e-8 are normal with a mean-over-4096-frames loss) and their rounding only perturbs the result
+// linearly, while forward rounding flips ReLU / max-pool decisions.
+typedef __half act_t;
+typedef __nv_bfloat16 grad_t;
+
+// fp16 pack with saturation to +-65504 (one F2FP.SATFINITE instruction): an overflow must not become inf
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+__device__ __forceinline__ void unpack8a(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_f16x2(u.x), b = unpack_f16x2(u.y), c = unpack_f16x2(u.z), d = unpack_f16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8a(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_f16x2(f[0], f[1]); u.y = pack_f16x2(f[2], f[3]);
+  u.z = pack_f16x2(f[4], f[5]); u.w = pack_f16x2(f[6], f[7]);
   return u;
 }
 

@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
     }
   };
 
-  constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 0, 0);
+  // forward: fp16 activations x fp16 weight image; dgrad: bf16 gradients x bf16 transposed weight image
+  constexpr uint32_t idesc = MODE == 0 ? make_idesc_f16(kTileM, BN, 0, 0, kFmtF16, kFmtF16) : make_idesc_bf16(kTileM, BN, 0, 0);
   // ---- software pipeline: cp.async runs kStages-1 chunks ahead of the tensor core ----
 #pragma unroll
   for (int c = 0; c < kStages - 1; ++c) {
@@ -321,10 +322,17 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         uint4 u;
-        u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
-        u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
-        u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
-        u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+        if (MODE == 0) {  // forward output y: fp16 (saturating)
+          u.x = pack_f16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+          u.y = pack_f16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+          u.z = pack_f16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+          u.w = pack_f16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+        } else {          // data gradient: bf16
+          u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+          u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+          u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+          u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+        }
         dst[v] = u;
       }
     }
@@ -421,7 +429,8 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const WgradArgs a) {
     }
   };
 
-  constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 1, 1);
+  // A = gathered forward activations x (fp16), B = output gradients dy (bf16): mixed-format kind::f16 MMA
+  constexpr uint32_t idesc = make_idesc_f16(kTileM, BN, 1, 1, kFmtF16, kFmtBF16);
 #pragma unroll
   for (int c = 0; c < kStages - 1; ++c) {
     if (c < nchunks) load_chunk(c, c);
@@ -610,7 +619,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* _
       }
       f[e] = val;
     }
-    reinterpret_cast<uint4*>(img)[v] = pack8(f);
+    // forward image: fp16 (multiplied with fp16 activations); transposed (dgrad) image: bf16 (with bf16 gradients)
+    reinterpret_cast<uint4*>(img)[v] = transposed ? pack8(f) : pack8a(f);
   }
 }
 

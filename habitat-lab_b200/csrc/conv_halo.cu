@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(128) conv_halo_kernel(const HaloArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+  // forward: fp16 input halo x fp16 weight image; dgrad: bf16 gradients x bf16 flipped / transposed image
+  constexpr uint32_t idesc = MODE == 0 ? make_idesc_f16(128, N, 0, 0, kFmtF16, kFmtF16) : make_idesc_bf16(128, N, 0, 0);
 
   const int py = tid >> 3, px = tid & 7;  // this thread's output pixel within the tile (epilogue)
 
@@ -220,10 +221,17 @@ __global__ void __launch_bounds__(128) conv_halo_kernel(const HaloArgs a) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           uint4 u;
-          u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
-          u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
-          u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
-          u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          if (MODE == 0) {  // forward output y: fp16 (saturating)
+            u.x = pack_f16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+            u.y = pack_f16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+            u.z = pack_f16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+            u.w = pack_f16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          } else {          // data gradient: bf16
+            u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+            u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+            u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+            u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          }
           dst[v] = u;
         }
       }
@@ -318,7 +326,8 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+  // A = forward activations (fp16 halo), B = output gradients (bf16): mixed-format kind::f16 MMA
+  constexpr uint32_t idesc = make_idesc_f16(128, N, 1, 1, kFmtF16, kFmtBF16);
 
   for (int it = 0; it < my_n; ++it) {
     if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
@@ -376,6 +385,150 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// weight gradient of the 3x3 pad-1 stride-1 convs on SMALL images (8x8: layer3, 4x4: layer4 / compression).
+// The gather kernel (conv.cu) re-reads x once per tap and dy once per 128-row M tile through L2 (1.2 GB per launch
+// for a 128->128 layer: L2-gather-bound at ~10 % of the tensor roofline).  Here the halo scheme of the kernel above
+// is applied to a tile made of SEVERAL images: a 16x8 output tile = 16/IMG images stacked vertically, each with its
+// own zero-padding rows in the halo buffer (and, for 4x4 images, 4 zero "virtual" pixels per 8-pixel row whose dy is
+// zero), so x is loaded once per (channel slice) and every tap is a shifted descriptor.  Channels are sliced to keep
+// the 9 accumulators inside TMEM: a CTA owns 32 input channels (the three vertical taps x 32 channels = 96 rows of
+// one M = 128 tile) and NS output channels: accumulators = 3 horizontal taps x NS columns (NS = 128 -> 384).
+// grid = (tile workers, Ci/32 * Co/NS slices); results are accumulated into dw with vector red.add.
+// ------------------------------------------------------------------------------------------
+struct HaloWgradSmallArgs {
+  const act_t* x;     // [B, IMG, IMG, Ci]  fp16
+  const grad_t* dy;   // [B, IMG, IMG, Co]  bf16
+  float* dw;          // [(r*3+s)*Ci + ci][Co]
+  int B, Ci, Co, ntiles;
+};
+
+template <int NS, int IMG>
+__global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWgradSmallArgs a) {
+  constexpr int CJ = 4, KH = 3, KW = 3, HWD = TW + KW - 1;
+  constexpr int P = HWD * 16, RP = CJ * P;
+  constexpr int IPT = TH / IMG;                 // images per 16-row tile
+  constexpr int RPI = IMG + 2;                  // halo rows per image (own top / bottom padding row)
+  constexpr int HROWS_LOAD = IPT * RPI;
+  constexpr int HROWS = (IPT - 1) * RPI + (IMG - 2) + 1 + 4;   // last K16 base row + second K8 row + 4 row blocks (M padding)
+  constexpr int HROWS_A = HROWS > HROWS_LOAD ? HROWS : HROWS_LOAD;
+  constexpr int HALO_BYTES = HROWS_A * RP;
+  constexpr int DY_BYTES = 128 * NS * 2;
+  constexpr int STAGE = HALO_BYTES + DY_BYTES;
+  constexpr int TCOLS_RAW = KW * NS;
+  constexpr int TMEM_COLS = TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
+  static_assert(TCOLS_RAW <= 512, "accumulators exceed TMEM");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int nsl = a.Co / NS;
+  const int c_off = (blockIdx.y / nsl) * 32, n_off = (blockIdx.y % nsl) * NS;
+
+  if (tid == 0) {
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
+  // rows beyond the loaded ones are read by the (discarded) padding M rows: keep them finite
+  for (int st = 0; st < 2; ++st)
+    for (int v = tid; v < (HROWS_A - HROWS_LOAD) * RP / 16; v += 128) {
+      const uint32_t addr = sbase + st * STAGE + HROWS_LOAD * RP + v * 16;
+      asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
+    }
+  auto load_tile = [&](int tile, int st) {
+    const uint32_t sh = sbase + st * STAGE;
+    const int b0 = tile * IPT;
+    // x halo: [halo row][cj][halo col] 16-byte vectors; image j occupies halo rows j*RPI .. j*RPI + IMG + 1
+    for (int v = tid; v < HROWS_LOAD * CJ * HWD; v += 128) {
+      const int cj = v % CJ;
+      const int t = v / CJ;
+      const int hx = t % HWD, hy = t / HWD;
+      const int j = hy / RPI, ih = hy - j * RPI - 1, iw = hx - 1;
+      const int b = b0 + j;
+      const bool ok = b < a.B && ih >= 0 && ih < IMG && iw >= 0 && iw < IMG;
+      const act_t* g = ok ? a.x + ((((size_t)b * IMG + ih) * IMG + iw) * a.Ci + c_off + cj * 8) : a.x;
+      cp_async16(sh + (uint32_t)(((hy * CJ + cj) * HWD + hx) * 16), g, ok);
+    }
+    // dy tile: [n-chunk][py][px]; pixels px >= IMG are virtual (dy = 0)
+    const uint32_t sd = sh + HALO_BYTES;
+    for (int v = tid; v < 128 * (NS / 8); v += 128) {
+      const int nj = v % (NS / 8), p = v / (NS / 8);
+      const int ppy = p >> 3, ppx = p & 7;
+      const int j = ppy / IMG, y = ppy - j * IMG;
+      const int b = b0 + j;
+      const bool ok = b < a.B && ppx < IMG;
+      const grad_t* g = ok ? a.dy + ((((size_t)b * IMG + y) * IMG + ppx) * a.Co + n_off + nj * 8) : a.dy;
+      cp_async16(sd + (uint32_t)(nj * 128 + p) * 16, g, ok);
+    }
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  if (my_n > 0) load_tile(first, 0);
+  cp_async_commit();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  constexpr uint32_t idesc = make_idesc_f16(128, NS, 1, 1, kFmtF16, kFmtBF16);
+
+  for (int it = 0; it < my_n; ++it) {
+    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+    if (it + 1 < my_n) load_tile(first + (it + 1) * stride, (it + 1) & 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t sh = sbase + (it & 1) * STAGE;
+      const uint32_t sd = sh + HALO_BYTES;
+#pragma unroll
+      for (int s = 0; s < KW; ++s)
+#pragma unroll
+        for (int ks = 0; ks < TH / 2; ++ks) {
+          // K16 = tile rows 2ks, 2ks+1 (never straddle an image: IMG is even) -> halo rows hb, hb+1 (+ tap r in M)
+          const int hb = ((2 * ks) / IMG) * RPI + (2 * ks) % IMG;
+          const uint64_t da = make_smem_desc(sh + hb * RP + s * 16, RP, P, kNoSwizzle);
+          const uint64_t db = make_smem_desc(sd + 2 * ks * 128, 128, 128 * 16, kNoSwizzle);
+          mma_bf16_ss(tmem_base + (uint32_t)(s * NS), da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+      mma_commit(&mma_bar[it & 1]);
+    }
+  }
+  if (my_n > 0) {
+    mbar_wait(&mma_bar[(my_n - 1) & 1], ((my_n - 1) >> 1) & 1);
+    fence_after_sync();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int blk = tid >> 3;                  // row block (r, cj)
+    const int r = blk / CJ, cj = blk % CJ;
+    const bool ok = r < KH;
+#pragma unroll 1
+    for (int s = 0; s < KW; ++s) {
+      const size_t row = (size_t)(r * KW + s) * a.Ci + c_off + cj * 8 + (tid & 7);
+#pragma unroll 1
+      for (int col0 = 0; col0 < NS; col0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + (uint32_t)(s * NS + col0), rr);
+        tmem_ld_wait();
+        if (ok) {
+          float* dst = a.dw + row * a.Co + n_off + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(dst + j, __uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
+                       __uint_as_float(rr[j + 3]));
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // ---- weight image for the halo kernels: [tap][C/8][N][8] bf16 ---------------------------------
 // mode 0 forward: img[t=(r,s)][ci][n=co] = W[co][ci][r][s]
 // mode 1 dgrad  : img[t=(r,s)][k=co][n=ci] = W[co][ci][KH-1-r][KW-1-s]     (flipped taps, transposed)
@@ -404,7 +557,9 @@ __global__ void pack_halo_weight_kernel(const float* __restrict__ w, __nv_bfloat
       const int fr = 2 * r + dy - 1, fs = 2 * s + dx - 1;  // 7x7 filter coordinates
       if (c < ci_real && fr >= 0 && fr < 7 && fs >= 0 && fs < 7) v = w[(((size_t)n * ci_real + c) * 7 + fr) * 7 + fs];
     }
-    img[i] = __float2bfloat16(v);
+    // forward / stem images multiply fp16 activations -> fp16; the dgrad image multiplies bf16 gradients -> bf16
+    if (mode == 1) img[i] = __float2bfloat16(v);
+    else reinterpret_cast<__half*>(img)[i] = __float2half_rn(v);
   }
 }
 
@@ -495,7 +650,8 @@ conv_halo_tma_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  constexpr uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+  // forward: fp16 input halo x fp16 weight image; dgrad: bf16 gradients x bf16 flipped / transposed image
+  constexpr uint32_t idesc = MODE == 0 ? make_idesc_f16(128, N, 0, 0, kFmtF16, kFmtF16) : make_idesc_bf16(128, N, 0, 0);
   const int py = tid >> 3, px = tid & 7;
 
   for (int it = 0; it <= my_n; ++it) {
@@ -573,10 +729,17 @@ conv_halo_tma_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap)
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           uint4 u;
-          u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
-          u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
-          u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
-          u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          if (MODE == 0) {  // forward output y: fp16 (saturating)
+            u.x = pack_f16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+            u.y = pack_f16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+            u.z = pack_f16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+            u.w = pack_f16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          } else {          // data gradient: bf16
+            u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+            u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+            u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+            u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          }
           dst[v] = u;
         }
       }
@@ -686,6 +849,28 @@ static int launch_halo_wgrad(const HaloWgradArgs& a, cudaStream_t st) {
   count_launch(1);
   return HB200_OK;
 }
+
+template <int NS, int IMG>
+static int launch_halo_wgrad_small(const HaloWgradSmallArgs& a, cudaStream_t st) {
+  constexpr int RP = 4 * (TW + 2) * 16, IPT = TH / IMG, RPI = IMG + 2;
+  constexpr int HROWS_LOAD = IPT * RPI, HROWS = (IPT - 1) * RPI + (IMG - 2) + 1 + 4;
+  constexpr int HROWS_A = HROWS > HROWS_LOAD ? HROWS : HROWS_LOAD;
+  const size_t smem = 2 * (size_t)(HROWS_A * RP + 128 * NS * 2) + 256;
+  auto kern = conv_halo_wgrad_small_kernel<NS, IMG>;
+  static bool attr = false;
+  if (!attr) {
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const int slices = (a.Ci / 32) * (a.Co / NS);
+  int workers = kNumSMs / slices;            // one CTA per SM (3 x NS accumulator columns need most of TMEM)
+  if (workers < 1) workers = 1;
+  if (workers > a.ntiles) workers = a.ntiles;
+  kern<<<dim3(workers, slices), 128, smem, st>>>(a);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
 }  // namespace hb200
 
 using namespace hb200;
@@ -696,6 +881,12 @@ extern "C" int hb200_conv_halo_supported(int c, int n, int k, int h, int w) {
   if (k == 3) return (c == 32 && n == 32) || (c == 64 && n == 64);
   if (k == 4) return c == 16 && n == 32;
   return 0;
+}
+
+/* weight-gradient variant: additionally the small-image layers (8x8 / 4x4, channels sliced 32 x 128) */
+extern "C" int hb200_conv_halo_wgrad_supported(int c, int n, int k, int h, int w) {
+  if (hb200_conv_halo_supported(c, n, k, h, w)) return 1;
+  return k == 3 && c % 32 == 0 && n % 128 == 0 && h == w && (h == 8 || h == 4);
 }
 
 extern "C" int hb200_pack_halo_weight(const float* w_oihw, hb200_bf16* img, int co, int ci_real, int c, int n,
@@ -745,7 +936,15 @@ extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb20
 extern "C" int hb200_conv_halo_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc, int batch, int h,
                                      int w, int c, int n, int k, hb200_stream_t stream) {
   HB_CHECK_ARG(x && dy && dw_acc, "conv_halo_wgrad: null pointer");
-  HB_CHECK_ARG(hb200_conv_halo_supported(c, n, k, h, w), "conv_halo_wgrad: unsupported shape C=%d N=%d k=%d %dx%d", c, n, k, h, w);
+  HB_CHECK_ARG(hb200_conv_halo_wgrad_supported(c, n, k, h, w), "conv_halo_wgrad: unsupported shape C=%d N=%d k=%d %dx%d", c, n, k, h, w);
+  if (!hb200_conv_halo_supported(c, n, k, h, w)) {   // small images: several images per tile, sliced channels
+    HaloWgradSmallArgs s;
+    s.x = (const act_t*)x; s.dy = (const grad_t*)dy; s.dw = dw_acc;
+    s.B = batch; s.Ci = c; s.Co = n;
+    const int ipt = TH / h;
+    s.ntiles = (batch + ipt - 1) / ipt;
+    return h == 8 ? launch_halo_wgrad_small<128, 8>(s, (cudaStream_t)stream) : launch_halo_wgrad_small<128, 4>(s, (cudaStream_t)stream);
+  }
   HaloWgradArgs a;
   a.x = (const __nv_bfloat16*)x; a.dy = (const __nv_bfloat16*)dy; a.dw = dw_acc;
   a.B = batch; a.H = h; a.W = w;

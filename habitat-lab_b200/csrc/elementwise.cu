@@ -1,4 +1,5 @@
-// hb200 -- HBM-bound passes around the conv stack (all bf16 NHWC, 16-byte vectors):
+// hb200 -- HBM-bound passes around the conv stack (NHWC, 16-byte vectors; forward values fp16 = act_t, gradients
+// bf16 = grad_t, see common.cuh):
 // input prep (u8/f32 gather + 2x2 mean + running mean/var), GroupNorm apply / residual / maxpool,
 // GroupNorm backward (reduce + apply), maxpool backward, dtype converts, goal/action embeddings.
 #include "common.cuh"
@@ -105,6 +106,9 @@ prep_stats_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ dep
     const double b = block_sum((double)q[c], red);
     if (threadIdx.x == 0) { atomicAdd(&stats[c], a); atomicAdd(&stats[8 + c], b); }
   }
+  // frame count (the reference's new_count = x.size(0), running_mean_and_var.py:27,36): written on the device -- no
+  // pageable-host copy in the hot path, safe under stream capture
+  if (blockIdx.x == 0 && threadIdx.x == 0) stats[16] = (double)B;
 }
 
 // S2D: write the pooled image space-to-depth'd, [B, Hp/2, Wp/2, 16] with channel = (dy*2+dx)*4 + c
@@ -113,7 +117,7 @@ template <bool HAS_RGB, bool HAS_DEPTH, bool S2D>
 __global__ void __launch_bounds__(256)
 prep_apply_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ depth,
                   const int32_t* __restrict__ frame_rows, int B, int H, int W, float rgb_scale,
-                  const float* __restrict__ scale_shift, __nv_bfloat16* __restrict__ out) {
+                  const float* __restrict__ scale_shift, act_t* __restrict__ out) {
   const int Hp = H / 2, Wq = W / 8;
   const long long total = (long long)B * Hp * Wq;
   float sc[4] = {1, 1, 1, 1}, sh[4] = {0, 0, 0, 0};
@@ -138,7 +142,7 @@ prep_apply_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ dep
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           if (c < C) v[c] = fmaf(o[p][c], sc[c], sh[c]);
-        dst[p] = pack8(v);
+        dst[p] = pack8a(v);
       }
     } else {
       // pooled pixels (py, 4*px4 + p): s2d row i = py/2, dy = py&1; col j = 2*px4 + p/2, dx = p&1
@@ -151,7 +155,7 @@ prep_apply_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ dep
 #pragma unroll
           for (int c = 0; c < 4; ++c) v[dx * 4 + c] = (c < C) ? fmaf(o[2 * q + dx][c], sc[c], sh[c]) : 0.f;
         const size_t pix = ((size_t)f * (Hp / 2) + i2) * (W / 4) + (size_t)px4 * 2 + q;
-        *reinterpret_cast<uint4*>(out + pix * 16 + dy * 8) = pack8(v);
+        *reinterpret_cast<uint4*>(out + pix * 16 + dy * 8) = pack8a(v);
       }
     }
   }
@@ -254,7 +258,7 @@ __device__ __forceinline__ GnSlab gn_slab(int C, int hw, int ppb) {
 
 template <int OUT_F32>  // 0: bf16 NHWC, 1: f32 NHWC, 2: f32 flattened in (c, h, w) order (nn.Flatten of NCHW)
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ out, int B, int hw, int relu, int ppb) {
+gn_apply_kernel(const act_t* __restrict__ y, GnP p, void* __restrict__ out, int B, int hw, int relu, int ppb) {
   const GnSlab t = gn_slab(p.C, hw, ppb);
   const int cv = p.C >> 3;
   float mu[8], rs[8], ga[8], be[8], sc[8], sh[8];
@@ -266,7 +270,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ o
   for (int pix = t.pix0 + t.pl; pix < t.pix1; pix += t.npl) {
     const size_t i = ((size_t)t.b * hw + pix) * cv + t.vec;
     float x[8];
-    unpack8(reinterpret_cast<const uint4*>(y)[i], x);
+    unpack8a(reinterpret_cast<const uint4*>(y)[i], x);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float z = fmaf(x[e], sc[e], sh[e]);
@@ -281,14 +285,14 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ y, GnP p, void* __restrict__ o
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[(size_t)(t.c0 + e) * hw + pix] = x[e];
     } else {
-      reinterpret_cast<uint4*>(out)[i] = pack8(x);
+      reinterpret_cast<uint4*>(out)[i] = pack8a(x);
     }
   }
 }
 
 __global__ void __launch_bounds__(256)
-gn_residual_relu_kernel(const __nv_bfloat16* __restrict__ y, GnP p, const __nv_bfloat16* __restrict__ res,
-                        GnP rp, int res_is_prenorm, __nv_bfloat16* __restrict__ out, int B, int hw, int ppb) {
+gn_residual_relu_kernel(const act_t* __restrict__ y, GnP p, const act_t* __restrict__ res,
+                        GnP rp, int res_is_prenorm, act_t* __restrict__ out, int B, int hw, int ppb) {
   const GnSlab t = gn_slab(p.C, hw, ppb);
   const int cv = p.C >> 3;
   float mu[8], rs[8], ga[8], be[8], sc[8], sh[8], rsc[8], rsh[8];
@@ -307,16 +311,16 @@ gn_residual_relu_kernel(const __nv_bfloat16* __restrict__ y, GnP p, const __nv_b
   for (int pix = t.pix0 + t.pl; pix < t.pix1; pix += t.npl) {
     const size_t i = ((size_t)t.b * hw + pix) * cv + t.vec;
     float x[8], r[8];
-    unpack8(reinterpret_cast<const uint4*>(y)[i], x);
-    unpack8(reinterpret_cast<const uint4*>(res)[i], r);
+    unpack8a(reinterpret_cast<const uint4*>(y)[i], x);
+    unpack8a(reinterpret_cast<const uint4*>(res)[i], r);
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], sc[e], sh[e]) + fmaf(r[e], rsc[e], rsh[e]), 0.f);
-    reinterpret_cast<uint4*>(out)[i] = pack8(x);
+    reinterpret_cast<uint4*>(out)[i] = pack8a(x);
   }
 }
 
 __global__ void __launch_bounds__(256)
-gn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfloat16* __restrict__ out,
+gn_relu_maxpool_kernel(const act_t* __restrict__ y, GnP p, act_t* __restrict__ out,
                        uint8_t* __restrict__ argmax, int B, int H, int W) {
   const int cv = p.C >> 3, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * Wo * cv;
@@ -344,7 +348,7 @@ gn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfloat16
         const int ix = 2 * ox - 1 + s;
         if (ix < 0 || ix >= W) continue;
         float x[8];
-        unpack8(*reinterpret_cast<const uint4*>(y + (((size_t)b * H + iy) * W + ix) * p.C + c0), x);
+        unpack8a(*reinterpret_cast<const uint4*>(y + (((size_t)b * H + iy) * W + ix) * p.C + c0), x);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float z = fmaxf(fmaf((x[e] - mu[e]) * rs[e], ga[e], be[e]), 0.f);
@@ -352,7 +356,7 @@ gn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfloat16
         }
       }
     }
-    reinterpret_cast<uint4*>(out)[i] = pack8(best);
+    reinterpret_cast<uint4*>(out)[i] = pack8a(best);
     uint2 a;
     a.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
     a.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
@@ -365,7 +369,7 @@ gn_relu_maxpool_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfloat16
 // window maximum is taken on x * sign(rstd*gamma) (the affine map is monotonic per channel) and the affine + ReLU
 // applied once per output.
 __global__ void __launch_bounds__(256)
-gn_relu_maxpool_slab_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfloat16* __restrict__ out,
+gn_relu_maxpool_slab_kernel(const act_t* __restrict__ y, GnP p, act_t* __restrict__ out,
                             uint8_t* __restrict__ argmax, int H, int W, int rows) {
   extern __shared__ __align__(16) uint8_t gsm[];
   uint4* sy = reinterpret_cast<uint4*>(gsm);
@@ -416,7 +420,7 @@ gn_relu_maxpool_slab_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfl
         const int ix = 2 * ox - 1 + s;
         if (ix < 0) continue;
         float x[8];
-        unpack8(sy[(lr * W + ix) * cv + vec], x);
+        unpack8a(sy[(lr * W + ix) * cv + vec], x);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float xs = x[e] * sg[e];
@@ -427,7 +431,7 @@ gn_relu_maxpool_slab_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfl
     float z[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) z[e] = fmaxf(fmaf(best[e], za[e], zd[e]), 0.f);
-    o4[it] = pack8(z);
+    o4[it] = pack8a(z);
     uint2 a;
     a.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
     a.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
@@ -436,8 +440,8 @@ gn_relu_maxpool_slab_kernel(const __nv_bfloat16* __restrict__ y, GnP p, __nv_bfl
 }
 
 __global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax,
-                   __nv_bfloat16* __restrict__ dz, int B, int H, int W, int C) {
+maxpool_bwd_kernel(const grad_t* __restrict__ dout, const uint8_t* __restrict__ argmax,
+                   grad_t* __restrict__ dz, int B, int H, int W, int C) {
   const int cv = C >> 3, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * H * W * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -490,8 +494,8 @@ __device__ __forceinline__ void gn_masked_grad(int mask_mode, const float (&g)[8
 }
 
 __global__ void __launch_bounds__(256)
-gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act,
-                     const __nv_bfloat16* __restrict__ y, GnP p, float* __restrict__ sums,
+gn_bwd_reduce_kernel(const grad_t* __restrict__ g, const act_t* __restrict__ act,
+                     const act_t* __restrict__ y, GnP p, float* __restrict__ sums,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int hw,
                      int pix_per_block, int mask_mode) {
   // block = (frame b, pixel slab); thread = (pixel lane, channel vector)
@@ -512,8 +516,8 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
     const size_t o = ((size_t)b * hw + pix) * cv + vec;
     float gg[8], x[8], z[8], ac[8], gz[8];
     unpack8(reinterpret_cast<const uint4*>(g)[o], gg);
-    unpack8(reinterpret_cast<const uint4*>(y)[o], x);
-    if (mask_mode == 2) unpack8(reinterpret_cast<const uint4*>(act)[o], ac);
+    unpack8a(reinterpret_cast<const uint4*>(y)[o], x);
+    if (mask_mode == 2) unpack8a(reinterpret_cast<const uint4*>(act)[o], ac);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       x[e] = (x[e] - mu[e]) * rs[e];
@@ -542,9 +546,9 @@ gn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
 }
 
 __global__ void __launch_bounds__(256)
-gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act,
-                    const __nv_bfloat16* __restrict__ y, GnP p, const float* __restrict__ sums,
-                    __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ gz_out, int B, int hw,
+gn_bwd_apply_kernel(const grad_t* __restrict__ g, const act_t* __restrict__ act,
+                    const act_t* __restrict__ y, GnP p, const float* __restrict__ sums,
+                    grad_t* __restrict__ dy, grad_t* __restrict__ gz_out, int B, int hw,
                     int mask_mode, int ppb) {
   const GnSlab t = gn_slab(p.C, hw, ppb);
   const int cv = p.C >> 3;
@@ -564,8 +568,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
     const size_t i = ((size_t)t.b * hw + pix) * cv + t.vec;
     float gg[8], x[8], z[8], ac[8], gz[8], o[8];
     unpack8(reinterpret_cast<const uint4*>(g)[i], gg);
-    unpack8(reinterpret_cast<const uint4*>(y)[i], x);
-    if (mask_mode == 2) unpack8(reinterpret_cast<const uint4*>(act)[i], ac);
+    unpack8a(reinterpret_cast<const uint4*>(y)[i], x);
+    if (mask_mode == 2) unpack8a(reinterpret_cast<const uint4*>(act)[i], ac);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       x[e] = (x[e] - mu[e]) * rs[e];
@@ -669,10 +673,10 @@ __device__ __forceinline__ void gn_bwd_cluster_sums(cg::cluster_group& cluster, 
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 4)
-gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act,
-                      const __nv_bfloat16* __restrict__ y, GnP p, float* __restrict__ dgamma,
-                      float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dy,
-                      __nv_bfloat16* __restrict__ gz_out, int hw, int ppc) {
+gn_bwd_cluster_kernel(const grad_t* __restrict__ g, const act_t* __restrict__ act,
+                      const act_t* __restrict__ y, GnP p, float* __restrict__ dgamma,
+                      float* __restrict__ dbeta, grad_t* __restrict__ dy,
+                      grad_t* __restrict__ gz_out, int hw, int ppc) {
   extern __shared__ __align__(16) uint8_t gsm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
@@ -719,8 +723,8 @@ gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* 
   for (int i = tid; i < n; i += 256) {
     float gg[8], x[8], ac[8];
     unpack8(sg[i], gg);
-    unpack8(sy[i], x);
-    if (MODE == 2) unpack8(sact[i], ac);
+    unpack8a(sy[i], x);
+    if (MODE == 2) unpack8a(sact[i], ac);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float gz = gg[e];
@@ -737,8 +741,8 @@ gn_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* 
   for (int i = tid; i < n; i += 256) {
     float gg[8], x[8], ac[8], gz[8], o[8];
     unpack8(sg[i], gg);
-    unpack8(sy[i], x);
-    if (MODE == 2) unpack8(sact[i], ac);
+    unpack8a(sy[i], x);
+    if (MODE == 2) unpack8a(sact[i], ac);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       gz[e] = gg[e];
@@ -790,9 +794,9 @@ __device__ __forceinline__ void pool_route_px(const uint4* __restrict__ sdp, con
 }
 
 __global__ void __launch_bounds__(256, 3)
-gn_pool_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_t* __restrict__ argmax,
-                           const __nv_bfloat16* __restrict__ y, GnP p, float* __restrict__ dgamma,
-                           float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dy, int H, int W, int rows) {
+gn_pool_bwd_cluster_kernel(const grad_t* __restrict__ dpool, const uint8_t* __restrict__ argmax,
+                           const act_t* __restrict__ y, GnP p, float* __restrict__ dgamma,
+                           float* __restrict__ dbeta, grad_t* __restrict__ dy, int H, int W, int rows) {
   extern __shared__ __align__(16) uint8_t gsm[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
@@ -843,7 +847,7 @@ gn_pool_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_
     float gz[8], x[8];                                                                 \
     pool_route_px<DY, DX>(sdp, sarg, o00, wrow, cv, row_ok, col_ok, gz);               \
     const int yi = ((2 * kb + DY) * W + 2 * j + DX) * cv + vec;                        \
-    unpack8(sy[yi], x);                                                                \
+    unpack8a(sy[yi], x);                                                                \
     BODY                                                                               \
   }
   for (int it = tid; it < nblk; it += 256) {
@@ -891,10 +895,10 @@ gn_pool_bwd_cluster_kernel(const __nv_bfloat16* __restrict__ dpool, const uint8_
 // gz).  Compared with gn_bwd_reduce + gn_bwd_apply this removes one full HBM read of every operand, the
 // per-(frame,group) atomics and a launch + memset per layer.
 __global__ void __launch_bounds__(256)
-gn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ act,
-                    const __nv_bfloat16* __restrict__ y, GnP p, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, __nv_bfloat16* __restrict__ dy,
-                    __nv_bfloat16* __restrict__ gz_out, int B, int hw, int mask_mode) {
+gn_bwd_fused_kernel(const grad_t* __restrict__ g, const act_t* __restrict__ act,
+                    const act_t* __restrict__ y, GnP p, float* __restrict__ dgamma,
+                    float* __restrict__ dbeta, grad_t* __restrict__ dy,
+                    grad_t* __restrict__ gz_out, int B, int hw, int mask_mode) {
   __shared__ float sa[256][9], sb[256][9];
   extern __shared__ float dyn[];  // [C] gamma*a, [C] gamma*b, [G] S1, [G] S2
   float* ch_a = dyn;
@@ -929,8 +933,8 @@ gn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
       if (pix + u * npl >= hw) continue;
       float gg[8], x[8], z[8], ac[8], gz[8];
       unpack8(G[u], gg);
-      unpack8(Y[u], x);
-      if (mask_mode == 2) unpack8(A[u], ac);
+      unpack8a(Y[u], x);
+      if (mask_mode == 2) unpack8a(A[u], ac);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         x[e] = (x[e] - mu[e]) * rs[e];
@@ -991,8 +995,8 @@ gn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
       const size_t o = ((size_t)b * hw + pp) * cv + vec;
       float gg[8], x[8], z[8], ac[8], gz[8], out[8];
       unpack8(G[u], gg);
-      unpack8(Y[u], x);
-      if (mask_mode == 2) unpack8(A[u], ac);
+      unpack8a(Y[u], x);
+      if (mask_mode == 2) unpack8a(A[u], ac);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         x[e] = (x[e] - mu[e]) * rs[e];
@@ -1198,7 +1202,7 @@ __global__ void transpose_f32_kernel(const float* __restrict__ src, long long ld
 // (simple_cnn.py:139-157).  One thread per pixel.
 __global__ void prep_plain_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ depth,
                                   const int32_t* __restrict__ rows, long long npix_per_frame, int B, int c_rgb,
-                                  int c_depth, __nv_bfloat16* __restrict__ out) {
+                                  int c_depth, act_t* __restrict__ out) {
   const long long total = (long long)B * npix_per_frame;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1208,13 +1212,13 @@ __global__ void prep_plain_kernel(const uint8_t* __restrict__ rgb, const float* 
     float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int c = 0; c < c_rgb; ++c) v[c] = (float)rgb[src * c_rgb + c] / 255.0f;
     for (int c = 0; c < c_depth; ++c) v[c_rgb + c] = depth[src * c_depth + c];
-    reinterpret_cast<uint4*>(out)[i] = pack8(v);
+    reinterpret_cast<uint4*>(out)[i] = pack8a(v);
   }
 }
 // backward of (conv + bias) -> ReLU: dy = g * (out > 0); dbias[c] += sum dy   (out = post-ReLU activation)
 __global__ void __launch_bounds__(256)
-relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ out, int use_mask,
-                     __nv_bfloat16* __restrict__ dy, float* __restrict__ dbias, long long npix, int C) {
+relu_bias_bwd_kernel(const grad_t* __restrict__ g, const act_t* __restrict__ out, int use_mask,
+                     grad_t* __restrict__ dy, float* __restrict__ dbias, long long npix, int C) {
   __shared__ float sacc[256][9];
   const int cv = C >> 3;
   const int vec = threadIdx.x % cv, pl = threadIdx.x / cv, npl = blockDim.x / cv;
@@ -1224,7 +1228,7 @@ relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
     float gg[8], oo[8];
     unpack8(reinterpret_cast<const uint4*>(g)[o], gg);
     if (use_mask) {
-      unpack8(reinterpret_cast<const uint4*>(out)[o], oo);
+      unpack8a(reinterpret_cast<const uint4*>(out)[o], oo);
 #pragma unroll
       for (int e = 0; e < 8; ++e) gg[e] = oo[e] > 0.f ? gg[e] : 0.f;
     }
@@ -1242,7 +1246,7 @@ relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* _
   }
 }
 // bf16 NHWC [B,hw,C] -> f32 [B, C*hw] flattened in (c,h,w) order (nn.Flatten of the NCHW map)
-__global__ void bf16_hwc_to_f32_chw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int B,
+__global__ void bf16_hwc_to_f32_chw_kernel(const act_t* __restrict__ x, float* __restrict__ out, int B,
                                            int hw, int C) {
   const int cv = C >> 3;
   const long long total = (long long)B * hw * cv;
@@ -1253,7 +1257,7 @@ __global__ void bf16_hwc_to_f32_chw_kernel(const __nv_bfloat16* __restrict__ x, 
     const int p = (int)(t % hw);
     const int b = (int)(t / hw);
     float f[8];
-    unpack8(reinterpret_cast<const uint4*>(x)[i], f);
+    unpack8a(reinterpret_cast<const uint4*>(x)[i], f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) out[((size_t)b * C + c0 + e) * hw + p] = f[e];
   }
@@ -1304,9 +1308,6 @@ extern "C" int hb200_prep_stats(const uint8_t* rgb, const float* depth, const in
   else if (c_rgb) prep_stats_kernel<true, false><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, stats_acc);
   else prep_stats_kernel<false, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, stats_acc);
   HB_LAUNCH_OK();
-  // frame count (the reference's new_count = x.size(0), running_mean_and_var.py:27,36)
-  const double frames = (double)batch;
-  HB_CUDA(cudaMemcpyAsync(stats_acc + 16, &frames, sizeof(double), cudaMemcpyHostToDevice, st));
   count_launch(1);
   return HB200_OK;
 }
@@ -1333,7 +1334,7 @@ extern "C" int hb200_prep_apply(const uint8_t* rgb, const float* depth, const in
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = (long long)batch * (height / 2) * (width / 8);
   const int grid = grid_for(total, 256);
-  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  act_t* o = (act_t*)out;
   HB_CHECK_ARG(!s2d || (height % 4 == 0), "prep_apply: s2d needs H %% 4 == 0");
 #define HB_PREP(R, D)                                                                                              \
   if (s2d) prep_apply_kernel<R, D, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o); \
@@ -1358,11 +1359,11 @@ extern "C" int hb200_gn_apply(const hb200_bf16* y, const double* stats, const fl
   rc = gn_slab_launch(channels, hw, batch, &ppb, &grid);
   if (rc) return rc;
   if (out_f32 == 1)
-    gn_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu, ppb);
+    gn_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)y, p, out, batch, hw, relu, ppb);
   else if (out_f32 == 2)
-    gn_apply_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu, ppb);
+    gn_apply_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)y, p, out, batch, hw, relu, ppb);
   else
-    gn_apply_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, out, batch, hw, relu, ppb);
+    gn_apply_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)y, p, out, batch, hw, relu, ppb);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1386,7 +1387,7 @@ extern "C" int hb200_gn_residual_relu(const hb200_bf16* y, const double* stats, 
   rc = gn_slab_launch(channels, hw, batch, &ppb, &grid);
   if (rc) return rc;
   gn_residual_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)y, p, (const __nv_bfloat16*)res, rp, res_stats ? 1 : 0, (__nv_bfloat16*)out, batch, hw, ppb);
+      (const act_t*)y, p, (const act_t*)res, rp, res_stats ? 1 : 0, (act_t*)out, batch, hw, ppb);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1410,7 +1411,7 @@ extern "C" int hb200_gn_relu_maxpool(const hb200_bf16* y, const double* stats, c
       const size_t smem = (size_t)(rows + 1) * w * channels * 2;
       auto kern = gn_relu_maxpool_slab_kernel;
       HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<batch * (h / rows), 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)y, p, (__nv_bfloat16*)out,
+      kern<<<batch * (h / rows), 256, smem, (cudaStream_t)stream>>>((const act_t*)y, p, (act_t*)out,
                                                                     argmax, h, w, rows);
       HB_LAUNCH_OK();
       count_launch(1);
@@ -1419,7 +1420,7 @@ extern "C" int hb200_gn_relu_maxpool(const hb200_bf16* y, const double* stats, c
   }
   const long long total = (long long)batch * (h / 2) * (w / 2) * (channels / 8);
   gn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)y, p, (__nv_bfloat16*)out, argmax, batch, h, w);
+      (const act_t*)y, p, (act_t*)out, argmax, batch, h, w);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1430,7 +1431,7 @@ extern "C" int hb200_maxpool_bwd(const hb200_bf16* dout, const uint8_t* argmax, 
   HB_CHECK_ARG(dout && argmax && dz && channels % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_bwd: bad args");
   const long long total = (long long)batch * h * w * (channels / 8);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dout, argmax, (__nv_bfloat16*)dz, batch, h, w, channels);
+      (const grad_t*)dout, argmax, (grad_t*)dz, batch, h, w, channels);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1453,8 +1454,8 @@ extern "C" int hb200_gn_bwd_reduce(const hb200_bf16* g, const hb200_bf16* act, c
   int ppb = npl * 16;  // 16 pixels per thread
   if (ppb > hw) ppb = hw;
   const int slabs = (hw + ppb - 1) / ppb;
-  gn_bwd_reduce_kernel<<<batch * slabs, 256, 0, st>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)act,
-                                                      (const __nv_bfloat16*)y, p, sums, dgamma, dbeta,
+  gn_bwd_reduce_kernel<<<batch * slabs, 256, 0, st>>>((const grad_t*)g, (const act_t*)act,
+                                                      (const act_t*)y, p, sums, dgamma, dbeta,
                                                       batch, hw, ppb, mask_mode);
   HB_LAUNCH_OK();
   count_launch(1);
@@ -1475,8 +1476,8 @@ extern "C" int hb200_gn_bwd_apply(const hb200_bf16* g, const hb200_bf16* act, co
   rc = gn_slab_launch(channels, hw, batch, &ppb, &grid);
   if (rc) return rc;
   gn_bwd_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)g, (const __nv_bfloat16*)act, (const __nv_bfloat16*)y, p, sums,
-      (__nv_bfloat16*)dy, (__nv_bfloat16*)gz_out, batch, hw, mask_mode, ppb);
+      (const grad_t*)g, (const act_t*)act, (const act_t*)y, p, sums,
+      (grad_t*)dy, (grad_t*)gz_out, batch, hw, mask_mode, ppb);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1607,8 +1608,9 @@ extern "C" int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb
       at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      const __nv_bfloat16 *G_ = (const __nv_bfloat16*)g, *A_ = (const __nv_bfloat16*)act, *Y_ = (const __nv_bfloat16*)y;
-      __nv_bfloat16 *D_ = (__nv_bfloat16*)dy, *Z_ = (__nv_bfloat16*)gz_out;
+      const grad_t* G_ = (const grad_t*)g;
+      const act_t *A_ = (const act_t*)act, *Y_ = (const act_t*)y;
+      grad_t *D_ = (grad_t*)dy, *Z_ = (grad_t*)gz_out;
 #define HB_GNB_CASE(m)                                                                                       \
   {                                                                                                          \
     auto kern = gn_bwd_cluster_kernel<m>;                                                                    \
@@ -1623,8 +1625,8 @@ extern "C" int hb200_gn_bwd(const hb200_bf16* g, const hb200_bf16* act, const hb
   }
   const size_t smem = sizeof(float) * (2 * (size_t)channels + 2 * (size_t)groups);
   gn_bwd_fused_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)g, (const __nv_bfloat16*)act, (const __nv_bfloat16*)y, p, dgamma, dbeta,
-      (__nv_bfloat16*)dy, (__nv_bfloat16*)gz_out, batch, hw, mask_mode);
+      (const grad_t*)g, (const act_t*)act, (const act_t*)y, p, dgamma, dbeta,
+      (grad_t*)dy, (grad_t*)gz_out, batch, hw, mask_mode);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1681,8 +1683,8 @@ extern "C" int hb200_gn_relu_maxpool_bwd(const hb200_bf16* dpool, const uint8_t*
   cfg.numAttrs = 1;
   auto kern = gn_pool_bwd_cluster_kernel;
   HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  HB_CUDA(cudaLaunchKernelEx(&cfg, kern, (const __nv_bfloat16*)dpool, argmax, (const __nv_bfloat16*)y, p, dgamma, dbeta,
-                             (__nv_bfloat16*)dy, h, w, rows));
+  HB_CUDA(cudaLaunchKernelEx(&cfg, kern, (const grad_t*)dpool, argmax, (const act_t*)y, p, dgamma, dbeta,
+                             (grad_t*)dy, h, w, rows));
   count_launch(1);
   return HB200_OK;
 }
@@ -1705,7 +1707,7 @@ extern "C" int hb200_prep_plain(const uint8_t* rgb, const float* depth, const in
   const long long total = (long long)batch * height * width;
   prep_plain_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(rgb, depth, frame_rows,
                                                                             (long long)height * width, batch, c_rgb,
-                                                                            c_depth, (__nv_bfloat16*)out);
+                                                                            c_depth, (act_t*)out);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1716,8 +1718,8 @@ extern "C" int hb200_relu_bias_bwd(const hb200_bf16* g, const hb200_bf16* out, h
   int grid = (int)((npix + 255) / 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   if (grid < 1) grid = 1;
-  relu_bias_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)g, (const __nv_bfloat16*)out,
-                                                               out != nullptr, (__nv_bfloat16*)dy, dbias, npix, channels);
+  relu_bias_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const grad_t*)g, (const act_t*)out,
+                                                               out != nullptr, (grad_t*)dy, dbias, npix, channels);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1726,7 +1728,7 @@ extern "C" int hb200_bf16_hwc_to_f32_chw(const hb200_bf16* x, float* out, int ba
                                          hb200_stream_t stream) {
   HB_CHECK_ARG(x && out && batch > 0 && hw > 0 && channels % 8 == 0, "bf16_hwc_to_f32_chw: bad args");
   const long long total = (long long)batch * hw * (channels / 8);
-  bf16_hwc_to_f32_chw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, batch, hw, channels);
+  bf16_hwc_to_f32_chw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const act_t*)x, out, batch, hw, channels);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;

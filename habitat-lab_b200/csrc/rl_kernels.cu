@@ -339,7 +339,9 @@ ppo_loss_main_kernel(const float* __restrict__ feat, const float* __restrict__ w
       if (a < A) se += expf(z[a] - mx);
     const float lse = mx + logf(se);
     const int act = (int)actions[f];
-    float logp[kMaxA], prob[kMaxA], ent = 0.f, lp = 0.f;
+    // an action outside [0, A) has no log-probability (torch's gather device-asserts): poison the frame with NaN so
+    // the loss and every metric show it instead of silently using log_prob = 0
+    float logp[kMaxA], prob[kMaxA], ent = 0.f, lp = (act >= 0 && act < A) ? 0.f : __int_as_float(0x7fc00000);
 #pragma unroll
     for (int a = 0; a < kMaxA; ++a) {
       if (a < A) {

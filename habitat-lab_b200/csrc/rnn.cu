@@ -208,9 +208,17 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
-    const long long t0 = clock64();
+    // The launch is cooperative (all CTAs co-resident), so the wait always ends; the bound only turns a programming
+    // error into a launch failure instead of a hung box.  It is WALL-CLOCK (globaltimer) and generous (30 s): time
+    // slicing, MPS, a debugger or profiler replay may stretch a healthy barrier far beyond any cycle budget.
+    unsigned long long t0 = 0, now;
+    unsigned spins = 0;
     while (ld_acquire_u32(counter) < target) {
-      if (clock64() - t0 > 4000000000ll) __trap();  // bounded: a lost CTA errors out instead of hanging
+      if ((++spins & 0xFFFu) == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 30000000000ull) __trap();
+      }
     }
     __threadfence();
   }

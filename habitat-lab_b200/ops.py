@@ -11,6 +11,7 @@ from . import _lib
 from ._lib import ConvShape, call, load, ptr
 
 BF16 = torch.bfloat16
+F16 = torch.float16
 N_METRICS = 12
 METRIC_KEYS = ("value_loss", "action_loss", "dist_entropy", "value_pred_min", "value_pred_mean",
                "value_pred_max", "prob_ratio_min", "prob_ratio_mean", "prob_ratio_max",
@@ -115,7 +116,7 @@ def pack_conv_weight(w_oihw: torch.Tensor, ci_pad: int, want_t: bool = True):
     co, ci_real, kh, kw = w_oihw.shape
     _chk(w_oihw, torch.float32, "w_oihw")
     dev = w_oihw.device
-    wp = torch.empty(packed_weight_elems(co, ci_pad, kh, kw), dtype=BF16, device=dev)
+    wp = torch.empty(packed_weight_elems(co, ci_pad, kh, kw), dtype=F16, device=dev)   # forward image: fp16
     wt = torch.empty(packed_weight_elems(ci_pad, co, kh, kw), dtype=BF16, device=dev) if want_t else None
     call("hb200_pack_conv_weight", ptr(w_oihw), ptr(wp), ptr(wt), co, ci_real, ci_pad, kh, kw)
     return wp, wt
@@ -161,6 +162,10 @@ def unpack_conv_wgrad(dw_acc, dw_oihw, ci_pad):
 
 def conv_halo_supported(c, n, k, h, w) -> bool:
     return bool(load().hb200_conv_halo_supported(c, n, k, h, w))
+
+
+def conv_halo_wgrad_supported(c, n, k, h, w) -> bool:
+    return bool(load().hb200_conv_halo_wgrad_supported(c, n, k, h, w))
 
 
 def pack_halo_weight(w_oihw, img, c, n, k, mode):
@@ -247,7 +252,9 @@ _scratch = {}
 
 
 def _scratch_f32(tag, shape, device):
-    key = (tag, tuple(shape), device)
+    # keyed by the CURRENT STREAM too: weight-gradient GEMMs run on a side stream while the main stream may stage
+    # another transpose of the same shape (two streams must never share a staging buffer)
+    key = (tag, tuple(shape), device, torch.cuda.current_stream(device).cuda_stream)
     t = _scratch.get(key)
     if t is None:
         t = torch.empty(*shape, device=device)

@@ -12,7 +12,7 @@ from torch import nn
 
 from .. import ops
 from ..common.baseline_registry import baseline_registry
-from .resnet_policy import BF16, POINTGOAL_UUID, NativeNetPolicy, _GRUStateEncoder
+from .resnet_policy import BF16, F16, POINTGOAL_UUID, NativeNetPolicy, _GRUStateEncoder
 
 
 class SimpleCNN(nn.Module):
@@ -101,10 +101,11 @@ class PointNavBaselinePolicy(NativeNetPolicy):
         if key in self._ws and self._ws[key]["x0"].device == dev:
             return self._ws[key]
         convs, fc, dims = self._layers()
-        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
-        ws = {"x0": e(B, *dims[0], 8)}
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731  (gradients)
+        ea = lambda *s: torch.empty(*s, dtype=F16, device=dev)  # noqa: E731  (forward values)
+        ws = {"x0": ea(B, *dims[0], 8)}
         for i, c in enumerate(convs):
-            ws[f"a{i}"] = e(B, *dims[i + 1], c.out_channels)
+            ws[f"a{i}"] = ea(B, *dims[i + 1], c.out_channels)
         ws["flat"] = torch.empty(B, fc.in_features, device=dev)
         if train:
             for i, c in enumerate(convs):
@@ -121,7 +122,7 @@ class PointNavBaselinePolicy(NativeNetPolicy):
             for i, c in enumerate(convs):
                 co, ci, k, _ = c.weight.shape
                 cip = 8 if i == 0 else ci
-                wp = torch.empty(ops.packed_weight_elems(co, cip, k, k), dtype=BF16, device=dev)
+                wp = torch.empty(ops.packed_weight_elems(co, cip, k, k), dtype=F16, device=dev)
                 wt = torch.empty(ops.packed_weight_elems(cip, co, k, k), dtype=BF16, device=dev) if i > 0 else None
                 acc = torch.empty(k * k * cip, co, device=dev)
                 self._wimgs.append((wp, wt, acc, cip))

@@ -132,14 +132,28 @@ class PPO(nn.Module):
             adv, stats = fused
         if not self.use_normalized_advantage:
             return adv
-        mean_var = self._compute_var_mean(adv, stats)
+        if self._var_mean_overridden():   # a subclass supplied its own statistic (reference signature: x -> (var, mean))
+            var, mean = self._compute_var_mean(adv[torch.isfinite(adv)])
+            mean_var = torch.stack([mean.reshape(()), var.reshape(())]).float()
+        else:
+            mean_var = self._fused_var_mean(stats)
         ops.adv_normalize(adv, stats=stats if mean_var is None else None, mean_var=mean_var)
         if hasattr(rollouts, "_adv_valid"):
             rollouts._adv_valid = False  # normalised in place: must be recomputed next time
         return adv
 
-    def _compute_var_mean(self, adv, stats):
-        """None -> single-process unbiased torch.var_mean, evaluated inside the normalise kernel."""
+    @staticmethod
+    def _compute_var_mean(x):
+        """The reference's overridable statistic (rl/ppo/ppo.py:160-162): (var, mean) of the finite advantages."""
+        return torch.var_mean(x)
+
+    def _var_mean_overridden(self) -> bool:
+        fn = getattr(type(self)._compute_var_mean, "__func__", type(self)._compute_var_mean)
+        return fn not in (PPO.__dict__["_compute_var_mean"].__func__, DDPPO.__dict__["_compute_var_mean"].__func__)
+
+    def _fused_var_mean(self, stats):
+        """None -> single-process unbiased torch.var_mean, evaluated inside the normalise kernel from the
+        (sum, sumsq, n) the GAE launch already produced."""
         return None
 
     def _set_grads_to_none(self):
@@ -167,6 +181,10 @@ class PPO(nn.Module):
 
     def after_step(self) -> None:
         pass
+
+    def after_update(self) -> None:
+        """Hook the agent access manager calls once per update (rl/ppo/updater.py; a no-op for PPO, the Lagrangian
+        entropy coefficient of continuous-control policies clamps itself here in the reference)."""
 
     # ---- whole update (ppo.py:301-332) --------------------------------------------------------------------
     def update(self, rollouts) -> Dict[str, float]:
@@ -234,7 +252,21 @@ class DDPPO(PPO):
             dist.broadcast(b, src=0)
         ac.mark_weights_changed()
 
-    def _compute_var_mean(self, adv, stats):
+    @staticmethod
+    def _compute_var_mean(x):
+        """distributed_var_mean with the reference's signature and collectives (ddppo.py:59-84, 103-105); the built-in
+        path below gets the same numbers from one packed all-reduce."""
+        import torch.distributed as dist
+
+        world = dist.get_world_size()
+        mean = x.mean()
+        dist.all_reduce(mean)
+        mean = mean / world
+        var = (x - mean).pow(2).mean()
+        dist.all_reduce(var)
+        return var / world, mean
+
+    def _fused_var_mean(self, stats):
         """distributed_var_mean (ddppo.py:59-84): mean of the rank means, mean of the rank BIASED
         variances around the global mean -- reproduced with one packed all-reduce of (sum, sumsq, n)
         partial statistics per rank instead of two dependent scalar all-reduces."""

@@ -23,9 +23,12 @@ from ..common.baseline_registry import baseline_registry
 from ..common.rollout_storage import RolloutStorage
 from ..common.tensor_dict import TensorDict
 from ..synthetic import pointnav_spaces
-from .ppo import DDPPO, PPO
+import os
+
+from .ppo import DDPPO, PPO  # noqa: F401  (registers the updaters)
 from . import policy as _policy  # noqa: F401  (registers PointNavBaselinePolicy)
-from .resnet_policy import PointNavResNetPolicy
+from .resnet_policy import PointNavResNetPolicy  # noqa: F401
+from .single_agent_access_mgr import SingleAgentAccessMgr
 
 
 # ---- config (field names and defaults: habitat_baselines/config/default_structured_configs.py:288-363) ----
@@ -70,7 +73,8 @@ def make_config(num_environments=4, total_num_steps=-1.0, num_updates=2, height=
     hb = SimpleNamespace(
         trainer_name="ddppo", updater_name="PPO", distrib_updater_name="DDPPO", rollout_storage_name="RolloutStorage",
         num_environments=num_environments, total_num_steps=total_num_steps, num_updates=num_updates,
-        log_interval=10, force_blind_policy=False,
+        log_interval=10, force_blind_policy=False, num_checkpoints=-1, checkpoint_interval=-1,
+        checkpoint_folder="data/checkpoints",
         rl=SimpleNamespace(ppo=ppo, ddppo=DDPPOConfig(), policy={"main_agent": SimpleNamespace(
             name="PointNavResNetPolicy", action_distribution_type="categorical")}),
         eval=SimpleNamespace(extra_sim_sensors={}),
@@ -118,6 +122,29 @@ class SyntheticVectorEnv:
         dones = torch.rand(n, generator=g, device=d) < self.p_done
         rewards = torch.randn(n, 1, generator=g, device=d) * 0.1 + 2.5 * dones.float().view(n, 1)
         return self._obs(), rewards, dones, [{} for _ in range(n)]
+
+    # -- the per-environment surface the REFERENCE's trainer drives (ppo_trainer.py:388, 409-419, 266-267):
+    #    async_step_at(i, a) for every env of a buffer, then wait_step_at(i) -> (obs, reward, done, info), post_step(obs)
+    def async_step_at(self, index_env: int, action) -> None:
+        if self._pending is None:
+            self._pending = {"n": 0, "out": None}
+        self._pending["n"] += 1
+
+    def wait_step_at(self, index_env: int):
+        if self._pending is None:
+            raise RuntimeError("wait_step_at without a matching async_step_at")
+        if self._pending["out"] is None:   # the whole batch is generated on the first wait of the round
+            self._pending["out"] = self.step(None)
+        obs, rewards, dones, infos = self._pending["out"]
+        res = ({k: v[index_env] for k, v in obs.items()}, float(rewards[index_env]), bool(dones[index_env]),
+               infos[index_env])
+        self._pending["n"] -= 1
+        if self._pending["n"] <= 0:
+            self._pending = None
+        return res
+
+    def post_step(self, observations):
+        return observations
 
     def close(self):
         pass
@@ -187,17 +214,14 @@ class PPOTrainer:
             torch.distributed.barrier()
         self.envs = SyntheticVectorEnvFactory().construct_envs(cfg, device=self.device, rank=rank)
         obs_space, act_space = self.envs.observation_spaces[0], self.envs.action_spaces[0]
-        policy_cls = baseline_registry.get_policy(hb.rl.policy["main_agent"].name) or PointNavResNetPolicy
-        self.actor_critic = policy_cls.from_config(cfg, obs_space, act_space).to(self.device)
-        upd_name = hb.distrib_updater_name if torch.distributed.is_initialized() else hb.updater_name
-        upd_cls = baseline_registry.get_updater(upd_name) or (DDPPO if torch.distributed.is_initialized() else PPO)
-        self.updater = upd_cls.from_config(self.actor_critic, ppo_cfg)
+        # policy + updater + storage are owned by the agent access manager, built from the registry names in the config
+        # (ppo_trainer.py:122-134, 246-259)
+        self._env_spec = SimpleNamespace(observation_space=obs_space, action_space=act_space,
+                                         orig_action_space=self.envs.orig_action_spaces[0])
+        self._agent = self._create_agent(None)
         if torch.distributed.is_initialized():
-            self.updater.init_distributed(find_unused_params=False)
-        storage_cls = baseline_registry.get_storage(hb.rollout_storage_name) or RolloutStorage
-        self.rollouts = storage_cls(ppo_cfg.num_steps, self.envs.num_envs, obs_space, act_space, self.actor_critic,
-                                    is_double_buffered=False)
-        self.rollouts.to(self.device)
+            self._agent.init_distributed(find_unused_params=False)
+        self._agent.post_init()
         obs = self.envs.reset()
         self.rollouts.insert_first_observations(TensorDict.from_tree(obs))
         n = self.envs.num_envs
@@ -205,9 +229,61 @@ class PPOTrainer:
         self.running_episode_stats = dict(count=torch.zeros(n, 1, device=self.device),
                                           reward=torch.zeros(n, 1, device=self.device))
         self.window_episode_stats = collections.defaultdict(lambda: collections.deque(maxlen=ppo_cfg.reward_window_size))
-        self._lr0 = ppo_cfg.lr
-        self._clip0 = ppo_cfg.clip_param
+        self._last_checkpoint_percent = -1.0
         self.t_start = time.time()
+
+    def _create_agent(self, resume_state, **kwargs) -> SingleAgentAccessMgr:
+        """ppo_trainer.py:122-134"""
+        agent = SingleAgentAccessMgr(config=self.config, env_spec=self._env_spec, is_distrib=torch.distributed.is_initialized(),
+                                     device=self.device, percent_done_fn=self.percent_done, **kwargs)
+        if resume_state is not None:
+            agent.load_state_dict(resume_state)
+        return agent
+
+    # the attributes round-1 callers (tests, bench) read
+    @property
+    def actor_critic(self):
+        return self._agent.actor_critic
+
+    @property
+    def updater(self):
+        return self._agent.updater
+
+    @property
+    def rollouts(self):
+        return self._agent.rollouts
+
+    # -- checkpoints (common/base_trainer.py:269-287, ppo_trainer.py:296-341)
+    def should_checkpoint(self) -> bool:
+        hb = self.config.habitat_baselines
+        if getattr(hb, "num_checkpoints", -1) != -1:
+            every = 1 / hb.num_checkpoints
+            if self._last_checkpoint_percent + every < self.percent_done():
+                self._last_checkpoint_percent = self.percent_done()
+                return True
+            return False
+        interval = getattr(hb, "checkpoint_interval", -1)
+        return interval > 0 and (self.num_updates_done % interval) == 0
+
+    def save_checkpoint(self, file_name: str, extra_state: Optional[Dict] = None) -> None:
+        ckpt = {**self._agent.get_save_state(), "config": self.config}
+        if extra_state is not None:
+            ckpt["extra_state"] = extra_state
+        folder = self.config.habitat_baselines.checkpoint_folder
+        os.makedirs(folder, exist_ok=True)
+        torch.save(ckpt, os.path.join(folder, file_name))
+        torch.save(ckpt, os.path.join(folder, "latest.pth"))
+
+    def load_checkpoint(self, checkpoint_path: str, *args, **kwargs) -> Dict:
+        return torch.load(checkpoint_path, *args, weights_only=False, **kwargs)
+
+    def get_resume_state(self) -> Dict:
+        """what ppo_trainer.py:707-726 hands to save_resume_state"""
+        return dict(**self._agent.get_resume_state(), config=self.config,
+                    requeue_stats=dict(num_steps_done=self.num_steps_done, num_updates_done=self.num_updates_done,
+                                       _last_checkpoint_percent=self._last_checkpoint_percent,
+                                       running_episode_stats=self.running_episode_stats,
+                                       window_episode_stats=dict(self.window_episode_stats)))
 
     # -- one environment step for all envs (ppo_trainer.py:343-482, batched: observations never leave the GPU)
     def _rollout_step(self):
@@ -246,15 +322,10 @@ class PPOTrainer:
         next_value = self.actor_critic.get_value(last["observations"], last["recurrent_hidden_states"],
                                                  last["prev_actions"], last["masks"])
         r.compute_returns(next_value, ppo_cfg.use_gae, ppo_cfg.gamma, ppo_cfg.tau)
-        self.actor_critic.train()
-        losses = self.updater.update(r)
+        self._agent.train()
+        losses = self._agent.updater.update(r)
         r.after_update()
-        # LambdaLR(1 - percent_done) / clip decay (single_agent_access_mgr.py:285-297)
-        if ppo_cfg.use_linear_lr_decay:
-            for g in self.updater.optimizer.param_groups:
-                g["lr"] = self._lr0 * (1 - self.percent_done())
-        if ppo_cfg.use_linear_clip_decay:
-            self.updater.clip_param = self._clip0 * (1 - self.percent_done())
+        self._agent.after_update()   # LambdaLR(1 - percent_done) step + updater.after_update (ppo_trainer.py:519-521)
         self.timings["learn"] += time.perf_counter() - t0
         return losses
 
@@ -281,7 +352,8 @@ class PPOTrainer:
         ppo_cfg = self.config.habitat_baselines.rl.ppo
         losses = {}
         while not self.is_done():
-            self.actor_critic.eval()
+            self._agent.pre_rollout()   # linear clip decay, evaluated AFTER the previous update's increment (:705)
+            self._agent.eval()
             count_steps_delta = 0
             t0 = time.perf_counter()
             for step in range(ppo_cfg.num_steps):
@@ -296,6 +368,8 @@ class PPOTrainer:
             torch.cuda.synchronize()
             self.num_updates_done += 1
             losses = self._coalesce_post_step(losses, count_steps_delta)
+            if self.should_checkpoint():
+                self.save_checkpoint(f"ckpt.{self.num_updates_done}.pth", dict(step=self.num_steps_done))
             self._last_fps = self.num_steps_done / max(time.time() - self.t_start, 1e-9)
         self.envs.close()
         return losses

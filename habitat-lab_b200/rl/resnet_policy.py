@@ -29,7 +29,8 @@ from .._lib import Hb200Error
 from ..common import spaces
 from ..common.baseline_registry import baseline_registry
 
-BF16 = torch.bfloat16
+BF16 = torch.bfloat16   # gradients (g, dy, gz) and the dgrad weight images
+F16 = torch.float16     # forward values: pooled input, conv outputs, activations, forward weight images
 POINTGOAL_UUID = "pointgoal_with_gps_compass"  # IntegratedPointGoalGPSAndCompassSensor.cls_uuid
 IMAGEGOAL_UUID = "imagegoal"
 
@@ -251,20 +252,21 @@ class _Conv:
         self.out_hw = tuple((d + 2 * self.pad - self.k) // self.stride + 1 for d in in_hw)
         self.wp = self.wt = self.dw_acc = None
         self.halo = False       # stride-1 3x3 layer served by the halo kernels (conv_halo.cu)
+        self.halo_w = False     # weight gradient served by the (multi-image tile) halo wgrad kernel
         self.stem_s2d = False   # 7x7 s2 stem as a 4x4 s1 conv over the space-to-depth input
         self.wh = self.wht = None
 
     def alloc_weights(self, dev, need_dgrad):
         if self.stem_s2d:
-            self.wh = torch.empty(16 * 16 * self.co, dtype=BF16, device=dev)
+            self.wh = torch.empty(16 * 16 * self.co, dtype=F16, device=dev)
             self.dw_acc = torch.empty(16 * 16, self.co, device=dev)
             return
         if self.halo:
-            self.wh = torch.empty(9 * self.ci * self.co, dtype=BF16, device=dev)
+            self.wh = torch.empty(9 * self.ci * self.co, dtype=F16, device=dev)
             self.wht = torch.empty(9 * self.ci * self.co, dtype=BF16, device=dev)
             self.dw_acc = torch.empty(9 * self.ci, self.co, device=dev)
             return
-        self.wp = torch.empty(ops.packed_weight_elems(self.co, self.ci, self.k, self.k), dtype=BF16, device=dev)
+        self.wp = torch.empty(ops.packed_weight_elems(self.co, self.ci, self.k, self.k), dtype=F16, device=dev)
         self.wt = (torch.empty(ops.packed_weight_elems(self.ci, self.co, self.k, self.k), dtype=BF16, device=dev)
                    if need_dgrad else None)
         self.dw_acc = torch.empty(self.k * self.k * self.ci, self.co, device=dev)
@@ -356,6 +358,7 @@ class EncoderEngine:
                                   ops.conv_halo_supported(16, c.co, 4, c.out_hw[0], c.out_hw[1]))
                 elif c.k == 3 and c.stride == 1 and c.pad == 1:
                     c.halo = ops.conv_halo_supported(c.ci, c.co, 3, c.in_hw[0], c.in_hw[1])
+                    c.halo_w = ops.conv_halo_wgrad_supported(c.ci, c.co, 3, c.in_hw[0], c.in_hw[1])
         self._ws = {}
         self._dev = None
         self._packed_key = None
@@ -370,7 +373,7 @@ class EncoderEngine:
         key = (B, train)
         if key in self._ws:
             return self._ws[key]
-        e = lambda *s: torch.empty(*s, dtype=BF16, device=dev)  # noqa: E731
+        e = lambda *s: torch.empty(*s, dtype=F16, device=dev)  # noqa: E731  (forward values)
         ws = {"x0": e(B, self.hp // 2, self.wp_ // 2, 16) if self.stem.stem_s2d else e(B, self.hp, self.wp_, 8)}
         # GroupNorm statistics of all convs live in one f64 arena (f64: reproducible atomics) zeroed by ONE memset
         tot = sum(B * c.groups * 2 for c in self.convs)
@@ -497,7 +500,7 @@ class EncoderEngine:
                     ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.out_hw[0], c.out_hw[1], 16, c.co, 4)
                     ops.unpack_stem_wgrad(c.dw_acc, c.w.grad)
                 else:
-                    if c.halo:
+                    if c.halo or c.halo_w:
                         ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, 3)
                     else:
                         ops.conv_wgrad(x, dy, c.dw_acc, c.shape(B))

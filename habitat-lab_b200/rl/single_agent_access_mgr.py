@@ -114,6 +114,7 @@ class SingleAgentAccessMgr:
     def after_update(self):
         if self._ppo_cfg.use_linear_lr_decay and self._lr_scheduler is not None:
             self._lr_scheduler.step()
+        self._updater.after_update()   # single_agent_access_mgr.py:291
 
     def pre_rollout(self):
         if self._ppo_cfg.use_linear_clip_decay:

@@ -19,14 +19,26 @@ class ObservationBatchingCache:
 
     def __init__(self):
         self._pool: Dict[tuple, torch.Tensor] = {}
+        self._in_flight: Dict[tuple, "torch.cuda.Event"] = {}
 
     def get(self, name: str, shape, dtype: torch.dtype, pin: bool) -> torch.Tensor:
+        """The staging buffer for `name`; blocks until the previous asynchronous H2D copy out of it has finished
+        (a second batch_obs with the same cache -- e.g. a double-buffered sampler -- must not overwrite host memory
+        the DMA engine is still reading)."""
         key = (name, tuple(shape), dtype, pin)
         buf = self._pool.get(key)
         if buf is None:
             buf = torch.empty(tuple(shape), dtype=dtype, pin_memory=pin)
             self._pool[key] = buf
+        ev = self._in_flight.pop(key, None)
+        if ev is not None:
+            ev.synchronize()
         return buf
+
+    def mark_in_flight(self, name: str, shape, dtype: torch.dtype, pin: bool) -> None:
+        ev = torch.cuda.Event()
+        ev.record()
+        self._in_flight[(name, tuple(shape), dtype, pin)] = ev
 
 
 def batch_obs(observations: List[dict], device: Optional[torch.device] = None,
@@ -53,6 +65,11 @@ def batch_obs(observations: List[dict], device: Optional[torch.device] = None,
         view = buf.numpy()
         for i, it in enumerate(items):
             view[i] = np.asarray(it)
-        return buf.to(device, non_blocking=True) if device.type == "cuda" else buf.clone()
+        if device.type != "cuda":
+            return buf.clone()
+        out = buf.to(device, non_blocking=True)
+        if pin:
+            cache.mark_in_flight(name, (len(items),) + arr0.shape, dtype, pin)
+        return out
 
     return TensorDict.from_tree(build(list(observations), "obs"))

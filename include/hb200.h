@@ -211,6 +211,11 @@ int hb200_pack_halo_weight(const float* w_oihw, hb200_bf16* img, int co, int ci_
 int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb200_bf16* y, const hb200_bf16* addend,
                     double* gn_stats, int gn_groups, int batch, int h, int w, int c, int n, int k, int mode,
                     hb200_stream_t stream);
+/* 1 if hb200_conv_halo_wgrad serves this 3x3 / stem shape: the hb200_conv_halo_supported shapes plus the small-image
+ * layers (8x8 and 4x4 inputs, c % 32 == 0, n % 128 == 0: layer3 / layer4 / compression of
+ * HB/rl/ddppo/policy/resnet.py:196-281, resnet_policy.py:200-240), whose tiles span several images. */
+int hb200_conv_halo_wgrad_supported(int c, int n, int k, int h, int w);
+
 /* dw_acc f32 [(r*k+s)*C + ci][N] accumulated with atomics (caller zeroes), like hb200_conv_wgrad */
 int hb200_conv_halo_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc, int batch, int h, int w,
                           int c, int n, int k, hb200_stream_t stream);

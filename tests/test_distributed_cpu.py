@@ -35,7 +35,9 @@ def _worker(rank, world, port, q):
                              torch.zeros((), dtype=torch.float64)])
         obj = DDPPO.__new__(DDPPO)
         obj._world, obj._group = world, None
-        mean_var = DDPPO._compute_var_mean(obj, adv, stats)
+        mean_var = DDPPO._fused_var_mean(obj, stats)
+        var_r, mean_r = DDPPO._compute_var_mean(adv.flatten())   # the reference-signature hook gives the same numbers
+        assert abs(float(mean_r) - float(mean_var[0])) < 1e-5 and abs(float(var_r) - float(mean_var[1])) < 1e-5
         # flat gradient exchange
         g = torch.randn(1000) + rank
         flat = g.clone()

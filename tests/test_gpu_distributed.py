@@ -65,8 +65,15 @@ def _worker(rank, world, port, ngpu, q):
         q.put((rank, p0.cpu().numpy(), g_local.cpu().numpy(), flat["grads"].detach().cpu().numpy(),
                flat["params"].detach().cpu().numpy(), float(gn), stats.cpu().numpy(),
                adv.detach().cpu().numpy(), st.buffers["returns"].cpu().numpy(), st.buffers["value_preds"].cpu().numpy()))
+    except BaseException:   # report instead of leaving the parent waiting on the queue
+        import traceback
+        q.put(("error", rank, traceback.format_exc()[-3000:]))
+        raise
     finally:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def test_ddppo_before_step_two_ranks(hb):
@@ -79,8 +86,27 @@ def test_ddppo_before_step_two_ranks(hb):
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, ngpu, q)) for r in range(world)]
     [p.start() for p in procs]
-    res = sorted([q.get(timeout=600) for _ in procs], key=lambda t: t[0])
-    [p.join(120) for p in procs]
+    res = []
+    import queue as _queue
+    import time as _time
+    deadline = _time.time() + 420
+    try:
+        while len(res) < world:
+            try:
+                item = q.get(timeout=5)
+            except _queue.Empty:
+                dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+                assert not dead, f"a rank died with exit code {dead} before reporting"
+                assert _time.time() < deadline, "ranks did not finish in time"
+                continue
+            assert item[0] != "error", f"rank {item[1]} failed:\n{item[2]}"
+            res.append(item)
+    finally:
+        for p in procs:
+            p.join(20)
+            if p.is_alive():
+                p.kill()
+    res.sort(key=lambda t: t[0])
     r0, r1 = [[torch.from_numpy(a) if hasattr(a, "shape") else a for a in r] for r in res]
     # 1. broadcast: both ranks start from rank 0's weights although they were initialised with different seeds
     assert torch.equal(r0[1], r1[1])

@@ -1,9 +1,10 @@
 """GPU parity tests, kernel by kernel, through the C ABI (libhb200.so) against the CPU oracle
 (oracle/torch_oracle.py) or a plain fp32 torch restatement of the same op.
 
-Tolerances (stated per test): GAE variant 1 is bit-exact; fp32 kernels 1e-5..1e-4; bf16
-tensor-core convolutions are compared against an fp32 convolution of the SAME bf16-rounded
-operands, so only accumulation order + the final bf16 rounding of the output differ (2^-8 rel).
+Tolerances (stated per test): GAE variant 1 is bit-exact; fp32 kernels 1e-5..1e-4; the tensor-core
+convolutions are compared against an fp32 convolution of the SAME rounded operands (forward values fp16 = hf(),
+gradients bf16 = bf()), so only accumulation order + the final rounding of the output differ (2^-11 rel for the
+fp16 forward outputs, 2^-8 for the bf16 data gradients).
 """
 import math
 import os
@@ -19,8 +20,12 @@ from oracle import torch_oracle as O  # noqa: E402  (checker only)
 DEV = "cuda"
 
 
-def bf(x):
+def bf(x):   # gradient storage type
     return x.to(torch.bfloat16)
+
+
+def hf(x):   # forward-value storage type (activations, forward weight images)
+    return x.to(torch.float16)
 
 
 def nhwc(x_nchw):
@@ -261,18 +266,18 @@ def test_conv_fwd_dgrad_wgrad(hb, case):
     torch.manual_seed(sum(case))
     x = torch.randn(B, ci_real, H, W, device=DEV)
     w = torch.randn(co, ci_real, k, k, device=DEV) * (1.0 / math.sqrt(ci_real * k * k))
-    xb, wb = bf(x).float(), bf(w).float()
-    y_ref = F.conv2d(xb, wb, stride=stride, padding=pad)
+    xb, wb, wh_ = hf(x).float(), bf(w).float(), hf(w).float()   # forward: fp16 x fp16; dgrad image: bf16
+    y_ref = F.conv2d(xb, wh_, stride=stride, padding=pad)
     s = ops.conv_shape(B, H, W, ci, co, k, k, stride, pad)
-    x_nhwc = torch.zeros(B, H, W, ci, device=DEV, dtype=torch.bfloat16)
-    x_nhwc[..., :ci_real] = bf(nhwc(x))
+    x_nhwc = torch.zeros(B, H, W, ci, device=DEV, dtype=torch.float16)
+    x_nhwc[..., :ci_real] = hf(nhwc(x))
     wp, wt = ops.pack_conv_weight(w, ci, want_t=ci >= 32)
-    y = torch.empty(B, s.ho, s.wo, co, device=DEV, dtype=torch.bfloat16)
+    y = torch.empty(B, s.ho, s.wo, co, device=DEV, dtype=torch.float16)
     groups = 16 if co % 16 == 0 and co // 16 >= 2 else 1
     stats = torch.zeros(B, groups, 2, device=DEV, dtype=torch.float64)
     ops.conv_fwd(x_nhwc, wp, y, s, stats, groups)
     torch.cuda.synchronize()
-    torch.testing.assert_close(nchw(y.float()), y_ref, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(nchw(y.float()), y_ref, rtol=2e-3, atol=2e-3)
     # fused GroupNorm statistics: sum / sum of squares per (frame, group) of the fp32 accumulators
     yg = y_ref.view(B, groups, -1)
     torch.testing.assert_close(stats[..., 0].float(), yg.sum(-1), rtol=1e-3, atol=2e-2)
@@ -315,19 +320,19 @@ def test_conv_halo_3x3(hb, B, H, W, C, N):
     torch.manual_seed(B + H + C)
     x = torch.randn(B, C, H, W, device=DEV)
     w = torch.randn(N, C, 3, 3, device=DEV) / math.sqrt(9 * C)
-    xb, wb = bf(x).float(), bf(w).float()
-    y_ref = F.conv2d(xb, wb, padding=1)
-    x_nhwc = bf(nhwc(x))
-    wh = torch.empty(9 * C * N, device=DEV, dtype=torch.bfloat16)
+    xb, wb = hf(x).float(), bf(w).float()
+    y_ref = F.conv2d(xb, hf(w).float(), padding=1)
+    x_nhwc = hf(nhwc(x))
+    wh = torch.empty(9 * C * N, device=DEV, dtype=torch.float16)
     wht = torch.empty(9 * C * N, device=DEV, dtype=torch.bfloat16)
     ops.pack_halo_weight(w, wh, C, N, 3, 0)
     ops.pack_halo_weight(w, wht, N, C, 3, 1)
-    y = torch.empty(B, H, W, N, device=DEV, dtype=torch.bfloat16)
+    y = torch.empty(B, H, W, N, device=DEV, dtype=torch.float16)
     G = 16
     stats = torch.zeros(B, G, 2, device=DEV, dtype=torch.float64)
     ops.conv_halo(x_nhwc, wh, y, B, H, W, C, N, 3, 0, gn_stats=stats, gn_groups=G)
     torch.cuda.synchronize()
-    torch.testing.assert_close(nchw(y.float()), y_ref, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(nchw(y.float()), y_ref, rtol=2e-3, atol=2e-3)
     yg = y_ref.view(B, G, -1)
     torch.testing.assert_close(stats[..., 0].float(), yg.sum(-1), rtol=1e-3, atol=2e-2)
     torch.testing.assert_close(stats[..., 1].float(), (yg * yg).sum(-1), rtol=1e-3, atol=2e-2)
@@ -349,6 +354,32 @@ def test_conv_halo_3x3(hb, B, H, W, C, N):
     torch.testing.assert_close(dw, dw_ref, rtol=2e-3, atol=2e-3 * dw_ref.abs().max().item())
 
 
+@pytest.mark.parametrize("B,HW,C,N", [(5, 8, 128, 128), (2, 8, 128, 128), (7, 4, 256, 256), (3, 4, 256, 128),
+                                      (600, 8, 128, 128), (1, 4, 32, 128)])
+def test_conv_halo_wgrad_small_images(hb, B, HW, C, N):
+    """weight gradient of the 8x8 / 4x4 layers: tiles of 2 / 4 stacked images (own padding rows, virtual zero pixels for
+    4x4), 32-channel x 128-column slices, vs fp32 conv2d_weight of the same rounded operands; odd B = ragged last tile"""
+    from habitat_lab_b200 import ops
+
+    assert ops.conv_halo_wgrad_supported(C, N, 3, HW, HW) and not ops.conv_halo_supported(C, N, 3, HW, HW)
+    torch.manual_seed(B + HW + C)
+    x = torch.randn(B, C, HW, HW, device=DEV)
+    dy = torch.randn(B, N, HW, HW, device=DEV)
+    xb, dyb = hf(x).float(), bf(dy).float()
+    dw_ref = torch.nn.grad.conv2d_weight(xb, (N, C, 3, 3), dyb, padding=1)
+    acc = torch.zeros(9 * C, N, device=DEV)
+    ops.conv_halo_wgrad(hf(nhwc(x)), bf(nhwc(dy)), acc, B, HW, HW, C, N, 3)
+    dw = torch.empty(N, C, 3, 3, device=DEV)
+    ops.unpack_conv_wgrad(acc, dw, C)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dw, dw_ref, rtol=2e-3, atol=2e-3 * dw_ref.abs().max().item())
+    # and it must agree with the gather kernel it replaces
+    acc2 = torch.zeros(9 * C, N, device=DEV)
+    ops.conv_wgrad(hf(nhwc(x)), bf(nhwc(dy)), acc2, ops.conv_shape(B, HW, HW, C, N, 3, 3, 1, 1))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(acc, acc2, rtol=2e-3, atol=2e-3 * acc2.abs().max().item())
+
+
 @pytest.mark.parametrize("B,Hp,Wp", [(2, 128, 128), (3, 64, 32)])
 def test_conv_halo_stem_s2d(hb, B, Hp, Wp):
     """7x7 stride-2 pad-3 stem == 4x4 stride-1 conv over the space-to-depth input"""
@@ -357,18 +388,18 @@ def test_conv_halo_stem_s2d(hb, B, Hp, Wp):
     torch.manual_seed(Hp)
     x = torch.randn(B, 4, Hp, Wp, device=DEV)
     w = torch.randn(32, 4, 7, 7, device=DEV) / math.sqrt(196)
-    xb, wb = bf(x).float(), bf(w).float()
+    xb, wb = hf(x).float(), hf(w).float()
     y_ref = F.conv2d(xb, wb, stride=2, padding=3)
     Ho, Wo = Hp // 2, Wp // 2
     # s2d: [B, Ho, Wo, (dy, dx, c)]
-    xs = bf(x).view(B, 4, Ho, 2, Wo, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Ho, Wo, 16).contiguous()
-    wh = torch.empty(16 * 16 * 32, device=DEV, dtype=torch.bfloat16)
+    xs = hf(x).view(B, 4, Ho, 2, Wo, 2).permute(0, 2, 4, 3, 5, 1).reshape(B, Ho, Wo, 16).contiguous()
+    wh = torch.empty(16 * 16 * 32, device=DEV, dtype=torch.float16)
     ops.pack_halo_weight(w, wh, 16, 32, 4, 2)
-    y = torch.empty(B, Ho, Wo, 32, device=DEV, dtype=torch.bfloat16)
+    y = torch.empty(B, Ho, Wo, 32, device=DEV, dtype=torch.float16)
     stats = torch.zeros(B, 16, 2, device=DEV, dtype=torch.float64)
     ops.conv_halo(xs, wh, y, B, Ho, Wo, 16, 32, 4, 0, gn_stats=stats, gn_groups=16)
     torch.cuda.synchronize()
-    torch.testing.assert_close(nchw(y.float()), y_ref, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(nchw(y.float()), y_ref, rtol=2e-3, atol=2e-3)
     dy = torch.randn_like(y_ref)
     dw_ref = torch.nn.grad.conv2d_weight(xb, w.shape, bf(dy).float(), stride=2, padding=3)
     acc = torch.zeros(256, 32, device=DEV)
@@ -414,7 +445,7 @@ def test_prep(hb, has_rgb, has_depth):
     stats = torch.zeros(17, dtype=torch.float64, device=DEV)
     rm, rv, rc = d(mean.view(-1)), d(var.view(-1)), d(count.view(1))
     ss = torch.zeros(16, device=DEV)
-    out = torch.empty(B, H // 2, W // 2, 8, device=DEV, dtype=torch.bfloat16)
+    out = torch.empty(B, H // 2, W // 2, 8, device=DEV, dtype=torch.float16)
     fr = d(frame_rows)
     ops.prep_stats(drgb, ddepth, fr, H, W, stats)
     ops.prep_finalize(stats, rm, rv, rc, ss, C, (H // 2) * (W // 2), True)
@@ -424,10 +455,10 @@ def test_prep(hb, has_rgb, has_depth):
     torch.testing.assert_close(rv.cpu(), v2.view(-1), rtol=1e-4, atol=1e-6)
     assert rc.item() == c2.item()
     got = nchw(out.float().cpu())
-    torch.testing.assert_close(got[:, :C], ref, rtol=1e-2, atol=1e-2)  # bf16 output
+    torch.testing.assert_close(got[:, :C], ref, rtol=2e-3, atol=2e-3)  # fp16 output
     assert (got[:, C:] == 0).all()
     # space-to-depth form used by the halo stem: [B, H/4, W/4, (dy, dx, c4)]
-    out2 = torch.empty(B, H // 4, W // 4, 16, device=DEV, dtype=torch.bfloat16)
+    out2 = torch.empty(B, H // 4, W // 4, 16, device=DEV, dtype=torch.float16)
     ops.prep_apply(drgb, ddepth, fr, H, W, ss, out2, s2d=True)
     exp = out[..., :4].view(B, H // 4, 2, W // 4, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(B, H // 4, W // 4, 16)
     assert torch.equal(out2, exp)
@@ -450,12 +481,12 @@ def test_groupnorm_passes(hb, B, C, H, W, G):
     from habitat_lab_b200 import ops
 
     torch.manual_seed(C + H)
-    y = bf(torch.randn(B, C, H, W, device=DEV) * 1.5 + 0.3).float()
-    res = bf(torch.randn(B, C, H, W, device=DEV)).float()
+    y = hf(torch.randn(B, C, H, W, device=DEV) * 1.5 + 0.3).float()
+    res = hf(torch.randn(B, C, H, W, device=DEV)).float()
     gamma = torch.rand(C, device=DEV) + 0.5
     beta = torch.randn(C, device=DEV) * 0.2
     stats = _stats_of(y, G)
-    yb, resb = bf(nhwc(y)), bf(nhwc(res))
+    yb, resb = hf(nhwc(y)), hf(nhwc(res))
     hw = H * W
     # --- forward: GN + ReLU
     out = torch.empty_like(yb)
@@ -464,7 +495,7 @@ def test_groupnorm_passes(hb, B, C, H, W, G):
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     z = F.group_norm(yr, G, gr, br, eps=1e-5)
     a = F.relu(z)
-    torch.testing.assert_close(nchw(out.float()), a.detach(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(nchw(out.float()), a.detach(), rtol=2e-3, atol=2e-3)
     outf = torch.empty(B, H, W, C, device=DEV)
     ops.gn_apply(yb, stats, gamma, beta, outf, B, hw, C, G, relu=True)
     torch.testing.assert_close(nchw(outf), a.detach(), rtol=1e-4, atol=1e-4)
@@ -475,13 +506,13 @@ def test_groupnorm_passes(hb, B, C, H, W, G):
     dga, dbe = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
     gb = bf(nhwc(g))
     ops.gn_bwd_reduce(gb, None, yb, stats, gamma, beta, sums, dga, dbe, B, hw, C, G, 1)
-    dy = torch.empty_like(yb)
+    dy = torch.empty_like(gb)
     ops.gn_bwd_apply(gb, None, yb, stats, gamma, beta, sums, dy, None, B, hw, C, G, 1)
     torch.cuda.synchronize()
     sc = yr.grad.abs().max().item()
     torch.testing.assert_close(nchw(dy.float()), yr.grad, rtol=2e-2, atol=1e-2 * sc)
     # fused single-launch variant must reproduce the two-pass result
-    dga2, dbe2, dy2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.empty_like(yb)
+    dga2, dbe2, dy2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.empty_like(gb)
     ops.gn_bwd(gb, None, yb, stats, gamma, beta, dga2, dbe2, dy2, None, B, hw, C, G, 1)
     torch.cuda.synchronize()
     torch.testing.assert_close(dy2.float(), dy.float(), rtol=1e-2, atol=1e-2 * sc)
@@ -495,19 +526,19 @@ def test_groupnorm_passes(hb, B, C, H, W, G):
     yr2 = y.clone().requires_grad_(True)
     rr2 = res.clone().requires_grad_(True)
     o2 = F.relu(F.group_norm(yr2, G, gamma, beta, eps=1e-5) + rr2)
-    torch.testing.assert_close(nchw(blk.float()), o2.detach(), rtol=1e-2, atol=2e-2)
+    torch.testing.assert_close(nchw(blk.float()), o2.detach(), rtol=2e-3, atol=4e-3)
     o2.backward(g)
     sums.zero_(); dga.zero_(); dbe.zero_()
-    gz = torch.empty_like(yb)
-    # mask from the exact fp32 block output (bf16 copies of tiny positives could flip the mask)
-    act = bf(nhwc(o2.detach()))
+    gz = torch.empty_like(gb)
+    # mask from the exact fp32 block output (rounded copies of tiny positives could flip the mask)
+    act = hf(nhwc(o2.detach()))
     ops.gn_bwd_reduce(gb, act, yb, stats, gamma, beta, sums, dga, dbe, B, hw, C, G, 2)
     ops.gn_bwd_apply(gb, act, yb, stats, gamma, beta, sums, dy, gz, B, hw, C, G, 2)
     torch.cuda.synchronize()
     torch.testing.assert_close(nchw(gz.float()), rr2.grad, rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(nchw(dy.float()), yr2.grad, rtol=2e-2, atol=1e-2 * yr2.grad.abs().max().item())
     dga2.zero_(); dbe2.zero_()
-    gz2 = torch.empty_like(yb)
+    gz2 = torch.empty_like(gb)
     ops.gn_bwd(gb, act, yb, stats, gamma, beta, dga2, dbe2, dy2, gz2, B, hw, C, G, 2)
     torch.cuda.synchronize()
     assert torch.equal(gz2, gz)
@@ -527,7 +558,7 @@ def test_groupnorm_passes(hb, B, C, H, W, G):
     rstats = _stats_of(res, G)
     ops.gn_residual_relu(yb, stats, gamma, beta, resb, blk, B, hw, C, G, rstats, gd, bd)
     o3 = F.relu(F.group_norm(y, G, gamma, beta, eps=1e-5) + F.group_norm(res, G, gd, bd, eps=1e-5))
-    torch.testing.assert_close(nchw(blk.float()), o3, rtol=1e-2, atol=3e-2)
+    torch.testing.assert_close(nchw(blk.float()), o3, rtol=2e-3, atol=6e-3)
 
 
 @pytest.mark.parametrize("B,C,H,W,G", [(3, 32, 16, 24, 16), (2, 32, 64, 64, 16), (2, 64, 32, 32, 16)])
@@ -535,18 +566,18 @@ def test_gn_relu_maxpool(hb, B, C, H, W, G):
     from habitat_lab_b200 import ops
 
     torch.manual_seed(5)
-    y = bf(torch.randn(B, C, H, W, device=DEV)).float()
+    y = hf(torch.randn(B, C, H, W, device=DEV)).float()
     gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.2
     stats = _stats_of(y, G)
-    yb = bf(nhwc(y))
-    out = torch.empty(B, H // 2, W // 2, C, device=DEV, dtype=torch.bfloat16)
+    yb = hf(nhwc(y))
+    out = torch.empty(B, H // 2, W // 2, C, device=DEV, dtype=torch.float16)
     arg = torch.empty(B, H // 2, W // 2, C, device=DEV, dtype=torch.uint8)
     ops.gn_relu_maxpool(yb, stats, gamma, beta, out, arg, B, H, W, C, G)
     yr = y.clone().requires_grad_(True)
     zr = F.relu(F.group_norm(yr, G, gamma, beta, eps=1e-5))
     zr.retain_grad()
     pr = F.max_pool2d(zr, 3, 2, 1)
-    torch.testing.assert_close(nchw(out.float()), pr.detach(), rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(nchw(out.float()), pr.detach(), rtol=2e-3, atol=2e-3)
     g = bf(torch.randn_like(pr)).float()
     pr.backward(g)
     dz = torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16)
