@@ -36,7 +36,7 @@ SIGNATURES = {
     "hb200_clip_adam": ("i", "pppp" + "l" + "fffffff" + "l" + "pppp"),
     "hb200_prep_stats": ("i", "ppp" + "iiiii" + "f" + "pp"),
     "hb200_prep_finalize": ("i", "ppppp" + "ili" + "p"),
-    "hb200_prep_apply": ("i", "ppp" + "iiiii" + "f" + "pp" + "i" + "p"),
+    "hb200_prep_apply": ("i", "ppp" + "iiiii" + "f" + "ppp" + "i" + "p"),
     "hb200_conv_fwd": ("i", "pppp" + "i" + "pp"),
     "hb200_conv_bias_act_fwd": ("i", "pppp" + "i" + "pp"),
     "hb200_prep_plain": ("i", "ppp" + "iiiii" + "pp"),
@@ -56,9 +56,9 @@ SIGNATURES = {
     "hb200_conv_halo_wgrad": ("i", "ppp" + "iiiiii" + "p"),
     "hb200_unpack_stem_wgrad": ("i", "pp" + "ii" + "p"),
     "hb200_umma_gemm_probe": ("i", "ppp" + "iiii" + "p"),
-    "hb200_gn_apply": ("i", "ppppp" + "iiiii" + "f" + "i" + "p"),
-    "hb200_gn_residual_relu": ("i", "ppppppppp" + "iiii" + "f" + "p"),
-    "hb200_gn_relu_maxpool": ("i", "pppppp" + "iiiii" + "f" + "p"),
+    "hb200_gn_apply": ("i", "pppppp" + "iiiii" + "f" + "i" + "p"),
+    "hb200_gn_residual_relu": ("i", "pppppppppp" + "iiii" + "f" + "p"),
+    "hb200_gn_relu_maxpool": ("i", "ppppppp" + "iiiii" + "f" + "p"),
     "hb200_maxpool_bwd": ("i", "ppp" + "iiii" + "p"),
     "hb200_gn_bwd_reduce": ("i", "ppppppppp" + "iiii" + "f" + "i" + "p"),
     "hb200_gn_bwd_apply": ("i", "ppppppppp" + "iiii" + "f" + "i" + "p"),
@@ -69,6 +69,7 @@ SIGNATURES = {
     "hb200_sgemm": ("i", "pll" + "pll" + "pl" + "p" + "iii" + "f" + "ii" + "p"),
     "hb200_tgemm": ("i", "pll" + "pll" + "pl" + "p" + "iii" + "ii" + "p"),
     "hb200_transpose_f32": ("i", "plpl" + "ii" + "p"),
+    "hb200_f16_to_bf16": ("i", "pplp"),
     "hb200_bf16_to_f32": ("i", "pplp"),
     "hb200_f32_to_bf16": ("i", "pplp"),
     "hb200_lstm_step_fwd": ("i", "ppppplplppp" + "ii" + "p"),

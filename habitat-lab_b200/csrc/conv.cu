@@ -429,8 +429,9 @@ __global__ void __launch_bounds__(128) conv_wgrad_kernel(const WgradArgs a) {
     }
   };
 
-  // A = gathered forward activations x (fp16), B = output gradients dy (bf16): mixed-format kind::f16 MMA
-  constexpr uint32_t idesc = make_idesc_f16(kTileM, BN, 1, 1, kFmtF16, kFmtBF16);
+  // A = the bf16 twin of the forward activations, B = output gradients dy (bf16).  tcgen05 kind::f16 rejects mixed
+  // fp16 x bf16 operands (illegal-instruction fault on B200), so the forward kernels write a bf16-rounded copy of x
+  constexpr uint32_t idesc = make_idesc_bf16(kTileM, BN, 1, 1);
 #pragma unroll
   for (int c = 0; c < kStages - 1; ++c) {
     if (c < nchunks) load_chunk(c, c);

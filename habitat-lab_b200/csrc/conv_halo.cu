@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  // A = forward activations (fp16 halo), B = output gradients (bf16): mixed-format kind::f16 MMA
-  constexpr uint32_t idesc = make_idesc_f16(128, N, 1, 1, kFmtF16, kFmtBF16);
+  // A = bf16 twin of the forward activations (halo), B = output gradients (bf16); mixed fp16 x bf16 is not legal
+  constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
 
   for (int it = 0; it < my_n; ++it) {
     if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
 // grid = (tile workers, Ci/32 * Co/NS slices); results are accumulated into dw with vector red.add.
 // ------------------------------------------------------------------------------------------
 struct HaloWgradSmallArgs {
-  const act_t* x;     // [B, IMG, IMG, Ci]  fp16
+  const grad_t* x;    // [B, IMG, IMG, Ci]  bf16 twin of the forward activation
   const grad_t* dy;   // [B, IMG, IMG, Co]  bf16
   float* dw;          // [(r*3+s)*Ci + ci][Co]
   int B, Ci, Co, ntiles;
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
       const int j = hy / RPI, ih = hy - j * RPI - 1, iw = hx - 1;
       const int b = b0 + j;
       const bool ok = b < a.B && ih >= 0 && ih < IMG && iw >= 0 && iw < IMG;
-      const act_t* g = ok ? a.x + ((((size_t)b * IMG + ih) * IMG + iw) * a.Ci + c_off + cj * 8) : a.x;
+      const grad_t* g = ok ? a.x + ((((size_t)b * IMG + ih) * IMG + iw) * a.Ci + c_off + cj * 8) : a.x;
       cp_async16(sh + (uint32_t)(((hy * CJ + cj) * HWD + hx) * 16), g, ok);
     }
     // dy tile: [n-chunk][py][px]; pixels px >= IMG are virtual (dy = 0)
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
-  constexpr uint32_t idesc = make_idesc_f16(128, NS, 1, 1, kFmtF16, kFmtBF16);
+  constexpr uint32_t idesc = make_idesc_bf16(128, NS, 1, 1);
 
   for (int it = 0; it < my_n; ++it) {
     if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
@@ -939,7 +939,7 @@ extern "C" int hb200_conv_halo_wgrad(const hb200_bf16* x, const hb200_bf16* dy, 
   HB_CHECK_ARG(hb200_conv_halo_wgrad_supported(c, n, k, h, w), "conv_halo_wgrad: unsupported shape C=%d N=%d k=%d %dx%d", c, n, k, h, w);
   if (!hb200_conv_halo_supported(c, n, k, h, w)) {   // small images: several images per tile, sliced channels
     HaloWgradSmallArgs s;
-    s.x = (const act_t*)x; s.dy = (const grad_t*)dy; s.dw = dw_acc;
+    s.x = (const grad_t*)x; s.dy = (const grad_t*)dy; s.dw = dw_acc;
     s.B = batch; s.Ci = c; s.Co = n;
     const int ipt = TH / h;
     s.ntiles = (batch + ipt - 1) / ipt;

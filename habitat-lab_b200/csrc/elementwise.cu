@@ -117,7 +117,7 @@ template <bool HAS_RGB, bool HAS_DEPTH, bool S2D>
 __global__ void __launch_bounds__(256)
 prep_apply_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ depth,
                   const int32_t* __restrict__ frame_rows, int B, int H, int W, float rgb_scale,
-                  const float* __restrict__ scale_shift, act_t* __restrict__ out) {
+                  const float* __restrict__ scale_shift, act_t* __restrict__ out, grad_t* __restrict__ out2) {
   const int Hp = H / 2, Wq = W / 8;
   const long long total = (long long)B * Hp * Wq;
   float sc[4] = {1, 1, 1, 1}, sh[4] = {0, 0, 0, 0};
@@ -143,6 +143,7 @@ prep_apply_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ dep
         for (int c = 0; c < 4; ++c)
           if (c < C) v[c] = fmaf(o[p][c], sc[c], sh[c]);
         dst[p] = pack8a(v);
+        if (out2) reinterpret_cast<uint4*>(out2 + (((size_t)f * Hp + py) * (W / 2) + (size_t)px4 * 4) * 8)[p] = pack8(v);
       }
     } else {
       // pooled pixels (py, 4*px4 + p): s2d row i = py/2, dy = py&1; col j = 2*px4 + p/2, dx = p&1
@@ -156,6 +157,7 @@ prep_apply_kernel(const uint8_t* __restrict__ rgb, const float* __restrict__ dep
           for (int c = 0; c < 4; ++c) v[dx * 4 + c] = (c < C) ? fmaf(o[2 * q + dx][c], sc[c], sh[c]) : 0.f;
         const size_t pix = ((size_t)f * (Hp / 2) + i2) * (W / 4) + (size_t)px4 * 2 + q;
         *reinterpret_cast<uint4*>(out + pix * 16 + dy * 8) = pack8a(v);
+        if (out2) *reinterpret_cast<uint4*>(out2 + pix * 16 + dy * 8) = pack8(v);
       }
     }
   }
@@ -258,7 +260,8 @@ __device__ __forceinline__ GnSlab gn_slab(int C, int hw, int ppb) {
 
 template <int OUT_F32>  // 0: bf16 NHWC, 1: f32 NHWC, 2: f32 flattened in (c, h, w) order (nn.Flatten of NCHW)
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const act_t* __restrict__ y, GnP p, void* __restrict__ out, int B, int hw, int relu, int ppb) {
+gn_apply_kernel(const act_t* __restrict__ y, GnP p, void* __restrict__ out, grad_t* __restrict__ out2, int B, int hw,
+                int relu, int ppb) {
   const GnSlab t = gn_slab(p.C, hw, ppb);
   const int cv = p.C >> 3;
   float mu[8], rs[8], ga[8], be[8], sc[8], sh[8];
@@ -286,13 +289,15 @@ gn_apply_kernel(const act_t* __restrict__ y, GnP p, void* __restrict__ out, int 
       for (int e = 0; e < 8; ++e) o[(size_t)(t.c0 + e) * hw + pix] = x[e];
     } else {
       reinterpret_cast<uint4*>(out)[i] = pack8a(x);
+      if (out2) reinterpret_cast<uint4*>(out2)[i] = pack8(x);   // bf16 twin for the weight-gradient kernels
     }
   }
 }
 
 __global__ void __launch_bounds__(256)
 gn_residual_relu_kernel(const act_t* __restrict__ y, GnP p, const act_t* __restrict__ res,
-                        GnP rp, int res_is_prenorm, act_t* __restrict__ out, int B, int hw, int ppb) {
+                        GnP rp, int res_is_prenorm, act_t* __restrict__ out, grad_t* __restrict__ out2, int B, int hw,
+                        int ppb) {
   const GnSlab t = gn_slab(p.C, hw, ppb);
   const int cv = p.C >> 3;
   float mu[8], rs[8], ga[8], be[8], sc[8], sh[8], rsc[8], rsh[8];
@@ -316,11 +321,12 @@ gn_residual_relu_kernel(const act_t* __restrict__ y, GnP p, const act_t* __restr
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], sc[e], sh[e]) + fmaf(r[e], rsc[e], rsh[e]), 0.f);
     reinterpret_cast<uint4*>(out)[i] = pack8a(x);
+    if (out2) reinterpret_cast<uint4*>(out2)[i] = pack8(x);
   }
 }
 
 __global__ void __launch_bounds__(256)
-gn_relu_maxpool_kernel(const act_t* __restrict__ y, GnP p, act_t* __restrict__ out,
+gn_relu_maxpool_kernel(const act_t* __restrict__ y, GnP p, act_t* __restrict__ out, grad_t* __restrict__ out2,
                        uint8_t* __restrict__ argmax, int B, int H, int W) {
   const int cv = p.C >> 3, Ho = H / 2, Wo = W / 2;
   const long long total = (long long)B * Ho * Wo * cv;
@@ -357,6 +363,7 @@ gn_relu_maxpool_kernel(const act_t* __restrict__ y, GnP p, act_t* __restrict__ o
       }
     }
     reinterpret_cast<uint4*>(out)[i] = pack8a(best);
+    if (out2) reinterpret_cast<uint4*>(out2)[i] = pack8(best);
     uint2 a;
     a.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
     a.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
@@ -369,7 +376,7 @@ gn_relu_maxpool_kernel(const act_t* __restrict__ y, GnP p, act_t* __restrict__ o
 // window maximum is taken on x * sign(rstd*gamma) (the affine map is monotonic per channel) and the affine + ReLU
 // applied once per output.
 __global__ void __launch_bounds__(256)
-gn_relu_maxpool_slab_kernel(const act_t* __restrict__ y, GnP p, act_t* __restrict__ out,
+gn_relu_maxpool_slab_kernel(const act_t* __restrict__ y, GnP p, act_t* __restrict__ out, grad_t* __restrict__ out2,
                             uint8_t* __restrict__ argmax, int H, int W, int rows) {
   extern __shared__ __align__(16) uint8_t gsm[];
   uint4* sy = reinterpret_cast<uint4*>(gsm);
@@ -404,6 +411,7 @@ gn_relu_maxpool_slab_kernel(const act_t* __restrict__ y, GnP p, act_t* __restric
   __syncthreads();
   const int nout = (rows >> 1) * Wo * cv;
   uint4* o4 = reinterpret_cast<uint4*>(out) + ((size_t)b * Ho + (iy0 >> 1)) * Wo * cv;
+  uint4* o4b = out2 ? reinterpret_cast<uint4*>(out2) + ((size_t)b * Ho + (iy0 >> 1)) * Wo * cv : nullptr;
   uint2* a2 = reinterpret_cast<uint2*>(argmax) + ((size_t)b * Ho + (iy0 >> 1)) * Wo * cv;
   for (int it = tid; it < nout; it += 256) {
     const int pos = it / cv, ol = pos / Wo, ox = pos - ol * Wo;
@@ -432,6 +440,7 @@ gn_relu_maxpool_slab_kernel(const act_t* __restrict__ y, GnP p, act_t* __restric
 #pragma unroll
     for (int e = 0; e < 8; ++e) z[e] = fmaxf(fmaf(best[e], za[e], zd[e]), 0.f);
     o4[it] = pack8a(z);
+    if (o4b) o4b[it] = pack8(z);
     uint2 a;
     a.x = (uint32_t)arg[0] | ((uint32_t)arg[1] << 8) | ((uint32_t)arg[2] << 16) | ((uint32_t)arg[3] << 24);
     a.y = (uint32_t)arg[4] | ((uint32_t)arg[5] << 8) | ((uint32_t)arg[6] << 16) | ((uint32_t)arg[7] << 24);
@@ -1022,6 +1031,14 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, float* _
     reinterpret_cast<float4*>(o)[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
   }
 }
+__global__ void f16_to_bf16_kernel(const act_t* __restrict__ x, grad_t* __restrict__ o, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8a(reinterpret_cast<const uint4*>(x)[i], f);
+    reinterpret_cast<uint4*>(o)[i] = pack8(f);
+  }
+}
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ o, long long n8) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1326,8 +1343,8 @@ extern "C" int hb200_prep_finalize(const double* stats_acc, float* run_mean, flo
 
 extern "C" int hb200_prep_apply(const uint8_t* rgb, const float* depth, const int32_t* frame_rows,
                                 int batch, int height, int width, int c_rgb, int c_depth,
-                                float rgb_scale, const float* scale_shift, hb200_bf16* out, int s2d,
-                                hb200_stream_t stream) {
+                                float rgb_scale, const float* scale_shift, hb200_f16* out, hb200_bf16* out_bf16,
+                                int s2d, hb200_stream_t stream) {
   int rc = prep_check(rgb, depth, frame_rows, batch, height, width, c_rgb, c_depth);
   if (rc) return rc;
   HB_CHECK_ARG(out, "prep_apply: null out");
@@ -1335,10 +1352,11 @@ extern "C" int hb200_prep_apply(const uint8_t* rgb, const float* depth, const in
   const long long total = (long long)batch * (height / 2) * (width / 8);
   const int grid = grid_for(total, 256);
   act_t* o = (act_t*)out;
+  grad_t* o2 = (grad_t*)out_bf16;
   HB_CHECK_ARG(!s2d || (height % 4 == 0), "prep_apply: s2d needs H %% 4 == 0");
 #define HB_PREP(R, D)                                                                                              \
-  if (s2d) prep_apply_kernel<R, D, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o); \
-  else prep_apply_kernel<R, D, false><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o)
+  if (s2d) prep_apply_kernel<R, D, true><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o, o2); \
+  else prep_apply_kernel<R, D, false><<<grid, 256, 0, st>>>(rgb, depth, frame_rows, batch, height, width, rgb_scale, scale_shift, o, o2)
   if (c_rgb && c_depth) { HB_PREP(true, true); }
   else if (c_rgb) { HB_PREP(true, false); }
   else { HB_PREP(false, true); }
@@ -1348,31 +1366,33 @@ extern "C" int hb200_prep_apply(const uint8_t* rgb, const float* depth, const in
   return HB200_OK;
 }
 
-extern "C" int hb200_gn_apply(const hb200_bf16* y, const double* stats, const float* gamma,
-                              const float* beta, void* out, int out_f32, int batch, int hw,
+extern "C" int hb200_gn_apply(const hb200_f16* y, const double* stats, const float* gamma,
+                              const float* beta, void* out, hb200_bf16* out_bf16, int out_f32, int batch, int hw,
                               int channels, int groups, float eps, int relu, hb200_stream_t stream) {
   GnP p;
   int rc = make_gn(p, stats, gamma, beta, channels, groups, hw, eps);
   if (rc) return rc;
   HB_CHECK_ARG(y && out, "gn_apply: null pointer");
+  HB_CHECK_ARG(!out_bf16 || out_f32 == 0, "gn_apply: the bf16 twin accompanies the fp16 output only");
+  grad_t* o2 = (grad_t*)out_bf16;
   int ppb = 0, grid = 0;
   rc = gn_slab_launch(channels, hw, batch, &ppb, &grid);
   if (rc) return rc;
   if (out_f32 == 1)
-    gn_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)y, p, out, batch, hw, relu, ppb);
+    gn_apply_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)y, p, out, o2, batch, hw, relu, ppb);
   else if (out_f32 == 2)
-    gn_apply_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)y, p, out, batch, hw, relu, ppb);
+    gn_apply_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)y, p, out, o2, batch, hw, relu, ppb);
   else
-    gn_apply_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)y, p, out, batch, hw, relu, ppb);
+    gn_apply_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)y, p, out, o2, batch, hw, relu, ppb);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
 }
 
-extern "C" int hb200_gn_residual_relu(const hb200_bf16* y, const double* stats, const float* gamma,
-                                      const float* beta, const hb200_bf16* res, const double* res_stats,
-                                      const float* res_gamma, const float* res_beta, hb200_bf16* out,
-                                      int batch, int hw, int channels, int groups, float eps,
+extern "C" int hb200_gn_residual_relu(const hb200_f16* y, const double* stats, const float* gamma,
+                                      const float* beta, const hb200_f16* res, const double* res_stats,
+                                      const float* res_gamma, const float* res_beta, hb200_f16* out,
+                                      hb200_bf16* out_bf16, int batch, int hw, int channels, int groups, float eps,
                                       hb200_stream_t stream) {
   GnP p, rp;
   int rc = make_gn(p, stats, gamma, beta, channels, groups, hw, eps);
@@ -1387,15 +1407,15 @@ extern "C" int hb200_gn_residual_relu(const hb200_bf16* y, const double* stats, 
   rc = gn_slab_launch(channels, hw, batch, &ppb, &grid);
   if (rc) return rc;
   gn_residual_relu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      (const act_t*)y, p, (const act_t*)res, rp, res_stats ? 1 : 0, (act_t*)out, batch, hw, ppb);
+      (const act_t*)y, p, (const act_t*)res, rp, res_stats ? 1 : 0, (act_t*)out, (grad_t*)out_bf16, batch, hw, ppb);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
 }
 
-extern "C" int hb200_gn_relu_maxpool(const hb200_bf16* y, const double* stats, const float* gamma,
-                                     const float* beta, hb200_bf16* out, uint8_t* argmax, int batch,
-                                     int h, int w, int channels, int groups, float eps,
+extern "C" int hb200_gn_relu_maxpool(const hb200_f16* y, const double* stats, const float* gamma,
+                                     const float* beta, hb200_f16* out, hb200_bf16* out_bf16, uint8_t* argmax,
+                                     int batch, int h, int w, int channels, int groups, float eps,
                                      hb200_stream_t stream) {
   GnP p;
   int rc = make_gn(p, stats, gamma, beta, channels, groups, h * w, eps);
@@ -1412,7 +1432,7 @@ extern "C" int hb200_gn_relu_maxpool(const hb200_bf16* y, const double* stats, c
       auto kern = gn_relu_maxpool_slab_kernel;
       HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       kern<<<batch * (h / rows), 256, smem, (cudaStream_t)stream>>>((const act_t*)y, p, (act_t*)out,
-                                                                    argmax, h, w, rows);
+                                                                    (grad_t*)out_bf16, argmax, h, w, rows);
       HB_LAUNCH_OK();
       count_launch(1);
       return HB200_OK;
@@ -1420,7 +1440,7 @@ extern "C" int hb200_gn_relu_maxpool(const hb200_bf16* y, const double* stats, c
   }
   const long long total = (long long)batch * (h / 2) * (w / 2) * (channels / 8);
   gn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const act_t*)y, p, (act_t*)out, argmax, batch, h, w);
+      (const act_t*)y, p, (act_t*)out, (grad_t*)out_bf16, argmax, batch, h, w);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1490,6 +1510,14 @@ extern "C" int hb200_bf16_to_f32(const hb200_bf16* x, float* out, long long n, h
   count_launch(1);
   return HB200_OK;
 }
+extern "C" int hb200_f16_to_bf16(const hb200_f16* x, hb200_bf16* out, long long n, hb200_stream_t stream) {
+  HB_CHECK_ARG(x && out && n % 8 == 0, "f16_to_bf16: n must be a multiple of 8");
+  f16_to_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const act_t*)x, (grad_t*)out, n / 8);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
 extern "C" int hb200_f32_to_bf16(const float* x, hb200_bf16* out, long long n, hb200_stream_t stream) {
   HB_CHECK_ARG(x && out && n > 0 && n % 8 == 0, "f32_to_bf16: n must be a positive multiple of 8");
   f32_to_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, n / 8);

@@ -40,7 +40,8 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 }
 
 // kind::f16 with per-operand formats: 0 = f16 (11-bit significand, the forward-activation / weight storage type),
-// 1 = bf16 (gradient storage type).  Mixed A/B formats are legal for kind::f16 (pinned by hb200_umma_gemm_probe).
+// 1 = bf16 (gradient storage type).  Both operands must use the SAME format: a mixed fp16 x bf16 descriptor raises an
+// illegal-instruction fault on B200 (measured), although the descriptor has independent A / B format fields.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
   return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

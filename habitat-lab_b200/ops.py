@@ -95,10 +95,10 @@ def prep_finalize(stats_acc, run_mean, run_var, run_count, scale_shift, channels
          channels, int(pixels_per_frame), int(bool(update)))
 
 
-def prep_apply(rgb, depth, frame_rows, H, W, scale_shift, out, rgb_scale=1.0 / 255.0, s2d=False):
+def prep_apply(rgb, depth, frame_rows, H, W, scale_shift, out, rgb_scale=1.0 / 255.0, s2d=False, out_bf16=None):
     call("hb200_prep_apply", ptr(rgb), ptr(depth), ptr(frame_rows), frame_rows.numel(), H, W,
          3 if rgb is not None else 0, 1 if depth is not None else 0, float(rgb_scale), ptr(scale_shift), ptr(out),
-         int(bool(s2d)))
+         ptr(out_bf16), int(bool(s2d)))
 
 
 # ---- conv ----------------------------------------------------------------------------------------------
@@ -191,21 +191,21 @@ def umma_gemm_probe(a, b, d, m, n, k, layout):
 
 
 # ---- GroupNorm & friends -----------------------------------------------------------------------------
-def gn_apply(y, stats, gamma, beta, out, batch, hw, channels, groups, relu, eps=1e-5, chw_flat=False):
+def gn_apply(y, stats, gamma, beta, out, batch, hw, channels, groups, relu, eps=1e-5, chw_flat=False, out_bf16=None):
     mode = 0 if out.dtype != torch.float32 else (2 if chw_flat else 1)
-    call("hb200_gn_apply", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(out), mode, batch, hw, channels, groups,
-         float(eps), int(bool(relu)))
+    call("hb200_gn_apply", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(out), ptr(out_bf16), mode, batch, hw,
+         channels, groups, float(eps), int(bool(relu)))
 
 
 def gn_residual_relu(y, stats, gamma, beta, res, out, batch, hw, channels, groups, res_stats=None,
-                     res_gamma=None, res_beta=None, eps=1e-5):
+                     res_gamma=None, res_beta=None, eps=1e-5, out_bf16=None):
     call("hb200_gn_residual_relu", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(res), ptr(res_stats),
-         ptr(res_gamma), ptr(res_beta), ptr(out), batch, hw, channels, groups, float(eps))
+         ptr(res_gamma), ptr(res_beta), ptr(out), ptr(out_bf16), batch, hw, channels, groups, float(eps))
 
 
-def gn_relu_maxpool(y, stats, gamma, beta, out, argmax, batch, h, w, channels, groups, eps=1e-5):
-    call("hb200_gn_relu_maxpool", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(out), ptr(argmax), batch, h, w,
-         channels, groups, float(eps))
+def gn_relu_maxpool(y, stats, gamma, beta, out, argmax, batch, h, w, channels, groups, eps=1e-5, out_bf16=None):
+    call("hb200_gn_relu_maxpool", ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(out), ptr(out_bf16), ptr(argmax),
+         batch, h, w, channels, groups, float(eps))
 
 
 def gn_relu_maxpool_bwd_supported(h, w, channels, groups) -> bool:
@@ -311,6 +311,10 @@ def linear_bwd_weight(dy, x, dw, accumulate=False, tf32=False):
         sgemm(dyt, M, 1, xt, 1, M, dw, dw.stride(0), N, K, M, accumulate=accumulate, tf32=True)
         return
     sgemm(dy, 1, dy.stride(0), x, x.stride(0), 1, dw, dw.stride(0), N, K, M, accumulate=accumulate)
+
+
+def f16_to_bf16(x, out):
+    call("hb200_f16_to_bf16", ptr(x), ptr(out), x.numel())
 
 
 def bf16_to_f32(x, out):

@@ -108,6 +108,9 @@ class PointNavBaselinePolicy(NativeNetPolicy):
             ws[f"a{i}"] = ea(B, *dims[i + 1], c.out_channels)
         ws["flat"] = torch.empty(B, fc.in_features, device=dev)
         if train:
+            ws["x0_b"] = e(B, *dims[0], 8)                 # bf16 twins of the conv inputs (weight-gradient operand)
+            for i, c in enumerate(convs[:-1]):
+                ws[f"a{i}_b"] = e(B, *dims[i + 1], c.out_channels)
             for i, c in enumerate(convs):
                 ws[f"g{i}"] = e(B, *dims[i + 1], c.out_channels)
                 ws[f"dy{i}"] = e(B, *dims[i + 1], c.out_channels)
@@ -146,9 +149,13 @@ class PointNavBaselinePolicy(NativeNetPolicy):
         ops.prep_plain(obs.get("rgb") if cnn._n_input_rgb else None, obs.get("depth") if cnn._n_input_depth else None,
                        rows, H, W, cnn._n_input_rgb, cnn._n_input_depth, ws["x0"])
         x = ws["x0"]
+        if train:
+            ops.f16_to_bf16(x, ws["x0_b"])
         for i, c in enumerate(convs):
             ops.conv_bias_act_fwd(x, self._wimgs[i][0], c.bias, ws[f"a{i}"], self._shape(i, B), relu=(i < 2))
             x = ws[f"a{i}"]
+            if train and i < len(convs) - 1:
+                ops.f16_to_bf16(x, ws[f"a{i}_b"])
         hw3 = dims[3][0] * dims[3][1]
         ops.bf16_hwc_to_f32_chw(x, ws["flat"], B, hw3, convs[2].out_channels)
         Hs = self.net._hidden_size
@@ -184,7 +191,7 @@ class PointNavBaselinePolicy(NativeNetPolicy):
                 ops.relu_bias_bwd(g, ws[f"a{i}"], ws[f"dy{i}"], c.bias.grad, npix, c.out_channels)
                 dy = ws[f"dy{i}"]
             wp, wt, acc, cip = self._wimgs[i]
-            x = ws[f"a{i - 1}"] if i > 0 else ws["x0"]
+            x = ws[f"a{i - 1}_b"] if i > 0 else ws["x0_b"]
             acc.zero_()
             ops.conv_wgrad(x, dy, acc, self._shape(i, B))
             ops.unpack_conv_wgrad(acc, c.weight.grad, cip)

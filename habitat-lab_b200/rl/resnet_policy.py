@@ -390,6 +390,11 @@ class EncoderEngine:
         for j, (ca, cb, cd) in enumerate(self.blocks):
             ws[f"a{j}"] = e(B, *ca.out_hw, ca.co)
             ws[f"o{j}"] = e(B, *cb.out_hw, cb.co)
+        if train:
+            # bf16 twins of every conv INPUT: the weight-gradient MMAs need x in the gradients' format (bf16 x bf16);
+            # the forward convs keep reading the fp16 originals.  Written by the same elementwise kernels.
+            for nm in ["x0", "x1"] + [f"{k}{j}" for j in range(len(self.blocks)) for k in ("a", "o")]:
+                ws[nm + "_b"] = torch.empty_like(ws[nm], dtype=BF16)
         ncomp, fh, fw = self.enc.output_shape
         ws["feat"] = torch.empty(B, ncomp * fh * fw, device=dev)
         if train:
@@ -425,7 +430,7 @@ class EncoderEngine:
         if train or wkey is None or wkey != self._packed_key:
             self.pack_weights()
             self._packed_key = wkey
-        x0_writer(ws["x0"])
+        x0_writer(ws["x0"], ws.get("x0_b"))
         idx = {id(c): i for i, c in enumerate(self.convs)}
         ws["st_all"].zero_()
 
@@ -444,19 +449,21 @@ class EncoderEngine:
         y, st = conv(self.stem, ws["x0"])
         sh, sw = self.stem.out_hw
         ops.gn_relu_maxpool(y, st, self.stem.gamma, self.stem.beta, ws["x1"], ws["argmax"], B, sh, sw,
-                            self.stem.co, self.stem.groups)
+                            self.stem.co, self.stem.groups, out_bf16=ws.get("x1_b"))
         x = ws["x1"]
         for j, (ca, cb, cd) in enumerate(self.blocks):
             ya, sa = conv(ca, x)
             hw = ca.out_hw[0] * ca.out_hw[1]
-            ops.gn_apply(ya, sa, ca.gamma, ca.beta, ws[f"a{j}"], B, hw, ca.co, ca.groups, relu=True)
+            ops.gn_apply(ya, sa, ca.gamma, ca.beta, ws[f"a{j}"], B, hw, ca.co, ca.groups, relu=True,
+                         out_bf16=ws.get(f"a{j}_b"))
             yb, sb = conv(cb, ws[f"a{j}"])
             if cd is not None:
                 yd, sd = conv(cd, x)
                 ops.gn_residual_relu(yb, sb, cb.gamma, cb.beta, yd, ws[f"o{j}"], B, hw, cb.co, cb.groups, sd,
-                                     cd.gamma, cd.beta)
+                                     cd.gamma, cd.beta, out_bf16=ws.get(f"o{j}_b"))
             else:
-                ops.gn_residual_relu(yb, sb, cb.gamma, cb.beta, x, ws[f"o{j}"], B, hw, cb.co, cb.groups)
+                ops.gn_residual_relu(yb, sb, cb.gamma, cb.beta, x, ws[f"o{j}"], B, hw, cb.co, cb.groups,
+                                     out_bf16=ws.get(f"o{j}_b"))
             x = ws[f"o{j}"]
         yc, sc = conv(self.comp, x)
         fhw = self.comp.out_hw[0] * self.comp.out_hw[1]
@@ -519,7 +526,7 @@ class EncoderEngine:
         ops.f32_chw_to_bf16_hwc(d_feat, g, B, fhw, comp.co)
         dy, _ = gn_bwd(comp, g, None, 1, False)
         x_last = ws[f"o{len(self.blocks) - 1}"]
-        wgrad(comp, x_last, dy)
+        wgrad(comp, ws[f"o{len(self.blocks) - 1}_b"], dy)
         cur ^= 1
         g = g_bufs[cur][: x_last.numel()].view_as(x_last)
         self._dgrad(comp, dy, g, B)
@@ -527,20 +534,21 @@ class EncoderEngine:
         for j in reversed(range(len(self.blocks))):
             ca, cb, cd = self.blocks[j]
             xin = ws[f"o{j - 1}"] if j > 0 else ws["x1"]
+            xin_b = ws[f"o{j - 1}_b"] if j > 0 else ws["x1_b"]    # bf16 twin: the weight gradients' x operand
             out = ws[f"o{j}"]
             dyb, gz = gn_bwd(cb, g, out, 2, True)                 # g: grad wrt block output
-            wgrad(cb, ws[f"a{j}"], dyb)
+            wgrad(cb, ws[f"a{j}_b"], dyb)
             cur ^= 1
             ga = g_bufs[cur][: ws[f"a{j}"].numel()].view_as(ws[f"a{j}"])
             self._dgrad(cb, dyb, ga, B)                           # grad wrt a = relu(GN(ya))
             gz_keep = gz  # ws["gz"] is only rewritten by the next block's GN_b backward
             dya, _ = gn_bwd(ca, ga, None, 1, False)
-            wgrad(ca, xin, dya)
+            wgrad(ca, xin_b, dya)
             gx = g_bufs[cur][: xin.numel()].view_as(xin)          # ga is consumed; reuse its buffer
             if cd is not None:
                 self._dgrad(ca, dya, gx, B)
                 dyd, _ = gn_bwd(cd, gz_keep, None, 0, False)
-                wgrad(cd, xin, dyd)
+                wgrad(cd, xin_b, dyd)
                 self._dgrad(cd, dyd, gx, B, addend=gx)
             else:
                 self._dgrad(ca, dya, gx, B, addend=gz_keep)
@@ -558,7 +566,7 @@ class EncoderEngine:
             gzs = g_bufs[cur][: Y(stem).numel()].view_as(Y(stem))
             ops.maxpool_bwd(g, ws["argmax"], gzs, B, sh, sw, stem.co)
             dy0, _ = gn_bwd(stem, gzs, None, 1, False)
-        wgrad(stem, ws["x0"], dy0)
+        wgrad(stem, ws["x0_b"], dy0)
         side.join()
 
 
@@ -922,8 +930,8 @@ class PointNavResNetPolicy(NativeNetPolicy):
                               update_stats)
         s2d = self._engine_().stem.stem_s2d
 
-        def write(x0):
-            ops.prep_apply(rgb, depth, rows, H, W, scale_shift, x0, s2d=s2d)
+        def write(x0, x0_bf16=None):
+            ops.prep_apply(rgb, depth, rows, H, W, scale_shift, x0, s2d=s2d, out_bf16=x0_bf16)
 
         return write
 

@@ -13,7 +13,15 @@
  *    status: 0 ok, <0 error (message via hb200_last_error()).
  *  - the library never allocates or frees caller memory; scratch is passed in and sized
  *    by the *_workspace_bytes twin.
- *  - activations are NHWC; "bf16" pointers are raw uint16 bfloat16 storage.
+ *  - activations are NHWC.  16-bit tensors are raw uint16 storage typed by ROLE (both typedefs are uint16_t, the
+ *    element format is fixed per argument): FORWARD values -- the pooled network input, conv outputs `y`, normalised
+ *    activations, the packed forward weight images -- are IEEE fp16 (11-bit significand: what the reference's TF32
+ *    cuDNN convolutions keep of their operands); GRADIENTS (g / dy / dx / gz / addend), the transposed (dgrad)
+ *    weight images and the `*_bf16` twin outputs read by the weight-gradient kernels are bfloat16.  tcgen05
+ *    kind::f16 needs both MMA operands in ONE format, so the forward kernels can write a second, bf16-rounded copy
+ *    of an activation (`out_bf16`, optional): the weight gradient dW = sum x * dy then multiplies bf16 x with bf16 dy.
+ *    Rounding x there is harmless (a linear perturbation); rounding it in the FORWARD pass is not (it flips ReLU /
+ *    max-pool decisions), which is why the forward copy is fp16.
  */
 #ifndef HB200_H_
 #define HB200_H_
@@ -31,7 +39,8 @@ extern "C" {
 #define HB200_ERR_UNSUPPORTED (-3)
 
 typedef void* hb200_stream_t; /* cudaStream_t */
-typedef uint16_t hb200_bf16;
+typedef uint16_t hb200_bf16; /* bfloat16 bits: gradients, dgrad weight images, bf16 activation twins */
+typedef uint16_t hb200_f16;  /* IEEE fp16 bits: forward values */
 
 /* ---- library ---------------------------------------------------------------- */
 const char* hb200_last_error(void);
@@ -140,7 +149,8 @@ int hb200_prep_finalize(const double* stats_acc, float* run_mean, float* run_var
  * a 4x4 stride-1 convolution.  scale_shift NULL -> no normalisation (normalize_visual_inputs=False). */
 int hb200_prep_apply(const uint8_t* rgb, const float* depth, const int32_t* frame_rows, int batch,
                      int height, int width, int c_rgb, int c_depth, float rgb_scale,
-                     const float* scale_shift, hb200_bf16* out, int s2d, hb200_stream_t stream);
+                     const float* scale_shift, hb200_f16* out, hb200_bf16* out_bf16, int s2d,
+                     hb200_stream_t stream);
 
 /* SimpleCNN input (HB/rl/models/simple_cnn.py:139-157): rgb/255 and raw depth concatenated, bf16 NHWC
  * [B,H,W,8] (zero padded channels), no pooling; rows gathered through frame_rows */
@@ -236,20 +246,20 @@ int hb200_umma_gemm_probe(const hb200_bf16* a, const hb200_bf16* b, float* d, in
  */
 /* out = act(gamma * (y - mu) * rstd + beta);  relu: 0/1;  out_f32: 0 -> bf16 NHWC, 1 -> f32 NHWC,
  * 2 -> f32 [B, C*hw] flattened in (c,h,w) order (what nn.Flatten of the NCHW map feeds visual_fc) */
-int hb200_gn_apply(const hb200_bf16* y, const double* stats, const float* gamma, const float* beta,
-                   void* out, int out_f32, int batch, int hw, int channels, int groups, float eps,
-                   int relu, hb200_stream_t stream);
+int hb200_gn_apply(const hb200_f16* y, const double* stats, const float* gamma, const float* beta,
+                   void* out, hb200_bf16* out_bf16, int out_f32, int batch, int hw, int channels, int groups,
+                   float eps, int relu, hb200_stream_t stream);
 /* out = relu(GN(y) + res)  with res either an activation tensor (res_stats NULL) or a second
  * pre-norm tensor normalised with (res_stats, res_gamma, res_beta) (downsample branch). */
-int hb200_gn_residual_relu(const hb200_bf16* y, const double* stats, const float* gamma,
-                           const float* beta, const hb200_bf16* res, const double* res_stats,
-                           const float* res_gamma, const float* res_beta, hb200_bf16* out,
-                           int batch, int hw, int channels, int groups, float eps,
+int hb200_gn_residual_relu(const hb200_f16* y, const double* stats, const float* gamma,
+                           const float* beta, const hb200_f16* res, const double* res_stats,
+                           const float* res_gamma, const float* res_beta, hb200_f16* out,
+                           hb200_bf16* out_bf16, int batch, int hw, int channels, int groups, float eps,
                            hb200_stream_t stream);
 /* out[B,H/2,W/2,C] = maxpool3x3s2p1(relu(GN(y[B,H,W,C]))); argmax u8 (0..8) saved for bwd */
-int hb200_gn_relu_maxpool(const hb200_bf16* y, const double* stats, const float* gamma,
-                          const float* beta, hb200_bf16* out, uint8_t* argmax, int batch, int h,
-                          int w, int channels, int groups, float eps, hb200_stream_t stream);
+int hb200_gn_relu_maxpool(const hb200_f16* y, const double* stats, const float* gamma,
+                          const float* beta, hb200_f16* out, hb200_bf16* out_bf16, uint8_t* argmax, int batch,
+                          int h, int w, int channels, int groups, float eps, hb200_stream_t stream);
 /* dz[B,H,W,C] (grad wrt the GN output BEFORE relu masking is applied by the GN backward)
  * scattered from dout[B,H/2,W/2,C] through argmax */
 int hb200_maxpool_bwd(const hb200_bf16* dout, const uint8_t* argmax, hb200_bf16* dz, int batch,
@@ -306,6 +316,9 @@ int hb200_tgemm(const float* a, long long a_ms, long long a_ks, const float* b, 
 /* dst[c,r] = src[r,c] (fp32): feeds hb200_tgemm K-major operands for the data / weight gradient GEMMs */
 int hb200_transpose_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int rows, int cols,
                         hb200_stream_t stream);
+/* out_bf16[i] = bf16(x_f16[i]) (n % 8 == 0): the bf16 twin of a forward activation produced by a conv epilogue
+ * (SimpleCNN, HB/rl/models/simple_cnn.py:68-93), read by the weight-gradient kernels */
+int hb200_f16_to_bf16(const hb200_f16* x, hb200_bf16* out, long long n, hb200_stream_t stream);
 /* bf16 activations [M,K] (optionally GN+ReLU applied on load: stats/gamma/beta non-NULL with
  * per-row frame = m, K laid out NHWC (hw, C)) -> f32 [M,K].  Feeds visual_fc. */
 int hb200_bf16_to_f32(const hb200_bf16* x, float* out, long long n, hb200_stream_t stream);
