@@ -632,13 +632,17 @@ conv_halo_tma_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap)
     oh0 = (r / tiles_x) * TH;
     ow0 = (r % tiles_x) * TW;
   };
-  auto issue_halo = [&](int tile, int stage) {   // thread 0 only
+  // The descriptor must be addressed in PARAM space: `&tmap` evaluated here, in the kernel body.  Inside the lambda a
+  // by-reference capture makes nvcc spill a thread-local copy of the 128-byte map and hand the TMA unit a stack
+  // address (round-1 version: every tile loaded garbage).
+  const CUtensorMap* const tmap_p = &tmap;
+  auto issue_halo = [&, tmap_p](int tile, int stage) {   // thread 0 only
     int b, oh0, ow0;
     tile_coords(tile, b, oh0, ow0);
     mbar_expect_tx(&ld_bar[stage], (uint32_t)(CJ * HH * HWD * 16));
 #pragma unroll
     for (int j = 0; j < CJ; ++j)
-      tma_load_4d(s_halo0 + (uint32_t)stage * STAGE + (uint32_t)j * SLAB, &tmap, &ld_bar[stage], j * 8, ow0 - PAD,
+      tma_load_4d(s_halo0 + (uint32_t)stage * STAGE + (uint32_t)j * SLAB, tmap_p, &ld_bar[stage], j * 8, ow0 - PAD,
                   oh0 - PAD, b);
   };
   const int first = blockIdx.x, stride = gridDim.x;
