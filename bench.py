@@ -505,9 +505,9 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
 
     inputs = {id(eng.stem): ws["x0"]}
     x = ws["x1"]
-    for j, (ca, cb, cd) in enumerate(eng.blocks):
-        inputs[id(ca)] = x
-        inputs[id(cb)] = ws[f"a{j}"]
+    for j, (convs, cd) in enumerate(eng.blocks):
+        for i, c in enumerate(convs):
+            inputs[id(c)] = x if i == 0 else ws[f"a{j}_{i - 1}"]
         if cd is not None:
             inputs[id(cd)] = x
         x = ws[f"o{j}"]

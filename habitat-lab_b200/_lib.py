@@ -85,6 +85,11 @@ SIGNATURES = {
     "hb200_heads_fwd": ("i", "ppppp" + "iii" + "pp" + "p"),
     "hb200_embed_fwd": ("i", "pppppppp" + "iii" + "p"),
     "hb200_embed_bwd": ("i", "ppppp" + "iiii" + "ppp" + "p"),
+    "hb200_sensor_linear_fwd": ("i", "pipii" + "ppp" + "iii" + "p"),
+    "hb200_sensor_linear_bwd": ("i", "pipii" + "p" + "iii" + "pp" + "p"),
+    "hb200_index_embed_fwd": ("i", "pppii" + "pip" + "ii" + "p"),
+    "hb200_index_embed_bwd": ("i", "pppiii" + "p" + "ii" + "p" + "p"),
+    "hb200_prep_generic": ("i", "pppp" + "i" + "p" + "iii" + "pppp" + "p"),
 }
 
 

@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
 // one M = 128 tile) and NS output channels: accumulators = 3 horizontal taps x NS columns (NS = 128 -> 384).
 // grid = (tile workers, Ci/32 * Co/NS slices); results are accumulated into dw with vector red.add.
 // ------------------------------------------------------------------------------------------
+constexpr int kSmallWgradStages = 3;
 struct HaloWgradSmallArgs {
   const grad_t* x;    // [B, IMG, IMG, Ci]  bf16 twin of the forward activation
   const grad_t* dy;   // [B, IMG, IMG, Co]  bf16
@@ -416,11 +417,12 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
   constexpr int HALO_BYTES = HROWS_A * RP;
   constexpr int DY_BYTES = 128 * NS * 2;
   constexpr int STAGE = HALO_BYTES + DY_BYTES;
+  constexpr int NST = kSmallWgradStages;        // 3-deep ring: the loads of tile it+2 overlap the MMAs of tiles it, it+1
   constexpr int TCOLS_RAW = KW * NS;
   constexpr int TMEM_COLS = TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
   static_assert(TCOLS_RAW <= 512, "accumulators exceed TMEM");
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ __align__(8) uint64_t mma_bar[NST];
   __shared__ uint32_t tmem_slot;
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -428,22 +430,26 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
   const int c_off = (blockIdx.y / nsl) * 32, n_off = (blockIdx.y % nsl) * NS;
 
   if (tid == 0) {
-    mbar_init(&mma_bar[0], 1);
-    mbar_init(&mma_bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < NST; ++i) mbar_init(&mma_bar[i], 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   // rows beyond the loaded ones are read by the (discarded) padding M rows: keep them finite
-  for (int st = 0; st < 2; ++st)
+  for (int st = 0; st < NST; ++st)
     for (int v = tid; v < (HROWS_A - HROWS_LOAD) * RP / 16; v += 128) {
       const uint32_t addr = sbase + st * STAGE + HROWS_LOAD * RP + v * 16;
       asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
     }
+  // Warps 1-3 are the loaders (96 threads), warp 0 only issues MMAs: the MMA-issuing thread never spends its issue
+  // slots on the ~22 address / predicate computations per tile (it was the critical path of the first version).
   auto load_tile = [&](int tile, int st) {
+    if (warp == 0) return;
+    const int lt = tid - 32;
     const uint32_t sh = sbase + st * STAGE;
     const int b0 = tile * IPT;
     // x halo: [halo row][cj][halo col] 16-byte vectors; image j occupies halo rows j*RPI .. j*RPI + IMG + 1
-    for (int v = tid; v < HROWS_LOAD * CJ * HWD; v += 128) {
+    for (int v = lt; v < HROWS_LOAD * CJ * HWD; v += 96) {
       const int cj = v % CJ;
       const int t = v / CJ;
       const int hx = t % HWD, hy = t / HWD;
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
     }
     // dy tile: [n-chunk][py][px]; pixels px >= IMG are virtual (dy = 0)
     const uint32_t sd = sh + HALO_BYTES;
-    for (int v = tid; v < 128 * (NS / 8); v += 128) {
+    for (int v = lt; v < 128 * (NS / 8); v += 96) {
       const int nj = v % (NS / 8), p = v / (NS / 8);
       const int ppy = p >> 3, ppx = p & 7;
       const int j = ppy / IMG, y = ppy - j * IMG;
@@ -467,8 +473,12 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
   };
   const int first = blockIdx.x, stride = gridDim.x;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
-  if (my_n > 0) load_tile(first, 0);
-  cp_async_commit();
+  // prologue: tiles 0 .. NST-2 in flight, one cp.async group per tile
+#pragma unroll
+  for (int i = 0; i < NST - 1; ++i) {
+    if (i < my_n) load_tile(first + i * stride, i);
+    cp_async_commit();
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -476,15 +486,13 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
   constexpr uint32_t idesc = make_idesc_bf16(128, NS, 1, 1);
 
   for (int it = 0; it < my_n; ++it) {
-    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-    if (it + 1 < my_n) load_tile(first + (it + 1) * stride, (it + 1) & 1);
-    cp_async_commit();
-    cp_async_wait<1>();
+    const int st = it % NST;
+    cp_async_wait<NST - 2>();        // this thread's copies of tile it have landed
     fence_proxy_async_smem();
-    __syncthreads();
+    __syncthreads();                 // ... and everybody else's
     if (tid == 0) {
       fence_after_sync();
-      const uint32_t sh = sbase + (it & 1) * STAGE;
+      const uint32_t sh = sbase + st * STAGE;
       const uint32_t sd = sh + HALO_BYTES;
 #pragma unroll
       for (int s = 0; s < KW; ++s)
@@ -496,11 +504,19 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
           const uint64_t db = make_smem_desc(sd + 2 * ks * 128, 128, 128 * 16, kNoSwizzle);
           mma_bf16_ss(tmem_base + (uint32_t)(s * NS), da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
         }
-      mma_commit(&mma_bar[it & 1]);
+      mma_commit(&mma_bar[st]);
     }
+    // refill the stage tile it-1 used with tile it+NST-1 (its MMAs were queued before tile it's, which now keep the
+    // tensor core busy while we wait and load)
+    const int nt = it + NST - 1;
+    if (nt < my_n) {
+      if (it >= 1) mbar_wait(&mma_bar[(it - 1) % NST], ((it - 1) / NST) & 1);
+      load_tile(first + nt * stride, nt % NST);
+    }
+    cp_async_commit();
   }
   if (my_n > 0) {
-    mbar_wait(&mma_bar[(my_n - 1) & 1], ((my_n - 1) >> 1) & 1);
+    mbar_wait(&mma_bar[(my_n - 1) % NST], ((my_n - 1) / NST) & 1);
     fence_after_sync();
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int blk = tid >> 3;                  // row block (r, cj)
@@ -575,8 +591,8 @@ __global__ void unpack_stem_wgrad_kernel(const float* __restrict__ acc, float* _
 
 // resident CTAs per SM from static limits (registers, shared memory, TMEM columns); cached per kernel
 // ------------------------------------------------------------------------------------------
-// EXPERIMENTAL (HB200_HALO_TMA=1, off by default; written at the end of round 1 without GPU time left to run it):
-// the same persistent forward / dgrad kernel with the halo loaded by TMA.  One thread issues C/8
+// DEFAULT for the 32-channel 3x3 layers and the stem since round 2 (HB200_NO_HALO_TMA=1 falls back to the cp.async
+// kernel above): the same persistent forward / dgrad kernel with the halo loaded by TMA.  One thread issues C/8
 // `cp.async.bulk.tensor.4d` box copies per tile (box = {8 channels, halo width, halo height, 1 frame}; the conv
 // padding is the TMA unit's out-of-bounds zero fill) that complete on an mbarrier, instead of ~6 predicated
 // cp.async per thread -- the address / predicate arithmetic that makes conv_halo_kernel<32,32> issue-bound
@@ -859,7 +875,7 @@ static int launch_halo_wgrad_small(const HaloWgradSmallArgs& a, cudaStream_t st)
   constexpr int RP = 4 * (TW + 2) * 16, IPT = TH / IMG, RPI = IMG + 2;
   constexpr int HROWS_LOAD = IPT * RPI, HROWS = (IPT - 1) * RPI + (IMG - 2) + 1 + 4;
   constexpr int HROWS_A = HROWS > HROWS_LOAD ? HROWS : HROWS_LOAD;
-  const size_t smem = 2 * (size_t)(HROWS_A * RP + 128 * NS * 2) + 256;
+  const size_t smem = kSmallWgradStages * (size_t)(HROWS_A * RP + 128 * NS * 2) + 256;
   auto kern = conv_halo_wgrad_small_kernel<NS, IMG>;
   static bool attr = false;
   if (!attr) {
@@ -927,7 +943,9 @@ extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb20
   a.B = batch; a.H = h; a.W = w; a.gn_groups = gn_groups > 0 ? gn_groups : 1;
   a.ntiles = batch * (h / TH) * (w / TW);
   cudaStream_t st = (cudaStream_t)stream;
-  static const bool use_tma = getenv("HB200_HALO_TMA") != nullptr;   // experimental TMA halo load (see above)
+  // TMA-fed halo (conv_halo_tma_kernel) for the 32-channel layers and the stem: measured 17-18 % faster than the
+  // cp.async gather on B200 (0.219 -> 0.183 ms per 32->32 layer, stem 0.711 -> 0.581 ms); HB200_NO_HALO_TMA=1 disables
+  static const bool use_tma = getenv("HB200_NO_HALO_TMA") == nullptr;
   if (use_tma && k == 3 && c == 32)
     return mode == 0 ? launch_halo_tma<32, 32, 3, 3, 1, 0>(a, st) : launch_halo_tma<32, 32, 3, 3, 1, 1>(a, st);
   if (use_tma && k == 4 && mode == 0) return launch_halo_tma<16, 32, 4, 4, 2, 0>(a, st);

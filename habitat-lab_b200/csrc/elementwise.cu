@@ -328,7 +328,7 @@ gn_residual_relu_kernel(const act_t* __restrict__ y, GnP p, const act_t* __restr
 __global__ void __launch_bounds__(256)
 gn_relu_maxpool_kernel(const act_t* __restrict__ y, GnP p, act_t* __restrict__ out, grad_t* __restrict__ out2,
                        uint8_t* __restrict__ argmax, int B, int H, int W) {
-  const int cv = p.C >> 3, Ho = H / 2, Wo = W / 2;
+  const int cv = p.C >> 3, Ho = (H + 1) / 2, Wo = (W + 1) / 2;   // MaxPool2d(3, 2, 1): floor((H + 2 - 3) / 2) + 1
   const long long total = (long long)B * Ho * Wo * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -451,7 +451,7 @@ gn_relu_maxpool_slab_kernel(const act_t* __restrict__ y, GnP p, act_t* __restric
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const grad_t* __restrict__ dout, const uint8_t* __restrict__ argmax,
                    grad_t* __restrict__ dz, int B, int H, int W, int C) {
-  const int cv = C >> 3, Ho = H / 2, Wo = W / 2;
+  const int cv = C >> 3, Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long long total = (long long)B * H * W * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1106,6 +1106,174 @@ __global__ void embed_bwd_kernel(const float* __restrict__ goal, const int64_t* 
   }
 }
 
+
+// ---- generic 1-D sensors of PointNavResNetNet.forward (resnet_policy.py:658-763) -----------------------------
+// feature transforms: 0 identity (gps, pointgoal, proximity, 1-D fuse keys), 1 polar-2D (r, cos(-t), sin(-t)),
+// 2 polar-3D (r, cos(-t) sin(p), sin(-t) sin(p), cos(p)), 3 angle -> (cos, sin) (compass, heading)
+__device__ __forceinline__ int sensor_features(const float* __restrict__ x, int in_dim, int transform, float (&f)[8]) {
+  if (transform == 1) {
+    f[0] = x[0]; f[1] = cosf(-x[1]); f[2] = sinf(-x[1]);
+    return 3;
+  }
+  if (transform == 2) {
+    const float vs = sinf(x[2]);
+    f[0] = x[0]; f[1] = cosf(-x[1]) * vs; f[2] = sinf(-x[1]) * vs; f[3] = cosf(x[2]);
+    return 4;
+  }
+  if (transform == 3) {
+    f[0] = cosf(x[0]); f[1] = sinf(x[0]);
+    return 2;
+  }
+  for (int k = 0; k < in_dim && k < 8; ++k) f[k] = x[k];
+  return in_dim < 8 ? in_dim : 8;
+}
+// out[f, col0 + j] = b[j] + sum_k w[j, k] feat_k(x[row_f])   (w == nullptr: the features themselves, j < nfeat)
+__global__ void sensor_linear_fwd_kernel(const float* __restrict__ x, int in_dim, const int32_t* __restrict__ rows,
+                                         int B, int transform, const float* __restrict__ w, const float* __restrict__ b,
+                                         float* __restrict__ out, int ld, int col0, int out_dim) {
+  const long long total = (long long)B * out_dim;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / out_dim), j = (int)(i - (long long)f * out_dim);
+    float ft[8];
+    const int nf = sensor_features(x + (size_t)rows[f] * in_dim, in_dim, transform, ft);
+    float v;
+    if (w == nullptr) {
+      v = ft[j];
+    } else {
+      v = b[j];
+      for (int k = 0; k < nf; ++k) v = fmaf(w[j * nf + k], ft[k], v);
+    }
+    out[(size_t)f * ld + col0 + j] = v;
+  }
+}
+// d_w[j, k] += sum_f d_out[f, col0 + j] feat_k ; d_b[j] += sum_f d_out[f, col0 + j]   (out_dim <= 64, nfeat <= 8)
+__global__ void sensor_linear_bwd_kernel(const float* __restrict__ x, int in_dim, const int32_t* __restrict__ rows,
+                                         int B, int transform, const float* __restrict__ d_out, int ld, int col0,
+                                         int out_dim, float* __restrict__ d_w, float* __restrict__ d_b) {
+  __shared__ float acc[64 * 9];
+  for (int i = threadIdx.x; i < out_dim * 9; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const long long total = (long long)B * out_dim;
+  int nf = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / out_dim), j = (int)(i - (long long)f * out_dim);
+    float ft[8];
+    nf = sensor_features(x + (size_t)rows[f] * in_dim, in_dim, transform, ft);
+    const float d = d_out[(size_t)f * ld + col0 + j];
+    for (int k = 0; k < nf; ++k) atomicAdd(&acc[j * 9 + k], d * ft[k]);
+    atomicAdd(&acc[j * 9 + 8], d);
+  }
+  __syncthreads();
+  float ft0[8];
+  const float zero[3] = {0.f, 0.f, 0.f};
+  nf = sensor_features(zero, in_dim, transform, ft0);   // feature count only
+  for (int i = threadIdx.x; i < out_dim * 9; i += blockDim.x) {
+    const int j = i / 9, k = i - j * 9;
+    const float v = acc[i];
+    if (v == 0.f) continue;
+    if (k == 8) atomicAdd(&d_b[j], v);
+    else if (k < nf) atomicAdd(&d_w[j * nf + k], v);
+  }
+}
+// out[f, col0 + j] = table[index_f, j]; index from an int64 tensor through rows (objectgoal) or, with masks,
+// masks[f] ? idx[f] + 1 : 0 (the previous-action embedding with its "start" token, resnet_policy.py:747-757)
+__global__ void index_embed_fwd_kernel(const int64_t* __restrict__ idx, const int32_t* __restrict__ rows,
+                                       const uint8_t* __restrict__ masks, int B, int n_rows_table,
+                                       const float* __restrict__ table, int width, float* __restrict__ out, int ld,
+                                       int col0) {
+  const long long total = (long long)B * width;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / width), j = (int)(i - (long long)f * width);
+    long long k = idx[rows ? (size_t)rows[f] : (size_t)f];
+    if (masks) k = masks[f] ? k + 1 : 0;
+    // an index outside the table has no embedding (torch device-asserts): poison the row
+    out[(size_t)f * ld + col0 + j] = (k >= 0 && k < n_rows_table) ? table[k * width + j] : __int_as_float(0x7fc00000);
+  }
+}
+__global__ void index_embed_bwd_kernel(const int64_t* __restrict__ idx, const int32_t* __restrict__ rows,
+                                       const uint8_t* __restrict__ masks, int B, int n_rows_table, int width,
+                                       const float* __restrict__ d_out, int ld, int col0, float* __restrict__ d_table) {
+  const long long total = (long long)B * width;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / width), j = (int)(i - (long long)f * width);
+    long long k = idx[rows ? (size_t)rows[f] : (size_t)f];
+    if (masks) k = masks[f] ? k + 1 : 0;
+    if (k >= 0 && k < n_rows_table) atomicAdd(&d_table[k * width + j], d_out[(size_t)f * ld + col0 + j]);
+  }
+}
+
+// ---- generic visual input prep: any mix of u8 / f32 / i32 HWC sensors, any H x W ----------------------------------
+// (ResNetEncoder.forward, resnet_policy.py:255-271: per-key permute, u8 keys scaled by 1 / high, channel concat,
+// avg_pool2d(2) -- the odd last row / column is dropped -- then RunningMeanAndVar.)  One thread per pooled pixel;
+// the fast rgb-u8 + depth-f32 kernels above stay the path for the PointNav sensor set.
+struct PrepSrcs {
+  const void* ptr[4];
+  int dtype[4];     // 0 u8, 1 f32, 2 i32
+  int channels[4];
+  float scale[4];   // multiplied BEFORE pooling (u8: 1 / high)
+  int n;
+};
+__device__ __forceinline__ float prep_load(const void* p, int dtype, size_t i) {
+  if (dtype == 0) return (float)reinterpret_cast<const uint8_t*>(p)[i];
+  if (dtype == 1) return reinterpret_cast<const float*>(p)[i];
+  return (float)reinterpret_cast<const int32_t*>(p)[i];
+}
+template <bool STATS>
+__global__ void __launch_bounds__(256)
+prep_generic_kernel(PrepSrcs src, const int32_t* __restrict__ frame_rows, int B, int H, int W,
+                    const float* __restrict__ scale_shift, act_t* __restrict__ out, grad_t* __restrict__ out2,
+                    double* __restrict__ stats) {
+  __shared__ double red[32];
+  const int Hp = H / 2, Wp = W / 2;
+  const long long total = (long long)B * Hp * Wp;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % Wp);
+    const long long t = i / Wp;
+    const int py = (int)(t % Hp), f = (int)(t / Hp);
+    const size_t row = (size_t)frame_rows[f];
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int c0 = 0;
+    for (int k = 0; k < src.n; ++k) {
+      const int C = src.channels[k];
+      const size_t base = ((row * H + 2 * py) * (size_t)W + 2 * px) * C;
+      for (int c = 0; c < C; ++c) {
+        // avg_pool2d sums the window row-major then divides (ATen); scaled keys are scaled first
+        float a = __fmul_rn(prep_load(src.ptr[k], src.dtype[k], base + c), src.scale[k]);
+        a = __fadd_rn(a, __fmul_rn(prep_load(src.ptr[k], src.dtype[k], base + C + c), src.scale[k]));
+        a = __fadd_rn(a, __fmul_rn(prep_load(src.ptr[k], src.dtype[k], base + (size_t)W * C + c), src.scale[k]));
+        a = __fadd_rn(a, __fmul_rn(prep_load(src.ptr[k], src.dtype[k], base + (size_t)W * C + C + c), src.scale[k]));
+        v[c0 + c] = a * 0.25f;
+      }
+      c0 += C;
+    }
+    if (STATS) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { s[c] += v[c]; q[c] = fmaf(v[c], v[c], q[c]); }
+    } else {
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = (c < c0) ? (scale_shift ? fmaf(v[c], scale_shift[c], scale_shift[8 + c]) : v[c]) : 0.f;
+      reinterpret_cast<uint4*>(out)[i] = pack8a(o);
+      if (out2) reinterpret_cast<uint4*>(out2)[i] = pack8(o);
+    }
+  }
+  if (STATS) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double a = block_sum((double)s[c], red);
+      const double b = block_sum((double)q[c], red);
+      if (threadIdx.x == 0) { atomicAdd(&stats[c], a); atomicAdd(&stats[8 + c], b); }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[16] = (double)B;
+  }
+}
+
 // mask / shift helpers for the recurrent encoder
 __global__ void rnn_shift_mask_kernel(const float* __restrict__ h_seq, const float* __restrict__ h0,
                                       long long h0_stride, const uint8_t* __restrict__ masks,
@@ -1420,8 +1588,8 @@ extern "C" int hb200_gn_relu_maxpool(const hb200_f16* y, const double* stats, co
   GnP p;
   int rc = make_gn(p, stats, gamma, beta, channels, groups, h * w, eps);
   if (rc) return rc;
-  HB_CHECK_ARG(y && out && argmax && h % 2 == 0 && w % 2 == 0, "gn_relu_maxpool: bad args");
-  {
+  HB_CHECK_ARG(y && out && argmax && h > 0 && w > 0, "gn_relu_maxpool: bad args");
+  if (h % 2 == 0 && w % 2 == 0) {
     // slab path: largest even row count <= 8 dividing h whose rows+1 staged rows fit in 64 KB
     const int cv = channels / 8;
     int rows = 0;
@@ -1438,7 +1606,7 @@ extern "C" int hb200_gn_relu_maxpool(const hb200_f16* y, const double* stats, co
       return HB200_OK;
     }
   }
-  const long long total = (long long)batch * (h / 2) * (w / 2) * (channels / 8);
+  const long long total = (long long)batch * ((h + 1) / 2) * ((w + 1) / 2) * (channels / 8);
   gn_relu_maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const act_t*)y, p, (act_t*)out, (grad_t*)out_bf16, argmax, batch, h, w);
   HB_LAUNCH_OK();
@@ -1448,7 +1616,7 @@ extern "C" int hb200_gn_relu_maxpool(const hb200_f16* y, const double* stats, co
 
 extern "C" int hb200_maxpool_bwd(const hb200_bf16* dout, const uint8_t* argmax, hb200_bf16* dz,
                                  int batch, int h, int w, int channels, hb200_stream_t stream) {
-  HB_CHECK_ARG(dout && argmax && dz && channels % 8 == 0 && h % 2 == 0 && w % 2 == 0, "maxpool_bwd: bad args");
+  HB_CHECK_ARG(dout && argmax && dz && channels % 8 == 0 && h > 0 && w > 0, "maxpool_bwd: bad args");
   const long long total = (long long)batch * h * w * (channels / 8);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const grad_t*)dout, argmax, (grad_t*)dz, batch, h, w, channels);
@@ -1554,6 +1722,88 @@ extern "C" int hb200_embed_bwd(const float* goal, const int64_t* prev_actions, c
   count_launch(1);
   return HB200_OK;
 }
+
+extern "C" int hb200_sensor_linear_fwd(const float* x, int in_dim, const int32_t* frame_rows, int batch, int transform,
+                                       const float* w, const float* b, float* out, int ld, int col0, int out_dim,
+                                       hb200_stream_t stream) {
+  HB_CHECK_ARG(x && frame_rows && out && batch > 0 && in_dim >= 1 && in_dim <= 8, "sensor_linear_fwd: bad args");
+  HB_CHECK_ARG(transform >= 0 && transform <= 3 && out_dim >= 1 && out_dim <= 64, "sensor_linear_fwd: bad transform / width");
+  HB_CHECK_ARG((w && b) || (!w && transform == 0 && out_dim == in_dim), "sensor_linear_fwd: raw copy needs identity features");
+  sensor_linear_fwd_kernel<<<grid_for((long long)batch * out_dim, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, in_dim, frame_rows, batch, transform, w, b, out, ld, col0, out_dim);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_sensor_linear_bwd(const float* x, int in_dim, const int32_t* frame_rows, int batch, int transform,
+                                       const float* d_out, int ld, int col0, int out_dim, float* d_w, float* d_b,
+                                       hb200_stream_t stream) {
+  HB_CHECK_ARG(x && frame_rows && d_out && d_w && d_b && batch > 0 && in_dim >= 1 && in_dim <= 8, "sensor_linear_bwd: bad args");
+  HB_CHECK_ARG(transform >= 0 && transform <= 3 && out_dim >= 1 && out_dim <= 64, "sensor_linear_bwd: bad transform / width");
+  int grid = grid_for((long long)batch * out_dim, 256);
+  if (grid > kNumSMs) grid = kNumSMs;
+  sensor_linear_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, in_dim, frame_rows, batch, transform, d_out, ld,
+                                                                   col0, out_dim, d_w, d_b);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_index_embed_fwd(const int64_t* idx, const int32_t* frame_rows, const uint8_t* masks, int batch,
+                                     int table_rows, const float* table, int width, float* out, int ld, int col0,
+                                     hb200_stream_t stream) {
+  HB_CHECK_ARG(idx && table && out && batch > 0 && table_rows > 0 && width > 0, "index_embed_fwd: bad args");
+  index_embed_fwd_kernel<<<grid_for((long long)batch * width, 256), 256, 0, (cudaStream_t)stream>>>(
+      idx, frame_rows, masks, batch, table_rows, table, width, out, ld, col0);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_index_embed_bwd(const int64_t* idx, const int32_t* frame_rows, const uint8_t* masks, int batch,
+                                     int table_rows, int width, const float* d_out, int ld, int col0, float* d_table,
+                                     hb200_stream_t stream) {
+  HB_CHECK_ARG(idx && d_out && d_table && batch > 0 && table_rows > 0 && width > 0, "index_embed_bwd: bad args");
+  index_embed_bwd_kernel<<<grid_for((long long)batch * width, 256), 256, 0, (cudaStream_t)stream>>>(
+      idx, frame_rows, masks, batch, table_rows, width, d_out, ld, col0, d_table);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_prep_generic(const void* const* h_srcs, const int* h_dtypes, const int* h_channels,
+                                  const float* h_scales, int n_srcs, const int32_t* frame_rows, int batch, int height,
+                                  int width, const float* scale_shift, hb200_f16* out, hb200_bf16* out_bf16,
+                                  double* stats_acc, hb200_stream_t stream) {
+  HB_CHECK_ARG(h_srcs && h_dtypes && h_channels && h_scales && n_srcs >= 1 && n_srcs <= 4, "prep_generic: 1..4 sources");
+  HB_CHECK_ARG(frame_rows && batch > 0 && height >= 2 && width >= 2, "prep_generic: bad shape");
+  HB_CHECK_ARG((stats_acc != nullptr) != (out != nullptr), "prep_generic: pass either stats_acc (statistics pass) or out (apply pass)");
+  PrepSrcs src;
+  int ctot = 0;
+  for (int k = 0; k < 4; ++k) { src.ptr[k] = nullptr; src.dtype[k] = 0; src.channels[k] = 0; src.scale[k] = 1.f; }
+  for (int k = 0; k < n_srcs; ++k) {
+    HB_CHECK_ARG(h_srcs[k] && h_dtypes[k] >= 0 && h_dtypes[k] <= 2 && h_channels[k] >= 1, "prep_generic: bad source %d", k);
+    src.ptr[k] = h_srcs[k]; src.dtype[k] = h_dtypes[k]; src.channels[k] = h_channels[k]; src.scale[k] = h_scales[k];
+    ctot += h_channels[k];
+  }
+  HB_CHECK_ARG(ctot <= 8, "prep_generic: at most 8 input channels (got %d)", ctot);
+  src.n = n_srcs;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)batch * (height / 2) * (width / 2);
+  const int grid = grid_for(total, 256);
+  if (stats_acc) {
+    HB_CUDA(cudaMemsetAsync(stats_acc, 0, 17 * sizeof(double), st));
+    prep_generic_kernel<true><<<grid, 256, 0, st>>>(src, frame_rows, batch, height, width, nullptr, nullptr, nullptr, stats_acc);
+  } else {
+    prep_generic_kernel<false><<<grid, 256, 0, st>>>(src, frame_rows, batch, height, width, scale_shift, (act_t*)out,
+                                                     (grad_t*)out_bf16, nullptr);
+  }
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
 
 extern "C" int hb200_rnn_shift_mask(const float* h_seq, const float* h0, long long h0_row_stride,
                                     const uint8_t* masks, float* h_in, int t_steps, int n, int hidden,

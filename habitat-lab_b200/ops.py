@@ -389,6 +389,46 @@ def embed_bwd(goal, prev_actions, masks, frame_rows, d_out, col0, d_w_tgt, d_b_t
          d_out.stride(0), col0, frame_rows.numel(), d_emb.shape[0], ptr(d_w_tgt), ptr(d_b_tgt), ptr(d_emb))
 
 
+# ---- generic 1-D sensors / embeddings / visual prep (any sensor set of PointNavResNetNet) ----------------
+T_IDENTITY, T_POLAR2, T_POLAR3, T_COSSIN = 0, 1, 2, 3
+
+
+def sensor_linear_fwd(x, frame_rows, transform, w, b, out, col0, out_dim):
+    """x f32 [rows, in_dim] observation buffer; out f32 [B, ld]: columns [col0, col0 + out_dim) (see hb200.h)"""
+    call("hb200_sensor_linear_fwd", ptr(x), x.shape[-1], ptr(frame_rows), frame_rows.numel(), int(transform), ptr(w),
+         ptr(b), ptr(out), out.stride(0), int(col0), int(out_dim))
+
+
+def sensor_linear_bwd(x, frame_rows, transform, d_out, col0, out_dim, d_w, d_b):
+    call("hb200_sensor_linear_bwd", ptr(x), x.shape[-1], ptr(frame_rows), frame_rows.numel(), int(transform),
+         ptr(d_out), d_out.stride(0), int(col0), int(out_dim), ptr(d_w), ptr(d_b))
+
+
+def index_embed_fwd(idx, frame_rows, masks, table, out, col0, batch):
+    call("hb200_index_embed_fwd", ptr(idx), ptr(frame_rows), ptr(as_u8(masks) if masks is not None else None), int(batch),
+         table.shape[0], ptr(table), table.shape[1], ptr(out), out.stride(0), int(col0))
+
+
+def index_embed_bwd(idx, frame_rows, masks, d_out, col0, d_table, batch):
+    call("hb200_index_embed_bwd", ptr(idx), ptr(frame_rows), ptr(as_u8(masks) if masks is not None else None), int(batch),
+         d_table.shape[0], d_table.shape[1], ptr(d_out), d_out.stride(0), int(col0), ptr(d_table))
+
+
+_PREP_DTYPE = {torch.uint8: 0, torch.float32: 1, torch.int32: 2}
+
+
+def prep_generic(sources, frame_rows, H, W, scale_shift=None, out=None, out_bf16=None, stats_acc=None):
+    """sources: list of (tensor [rows, H, W, C] u8 / f32 / i32, scale).  Either `stats_acc` (statistics pass) or `out`."""
+    n = len(sources)
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t, _ in sources])
+    dts = (ctypes.c_int * n)(*[_PREP_DTYPE[t.dtype] for t, _ in sources])
+    chs = (ctypes.c_int * n)(*[t.shape[-1] for t, _ in sources])
+    scs = (ctypes.c_float * n)(*[float(s) for _, s in sources])
+    call("hb200_prep_generic", ctypes.addressof(ptrs), ctypes.addressof(dts), ctypes.addressof(chs),
+         ctypes.addressof(scs), n, ptr(frame_rows), frame_rows.numel(), int(H), int(W), ptr(scale_shift), ptr(out),
+         ptr(out_bf16), ptr(stats_acc))
+
+
 # ---- experimental probes (not on the product path) ------------------------------------------------------
 def tma_halo_probe(x, out, b, oh0, ow0, halo_h, halo_w, pad):
     """x bf16 [B,H,W,C] -> out bf16 [C/8, halo_h, halo_w, 8]: one tile's input halo loaded by TMA (see hb200.h)."""

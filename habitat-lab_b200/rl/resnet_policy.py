@@ -28,6 +28,7 @@ from .. import ops
 from .._lib import Hb200Error
 from ..common import spaces
 from ..common.baseline_registry import baseline_registry
+from .backbones import make_backbone
 
 BF16 = torch.bfloat16   # gradients (g, dy, gz) and the dgrad weight images
 F16 = torch.float16     # forward values: pooled input, conv outputs, activations, forward weight images
@@ -62,38 +63,11 @@ class RunningMeanAndVar(nn.Module):
         self.register_buffer("_count", torch.zeros(()))
 
 
-class _BasicBlock(nn.Module):
-    def __init__(self, inplanes, planes, ngroups, stride=1, downsample=None):
-        super().__init__()
-        self.convs = nn.Sequential(
-            nn.Conv2d(inplanes, planes, 3, stride, 1, bias=False), nn.GroupNorm(ngroups, planes), nn.ReLU(True),
-            nn.Conv2d(planes, planes, 3, 1, 1, bias=False), nn.GroupNorm(ngroups, planes))
-        self.downsample = downsample
-        self.stride = stride
-
-
-class _ResNet18(nn.Module):
-    def __init__(self, in_channels, base_planes, ngroups):
-        super().__init__()
-        self.conv1 = nn.Sequential(nn.Conv2d(in_channels, base_planes, 7, 2, 3, bias=False),
-                                   nn.GroupNorm(ngroups, base_planes), nn.ReLU(True))
-        inplanes = base_planes
-        for li, mult in enumerate((1, 2, 4, 8), start=1):
-            planes, stride = base_planes * mult, (1 if li == 1 else 2)
-            blocks = []
-            for b in range(2):
-                ds = None
-                s = stride if b == 0 else 1
-                if b == 0 and (s != 1 or inplanes != planes):
-                    ds = nn.Sequential(nn.Conv2d(inplanes, planes, 1, s, bias=False), nn.GroupNorm(ngroups, planes))
-                blocks.append(_BasicBlock(inplanes, planes, ngroups, s, ds))
-                inplanes = planes
-            setattr(self, f"layer{li}", nn.Sequential(*blocks))
-        self.final_channels = inplanes
-        self.final_spatial_compress = 1.0 / 32
-
-
 class ResNetEncoder(nn.Module):
+    """Parameter holder with the reference's constructor logic (resnet_policy.py:165-253): every 3-D observation
+    except the image goal is a visual key, u8 keys are rescaled by 1 / high, channels are concatenated in
+    observation-space order; the spatial / compression rule of :200-240 decides the output shape."""
+
     def __init__(self, observation_space, baseplanes=32, ngroups=16, normalize_visual_inputs=False,
                  backbone="resnet18"):
         super().__init__()
@@ -104,16 +78,14 @@ class ResNetEncoder(nn.Module):
             if v.dtype == np.uint8:
                 self.key_needs_rescaling[k] = 1.0 / float(np.max(v.high))
         self._n_input_channels = sum(observation_space.spaces[k].shape[2] for k in self.visual_keys)
+        self.key_channels = {k: observation_space.spaces[k].shape[2] for k in self.visual_keys}
         self.running_mean_and_var = (RunningMeanAndVar(self._n_input_channels)
                                      if normalize_visual_inputs else nn.Sequential())
         self.ngroups = ngroups
         if not self.is_blind:
-            if backbone != "resnet18":
-                raise NotImplementedError(f"backbone {backbone!r}: only resnet18 has sm_100a kernels so far "
-                                          "(resnet50 / resneXt50 are 'next' rows, SURVEY.md section 8f)")
             h, w = observation_space.spaces[self.visual_keys[0]].shape[:2]
             self.in_hw = (h, w)
-            self.backbone = _ResNet18(self._n_input_channels, baseplanes, ngroups)
+            self.backbone = make_backbone(backbone, self._n_input_channels, baseplanes, ngroups)
             fh = int(np.ceil((h // 2) * self.backbone.final_spatial_compress))
             fw = int(np.ceil((w // 2) * self.backbone.final_spatial_compress))
             ncomp = int(round(2048 / (fh * fw)))
@@ -150,32 +122,96 @@ class _GRUStateEncoder(nn.Module):
                 nn.init.constant_(p, 0)
 
 
+# sensor uuids (habitat/tasks/nav/nav.py:129-464, object_nav_task.py, instance_image_nav_task.py)
+OBJECTGOAL_UUID, GPS_UUID, POINTGOAL_SENSOR_UUID = "objectgoal", "gps", "pointgoal"
+HEADING_UUID, PROXIMITY_UUID, COMPASS_UUID = "heading", "proximity", "compass"
+INSTANCE_IMAGEGOAL_UUID = "instance_imagegoal"
+_GOAL_SENSOR_KEYS = {POINTGOAL_UUID, OBJECTGOAL_UUID, GPS_UUID, POINTGOAL_SENSOR_UUID, HEADING_UUID, PROXIMITY_UUID,
+                     COMPASS_UUID, IMAGEGOAL_UUID, INSTANCE_IMAGEGOAL_UUID}
+
+
 class PointNavResNetNet(nn.Module):
+    """Parameter holder + input layout of the reference Net (resnet_policy.py:394-623): one module per sensor with
+    the reference's attribute names (checkpoint keys), and `self.segments`: the column layout of the RNN input in the
+    reference's concatenation order (:625-763)."""
+
     def __init__(self, observation_space, action_space, hidden_size, num_recurrent_layers, rnn_type, backbone,
-                 resnet_baseplanes, normalize_visual_inputs):
+                 resnet_baseplanes, normalize_visual_inputs, fuse_keys=None, discrete_actions=True):
         super().__init__()
+        if not discrete_actions:
+            raise NotImplementedError("continuous prev-action input (gaussian policies) is a 'next' row (SURVEY 8f-4)")
+        sp = observation_space.spaces
         self.prev_action_embedding = nn.Embedding(action_space.n + 1, 32)
-        rnn_input_size = 32
-        if POINTGOAL_UUID not in observation_space.spaces:
-            raise NotImplementedError("hb200 policy needs the pointgoal_with_gps_compass sensor (PointNav); "
-                                      "other goal sensors are 'next' rows")
-        n_goal = observation_space.spaces[POINTGOAL_UUID].shape[0]
-        if n_goal != 2:
-            raise NotImplementedError("only the 2-D polar pointgoal is implemented")
-        self.tgt_embeding = nn.Linear(n_goal + 1, 32)  # sic: the reference's spelling
-        rnn_input_size += 32
+        if fuse_keys is None:
+            fuse_keys = [k for k in sp.keys() if k not in _GOAL_SENSOR_KEYS]
+        self._fuse_keys_1d = [k for k in fuse_keys if len(sp[k].shape) == 1]
+        segs = []   # (kind, obs key, width, module attr, transform)
+        if self._fuse_keys_1d:
+            for k in self._fuse_keys_1d:
+                segs.append(("raw", k, sp[k].shape[0], None, ops.T_IDENTITY))
+        if POINTGOAL_UUID in sp:
+            n_goal = sp[POINTGOAL_UUID].shape[0]
+            if n_goal not in (2, 3):
+                raise AssertionError("Unsupported dimensionality")   # resnet_policy.py:675-677
+            self.tgt_embeding = nn.Linear(n_goal + 1, 32)  # sic: the reference's spelling
+            segs.append(("linear", POINTGOAL_UUID, 32, "tgt_embeding", ops.T_POLAR2 if n_goal == 2 else ops.T_POLAR3))
+        if OBJECTGOAL_UUID in sp:
+            self._n_object_categories = int(sp[OBJECTGOAL_UUID].high[0]) + 1
+            self.obj_categories_embedding = nn.Embedding(self._n_object_categories, 32)
+        if GPS_UUID in sp:
+            self.gps_embedding = nn.Linear(sp[GPS_UUID].shape[0], 32)
+        if POINTGOAL_SENSOR_UUID in sp:
+            self.pointgoal_embedding = nn.Linear(sp[POINTGOAL_SENSOR_UUID].shape[0], 32)
+            segs.append(("linear", POINTGOAL_SENSOR_UUID, 32, "pointgoal_embedding", ops.T_IDENTITY))
+        if HEADING_UUID in sp:
+            assert sp[HEADING_UUID].shape[0] + 1 == 2, "Expected heading with 2D rotation."
+            self.heading_embedding = nn.Linear(2, 32)
+        if PROXIMITY_UUID in sp:
+            self.proximity_embedding = nn.Linear(sp[PROXIMITY_UUID].shape[0], 32)
+            segs.append(("linear", PROXIMITY_UUID, 32, "proximity_embedding", ops.T_IDENTITY))
+        if HEADING_UUID in sp:
+            # the reference indexes the BATCH dimension here (`sensor_observations[0]`, :703-712), which only
+            # type-checks for a single frame; per frame this is the same cos / sin feature
+            segs.append(("linear", HEADING_UUID, 32, "heading_embedding", ops.T_COSSIN))
+        if OBJECTGOAL_UUID in sp:
+            segs.append(("embed", OBJECTGOAL_UUID, 32, "obj_categories_embedding", None))
+        if COMPASS_UUID in sp:
+            assert sp[COMPASS_UUID].shape[0] == 1, "Expected compass with 2D rotation."
+            self.compass_embedding = nn.Linear(2, 32)
+            segs.append(("linear", COMPASS_UUID, 32, "compass_embedding", ops.T_COSSIN))
+        if GPS_UUID in sp:
+            segs.append(("linear", GPS_UUID, 32, "gps_embedding", ops.T_IDENTITY))
+        self._goal_encoder_uuids = []
+        for uuid in (IMAGEGOAL_UUID, INSTANCE_IMAGEGOAL_UUID):
+            if uuid in sp:
+                genc = ResNetEncoder(spaces.Dict({"rgb": sp[uuid]}), baseplanes=resnet_baseplanes,
+                                     ngroups=resnet_baseplanes // 2, normalize_visual_inputs=normalize_visual_inputs,
+                                     backbone=backbone)
+                setattr(self, f"{uuid}_encoder", genc)
+                setattr(self, f"{uuid}_fc", nn.Sequential(nn.Flatten(), nn.Linear(int(np.prod(genc.output_shape)),
+                                                                                  hidden_size), nn.ReLU(True)))
+                self._goal_encoder_uuids.append(uuid)
+                segs.append(("imagegoal", uuid, hidden_size, f"{uuid}_fc", None))
+        segs.append(("prev_action", None, 32, "prev_action_embedding", None))
         self._hidden_size = hidden_size
-        self.visual_encoder = ResNetEncoder(observation_space, baseplanes=resnet_baseplanes,
-                                            ngroups=resnet_baseplanes // 2,
+        use_space = spaces.Dict(OrderedDict((k, sp[k]) for k in fuse_keys if len(sp[k].shape) == 3))
+        self.visual_encoder = ResNetEncoder(use_space, baseplanes=resnet_baseplanes, ngroups=resnet_baseplanes // 2,
                                             normalize_visual_inputs=normalize_visual_inputs, backbone=backbone)
         if self.visual_encoder.is_blind:
             raise NotImplementedError("blind policies are not implemented")
         self.visual_fc = nn.Sequential(nn.Flatten(), nn.Linear(int(np.prod(self.visual_encoder.output_shape)),
                                                                hidden_size), nn.ReLU(True))
+        # column layout of the RNN input: [visual_fc | segments in the reference's cat order]
+        col = hidden_size
+        self.segments = []
+        for kind, key, width, attr, transform in segs:
+            self.segments.append(dict(kind=kind, key=key, width=width, attr=attr, transform=transform, col=col))
+            col += width
+        self.rnn_input_size = col
         if rnn_type.lower() == "lstm":
-            self.state_encoder = _LSTMStateEncoder(hidden_size + rnn_input_size, hidden_size, num_recurrent_layers)
+            self.state_encoder = _LSTMStateEncoder(col, hidden_size, num_recurrent_layers)
         elif rnn_type.lower() == "gru":
-            self.state_encoder = _GRUStateEncoder(hidden_size + rnn_input_size, hidden_size, num_recurrent_layers)
+            self.state_encoder = _GRUStateEncoder(col, hidden_size, num_recurrent_layers)
         else:
             raise RuntimeError(f"Did not recognize rnn type '{rnn_type}'")  # rnn_state_encoder.py:445
         self.train()
@@ -242,10 +278,17 @@ def _as_rows(observations, device):
 # conv stack engine
 # ---------------------------------------------------------------------------------------------
 class _Conv:
+    """One conv + GroupNorm unit of the encoder: geometry, packed weight images, the kernel family that serves it.
+    A grouped conv (ResNeXt's 3x3 with groups = cardinality, resnet.py:72-89) runs as a dense conv over a
+    block-diagonal weight: `dense_weight()` expands the [co, ci/g, k, k] parameter, `store_grad()` keeps the diagonal
+    blocks of the dense gradient -- copies only, the arithmetic stays on the tensor cores."""
+
     def __init__(self, conv: nn.Conv2d, gn: nn.GroupNorm, in_hw, ci_pad=None):
         self.w, self.gamma, self.beta = conv.weight, gn.weight, gn.bias
         self.groups = gn.num_groups
-        self.co, self.ci_real, self.k, _ = conv.weight.shape
+        self.conv_groups = conv.groups
+        self.co, _, self.k, _ = conv.weight.shape
+        self.ci_real = conv.in_channels
         self.ci = ci_pad or self.ci_real
         self.stride, self.pad = conv.stride[0], conv.padding[0]
         self.in_hw = in_hw
@@ -255,8 +298,12 @@ class _Conv:
         self.halo_w = False     # weight gradient served by the (multi-image tile) halo wgrad kernel
         self.stem_s2d = False   # 7x7 s2 stem as a 4x4 s1 conv over the space-to-depth input
         self.wh = self.wht = None
+        self._wd = self._gd = None
 
     def alloc_weights(self, dev, need_dgrad):
+        if self.conv_groups > 1:
+            self._wd = torch.zeros(self.co, self.ci_real, self.k, self.k, device=dev)
+            self._gd = torch.empty_like(self._wd)
         if self.stem_s2d:
             self.wh = torch.empty(16 * 16 * self.co, dtype=F16, device=dev)
             self.dw_acc = torch.empty(16 * 16, self.co, device=dev)
@@ -270,6 +317,25 @@ class _Conv:
         self.wt = (torch.empty(ops.packed_weight_elems(self.ci, self.co, self.k, self.k), dtype=BF16, device=dev)
                    if need_dgrad else None)
         self.dw_acc = torch.empty(self.k * self.k * self.ci, self.co, device=dev)
+
+    def _diag(self, dense):
+        g = self.conv_groups
+        return dense.view(g, self.co // g, g, self.ci_real // g, self.k, self.k).diagonal(dim1=0, dim2=2)
+
+    def dense_weight(self):
+        if self.conv_groups == 1:
+            return self.w.data
+        g = self.conv_groups
+        self._diag(self._wd).copy_(self.w.data.view(g, self.co // g, self.ci_real // g, self.k, self.k).permute(1, 2, 3, 4, 0))
+        return self._wd
+
+    def grad_target(self):
+        return self.w.grad if self.conv_groups == 1 else self._gd
+
+    def store_grad(self):
+        if self.conv_groups > 1:
+            g = self.conv_groups
+            self.w.grad.view(g, self.co // g, self.ci_real // g, self.k, self.k).copy_(self._diag(self._gd).permute(4, 0, 1, 2, 3))
 
     def shape(self, B):
         return ops.conv_shape(B, self.in_hw[0], self.in_hw[1], self.ci, self.co, self.k, self.k, self.stride, self.pad)
@@ -327,34 +393,46 @@ class SideStream:
 
 
 class EncoderEngine:
-    """ResNet18 (BasicBlock) + compression forward/backward on NHWC bf16 activations."""
+    """ResNet backbone (BasicBlock or Bottleneck / ResNeXt stages, resnet.py:37-151, 196-281) + compression, forward
+    and backward on NHWC activations: forward values fp16 (+ a bf16 twin of every conv input for the weight-gradient
+    MMAs), gradients bf16.  Any input size: layers whose shape the halo kernels cannot tile fall back to the gather
+    kernels automatically."""
 
     def __init__(self, enc: ResNetEncoder):
         self.enc = enc
         h, w = enc.in_hw
-        if h % 64 or w % 64:
-            raise NotImplementedError(f"visual input {h}x{w}: the sm_100a conv stack needs H, W multiples of 64")
         self.hp, self.wp_ = h // 2, w // 2
+        if enc._n_input_channels > 8:
+            raise NotImplementedError(f"{enc._n_input_channels} visual input channels: the stem kernels take up to 8")
         bb = enc.backbone
         self.stem = _Conv(bb.conv1[0], bb.conv1[1], (self.hp, self.wp_), ci_pad=8)
-        hw = tuple(d // 2 for d in self.stem.out_hw)  # maxpool 3x3 s2 p1
+        hw = tuple((d - 1) // 2 + 1 for d in self.stem.out_hw)  # MaxPool2d(3, 2, 1)
         self.pool_hw = hw
-        self.blocks = []
+        self.blocks = []   # (main-branch convs, downsample conv or None)
         for li in (1, 2, 3, 4):
             for blk in getattr(bb, f"layer{li}"):
-                ca = _Conv(blk.convs[0], blk.convs[1], hw)
-                cb = _Conv(blk.convs[3], blk.convs[4], ca.out_hw)
+                if hasattr(blk, "se"):
+                    raise NotImplementedError("squeeze-excite backbones (se_resnet50 / se_resneXt*) have no kernels yet")
+                seq = blk.convs
+                pairs = [(i, i + 1) for i in range(0, len(seq), 3)]   # (conv, GroupNorm) positions: 0-1, 3-4 (, 6-7)
+                convs, cur = [], hw
+                for ci_, gi_ in pairs:
+                    c = _Conv(seq[ci_], seq[gi_], cur)
+                    convs.append(c)
+                    cur = c.out_hw
                 cd = _Conv(blk.downsample[0], blk.downsample[1], hw) if blk.downsample is not None else None
-                self.blocks.append((ca, cb, cd))
-                hw = ca.out_hw
+                self.blocks.append((convs, cd))
+                hw = cur
         self.comp = _Conv(enc.compression[0], enc.compression[1], hw)
         assert self.comp.out_hw == tuple(enc.output_shape[1:]), (self.comp.out_hw, enc.output_shape)
-        self.convs: List[_Conv] = [self.stem] + [c for blk in self.blocks for c in blk if c is not None] + [self.comp]
+        self.convs: List[_Conv] = ([self.stem] + [c for convs, cd in self.blocks for c in convs + ([cd] if cd else [])]
+                                   + [self.comp])
         import os
         if not os.environ.get("HB200_NO_HALO"):
             for c in self.convs:
                 if c is self.stem:
                     c.stem_s2d = (c.k == 7 and c.stride == 2 and c.pad == 3 and c.ci_real <= 4 and
+                                  self.hp % 2 == 0 and self.wp_ % 2 == 0 and
                                   ops.conv_halo_supported(16, c.co, 4, c.out_hw[0], c.out_hw[1]))
                 elif c.k == 3 and c.stride == 1 and c.pad == 1:
                     c.halo = ops.conv_halo_supported(c.ci, c.co, 3, c.in_hw[0], c.in_hw[1])
@@ -365,6 +443,12 @@ class EncoderEngine:
         self.side = SideStream()
 
     # ---- buffers -----------------------------------------------------------------------------
+    def _act_names(self):
+        names = ["x0", "x1"]
+        for j, (convs, cd) in enumerate(self.blocks):
+            names += [f"a{j}_{i}" for i in range(len(convs) - 1)] + [f"o{j}"]
+        return names
+
     def _ensure(self, B, dev, train):
         if self._dev != dev:
             for c in self.convs:
@@ -383,22 +467,20 @@ class EncoderEngine:
             ws[f"y{i}"] = e(B, *c.out_hw, c.co)
             ws[f"st{i}"] = ws["st_all"][off: off + B * c.groups * 2].view(B, c.groups, 2)
             off += B * c.groups * 2
-            if train:
-                ws[f"sums{i}"] = torch.empty(B, c.groups, 2, device=dev)
         ws["x1"] = e(B, *self.pool_hw, self.stem.co)
         ws["argmax"] = torch.empty(B, *self.pool_hw, self.stem.co, dtype=torch.uint8, device=dev)
-        for j, (ca, cb, cd) in enumerate(self.blocks):
-            ws[f"a{j}"] = e(B, *ca.out_hw, ca.co)
-            ws[f"o{j}"] = e(B, *cb.out_hw, cb.co)
-        if train:
-            # bf16 twins of every conv INPUT: the weight-gradient MMAs need x in the gradients' format (bf16 x bf16);
-            # the forward convs keep reading the fp16 originals.  Written by the same elementwise kernels.
-            for nm in ["x0", "x1"] + [f"{k}{j}" for j in range(len(self.blocks)) for k in ("a", "o")]:
-                ws[nm + "_b"] = torch.empty_like(ws[nm], dtype=BF16)
+        for j, (convs, cd) in enumerate(self.blocks):
+            for i, c in enumerate(convs[:-1]):
+                ws[f"a{j}_{i}"] = e(B, *c.out_hw, c.co)
+            ws[f"o{j}"] = e(B, *convs[-1].out_hw, convs[-1].co)
         ncomp, fh, fw = self.enc.output_shape
         ws["feat"] = torch.empty(B, ncomp * fh * fw, device=dev)
         if train:
-            big = max(int(np.prod(c.out_hw)) * c.co for c in self.convs)
+            # bf16 twins of every conv INPUT: the weight-gradient MMAs need x in the gradients' format (bf16 x bf16);
+            # the forward convs keep reading the fp16 originals.  Written by the same elementwise kernels.
+            for nm in self._act_names():
+                ws[nm + "_b"] = torch.empty_like(ws[nm], dtype=BF16)
+            big = max(max(int(np.prod(c.out_hw)) * c.co, int(np.prod(c.in_hw)) * c.ci) for c in self.convs)
             for nm in ("g0", "g1", "dy", "dy2", "gz"):
                 ws[nm] = torch.empty(B * big, dtype=BF16, device=dev)
         self._ws[key] = ws
@@ -406,13 +488,14 @@ class EncoderEngine:
 
     def pack_weights(self):
         for c in self.convs:
+            w = c.dense_weight()
             if c.stem_s2d:
-                ops.pack_halo_weight(c.w.data, c.wh, 16, c.co, 4, 2)
+                ops.pack_halo_weight(w, c.wh, 16, c.co, 4, 2)
             elif c.halo:
-                ops.pack_halo_weight(c.w.data, c.wh, c.ci, c.co, 3, 0)
-                ops.pack_halo_weight(c.w.data, c.wht, c.co, c.ci, 3, 1)
+                ops.pack_halo_weight(w, c.wh, c.ci, c.co, 3, 0)
+                ops.pack_halo_weight(w, c.wht, c.co, c.ci, 3, 1)
             else:
-                ops.pack_conv_weight_into(c.w.data, c.wp, c.wt, c.ci)
+                ops.pack_conv_weight_into(w, c.wp, c.wt, c.ci)
 
     def _dgrad(self, c, dy, dx, B, addend=None):
         if c.halo:
@@ -422,10 +505,10 @@ class EncoderEngine:
 
     # ---- forward -----------------------------------------------------------------------------
     def forward(self, x0_writer, B, dev, train, wkey=None):
-        """x0_writer(x0) fills the pooled/normalised input.  Returns feat f32 [B, C*h*w] in the
+        """x0_writer(x0, x0_bf16) fills the pooled / normalised input.  Returns feat f32 [B, C*h*w] in the
         reference's (c,h,w) flatten order.  `wkey` identifies the weight values: inference calls (act / get_value
-        during a rollout) with an unchanged key reuse the packed bf16 weight images instead of re-packing 41 tensors
-        per step; training forwards always re-pack."""
+        during a rollout) with an unchanged key reuse the packed weight images instead of re-packing every tensor per
+        step; training forwards always re-pack."""
         ws = self._ensure(B, dev, train)
         if train or wkey is None or wkey != self._packed_key:
             self.pack_weights()
@@ -451,19 +534,22 @@ class EncoderEngine:
         ops.gn_relu_maxpool(y, st, self.stem.gamma, self.stem.beta, ws["x1"], ws["argmax"], B, sh, sw,
                             self.stem.co, self.stem.groups, out_bf16=ws.get("x1_b"))
         x = ws["x1"]
-        for j, (ca, cb, cd) in enumerate(self.blocks):
-            ya, sa = conv(ca, x)
-            hw = ca.out_hw[0] * ca.out_hw[1]
-            ops.gn_apply(ya, sa, ca.gamma, ca.beta, ws[f"a{j}"], B, hw, ca.co, ca.groups, relu=True,
-                         out_bf16=ws.get(f"a{j}_b"))
-            yb, sb = conv(cb, ws[f"a{j}"])
-            if cd is not None:
-                yd, sd = conv(cd, x)
-                ops.gn_residual_relu(yb, sb, cb.gamma, cb.beta, yd, ws[f"o{j}"], B, hw, cb.co, cb.groups, sd,
-                                     cd.gamma, cd.beta, out_bf16=ws.get(f"o{j}_b"))
-            else:
-                ops.gn_residual_relu(yb, sb, cb.gamma, cb.beta, x, ws[f"o{j}"], B, hw, cb.co, cb.groups,
-                                     out_bf16=ws.get(f"o{j}_b"))
+        for j, (convs, cd) in enumerate(self.blocks):
+            cur = x
+            for i, c in enumerate(convs):
+                yc, sc = conv(c, cur)
+                hw = c.out_hw[0] * c.out_hw[1]
+                if i < len(convs) - 1:     # conv -> GroupNorm -> ReLU
+                    ops.gn_apply(yc, sc, c.gamma, c.beta, ws[f"a{j}_{i}"], B, hw, c.co, c.groups, relu=True,
+                                 out_bf16=ws.get(f"a{j}_{i}_b"))
+                    cur = ws[f"a{j}_{i}"]
+                elif cd is not None:       # last conv: relu(GN(y) + GN_d(conv_d(x)))
+                    yd, sd = conv(cd, x)
+                    ops.gn_residual_relu(yc, sc, c.gamma, c.beta, yd, ws[f"o{j}"], B, hw, c.co, c.groups, sd,
+                                         cd.gamma, cd.beta, out_bf16=ws.get(f"o{j}_b"))
+                else:                      # last conv: relu(GN(y) + x)
+                    ops.gn_residual_relu(yc, sc, c.gamma, c.beta, x, ws[f"o{j}"], B, hw, c.co, c.groups,
+                                         out_bf16=ws.get(f"o{j}_b"))
             x = ws[f"o{j}"]
         yc, sc = conv(self.comp, x)
         fhw = self.comp.out_hw[0] * self.comp.out_hw[1]
@@ -511,7 +597,8 @@ class EncoderEngine:
                         ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, 3)
                     else:
                         ops.conv_wgrad(x, dy, c.dw_acc, c.shape(B))
-                    ops.unpack_conv_wgrad(c.dw_acc, c.w.grad, c.ci)
+                    ops.unpack_conv_wgrad(c.dw_acc, c.grad_target(), c.ci)
+                    c.store_grad()
                 ev = side.mark()
             for i in (0, 1):
                 if dy.data_ptr() == dy_bufs[i].data_ptr():
@@ -519,51 +606,57 @@ class EncoderEngine:
 
         g_bufs = [ws["g0"], ws["g1"]]
         cur = 0
+        like = lambda buf, t: buf[: t.numel()].view_as(t)  # noqa: E731
         # compression: relu(GN(yc)) -> visual_fc
         comp = self.comp
         fhw = comp.out_hw[0] * comp.out_hw[1]
         g = view(g_bufs[cur], comp)
         ops.f32_chw_to_bf16_hwc(d_feat, g, B, fhw, comp.co)
         dy, _ = gn_bwd(comp, g, None, 1, False)
-        x_last = ws[f"o{len(self.blocks) - 1}"]
-        wgrad(comp, ws[f"o{len(self.blocks) - 1}_b"], dy)
+        last = len(self.blocks) - 1
+        wgrad(comp, ws[f"o{last}_b"], dy)
         cur ^= 1
-        g = g_bufs[cur][: x_last.numel()].view_as(x_last)
+        g = like(g_bufs[cur], ws[f"o{last}"])
         self._dgrad(comp, dy, g, B)
         # residual blocks, last to first
         for j in reversed(range(len(self.blocks))):
-            ca, cb, cd = self.blocks[j]
+            convs, cd = self.blocks[j]
             xin = ws[f"o{j - 1}"] if j > 0 else ws["x1"]
             xin_b = ws[f"o{j - 1}_b"] if j > 0 else ws["x1_b"]    # bf16 twin: the weight gradients' x operand
-            out = ws[f"o{j}"]
-            dyb, gz = gn_bwd(cb, g, out, 2, True)                 # g: grad wrt block output
-            wgrad(cb, ws[f"a{j}_b"], dyb)
+            n = len(convs)
+            dyl, gz = gn_bwd(convs[-1], g, ws[f"o{j}"], 2, True)  # g: grad wrt the block output; gz = g * [o > 0]
+            wgrad(convs[-1], ws[f"a{j}_{n - 2}_b"], dyl)
             cur ^= 1
-            ga = g_bufs[cur][: ws[f"a{j}"].numel()].view_as(ws[f"a{j}"])
-            self._dgrad(cb, dyb, ga, B)                           # grad wrt a = relu(GN(ya))
-            gz_keep = gz  # ws["gz"] is only rewritten by the next block's GN_b backward
-            dya, _ = gn_bwd(ca, ga, None, 1, False)
-            wgrad(ca, xin_b, dya)
-            gx = g_bufs[cur][: xin.numel()].view_as(xin)          # ga is consumed; reuse its buffer
+            ga = like(g_bufs[cur], ws[f"a{j}_{n - 2}"])
+            self._dgrad(convs[-1], dyl, ga, B)                    # grad wrt a = relu(GN(y)) of the previous conv
+            for i in range(n - 2, 0, -1):
+                dyi, _ = gn_bwd(convs[i], ga, None, 1, False)
+                wgrad(convs[i], ws[f"a{j}_{i - 1}_b"], dyi)
+                cur ^= 1
+                ga = like(g_bufs[cur], ws[f"a{j}_{i - 1}"])
+                self._dgrad(convs[i], dyi, ga, B)
+            dy0, _ = gn_bwd(convs[0], ga, None, 1, False)
+            wgrad(convs[0], xin_b, dy0)
+            gx = like(g_bufs[cur], xin)                           # ga is consumed; reuse its buffer
             if cd is not None:
-                self._dgrad(ca, dya, gx, B)
-                dyd, _ = gn_bwd(cd, gz_keep, None, 0, False)
+                self._dgrad(convs[0], dy0, gx, B)
+                dyd, _ = gn_bwd(cd, gz, None, 0, False)           # ws["gz"] is only rewritten by the next block
                 wgrad(cd, xin_b, dyd)
                 self._dgrad(cd, dyd, gx, B, addend=gx)
             else:
-                self._dgrad(ca, dya, gx, B, addend=gz_keep)
+                self._dgrad(convs[0], dy0, gx, B, addend=gz)
             g = gx
         # stem: maxpool -> relu(GN(y0)) -> conv1 (input needs no gradient)
         stem = self.stem
         sh, sw = stem.out_hw
         cur ^= 1
-        if ops.gn_relu_maxpool_bwd_supported(sh, sw, stem.co, stem.groups):
+        if sh % 2 == 0 and sw % 2 == 0 and ops.gn_relu_maxpool_bwd_supported(sh, sw, stem.co, stem.groups):
             # pooled gradient -> dy of the stem conv in one pass (the 64x64 pooled gradient is never materialised)
-            dy0 = g_bufs[cur][: Y(stem).numel()].view_as(Y(stem))
+            dy0 = like(g_bufs[cur], Y(stem))
             ops.gn_relu_maxpool_bwd(g, ws["argmax"], Y(stem), ST(stem), stem.gamma, stem.beta, stem.gamma.grad,
                                     stem.beta.grad, dy0, B, sh, sw, stem.co, stem.groups)
         else:
-            gzs = g_bufs[cur][: Y(stem).numel()].view_as(Y(stem))
+            gzs = like(g_bufs[cur], Y(stem))
             ops.maxpool_bwd(g, ws["argmax"], gzs, B, sh, sw, stem.co)
             dy0, _ = gn_bwd(stem, gzs, None, 1, False)
         wgrad(stem, ws["x0_b"], dy0)
@@ -867,10 +960,11 @@ class PointNavResNetPolicy(NativeNetPolicy):
         if policy_config is not None and getattr(policy_config, "action_distribution_type", "categorical") != "categorical":
             raise NotImplementedError("only categorical action distributions are implemented")
         super().__init__(PointNavResNetNet(observation_space, action_space, hidden_size, num_recurrent_layers,
-                                           rnn_type, backbone, resnet_baseplanes, normalize_visual_inputs),
+                                           rnn_type, backbone, resnet_baseplanes, normalize_visual_inputs,
+                                           fuse_keys=fuse_keys),
                          action_space)
         self.observation_space = observation_space
-        self._engine: Optional[EncoderEngine] = None
+        self._engines: Dict[str, EncoderEngine] = {}
 
     @classmethod
     def from_config(cls, config, observation_space, action_space, **kwargs):
@@ -894,73 +988,151 @@ class PointNavResNetPolicy(NativeNetPolicy):
                    backbone=hb.rl.ddppo.backbone, normalize_visual_inputs="rgb" in observation_space.spaces,
                    force_blind_policy=getattr(hb, "force_blind_policy", False), policy_config=policy_cfg)
 
-    def _engine_(self):
-        if self._engine is None:
-            self._engine = EncoderEngine(self.net.visual_encoder)
-            self._engine.side = self._side   # one side stream for the whole backward pass
-        return self._engine
+    # ---- encoders -------------------------------------------------------------------------------------------------
+    def _encoder(self, name):
+        """name: 'visual' or an image-goal uuid -> (ResNetEncoder holder, its fc Sequential)"""
+        if name == "visual":
+            return self.net.visual_encoder, self.net.visual_fc
+        return getattr(self.net, f"{name}_encoder"), getattr(self.net, f"{name}_fc")
+
+    def _engine_(self, name="visual"):
+        if name not in self._engines:
+            eng = EncoderEngine(self._encoder(name)[0])
+            eng.side = self._side   # one side stream for the whole backward pass
+            self._engines[name] = eng
+        return self._engines[name]
 
     def refresh_inference_weights(self) -> None:
-        """Re-pack the bf16 weight images now (same buffers) and mark them current: used by GraphedActor, whose
+        """Re-pack the weight images now (same buffers) and mark them current: used by GraphedActor, whose
         captured act() step does not contain the packing kernels."""
         self.flatten_parameters_()
-        eng = self._engine_()
-        eng.pack_weights()
-        eng._packed_key = self.weights_key()
+        for name in ["visual"] + list(self.net._goal_encoder_uuids):
+            eng = self._engine_(name)
+            eng.pack_weights()
+            eng._packed_key = self.weights_key()
 
-    def _visual_prep(self, observations, rows, B, dev, update_stats):
-        enc = self.net.visual_encoder
+    def _visual_prep(self, name, observations, rows, B, dev, update_stats):
+        """Input prep of one encoder (ResNetEncoder.forward, resnet_policy.py:255-271): u8 / f32 / i32 HWC sensors ->
+        [running mean/var statistics] -> pooled, normalised fp16 NHWC (+ bf16 twin).  The rgb-u8 + depth-f32 PointNav
+        sensor set takes the vectorised kernels, anything else the generic ones."""
+        enc, _ = self._encoder(name)
+        eng = self._engine_(name)
         H, W = enc.in_hw
-        rgb = observations.get("rgb") if "rgb" in enc.visual_keys else None
-        depth = observations.get("depth") if "depth" in enc.visual_keys else None
-        for k in enc.visual_keys:
-            if k not in ("rgb", "depth"):
-                raise NotImplementedError(f"visual sensor {k!r}: only rgb (u8x3) and depth (f32x1) are implemented")
+        if name == "visual":
+            srcs = [(observations[k], enc.key_needs_rescaling[k] or 1.0) for k in enc.visual_keys]
+        else:   # goal_visual_encoder({"rgb": goal_image}), resnet_policy.py:739-742
+            srcs = [(observations[name], enc.key_needs_rescaling["rgb"] or 1.0)]
+        keys = list(enc.visual_keys)
+        fast = (keys in (["rgb", "depth"], ["rgb"], ["depth"]) and W % 8 == 0 and H % 2 == 0 and
+                all((t.dtype == torch.uint8 and t.shape[-1] == 3) if k == "rgb" else (t.dtype == torch.float32 and t.shape[-1] == 1)
+                    for k, (t, _) in zip(keys, srcs)))
+        rgb = srcs[keys.index("rgb")][0] if fast and "rgb" in keys else None
+        depth = srcs[keys.index("depth")][0] if fast and "depth" in keys else None
+        rgb_scale = srcs[keys.index("rgb")][1] if rgb is not None else 1.0 / 255.0
         rmv = enc.running_mean_and_var
         scale_shift = None
         if isinstance(rmv, RunningMeanAndVar):
             C = enc._n_input_channels
-            scale_shift = self._tmp("scale_shift", (16,), dev)
-            stats = self._tmp("prep_stats", (17,), dev, torch.float64)
+            scale_shift = self._tmp(f"scale_shift/{name}", (16,), dev)
+            stats = self._tmp(f"prep_stats/{name}", (17,), dev, torch.float64)
             if update_stats:
-                ops.prep_stats(rgb, depth, rows, H, W, stats)
+                if fast:
+                    ops.prep_stats(rgb, depth, rows, H, W, stats, rgb_scale=rgb_scale)
+                else:
+                    ops.prep_generic(srcs, rows, H, W, stats_acc=stats)
                 if self.world_size > 1:  # one packed collective instead of the reference's three
                     torch.distributed.all_reduce(stats, group=self.dist_group)
             ops.prep_finalize(stats, rmv._mean, rmv._var, rmv._count, scale_shift, C, (H // 2) * (W // 2),
                               update_stats)
-        s2d = self._engine_().stem.stem_s2d
+        s2d = eng.stem.stem_s2d
 
         def write(x0, x0_bf16=None):
-            ops.prep_apply(rgb, depth, rows, H, W, scale_shift, x0, s2d=s2d, out_bf16=x0_bf16)
+            if fast:
+                ops.prep_apply(rgb, depth, rows, H, W, scale_shift, x0, rgb_scale=rgb_scale, s2d=s2d, out_bf16=x0_bf16)
+            else:
+                ops.prep_generic(srcs, rows, H, W, scale_shift=scale_shift, out=x0, out_bf16=x0_bf16)
 
         return write
 
+    def _encode(self, name, obs, rows, B, dev, train, rnn_in, col):
+        """one encoder + its Linear/ReLU head into columns [col, col + hidden) of the RNN input"""
+        enc, fcs = self._encoder(name)
+        write_x0 = self._visual_prep(name, obs, rows, B, dev, update_stats=train and self.training)
+        feat = self._engine_(name).forward(write_x0, B, dev, train, wkey=self.weights_key())
+        fc = fcs[1]
+        ops.linear_fwd(feat, fc.weight, fc.bias, rnn_in[:, col:], relu=True, ldc=rnn_in.stride(0), tf32=True)
+        return feat
+
     def _visual_forward(self, obs, rows, pa, mk, B, dev, train):
-        H = self.net._hidden_size
-        eng = self._engine_()
-        write_x0 = self._visual_prep(obs, rows, B, dev, update_stats=train and self.training)
-        feat = eng.forward(write_x0, B, dev, train, wkey=self.weights_key())
-        # rnn input = [visual_fc | goal embedding | prev-action embedding]
-        fc = self.net.visual_fc[1]
-        D = H + 64
-        rnn_in = self._tmp("rnn_in", (B, D), dev)
-        ops.linear_fwd(feat, fc.weight, fc.bias, rnn_in, relu=True, ldc=D, tf32=True)
-        ops.embed_fwd(obs[POINTGOAL_UUID].reshape(-1, 2), pa, mk, rows, self.net.tgt_embeding.weight,
-                      self.net.tgt_embeding.bias, self.net.prev_action_embedding.weight, rnn_in, H)
-        return rnn_in, dict(feat=feat, rnn_in=rnn_in)
+        net = self.net
+        H = net._hidden_size
+        D = net.rnn_input_size
+        Dp = (D + 3) // 4 * 4                       # row pitch padded to 16 bytes (TF32 GEMM operand rows)
+        rnn_in = self._tmp("rnn_in", (B, Dp), dev)[:, :D]
+        feats = {"visual": self._encode("visual", obs, rows, B, dev, train, rnn_in, 0)}
+        segs = net.segments
+        if [sg["kind"] for sg in segs] == ["linear", "prev_action"] and segs[0]["transform"] == ops.T_POLAR2:
+            # PointNav sensor set: goal embedding + prev-action embedding in one launch
+            ops.embed_fwd(obs[POINTGOAL_UUID].reshape(-1, 2), pa, mk, rows, net.tgt_embeding.weight,
+                          net.tgt_embeding.bias, net.prev_action_embedding.weight, rnn_in, H)
+        else:
+            for sg in segs:
+                kind, col = sg["kind"], sg["col"]
+                if kind in ("linear", "raw"):
+                    x = obs[sg["key"]]
+                    x = x.reshape(-1, x.shape[-1])
+                    if x.dtype != torch.float32:
+                        raise Hb200Error(f"sensor {sg['key']!r}: expected float32 observations")
+                    m = getattr(net, sg["attr"]) if kind == "linear" else None
+                    ops.sensor_linear_fwd(x, rows, sg["transform"], m.weight if m is not None else None,
+                                          m.bias if m is not None else None, rnn_in, col, sg["width"])
+                elif kind == "embed":
+                    idx = obs[sg["key"]].reshape(-1)
+                    if idx.dtype != torch.int64:
+                        idx = idx.long()
+                    ops.index_embed_fwd(idx, rows, None, getattr(net, sg["attr"]).weight, rnn_in, col, B)
+                elif kind == "prev_action":
+                    ops.index_embed_fwd(pa, None, mk, net.prev_action_embedding.weight, rnn_in, col, B)
+                elif kind == "imagegoal":
+                    feats[sg["key"]] = self._encode(sg["key"], obs, rows, B, dev, train, rnn_in, col)
+        return rnn_in, dict(feats=feats, rnn_in=rnn_in)
 
     def _visual_backward(self, d_rnn_in, s, B, dev):
-        H = self.net._hidden_size
+        net = self.net
+        H = net._hidden_size
         v = s["visual"]
-        tg, emb = self.net.tgt_embeding, self.net.prev_action_embedding
-        ops.embed_bwd(s["obs"][POINTGOAL_UUID].reshape(-1, 2), s["pa"], s["masks"], s["rows"], d_rnn_in, H,
-                      tg.weight.grad, tg.bias.grad, emb.weight.grad)
-        fc = self.net.visual_fc[1]
-        ops.relu_bwd(d_rnn_in, v["rnn_in"], H)
-        dvis = d_rnn_in[:, :H]
-        with self._side.after_main():
-            ops.linear_bwd_weight(dvis, v["feat"], fc.weight.grad, accumulate=True, tf32=True)
-            ops.colsum(dvis, fc.bias.grad, n_cols=H)
-        d_feat = self._tmp("d_feat", tuple(v["feat"].shape), dev)
-        ops.linear_bwd_input(dvis, fc.weight, d_feat, tf32=True)
-        self._engine_().backward(d_feat, B, dev)
+        obs, rows, pa, mk = s["obs"], s["rows"], s["pa"], s["masks"]
+        segs = net.segments
+        if [sg["kind"] for sg in segs] == ["linear", "prev_action"] and segs[0]["transform"] == ops.T_POLAR2:
+            tg, emb = net.tgt_embeding, net.prev_action_embedding
+            ops.embed_bwd(obs[POINTGOAL_UUID].reshape(-1, 2), pa, mk, rows, d_rnn_in, H, tg.weight.grad, tg.bias.grad,
+                          emb.weight.grad)
+        else:
+            for sg in segs:
+                kind, col = sg["kind"], sg["col"]
+                if kind == "linear":
+                    x = obs[sg["key"]]
+                    m = getattr(net, sg["attr"])
+                    ops.sensor_linear_bwd(x.reshape(-1, x.shape[-1]), rows, sg["transform"], d_rnn_in, col, sg["width"],
+                                          m.weight.grad, m.bias.grad)
+                elif kind == "embed":
+                    idx = obs[sg["key"]].reshape(-1)
+                    ops.index_embed_bwd(idx if idx.dtype == torch.int64 else idx.long(), rows, None, d_rnn_in, col,
+                                        getattr(net, sg["attr"]).weight.grad, B)
+                elif kind == "prev_action":
+                    ops.index_embed_bwd(pa, None, mk, d_rnn_in, col, net.prev_action_embedding.weight.grad, B)
+        # encoders: visual_fc (+ image-goal fc) -> conv stacks
+        cols = [("visual", 0)] + [(sg["key"], sg["col"]) for sg in segs if sg["kind"] == "imagegoal"]
+        for name, col in cols:
+            _, fcs = self._encoder(name)
+            fc = fcs[1]
+            feat = v["feats"][name]
+            d_seg, y_seg = d_rnn_in[:, col:], v["rnn_in"][:, col:]
+            ops.relu_bwd(d_seg, y_seg, H)
+            dvis = d_seg[:, :H]
+            with self._side.after_main():
+                ops.linear_bwd_weight(dvis, feat, fc.weight.grad, accumulate=True, tf32=True)
+                ops.colsum(dvis, fc.bias.grad, n_cols=H)
+            d_feat = self._tmp(f"d_feat/{name}", tuple(feat.shape), dev)
+            ops.linear_bwd_input(dvis, fc.weight, d_feat, tf32=True)
+            self._engine_(name).backward(d_feat, B, dev)

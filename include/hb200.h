@@ -407,6 +407,38 @@ int hb200_embed_bwd(const float* goal, const int64_t* prev_actions, const uint8_
                     int n_emb, float* d_w_tgt, float* d_b_tgt, float* d_emb,
                     hb200_stream_t stream);
 
+/* ---- generic 1-D sensors of PointNavResNetNet.forward (HB/rl/ddppo/policy/resnet_policy.py:658-763) ------------
+ * x f32 [rows, in_dim] is a rollout observation buffer addressed through frame_rows (int32 [batch]).
+ * transform: 0 identity (gps :730-733, pointgoal :695-697, proximity :699-701, 1-D fuse keys :649-656),
+ *            1 2-D polar pointgoal (r, cos(-t), sin(-t)) (:662-673), 2 3-D polar (:674-691),
+ *            3 angle -> (cos, sin) (compass :718-728, heading :703-712).
+ * out[f, col0 + j] = b[j] + sum_k w[j, k] feat_k  (w f32 [out_dim, n_feat], nn.Linear layout; out_dim <= 64);
+ * w == NULL copies the features themselves (fuse keys).  _bwd accumulates d_w / d_b with atomics. */
+int hb200_sensor_linear_fwd(const float* x, int in_dim, const int32_t* frame_rows, int batch, int transform,
+                            const float* w, const float* b, float* out, int ld, int col0, int out_dim,
+                            hb200_stream_t stream);
+int hb200_sensor_linear_bwd(const float* x, int in_dim, const int32_t* frame_rows, int batch, int transform,
+                            const float* d_out, int ld, int col0, int out_dim, float* d_w, float* d_b,
+                            hb200_stream_t stream);
+/* nn.Embedding lookups: out[f, col0 + j] = table[k_f, j] with k_f = idx[frame_rows[f]] (objectgoal, :714-716;
+ * frame_rows NULL -> idx[f]) or, when masks (u8 [batch]) is given, masks[f] ? idx[f] + 1 : 0 (previous action with
+ * its start token, :747-757).  An index outside the table poisons the row with NaN.  _bwd: d_table[k_f] += d_out row. */
+int hb200_index_embed_fwd(const int64_t* idx, const int32_t* frame_rows, const uint8_t* masks, int batch,
+                          int table_rows, const float* table, int width, float* out, int ld, int col0,
+                          hb200_stream_t stream);
+int hb200_index_embed_bwd(const int64_t* idx, const int32_t* frame_rows, const uint8_t* masks, int batch,
+                          int table_rows, int width, const float* d_out, int ld, int col0, float* d_table,
+                          hb200_stream_t stream);
+/* Generic visual input prep (ResNetEncoder.forward, HB/rl/ddppo/policy/resnet_policy.py:255-271) for ANY sensor mix
+ * and size: up to 4 HWC sources (h_* are HOST arrays of n_srcs entries: device pointers, dtype 0 u8 / 1 f32 / 2 i32,
+ * channels, pre-pool scale = 1/high for u8 keys), <= 8 channels in total, concatenated in order, avg_pool2d(2) (odd
+ * last row / column dropped).  stats_acc != NULL: statistics pass (17 doubles like hb200_prep_stats); otherwise the
+ * apply pass writes out f16 [batch, H/2, W/2, 8] (+ optional bf16 twin) normalised with scale_shift (NULL: raw). */
+int hb200_prep_generic(const void* const* h_srcs, const int* h_dtypes, const int* h_channels, const float* h_scales,
+                       int n_srcs, const int32_t* frame_rows, int batch, int height, int width,
+                       const float* scale_shift, hb200_f16* out, hb200_bf16* out_bf16, double* stats_acc,
+                       hb200_stream_t stream);
+
 /* Not on the product path yet: mechanism probe (verified on hardware) for the TMA halo load of the halo convolutions
  * (NOTES_NEXT.md): loads the halo_h x halo_w halo of the tile whose first output pixel is (oh0, ow0) of frame b from the
  * NHWC bf16 tensor x [batch, h, w, channels] with channels/8 `cp.async.bulk.tensor.4d` box copies (out-of-bounds rows /
