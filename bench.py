@@ -29,12 +29,68 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-CFG = dict(T=128, N=64, H=256, W=256, hidden=512, layers=2, ppo_epoch=2, num_mini_batch=2, clip_param=0.2,
-           value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, gamma=0.99, tau=0.95)
-METRIC = "DD-PPO learner frames/sec (ResNet18 RGB-D 256x256)"
+_PPO = dict(clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4, eps=1e-5, max_grad_norm=0.2, gamma=0.99, tau=0.95)
+# BASELINE.json configs[1..3]; config 2 is the headline (the default), 3 / 4 are selected with --config
+WORKLOADS = {
+    2: dict(cfg=dict(T=128, N=64, H=256, W=256, hidden=512, layers=2, rnn="LSTM", backbone="resnet18", ppo_epoch=2,
+                     num_mini_batch=2, sensors="pointnav", n_actions=4, **_PPO),
+            metric="DD-PPO learner frames/sec (ResNet18 RGB-D 256x256)",
+            text="BASELINE configs[1]: PointNav DD-PPO ResNet18 RGB-D 256x256, LSTM-512x2, 64 envs/rank, T=128, 2 epochs x 2 "
+                 "minibatches (4096 frames each), synthetic obs"),
+    3: dict(cfg=dict(T=64, N=32, H=256, W=256, hidden=512, layers=1, rnn="GRU", backbone="resnet50", ppo_epoch=4,
+                     num_mini_batch=2, sensors="objectnav", n_actions=6, n_categories=21, **_PPO),
+            metric="DD-PPO learner frames/sec (ResNet50 RGB-D + semantic 256x256, ObjectNav)",
+            text="BASELINE configs[2]: ObjectNav DD-PPO ResNet50 RGB-D + int32 semantic channel 256x256, objectgoal / compass "
+                 "/ gps embeddings, GRU-512, 32 envs/rank, T=64, 4 epochs x 2 minibatches (1024 frames each), synthetic obs"),
+    4: dict(cfg=dict(T=64, N=32, H=256, W=256, hidden=512, layers=2, rnn="LSTM", backbone="resneXt50", ppo_epoch=4,
+                     num_mini_batch=2, sensors="imagenav", n_actions=4, **_PPO),
+            metric="DD-PPO learner frames/sec (ResNeXt50 dual encoder RGB 256x256, ImageNav)",
+            text="BASELINE configs[3]: ImageNav DD-PPO ResNeXt50 dual encoder (observation + goal image) RGB 256x256, compass "
+                 "/ gps embeddings, LSTM-512x2, 32 envs/rank, T=64, 4 epochs x 2 minibatches (1024 frames each), synthetic obs"),
+}
+CONFIG_ID = 2
+CFG = WORKLOADS[2]["cfg"]
+METRIC = WORKLOADS[2]["metric"]
+
+
+def select_workload(config_id: int) -> None:
+    global CONFIG_ID, CFG, METRIC
+    CONFIG_ID, CFG, METRIC = config_id, WORKLOADS[config_id]["cfg"], WORKLOADS[config_id]["metric"]
+
+
+def make_spaces():
+    from habitat_lab_b200 import synthetic as syn
+    if CFG["sensors"] == "pointnav":
+        return syn.pointnav_spaces(CFG["H"], CFG["W"], CFG["n_actions"])
+    if CFG["sensors"] == "objectnav":
+        return syn.objectnav_spaces(CFG["H"], CFG["W"], CFG["n_actions"], CFG["n_categories"])
+    return syn.imagenav_spaces(CFG["H"], CFG["W"], CFG["n_actions"])
+
+
+def make_policy(hb, obs_space, act_space):
+    return hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=CFG["hidden"], num_recurrent_layers=CFG["layers"],
+                                   rnn_type=CFG["rnn"], resnet_baseplanes=32, backbone=CFG["backbone"],
+                                   normalize_visual_inputs=True)
+
+
+def fill(st, seed, obs_space):
+    from habitat_lab_b200.synthetic import fill_rollout_
+    if CFG["sensors"] == "pointnav":
+        return fill_rollout_(st, seed=seed)
+    return fill_rollout_(st, seed=seed, observation_space=obs_space, n_actions=CFG["n_actions"])
 # algorithmic work per frame of config #2 (SURVEY.md section 8d / DESIGN.md)
 CONV_FWD_GFLOP = 0.3376
-CONV_TRAIN_GFLOP = 0.9614  # fwd + dgrad + wgrad, no dgrad for conv1
+CONV_TRAIN_GFLOP = 0.9614  # config #2: fwd + dgrad + wgrad, no dgrad for conv1; other configs: from the engine
+
+
+def conv_train_gflop_per_frame(policy):
+    """algorithmic conv FLOPs of one training frame-pass (fwd + dgrad + wgrad, no dgrad for the stems), all encoders"""
+    tot = 0.0
+    for eng in policy._engines.values():
+        for c in eng.convs:
+            f = 2.0 * c.out_hw[0] * c.out_hw[1] * c.co * (c.ci_real // c.conv_groups) * c.k * c.k
+            tot += f * (2 if c is eng.stem else 3)
+    return tot * 1e-9
 
 
 def _peaks():
@@ -102,8 +158,18 @@ if os.environ.get("HB200_CPU_SAMPLE"):   # "T,N": the contract test shrinks the 
 
 def _recipe_rollout(T, N, seed=5):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-    from recipe import synthetic_rollout
-    return synthetic_rollout(T, N, CFG["H"], CFG["W"], 4, 2 * CFG["layers"], CFG["hidden"], seed, p_done=1.0 / 250.0)
+    from recipe import objectnav_rollout, synthetic_rollout
+    layers_h = CFG["layers"] * (2 if CFG["rnn"] == "LSTM" else 1)
+    if CFG["sensors"] == "pointnav":
+        return synthetic_rollout(T, N, CFG["H"], CFG["W"], 4, layers_h, CFG["hidden"], seed, p_done=1.0 / 250.0)
+    return objectnav_rollout(T, N, CFG["H"], CFG["W"], CFG["n_actions"], layers_h, CFG["hidden"], seed,
+                             CFG.get("n_categories", 0), CFG["sensors"] == "imagenav")
+
+
+def _ref_kwargs():
+    return dict(hidden=CFG["hidden"], layers=CFG["layers"], rnn_type=CFG["rnn"], backbone=CFG["backbone"],
+                sensors=CFG["sensors"], n_actions=CFG["n_actions"], n_categories=CFG.get("n_categories", 0),
+                ppo_epoch=CFG["ppo_epoch"], num_mini_batch=CFG["num_mini_batch"])
 
 
 def _make_cpu_learner(T=CPU_SAMPLE["T"], N=CPU_SAMPLE["N"]):
@@ -111,16 +177,15 @@ def _make_cpu_learner(T=CPU_SAMPLE["T"], N=CPU_SAMPLE["N"]):
     + PPO.update on device="cpu" -- the reference's own CPU PPO path."""
     from oracle.ref_learner import ReferenceLearner
 
-    learner = ReferenceLearner(T, N, CFG["H"], CFG["W"], "cpu", hidden=CFG["hidden"], layers=CFG["layers"],
-                               ppo_epoch=CFG["ppo_epoch"], num_mini_batch=CFG["num_mini_batch"])
+    learner = ReferenceLearner(T, N, CFG["H"], CFG["W"], "cpu", **_ref_kwargs())
     bufs, next_value = _recipe_rollout(T, N)
     learner.load_rollout(bufs, next_value)
     return learner.step, T * N
 
 
 def _cpu_sample_text(threads):
-    return (f"learner iteration(s) of T={CPU_SAMPLE['T']} x N={CPU_SAMPLE['N']} frames (256x256 RGB-D; the config has T=128, "
-            f"N=64 envs per rank; {CFG['ppo_epoch']} epochs x {CFG['num_mini_batch']} minibatches of "
+    return (f"learner iteration(s) of T={CPU_SAMPLE['T']} x N={CPU_SAMPLE['N']} frames ({CFG['H']}x{CFG['W']}, config "
+            f"#{CONFIG_ID} sensors and policy; the config has T={CFG['T']}, N={CFG['N']} envs per rank; {CFG['ppo_epoch']} epochs x {CFG['num_mini_batch']} minibatches of "
             f"{CPU_SAMPLE['T'] * CPU_SAMPLE['N'] // CFG['num_mini_batch']} frames), unmodified reference classes on "
             f"device=cpu, {threads} threads")
 
@@ -171,9 +236,7 @@ def torch_cuda_measure(dev, world, rollout_buffers, next_value, steps, warmup, s
 
     settings = cuda_settings()
     T, N = CFG["T"], CFG["N"]
-    learner = ReferenceLearner(T, N, CFG["H"], CFG["W"], dev, hidden=CFG["hidden"], layers=CFG["layers"],
-                               ppo_epoch=CFG["ppo_epoch"], num_mini_batch=CFG["num_mini_batch"],
-                               distributed=world > 1, seed=seed)
+    learner = ReferenceLearner(T, N, CFG["H"], CFG["W"], dev, distributed=world > 1, seed=seed, **_ref_kwargs())
     learner.load_rollout(rollout_buffers, next_value)
 
     def barrier():
@@ -207,8 +270,6 @@ def torch_cuda_measure(dev, world, rollout_buffers, next_value, steps, warmup, s
 def run_torch_cuda(args):
     """bench.py --impl torch_cuda: the competitor arm alone, launched like the hb200 arm (torchrun for N > 1)."""
     import habitat_lab_b200 as hb
-    from habitat_lab_b200.synthetic import fill_rollout_, pointnav_spaces
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -217,14 +278,14 @@ def run_torch_cuda(args):
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
     T, N = CFG["T"], CFG["N"]
-    obs_space, act_space = pointnav_spaces(CFG["H"], CFG["W"])
+    obs_space, act_space = make_spaces()
 
     class _Shape:   # RolloutStorage only reads these two attributes of the policy
-        num_recurrent_layers, recurrent_hidden_size = 2 * CFG["layers"], CFG["hidden"]
+        num_recurrent_layers, recurrent_hidden_size = CFG["layers"] * (2 if CFG["rnn"] == "LSTM" else 1), CFG["hidden"]
 
     st = hb.RolloutStorage(T, N, obs_space, act_space, _Shape())
     st.to(dev)
-    next_value = fill_rollout_(st, seed=100 + rank * N)
+    next_value = fill(st, 100 + rank * N, obs_space)
     res = torch_cuda_measure(dev, world, st.buffers, next_value, args.steps, args.warmup, seed=100)
     if rank == 0:
         line = {"impl": "torch_cuda", "metric": METRIC, "value": res["value"], "unit": "frames/s", "n_gpus": world,
@@ -237,8 +298,7 @@ def run_torch_cuda(args):
 
 
 def _config(n):
-    return {"workload": "BASELINE configs[1]: PointNav DD-PPO ResNet18 RGB-D 256x256, LSTM-512x2, 64 envs/rank, "
-                        "T=128, 2 epochs x 2 minibatches (4096 frames each), synthetic obs",
+    return {"workload": WORKLOADS[CONFIG_ID]["text"],
             "num_envs_per_rank": CFG["N"], "rollout_steps": CFG["T"], "frames_per_step_per_rank": CFG["T"] * CFG["N"],
             "parallelism": f"dp{n}", "l2_policy": "inputs (3.8 GB of observations per rank) far exceed the 126 MB L2"}
 
@@ -249,7 +309,6 @@ def _config(n):
 def run_hb200(args):
     import habitat_lab_b200 as hb
     from habitat_lab_b200 import ops
-    from habitat_lab_b200.synthetic import fill_rollout_, pointnav_spaces
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -266,10 +325,8 @@ def run_hb200(args):
     lib = hb.load()
     T, N = CFG["T"], CFG["N"]
     torch.manual_seed(100 + rank * N)  # habitat.seed=100, ppo_trainer.py:207-215
-    obs_space, act_space = pointnav_spaces(CFG["H"], CFG["W"])
-    policy = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=CFG["hidden"], num_recurrent_layers=CFG["layers"],
-                                     rnn_type="LSTM", resnet_baseplanes=32, backbone="resnet18",
-                                     normalize_visual_inputs=True).to(dev)
+    obs_space, act_space = make_spaces()
+    policy = make_policy(hb, obs_space, act_space).to(dev)
     cls = hb.DDPPO if world > 1 else hb.PPO
     ppo = cls(policy, clip_param=CFG["clip_param"], ppo_epoch=CFG["ppo_epoch"], num_mini_batch=CFG["num_mini_batch"],
               value_loss_coef=CFG["value_loss_coef"], entropy_coef=CFG["entropy_coef"], lr=CFG["lr"], eps=CFG["eps"],
@@ -279,7 +336,7 @@ def run_hb200(args):
     policy.train()
     st = hb.RolloutStorage(T, N, obs_space, act_space, policy)
     st.to(dev)
-    next_value = fill_rollout_(st, seed=100 + rank * N)
+    next_value = fill(st, 100 + rank * N, obs_space)
 
     def learner_step():
         st.current_rollout_step_idxs = [T]
@@ -440,12 +497,129 @@ def run_hb200(args):
                         "h2d": "pinned host -> device on a copy stream, double-buffered across steps; first copy exposed"},
                 "roofline": roof, "hbm_kernel_rooflines": hbm_roofs, "cpu_baseline": cpu, "actor": actor,
                 "torch_cuda_baseline": torch_cuda, "cross_rank_equality": cross_rank,
-                "conv_tensor_frac_of_step": (world * T * N * CFG["ppo_epoch"] * CONV_TRAIN_GFLOP * 1e-3 * args.steps)
+                "conv_tensor_frac_of_step": (world * T * N * CFG["ppo_epoch"] * conv_train_gflop_per_frame(policy) * 1e-3 * args.steps)
                 / (ms * 1e-3) / (peaks["bf16_sustained"] * world),
                 "learner_metrics": {k: round(float(v), 6) for k, v in metrics.items()}}
         _emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[4]: PPO.update minibatch sweep -- GAE-scan HBM GB/s + conv tensor-pipe fraction vs the reference
+# ---------------------------------------------------------------------------------------------
+def run_sweep(args):
+    """frames per rollout in {1k, 4k, 16k, 64k, 256k} = T=128 x N in {8, 32, 128, 512, 2048} envs.
+    Per size: (a) the fused GAE + advantage kernel on the [T+1, N] scalars -- time, algorithmic GB/s (17 B per element) and
+    the reference's `RolloutStorage.compute_returns` python loop on the same CUDA tensors; (b) one PPO minibatch
+    (frames / 2, forward + loss + backward + clip/Adam) through hb200 and through the unmodified reference on CUDA:
+    ms, frames/s, algorithmic conv TFLOP/s and its fraction of the measured bf16 peak.  Minibatches above 16384
+    frames are not materialised (their rollout alone is 30-120 GB): the 64k / 256k rows repeat the 16k-frame pass, which
+    is what a larger minibatch is to these kernels (same tiles, more of them); the reference arm stops where its
+    autograd graph no longer fits next to it (8192 frames = 100 GB)."""
+    import habitat_lab_b200 as hb
+    from habitat_lab_b200 import ops
+
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    hb.load()
+    peaks = _peaks()
+    obs_space, act_space = make_spaces()
+    T = CFG["T"]
+    rows = []
+
+    def ev_ms(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ref_ok = True
+    for N in (8, 32, 128, 512, 2048):
+        frames = T * N
+        row = {"frames": frames, "envs": N}
+        # ---- (a) GAE + advantages
+        g = torch.Generator(device=dev).manual_seed(N)
+        rewards = torch.randn(T + 1, N, 1, device=dev, generator=g)
+        values = torch.randn(T + 1, N, 1, device=dev, generator=g)
+        masks = torch.rand(T + 1, N, 1, device=dev, generator=g) > 0.004
+        nv = torch.randn(N, device=dev, generator=g)
+        returns, adv = torch.empty_like(rewards), torch.empty_like(rewards)
+        stats = torch.zeros(4, dtype=torch.float64, device=dev)
+        ms = ev_ms(lambda: ops.gae_adv(rewards, values, masks, nv, returns, adv, stats, T, 0.99, 0.95, True, 1), 50)
+        by = 17.0 * (T + 1) * N
+        row["gae"] = {"ms": ms, "gbs": by / ms * 1e-6, "frac_hbm": by / ms * 1e-6 / peaks["hbm"],
+                      "note": "launch-latency bound below ~1 MB (17 B x (T+1) x N = %.2f MB)" % (by * 1e-6)}
+
+        def ref_gae():   # rollout_storage.py:174-205 on the same CUDA tensors
+            vp = values.clone()
+            vp[T] = nv.view(-1, 1)
+            gae = 0
+            for step in reversed(range(T)):
+                delta = rewards[step] + 0.99 * vp[step + 1] * masks[step + 1] - vp[step]
+                gae = delta + 0.99 * 0.95 * gae * masks[step + 1]
+                returns[step] = gae + vp[step]
+        row["gae"]["torch_cuda_ms"] = ev_ms(ref_gae, 3)
+        del rewards, values, masks, returns, adv
+        # ---- (b) one minibatch through the learner
+        mb_frames = min(frames // 2, 16384)
+        n_env_mb = mb_frames // T
+        row["minibatch_frames"] = frames // 2
+        row["materialised_minibatch_frames"] = mb_frames
+        policy = make_policy(hb, obs_space, act_space).to(dev)
+        policy.train()
+        ppo = hb.PPO(policy, clip_param=CFG["clip_param"], ppo_epoch=1, num_mini_batch=1, value_loss_coef=CFG["value_loss_coef"],
+                     entropy_coef=CFG["entropy_coef"], lr=CFG["lr"], eps=CFG["eps"], max_grad_norm=CFG["max_grad_norm"],
+                     use_clipped_value_loss=True, use_normalized_advantage=False)
+        st = hb.RolloutStorage(T, n_env_mb, obs_space, act_space, policy)
+        st.to(dev)
+        nvv = fill(st, 100 + N, obs_space)
+
+        def step():
+            st.current_rollout_step_idxs = [T]
+            st.compute_returns(nvv, True, CFG["gamma"], CFG["tau"])
+            return ppo.update(st)
+
+        for _ in range(2):
+            step()
+        ms = ev_ms(step, 3)
+        gf = conv_train_gflop_per_frame(policy) * mb_frames
+        row["hb200"] = {"ms_per_minibatch": ms, "frames_per_s": mb_frames / ms * 1e3, "conv_tflops": gf / ms,
+                        "conv_frac_of_bf16_peak": gf / ms / peaks["bf16_sustained"]}
+        bufs, nv_keep = st.buffers, nvv
+        del policy, ppo
+        torch.cuda.empty_cache()
+        if ref_ok and mb_frames <= 8192:
+            try:
+                from oracle.ref_learner import ReferenceLearner, cuda_settings
+                cuda_settings()
+                kw = _ref_kwargs()
+                kw.update(ppo_epoch=1, num_mini_batch=1)
+                learner = ReferenceLearner(T, n_env_mb, CFG["H"], CFG["W"], dev, seed=100, **kw)
+                learner.load_rollout(bufs, nv_keep)
+                for _ in range(2):
+                    learner.step()
+                ms_r = ev_ms(learner.step, 3)
+                row["torch_cuda"] = {"ms_per_minibatch": ms_r, "frames_per_s": mb_frames / ms_r * 1e3,
+                                     "conv_tflops": gf / ms_r, "hb200_over_torch_cuda": ms_r / ms}
+                del learner
+            except Exception as e:   # out of memory at the large sizes: stop trying
+                row["torch_cuda"] = {"unavailable": repr(e)[:200]}
+                ref_ok = False
+        del st, bufs
+        torch.cuda.empty_cache()
+        rows.append(row)
+        print("sweep", json.dumps(row), file=sys.stderr, flush=True)
+    _emit({"metric": "PPO.update minibatch sweep (BASELINE configs[4])", "unit": "per-size table", "n_gpus": 1,
+           "config": {"workload": "T=128 x N in {8,32,128,512,2048} envs of config #%d; minibatch = frames / 2" % CONFIG_ID},
+           "peaks": {"hbm_gbs": peaks["hbm"], "bf16_tflops_sustained": peaks["bf16_sustained"], "source": peaks["src"]},
+           "rows": rows, "data": "synthetic"})
+
 
 
 def cross_rank_equality(policy, dev, world):
@@ -518,7 +692,7 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
     for c in eng.convs:
         i = idx[id(c)]
         s = c.shape(B)
-        flop = 2.0 * B * c.out_hw[0] * c.out_hw[1] * c.co * c.ci_real * c.k * c.k
+        flop = 2.0 * B * c.out_hw[0] * c.out_hw[1] * c.co * (c.ci_real // c.conv_groups) * c.k * c.k
         xin, y = inputs[id(c)], ws[f"y{i}"]
         stats = ws[f"st{i}"]
         if c.stem_s2d:
@@ -650,9 +824,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="hb200", choices=["hb200", "reference", "torch_cuda"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json configs[N-1]; 2 (the headline metric) is the default")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-cuda", action="store_true", help="skip the reference PyTorch-CUDA competitor leg")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: minibatch-size sweep (1 GPU), one JSON line")
     args = ap.parse_args()
+    select_workload(args.config)
+    if args.sweep:
+        return run_sweep(args)
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "torch_cuda":

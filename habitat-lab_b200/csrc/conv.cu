@@ -28,6 +28,7 @@ using namespace umma;
 constexpr int kStages = 3;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;  // bf16 elements per K chunk (8 x 16-byte vectors)
+constexpr int kMaxChunks = 512;  // K = taps * Ci up to 32768 (the 3x3 compression conv of ResNet50 has K = 9 * 1024)
 
 template <int LAYOUT>
 __device__ __forceinline__ uint32_t tile_off(int row, int k8, int rows_total) {
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.y * BN;
-  __shared__ int chunk_ids[64];
+  __shared__ short chunk_ids[kMaxChunks];
   __shared__ int n_valid_s;
   // ---- row -> output pixel.  Stride-2 dgrad: tiles are grouped by the parity class (ph, pw) of the
   // output pixel, because a class only ever touches the filter taps with r = ph+pad (mod 2),
@@ -108,14 +109,14 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
   if (tid == 0) {
     int nv = 0;
     const int cpt = a.SC >> 6;  // 64-channel chunks per tap (>= 1 in class mode)
-    for (int c = 0; c < a.nchunks && nv < 64; ++c) {
+    for (int c = 0; c < a.nchunks && nv < kMaxChunks; ++c) {
       bool ok = true;
       if (MODE == 1 && a.s2_classes) {
         const int tap = c / cpt;
         const int r = tap / a.kw, sx = tap - r * a.kw;
         ok = tap < a.kh * a.kw && (((ph + a.pad - r) & 1) == 0) && (((pw + a.pad - sx) & 1) == 0);
       }
-      if (ok) chunk_ids[nv++] = c;
+      if (ok) chunk_ids[nv++] = (short)c;
     }
     n_valid_s = nv;
   }
@@ -650,6 +651,8 @@ static int pick_bn(int n) { return n >= 256 ? 256 : n; }
 
 template <int MODE>
 static int launch_igemm(const ConvArgs& a, int BN, cudaStream_t st) {
+  // the kernel walks a per-CTA list of K chunks held in shared memory: a longer reduction must fail loudly, never truncate
+  HB_CHECK_ARG(a.nchunks <= kMaxChunks, "conv: K = kh*kw*C = %d exceeds %d", a.nchunks * kChunkK, kMaxChunks * kChunkK);
   dim3 grid(a.s2_classes ? 4 * cdiv(a.M / 4, kTileM) : cdiv(a.M, kTileM), a.OC / BN);
   const size_t smem = (size_t)kStages * (kTileM * kChunkK * 2 + BN * kChunkK * 2) + 1024;
 #define HB_CONV_CASE(bn, L)                                                                     \

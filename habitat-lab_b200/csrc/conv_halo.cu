@@ -311,8 +311,13 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
     load_halo<C, KH, KW, PAD, HROWS_LOAD>(a.x, sh, b, oh0, ow0, a.H, a.W);
     // dy tile: [n-chunk][py][px] 16-byte vectors  (MN-major B: SBO = 128*16, LBO = 8*16)
     const uint32_t sd = sh + HALO_BYTES;
+    // lane mapping: 8 consecutive lanes take the SAME 16-byte channel chunk of 8 consecutive pixels (one 128-byte
+    // core-matrix row group in shared memory: bank-conflict free), the next lane octets the next 3 chunks of those
+    // pixels (64 contiguous bytes per pixel in global memory: full 32-byte sectors).  The first version walked the
+    // chunks of one pixel with consecutive lanes: 2 KB apart in shared memory = an N/8-way bank conflict per copy.
     for (int v = tid; v < 128 * (N / 8); v += 128) {
-      const int nj = v % (N / 8), p = v / (N / 8);  // consecutive threads: consecutive 16 B of one pixel
+      const int q = v & 7, r = (v >> 3) & 3, hi = v >> 5;
+      const int nj = (hi % (N / 32)) * 4 + r, p = (hi / (N / 32)) * 8 + q;
       const int ppy = p >> 3, ppx = p & 7;
       const __nv_bfloat16* g = a.dy + (((size_t)b * a.H + oh0 + ppy) * a.W + ow0 + ppx) * N + nj * 8;
       cp_async16(sd + (uint32_t)(nj * 128 + p) * 16, g, true);
@@ -461,8 +466,11 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
     }
     // dy tile: [n-chunk][py][px]; pixels px >= IMG are virtual (dy = 0)
     const uint32_t sd = sh + HALO_BYTES;
+    // lane octets = 8 consecutive pixels of one 16-byte channel chunk (conflict-free 128-byte shared-memory rows),
+    // 4 octets = 4 consecutive chunks (64 contiguous bytes per pixel in global memory); see conv_halo_wgrad_kernel
     for (int v = lt; v < 128 * (NS / 8); v += 96) {
-      const int nj = v % (NS / 8), p = v / (NS / 8);
+      const int q = v & 7, r = (v >> 3) & 3, hi = v >> 5;
+      const int nj = (hi % (NS / 32)) * 4 + r, p = (hi / (NS / 32)) * 8 + q;
       const int ppy = p >> 3, ppx = p & 7;
       const int j = ppy / IMG, y = ppy - j * IMG;
       const int b = b0 + j;

@@ -356,7 +356,8 @@ ppo_loss_main_kernel(const float* __restrict__ feat, const float* __restrict__ w
     const float ratio = expf(lp - old_lp[f]);
     const float s1 = adv * ratio;
     const float s2 = adv * fminf(fmaxf(ratio, 1.0f - clip), 1.0f + clip);
-    const float a_loss = -fminf(s1, s2);
+    // fminf / fmaxf return the non-NaN operand: re-poison explicitly for an out-of-range action
+    const float a_loss = (act >= 0 && act < A) ? -fminf(s1, s2) : __int_as_float(0x7fc00000);
     float v_used = v;
     bool v_live = true;
     if (use_clip_v) {

@@ -398,7 +398,9 @@ class EncoderEngine:
     MMAs), gradients bf16.  Any input size: layers whose shape the halo kernels cannot tile fall back to the gather
     kernels automatically."""
 
-    def __init__(self, enc: ResNetEncoder):
+    def __init__(self, enc: ResNetEncoder, allow_s2d: bool = True):
+        """allow_s2d: the input prep can write the space-to-depth form the halo stem kernel reads (only the vectorised
+        rgb / depth prep does; the generic prep writes plain NHWC and the stem runs as a gather conv)."""
         self.enc = enc
         h, w = enc.in_hw
         self.hp, self.wp_ = h // 2, w // 2
@@ -431,7 +433,7 @@ class EncoderEngine:
         if not os.environ.get("HB200_NO_HALO"):
             for c in self.convs:
                 if c is self.stem:
-                    c.stem_s2d = (c.k == 7 and c.stride == 2 and c.pad == 3 and c.ci_real <= 4 and
+                    c.stem_s2d = (allow_s2d and c.k == 7 and c.stride == 2 and c.pad == 3 and c.ci_real <= 4 and
                                   self.hp % 2 == 0 and self.wp_ % 2 == 0 and
                                   ops.conv_halo_supported(16, c.co, 4, c.out_hw[0], c.out_hw[1]))
                 elif c.k == 3 and c.stride == 1 and c.pad == 1:
@@ -688,6 +690,7 @@ class NativeNetPolicy(nn.Module):
         self._side = SideStream()
         self.world_size = 1  # set by the distributed updater
         self.dist_group = None
+        self.tail_grads_hook = None   # DDPPO: called (on the side stream) once the recurrent + head gradients are final
 
     # ---- reference API surface ----------------------------------------------------------------
     @property
@@ -759,6 +762,16 @@ class NativeNetPolicy(nn.Module):
         self._flat = dict(params=flat_p, grads=flat_g, offsets=offs, n=o, n_real=n, plist=params)
         self.mark_weights_changed()
         return self._flat
+
+    def tail_offset(self) -> int:
+        """First element of the flat buffers that belongs to the recurrent encoder / heads.  Their gradients are final
+        as soon as the RNN backward is done, long before the conv stack's: the distributed updater reduces
+        [tail_offset, n) while the encoder backward still runs (rl/ppo.py DDPPO)."""
+        f = self.flatten_parameters_()
+        for (name, _), off in zip(self.named_parameters(), f["offsets"]):
+            if name.startswith("net.state_encoder."):
+                return off
+        return f["n"]
 
     def mark_weights_changed(self) -> None:
         """Called by FusedAdam.step / load_state_dict / the DD-PPO broadcast: invalidates cached weight images."""
@@ -939,6 +952,9 @@ class NativeNetPolicy(nn.Module):
                      f32(batch["returns"]), clip_param, value_loss_coef, entropy_coef, use_clipped_value_loss, True,
                      out, self._loss_ws(B, dev), is_coeffs=f32(batch["is_coeffs"]) if "is_coeffs" in batch else None)
         d_rnn_in = self._rnn_backward(out["d_features"], s["layers"], s["masks"], T, n, B, dev)
+        if self.tail_grads_hook is not None:
+            with self._side.after_main():   # after the head gradients (main) and the RNN weight gradients (side)
+                self.tail_grads_hook()
         self._visual_backward(d_rnn_in, s, B, dev)
         self._side.join()
         self._last = dict(values=out["values"], log_probs=out["log_probs"], entropy=out["entropy"],
@@ -995,9 +1011,20 @@ class PointNavResNetPolicy(NativeNetPolicy):
             return self.net.visual_encoder, self.net.visual_fc
         return getattr(self.net, f"{name}_encoder"), getattr(self.net, f"{name}_fc")
 
+    def _fast_prep(self, name) -> bool:
+        """True when the vectorised rgb-u8 (x3) / depth-f32 (x1) prep kernels serve this encoder's sensor set"""
+        enc, _ = self._encoder(name)
+        sp = self.observation_space.spaces
+        keys = list(enc.visual_keys)
+        kinds = {"rgb": (np.uint8, 3), "depth": (np.float32, 1)}
+        src = {k: sp[k] for k in keys} if name == "visual" else {"rgb": sp[name]}
+        H, W = enc.in_hw
+        return (keys in (["rgb", "depth"], ["rgb"], ["depth"]) and W % 8 == 0 and H % 2 == 0 and
+                all(np.dtype(src[k].dtype) == np.dtype(kinds[k][0]) and src[k].shape[2] == kinds[k][1] for k in keys))
+
     def _engine_(self, name="visual"):
         if name not in self._engines:
-            eng = EncoderEngine(self._encoder(name)[0])
+            eng = EncoderEngine(self._encoder(name)[0], allow_s2d=self._fast_prep(name))
             eng.side = self._side   # one side stream for the whole backward pass
             self._engines[name] = eng
         return self._engines[name]
@@ -1023,9 +1050,7 @@ class PointNavResNetPolicy(NativeNetPolicy):
         else:   # goal_visual_encoder({"rgb": goal_image}), resnet_policy.py:739-742
             srcs = [(observations[name], enc.key_needs_rescaling["rgb"] or 1.0)]
         keys = list(enc.visual_keys)
-        fast = (keys in (["rgb", "depth"], ["rgb"], ["depth"]) and W % 8 == 0 and H % 2 == 0 and
-                all((t.dtype == torch.uint8 and t.shape[-1] == 3) if k == "rgb" else (t.dtype == torch.float32 and t.shape[-1] == 1)
-                    for k, (t, _) in zip(keys, srcs)))
+        fast = self._fast_prep(name)
         rgb = srcs[keys.index("rgb")][0] if fast and "rgb" in keys else None
         depth = srcs[keys.index("depth")][0] if fast and "depth" in keys else None
         rgb_scale = srcs[keys.index("rgb")][1] if rgb is not None else 1.0 / 255.0

@@ -22,20 +22,34 @@ PPO_KW = dict(clip_param=0.2, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4,
 
 class ReferenceLearner:
     def __init__(self, T: int, N: int, H: int, W: int, device, hidden=512, layers=2, rnn_type="LSTM", ppo_epoch=2,
-                 num_mini_batch=2, use_normalized_advantage=False, distributed=False, state_dict=None, seed=100):
+                 num_mini_batch=2, use_normalized_advantage=False, distributed=False, state_dict=None, seed=100,
+                 backbone="resnet18", sensors="pointnav", n_actions=4, n_categories=21):
+        import collections
+
         R = ref_shim.ref()
         self.R = R
         sp = R.spaces
         self.device = torch.device(device)
-        obs_space = sp.Dict({
-            "rgb": sp.Box(0, 255, (H, W, 3), np.uint8),
-            "depth": sp.Box(0, 1, (H, W, 1), np.float32),
-            "pointgoal_with_gps_compass": sp.Box(-1e9, 1e9, (2,), np.float32),
-        })
-        act_space = sp.Discrete(4)
+        od = collections.OrderedDict()
+        od["rgb"] = sp.Box(0, 255, (H, W, 3), np.uint8)
+        if sensors == "pointnav":      # BASELINE config #2
+            od["depth"] = sp.Box(0, 1, (H, W, 1), np.float32)
+            od["pointgoal_with_gps_compass"] = sp.Box(-1e9, 1e9, (2,), np.float32)
+        elif sensors == "objectnav":   # config #3
+            od["depth"] = sp.Box(0, 1, (H, W, 1), np.float32)
+            od["semantic"] = sp.Box(0, 2 ** 30, (H, W, 1), np.int32)
+            od["objectgoal"] = sp.Box(0, n_categories - 1, (1,), np.int64)
+            od["compass"] = sp.Box(-np.pi, np.pi, (1,), np.float32)
+            od["gps"] = sp.Box(-1e9, 1e9, (2,), np.float32)
+        else:                          # config #4 (imagenav)
+            od["imagegoal"] = sp.Box(0, 255, (H, W, 3), np.uint8)
+            od["compass"] = sp.Box(-np.pi, np.pi, (1,), np.float32)
+            od["gps"] = sp.Box(-1e9, 1e9, (2,), np.float32)
+        obs_space = sp.Dict(od)
+        act_space = sp.Discrete(n_actions)
         torch.manual_seed(seed)
         pol = R.PointNavResNetPolicy(obs_space, act_space, hidden_size=hidden, num_recurrent_layers=layers,
-                                     rnn_type=rnn_type, resnet_baseplanes=32, backbone="resnet18",
+                                     rnn_type=rnn_type, resnet_baseplanes=32, backbone=backbone,
                                      normalize_visual_inputs=True)
         if state_dict is not None:
             pol.load_state_dict(state_dict)

@@ -198,6 +198,52 @@ def test_clip_adam(hb, n, max_norm):
     torch.testing.assert_close(flat[3, :n].cpu(), st["exp_avg_sq"], rtol=2e-3, atol=1e-10)
 
 
+def test_ppo_loss_importance_coefficients(hb):
+    """VER's importance-sampling weights (rl/ppo/ppo.py:226-232: every per-frame loss term is weighted by
+    is_coeffs.clamp(max=1) before the mean) through the fused loss kernel, forward and backward."""
+    from habitat_lab_b200 import ops
+
+    B, H, A = 1000, 512, 4
+    g = torch.Generator().manual_seed(9)
+    feats = torch.randn(B, H, generator=g)
+    w_act, b_act = torch.randn(A, H, generator=g) * 0.05, torch.randn(A, generator=g) * 0.1
+    w_val, b_val = torch.randn(1, H, generator=g) * 0.05, torch.randn(1, generator=g)
+    actions = torch.randint(0, A, (B, 1), generator=g)
+    with torch.no_grad():
+        v0, lp0, _ = O.heads(feats, w_act, b_act, w_val, b_val, actions)
+    batch = dict(action_log_probs=lp0 + 0.1 * torch.randn(B, 1, generator=g), advantages=torch.randn(B, 1, generator=g),
+                 value_preds=v0 + 0.3 * torch.randn(B, 1, generator=g), returns=v0 + torch.randn(B, 1, generator=g),
+                 is_coeffs=torch.rand(B, 1, generator=g) * 1.6)   # ~40 % above 1: the clamp matters
+    req = [t.clone().requires_grad_(True) for t in (feats, w_act, b_act, w_val, b_val)]
+    v, lp, ent = O.heads(*req, actions)
+    ref = O.ppo_loss(v, lp, ent, batch, 0.2, 0.5, 0.01, True)
+    ref["total_loss"].backward()
+    d = lambda t: t.to(DEV).contiguous()  # noqa: E731
+    out = dict(values=torch.empty(B, device=DEV), log_probs=torch.empty(B, device=DEV), entropy=torch.empty(B, device=DEV),
+               d_features=torch.empty(B, H, device=DEV), d_w_act=torch.empty(A, H, device=DEV),
+               d_b_act=torch.empty(A, device=DEV), d_w_val=torch.empty(H, device=DEV), d_b_val=torch.empty(1, device=DEV),
+               metrics=torch.empty(ops.N_METRICS, device=DEV))
+    ops.ppo_loss(d(feats), d(w_act), d(b_act), d(w_val), d(b_val), d(actions.view(-1)), d(batch["action_log_probs"].view(-1)),
+                 d(batch["advantages"].view(-1)), d(batch["value_preds"].view(-1)), d(batch["returns"].view(-1)), 0.2, 0.5,
+                 0.01, True, True, out, ops.ppo_loss_workspace(B, H, A, DEV), is_coeffs=d(batch["is_coeffs"].view(-1)))
+    torch.cuda.synchronize()
+    mt = out["metrics"].cpu()
+    for i, k in enumerate(("value_loss", "action_loss", "dist_entropy")):
+        torch.testing.assert_close(mt[i], ref[k].float().reshape(()), rtol=2e-4, atol=2e-6, msg=lambda s, k=k: f"{k}: {s}")
+    torch.testing.assert_close(mt[10], ref["total_loss"].detach().float().reshape(()), rtol=2e-4, atol=2e-6)
+    torch.testing.assert_close(out["d_features"].cpu(), req[0].grad, rtol=1e-3, atol=1e-3 / B)
+    torch.testing.assert_close(out["d_w_act"].cpu(), req[1].grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(out["d_w_val"].cpu().view(1, -1), req[3].grad, rtol=1e-3, atol=1e-5)
+    # an action outside [0, A) poisons the loss instead of silently scoring log_prob = 0
+    bad = d(actions.view(-1)).clone()
+    bad[3] = A
+    ops.ppo_loss(d(feats), d(w_act), d(b_act), d(w_val), d(b_val), bad, d(batch["action_log_probs"].view(-1)),
+                 d(batch["advantages"].view(-1)), d(batch["value_preds"].view(-1)), d(batch["returns"].view(-1)), 0.2, 0.5,
+                 0.01, True, True, out, ops.ppo_loss_workspace(B, H, A, DEV))
+    torch.cuda.synchronize()
+    assert torch.isnan(out["metrics"][1]).item()
+
+
 # ---------------------------------------------------------------------------------------------
 # tcgen05 descriptor probe + convolutions
 # ---------------------------------------------------------------------------------------------

@@ -102,7 +102,7 @@ def test_minibatch_forward_backward_vs_reference(hb, name):
         gn_ref = G["grad_norms"][k]
         gn = prm.grad.norm().item()
         # small fixtures: 32 / 8 frames; their 32-element GroupNorm tensors (1-D) are sums over very few frames
-        tol = ((0.05 if big else (0.20 if prm.dim() == 1 else 0.12)) if "visual_encoder" in k else 2e-2)
+        tol = ((0.05 if big else (0.20 if prm.dim() == 1 else 0.15)) if "visual_encoder" in k else 2e-2)
         if abs(gn - gn_ref) > tol * gn_ref + 1e-7:
             bad.append((k, gn, gn_ref))
     assert not bad, bad

@@ -60,14 +60,23 @@ def _worker(rank, world, port, ngpu, q):
         adv = ppo.get_advantages(st)                        # distributed var/mean: one packed all-reduce
         torch.manual_seed(7)
         batch = next(iter(st.data_generator(adv, 1)))
+        hook, pol.tail_grads_hook = pol.tail_grads_hook, None   # step 1: the plain path, so the LOCAL gradients can be read
         pol.loss_and_backward(batch, 0.2, 0.5, 0.01, True)   # includes the packed RunningMeanAndVar all-reduce
         g_local = flat["grads"].detach().clone()
         gn = ppo.before_step()                                # all-reduce + clip + Adam (the code under test)
         torch.cuda.synchronize()
         stats = torch.cat([b.detach().flatten().double() for b in pol.buffers()])
-        q.put((rank, p0.cpu().numpy(), g_local.cpu().numpy(), flat["grads"].detach().cpu().numpy(),
-               flat["params"].detach().cpu().numpy(), float(gn), stats.cpu().numpy(),
-               adv.detach().cpu().numpy(), st.buffers["returns"].cpu().numpy(), st.buffers["value_preds"].cpu().numpy()))
+        g_red, p_after = flat["grads"].detach().cpu().numpy(), flat["params"].detach().cpu().numpy()
+        # step 2: the overlapped path -- the recurrent / head chunk is reduced from inside the backward pass
+        assert hook is not None, "DDPPO.init_distributed must install the tail-gradient hook"
+        pol.tail_grads_hook = hook
+        pol.loss_and_backward(batch, 0.2, 0.5, 0.01, True)
+        ppo.before_step()
+        torch.cuda.synchronize()
+        p_after2 = flat["params"].detach().cpu().numpy()
+        q.put((rank, p0.cpu().numpy(), g_local.cpu().numpy(), g_red, p_after, float(gn), stats.cpu().numpy(),
+               adv.detach().cpu().numpy(), st.buffers["returns"].cpu().numpy(), st.buffers["value_preds"].cpu().numpy(),
+               p_after2))
     except BaseException:   # report instead of leaving the parent waiting on the queue
         import traceback
         q.put(("error", rank, traceback.format_exc()[-3000:]))
@@ -127,6 +136,8 @@ def test_ddppo_before_step_two_ranks(hb):
     p, m, v = r0[1].clone(), torch.zeros_like(r0[1]), torch.zeros_like(r0[1])
     O.clip_adam_step([p], [mean_g], [m], [v], 1, 2.5e-4, (0.9, 0.999), 1e-5, 0.2)
     torch.testing.assert_close(r0[4], p, rtol=1e-5, atol=2e-7)
+    # 3b. second step through the overlapped exchange (tail chunk all-reduced during the encoder backward): still identical
+    assert torch.equal(r0[10], r1[10]) and torch.isfinite(r0[10]).all() and not torch.equal(r0[10], r0[4])
     # 4. RunningMeanAndVar buffers (synced by the packed statistics all-reduce) identical on both ranks
     assert torch.equal(r0[6], r1[6])
     assert r0[6][-1].item() == 2 * 32, "count = frames of both ranks (T*N each)"
