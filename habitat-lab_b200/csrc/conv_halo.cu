@@ -411,7 +411,8 @@ struct HaloWgradSmallArgs {
 };
 
 template <int NS, int IMG>
-__global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWgradSmallArgs a) {
+__global__ void __launch_bounds__(128)
+conv_halo_wgrad_small_kernel(const HaloWgradSmallArgs a, const __grid_constant__ CUtensorMap tmap_dy) {
   constexpr int CJ = 4, KH = 3, KW = 3, HWD = TW + KW - 1;
   constexpr int P = HWD * 16, RP = CJ * P;
   constexpr int IPT = TH / IMG;                 // images per 16-row tile
@@ -419,8 +420,9 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
   constexpr int HROWS_LOAD = IPT * RPI;
   constexpr int HROWS = (IPT - 1) * RPI + (IMG - 2) + 1 + 4;   // last K16 base row + second K8 row + 4 row blocks (M padding)
   constexpr int HROWS_A = HROWS > HROWS_LOAD ? HROWS : HROWS_LOAD;
-  constexpr int HALO_BYTES = HROWS_A * RP;
-  constexpr int DY_BYTES = 128 * NS * 2;
+  constexpr int HALO_BYTES = (HROWS_A * RP + 1023) / 1024 * 1024;   // the dy tile behind it must be 1024-byte aligned
+  constexpr int NB = NS / 64;                   // 64-channel (128-byte) column blocks of the dy tile
+  constexpr int DY_BYTES = NB * 128 * 128;      // [block][pixel][128 B], TMA SWIZZLE_128B
   constexpr int STAGE = HALO_BYTES + DY_BYTES;
   constexpr int NST = kSmallWgradStages;        // 3-deep ring: the loads of tile it+2 overlap the MMAs of tiles it, it+1
   constexpr int TCOLS_RAW = KW * NS;
@@ -428,15 +430,17 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
   static_assert(TCOLS_RAW <= 512, "accumulators exceed TMEM");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar[NST];
+  __shared__ __align__(8) uint64_t dy_bar[NST];
   __shared__ uint32_t tmem_slot;
-  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int nsl = a.Co / NS;
   const int c_off = (blockIdx.y / nsl) * 32, n_off = (blockIdx.y % nsl) * NS;
+  const CUtensorMap* const tmap_p = &tmap_dy;   // param-space address (see conv_halo_tma_kernel)
 
   if (tid == 0) {
 #pragma unroll
-    for (int i = 0; i < NST; ++i) mbar_init(&mma_bar[i], 1);
+    for (int i = 0; i < NST; ++i) { mbar_init(&mma_bar[i], 1); mbar_init(&dy_bar[i], 1); }
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
@@ -446,14 +450,18 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
       const uint32_t addr = sbase + st * STAGE + HROWS_LOAD * RP + v * 16;
       asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
     }
-  // Warps 1-3 are the loaders (96 threads), warp 0 only issues MMAs: the MMA-issuing thread never spends its issue
-  // slots on the ~22 address / predicate computations per tile (it was the critical path of the first version).
-  auto load_tile = [&](int tile, int st) {
+  // Operand traffic.  ncu on the all-cp.async version: every LDGSTS of the dy tile cost 64 shared-memory wavefronts
+  // (ideal 8) -- a 16-byte copy only coalesces with its neighbours when 8 lanes are contiguous in BOTH global and
+  // shared memory, and the MN-major no-swizzle layout ([channel chunk][pixel][16 B]) is a transpose of the pixel-major
+  // tensor; 5700 LSU cycles per tile against 1536 tensor cycles.  The dy tile now arrives by TMA (box = 64 channels x
+  // 8 x IMG x IPT pixels, hardware 128-byte swizzle = the MN-major SWIZZLE_128B operand layout; for 4x4 images the box
+  // is 8 wide and the 4 out-of-range columns are the zero "virtual pixels"): zero LSU work, one thread.  Warps 1-3
+  // keep loading the x halo with cp.async (its shifted-descriptor layout has no TMA box form).
+  auto load_x = [&](int tile, int st) {
     if (warp == 0) return;
     const int lt = tid - 32;
     const uint32_t sh = sbase + st * STAGE;
     const int b0 = tile * IPT;
-    // x halo: [halo row][cj][halo col] 16-byte vectors; image j occupies halo rows j*RPI .. j*RPI + IMG + 1
     for (int v = lt; v < HROWS_LOAD * CJ * HWD; v += 96) {
       const int cj = v % CJ;
       const int t = v / CJ;
@@ -464,27 +472,23 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
       const grad_t* g = ok ? a.x + ((((size_t)b * IMG + ih) * IMG + iw) * a.Ci + c_off + cj * 8) : a.x;
       cp_async16(sh + (uint32_t)(((hy * CJ + cj) * HWD + hx) * 16), g, ok);
     }
-    // dy tile: [n-chunk][py][px]; pixels px >= IMG are virtual (dy = 0)
-    const uint32_t sd = sh + HALO_BYTES;
-    // lane octets = 8 consecutive pixels of one 16-byte channel chunk (conflict-free 128-byte shared-memory rows),
-    // 4 octets = 4 consecutive chunks (64 contiguous bytes per pixel in global memory); see conv_halo_wgrad_kernel
-    for (int v = lt; v < 128 * (NS / 8); v += 96) {
-      const int q = v & 7, r = (v >> 3) & 3, hi = v >> 5;
-      const int nj = (hi % (NS / 32)) * 4 + r, p = (hi / (NS / 32)) * 8 + q;
-      const int ppy = p >> 3, ppx = p & 7;
-      const int j = ppy / IMG, y = ppy - j * IMG;
-      const int b = b0 + j;
-      const bool ok = b < a.B && ppx < IMG;
-      const grad_t* g = ok ? a.dy + ((((size_t)b * IMG + y) * IMG + ppx) * a.Co + n_off + nj * 8) : a.dy;
-      cp_async16(sd + (uint32_t)(nj * 128 + p) * 16, g, ok);
-    }
+  };
+  auto load_dy = [&, tmap_p](int tile, int st) {   // thread 0 only
+    const uint32_t sd = sbase + st * STAGE + HALO_BYTES;
+    mbar_expect_tx(&dy_bar[st], (uint32_t)DY_BYTES);
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+      tma_load_4d(sd + (uint32_t)nb * (128 * 128), tmap_p, &dy_bar[st], n_off + nb * 64, 0, 0, tile * IPT);
   };
   const int first = blockIdx.x, stride = gridDim.x;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
   // prologue: tiles 0 .. NST-2 in flight, one cp.async group per tile
 #pragma unroll
   for (int i = 0; i < NST - 1; ++i) {
-    if (i < my_n) load_tile(first + i * stride, i);
+    if (i < my_n) {
+      load_x(first + i * stride, i);
+      if (tid == 0) load_dy(first + i * stride, i);
+    }
     cp_async_commit();
   }
   fence_before_sync();
@@ -495,10 +499,11 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
 
   for (int it = 0; it < my_n; ++it) {
     const int st = it % NST;
-    cp_async_wait<NST - 2>();        // this thread's copies of tile it have landed
+    cp_async_wait<NST - 2>();        // this thread's x-halo copies of tile it have landed
     fence_proxy_async_smem();
     __syncthreads();                 // ... and everybody else's
     if (tid == 0) {
+      mbar_wait(&dy_bar[st], (it / NST) & 1);   // the TMA'd dy tile
       fence_after_sync();
       const uint32_t sh = sbase + st * STAGE;
       const uint32_t sd = sh + HALO_BYTES;
@@ -509,7 +514,9 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
           // K16 = tile rows 2ks, 2ks+1 (never straddle an image: IMG is even) -> halo rows hb, hb+1 (+ tap r in M)
           const int hb = ((2 * ks) / IMG) * RPI + (2 * ks) % IMG;
           const uint64_t da = make_smem_desc(sh + hb * RP + s * 16, RP, P, kNoSwizzle);
-          const uint64_t db = make_smem_desc(sd + 2 * ks * 128, 128, 128 * 16, kNoSwizzle);
+          // B: MN-major, 128-byte swizzle: rows = pixels (K), 128 B = 64 channels; K16 = 2 groups of 8 rows (1024 B each);
+          // LBO = next 64-channel block (128 rows x 128 B), SBO = next 8-row group
+          const uint64_t db = make_smem_desc(sd + ks * 2048, 128 * 128, 1024, kSwizzle128B);
           mma_bf16_ss(tmem_base + (uint32_t)(s * NS), da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
         }
       mma_commit(&mma_bar[st]);
@@ -519,7 +526,8 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_small_kernel(const HaloWg
     const int nt = it + NST - 1;
     if (nt < my_n) {
       if (it >= 1) mbar_wait(&mma_bar[(it - 1) % NST], ((it - 1) / NST) & 1);
-      load_tile(first + nt * stride, nt % NST);
+      load_x(first + nt * stride, nt % NST);
+      if (tid == 0) load_dy(first + nt * stride, nt % NST);
     }
     cp_async_commit();
   }
@@ -608,16 +616,6 @@ __global__ void unpack_stem_wgrad_kernel(const float* __restrict__ acc, float* _
 //   start = stage + 2kk*SLAB + r*HWD*16 + s*16,   LBO = SLAB (next 8 channels),   SBO = HWD*16 (next tile row).
 // Only the MMA-issuing thread waits for the load; the epilogue warps never touch the halo.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
 
 template <int C, int N, int KH, int KW, int PAD, int MODE>
 __global__ void __launch_bounds__(128)
@@ -883,7 +881,27 @@ static int launch_halo_wgrad_small(const HaloWgradSmallArgs& a, cudaStream_t st)
   constexpr int RP = 4 * (TW + 2) * 16, IPT = TH / IMG, RPI = IMG + 2;
   constexpr int HROWS_LOAD = IPT * RPI, HROWS = (IPT - 1) * RPI + (IMG - 2) + 1 + 4;
   constexpr int HROWS_A = HROWS > HROWS_LOAD ? HROWS : HROWS_LOAD;
-  const size_t smem = kSmallWgradStages * (size_t)(HROWS_A * RP + 128 * NS * 2) + 256;
+  constexpr int HALO_BYTES = (HROWS_A * RP + 1023) / 1024 * 1024;
+  const size_t smem = kSmallWgradStages * (size_t)(HALO_BYTES + (NS / 64) * 128 * 128) + 1024 + 64;
+  EncodeTiledFn enc = halo_encode_fn();
+  if (!enc) {
+    set_last_error("conv_halo_wgrad (small images): cuTensorMapEncodeTiled is not available from this driver");
+    return HB200_ERR_UNSUPPORTED;
+  }
+  // dy bf16 [B, IMG, IMG, Co]: box = 64 channels (one 128-byte swizzled row per pixel) x 8 columns x IMG rows x IPT images;
+  // columns / images past the tensor are zero-filled (the virtual pixels of 4x4 images, the ragged last tile)
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {(cuuint64_t)a.Co, (cuuint64_t)IMG, (cuuint64_t)IMG, (cuuint64_t)a.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)a.Co * 2, (cuuint64_t)IMG * a.Co * 2, (cuuint64_t)IMG * IMG * a.Co * 2};
+  const cuuint32_t box[4] = {64u, 8u, (cuuint32_t)IMG, (cuuint32_t)IPT};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.dy, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("conv_halo_wgrad (small images): cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HB200_ERR_CUDA;
+  }
   auto kern = conv_halo_wgrad_small_kernel<NS, IMG>;
   static bool attr = false;
   if (!attr) {
@@ -894,7 +912,7 @@ static int launch_halo_wgrad_small(const HaloWgradSmallArgs& a, cudaStream_t st)
   int workers = kNumSMs / slices;            // one CTA per SM (3 x NS accumulator columns need most of TMEM)
   if (workers < 1) workers = 1;
   if (workers > a.ntiles) workers = a.ntiles;
-  kern<<<dim3(workers, slices), 128, smem, st>>>(a);
+  kern<<<dim3(workers, slices), 128, smem, st>>>(a, tmap);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;

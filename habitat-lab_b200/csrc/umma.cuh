@@ -148,6 +148,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---- TMA (cp.async.bulk.tensor) ------------------------------------------------------------------
+// arrive with an expected transaction byte count (the issuing thread's arrival + the bytes the TMA unit will deposit)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 4-D box load; `tmap` must be the PARAM-space address of a `const __grid_constant__ CUtensorMap` kernel parameter
+// (taken in the kernel body, never through a by-reference lambda capture: that spills a local copy)
+__device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // ---- cp.async (LDGSTS), 16 B with zero fill ---------------------------------------------
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {
   const uint32_t sz = valid ? 16u : 0u;

@@ -63,8 +63,8 @@ def _worker(rank, world, port, ngpu, q):
         hook, pol.tail_grads_hook = pol.tail_grads_hook, None   # step 1: the plain path, so the LOCAL gradients can be read
         pol.loss_and_backward(batch, 0.2, 0.5, 0.01, True)   # includes the packed RunningMeanAndVar all-reduce
         g_local = flat["grads"].detach().clone()
-        gn = ppo.before_step()                                # all-reduce + clip + Adam (the code under test)
-        torch.cuda.synchronize()
+        gn = float(ppo.before_step())                         # all-reduce + clip + Adam (the code under test); the
+        torch.cuda.synchronize()                              # returned tensor is a reused device scalar: read it now
         stats = torch.cat([b.detach().flatten().double() for b in pol.buffers()])
         g_red, p_after = flat["grads"].detach().cpu().numpy(), flat["params"].detach().cpu().numpy()
         # step 2: the overlapped path -- the recurrent / head chunk is reduced from inside the backward pass
@@ -74,7 +74,7 @@ def _worker(rank, world, port, ngpu, q):
         ppo.before_step()
         torch.cuda.synchronize()
         p_after2 = flat["params"].detach().cpu().numpy()
-        q.put((rank, p0.cpu().numpy(), g_local.cpu().numpy(), g_red, p_after, float(gn), stats.cpu().numpy(),
+        q.put((rank, p0.cpu().numpy(), g_local.cpu().numpy(), g_red, p_after, gn, stats.cpu().numpy(),
                adv.detach().cpu().numpy(), st.buffers["returns"].cpu().numpy(), st.buffers["value_preds"].cpu().numpy(),
                p_after2))
     except BaseException:   # report instead of leaving the parent waiting on the queue
