@@ -265,7 +265,8 @@ struct HaloWgradArgs {
 };
 
 template <int C, int N, int KH, int KW, int PAD>
-__global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArgs a) {
+__global__ void __launch_bounds__(128)
+conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMap tmap_dy) {
   constexpr int CJ = C / 8, HWD = TW + KW - 1;
   constexpr int P = HWD * 16, RP = CJ * P;
   constexpr int MT = (KH * CJ + 15) / 16;                  // 128-row M tiles over the (r, cj) row blocks
@@ -273,28 +274,33 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
   constexpr int HROWS = TH - 1 + RMAX;                     // halo rows that descriptors may touch
   constexpr int HROWS_LOAD = TH + KH - 1;                  // rows that hold real data
   constexpr int HALO_BYTES = HROWS * RP;
-  constexpr int DY_BYTES = 128 * N * 2;
-  constexpr int STAGE = HALO_BYTES + DY_BYTES;
+  constexpr int DY_BYTES = 128 * N * 2;                    // [pixel][N channels]: one swizzled row per pixel (TMA)
+  constexpr int STAGE = (DY_BYTES + HALO_BYTES + 1023) / 1024 * 1024;   // dy tile first: swizzle atoms need 1024-byte alignment
   constexpr int NACC = KW * MT;
   constexpr int TCOLS_RAW = NACC * N;
   constexpr int TMEM_COLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
   static_assert(TCOLS_RAW <= 512, "accumulators exceed TMEM");
+  static_assert(N == 32 || N == 64, "dy rows are 64 / 128 bytes: SWIZZLE_64B / SWIZZLE_128B");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ __align__(8) uint64_t dy_bar[2];
   __shared__ uint32_t tmem_slot;
-  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5;
+  const CUtensorMap* const tmap_p = &tmap_dy;   // param-space address (never through a by-reference lambda capture)
 
   if (tid == 0) {
     mbar_init(&mma_bar[0], 1);
     mbar_init(&mma_bar[1], 1);
+    mbar_init(&dy_bar[0], 1);
+    mbar_init(&dy_bar[1], 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   // the padding halo rows are read by the (discarded) padding M rows: keep them finite
   for (int st = 0; st < 2; ++st)
     for (int v = tid; v < (HROWS - HROWS_LOAD) * RP / 16; v += 128) {
-      const uint32_t addr = sbase + st * STAGE + HROWS_LOAD * RP + v * 16;
+      const uint32_t addr = sbase + st * STAGE + DY_BYTES + HROWS_LOAD * RP + v * 16;
       asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
     }
   const int tiles_x = a.W / TW, tiles_y = a.H / TH, tiles_per_img = tiles_x * tiles_y;
@@ -304,23 +310,18 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
     oh0 = (r / tiles_x) * TH;
     ow0 = (r % tiles_x) * TW;
   };
-  auto load_tile = [&](int tile, int st) {
+  // x halo: zero-filling cp.async into the shifted-descriptor layout (all threads).  dy tile: ONE TMA box (N channels x
+  // 8 x 16 pixels) into the MN-major swizzled layout -- as LDGSTS it was a transpose (pixel-major tensor -> channel-chunk-
+  // major rows), 2 shared-memory wavefronts per 16-byte copy, which made this kernel LSU-bound (see the small-image
+  // kernel below).
+  auto load_tile = [&, tmap_p](int tile, int st) {
     int b, oh0, ow0;
     tile_coords(tile, b, oh0, ow0);
-    const uint32_t sh = sbase + st * STAGE;
-    load_halo<C, KH, KW, PAD, HROWS_LOAD>(a.x, sh, b, oh0, ow0, a.H, a.W);
-    // dy tile: [n-chunk][py][px] 16-byte vectors  (MN-major B: SBO = 128*16, LBO = 8*16)
-    const uint32_t sd = sh + HALO_BYTES;
-    // lane mapping: 8 consecutive lanes take the SAME 16-byte channel chunk of 8 consecutive pixels (one 128-byte
-    // core-matrix row group in shared memory: bank-conflict free), the next lane octets the next 3 chunks of those
-    // pixels (64 contiguous bytes per pixel in global memory: full 32-byte sectors).  The first version walked the
-    // chunks of one pixel with consecutive lanes: 2 KB apart in shared memory = an N/8-way bank conflict per copy.
-    for (int v = tid; v < 128 * (N / 8); v += 128) {
-      const int q = v & 7, r = (v >> 3) & 3, hi = v >> 5;
-      const int nj = (hi % (N / 32)) * 4 + r, p = (hi / (N / 32)) * 8 + q;
-      const int ppy = p >> 3, ppx = p & 7;
-      const __nv_bfloat16* g = a.dy + (((size_t)b * a.H + oh0 + ppy) * a.W + ow0 + ppx) * N + nj * 8;
-      cp_async16(sd + (uint32_t)(nj * 128 + p) * 16, g, true);
+    const uint32_t sd = sbase + st * STAGE;
+    load_halo<C, KH, KW, PAD, HROWS_LOAD>(a.x, sd + DY_BYTES, b, oh0, ow0, a.H, a.W);
+    if (tid == 0) {
+      mbar_expect_tx(&dy_bar[st], (uint32_t)DY_BYTES);
+      tma_load_4d(sd, tmap_p, &dy_bar[st], 0, ow0, oh0, b);
     }
   };
   const int first = blockIdx.x, stride = gridDim.x;
@@ -342,9 +343,10 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
+      mbar_wait(&dy_bar[it & 1], (it >> 1) & 1);   // the TMA'd dy tile
       fence_after_sync();
-      const uint32_t sh = sbase + (it & 1) * STAGE;
-      const uint32_t sd = sh + HALO_BYTES;
+      const uint32_t sd = sbase + (it & 1) * STAGE;
+      const uint32_t sh = sd + DY_BYTES;
 #pragma unroll
       for (int s = 0; s < KW; ++s)
 #pragma unroll
@@ -353,7 +355,8 @@ __global__ void __launch_bounds__(128) conv_halo_wgrad_kernel(const HaloWgradArg
           for (int ks = 0; ks < TH / 2; ++ks) {
             // A: M = row blocks (stride P), K = 16 pixels = tile rows 2ks, 2ks+1 (stride RP)
             const uint64_t da = make_smem_desc(sh + 2 * ks * RP + s * 16 + mt * 16 * P, RP, P, kNoSwizzle);
-            const uint64_t db = make_smem_desc(sd + 2 * ks * 128, 128, 128 * 16, kNoSwizzle);
+            // B: MN-major swizzled rows (one pixel = N channels = 64 / 128 bytes); K16 = 2 groups of 8 rows
+            const uint64_t db = make_smem_desc(sd + ks * (16 * N * 2), 0, 8 * N * 2, N == 64 ? kSwizzle128B : kSwizzle64B);
             mma_bf16_ss(tmem_base + (uint32_t)((s * MT + mt) * N), da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
           }
       mma_commit(&mma_bar[it & 1]);
@@ -861,7 +864,26 @@ template <int C, int N, int KH, int KW, int PAD>
 static int launch_halo_wgrad(const HaloWgradArgs& a, cudaStream_t st) {
   constexpr int CJ = C / 8, HWD = TW + KW - 1, P = HWD * 16, RP = CJ * P;
   constexpr int MT = (KH * CJ + 15) / 16, RMAX = (MT * 16 + CJ - 1) / CJ, HROWS = TH - 1 + RMAX;
-  const size_t smem = 2 * (size_t)(HROWS * RP + 128 * N * 2) + 256;
+  constexpr int STAGE = (128 * N * 2 + HROWS * RP + 1023) / 1024 * 1024;
+  const size_t smem = 2 * (size_t)STAGE + 1024 + 64;
+  EncodeTiledFn enc = halo_encode_fn();
+  if (!enc) {
+    set_last_error("conv_halo_wgrad: cuTensorMapEncodeTiled is not available from this driver");
+    return HB200_ERR_UNSUPPORTED;
+  }
+  // dy bf16 [B, H, W, N]: box = N channels (one swizzled 64- / 128-byte row per pixel) x 8 x 16 pixels of one frame
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)N * 2, (cuuint64_t)a.W * N * 2, (cuuint64_t)a.H * a.W * N * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)N, (cuuint32_t)TW, (cuuint32_t)TH, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.dy, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, N == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("conv_halo_wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HB200_ERR_CUDA;
+  }
   auto kern = conv_halo_wgrad_kernel<C, N, KH, KW, PAD>;
   static int cache = 0;
   if (cache == 0) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -870,7 +892,7 @@ static int launch_halo_wgrad(const HaloWgradArgs& a, cudaStream_t st) {
   const int per_sm = blocks_per_sm((const void*)kern, smem, tcols, &cache);
   int grid = kNumSMs * per_sm;
   if (grid > a.ntiles) grid = a.ntiles;
-  kern<<<grid, 128, smem, st>>>(a);
+  kern<<<grid, 128, smem, st>>>(a, tmap);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -975,6 +997,9 @@ extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb20
   if (use_tma && k == 3 && c == 32)
     return mode == 0 ? launch_halo_tma<32, 32, 3, 3, 1, 0>(a, st) : launch_halo_tma<32, 32, 3, 3, 1, 1>(a, st);
   if (use_tma && k == 4 && mode == 0) return launch_halo_tma<16, 32, 4, 4, 2, 0>(a, st);
+  static const bool tma64 = getenv("HB200_HALO_TMA64") != nullptr;   // 64-channel layers: two TMA stages = one CTA / SM
+  if (use_tma && tma64 && k == 3 && c == 64)
+    return mode == 0 ? launch_halo_tma<64, 64, 3, 3, 1, 0>(a, st) : launch_halo_tma<64, 64, 3, 3, 1, 1>(a, st);
   if (k == 3 && c == 32) return mode == 0 ? launch_halo<32, 32, 3, 3, 1, 0>(a, st) : launch_halo<32, 32, 3, 3, 1, 1>(a, st);
   if (k == 3 && c == 64) return mode == 0 ? launch_halo<64, 64, 3, 3, 1, 0>(a, st) : launch_halo<64, 64, 3, 3, 1, 1>(a, st);
   HB_CHECK_ARG(mode == 0, "conv_halo: the stem has no data gradient");

@@ -20,7 +20,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ---- descriptors ---------------------------------------------------------------------
-enum Layout : uint32_t { kNoSwizzle = 0, kSwizzle128B = 2 };
+enum Layout : uint32_t { kNoSwizzle = 0, kSwizzle128B = 2, kSwizzle64B = 4 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
                                                    uint32_t sbo_bytes, uint32_t layout) {
