@@ -627,6 +627,10 @@ conv_halo_tma_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap)
   constexpr int CJ = Cfg::CJ, HH = Cfg::HH, HWD = Cfg::HWD;
   constexpr uint32_t SLAB = (uint32_t)((HH * HWD * 16 + 127) / 128 * 128);
   constexpr uint32_t STAGE = CJ * SLAB;
+  // halo stages: two when they fit next to the resident weights with >= 2 CTAs per SM; ONE for C = N = 64 (72 KB of
+  // weights): the load of tile it+1 then starts when the MMAs of tile it are done, and the second CTA on the SM covers
+  // the gap -- like conv_halo_kernel, minus the 2880 LSU cycles per tile its cp.async halo gather costs
+  constexpr int NB = (Cfg::W_BYTES + 2 * (int)STAGE > 110 * 1024) ? 1 : 2;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar[2];
   __shared__ __align__(8) uint64_t ld_bar[2];
@@ -686,16 +690,16 @@ conv_halo_tma_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap)
   for (int it = 0; it <= my_n; ++it) {
     // (1) MMAs of tile it-1 are complete (frees halo stage (it+1)&1 and fills TMEM stage (it-1)&1)
     if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-    // (2) one thread starts the TMA load of tile it+1
-    if (tid == 0 && it + 1 < my_n) issue_halo(first + (it + 1) * stride, (it + 1) & 1);
+    // (2) one thread starts the TMA load of tile it+1 (two stages; with one stage see (5))
+    if (NB == 2 && tid == 0 && it + 1 < my_n) issue_halo(first + (it + 1) * stride, (it + 1) & 1);
     // (3) MMAs of tile it as soon as its halo has landed
     if (it < my_n) {
       fence_before_sync();  // orders the previous iteration's tcgen05.ld (TMEM stage reuse)
       __syncthreads();
       if (tid == 0) {
-        mbar_wait(&ld_bar[it & 1], (it >> 1) & 1);
+        mbar_wait(&ld_bar[NB == 2 ? (it & 1) : 0], NB == 2 ? ((it >> 1) & 1) : (it & 1));
         fence_after_sync();
-        const uint32_t sh = s_halo0 + (uint32_t)(it & 1) * STAGE;
+        const uint32_t sh = s_halo0 + (uint32_t)(NB == 2 ? (it & 1) : 0) * STAGE;
         const uint32_t tacc = tmem_base + (uint32_t)((it & 1) * N);
         uint32_t accum = 0;
 #pragma unroll
@@ -773,6 +777,11 @@ conv_halo_tma_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap)
         }
       }
     }
+    // (5) single halo stage: tile it+1 may be loaded once the MMAs of tile it have consumed the stage
+    if (NB == 1 && tid == 0 && it + 1 < my_n) {
+      mbar_wait(&mma_bar[it & 1], (it >> 1) & 1);
+      issue_halo(first + (it + 1) * stride, 0);
+    }
   }
   fence_before_sync();
   __syncthreads();
@@ -847,7 +856,8 @@ static int launch_halo_tma(const HaloArgs& a, cudaStream_t st) {
     return HB200_ERR_CUDA;
   }
   constexpr size_t slab = (size_t)((Cfg::HH * Cfg::HWD * 16 + 127) / 128 * 128);
-  const size_t smem = Cfg::W_BYTES + 2 * Cfg::CJ * slab + 256;
+  constexpr int nstage = (Cfg::W_BYTES + 2 * (int)(Cfg::CJ * slab) > 110 * 1024) ? 1 : 2;
+  const size_t smem = Cfg::W_BYTES + nstage * Cfg::CJ * slab + 256;
   auto kern = conv_halo_tma_kernel<C, N, KH, KW, PAD, MODE>;
   static int cache = 0;
   if (cache == 0) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
