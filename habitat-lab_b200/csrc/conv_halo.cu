@@ -1001,14 +1001,15 @@ extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb20
   a.B = batch; a.H = h; a.W = w; a.gn_groups = gn_groups > 0 ? gn_groups : 1;
   a.ntiles = batch * (h / TH) * (w / TW);
   cudaStream_t st = (cudaStream_t)stream;
-  // TMA-fed halo (conv_halo_tma_kernel) for the 32-channel layers and the stem: measured 17-18 % faster than the
-  // cp.async gather on B200 (0.219 -> 0.183 ms per 32->32 layer, stem 0.711 -> 0.581 ms); HB200_NO_HALO_TMA=1 disables
+  // TMA-fed halo (conv_halo_tma_kernel) for every halo layer: measured 17-18 % faster than the cp.async gather on
+  // B200 for the 32-channel layers and the stem (0.219 -> 0.183 ms, 0.711 -> 0.581 ms); HB200_NO_HALO_TMA=1 disables
   static const bool use_tma = getenv("HB200_NO_HALO_TMA") == nullptr;
   if (use_tma && k == 3 && c == 32)
     return mode == 0 ? launch_halo_tma<32, 32, 3, 3, 1, 0>(a, st) : launch_halo_tma<32, 32, 3, 3, 1, 1>(a, st);
   if (use_tma && k == 4 && mode == 0) return launch_halo_tma<16, 32, 4, 4, 2, 0>(a, st);
-  static const bool tma64 = getenv("HB200_HALO_TMA64") != nullptr;   // 64-channel layers: two TMA stages = one CTA / SM
-  if (use_tma && tma64 && k == 3 && c == 64)
+  // 64-channel layers: single halo stage (72 KB of resident weights), two CTAs per SM: 0.156 -> 0.146 ms forward,
+  // 0.128 -> 0.101 ms dgrad per layer against the cp.async gather (its 1440 copies per tile = 2880 LSU cycles)
+  if (use_tma && k == 3 && c == 64)
     return mode == 0 ? launch_halo_tma<64, 64, 3, 3, 1, 0>(a, st) : launch_halo_tma<64, 64, 3, 3, 1, 1>(a, st);
   if (k == 3 && c == 32) return mode == 0 ? launch_halo<32, 32, 3, 3, 1, 0>(a, st) : launch_halo<32, 32, 3, 3, 1, 1>(a, st);
   if (k == 3 && c == 64) return mode == 0 ? launch_halo<64, 64, 3, 3, 1, 0>(a, st) : launch_halo<64, 64, 3, 3, 1, 1>(a, st);
