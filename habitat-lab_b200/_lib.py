@@ -49,6 +49,8 @@ SIGNATURES = {
     "hb200_packed_weight_elems": ("z", "iiii"),
     "hb200_set_umma_layout": ("i", "i"),
     "hb200_get_umma_layout": ("i", ""),
+    "hb200_set_halo_tma": ("i", "i"),
+    "hb200_get_halo_tma": ("i", ""),
     "hb200_conv_halo_supported": ("i", "iiiii"),
     "hb200_conv_halo_wgrad_supported": ("i", "iiiii"),
     "hb200_pack_halo_weight": ("i", "pp" + "iiiiii" + "p"),

@@ -953,6 +953,14 @@ static int launch_halo_wgrad_small(const HaloWgradSmallArgs& a, cudaStream_t st)
 
 using namespace hb200;
 
+// halo loads by TMA (default) or by the cp.async gather kernel (HB200_NO_HALO_TMA=1, or hb200_set_halo_tma(0) from tests)
+static int g_halo_tma = getenv("HB200_NO_HALO_TMA") == nullptr ? 1 : 0;
+extern "C" int hb200_set_halo_tma(int enable) {
+  g_halo_tma = enable ? 1 : 0;
+  return HB200_OK;
+}
+extern "C" int hb200_get_halo_tma(void) { return g_halo_tma; }
+
 /* which (C, N, k) combinations have a halo instantiation */
 extern "C" int hb200_conv_halo_supported(int c, int n, int k, int h, int w) {
   if (h % TH || w % TW) return 0;
@@ -1003,7 +1011,7 @@ extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb20
   cudaStream_t st = (cudaStream_t)stream;
   // TMA-fed halo (conv_halo_tma_kernel) for every halo layer: measured 17-18 % faster than the cp.async gather on
   // B200 for the 32-channel layers and the stem (0.219 -> 0.183 ms, 0.711 -> 0.581 ms); HB200_NO_HALO_TMA=1 disables
-  static const bool use_tma = getenv("HB200_NO_HALO_TMA") == nullptr;
+  const bool use_tma = g_halo_tma != 0;
   if (use_tma && k == 3 && c == 32)
     return mode == 0 ? launch_halo_tma<32, 32, 3, 3, 1, 0>(a, st) : launch_halo_tma<32, 32, 3, 3, 1, 1>(a, st);
   if (use_tma && k == 4 && mode == 0) return launch_halo_tma<16, 32, 4, 4, 2, 0>(a, st);

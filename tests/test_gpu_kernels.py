@@ -361,9 +361,19 @@ def test_conv_fwd_dgrad_wgrad(hb, case):
 HALO_CASES = [(3, 32, 32, 32, 32), (2, 16, 16, 64, 64), (5, 16, 8, 32, 32), (600, 32, 32, 32, 32)]
 
 
+@pytest.fixture(params=[1, 0], ids=["tma", "cp_async"])
+def halo_loader(hb, request):
+    """both halo load paths of the forward / dgrad halo kernels: TMA box copies (default) and the cp.async gather"""
+    lib = hb.load()
+    prev = lib.hb200_get_halo_tma()
+    lib.hb200_set_halo_tma(request.param)
+    yield request.param
+    lib.hb200_set_halo_tma(prev)
+
+
 @pytest.mark.parametrize("B,H,W,C,N", HALO_CASES)
-def test_conv_halo_3x3(hb, B, H, W, C, N):
-    """halo kernels (one input load per tile, taps by descriptor shift) vs fp32 conv of the same bf16 operands"""
+def test_conv_halo_3x3(hb, halo_loader, B, H, W, C, N):
+    """halo kernels (one input load per tile, taps by descriptor shift) vs fp32 conv of the same rounded operands"""
     from habitat_lab_b200 import ops
 
     assert ops.conv_halo_supported(C, N, 3, H, W)
@@ -431,7 +441,7 @@ def test_conv_halo_wgrad_small_images(hb, B, HW, C, N):
 
 
 @pytest.mark.parametrize("B,Hp,Wp", [(2, 128, 128), (3, 64, 32)])
-def test_conv_halo_stem_s2d(hb, B, Hp, Wp):
+def test_conv_halo_stem_s2d(hb, halo_loader, B, Hp, Wp):
     """7x7 stride-2 pad-3 stem == 4x4 stride-1 conv over the space-to-depth input"""
     from habitat_lab_b200 import ops
 
