@@ -88,6 +88,48 @@ __device__ __forceinline__ void load_halo(const __nv_bfloat16* __restrict__ x, u
   }
 }
 
+// Register-staged variant of load_halo for the weight-gradient kernels: coalesced LDG.128 (consecutive lanes walk the
+// channel chunks of consecutive pixels of a halo row = contiguous global bytes) into registers, later STS.128 into the
+// shifted-descriptor layout (bank-conflict free per 8-lane phase).  As LDGSTS the same copies cost 2 shared-memory
+// wavefronts per lane (ncu, profiles/r02_notes.md); staged through registers they cost ~8x fewer LSU cycles, and the
+// global latency hides behind the wait for the previous tile's MMAs.
+template <int C, int KH, int KW, int PAD, int ROWS, int NTHR>
+struct HaloRegs {
+  static constexpr int CJ = C / 8, HWD = TW + KW - 1;
+  static constexpr int NV = ROWS * CJ * HWD;
+  static constexpr int PER = (NV + NTHR - 1) / NTHR;
+  uint4 v[PER];
+  __device__ __forceinline__ void load(const __nv_bfloat16* __restrict__ x, int lt, int b, int oh0, int ow0, int H, int W) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = lt + i * NTHR;
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      if (idx < NV) {
+        const int cj = idx % CJ;
+        const int t = idx / CJ;
+        const int hx = t % HWD, hy = t / HWD;
+        const int ih = oh0 - PAD + hy, iw = ow0 - PAD + hx;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+          r = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)b * H + ih) * W + iw) * C + cj * 8));
+      }
+      v[i] = r;
+    }
+  }
+  __device__ __forceinline__ void store(uint32_t sdst, int lt) const {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int idx = lt + i * NTHR;
+      if (idx < NV) {
+        const int cj = idx % CJ;
+        const int t = idx / CJ;
+        const int hx = t % HWD, hy = t / HWD;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sdst + (uint32_t)(((hy * CJ + cj) * HWD + hx) * 16)),
+                     "r"(v[i].x), "r"(v[i].y), "r"(v[i].z), "r"(v[i].w) : "memory");
+      }
+    }
+  }
+};
+
 template <int C, int N, int KH, int KW, int PAD, int MODE>  // MODE 0: fwd (+stats), 1: dgrad (+addend)
 __global__ void __launch_bounds__(128) conv_halo_kernel(const HaloArgs a) {
   using Cfg = HaloCfg<C, N, KH, KW, PAD>;
@@ -314,11 +356,17 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   // 8 x 16 pixels) into the MN-major swizzled layout -- as LDGSTS it was a transpose (pixel-major tensor -> channel-chunk-
   // major rows), 2 shared-memory wavefronts per 16-byte copy, which made this kernel LSU-bound (see the small-image
   // kernel below).
-  auto load_tile = [&, tmap_p](int tile, int st) {
+  HaloRegs<C, KH, KW, PAD, HROWS_LOAD, 128> xr;   // the x halo of the NEXT tile, in flight in registers
+  auto fetch_x = [&](int tile) {
+    int b, oh0, ow0;
+    tile_coords(tile, b, oh0, ow0);
+    xr.load(reinterpret_cast<const __nv_bfloat16*>(a.x), tid, b, oh0, ow0, a.H, a.W);
+  };
+  auto commit_tile = [&, tmap_p](int tile, int st) {   // stage `st` is free: x halo registers -> smem, dy tile by TMA
     int b, oh0, ow0;
     tile_coords(tile, b, oh0, ow0);
     const uint32_t sd = sbase + st * STAGE;
-    load_halo<C, KH, KW, PAD, HROWS_LOAD>(a.x, sd + DY_BYTES, b, oh0, ow0, a.H, a.W);
+    xr.store(sd + DY_BYTES, tid);
     if (tid == 0) {
       mbar_expect_tx(&dy_bar[st], (uint32_t)DY_BYTES);
       tma_load_4d(sd, tmap_p, &dy_bar[st], 0, ow0, oh0, b);
@@ -326,8 +374,11 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   };
   const int first = blockIdx.x, stride = gridDim.x;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
-  if (my_n > 0) load_tile(first, 0);
-  cp_async_commit();
+  if (my_n > 0) {
+    fetch_x(first);
+    commit_tile(first, 0);
+  }
+  fence_proxy_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -336,11 +387,11 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
 
   for (int it = 0; it < my_n; ++it) {
-    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-    if (it + 1 < my_n) load_tile(first + (it + 1) * stride, (it + 1) & 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    fence_proxy_async_smem();
+    const bool more = it + 1 < my_n;
+    if (more) fetch_x(first + (it + 1) * stride);                 // global loads in flight ...
+    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);   // ... while the stage drains
+    if (more) commit_tile(first + (it + 1) * stride, (it + 1) & 1);
+    fence_proxy_async_smem();   // st.shared (generic proxy) -> tcgen05 (async proxy)
     __syncthreads();
     if (tid == 0) {
       mbar_wait(&dy_bar[it & 1], (it >> 1) & 1);   // the TMA'd dy tile
@@ -460,20 +511,44 @@ conv_halo_wgrad_small_kernel(const HaloWgradSmallArgs a, const __grid_constant__
   // 8 x IMG x IPT pixels, hardware 128-byte swizzle = the MN-major SWIZZLE_128B operand layout; for 4x4 images the box
   // is 8 wide and the 4 out-of-range columns are the zero "virtual pixels"): zero LSU work, one thread.  Warps 1-3
   // keep loading the x halo with cp.async (its shifted-descriptor layout has no TMA box form).
-  auto load_x = [&](int tile, int st) {
+  // x halo: LDG.128 into registers (4 lanes = the 64 bytes of one pixel's channel slice, consecutive pixels follow),
+  // later STS.128 into the shifted-descriptor layout -- 8x fewer LSU cycles than the same copies as LDGSTS
+  constexpr int XV = HROWS_LOAD * CJ * HWD, XPER = (XV + 95) / 96;
+  uint4 xr[XPER];
+  auto fetch_x = [&](int tile) {
+    if (warp == 0) return;
+    const int lt = tid - 32;
+    const int b0 = tile * IPT;
+#pragma unroll
+    for (int i = 0; i < XPER; ++i) {
+      const int v = lt + i * 96;
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      if (v < XV) {
+        const int cj = v % CJ;
+        const int t = v / CJ;
+        const int hx = t % HWD, hy = t / HWD;
+        const int j = hy / RPI, ih = hy - j * RPI - 1, iw = hx - 1;
+        const int b = b0 + j;
+        if (b < a.B && ih >= 0 && ih < IMG && iw >= 0 && iw < IMG)
+          r = __ldg(reinterpret_cast<const uint4*>(a.x + ((((size_t)b * IMG + ih) * IMG + iw) * a.Ci + c_off + cj * 8)));
+      }
+      xr[i] = r;
+    }
+  };
+  auto store_x = [&](int st) {
     if (warp == 0) return;
     const int lt = tid - 32;
     const uint32_t sh = sbase + st * STAGE;
-    const int b0 = tile * IPT;
-    for (int v = lt; v < HROWS_LOAD * CJ * HWD; v += 96) {
-      const int cj = v % CJ;
-      const int t = v / CJ;
-      const int hx = t % HWD, hy = t / HWD;
-      const int j = hy / RPI, ih = hy - j * RPI - 1, iw = hx - 1;
-      const int b = b0 + j;
-      const bool ok = b < a.B && ih >= 0 && ih < IMG && iw >= 0 && iw < IMG;
-      const grad_t* g = ok ? a.x + ((((size_t)b * IMG + ih) * IMG + iw) * a.Ci + c_off + cj * 8) : a.x;
-      cp_async16(sh + (uint32_t)(((hy * CJ + cj) * HWD + hx) * 16), g, ok);
+#pragma unroll
+    for (int i = 0; i < XPER; ++i) {
+      const int v = lt + i * 96;
+      if (v < XV) {
+        const int cj = v % CJ;
+        const int t = v / CJ;
+        const int hx = t % HWD, hy = t / HWD;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(sh + (uint32_t)(((hy * CJ + cj) * HWD + hx) * 16)),
+                     "r"(xr[i].x), "r"(xr[i].y), "r"(xr[i].z), "r"(xr[i].w) : "memory");
+      }
     }
   };
   auto load_dy = [&, tmap_p](int tile, int st) {   // thread 0 only
@@ -485,15 +560,16 @@ conv_halo_wgrad_small_kernel(const HaloWgradSmallArgs a, const __grid_constant__
   };
   const int first = blockIdx.x, stride = gridDim.x;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
-  // prologue: tiles 0 .. NST-2 in flight, one cp.async group per tile
+  // prologue: tiles 0 .. NST-2 staged
 #pragma unroll
   for (int i = 0; i < NST - 1; ++i) {
     if (i < my_n) {
-      load_x(first + i * stride, i);
+      fetch_x(first + i * stride);
+      store_x(i);
       if (tid == 0) load_dy(first + i * stride, i);
     }
-    cp_async_commit();
   }
+  fence_proxy_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -502,9 +578,10 @@ conv_halo_wgrad_small_kernel(const HaloWgradSmallArgs a, const __grid_constant__
 
   for (int it = 0; it < my_n; ++it) {
     const int st = it % NST;
-    cp_async_wait<NST - 2>();        // this thread's x-halo copies of tile it have landed
-    fence_proxy_async_smem();
-    __syncthreads();                 // ... and everybody else's
+    const int nt = it + NST - 1;     // the tile that will refill the stage tile it-1 used
+    if (nt < my_n) fetch_x(first + nt * stride);   // its x halo: global loads in flight from here on
+    fence_proxy_async_smem();        // x halo of tile it was stored (st.shared) an iteration ago
+    __syncthreads();
     if (tid == 0) {
       mbar_wait(&dy_bar[st], (it / NST) & 1);   // the TMA'd dy tile
       fence_after_sync();
@@ -526,13 +603,11 @@ conv_halo_wgrad_small_kernel(const HaloWgradSmallArgs a, const __grid_constant__
     }
     // refill the stage tile it-1 used with tile it+NST-1 (its MMAs were queued before tile it's, which now keep the
     // tensor core busy while we wait and load)
-    const int nt = it + NST - 1;
     if (nt < my_n) {
       if (it >= 1) mbar_wait(&mma_bar[(it - 1) % NST], ((it - 1) / NST) & 1);
-      load_x(first + nt * stride, nt % NST);
+      store_x(nt % NST);
       if (tid == 0) load_dy(first + nt * stride, nt % NST);
     }
-    cp_async_commit();
   }
   if (my_n > 0) {
     mbar_wait(&mma_bar[(my_n - 1) % NST], ((my_n - 1) / NST) & 1);
