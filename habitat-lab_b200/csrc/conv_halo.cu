@@ -356,8 +356,12 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   // 8 x 16 pixels) into the MN-major swizzled layout -- as LDGSTS it was a transpose (pixel-major tensor -> channel-chunk-
   // major rows), 2 shared-memory wavefronts per 16-byte copy, which made this kernel LSU-bound (see the small-image
   // kernel below).
-  HaloRegs<C, KH, KW, PAD, HROWS_LOAD, 128> xr;   // the x halo of the NEXT tile, in flight in registers
+  // Register staging pays while the halo is <= 8 vectors per thread (C <= 32: 0.211 -> 0.165 ms per layer, stem 0.79 ->
+  // 0.67); for C = 64 (12 vectors, 128 registers) the lost occupancy costs more than the LDGSTS wavefronts: cp.async there.
+  constexpr bool kRegStage = HROWS_LOAD * CJ * HWD <= 128 * 8;
+  HaloRegs<C, KH, KW, PAD, kRegStage ? HROWS_LOAD : 1, 128> xr;   // the x halo of the NEXT tile, in flight in registers
   auto fetch_x = [&](int tile) {
+    if (!kRegStage) return;
     int b, oh0, ow0;
     tile_coords(tile, b, oh0, ow0);
     xr.load(reinterpret_cast<const __nv_bfloat16*>(a.x), tid, b, oh0, ow0, a.H, a.W);
@@ -366,7 +370,8 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
     int b, oh0, ow0;
     tile_coords(tile, b, oh0, ow0);
     const uint32_t sd = sbase + st * STAGE;
-    xr.store(sd + DY_BYTES, tid);
+    if (kRegStage) xr.store(sd + DY_BYTES, tid);
+    else load_halo<C, KH, KW, PAD, HROWS_LOAD>(a.x, sd + DY_BYTES, b, oh0, ow0, a.H, a.W);
     if (tid == 0) {
       mbar_expect_tx(&dy_bar[st], (uint32_t)DY_BYTES);
       tma_load_4d(sd, tmap_p, &dy_bar[st], 0, ow0, oh0, b);
@@ -378,6 +383,7 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
     fetch_x(first);
     commit_tile(first, 0);
   }
+  cp_async_commit();
   fence_proxy_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -391,7 +397,9 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
     if (more) fetch_x(first + (it + 1) * stride);                 // global loads in flight ...
     if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);   // ... while the stage drains
     if (more) commit_tile(first + (it + 1) * stride, (it + 1) & 1);
-    fence_proxy_async_smem();   // st.shared (generic proxy) -> tcgen05 (async proxy)
+    cp_async_commit();
+    cp_async_wait<1>();         // cp.async variant: this thread's copies of tile it (issued an iteration ago)
+    fence_proxy_async_smem();   // st.shared / cp.async (generic proxy) -> tcgen05 (async proxy)
     __syncthreads();
     if (tid == 0) {
       mbar_wait(&dy_bar[it & 1], (it >> 1) & 1);   // the TMA'd dy tile
