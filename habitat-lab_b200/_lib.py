@@ -85,6 +85,7 @@ SIGNATURES = {
     "hb200_relu_bwd": ("i", "pplll" + "i" + "p"),
     "hb200_f32_chw_to_bf16_hwc": ("i", "pp" + "iii" + "p"),
     "hb200_heads_fwd": ("i", "ppppp" + "iii" + "pp" + "p"),
+    "hb200_heads_act": ("i", "pppppp" + "iii" + "pppp" + "p"),
     "hb200_embed_fwd": ("i", "pppppppp" + "iii" + "p"),
     "hb200_embed_bwd": ("i", "ppppp" + "iiii" + "ppp" + "p"),
     "hb200_sensor_linear_fwd": ("i", "pipii" + "ppp" + "iii" + "p"),

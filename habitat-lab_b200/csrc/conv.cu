@@ -55,12 +55,15 @@ struct ConvArgs {
   const float* bias;  // forward only: per-output-channel bias (SimpleCNN), or nullptr
   int relu;           // forward only: ReLU in the epilogue
   int s2_classes;  // dgrad of a stride-2 conv: rows are grouped by output-pixel parity class (4 x M/4)
+  int wbn;         // N tile the weight image was packed for (>= the kernel's BN: a CTA may take a row slice of a tile)
 };
 
-template <int BN, int MODE, int LAYOUT>
+// NST = depth of the cp.async ring.  3 at the learner's sizes (several CTAs per SM hide the latency); the few-CTA launches
+// of the actor are one dependent memory latency per chunk and get a deeper ring instead.
+template <int BN, int MODE, int LAYOUT, int NST = kStages>
 __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mma_bar[kStages];
+  __shared__ __align__(8) uint64_t mma_bar[NST];
   __shared__ uint32_t tmem_slot;
   constexpr uint32_t kABytes = kTileM * kChunkK * 2;
   constexpr uint32_t kBBytes = BN * kChunkK * 2;
@@ -123,7 +126,7 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kStages; ++s) mbar_init(&mma_bar[s], 1);
+    for (int s = 0; s < NST; ++s) mbar_init(&mma_bar[s], 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
@@ -133,38 +136,69 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
   const uint32_t tmem_base = tmem_slot;
   const int n_valid = n_valid_s;
   const int taps = a.kh * a.kw;
-  const __nv_bfloat16* wtile = a.wimg + (size_t)blockIdx.y * a.nchunks * (BN * kChunkK);
+  // the image is [packed tile][chunk][wbn rows x 64]; in the 128B-swizzle layout a BN-row slice of a packed tile is a
+  // contiguous run of whole 8-row groups, so a narrower CTA tile reads rows [n0 % wbn, +BN) of every chunk
+  const int wbn = a.wbn;
+  const __nv_bfloat16* wtile =
+      a.wimg + (size_t)(n0 / wbn) * a.nchunks * ((size_t)wbn * kChunkK) + (size_t)(n0 % wbn) * kChunkK;
+
+  // LAYOUT 1: the 8 rows this thread gathers for (row = tid/8 + 16 i) never change -> their pixel origin lives in
+  // registers (frame base, first input row / column of the window; an out-of-range row gets an origin no tap can reach).
+  // Per chunk and row that leaves two adds, two unsigned range checks and the address (this loop was 440 warp
+  // instructions per chunk and the whole cost of the few-CTA launches: ncu, one warp per scheduler, 9 % issue).
+  int rbase[8], rh[8], rw[8];
+  uint32_t soff[8];
+  const int jv = tid & 7;
+  if (LAYOUT == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = (tid >> 3) + 16 * i;
+      const int4 ri = row_info[row];
+      rbase[i] = ri.x * a.SH * a.SW;
+      if (MODE == 0) {
+        rh[i] = ri.w ? ri.y * a.stride - a.pad : -(1 << 20);
+        rw[i] = ri.z * a.stride - a.pad;
+      } else {
+        rh[i] = ri.w ? ri.y + a.pad : -(1 << 20);
+        rw[i] = ri.z + a.pad;
+      }
+      soff[i] = tile_off<1>(row, jv, kTileM);
+    }
+  }
+  const int inv_kw = 65536 / a.kw + 1;   // tap / kw == (tap * inv_kw) >> 16 for tap < 8192, kw <= 8
 
   auto load_chunk = [&](int chunk, int stage) {
     const uint32_t sa = smem_base + stage * kStageBytes;
     const uint32_t sb = sa + kABytes;
     if (LAYOUT == 1) {
-      const int j = tid & 7;
-      const int k0 = (chunk * 8 + j) << 3;
+      const int k0 = (chunk * 8 + jv) << 3;
       const int tap = k0 >> a.cshift;
       const int c0 = k0 & (a.SC - 1);
-      const int r = tap / a.kw, s = tap - r * a.kw;
+      const int r = (tap * inv_kw) >> 16, s = tap - r * a.kw;
       const bool tap_ok = tap < taps;
+      const __nv_bfloat16* srcc = a.src + c0;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int row = (tid >> 3) + 16 * i;
-        const int4 ri = row_info[row];
-        bool ok = ri.w && tap_ok;
         int ih, iw;
+        bool ok = tap_ok;
         if (MODE == 0) {
-          ih = ri.y * a.stride - a.pad + r;
-          iw = ri.z * a.stride - a.pad + s;
-          ok = ok && ih >= 0 && ih < a.SH && iw >= 0 && iw < a.SW;
+          ih = rh[i] + r;
+          iw = rw[i] + s;
         } else {
-          const int th = ri.y + a.pad - r, tw = ri.z + a.pad - s;
-          ih = th / a.stride;
-          iw = tw / a.stride;
-          ok = ok && th >= 0 && tw >= 0 && (ih * a.stride == th) && (iw * a.stride == tw) &&
-               ih < a.SH && iw < a.SW;
+          const int th = rh[i] - r, tw = rw[i] - s;
+          if (a.stride == 1) {
+            ih = th; iw = tw;
+          } else if (a.stride == 2) {
+            ih = th >> 1; iw = tw >> 1;
+            ok = ok && (((th | tw) & 1) == 0);
+          } else {
+            ih = th / a.stride; iw = tw / a.stride;
+            ok = ok && th >= 0 && tw >= 0 && (ih * a.stride == th) && (iw * a.stride == tw);
+          }
         }
-        const __nv_bfloat16* g =
-            ok ? a.src + ((((size_t)ri.x * a.SH + ih) * a.SW + iw) << a.cshift) + c0 : a.src;
-        cp_async16(sa + tile_off<1>(row, j, kTileM), g, ok);
+        ok = ok && (unsigned)ih < (unsigned)a.SH && (unsigned)iw < (unsigned)a.SW;
+        const __nv_bfloat16* g = ok ? srcc + ((size_t)(rbase[i] + ih * a.SW + iw) << a.cshift) : a.src;
+        cp_async16(sa + soff[i], g, ok);
       }
     } else {
 #pragma unroll
@@ -191,7 +225,7 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
       cp_async16(sa + tile_off<LAYOUT>(tid, j, kTileM), g, ok);
     }
     }
-    const uint4* wsrc = reinterpret_cast<const uint4*>(wtile + (size_t)chunk * (BN * kChunkK));
+    const uint4* wsrc = reinterpret_cast<const uint4*>(wtile + (size_t)chunk * ((size_t)wbn * kChunkK));
 #pragma unroll
     for (int i = 0; i < BN / 16; ++i) {
       const int v = tid + i * 128;
@@ -201,15 +235,15 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
 
   // forward: fp16 activations x fp16 weight image; dgrad: bf16 gradients x bf16 transposed weight image
   constexpr uint32_t idesc = MODE == 0 ? make_idesc_f16(kTileM, BN, 0, 0, kFmtF16, kFmtF16) : make_idesc_bf16(kTileM, BN, 0, 0);
-  // ---- software pipeline: cp.async runs kStages-1 chunks ahead of the tensor core ----
+  // ---- software pipeline: cp.async runs NST-1 chunks ahead of the tensor core ----
 #pragma unroll
-  for (int c = 0; c < kStages - 1; ++c) {
+  for (int c = 0; c < NST - 1; ++c) {
     if (c < n_valid) load_chunk(chunk_ids[c], c);
     cp_async_commit();
   }
   for (int c = 0; c < n_valid; ++c) {
-    const int stage = c % kStages;
-    cp_async_wait<kStages - 2>();
+    const int stage = c % NST;
+    cp_async_wait<NST - 2>();
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -222,16 +256,16 @@ __global__ void __launch_bounds__(128) conv_igemm_kernel(const ConvArgs a) {
                     idesc, (c > 0 || kk > 0) ? 1u : 0u);
       mma_commit(&mma_bar[stage]);
     }
-    const int nc = c + kStages - 1;
+    const int nc = c + NST - 1;
     if (nc < n_valid) {
-      if (c >= 1) mbar_wait(&mma_bar[(c - 1) % kStages], ((c - 1) / kStages) & 1);
-      load_chunk(chunk_ids[nc], nc % kStages);
+      if (c >= 1) mbar_wait(&mma_bar[(c - 1) % NST], ((c - 1) / NST) & 1);
+      load_chunk(chunk_ids[nc], nc % NST);
     }
     cp_async_commit();
   }
   if (n_valid > 0) {
     const int last = n_valid - 1;
-    mbar_wait(&mma_bar[last % kStages], (last / kStages) & 1);
+    mbar_wait(&mma_bar[last % NST], (last / NST) & 1);
   }
   fence_after_sync();
 
@@ -650,24 +684,37 @@ static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 static int pick_bn(int n) { return n >= 256 ? 256 : n; }
 
 template <int MODE>
-static int launch_igemm(const ConvArgs& a, int BN, cudaStream_t st) {
+static int launch_igemm(ConvArgs a, int BN, cudaStream_t st) {
+  a.wbn = BN;
+  // few output rows (the actor's 64-frame batches: 8 row tiles for the 4x4 layers): a 256-wide N tile leaves 8 CTAs on
+  // 148 SMs, each walking the whole K serially.  Narrower N tiles (slices of the packed tile, 128B-swizzle layout
+  // only) multiply the CTA count; the activation rows are re-gathered per slice out of L2.
+  bool deep = false;
+  if (g_umma_layout == 1) {
+    const int mt = a.s2_classes ? 4 * cdiv(a.M / 4, kTileM) : cdiv(a.M, kTileM);
+    while (BN > 32 && 2LL * mt * (a.OC / BN) <= kNumSMs) BN /= 2;
+    // at most one CTA per SM: nothing else hides the gather latency -> deep ring (uses the whole shared memory)
+    deep = (long long)mt * (a.OC / BN) <= kNumSMs && a.nchunks > kStages;
+  }
   // the kernel walks a per-CTA list of K chunks held in shared memory: a longer reduction must fail loudly, never truncate
   HB_CHECK_ARG(a.nchunks <= kMaxChunks, "conv: K = kh*kw*C = %d exceeds %d", a.nchunks * kChunkK, kMaxChunks * kChunkK);
   dim3 grid(a.s2_classes ? 4 * cdiv(a.M / 4, kTileM) : cdiv(a.M, kTileM), a.OC / BN);
-  const size_t smem = (size_t)kStages * (kTileM * kChunkK * 2 + BN * kChunkK * 2) + 1024;
-#define HB_CONV_CASE(bn, L)                                                                     \
+#define HB_CONV_CASE(bn, L, nst)                                                                \
   {                                                                                             \
-    auto kern = conv_igemm_kernel<bn, MODE, L>;                                                 \
+    const size_t smem = (size_t)(nst) * (kTileM * kChunkK * 2 + bn * kChunkK * 2) + 1024;       \
+    auto kern = conv_igemm_kernel<bn, MODE, L, nst>;                                            \
     HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, 128, smem, st>>>(a);                                                           \
   }
-#define HB_CONV_BN(bn)                      \
-  if (g_umma_layout == 0) HB_CONV_CASE(bn, 0) else HB_CONV_CASE(bn, 1)
+#define HB_CONV_BN(bn, nst_deep)                                \
+  if (g_umma_layout == 0) HB_CONV_CASE(bn, 0, kStages)          \
+  else if (deep) HB_CONV_CASE(bn, 1, nst_deep)                  \
+  else HB_CONV_CASE(bn, 1, kStages)
   switch (BN) {
-    case 32: HB_CONV_BN(32); break;
-    case 64: HB_CONV_BN(64); break;
-    case 128: HB_CONV_BN(128); break;
-    case 256: HB_CONV_BN(256); break;
+    case 32: HB_CONV_BN(32, 8); break;
+    case 64: HB_CONV_BN(64, 8); break;
+    case 128: HB_CONV_BN(128, 6); break;
+    case 256: HB_CONV_BN(256, 4); break;
     default:
       set_last_error("conv: unsupported N tile %d", BN);
       return HB200_ERR_UNSUPPORTED;

@@ -1354,6 +1354,82 @@ __global__ void heads_fwd_kernel(const float* __restrict__ feat, const float* __
   }
 }
 
+// actor step in one launch: both heads, log-softmax, and either the mode (uniform == nullptr) or an inverse-CDF draw
+// from the caller's uniform [0,1) numbers: action = first index whose cumulative probability exceeds u.
+// One warp per frame; lane 0 finishes the (tiny) per-action arithmetic.
+__global__ void heads_act_kernel(const float* __restrict__ feat, const float* __restrict__ w_act,
+                                 const float* __restrict__ b_act, const float* __restrict__ w_val,
+                                 const float* __restrict__ b_val, const float* __restrict__ uniform, int B, int H, int A,
+                                 float* __restrict__ logp, float* __restrict__ values, long long* __restrict__ actions,
+                                 float* __restrict__ action_logp) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= B) return;
+  float* lp = logp + (size_t)f * A;
+  float mx = -INFINITY;
+  // 8 output rows (actions, then the value head) per pass: 8 independent load streams per lane instead of one
+  // dependent dot product after the other (this kernel is pure latency: 64 frames x 5 rows x 2 KB)
+  for (int a0 = 0; a0 <= A; a0 += 8) {
+    const float* w[8];
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int a = a0 + j;
+      w[j] = (a < A) ? w_act + (size_t)a * H : w_val;   // rows past the value head re-read it (discarded)
+      acc[j] = 0.f;
+    }
+#pragma unroll 4
+    for (int k = lane; k < H; k += 32) {
+      const float x = feat[(size_t)f * H + k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, w[j][k], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = warp_sum(acc[j]);
+      const int a = a0 + j;
+      if (lane == 0 && a <= A) {
+        if (a < A) {
+          const float l = v + b_act[a];
+          lp[a] = l;
+          mx = fmaxf(mx, l);
+        } else {
+          values[f] = v + b_val[0];
+        }
+      }
+    }
+  }
+  if (lane != 0) return;
+  float se = 0.f;
+  for (int a = 0; a < A; ++a) se += __expf(lp[a] - mx);
+  const float lse = mx + __logf(se);
+  int pick = 0;
+  if (uniform) {
+    const float u = uniform[f];
+    float cum = 0.f;
+    pick = -1;
+    int last = 0;
+    for (int a = 0; a < A; ++a) {
+      const float l = lp[a] - lse;
+      lp[a] = l;
+      const float p = __expf(l);
+      if (p > 0.f) last = a;
+      cum += p;
+      if (pick < 0 && u < cum) pick = a;
+    }
+    if (pick < 0) pick = last;   // u beyond the rounded total: the last action with non-zero probability
+  } else {
+    float best = -INFINITY;
+    for (int a = 0; a < A; ++a) {
+      const float l = lp[a] - lse;
+      lp[a] = l;
+      if (l > best) { best = l; pick = a; }   // first maximum, like argmax
+    }
+  }
+  actions[f] = pick;
+  action_logp[f] = lp[pick];
+}
+
 // block = (frame, slab of ppb pixels); 256 threads = (C/8 vectors) x (pixel lanes)
 static int gn_slab_launch(int C, int hw, int B, int* ppb, int* grid) {
   const int cv = C / 8;
@@ -1848,6 +1924,21 @@ extern "C" int hb200_heads_fwd(const float* features, const float* w_act, const 
   HB_CHECK_ARG(features && w_act && b_act && w_val && b_val && logits && values && batch > 0, "heads_fwd: bad args");
   heads_fwd_kernel<<<cdiv(batch, 8), 256, 0, (cudaStream_t)stream>>>(features, w_act, b_act, w_val, b_val, batch,
                                                                       hidden, n_actions, logits, values);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+extern "C" int hb200_heads_act(const float* features, const float* w_act, const float* b_act, const float* w_val,
+                               const float* b_val, const float* uniform, int batch, int hidden, int n_actions,
+                               float* log_probs, float* values, long long* actions, float* action_log_probs,
+                               hb200_stream_t stream) {
+  HB_CHECK_ARG(features && w_act && b_act && w_val && b_val && log_probs && values && actions && action_log_probs &&
+                   batch > 0 && n_actions > 0,
+               "heads_act: bad args");
+  heads_act_kernel<<<cdiv(batch, 8), 256, 0, (cudaStream_t)stream>>>(features, w_act, b_act, w_val, b_val, uniform, batch,
+                                                                      hidden, n_actions, log_probs, values, actions,
+                                                                      action_log_probs);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;

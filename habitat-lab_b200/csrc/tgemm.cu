@@ -16,6 +16,8 @@
 // Weight gradients (K = frames, tiny M x N tile grid) are split over K with fp32 atomics.
 #include "common.cuh"
 #include <stdlib.h>
+#include <map>
+#include <mutex>
 #include "umma.cuh"
 
 namespace hb200 {
@@ -44,6 +46,10 @@ struct TgemmArgs {
   float* c; long long ldc;
   const float* bias;
   int M, N, K, k_per_split, accumulate, relu;
+  // deterministic split-K for skinny problems (the actor's 64-row batches): every split stores its partial tile to
+  // ws[split][M][N]; the last CTA of a tile to arrive (ticket counter) sums the splits in order and runs the epilogue
+  float* ws;
+  int* tickets;
 };
 
 // load one [ROWS x 32] operand tile (rows = m or n, zero-filled out of range)
@@ -78,10 +84,11 @@ __device__ __forceinline__ void tg_load(const float* __restrict__ p, long long s
   }
 }
 
-template <int BN, int A_MN, int B_MN>
+// NST = cp.async ring depth: 3 for the learner's many-CTA launches, deeper for the skinny (few CTAs, latency-bound) path
+template <int BN, int A_MN, int B_MN, int NST = GT_STAGES>
 __global__ void __launch_bounds__(128) tgemm_kernel(const TgemmArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mma_bar[GT_STAGES];
+  __shared__ __align__(8) uint64_t mma_bar[NST];
   __shared__ uint32_t tmem_slot;
   constexpr uint32_t kABytes = GT_M * GT_K * 4, kBBytes = BN * GT_K * 4, kStage = kABytes + kBBytes;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
@@ -95,7 +102,7 @@ __global__ void __launch_bounds__(128) tgemm_kernel(const TgemmArgs a) {
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < GT_STAGES; ++s) mbar_init(&mma_bar[s], 1);
+    for (int s = 0; s < NST; ++s) mbar_init(&mma_bar[s], 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
@@ -112,13 +119,13 @@ __global__ void __launch_bounds__(128) tgemm_kernel(const TgemmArgs a) {
     tg_load<B_MN>(a.b, a.b_ns, a.b_ks, n0, a.N, k0, k_end, sb, BN);
   };
 #pragma unroll
-  for (int c = 0; c < GT_STAGES - 1; ++c) {
+  for (int c = 0; c < NST - 1; ++c) {
     if (c < nchunks) load_chunk(c, c);
     cp_async_commit();
   }
   for (int c = 0; c < nchunks; ++c) {
-    const int st = c % GT_STAGES;
-    cp_async_wait<GT_STAGES - 2>();
+    const int st = c % NST;
+    cp_async_wait<NST - 2>();
     fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -136,18 +143,68 @@ __global__ void __launch_bounds__(128) tgemm_kernel(const TgemmArgs a) {
       }
       mma_commit(&mma_bar[st]);
     }
-    const int nc = c + GT_STAGES - 1;
+    const int nc = c + NST - 1;
     if (nc < nchunks) {
-      if (c >= 1) mbar_wait(&mma_bar[(c - 1) % GT_STAGES], ((c - 1) / GT_STAGES) & 1);
-      load_chunk(nc, nc % GT_STAGES);
+      if (c >= 1) mbar_wait(&mma_bar[(c - 1) % NST], ((c - 1) / NST) & 1);
+      load_chunk(nc, nc % NST);
     }
     cp_async_commit();
   }
-  mbar_wait(&mma_bar[(nchunks - 1) % GT_STAGES], ((nchunks - 1) / GT_STAGES) & 1);
+  mbar_wait(&mma_bar[(nchunks - 1) % NST], ((nchunks - 1) / NST) & 1);
   fence_after_sync();
 
   const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
   const int m = m0 + tid;
+  if (a.ws) {
+    __shared__ int s_last;
+    float* wrow = a.ws + ((size_t)blockIdx.z * a.M + m) * a.N + n0;
+#pragma unroll 1
+    for (int col0 = 0; col0 < BN; col0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + col0, r);
+      tmem_ld_wait();
+      if (m < a.M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (n0 + col0 + j < a.N)   // N % 4 == 0
+            __stcg(reinterpret_cast<float4*>(wrow + col0 + j),
+                   make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                               __uint_as_float(r[j + 3])));
+        }
+      }
+    }
+    fence_before_sync();
+    __threadfence();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+    if (tid == 0) s_last = (atomicAdd(&a.tickets[tile], 1) == (int)gridDim.z - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int rows = min(GT_M, a.M - m0), cols4 = min(BN, a.N - n0) >> 2;
+    for (int i = tid; i < rows * cols4; i += 128) {
+      const int r = i / cols4, c = (i - r * cols4) << 2;
+      const size_t off = (size_t)(m0 + r) * a.N + n0 + c;
+      float4 acc = __ldcg(reinterpret_cast<const float4*>(a.ws + off));
+#pragma unroll 8
+      for (int z = 1; z < (int)gridDim.z; ++z) {
+        const float4 p = __ldcg(reinterpret_cast<const float4*>(a.ws + (size_t)z * a.M * a.N + off));
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+      }
+      float v[4] = {acc.x, acc.y, acc.z, acc.w};
+      float* dst = a.c + (long long)(m0 + r) * a.ldc + n0 + c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (a.bias) v[j] += a.bias[n0 + c + j];
+        if (a.accumulate) v[j] += dst[j];
+        if (a.relu) v[j] = fmaxf(v[j], 0.f);
+        dst[j] = v[j];
+      }
+    }
+    if (tid == 0) a.tickets[tile] = 0;   // ready for the next launch on this stream
+    return;
+  }
 #pragma unroll 1
   for (int col0 = 0; col0 < BN; col0 += 32) {
     uint32_t r[32];
@@ -180,6 +237,46 @@ __global__ void __launch_bounds__(128) tgemm_kernel(const TgemmArgs a) {
 
 using namespace hb200;
 
+// workspace of the skinny split-K path: one per stream (launches on a stream are ordered; two streams never share one),
+// and one per CUDA-graph capture (keyed by the capture id: the graph keeps using its buffers after the capturing stream
+// has gone back to the pool).  Under capture the allocation runs in relaxed capture mode -- cudaMalloc is not a stream
+// operation -- and the ticket memset becomes the graph's first node (tickets are zero between launches anyway).
+static int skinny_workspace(cudaStream_t st, size_t floats, int tiles, float** ws, int** tickets) {
+  struct Ws { float* buf = nullptr; size_t cap = 0; int* tickets = nullptr; };
+  static std::mutex mu;
+  static std::map<unsigned long long, Ws> table;
+  constexpr int kTickets = 1024;
+  HB_CHECK_ARG(tiles <= kTickets, "tgemm: %d tiles exceed the ticket table", tiles);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  unsigned long long cap_id = 0;
+  HB_CUDA(cudaStreamGetCaptureInfo(st, &cs, &cap_id));
+  const bool capturing = cs == cudaStreamCaptureStatusActive;
+  const unsigned long long key = capturing ? ((1ull << 63) | cap_id) : (unsigned long long)(uintptr_t)st;
+  std::lock_guard<std::mutex> lock(mu);
+  Ws& w = table[key];
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  if (capturing) HB_CUDA(cudaThreadExchangeStreamCaptureMode(&mode));
+  cudaError_t e = cudaSuccess;
+  if (!w.tickets) {
+    e = cudaMalloc(&w.tickets, kTickets * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(w.tickets, 0, kTickets * sizeof(int), st);
+  }
+  if (e == cudaSuccess && w.cap < floats) {
+    if (w.buf && !capturing) {   // earlier launches of a capture keep their pointer: never freed there
+      e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) e = cudaFree(w.buf);
+    }
+    w.buf = nullptr; w.cap = 0;
+    const size_t cap = floats < (size_t)(4 << 20) ? (size_t)(4 << 20) : floats;
+    if (e == cudaSuccess) e = cudaMalloc(&w.buf, cap * sizeof(float));
+    if (e == cudaSuccess) w.cap = cap;
+  }
+  if (capturing) cudaThreadExchangeStreamCaptureMode(&mode);
+  HB_CUDA(e);
+  *ws = w.buf; *tickets = w.tickets;
+  return HB200_OK;
+}
+
 extern "C" int hb200_tgemm(const float* a, long long a_ms, long long a_ks, const float* b, long long b_ks,
                            long long b_ns, float* c, long long ldc, const float* bias, int m, int n, int k,
                            int accumulate, int relu, hb200_stream_t stream) {
@@ -208,6 +305,36 @@ extern "C" int hb200_tgemm(const float* a, long long a_ms, long long a_ks, const
   TgemmArgs g;
   g.a = a; g.a_ms = a_ms; g.a_ks = a_ks; g.b = b; g.b_ks = b_ks; g.b_ns = b_ns; g.c = c; g.ldc = ldc; g.bias = bias;
   g.M = m; g.N = n; g.K = k; g.accumulate = accumulate; g.relu = relu;
+  g.ws = nullptr; g.tickets = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m <= GT_M && k >= 256 && cdiv(n, BN) < kNumSMs / 2 && !a_mn && !b_mn) {
+    // one row tile (the actor: 64 frames): a handful of CTAs would each walk the whole K, one DRAM latency per
+    // 32-wide chunk (77 us for visual_fc at K = 2048).  32-wide N tiles x K splits of >= 4 chunks put one CTA on every SM,
+    // each with a deep cp.async ring; partial tiles meet in an L2-resident workspace and the last CTA of each tile
+    // reduces them in split order (8 KB per split).
+    BN = 32;
+    constexpr int kDeep = 6;   // 6 x (16 KB + 4 KB) stages
+    const int nt = cdiv(n, BN);
+    int sp = kNumSMs / nt;
+    if (sp > k / 128) sp = k / 128;
+    if (sp > 32) sp = 32;
+    if (sp < 1) sp = 1;
+    const int kps = ((cdiv(k, sp) + GT_K - 1) / GT_K) * GT_K;
+    sp = cdiv(k, kps);
+    if (sp > 1) {
+      int rc = skinny_workspace(st, (size_t)sp * m * n, nt, &g.ws, &g.tickets);
+      if (rc) return rc;
+    }
+    g.k_per_split = kps;
+    dim3 grid(nt, 1, sp);
+    const size_t smem = (size_t)kDeep * (GT_M * GT_K * 4 + 32 * GT_K * 4) + 1024;
+    auto kern = tgemm_kernel<32, 0, 0, kDeep>;
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 128, smem, st>>>(g);
+    HB_LAUNCH_OK();
+    count_launch(1);
+    return HB200_OK;
+  }
   const long long tiles = (long long)cdiv(n, BN) * cdiv(m, GT_M);
   int splits = 1;
   if (accumulate && !relu && tiles < kNumSMs && k >= 1024) {
@@ -218,7 +345,6 @@ extern "C" int hb200_tgemm(const float* a, long long a_ms, long long a_ks, const
   g.k_per_split = ((cdiv(k, splits) + GT_K - 1) / GT_K) * GT_K;
   splits = cdiv(k, g.k_per_split);
   dim3 grid(cdiv(n, BN), cdiv(m, GT_M), splits);
-  cudaStream_t st = (cudaStream_t)stream;
 #define HB_TG(bn, AM, BM)                                                                          \
   {                                                                                                \
     const size_t smem = (size_t)GT_STAGES * (GT_M * GT_K * 4 + bn * GT_K * 4) + 1024;              \

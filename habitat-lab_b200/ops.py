@@ -379,6 +379,15 @@ def heads_fwd(features, w_act, b_act, w_val, b_val, logits, values):
          ptr(logits), ptr(values))
 
 
+def heads_act(features, w_act, b_act, w_val, b_val, uniform, log_probs, values, actions, action_log_probs):
+    """uniform: f32 [B] in [0,1) for a draw, or None for the mode."""
+    B, H = features.shape
+    assert actions.dtype == torch.int64
+    call("hb200_heads_act", ptr(features), ptr(w_act), ptr(b_act), ptr(w_val), ptr(b_val),
+         ptr(uniform), B, H, w_act.shape[0], ptr(log_probs), ptr(values), ptr(actions),
+         ptr(action_log_probs))
+
+
 def embed_fwd(goal, prev_actions, masks, frame_rows, w_tgt, b_tgt, emb, out, col0):
     call("hb200_embed_fwd", ptr(goal), ptr(prev_actions), ptr(as_u8(masks)), ptr(frame_rows), ptr(w_tgt),
          ptr(b_tgt), ptr(emb), ptr(out), out.stride(0), col0, frame_rows.numel())

@@ -895,16 +895,21 @@ class NativeNetPolicy(nn.Module):
 
     @torch.no_grad()
     def act(self, observations, rnn_hidden_states, prev_actions, masks, deterministic=False):
+        """Policy.act (rl/ppo/policy.py:300-359).  The heads, the log-softmax, the draw (inverse CDF at one torch.rand number
+        per frame -- same distribution as Categorical.sample, not the same random stream) or the mode, and
+        log_probs(action) are ONE kernel (ops.heads_act)."""
         s = self._trunk(observations, rnn_hidden_states, prev_actions, masks, train=False)
         B = s["B"]
-        logits, values = self._heads(s["features"], B, s["features"].device)
-        logp = torch.log_softmax(logits, dim=-1)
-        if deterministic:
-            action = logp.argmax(dim=-1, keepdim=True)
-        else:  # sampling is not bit-reproducible across implementations (torch.multinomial, Philox)
-            action = torch.multinomial(logp.exp(), 1)
-        return PolicyActionData(values=values.view(B, 1).clone(), actions=action,
-                                action_log_probs=logp.gather(1, action), rnn_hidden_states=s["hidden_out"])
+        feats = s["features"]
+        dev = feats.device
+        logp = self._tmp("logits", (B, self.dim_actions), dev)
+        action = torch.empty(B, 1, dtype=torch.int64, device=dev)
+        alp = torch.empty(B, 1, dtype=torch.float32, device=dev)
+        vout = torch.empty(B, 1, dtype=torch.float32, device=dev)
+        u = None if deterministic else torch.rand(B, device=dev, dtype=torch.float32)
+        ad, cr = self.action_distribution.linear, self.critic.fc
+        ops.heads_act(feats, ad.weight, ad.bias, cr.weight, cr.bias, u, logp, vout, action, alp)
+        return PolicyActionData(values=vout, actions=action, action_log_probs=alp, rnn_hidden_states=s["hidden_out"])
 
     @torch.no_grad()
     def get_value(self, observations, rnn_hidden_states, prev_actions, masks):

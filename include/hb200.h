@@ -395,6 +395,15 @@ int hb200_f32_chw_to_bf16_hwc(const float* x, hb200_bf16* out, int batch, int hw
 int hb200_heads_fwd(const float* features, const float* w_act, const float* b_act, const float* w_val,
                     const float* b_val, int batch, int hidden, int n_actions, float* logits,
                     float* values, hb200_stream_t stream);
+/* the whole tail of Policy.act (HB/rl/ppo/policy.py:300-359: action_distribution(features), critic(features),
+ * distribution.sample() / .mode(), distribution.log_probs(action)) in one launch.  log_probs f32 [B,A] = normalised
+ * logits (what CustomFixedCategorical holds); actions i64 [B]; action_log_probs f32 [B].  uniform f32 [B] in [0,1): the
+ * draw is the inverse CDF at uniform[b] (same distribution as torch.multinomial, different random stream);
+ * uniform == NULL takes the mode (deterministic=True). */
+int hb200_heads_act(const float* features, const float* w_act, const float* b_act, const float* w_val,
+                    const float* b_val, const float* uniform, int batch, int hidden, int n_actions,
+                    float* log_probs, float* values, long long* actions, float* action_log_probs,
+                    hb200_stream_t stream);
 
 /* ---- goal / previous-action embeddings --------------------------------------------------------
  * replaces tgt_embeding + prev_action_embedding + torch.cat of PointNavResNetNet.forward

@@ -303,6 +303,11 @@ CONV_CASES = [
     (2, 128, 128, 1, 8, 32, 8, 4, 0),     # SimpleCNN conv 1 (depth only), simple_cnn.py:84-96
     (2, 31, 31, 32, 32, 64, 4, 2, 0),     # SimpleCNN conv 2 (odd input, last row/col unused)
     (2, 14, 14, 64, 64, 32, 3, 1, 0),     # SimpleCNN conv 3 (no padding)
+    # the cases above have < 148 row tiles: the gather kernel slices the packed N tile (32-wide CTAs, the actor's
+    # launch shape); these two keep the full-width tiles of the learner's 4096-frame minibatches covered
+    (1200, 4, 4, 256, 256, 256, 3, 1, 1),
+    (300, 8, 8, 64, 64, 128, 3, 2, 1),
+    (64, 4, 4, 256, 256, 256, 3, 1, 1),   # the actor's layer4 launch: 8 row tiles x 8 slices of 32 channels
 ]
 
 
@@ -701,7 +706,9 @@ def test_sgemm_linear(hb, M, N, K):
     torch.testing.assert_close(db, dy.sum(0), rtol=1e-4, atol=1e-3)
 
 
-@pytest.mark.parametrize("M,N,K", [(4096, 512, 2048), (4096, 2048, 576), (128, 64, 64), (260, 36, 100)])
+@pytest.mark.parametrize("M,N,K", [(4096, 512, 2048), (4096, 2048, 576), (128, 64, 64), (260, 36, 100),
+                                   # one row tile (the actor's batches): deterministic split-K through the workspace
+                                   (64, 512, 2048), (64, 2048, 576), (64, 2048, 512), (3, 36, 260), (128, 512, 4096)])
 def test_tgemm_tf32(hb, M, N, K):
     """tcgen05 kind::tf32 dense layers: forward (K-major x K-major), data gradient (K-major x N-major) and
     split-K weight gradient (M-major x N-major) vs fp64; tolerance = TF32 operand rounding (2^-11 relative)."""
@@ -855,6 +862,83 @@ def test_gru_masked_recurrence(hb, T, n, H, D):
     torch.testing.assert_close(dw_hh.cpu(), sdr["rnn.weight_hh_l0"].grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(db_ih.cpu(), sdr["rnn.bias_ih_l0"].grad, rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(db_hh.cpu(), sdr["rnn.bias_hh_l0"].grad, rtol=1e-3, atol=1e-3)
+
+
+def test_tgemm_skinny_split_k_is_deterministic_and_accumulates(hb):
+    """The one-row-tile path reduces its K splits in split order (no atomics): repeated launches are bit-identical, and
+    accumulate / ReLU / bias run once, in the reducing CTA."""
+    from habitat_lab_b200 import ops
+
+    torch.manual_seed(3)
+    M, N, K = 64, 512, 2048
+    x = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / math.sqrt(K)
+    b = torch.randn(N, device=DEV)
+    outs = []
+    for _ in range(3):
+        o = torch.full((M, N), 7.0, device=DEV)
+        ops.linear_fwd(x, w, b, o, relu=True, tf32=True)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    ref = F.relu(F.linear(x.double(), w.double(), b.double())).float()
+    torch.testing.assert_close(outs[0], ref, rtol=2e-3, atol=4e-3)
+    # on a side stream (its own workspace), interleaved with the main stream
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    o_main = torch.empty(M, N, device=DEV)
+    o_side = torch.empty(M, N, device=DEV)
+    for _ in range(4):
+        ops.linear_fwd(x, w, b, o_main, relu=False, tf32=True)
+        with torch.cuda.stream(side):
+            ops.linear_fwd(x, w, None, o_side, relu=False, tf32=True)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(o_main - b, o_side, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,H,A", [(64, 512, 4), (7, 32, 6), (300, 128, 2)])
+def test_heads_act(hb, B, H, A):
+    """Fused tail of Policy.act: heads + log-softmax + draw / mode + log_probs(action) vs torch."""
+    from habitat_lab_b200 import ops
+
+    torch.manual_seed(B + A)
+    feat = torch.randn(B, H, device=DEV)
+    wa = torch.randn(A, H, device=DEV) * 0.2
+    ba = torch.randn(A, device=DEV)
+    wv = torch.randn(1, H, device=DEV) * 0.1
+    bv = torch.randn(1, device=DEV)
+    ref_lp = torch.log_softmax(F.linear(feat.double(), wa.double(), ba.double()), -1)
+    ref_v = F.linear(feat.double(), wv.double(), bv.double())
+    for u in (None, torch.rand(B, device=DEV), torch.zeros(B, device=DEV), torch.full((B,), 1.0 - 2 ** -24, device=DEV)):
+        lp = torch.empty(B, A, device=DEV)
+        val = torch.empty(B, 1, device=DEV)
+        act = torch.full((B, 1), -1, device=DEV, dtype=torch.int64)
+        alp = torch.empty(B, 1, device=DEV)
+        ops.heads_act(feat, wa, ba, wv, bv, u, lp, val, act, alp)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(lp.double(), ref_lp, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(val.double(), ref_v, rtol=1e-4, atol=1e-4)
+        assert int(act.min()) >= 0 and int(act.max()) < A
+        torch.testing.assert_close(alp, lp.gather(1, act), rtol=0, atol=0)
+        if u is None:
+            assert torch.equal(act.view(-1), lp.argmax(-1))
+        else:
+            # inverse CDF: the first action whose cumulative probability exceeds u (boundaries: within fp32 rounding)
+            cdf = ref_lp.exp().cumsum(-1)
+            lo = (cdf < (u.double().view(-1, 1) - 1e-5)).sum(-1).clamp(max=A - 1)
+            hi = (cdf < (u.double().view(-1, 1) + 1e-5)).sum(-1).clamp(max=A - 1)
+            a = act.view(-1)
+            assert bool(((a >= lo) & (a <= hi)).all())
+    # the draw follows the distribution: 20000 uniform numbers against one frame's probabilities
+    n = 20000
+    f1 = feat[:1].expand(n, H).contiguous()
+    lp = torch.empty(n, A, device=DEV)
+    val = torch.empty(n, 1, device=DEV)
+    act = torch.empty(n, 1, device=DEV, dtype=torch.int64)
+    alp = torch.empty(n, 1, device=DEV)
+    ops.heads_act(f1, wa, ba, wv, bv, torch.rand(n, device=DEV), lp, val, act, alp)
+    freq = torch.bincount(act.view(-1), minlength=A).double() / n
+    assert (freq - ref_lp[0].exp()).abs().max().item() < 0.02
 
 
 def test_embeddings(hb):

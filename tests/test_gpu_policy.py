@@ -409,6 +409,36 @@ def test_graphed_actor_replays_act(hb):
     torch.testing.assert_close(got.values, ref.values, rtol=0, atol=0)
 
 
+def test_graphed_actor_samples_actions(hb):
+    """Sampling mode under graph replay: fresh random numbers every replay (torch.rand is captured with its graph-safe
+    Philox offset), actions in range, log-probs consistent with the distribution act() holds."""
+    from habitat_lab_b200.synthetic import fill_rollout_, pointnav_spaces
+
+    T, N = 2, 64
+    torch.manual_seed(6)
+    obs_space, act_space = pointnav_spaces(64, 64)
+    pol = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=512, num_recurrent_layers=2, rnn_type="LSTM",
+                                  normalize_visual_inputs=True).to(DEV)
+    st = hb.RolloutStorage(T, N, obs_space, act_space, pol)
+    st.to(DEV)
+    fill_rollout_(st, seed=3, p_done=0.2)
+    ob = st.buffers["observations"]
+    step = ({k: v[0] for k, v in ob.items()}, st.buffers["recurrent_hidden_states"][0], st.buffers["prev_actions"][0],
+            st.buffers["masks"][0])
+    greedy = pol.act(*step, deterministic=True)
+    ga = hb.GraphedActor(pol, *step, deterministic=False)
+    draws = []
+    for _ in range(8):
+        out = ga(*step)
+        torch.cuda.synchronize()
+        assert int(out.actions.min()) >= 0 and int(out.actions.max()) < 4
+        assert bool((out.action_log_probs <= 0).all())
+        torch.testing.assert_close(out.values, greedy.values, rtol=0, atol=0)
+        assert bool((out.action_log_probs <= greedy.action_log_probs + 1e-6).all())   # the mode has the largest log-prob
+        draws.append(out.actions.clone())
+    assert any(not torch.equal(draws[0], d) for d in draws[1:]), "graph replays repeated the same random numbers"
+
+
 def test_resnet_policy_with_gru_vs_oracle(hb):
     """PointNavResNetPolicy with rnn_type GRU (the reference default, resnet_policy.py:58): ResNet18 encoder + persistent
     GRU kernels, minibatch losses and the GRU gradients against the CPU oracle on the same weights and rollout."""

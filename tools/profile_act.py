@@ -35,3 +35,14 @@ e1.record()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
 print(f"act() at batch {N}: {e0.elapsed_time(e1):.3f} ms device")
+# CUDA-graph replay of the same step (what the trainer's rollout loop runs)
+ga = hb.GraphedActor(policy, *step(0))
+for _ in range(5):
+    ga(*step(1))
+torch.cuda.synchronize()
+e0.record()
+for _ in range(50):
+    ga.graph.replay()
+e1.record()
+torch.cuda.synchronize()
+print(f"graph replay at batch {N}: {e0.elapsed_time(e1) / 50:.3f} ms device per step")
