@@ -51,6 +51,8 @@ SIGNATURES = {
     "hb200_get_umma_layout": ("i", ""),
     "hb200_set_halo_tma": ("i", "i"),
     "hb200_get_halo_tma": ("i", ""),
+    "hb200_set_tgemm_tma": ("i", "i"),
+    "hb200_get_tgemm_tma": ("i", ""),
     "hb200_conv_halo_supported": ("i", "iiiii"),
     "hb200_conv_halo_wgrad_supported": ("i", "iiiii"),
     "hb200_pack_halo_weight": ("i", "pp" + "iiiiii" + "p"),

@@ -163,6 +163,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap,
       : "memory");
 }
 
+// 2-D box load (row-major matrices: c0 = column / k index, c1 = row)
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // ---- cp.async (LDGSTS), 16 B with zero fill ---------------------------------------------
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {
   const uint32_t sz = valid ? 16u : 0u;

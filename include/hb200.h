@@ -318,6 +318,10 @@ int hb200_sgemm(const float* a, long long a_ms, long long a_ks, const float* b, 
 int hb200_tgemm(const float* a, long long a_ms, long long a_ks, const float* b, long long b_ks, long long b_ns,
                 float* c, long long ldc, const float* bias, int m, int n, int k, int accumulate, int relu,
                 hb200_stream_t stream);
+/* operand feed of hb200_tgemm: 1 (default) = TMA box loads, 0 = the 16-byte cp.async gather (kept for A/B tests;
+ * environment HB200_NO_TGEMM_TMA=1 selects it at load time) */
+int hb200_set_tgemm_tma(int on);
+int hb200_get_tgemm_tma(void);
 /* dst[c,r] = src[r,c] (fp32): feeds hb200_tgemm K-major operands for the data / weight gradient GEMMs */
 int hb200_transpose_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int rows, int cols,
                         hb200_stream_t stream);

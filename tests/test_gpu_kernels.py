@@ -706,10 +706,20 @@ def test_sgemm_linear(hb, M, N, K):
     torch.testing.assert_close(db, dy.sum(0), rtol=1e-4, atol=1e-3)
 
 
+@pytest.fixture(params=[1, 0], ids=["tma", "cp_async"])
+def tgemm_feed(hb, request):
+    """both operand feeds of hb200_tgemm: TMA box loads (default) and the 16-byte cp.async gather"""
+    lib = hb.load()
+    prev = lib.hb200_get_tgemm_tma()
+    lib.hb200_set_tgemm_tma(request.param)
+    yield request.param
+    lib.hb200_set_tgemm_tma(prev)
+
+
 @pytest.mark.parametrize("M,N,K", [(4096, 512, 2048), (4096, 2048, 576), (128, 64, 64), (260, 36, 100),
                                    # one row tile (the actor's batches): deterministic split-K through the workspace
                                    (64, 512, 2048), (64, 2048, 576), (64, 2048, 512), (3, 36, 260), (128, 512, 4096)])
-def test_tgemm_tf32(hb, M, N, K):
+def test_tgemm_tf32(hb, tgemm_feed, M, N, K):
     """tcgen05 kind::tf32 dense layers: forward (K-major x K-major), data gradient (K-major x N-major) and
     split-K weight gradient (M-major x N-major) vs fp64; tolerance = TF32 operand rounding (2^-11 relative)."""
     from habitat_lab_b200 import ops
@@ -864,7 +874,7 @@ def test_gru_masked_recurrence(hb, T, n, H, D):
     torch.testing.assert_close(db_hh.cpu(), sdr["rnn.bias_hh_l0"].grad, rtol=1e-3, atol=1e-3)
 
 
-def test_tgemm_skinny_split_k_is_deterministic_and_accumulates(hb):
+def test_tgemm_skinny_split_k_is_deterministic_and_accumulates(hb, tgemm_feed):
     """The one-row-tile path reduces its K splits in split order (no atomics): repeated launches are bit-identical, and
     accumulate / ReLU / bias run once, in the reducing CTA."""
     from habitat_lab_b200 import ops
