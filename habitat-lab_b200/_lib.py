@@ -80,6 +80,7 @@ SIGNATURES = {
     "hb200_lstm_step_bwd": ("i", "ppppppl" + "ppppp" + "ii" + "p"),
     "hb200_lstm_seq_fwd": ("i", "ppppplplppp" + "iii" + "pp"),
     "hb200_lstm_seq_bwd": ("i", "pppplppp" + "iii" + "pp"),
+    "hb200_lstm_seq_bwd_chunk": ("i", "pppplppp" + "iii" + "pp" + "ii" + "p"),
     "hb200_gru_seq_fwd": ("i", "ppppplpp" + "iii" + "pp"),
     "hb200_gru_seq_bwd": ("i", "pppplpppp" + "iii" + "pp"),
     "hb200_rnn_shift_mask": ("i", "pplpp" + "iii" + "p"),

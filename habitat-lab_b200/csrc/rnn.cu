@@ -574,7 +574,10 @@ __global__ void __launch_bounds__(kV2Threads)
 lstm_seq_bwd_v2_kernel(const float* __restrict__ dh_out, const float* __restrict__ gates,
                        const float* __restrict__ cs, const float* __restrict__ c0, long long c0_stride,
                        const float* __restrict__ w_hh, const uint8_t* __restrict__ masks,
-                       float* __restrict__ dgates, int T, int n, unsigned* counter) {
+                       float* __restrict__ dgates, int T, int n, unsigned* counter, float* __restrict__ carry,
+                       int carry_in, int carry_out) {
+  // carry [2][n][H] (dh, dc of the step before this launch's first one): lets a sequence be processed as several
+  // launches over time chunks (last chunk first), so that two layers can run as a wavefront on two streams
   extern __shared__ __align__(16) float sm2[];
   constexpr int R = 4 * H;
   float* wt = sm2;                 // [4][R]  W_hh^T columns of this CTA's 4 units
@@ -587,7 +590,11 @@ lstm_seq_bwd_v2_kernel(const float* __restrict__ dh_out, const float* __restrict
     const int u = i / R, r = i - u * R;
     wt[i] = w_hh[(size_t)r * H + u0 + u];
   }
-  for (int i = tid; i < 4 * n; i += kV2Threads) { dh_rec[i] = 0.f; dc_rec[i] = 0.f; }
+  for (int i = tid; i < 4 * n; i += kV2Threads) {
+    const size_t o = (size_t)(i >> 2) * H + u0 + (i & 3);
+    dh_rec[i] = carry_in ? carry[o] : 0.f;
+    dc_rec[i] = carry_in ? carry[(size_t)n * H + o] : 0.f;
+  }
   __syncthreads();
   const int sg = warp & 3, rh = warp >> 2;  // 8-sequence group, half of the 4H gate rows
   for (int t = T - 1; t >= 0; --t) {
@@ -612,7 +619,7 @@ lstm_seq_bwd_v2_kernel(const float* __restrict__ dh_out, const float* __restrict
       dg[3 * H + col] = dh * tc * o_ * (1.f - o_);
       dc_rec[i] = dc * f_ * m;
     }
-    if (t == 0) break;
+    if (t == 0 && !carry_out) break;
     grid_barrier(counter, (unsigned)(T - t) * gridDim.x);
     asm volatile("" ::: "memory");
     // ---- dh_{t-1}[s, own 4 cols] = m_t[s] * sum_r dgates_t[s, r] * W_hh[r, col]
@@ -653,6 +660,14 @@ lstm_seq_bwd_v2_kernel(const float* __restrict__ dh_out, const float* __restrict
         dh_rec[4 * s + (tid & 3)] = (spart[tid] + spart[128 + tid]) * m;
       }
       __syncthreads();
+    }
+    if (t == 0) {   // carry_out: hand the recurrent gradients to the launch that covers the earlier steps
+      for (int i = tid; i < 4 * n; i += kV2Threads) {
+        const size_t o = (size_t)(i >> 2) * H + u0 + (i & 3);
+        carry[o] = dh_rec[i];
+        carry[(size_t)n * H + o] = dc_rec[i];
+      }
+      break;
     }
   }
 }
@@ -715,9 +730,10 @@ extern "C" int hb200_lstm_seq_fwd(const float* xproj, const float* w_hh, const f
   return HB200_OK;
 }
 
-extern "C" int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const float* cs, const float* c0,
-                                  long long c0_stride, const float* w_hh, const uint8_t* masks, float* dgates,
-                                  int t_steps, int n, int hidden, void* workspace, hb200_stream_t stream) {
+static int lstm_seq_bwd_impl(const float* dh_out, const float* gates, const float* cs, const float* c0,
+                             long long c0_stride, const float* w_hh, const uint8_t* masks, float* dgates,
+                             int t_steps, int n, int hidden, void* workspace, float* carry, int carry_in,
+                             int carry_out, hb200_stream_t stream) {
   HB_CHECK_ARG(dh_out && gates && cs && c0 && w_hh && masks && dgates && workspace && t_steps > 0 && n > 0,
                "lstm_seq_bwd: bad args");
   HB_CHECK_ARG(hidden % kUnits == 0 && hidden % 32 == 0, "lstm_seq_bwd: hidden must be a multiple of 32");
@@ -732,7 +748,8 @@ extern "C" int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const
     const void* k2 = (const void*)lstm_seq_bwd_v2_kernel<512>;
     const size_t smem2 = smem + sizeof(float) * 256;
     void* args2[] = {(void*)&dh_out, (void*)&gates, (void*)&cs, (void*)&c0, (void*)&c0_stride, (void*)&w_hh,
-                     (void*)&masks, (void*)&dgates, (void*)&t_steps, (void*)&n, (void*)&counter};
+                     (void*)&masks, (void*)&dgates, (void*)&t_steps, (void*)&n, (void*)&counter,
+                     (void*)&carry, (void*)&carry_in, (void*)&carry_out};
     if (smem2 > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     int rc2 = coop_check(k2, kV2Threads, smem2, grid);
     if (rc2) return rc2;
@@ -740,6 +757,7 @@ extern "C" int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const
     count_launch(1);
     return HB200_OK;
   }
+  HB_CHECK_ARG(!carry_in && !carry_out, "lstm_seq_bwd: time chunks (carry) need hidden == 512 and 16-byte aligned dgates");
   const void* kern = (const void*)lstm_seq_bwd_kernel;
   if (smem > 48 * 1024) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int rc = coop_check(kern, kSeqThreads, smem, grid);
@@ -749,6 +767,21 @@ extern "C" int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const
   HB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kSeqThreads), args, smem, st));
   count_launch(1);
   return HB200_OK;
+}
+
+extern "C" int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const float* cs, const float* c0,
+                                  long long c0_stride, const float* w_hh, const uint8_t* masks, float* dgates,
+                                  int t_steps, int n, int hidden, void* workspace, hb200_stream_t stream) {
+  return lstm_seq_bwd_impl(dh_out, gates, cs, c0, c0_stride, w_hh, masks, dgates, t_steps, n, hidden, workspace, nullptr,
+                           0, 0, stream);
+}
+extern "C" int hb200_lstm_seq_bwd_chunk(const float* dh_out, const float* gates, const float* cs, const float* c0,
+                                        long long c0_stride, const float* w_hh, const uint8_t* masks, float* dgates,
+                                        int t_steps, int n, int hidden, void* workspace, float* carry, int carry_in,
+                                        int carry_out, hb200_stream_t stream) {
+  HB_CHECK_ARG(carry || (!carry_in && !carry_out), "lstm_seq_bwd_chunk: carry buffer missing");
+  return lstm_seq_bwd_impl(dh_out, gates, cs, c0, c0_stride, w_hh, masks, dgates, t_steps, n, hidden, workspace, carry,
+                           carry_in, carry_out, stream);
 }
 
 // =====================================================================================

@@ -345,6 +345,12 @@ def lstm_seq_bwd(dh_out, gates, cs, c0, w_hh, masks, dgates, T, n, hidden, works
          ptr(dgates), T, n, hidden, ptr(workspace))
 
 
+def lstm_seq_bwd_chunk(dh_out, gates, cs, c0, w_hh, masks, dgates, T, n, hidden, workspace, carry, carry_in, carry_out):
+    """one time chunk of the backward recurrence; carry f32 [2, n, H] links it to its neighbours (see hb200.h)"""
+    call("hb200_lstm_seq_bwd_chunk", ptr(dh_out), ptr(gates), ptr(cs), ptr(c0), c0.stride(0), ptr(w_hh), ptr(masks),
+         ptr(dgates), T, n, hidden, ptr(workspace), ptr(carry), int(bool(carry_in)), int(bool(carry_out)))
+
+
 def gru_seq_fwd(xproj, w_hh, b_hh, masks, h0, hs, saved, T, n, hidden, workspace):
     call("hb200_gru_seq_fwd", ptr(xproj), ptr(w_hh), ptr(b_hh), ptr(masks), ptr(h0), h0.stride(0), ptr(hs), ptr(saved),
          T, n, hidden, ptr(workspace))

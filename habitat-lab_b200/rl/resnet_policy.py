@@ -16,6 +16,7 @@ There is no CPU / PyTorch fallback: tensors must live on a CUDA device.
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional
@@ -805,10 +806,30 @@ class NativeNetPolicy(nn.Module):
         return self._buf[key]
 
     # ---- recurrent state encoder -----------------------------------------------------------------------
+    # ---- two stacked LSTM layers as a wavefront ----------------------------------------------------------------
+    # A layer is T dependent steps of ~6 us (grid barrier + a 32 x 512 x 2048 mat-vec): latency, not throughput, and
+    # the second layer only needs step t of the first.  The sequence is cut into time chunks; layer l runs chunk c on
+    # its own stream as soon as layer l-1 has finished chunk c (forward; backward: top layer first, chunks last to
+    # first), so the two persistent kernels are co-resident (128 CTAs each, two fit per SM) and the critical path is
+    # (chunks + 1) / (2 * chunks) of the sequential one.  Arithmetic and its order are unchanged: bit-identical results.
+    _RNN_CHUNKS = int(os.environ.get("HB200_RNN_CHUNKS", "4"))
+
+    def _rnn_wavefront(self, lstm, H, L, T):
+        return (lstm and H == 512 and L >= 2 and T >= 8 * self._RNN_CHUNKS and T % self._RNN_CHUNKS == 0
+                and not os.environ.get("HB200_NO_RNN_WAVEFRONT"))
+
+    def _rnn_streams(self, L):
+        st = getattr(self, "_rnn_side_streams", None)
+        if st is None or len(st) < L - 1:
+            st = self._rnn_side_streams = [torch.cuda.Stream() for _ in range(L - 1)]
+        return st
+
     def _rnn_forward(self, rnn_in, hid, mk, T, n, B, dev, train):
         rnn = self.net.state_encoder.rnn
         H, L = rnn.hidden_size, rnn.num_layers
         lstm = isinstance(rnn, nn.LSTM)
+        if self._rnn_wavefront(lstm, H, L, T):
+            return self._rnn_forward_wavefront(rnn_in, hid, mk, T, n, B, dev, train)
         ws = self._tmp("rnn_ws", (64,), dev, torch.uint8)
         layers, x = [], rnn_in
         for l in range(L):
@@ -833,15 +854,60 @@ class NativeNetPolicy(nn.Module):
         parts = [ly["hs"][T - 1] for ly in layers] + ([ly["cs"][T - 1] for ly in layers] if lstm else [])
         return x, layers, torch.stack(parts, dim=1)
 
+    def _rnn_forward_wavefront(self, rnn_in, hid, mk, T, n, B, dev, train):
+        rnn = self.net.state_encoder.rnn
+        H, L = rnn.hidden_size, rnn.num_layers
+        C = self._RNN_CHUNKS
+        Tc = T // C
+        main = torch.cuda.current_stream()
+        streams = [main] + self._rnn_streams(L)
+        layers = []
+        # every buffer is allocated (and the first layer's input projection runs for all frames) before the fork
+        for l in range(L):
+            layers.append(dict(
+                x=rnn_in if l == 0 else layers[l - 1]["hs"].view(B, H),
+                xproj=self._tmp(f"xproj{l}", (B, 4 * H), dev), hs=self._tmp(f"hs{l}", (T, n, H), dev),
+                cs=self._tmp(f"cs{l}", (T, n, H), dev),
+                gates=self._tmp(f"gates{l}", (T, n, 4 * H), dev) if train else None,
+                h0=hid[:, l], c0=hid[:, L + l], ws=self._tmp(f"rnn_ws{l}", (64,), dev, torch.uint8)))
+        ops.linear_fwd(rnn_in, rnn.weight_ih_l0, rnn.bias_ih_l0, layers[0]["xproj"], tf32=True)
+        for s_ in streams[1:]:
+            s_.wait_stream(main)
+        done = [[None] * C for _ in range(L)]
+        for c in range(C):
+            t0, t1 = c * Tc, (c + 1) * Tc
+            r0, r1 = t0 * n, t1 * n
+            for l in range(L):
+                ly = layers[l]
+                w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
+                b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
+                with torch.cuda.stream(streams[l]):
+                    if l > 0:
+                        streams[l].wait_event(done[l - 1][c])
+                        ops.linear_fwd(ly["x"][r0:r1], w_ih, b_ih, ly["xproj"][r0:r1], tf32=True)
+                    h0 = ly["h0"] if c == 0 else ly["hs"][t0 - 1]
+                    c0 = ly["c0"] if c == 0 else ly["cs"][t0 - 1]
+                    ops.lstm_seq_fwd(ly["xproj"][r0:r1], w_hh, b_hh, mk[r0:r1], h0, c0, ly["hs"][t0:t1], ly["cs"][t0:t1],
+                                     ly["gates"][t0:t1] if train else None, Tc, n, H, ly["ws"])
+                    if l + 1 < L:
+                        done[l][c] = torch.cuda.Event()
+                        done[l][c].record(streams[l])
+        for s_ in streams[1:]:
+            main.wait_stream(s_)
+        out = [dict(x=ly["x"], hs=ly["hs"], cs=ly["cs"], gates=ly["gates"], h0=ly["h0"], c0=ly["c0"]) for ly in layers]
+        parts = [ly["hs"][T - 1] for ly in out] + [ly["cs"][T - 1] for ly in out]
+        return out[-1]["hs"].view(B, H), out, torch.stack(parts, dim=1)
+
     def _rnn_backward(self, d_out, layers, mk, T, n, B, dev):
         rnn = self.net.state_encoder.rnn
         H, L = rnn.hidden_size, rnn.num_layers
         lstm = isinstance(rnn, nn.LSTM)
+        if self._rnn_wavefront(lstm, H, L, T):
+            return self._rnn_backward_wavefront(d_out, layers, mk, T, n, B, dev)
         ws = self._tmp("rnn_ws", (64,), dev, torch.uint8)
         for l in reversed(range(L)):
             ly = layers[l]
             w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
-            b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
             G = 4 if lstm else 3
             dgx = self._tmp(f"dgates{l}", (T, n, G * H), dev)
             if lstm:
@@ -850,22 +916,79 @@ class NativeNetPolicy(nn.Module):
             else:
                 dgh = self._tmp(f"dgh{l}", (T, n, G * H), dev)
                 ops.gru_seq_bwd(d_out.view(T, n, H), ly["gates"], ly["hs"], ly["h0"], w_hh, mk, dgx, dgh, T, n, H, ws)
-            dgxf, dghf = dgx.view(B, G * H), dgh.view(B, G * H)
+            self._rnn_weight_grads(l, ly, dgx, dgh, mk, T, n, B, dev, lstm)
             x = ly["x"]
-            with self._side.after_main():   # weight gradients: off the critical path (SideStream)
-                ops.linear_bwd_weight(dgxf, x, w_ih.grad, accumulate=True, tf32=True)  # grads pre-zeroed: split-K
-                hin = self._tmp("hin", (T, n, H), dev)
-                ops.rnn_shift_mask(ly["hs"], ly["h0"], mk, hin, T, n, H)
-                ops.linear_bwd_weight(dghf, hin.view(B, H), w_hh.grad, accumulate=True, tf32=True)
-                ops.colsum(dgxf, b_ih.grad)
-                if lstm:
-                    b_hh.grad.copy_(b_ih.grad)
-                else:
-                    ops.colsum(dghf, b_hh.grad)
             dx = self._tmp(f"dx{l}", (B, x.stride(0)), dev)[:, : x.shape[1]]   # same (16-byte) row pitch as x
-            ops.linear_bwd_input(dgxf, w_ih, dx, tf32=True)
+            ops.linear_bwd_input(dgx.view(B, G * H), w_ih, dx, tf32=True)
             d_out = dx
         return d_out
+
+    def _rnn_weight_grads(self, l, ly, dgx, dgh, mk, T, n, B, dev, lstm):
+        rnn = self.net.state_encoder.rnn
+        H = rnn.hidden_size
+        G = 4 if lstm else 3
+        w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
+        b_ih, b_hh = getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}")
+        dgxf, dghf = dgx.view(B, G * H), dgh.view(B, G * H)
+        x = ly["x"]
+        with self._side.after_main():   # weight gradients: off the critical path (SideStream)
+            ops.linear_bwd_weight(dgxf, x, w_ih.grad, accumulate=True, tf32=True)  # grads pre-zeroed: split-K
+            hin = self._tmp(f"hin{l}", (T, n, H), dev)
+            ops.rnn_shift_mask(ly["hs"], ly["h0"], mk, hin, T, n, H)
+            ops.linear_bwd_weight(dghf, hin.view(B, H), w_hh.grad, accumulate=True, tf32=True)
+            ops.colsum(dgxf, b_ih.grad)
+            if lstm:
+                b_hh.grad.copy_(b_ih.grad)
+            else:
+                ops.colsum(dghf, b_hh.grad)
+
+    def _rnn_backward_wavefront(self, d_out, layers, mk, T, n, B, dev):
+        """Mirror of _rnn_forward_wavefront: the top layer walks the time chunks last to first on the main stream and
+        hands each chunk's input gradient (one TF32 GEMM per chunk) to the layer below, which follows one chunk behind on
+        its own stream.  Weight gradients need all T steps of a layer: side stream, after that layer's last chunk."""
+        rnn = self.net.state_encoder.rnn
+        H, L = rnn.hidden_size, rnn.num_layers
+        C = self._RNN_CHUNKS
+        Tc = T // C
+        main = torch.cuda.current_stream()
+        order = list(reversed(range(L)))                 # top layer first
+        streams = {l: s_ for l, s_ in zip(order, [main] + self._rnn_streams(L))}
+        dgx = {l: self._tmp(f"dgates{l}", (T, n, 4 * H), dev) for l in range(L)}
+        carry = {l: self._tmp(f"rnn_carry{l}", (2, n, H), dev) for l in range(L)}
+        wsb = {l: self._tmp(f"rnn_ws{l}", (64,), dev, torch.uint8) for l in range(L)}
+        dxs = {}
+        for l in range(L):
+            x = layers[l]["x"]
+            dxs[l] = self._tmp(f"dx{l}", (B, x.stride(0)), dev)[:, : x.shape[1]]
+        for l in order[1:]:
+            streams[l].wait_stream(main)
+        d_in = {order[0]: d_out}
+        for l in order[1:]:
+            d_in[l] = dxs[l + 1]
+        done = {l: [None] * C for l in range(L)}
+        for c in reversed(range(C)):
+            t0, t1 = c * Tc, (c + 1) * Tc
+            r0, r1 = t0 * n, t1 * n
+            for l in order:
+                ly = layers[l]
+                w_ih, w_hh = getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}")
+                with torch.cuda.stream(streams[l]):
+                    if l != order[0]:
+                        streams[l].wait_event(done[l + 1][c])
+                    c0 = ly["c0"] if c == 0 else ly["cs"][t0 - 1]
+                    ops.lstm_seq_bwd_chunk(d_in[l][r0:r1].view(Tc, n, H), ly["gates"][t0:t1], ly["cs"][t0:t1], c0, w_hh,
+                                           mk[r0:r1], dgx[l][t0:t1], Tc, n, H, wsb[l], carry[l], carry_in=c < C - 1,
+                                           carry_out=c > 0)
+                    if l > 0:   # the layer below consumes this chunk's input gradient
+                        ops.linear_bwd_input(dgx[l][t0:t1].view(Tc * n, 4 * H), w_ih, dxs[l][r0:r1], tf32=True)
+                        done[l][c] = torch.cuda.Event()
+                        done[l][c].record(streams[l])
+        for l in order[1:]:
+            main.wait_stream(streams[l])
+        for l in order:
+            self._rnn_weight_grads(l, layers[l], dgx[l], dgx[l], mk, T, n, B, dev, True)
+        ops.linear_bwd_input(dgx[0].view(B, 4 * H), rnn.weight_ih_l0, dxs[0], tf32=True)
+        return dxs[0]
 
     # ---- shared forward ----------------------------------------------------------------------------------
     def _trunk(self, observations, rnn_hidden_states, prev_actions, masks, train: bool):

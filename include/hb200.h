@@ -372,6 +372,15 @@ int hb200_lstm_seq_fwd(const float* xproj, const float* w_hh, const float* b_hh,
 int hb200_lstm_seq_bwd(const float* dh_out, const float* gates, const float* cs, const float* c0,
                        long long c0_stride, const float* w_hh, const uint8_t* masks, float* dgates,
                        int t_steps, int n, int hidden, void* workspace, hb200_stream_t stream);
+/* The same launch over a time chunk of a longer sequence (chunks are processed last-to-first): carry f32 [2][n][H]
+ * holds (dh, dc) flowing into the step before the chunk's first one -- read when carry_in, written when carry_out.
+ * c0 must then be the cell state of the step before the chunk (cs row of step t0 - 1, stride H).  hidden == 512 only.
+ * With hb200_lstm_seq_fwd called per chunk (h0 / c0 = the previous chunk's last hs / cs rows) two stacked layers run
+ * as a wavefront on two streams; every launch needs its own workspace. */
+int hb200_lstm_seq_bwd_chunk(const float* dh_out, const float* gates, const float* cs, const float* c0,
+                             long long c0_stride, const float* w_hh, const uint8_t* masks, float* dgates,
+                             int t_steps, int n, int hidden, void* workspace, float* carry, int carry_in,
+                             int carry_out, hb200_stream_t stream);
 /* GRU (gate order r,z,n), same persistent cooperative structure.  xproj [T*n,3H] = x W_ih^T + b_ih;
  * saved [T,n,4H] = (r, z, n, W_hn h + b_hn) for backward (NULL in inference).  Backward writes
  * dgx [T,n,3H] = d xproj (-> dW_ih, db_ih, dx) and dgh [T,n,3H] = d(h-side pre-activations) (-> dW_hh, db_hh). */

@@ -376,6 +376,46 @@ def test_full_size_minibatch_is_additive_over_envs(hb):
     assert rel < 2e-3, (rel, worst[:8], worst[-3:])
 
 
+def test_lstm_wavefront_matches_sequential(hb, monkeypatch):
+    """The two LSTM layers run as a wavefront over 4 time chunks on two streams (forward and backward); chunking must
+    not change the arithmetic: forward outputs bit-identical to the one-launch-per-layer path, gradients identical
+    up to the fp32 atomic ordering of the split-K weight-gradient kernels."""
+    from habitat_lab_b200.synthetic import fill_rollout_, pointnav_spaces
+
+    T, N = 32, 32   # 256 frames per chunk: the same (multi-row-tile) GEMM path as the unchunked projections
+    torch.manual_seed(11)
+    obs_space, act_space = pointnav_spaces(64, 64)
+    pol = hb.PointNavResNetPolicy(obs_space, act_space, hidden_size=512, num_recurrent_layers=2, rnn_type="LSTM",
+                                  normalize_visual_inputs=True).to(DEV)
+    pol.eval()
+    ppo = hb.PPO(pol, clip_param=0.2, ppo_epoch=1, num_mini_batch=1, value_loss_coef=0.5, entropy_coef=0.01, lr=2.5e-4,
+                 eps=1e-5, max_grad_norm=0.2, use_clipped_value_loss=True, use_normalized_advantage=False)
+    st = hb.RolloutStorage(T, N, obs_space, act_space, pol)
+    st.to(DEV)
+    nv = fill_rollout_(st, seed=4, p_done=0.1)
+    st.compute_returns(nv, True, 0.99, 0.95)
+    adv = ppo.get_advantages(st)
+
+    def run():
+        torch.manual_seed(5)
+        batch = next(iter(st.data_generator(adv, 1)))
+        m = pol.loss_and_backward(batch, 0.2, 0.5, 0.01, True)
+        torch.cuda.synchronize()
+        return (m[:3].clone(), pol._last["values"].clone(), pol._last["hidden_out"].clone(),
+                pol._flat["grads"].double().clone())
+
+    assert pol._rnn_wavefront(True, 512, 2, T)
+    m_w, v_w, h_w, g_w = run()
+    monkeypatch.setenv("HB200_NO_RNN_WAVEFRONT", "1")
+    assert not pol._rnn_wavefront(True, 512, 2, T)
+    m_s, v_s, h_s, g_s = run()
+    assert torch.equal(v_w, v_s) and torch.equal(h_w, h_s)
+    torch.testing.assert_close(m_w, m_s, rtol=1e-6, atol=1e-7)
+    assert torch.isfinite(g_w).all() and g_w.abs().max().item() > 0
+    rel = (g_w - g_s).norm().item() / g_s.norm().item()
+    assert rel < 1e-5, rel
+
+
 def test_graphed_actor_replays_act(hb):
     """CUDA-graph replay of the actor step must reproduce eager act() (deterministic mode: same logits -> same action),
     also after the weights changed (the packed weight images are refreshed outside the graph)."""
