@@ -51,6 +51,9 @@ SIGNATURES = {
     "hb200_get_umma_layout": ("i", ""),
     "hb200_set_halo_tma": ("i", "i"),
     "hb200_get_halo_tma": ("i", ""),
+    "hb200_conv_s2_supported": ("i", "iiiii"),
+    "hb200_conv_s2_fwd": ("i", "pppp" + "pipi" + "iiiiii" + "p"),
+    "hb200_conv_s2_dgrad": ("i", "ppppp" + "iiiiii" + "p"),
     "hb200_set_tgemm_tma": ("i", "i"),
     "hb200_get_tgemm_tma": ("i", ""),
     "hb200_conv_halo_supported": ("i", "iiiii"),

@@ -178,6 +178,20 @@ def conv_halo(x, wimg, y, batch, h, w, c, n, k, mode, addend=None, gn_stats=None
          k, mode)
 
 
+def conv_s2_supported(c, na, nb, h, w) -> bool:
+    return bool(load().hb200_conv_s2_supported(int(c), int(na), int(nb), int(h), int(w)))
+
+
+def conv_s2_fwd(x, wimg, ya, yb, batch, h, w, c, na, nb, stats_a=None, groups_a=0, stats_b=None, groups_b=0):
+    """3x3 stride-2 conv (ya) + 1x1 stride-2 downsample conv (yb) of the same input in one launch (csrc/conv_s2.cu)"""
+    call("hb200_conv_s2_fwd", ptr(x), ptr(wimg), ptr(ya), ptr(yb), ptr(stats_a), int(groups_a), ptr(stats_b),
+         int(groups_b), batch, h, w, c, na, nb)
+
+
+def conv_s2_dgrad(dya, dyb, wimg_t, dx, batch, h, w, c, na, nb, addend=None):
+    call("hb200_conv_s2_dgrad", ptr(dya), ptr(dyb), ptr(wimg_t), ptr(addend), ptr(dx), batch, h, w, c, na, nb)
+
+
 def conv_halo_wgrad(x, dy, dw_acc, batch, h, w, c, n, k):
     call("hb200_conv_halo_wgrad", ptr(x), ptr(dy), ptr(dw_acc), batch, h, w, c, n, k)
 

@@ -298,6 +298,8 @@ class _Conv:
         self.halo = False       # stride-1 3x3 layer served by the halo kernels (conv_halo.cu)
         self.halo_w = False     # weight gradient served by the (multi-image tile) halo wgrad kernel
         self.stem_s2d = False   # 7x7 s2 stem as a 4x4 s1 conv over the space-to-depth input
+        self.s2_pair = None     # 3x3 stride-2 conv whose block's 1x1 stride-2 downsample conv shares its kernel (conv_s2.cu)
+        self.s2_main = None     # ... and the downsample conv's pointer back
         self.wh = self.wht = None
         self._wd = self._gd = None
 
@@ -314,6 +316,11 @@ class _Conv:
             self.wht = torch.empty(9 * self.ci * self.co, dtype=BF16, device=dev)
             self.dw_acc = torch.empty(9 * self.ci, self.co, device=dev)
             return
+        if self.s2_pair is not None:   # images of the concatenated filter [co + co_d, ci, 3, 3] (fwd fp16, dgrad bf16)
+            ntot = self.co + self.s2_pair.co
+            self.wh = torch.empty(9 * self.ci * ntot, dtype=F16, device=dev)
+            self.wht = torch.empty(9 * self.ci * ntot, dtype=BF16, device=dev)
+            self._wcat = torch.zeros(ntot, self.ci, 3, 3, device=dev)
         self.wp = torch.empty(ops.packed_weight_elems(self.co, self.ci, self.k, self.k), dtype=F16, device=dev)
         self.wt = (torch.empty(ops.packed_weight_elems(self.ci, self.co, self.k, self.k), dtype=BF16, device=dev)
                    if need_dgrad else None)
@@ -430,7 +437,6 @@ class EncoderEngine:
         assert self.comp.out_hw == tuple(enc.output_shape[1:]), (self.comp.out_hw, enc.output_shape)
         self.convs: List[_Conv] = ([self.stem] + [c for convs, cd in self.blocks for c in convs + ([cd] if cd else [])]
                                    + [self.comp])
-        import os
         if not os.environ.get("HB200_NO_HALO"):
             for c in self.convs:
                 if c is self.stem:
@@ -440,6 +446,13 @@ class EncoderEngine:
                 elif c.k == 3 and c.stride == 1 and c.pad == 1:
                     c.halo = ops.conv_halo_supported(c.ci, c.co, 3, c.in_hw[0], c.in_hw[1])
                     c.halo_w = ops.conv_halo_wgrad_supported(c.ci, c.co, 3, c.in_hw[0], c.in_hw[1])
+            if not os.environ.get("HB200_NO_CONV_S2"):
+                for convs, cd in self.blocks:   # stride-2 block entry: 3x3 s2 conv + 1x1 s2 downsample in one kernel
+                    c = convs[0]
+                    if (cd is not None and c.k == 3 and c.stride == 2 and c.pad == 1 and cd.k == 1 and cd.stride == 2
+                            and cd.pad == 0 and c.conv_groups == 1 and cd.conv_groups == 1 and c.ci == c.ci_real
+                            and ops.conv_s2_supported(c.ci, c.co, cd.co, c.in_hw[0], c.in_hw[1])):
+                        c.s2_pair, cd.s2_main = cd, c
         self._ws = {}
         self._dev = None
         self._packed_key = None
@@ -497,6 +510,14 @@ class EncoderEngine:
             elif c.halo:
                 ops.pack_halo_weight(w, c.wh, c.ci, c.co, 3, 0)
                 ops.pack_halo_weight(w, c.wht, c.co, c.ci, 3, 1)
+            elif c.s2_pair is not None:
+                c._wcat[: c.co].copy_(w)
+                c._wcat[c.co:, :, 1, 1].copy_(c.s2_pair.dense_weight()[:, :, 0, 0])
+                ntot = c._wcat.shape[0]
+                ops.pack_halo_weight(c._wcat, c.wh, c.ci, ntot, 3, 0)
+                ops.pack_halo_weight(c._wcat, c.wht, ntot, c.ci, 3, 1)
+            elif c.s2_main is not None:
+                pass   # lives in the centre tap of its partner's images
             else:
                 ops.pack_conv_weight_into(w, c.wp, c.wt, c.ci)
 
@@ -522,6 +543,13 @@ class EncoderEngine:
 
         def conv(c, x):
             i = idx[id(c)]
+            if c.s2_main is not None:      # computed by its partner's launch
+                return ws[f"y{i}"], ws[f"st{i}"]
+            if c.s2_pair is not None:
+                d, k = c.s2_pair, idx[id(c.s2_pair)]
+                ops.conv_s2_fwd(x, c.wh, ws[f"y{i}"], ws[f"y{k}"], B, c.in_hw[0], c.in_hw[1], c.ci, c.co, d.co,
+                                stats_a=ws[f"st{i}"], groups_a=c.groups, stats_b=ws[f"st{k}"], groups_b=d.groups)
+                return ws[f"y{i}"], ws[f"st{i}"]
             if c.stem_s2d:
                 ops.conv_halo(x, c.wh, ws[f"y{i}"], B, c.out_hw[0], c.out_hw[1], 16, c.co, 4, 0, gn_stats=ws[f"st{i}"],
                               gn_groups=c.groups)
@@ -641,7 +669,12 @@ class EncoderEngine:
             dy0, _ = gn_bwd(convs[0], ga, None, 1, False)
             wgrad(convs[0], xin_b, dy0)
             gx = like(g_bufs[cur], xin)                           # ga is consumed; reuse its buffer
-            if cd is not None:
+            if cd is not None and convs[0].s2_pair is cd:
+                c0 = convs[0]
+                dyd, _ = gn_bwd(cd, gz, None, 0, False)
+                wgrad(cd, xin_b, dyd)
+                ops.conv_s2_dgrad(dy0, dyd, c0.wht, gx, B, c0.in_hw[0], c0.in_hw[1], c0.ci, c0.co, cd.co)
+            elif cd is not None:
                 self._dgrad(convs[0], dy0, gx, B)
                 dyd, _ = gn_bwd(cd, gz, None, 0, False)           # ws["gz"] is only rewritten by the next block
                 wgrad(cd, xin_b, dyd)

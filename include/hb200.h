@@ -231,6 +231,24 @@ int hb200_get_halo_tma(void);
  * HB/rl/ddppo/policy/resnet.py:196-281, resnet_policy.py:200-240), whose tiles span several images. */
 int hb200_conv_halo_wgrad_supported(int c, int n, int k, int h, int w);
 
+/* ---- stride-2 block entry: 3x3 stride-2 pad-1 conv + 1x1 stride-2 downsample conv of the same input -------------------
+ * (BasicBlock with a downsample branch, HB/rl/ddppo/policy/resnet.py:26-77, 143-160), one TMA-fed halo kernel per
+ * direction over the 2x2 space-to-depth VIEW of x (5-D tensor map on the NHWC tensor, no copy): see csrc/conv_s2.cu.
+ *   forward: x f16 [B,H,W,C] -> ya f16 [B,H/2,W/2,NA] (3x3 branch), yb f16 [B,H/2,W/2,NB] (1x1 branch), each with
+ *            optional fused GroupNorm sums (stats f64 [B,G,2], pre-zeroed).
+ *            wimg = hb200_pack_halo_weight(mode 0, c = C, n = NA + NB, k = 3) of the concatenated filter
+ *            [NA + NB, C, 3, 3] whose last NB rows hold the 1x1 filter in the centre tap, zeros elsewhere.
+ *   dgrad:   dx bf16 [B,H,W,C] = conv3x3^T(dya) + conv1x1^T(dyb) (+ addend); wimg_t = the same concatenated filter
+ *            packed with mode 1 (c = NA + NB, n = C).
+ * Supported: C = 32, NA = NB = 64, H % 32 == 0, W % 16 == 0 (layer2.0 of the resnet18 encoder at 256x256 input). */
+int hb200_conv_s2_supported(int c, int na, int nb, int h, int w);
+int hb200_conv_s2_fwd(const hb200_f16* x, const hb200_f16* wimg, hb200_f16* ya, hb200_f16* yb, double* stats_a,
+                      int groups_a, double* stats_b, int groups_b, int batch, int h, int w, int c, int na, int nb,
+                      hb200_stream_t stream);
+int hb200_conv_s2_dgrad(const hb200_bf16* dya, const hb200_bf16* dyb, const hb200_bf16* wimg_t,
+                        const hb200_bf16* addend, hb200_bf16* dx, int batch, int h, int w, int c, int na, int nb,
+                        hb200_stream_t stream);
+
 /* dw_acc f32 [(r*k+s)*C + ci][N] accumulated with atomics (caller zeroes), like hb200_conv_wgrad */
 int hb200_conv_halo_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc, int batch, int h, int w,
                           int c, int n, int k, hb200_stream_t stream);

@@ -363,6 +363,57 @@ def test_conv_fwd_dgrad_wgrad(hb, case):
                                    atol=2e-2 * max(1.0, dx_ref.abs().max().item()))
 
 
+@pytest.mark.parametrize("B,H,W", [(3, 32, 32), (2, 64, 16), (160, 32, 32)])
+def test_conv_s2_block_entry(hb, B, H, W):
+    """conv_s2.cu: 3x3 stride-2 conv + 1x1 stride-2 downsample conv of one input in one launch (forward with both
+    GroupNorm sums, and the summed data gradient) over the TMA space-to-depth view, vs torch convolutions."""
+    from habitat_lab_b200 import ops
+
+    C, NA, NB, G = 32, 64, 64, 16
+    assert ops.conv_s2_supported(C, NA, NB, H, W)
+    torch.manual_seed(B + H + W)
+    x = torch.randn(B, C, H, W, device=DEV)
+    wa = torch.randn(NA, C, 3, 3, device=DEV) / math.sqrt(9 * C)
+    wd = torch.randn(NB, C, 1, 1, device=DEV) / math.sqrt(C)
+    wcat = torch.zeros(NA + NB, C, 3, 3, device=DEV)
+    wcat[:NA] = wa
+    wcat[NA:, :, 1, 1] = wd[:, :, 0, 0]
+    img = torch.empty(9 * C * (NA + NB), device=DEV, dtype=torch.float16)
+    img_t = torch.empty(9 * C * (NA + NB), device=DEV, dtype=torch.bfloat16)
+    ops.pack_halo_weight(wcat, img, C, NA + NB, 3, 0)
+    ops.pack_halo_weight(wcat, img_t, NA + NB, C, 3, 1)
+    x_nhwc = hf(nhwc(x))
+    ya = torch.empty(B, H // 2, W // 2, NA, device=DEV, dtype=torch.float16)
+    yb = torch.empty(B, H // 2, W // 2, NB, device=DEV, dtype=torch.float16)
+    sa = torch.zeros(B, G, 2, device=DEV, dtype=torch.float64)
+    sb = torch.zeros(B, G, 2, device=DEV, dtype=torch.float64)
+    ops.conv_s2_fwd(x_nhwc, img, ya, yb, B, H, W, C, NA, NB, stats_a=sa, groups_a=G, stats_b=sb, groups_b=G)
+    torch.cuda.synchronize()
+    xh = hf(x).float()
+    ya_ref = F.conv2d(xh, hf(wa).float(), stride=2, padding=1)
+    yb_ref = F.conv2d(xh, hf(wd).float(), stride=2)
+    torch.testing.assert_close(nchw(ya.float()), ya_ref, rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(nchw(yb.float()), yb_ref, rtol=2e-3, atol=2e-3)
+    for st, ref in ((sa, ya_ref), (sb, yb_ref)):
+        yg = ref.reshape(B, G, -1)
+        torch.testing.assert_close(st[..., 0].float(), yg.sum(-1), rtol=1e-3, atol=2e-2)
+        torch.testing.assert_close(st[..., 1].float(), (yg * yg).sum(-1), rtol=1e-3, atol=2e-2)
+    # data gradient of both branches, summed (+ optional addend)
+    dya = torch.randn_like(ya_ref)
+    dyb = torch.randn_like(yb_ref)
+    dx_ref = (torch.nn.grad.conv2d_input(x.shape, bf(wa).float(), bf(dya).float(), stride=2, padding=1) +
+              torch.nn.grad.conv2d_input(x.shape, bf(wd).float(), bf(dyb).float(), stride=2))
+    dx = torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16)
+    ops.conv_s2_dgrad(bf(nhwc(dya)), bf(nhwc(dyb)), img_t, dx, B, H, W, C, NA, NB)
+    torch.cuda.synchronize()
+    tol = 1e-2 * max(1.0, dx_ref.abs().max().item())
+    torch.testing.assert_close(nchw(dx.float()), dx_ref, rtol=1e-2, atol=tol)
+    addend = bf(torch.randn(B, H, W, C, device=DEV))
+    ops.conv_s2_dgrad(bf(nhwc(dya)), bf(nhwc(dyb)), img_t, dx, B, H, W, C, NA, NB, addend=addend)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(nchw(dx.float()), dx_ref + nchw(addend.float()), rtol=1e-2, atol=2 * tol)
+
+
 HALO_CASES = [(3, 32, 32, 32, 32), (2, 16, 16, 64, 64), (5, 16, 8, 32, 32), (600, 32, 32, 32, 32)]
 
 
