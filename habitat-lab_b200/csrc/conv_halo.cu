@@ -47,6 +47,73 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
   return d;
 }
 
+// lane l ends with the warp sum of v[l] (31 shuffles for 32 values)
+__device__ __forceinline__ float halo_warp_reduce32(float (&v)[32], int lane) {
+  float a[16], b[8], c[4], d[2];
+  { const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float send = hi ? v[i] : v[i + 16], keep = hi ? v[i + 16] : v[i];
+                                   a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); } }
+  { const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float send = hi ? a[i] : a[i + 8], keep = hi ? a[i + 8] : a[i];
+                                  b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); } }
+  { const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float send = hi ? b[i] : b[i + 4], keep = hi ? b[i + 4] : b[i];
+                                  c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); } }
+  { const bool hi = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const float send = hi ? c[i] : c[i + 2], keep = hi ? c[i + 2] : c[i];
+                                  d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); } }
+  const bool hi = lane & 1;
+  const float send = hi ? d[0] : d[1], keep = hi ? d[1] : d[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// GroupNorm sums of one 32-channel chunk of a 128-pixel tile (one warp = 32 pixels): per-pixel group partials first
+// (channels of a group are adjacent), then ONE transpose-reduce over sums and squares together -- 31 shuffles for
+// 2-channel groups, 16 for 4-channel groups, instead of two 16-value trees per chunk.
+// stats_b = stats + b * groups * 2; ch0 = first channel of the chunk.
+__device__ __forceinline__ void halo_gn_stats_chunk(const float (&acc)[32], int lane, int cpg, double* stats_b, int ch0) {
+  if (cpg == 2) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      v[i] = acc[2 * i] + acc[2 * i + 1];
+      v[16 + i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
+    }
+    const float t = halo_warp_reduce32(v, lane);   // lane < 16: sum of group lane; else sum of squares of group lane-16
+    atomicAdd(stats_b + ((ch0 >> 1) + (lane & 15)) * 2 + (lane >> 4), (double)t);
+  } else if (cpg == 4) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a0 = acc[4 * i], a1 = acc[4 * i + 1], a2 = acc[4 * i + 2], a3 = acc[4 * i + 3];
+      v[i] = (a0 + a1) + (a2 + a3);
+      v[8 + i] = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float t = warp_reduce16(v, lane);        // lanes 2i, 2i+1 hold value i
+    if ((lane & 1) == 0) {
+      const int i = lane >> 1;
+      atomicAdd(stats_b + ((ch0 >> 2) + (i & 7)) * 2 + (i >> 3), (double)t);
+    }
+  } else {
+    float s2[16], q2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      s2[i] = acc[2 * i] + acc[2 * i + 1];
+      q2[i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
+    }
+    const float ts = warp_reduce16(s2, lane), tq = warp_reduce16(q2, lane);
+    if ((lane & 1) == 0) {
+      double* dst = stats_b + ((ch0 + lane) / cpg) * 2;
+      atomicAdd(dst, (double)ts);
+      atomicAdd(dst + 1, (double)tq);
+    }
+  }
+}
+
 struct HaloArgs {
   const __nv_bfloat16* x;      // [B,H,W,C] input of the conv (x for fwd, dy for dgrad)
   const __nv_bfloat16* wimg;   // [taps][C/8][N][8] weight image (K-major no-swizzle per tap)
@@ -814,22 +881,8 @@ conv_halo_tma_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap)
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rr[j]);
-        if (MODE == 0 && a.stats != nullptr) {
-          const int cpg = N / a.gn_groups;
-          float s2[16], q2[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            s2[i] = acc[2 * i] + acc[2 * i + 1];
-            q2[i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
-          }
-          const float ts = warp_reduce16(s2, lane), tq = warp_reduce16(q2, lane);
-          if ((lane & 1) == 0) {
-            const int ch = col0 + lane;
-            double* dst = a.stats + ((size_t)b * a.gn_groups + ch / cpg) * 2;
-            atomicAdd(dst, (double)ts);
-            atomicAdd(dst + 1, (double)tq);
-          }
-        }
+        if (MODE == 0 && a.stats != nullptr)
+          halo_gn_stats_chunk(acc, lane, N / a.gn_groups, a.stats + (size_t)b * a.gn_groups * 2, col0);
         const size_t o = pix * N + col0;
         if (MODE == 1 && a.addend != nullptr) {
           const uint4* ad = reinterpret_cast<const uint4*>(a.addend + o);
@@ -864,6 +917,332 @@ conv_halo_tma_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap)
     if (NB == 1 && tid == 0 && it + 1 < my_n) {
       mbar_wait(&mma_bar[it & 1], (it >> 1) & 1);
       issue_halo(first + (it + 1) * stride, 0);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int C, int N, int MODE>
+__global__ void __launch_bounds__(128)
+conv_halo_sw_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
+  // 3x3 stride-1 pad-1.  The halo is staged as KW = 3 copies of the tile rows, copy kx pre-shifted by kx pixels, each
+  // copy [HH rows][8 pixels][C channels] in the 64- / 128-byte-swizzle K-major layout (one TMA box per copy: rows of
+  // C*2 bytes instead of the 16-byte pieces of the no-swizzle slabs, whose rate -- not bytes -- bounded the halo kernels
+  // at ~2.1 TB/s).  A filter tap (r, s) is then copy s shifted by r whole swizzle atoms: aligned descriptors only.
+  using Cfg = HaloCfg<C, N, 3, 3, 1>;
+  constexpr int KH = 3, KW = 3, PAD = 1, HH = Cfg::HH;
+  constexpr uint32_t RB = C * 2;                 // bytes per pixel row of the operand: 64 (SWIZZLE_64B) or 128
+  constexpr uint32_t ATOM = 8 * RB;              // 8 pixels = one output row of the tile = one swizzle atom
+  constexpr uint32_t COPY = HH * ATOM;
+  constexpr uint32_t STAGE = KW * COPY;
+  constexpr int NB = (Cfg::W_BYTES + 2 * (int)STAGE > 200 * 1024) ? 1 : 2;
+  constexpr int kSw = RB == 128 ? kSwizzle128B : kSwizzle64B;
+  static_assert(RB == 64 || RB == 128, "conv_halo_sw: 32 or 64 channels");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ __align__(8) uint64_t ld_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms: 1024-byte aligned
+  const uint32_t s_w = sbase;
+  const uint32_t s_halo0 = s_w + Cfg::W_BYTES;   // W_BYTES is a multiple of 128
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
+    mbar_init(&ld_bar[0], 1);
+    mbar_init(&ld_bar[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.wimg);
+    for (int v = tid; v < Cfg::W_BYTES / 16; v += 128) cp_async16(s_w + (uint32_t)v * 16, src + v, true);
+  }
+  cp_async_commit();
+  const int tiles_x = a.W / TW, tiles_y = a.H / TH;
+  const int tiles_per_img = tiles_x * tiles_y;
+  auto tile_coords = [&](int tile, int& b, int& oh0, int& ow0) {
+    b = tile / tiles_per_img;
+    const int r = tile - b * tiles_per_img;
+    oh0 = (r / tiles_x) * TH;
+    ow0 = (r % tiles_x) * TW;
+  };
+  // The descriptor must be addressed in PARAM space: `&tmap` evaluated here, in the kernel body.  Inside the lambda a
+  // by-reference capture makes nvcc spill a thread-local copy of the 128-byte map and hand the TMA unit a stack
+  // address (round-1 version: every tile loaded garbage).
+  const CUtensorMap* const tmap_p = &tmap;
+  auto issue_halo = [&, tmap_p](int tile, int stage) {   // thread 0 only
+    int b, oh0, ow0;
+    tile_coords(tile, b, oh0, ow0);
+    mbar_expect_tx(&ld_bar[stage], STAGE);
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx)
+      tma_load_4d(s_halo0 + (uint32_t)stage * STAGE + (uint32_t)kx * COPY, tmap_p, &ld_bar[stage], 0, ow0 - PAD + kx,
+                  oh0 - PAD, b);
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  if (tid == 0 && my_n > 0) issue_halo(first, 0);
+  cp_async_wait<0>();          // weights
+  fence_proxy_async_smem();    // cp.async (generic proxy) -> tcgen05 (async proxy)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  // forward: fp16 input halo x fp16 weight image; dgrad: bf16 gradients x bf16 flipped / transposed image
+  constexpr uint32_t idesc = MODE == 0 ? make_idesc_f16(128, N, 0, 0, kFmtF16, kFmtF16) : make_idesc_bf16(128, N, 0, 0);
+  const int py = tid >> 3, px = tid & 7;
+
+  for (int it = 0; it <= my_n; ++it) {
+    // (1) MMAs of tile it-1 are complete (frees halo stage (it+1)&1 and fills TMEM stage (it-1)&1)
+    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+    // (2) one thread starts the TMA load of tile it+1 (two stages; with one stage see (5))
+    if (NB == 2 && tid == 0 && it + 1 < my_n) issue_halo(first + (it + 1) * stride, (it + 1) & 1);
+    // (3) MMAs of tile it as soon as its halo has landed
+    if (it < my_n) {
+      fence_before_sync();  // orders the previous iteration's tcgen05.ld (TMEM stage reuse)
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(&ld_bar[NB == 2 ? (it & 1) : 0], NB == 2 ? ((it >> 1) & 1) : (it & 1));
+        fence_after_sync();
+        const uint32_t sh = s_halo0 + (uint32_t)(NB == 2 ? (it & 1) : 0) * STAGE;
+        const uint32_t tacc = tmem_base + (uint32_t)((it & 1) * N);
+        uint32_t accum = 0;
+#pragma unroll
+        for (int r = 0; r < KH; ++r)
+#pragma unroll
+          for (int s = 0; s < KW; ++s)
+#pragma unroll
+            for (int kk = 0; kk < C / 16; ++kk) {
+              const uint64_t da = make_smem_desc(sh + s * COPY + r * ATOM + kk * 32, 16, ATOM, (Layout)kSw);
+              const uint64_t db = make_smem_desc(s_w + (r * KW + s) * (C * N * 2) + 2 * kk * (N * 16), N * 16, 128, kNoSwizzle);
+              mma_bf16_ss(tacc, da, db, idesc, accum);
+              accum = 1;
+            }
+        mma_commit(&mma_bar[it & 1]);
+      }
+    }
+    // (4) epilogue of tile it-1 (same as conv_halo_kernel)
+    if (it >= 1) {
+      fence_after_sync();
+      int b, oh0, ow0;
+      tile_coords(first + (it - 1) * stride, b, oh0, ow0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(((it - 1) & 1) * N);
+      const size_t pix = ((size_t)b * a.H + oh0 + py) * a.W + ow0 + px;
+#pragma unroll 1
+      for (int col0 = 0; col0 < N; col0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + col0, rr);
+        tmem_ld_wait();
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(rr[j]);
+        if (MODE == 0 && a.stats != nullptr)
+          halo_gn_stats_chunk(acc, lane, N / a.gn_groups, a.stats + (size_t)b * a.gn_groups * 2, col0);
+        const size_t o = pix * N + col0;
+        if (MODE == 1 && a.addend != nullptr) {
+          const uint4* ad = reinterpret_cast<const uint4*>(a.addend + o);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            float f[8];
+            unpack8(ad[v], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[v * 8 + e] += f[e];
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(a.y + o);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 u;
+          if (MODE == 0) {  // forward output y: fp16 (saturating)
+            u.x = pack_f16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+            u.y = pack_f16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+            u.z = pack_f16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+            u.w = pack_f16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          } else {          // data gradient: bf16
+            u.x = pack_bf16x2(acc[v * 8 + 0], acc[v * 8 + 1]);
+            u.y = pack_bf16x2(acc[v * 8 + 2], acc[v * 8 + 3]);
+            u.z = pack_bf16x2(acc[v * 8 + 4], acc[v * 8 + 5]);
+            u.w = pack_bf16x2(acc[v * 8 + 6], acc[v * 8 + 7]);
+          }
+          dst[v] = u;
+        }
+      }
+    }
+    // (5) single halo stage: tile it+1 may be loaded once the MMAs of tile it have consumed the stage
+    if (NB == 1 && tid == 0 && it + 1 < my_n) {
+      mbar_wait(&mma_bar[it & 1], (it >> 1) & 1);
+      issue_halo(first + (it + 1) * stride, 0);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+
+// ---- warp-specialised variant ---------------------------------------------------------------------------------------
+// conv_halo_tma_kernel runs load -> MMA -> epilogue of consecutive tiles from ONE thread's program order: with a single
+// halo stage the TMA latency of tile it+1 (~1.5-2 us) is exposed after every tile, and only the second CTA of the SM
+// hides it (64-channel dgrad: 3.6 us per tile per CTA for 0.6 us of MMAs).  Here the three phases are separate warps
+// that meet only at mbarriers:
+//   warp 4 (one lane)  producer: halo stage ring, NS deep (as many as fit next to the resident weights)
+//   warp 5 (one lane)  MMA issue: waits full[stage] + the accumulator's release, commits to empty[stage] and tfull[acc]
+//   warps 0-3          epilogue: TMEM -> registers, release the accumulator right after the last tcgen05.ld, then
+//                      GroupNorm sums / addend / pack / store while the next tile's MMAs already run
+// SW: stage the halo as KW pre-shifted copies of whole pixel rows in the swizzled K-major layout (conv_halo_sw_kernel)
+// instead of 16-byte channel slabs: aligned operand reads for the MMAs at KW times the TMA bytes
+template <int C, int N, int KH, int KW, int PAD, int MODE, int NS, bool SW = false>
+__global__ void __launch_bounds__(192)
+conv_halo_ws_kernel(const HaloArgs a, const __grid_constant__ CUtensorMap tmap) {
+  using Cfg = HaloCfg<C, N, KH, KW, PAD>;
+  constexpr int CJ = Cfg::CJ, HH = Cfg::HH, HWD = Cfg::HWD;
+  constexpr uint32_t SLAB = (uint32_t)((HH * HWD * 16 + 127) / 128 * 128);
+  constexpr uint32_t RB = C * 2, ATOM = 8 * RB, COPY = HH * ATOM;   // swizzled copies: pixel rows, 8-pixel atoms
+  constexpr uint32_t STAGE = SW ? KW * COPY : CJ * SLAB;
+  constexpr int kSw = RB == 128 ? kSwizzle128B : kSwizzle64B;
+  static_assert(!SW || RB == 64 || RB == 128, "swizzled halo copies: 32 or 64 channels");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms are 1024-byte aligned
+  const uint32_t s_w = sbase;
+  const uint32_t s_halo0 = s_w + Cfg::W_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 4); mbar_init(&tempty_bar[1], 4);   // one arrival per epilogue warp
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.wimg);
+    for (int v = tid; v < Cfg::W_BYTES / 16; v += 192) cp_async16(s_w + (uint32_t)v * 16, src + v, true);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const int tiles_x = a.W / TW, tiles_per_img = tiles_x * (a.H / TH);
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  const CUtensorMap* const tmap_p = &tmap;   // param-space address, taken in the kernel body
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int it = 0; it < my_n; ++it) {
+        const int st = it % NS;
+        if (it >= NS) mbar_wait(&empty_bar[st], ((it / NS) - 1) & 1);
+        const int tile = first + it * stride;
+        const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+        const int oh0 = (r / tiles_x) * TH, ow0 = (r % tiles_x) * TW;
+        if constexpr (SW) {
+          mbar_expect_tx(&full_bar[st], STAGE);
+#pragma unroll
+          for (int kx = 0; kx < KW; ++kx)
+            tma_load_4d(s_halo0 + (uint32_t)st * STAGE + (uint32_t)kx * COPY, tmap_p, &full_bar[st], 0, ow0 - PAD + kx,
+                        oh0 - PAD, b);
+        } else {
+          mbar_expect_tx(&full_bar[st], (uint32_t)(CJ * HH * HWD * 16));
+#pragma unroll
+          for (int j = 0; j < CJ; ++j)
+            tma_load_4d(s_halo0 + (uint32_t)st * STAGE + (uint32_t)j * SLAB, tmap_p, &full_bar[st], j * 8, ow0 - PAD,
+                        oh0 - PAD, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // forward: fp16 input halo x fp16 weight image; dgrad: bf16 gradients x bf16 flipped / transposed image
+      constexpr uint32_t idesc = MODE == 0 ? make_idesc_f16(128, N, 0, 0, kFmtF16, kFmtF16) : make_idesc_bf16(128, N, 0, 0);
+      for (int it = 0; it < my_n; ++it) {
+        const int st = it % NS, acc = it & 1;
+        if (it >= 2) mbar_wait(&tempty_bar[acc], ((it >> 1) - 1) & 1);
+        mbar_wait(&full_bar[st], (it / NS) & 1);
+        fence_after_sync();
+        const uint32_t sh = s_halo0 + (uint32_t)st * STAGE;
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * N);
+        uint32_t accum = 0;
+#pragma unroll
+        for (int r = 0; r < KH; ++r)
+#pragma unroll
+          for (int s = 0; s < KW; ++s)
+#pragma unroll
+            for (int kk = 0; kk < C / 16; ++kk) {
+              const uint64_t da = SW ? make_smem_desc(sh + s * COPY + r * ATOM + kk * 32, 16, ATOM, (Layout)kSw)
+                                     : make_smem_desc(sh + 2 * kk * SLAB + r * (HWD * 16) + s * 16, SLAB, HWD * 16, kNoSwizzle);
+              const uint64_t db = make_smem_desc(s_w + (r * KW + s) * (C * N * 2) + 2 * kk * (N * 16), N * 16, 128, kNoSwizzle);
+              mma_bf16_ss(tacc, da, db, idesc, accum);
+              accum = 1;
+            }
+        mma_commit(&empty_bar[st]);    // the halo stage is free once these MMAs have read it
+        mma_commit(&tfull_bar[acc]);   // ... and the accumulator is complete
+      }
+    }
+    __syncwarp();
+  } else {
+    const int py = tid >> 3, px = tid & 7;
+    for (int it = 0; it < my_n; ++it) {
+      const int acc = it & 1;
+      const int tile = first + it * stride;
+      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+      const int oh0 = (r / tiles_x) * TH, ow0 = (r % tiles_x) * TW;
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * N);
+      const size_t pix = ((size_t)b * a.H + oh0 + py) * a.W + ow0 + px;
+      uint32_t rr[N];
+#pragma unroll
+      for (int col0 = 0; col0 < N; col0 += 32) tmem_ld32(taddr + col0, *reinterpret_cast<uint32_t(*)[32]>(&rr[col0]));
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);   // the MMA warp may overwrite this accumulator now
+#pragma unroll
+      for (int col0 = 0; col0 < N; col0 += 32) {
+        float acc_[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc_[j] = __uint_as_float(rr[col0 + j]);
+        if (MODE == 0 && a.stats != nullptr)
+          halo_gn_stats_chunk(acc_, lane, N / a.gn_groups, a.stats + (size_t)b * a.gn_groups * 2, col0);
+        const size_t o = pix * N + col0;
+        if (MODE == 1 && a.addend != nullptr) {
+          const uint4* ad = reinterpret_cast<const uint4*>(a.addend + o);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            float f[8];
+            unpack8(ad[v], f);
+#pragma unroll
+            for (int e2 = 0; e2 < 8; ++e2) acc_[v * 8 + e2] += f[e2];
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(a.y + o);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 u;
+          if (MODE == 0) {
+            u.x = pack_f16x2(acc_[v * 8 + 0], acc_[v * 8 + 1]);
+            u.y = pack_f16x2(acc_[v * 8 + 2], acc_[v * 8 + 3]);
+            u.z = pack_f16x2(acc_[v * 8 + 4], acc_[v * 8 + 5]);
+            u.w = pack_f16x2(acc_[v * 8 + 6], acc_[v * 8 + 7]);
+          } else {
+            u.x = pack_bf16x2(acc_[v * 8 + 0], acc_[v * 8 + 1]);
+            u.y = pack_bf16x2(acc_[v * 8 + 2], acc_[v * 8 + 3]);
+            u.z = pack_bf16x2(acc_[v * 8 + 4], acc_[v * 8 + 5]);
+            u.w = pack_bf16x2(acc_[v * 8 + 6], acc_[v * 8 + 7]);
+          }
+          dst[v] = u;
+        }
+      }
     }
   }
   fence_before_sync();
@@ -942,6 +1321,83 @@ static int launch_halo_tma(const HaloArgs& a, cudaStream_t st) {
   constexpr int nstage = (Cfg::W_BYTES + 2 * (int)(Cfg::CJ * slab) > 110 * 1024) ? 1 : 2;
   const size_t smem = Cfg::W_BYTES + nstage * Cfg::CJ * slab + 256;
   auto kern = conv_halo_tma_kernel<C, N, KH, KW, PAD, MODE>;
+  static int cache = 0;
+  if (cache == 0) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = blocks_per_sm((const void*)kern, smem, Cfg::TMEM_COLS, &cache);
+  int grid = kNumSMs * per_sm;
+  if (grid > a.ntiles) grid = a.ntiles;
+  kern<<<grid, 128, smem, st>>>(a, tmap);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+template <int C, int N, int KH, int KW, int PAD, int MODE, int NS, bool SW = false>
+static int launch_halo_ws(const HaloArgs& a, cudaStream_t st) {
+  using Cfg = HaloCfg<C, N, KH, KW, PAD>;
+  EncodeTiledFn enc = halo_encode_fn();
+  if (!enc) {
+    set_last_error("conv_halo (TMA): cuTensorMapEncodeTiled is not available from this driver");
+    return HB200_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)a.W * C * 2, (cuuint64_t)a.H * a.W * C * 2};
+  const cuuint32_t box_slab[4] = {8u, (cuuint32_t)Cfg::HWD, (cuuint32_t)Cfg::HH, 1u};
+  const cuuint32_t box_rows[4] = {(cuuint32_t)C, (cuuint32_t)TW, (cuuint32_t)Cfg::HH, 1u};
+  const cuuint32_t* box = SW ? box_rows : box_slab;
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.x, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         !SW ? CU_TENSOR_MAP_SWIZZLE_NONE : (C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("conv_halo (TMA): cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HB200_ERR_CUDA;
+  }
+  constexpr size_t slab = (size_t)((Cfg::HH * Cfg::HWD * 16 + 127) / 128 * 128);
+  const size_t stage = SW ? (size_t)KW * Cfg::HH * 8 * C * 2 : Cfg::CJ * slab;
+  const size_t smem = Cfg::W_BYTES + (size_t)NS * stage + 1024;
+  auto kern = conv_halo_ws_kernel<C, N, KH, KW, PAD, MODE, NS, SW>;
+  static int grid_cache = 0;
+  if (grid_cache == 0) {
+    HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 192, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (per_sm > 512 / Cfg::TMEM_COLS) per_sm = 512 / Cfg::TMEM_COLS;
+    grid_cache = kNumSMs * per_sm;
+  }
+  const int grid = grid_cache < a.ntiles ? grid_cache : a.ntiles;
+  kern<<<grid, 192, smem, st>>>(a, tmap);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
+template <int C, int N, int MODE>
+static int launch_halo_sw(const HaloArgs& a, cudaStream_t st) {
+  using Cfg = HaloCfg<C, N, 3, 3, 1>;
+  EncodeTiledFn enc = halo_encode_fn();
+  if (!enc) {
+    set_last_error("conv_halo (swizzled TMA): cuTensorMapEncodeTiled is not available from this driver");
+    return HB200_ERR_UNSUPPORTED;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)a.W * C * 2, (cuuint64_t)a.H * a.W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)TW, (cuuint32_t)Cfg::HH, 1u};   // whole pixels: C*2-byte rows
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)a.x, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("conv_halo (swizzled TMA): cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return HB200_ERR_CUDA;
+  }
+  constexpr size_t stage = (size_t)3 * Cfg::HH * 8 * C * 2;
+  constexpr int nstage = (Cfg::W_BYTES + 2 * (int)stage > 200 * 1024) ? 1 : 2;
+  const size_t smem = Cfg::W_BYTES + nstage * stage + 1024;
+  auto kern = conv_halo_sw_kernel<C, N, MODE>;
   static int cache = 0;
   if (cache == 0) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int per_sm = blocks_per_sm((const void*)kern, smem, Cfg::TMEM_COLS, &cache);
@@ -1039,7 +1495,7 @@ using namespace hb200;
 // halo loads by TMA (default) or by the cp.async gather kernel (HB200_NO_HALO_TMA=1, or hb200_set_halo_tma(0) from tests)
 static int g_halo_tma = getenv("HB200_NO_HALO_TMA") == nullptr ? 1 : 0;
 extern "C" int hb200_set_halo_tma(int enable) {
-  g_halo_tma = enable ? 1 : 0;
+  g_halo_tma = enable;   // 0 cp.async gather, 1 best per layer (default), 2 swizzled rows, 3 warp-specialised slabs, 4 both, 5 plain TMA slabs
   return HB200_OK;
 }
 extern "C" int hb200_get_halo_tma(void) { return g_halo_tma; }
@@ -1095,6 +1551,26 @@ extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb20
   // TMA-fed halo (conv_halo_tma_kernel) for every halo layer: measured 17-18 % faster than the cp.async gather on
   // B200 for the 32-channel layers and the stem (0.219 -> 0.183 ms, 0.711 -> 0.581 ms); HB200_NO_HALO_TMA=1 disables
   const bool use_tma = g_halo_tma != 0;
+  // Loader per layer (hb200_set_halo_tma): 1 = the measured best of the variants below (tools/halo_bench.py, 4096 frames):
+  //   64 channels: warp-specialised + swizzled pixel-row copies  fwd 126 -> 93 us, dgrad 99 -> 88 us
+  //   32 channels: dgrad with swizzled copies 177 -> 146 us; forward stays on the 16-byte slabs (175 us vs 182 / 209)
+  // 2 / 3 / 4 / 5 force swizzled copies / warp-specialised slabs / warp-specialised swizzled / plain slabs everywhere.
+  if (g_halo_tma == 1 && k == 3 && c == 64)
+    return mode == 0 ? launch_halo_ws<64, 64, 3, 3, 1, 0, 2, true>(a, st) : launch_halo_ws<64, 64, 3, 3, 1, 1, 2, true>(a, st);
+  if (g_halo_tma == 1 && k == 3 && c == 32 && mode == 1) return launch_halo_sw<32, 32, 1>(a, st);
+  if (g_halo_tma == 4 && k == 3 && c == 32)
+    return mode == 0 ? launch_halo_ws<32, 32, 3, 3, 1, 0, 3, true>(a, st) : launch_halo_ws<32, 32, 3, 3, 1, 1, 3, true>(a, st);
+  if (g_halo_tma == 4 && k == 3 && c == 64)
+    return mode == 0 ? launch_halo_ws<64, 64, 3, 3, 1, 0, 2, true>(a, st) : launch_halo_ws<64, 64, 3, 3, 1, 1, 2, true>(a, st);
+  if (g_halo_tma == 3 && k == 3 && c == 32)
+    return mode == 0 ? launch_halo_ws<32, 32, 3, 3, 1, 0, 4>(a, st) : launch_halo_ws<32, 32, 3, 3, 1, 1, 4>(a, st);
+  if (g_halo_tma == 3 && k == 3 && c == 64)
+    return mode == 0 ? launch_halo_ws<64, 64, 3, 3, 1, 0, 6>(a, st) : launch_halo_ws<64, 64, 3, 3, 1, 1, 6>(a, st);
+  if (g_halo_tma == 3 && k == 4 && mode == 0) return launch_halo_ws<16, 32, 4, 4, 2, 0, 6>(a, st);
+  if (g_halo_tma == 2 && k == 3 && c == 32)
+    return mode == 0 ? launch_halo_sw<32, 32, 0>(a, st) : launch_halo_sw<32, 32, 1>(a, st);
+  if (g_halo_tma == 2 && k == 3 && c == 64)
+    return mode == 0 ? launch_halo_sw<64, 64, 0>(a, st) : launch_halo_sw<64, 64, 1>(a, st);
   if (use_tma && k == 3 && c == 32)
     return mode == 0 ? launch_halo_tma<32, 32, 3, 3, 1, 0>(a, st) : launch_halo_tma<32, 32, 3, 3, 1, 1>(a, st);
   if (use_tma && k == 4 && mode == 0) return launch_halo_tma<16, 32, 4, 4, 2, 0>(a, st);

@@ -40,6 +40,73 @@ __device__ __forceinline__ float s2_warp_reduce16(float (&v)[16], int lane) {
   return d;
 }
 
+// lane l ends with the warp sum of v[l] (31 shuffles for 32 values)
+__device__ __forceinline__ float s2_warp_reduce32(float (&v)[32], int lane) {
+  float a[16], b[8], c[4], d[2];
+  { const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { const float send = hi ? v[i] : v[i + 16], keep = hi ? v[i + 16] : v[i];
+                                   a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); } }
+  { const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float send = hi ? a[i] : a[i + 8], keep = hi ? a[i + 8] : a[i];
+                                  b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); } }
+  { const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float send = hi ? b[i] : b[i + 4], keep = hi ? b[i + 4] : b[i];
+                                  c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); } }
+  { const bool hi = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const float send = hi ? c[i] : c[i + 2], keep = hi ? c[i + 2] : c[i];
+                                  d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2); } }
+  const bool hi = lane & 1;
+  const float send = hi ? d[0] : d[1], keep = hi ? d[1] : d[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+// GroupNorm sums of one 32-channel chunk of a 128-pixel tile (one warp = 32 pixels): per-pixel group partials first
+// (channels of a group are adjacent), then ONE transpose-reduce over sums and squares together -- 31 shuffles for
+// 2-channel groups, 16 for 4-channel groups, instead of two 16-value trees per chunk.
+// stats_b = stats + b * groups * 2; ch0 = first channel of the chunk.
+__device__ __forceinline__ void s2_gn_stats_chunk(const float (&acc)[32], int lane, int cpg, double* stats_b, int ch0) {
+  if (cpg == 2) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      v[i] = acc[2 * i] + acc[2 * i + 1];
+      v[16 + i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
+    }
+    const float t = s2_warp_reduce32(v, lane);   // lane < 16: sum of group lane; else sum of squares of group lane-16
+    atomicAdd(stats_b + ((ch0 >> 1) + (lane & 15)) * 2 + (lane >> 4), (double)t);
+  } else if (cpg == 4) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a0 = acc[4 * i], a1 = acc[4 * i + 1], a2 = acc[4 * i + 2], a3 = acc[4 * i + 3];
+      v[i] = (a0 + a1) + (a2 + a3);
+      v[8 + i] = (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float t = s2_warp_reduce16(v, lane);        // lanes 2i, 2i+1 hold value i
+    if ((lane & 1) == 0) {
+      const int i = lane >> 1;
+      atomicAdd(stats_b + ((ch0 >> 2) + (i & 7)) * 2 + (i >> 3), (double)t);
+    }
+  } else {
+    float s2[16], q2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      s2[i] = acc[2 * i] + acc[2 * i + 1];
+      q2[i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
+    }
+    const float ts = s2_warp_reduce16(s2, lane), tq = s2_warp_reduce16(q2, lane);
+    if ((lane & 1) == 0) {
+      double* dst = stats_b + ((ch0 + lane) / cpg) * 2;
+      atomicAdd(dst, (double)ts);
+      atomicAdd(dst + 1, (double)tq);
+    }
+  }
+}
+
 __device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -162,20 +229,8 @@ __global__ void __launch_bounds__(128) conv_s2_fwd_kernel(const S2Args a, const 
         double* stats = second ? a.stats_b : a.stats_a;
         if (stats != nullptr) {
           const int groups = second ? a.groups_b : a.groups_a;
-          const int cpg = (second ? NB : NA) / groups;
-          float s2[16], q2[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            s2[i] = acc[2 * i] + acc[2 * i + 1];
-            q2[i] = acc[2 * i] * acc[2 * i] + acc[2 * i + 1] * acc[2 * i + 1];
-          }
-          const float ts = s2_warp_reduce16(s2, lane), tq = s2_warp_reduce16(q2, lane);
-          if ((lane & 1) == 0) {
-            const int ch = col0 - (second ? NA : 0) + lane;
-            double* dst = stats + ((size_t)b * groups + ch / cpg) * 2;
-            atomicAdd(dst, (double)ts);
-            atomicAdd(dst + 1, (double)tq);
-          }
+          s2_gn_stats_chunk(acc, lane, (second ? NB : NA) / groups, stats + (size_t)b * groups * 2,
+                            col0 - (second ? NA : 0));
         }
         __half* out = second ? reinterpret_cast<__half*>(a.yb) + pix * NB + (col0 - NA)
                              : reinterpret_cast<__half*>(a.ya) + pix * NA + col0;

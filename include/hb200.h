@@ -221,9 +221,11 @@ int hb200_pack_halo_weight(const float* w_oihw, hb200_bf16* img, int co, int ci_
 int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb200_bf16* y, const hb200_bf16* addend,
                     double* gn_stats, int gn_groups, int batch, int h, int w, int c, int n, int k, int mode,
                     hb200_stream_t stream);
-/* Forward / dgrad halo tiles are loaded by TMA box copies (default) or by the zero-filling cp.async gather kernel
- * (enable = 0; also HB200_NO_HALO_TMA=1 in the environment).  Both are kept parity-tested. */
-int hb200_set_halo_tma(int enable);
+/* Halo loader of the forward / dgrad halo kernels: 0 = zero-filling cp.async gather (also HB200_NO_HALO_TMA=1 in the
+ * environment), 1 = the measured best TMA variant per layer (default), 2 = TMA copies of whole pixel rows into the
+ * swizzled K-major layout, 3 = warp-specialised pipeline over 16-byte channel slabs, 4 = warp-specialised + swizzled
+ * rows, 5 = plain TMA slabs.  All are kept parity-tested (tests/test_gpu_kernels.py::test_conv_halo_3x3). */
+int hb200_set_halo_tma(int mode);
 int hb200_get_halo_tma(void);
 
 /* 1 if hb200_conv_halo_wgrad serves this 3x3 / stem shape: the hb200_conv_halo_supported shapes plus the small-image

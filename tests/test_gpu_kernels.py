@@ -417,9 +417,12 @@ def test_conv_s2_block_entry(hb, B, H, W):
 HALO_CASES = [(3, 32, 32, 32, 32), (2, 16, 16, 64, 64), (5, 16, 8, 32, 32), (600, 32, 32, 32, 32)]
 
 
-@pytest.fixture(params=[1, 0], ids=["tma", "cp_async"])
+@pytest.fixture(params=[1, 0, 2, 3, 4, 5],
+                ids=["default", "cp_async", "tma_swizzled", "tma_warp_specialised", "tma_ws_swizzled", "tma_slabs"])
 def halo_loader(hb, request):
-    """both halo load paths of the forward / dgrad halo kernels: TMA box copies (default) and the cp.async gather"""
+    """the halo load paths of the forward / dgrad halo kernels: the per-layer default, the cp.async gather, TMA copies of
+    whole pixel rows into the swizzled K-major layout (three pre-shifted copies per tile), the warp-specialised pipeline
+    (slabs / swizzled rows) and plain TMA box copies of 16-byte channel slabs"""
     lib = hb.load()
     prev = lib.hb200_get_halo_tma()
     lib.hb200_set_halo_tma(request.param)
