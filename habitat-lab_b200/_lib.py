@@ -52,8 +52,13 @@ SIGNATURES = {
     "hb200_set_halo_tma": ("i", "i"),
     "hb200_get_halo_tma": ("i", ""),
     "hb200_conv_s2_supported": ("i", "iiiii"),
+    "hb200_conv_s2_wgrad_supported": ("i", "iiii"),
+    "hb200_conv_s2_wgrad": ("i", "ppp" + "iiiii" + "p"),
+    "hb200_unpack_s2_wgrad": ("i", "pp" + "ii" + "p"),
     "hb200_conv_s2_fwd": ("i", "pppp" + "pipi" + "iiiiii" + "p"),
     "hb200_conv_s2_dgrad": ("i", "ppppp" + "iiiiii" + "p"),
+    "hb200_set_wgrad_xtma": ("i", "i"),
+    "hb200_get_wgrad_xtma": ("i", ""),
     "hb200_set_tgemm_tma": ("i", "i"),
     "hb200_get_tgemm_tma": ("i", ""),
     "hb200_conv_halo_supported": ("i", "iiiii"),

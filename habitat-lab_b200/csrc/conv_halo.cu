@@ -373,9 +373,15 @@ struct HaloWgradArgs {
   int B, H, W, ntiles;
 };
 
-template <int C, int N, int KH, int KW, int PAD>
+// XMODE: how the x halo reaches shared memory.  0 = registers / cp.async (below).  1 = one 5-D TMA box over x viewed as
+// [B, H, C/8, W, 8] (box = 8 channels x HWD pixels x C/8 chunks x halo rows = exactly the [row][chunk][pixel] layout the
+// shifted descriptors read).  2 = the same over the 2x2 SPACE-TO-DEPTH view of a tensor with C/4 real channels: a
+// 3x3 stride-2 pad-1 conv of x is a 2x2 stride-1 pad-1 conv of the view (csrc/conv_s2.cu), whose block row `by` is image
+// rows 2by, 2by+1 -- the box simply covers twice the rows of the real tensor with (dx, c) as the chunk dimension.
+template <int C, int N, int KH, int KW, int PAD, int XMODE = 0>
 __global__ void __launch_bounds__(128)
-conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMap tmap_dy) {
+conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMap tmap_dy,
+                       const __grid_constant__ CUtensorMap tmap_x) {
   constexpr int CJ = C / 8, HWD = TW + KW - 1;
   constexpr int P = HWD * 16, RP = CJ * P;
   constexpr int MT = (KH * CJ + 15) / 16;                  // 128-row M tiles over the (r, cj) row blocks
@@ -397,6 +403,7 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5;
   const CUtensorMap* const tmap_p = &tmap_dy;   // param-space address (never through a by-reference lambda capture)
+  const CUtensorMap* const tmap_xp = &tmap_x;
 
   if (tid == 0) {
     mbar_init(&mma_bar[0], 1);
@@ -425,7 +432,7 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   // kernel below).
   // Register staging pays while the halo is <= 8 vectors per thread (C <= 32: 0.211 -> 0.165 ms per layer, stem 0.79 ->
   // 0.67); for C = 64 (12 vectors, 128 registers) the lost occupancy costs more than the LDGSTS wavefronts: cp.async there.
-  constexpr bool kRegStage = HROWS_LOAD * CJ * HWD <= 128 * 8;
+  constexpr bool kRegStage = XMODE == 0 && HROWS_LOAD * CJ * HWD <= 128 * 8;
   HaloRegs<C, KH, KW, PAD, kRegStage ? HROWS_LOAD : 1, 128> xr;   // the x halo of the NEXT tile, in flight in registers
   auto fetch_x = [&](int tile) {
     if (!kRegStage) return;
@@ -433,15 +440,20 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
     tile_coords(tile, b, oh0, ow0);
     xr.load(reinterpret_cast<const __nv_bfloat16*>(a.x), tid, b, oh0, ow0, a.H, a.W);
   };
-  auto commit_tile = [&, tmap_p](int tile, int st) {   // stage `st` is free: x halo registers -> smem, dy tile by TMA
+  auto commit_tile = [&, tmap_p, tmap_xp](int tile, int st) {   // stage `st` is free: x halo -> smem, dy tile by TMA
     int b, oh0, ow0;
     tile_coords(tile, b, oh0, ow0);
     const uint32_t sd = sbase + st * STAGE;
-    if (kRegStage) xr.store(sd + DY_BYTES, tid);
-    else load_halo<C, KH, KW, PAD, HROWS_LOAD>(a.x, sd + DY_BYTES, b, oh0, ow0, a.H, a.W);
+    if (XMODE == 0) {
+      if (kRegStage) xr.store(sd + DY_BYTES, tid);
+      else load_halo<C, KH, KW, PAD, HROWS_LOAD>(a.x, sd + DY_BYTES, b, oh0, ow0, a.H, a.W);
+    }
     if (tid == 0) {
-      mbar_expect_tx(&dy_bar[st], (uint32_t)DY_BYTES);
+      mbar_expect_tx(&dy_bar[st], (uint32_t)(DY_BYTES + (XMODE ? HROWS_LOAD * RP : 0)));
       tma_load_4d(sd, tmap_p, &dy_bar[st], 0, ow0, oh0, b);
+      // coordinates (channel-in-chunk, pixel column, chunk, row, frame); space-to-depth: rows of the REAL tensor
+      if (XMODE == 1) tma_load_5d(sd + DY_BYTES, tmap_xp, &dy_bar[st], 0, ow0 - PAD, 0, oh0 - PAD, b);
+      if (XMODE == 2) tma_load_5d(sd + DY_BYTES, tmap_xp, &dy_bar[st], 0, ow0 - PAD, 0, 2 * (oh0 - PAD), b);
     }
   };
   const int first = blockIdx.x, stride = gridDim.x;
@@ -1409,7 +1421,7 @@ static int launch_halo_sw(const HaloArgs& a, cudaStream_t st) {
   return HB200_OK;
 }
 
-template <int C, int N, int KH, int KW, int PAD>
+template <int C, int N, int KH, int KW, int PAD, int XMODE = 0>
 static int launch_halo_wgrad(const HaloWgradArgs& a, cudaStream_t st) {
   constexpr int CJ = C / 8, HWD = TW + KW - 1, P = HWD * 16, RP = CJ * P;
   constexpr int MT = (KH * CJ + 15) / 16, RMAX = (MT * 16 + CJ - 1) / CJ, HROWS = TH - 1 + RMAX;
@@ -1433,7 +1445,28 @@ static int launch_halo_wgrad(const HaloWgradArgs& a, cudaStream_t st) {
     set_last_error("conv_halo_wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return HB200_ERR_CUDA;
   }
-  auto kern = conv_halo_wgrad_kernel<C, N, KH, KW, PAD>;
+  // x halo by TMA: x bf16 [B, Hx, Wx, Cx] seen as (8 | pixel column | chunk | row | frame).  XMODE 2: a.H, a.W are the
+  // dims of the space-to-depth view; the real tensor has 2H x 2W pixels of C/4 channels, "pixel column" steps over
+  // pixel PAIRS (2 * Cx * 2 bytes) and a row of the view's chunks = the (dx, c) run of one image row
+  CUtensorMap tmap_x = tmap;
+  if (XMODE != 0) {
+    const int cx = XMODE == 2 ? C / 4 : C, hx = XMODE == 2 ? 2 * a.H : a.H, wx = XMODE == 2 ? 2 * a.W : a.W;
+    const int chunks_per_row = XMODE == 2 ? CJ / 2 : CJ, col_bytes = (XMODE == 2 ? 2 : 1) * cx * 2;
+    const cuuint64_t xd[5] = {8u, (cuuint64_t)a.W, (cuuint64_t)chunks_per_row, (cuuint64_t)hx, (cuuint64_t)a.B};
+    const cuuint64_t xs[4] = {(cuuint64_t)col_bytes, 16u, (cuuint64_t)wx * cx * 2, (cuuint64_t)hx * wx * cx * 2};
+    constexpr int HROWS_LOAD = TH + KH - 1;
+    const cuuint32_t xb[5] = {8u, (cuuint32_t)HWD, (cuuint32_t)chunks_per_row,
+                              (cuuint32_t)(XMODE == 2 ? 2 * HROWS_LOAD : HROWS_LOAD), 1u};
+    const cuuint32_t xe[5] = {1u, 1u, 1u, 1u, 1u};
+    const CUresult rx = enc(&tmap_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)a.x, xd, xs, xb, xe,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rx != CUDA_SUCCESS) {
+      set_last_error("conv_halo_wgrad: cuTensorMapEncodeTiled (x halo) failed (%d)", (int)rx);
+      return HB200_ERR_CUDA;
+    }
+  }
+  auto kern = conv_halo_wgrad_kernel<C, N, KH, KW, PAD, XMODE>;
   static int cache = 0;
   if (cache == 0) HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   constexpr int raw = KW * MT * N;
@@ -1441,7 +1474,7 @@ static int launch_halo_wgrad(const HaloWgradArgs& a, cudaStream_t st) {
   const int per_sm = blocks_per_sm((const void*)kern, smem, tcols, &cache);
   int grid = kNumSMs * per_sm;
   if (grid > a.ntiles) grid = a.ntiles;
-  kern<<<grid, 128, smem, st>>>(a, tmap);
+  kern<<<grid, 128, smem, st>>>(a, tmap, tmap_x);
   HB_LAUNCH_OK();
   count_launch(1);
   return HB200_OK;
@@ -1494,6 +1527,8 @@ using namespace hb200;
 
 // halo loads by TMA (default) or by the cp.async gather kernel (HB200_NO_HALO_TMA=1, or hb200_set_halo_tma(0) from tests)
 static int g_halo_tma = getenv("HB200_NO_HALO_TMA") == nullptr ? 1 : 0;
+// 4096 frames: 32-channel layers 172 -> 159 us, 64-channel 169 -> 133 us, stem 671 -> 650 us with the TMA box
+static int g_wgrad_xtma = getenv("HB200_WGRAD_XTMA") ? atoi(getenv("HB200_WGRAD_XTMA")) : 1;
 extern "C" int hb200_set_halo_tma(int enable) {
   g_halo_tma = enable;   // 0 cp.async gather, 1 best per layer (default), 2 swizzled rows, 3 warp-specialised slabs, 4 both, 5 plain TMA slabs
   return HB200_OK;
@@ -1584,6 +1619,40 @@ extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb20
   return launch_halo<16, 32, 4, 4, 2, 0>(a, st);
 }
 
+// accumulator of the space-to-depth weight gradient [((ky*2+kx)*4 + dy*2+dx) * ci + c][co] -> OIHW 3x3 gradient
+__global__ void unpack_s2_wgrad_kernel(const float* __restrict__ acc, float* __restrict__ dw, int co, int ci) {
+  const int total = co * ci * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int s = i % 3, r = (i / 3) % 3, c = (i / 9) % ci, o = i / (9 * ci);
+    const int ky = r == 0 ? 0 : 1, dy = r == 0 ? 1 : r - 1, kx = s == 0 ? 0 : 1, dx = s == 0 ? 1 : s - 1;
+    dw[i] = acc[((size_t)((ky * 2 + kx) * 4 + dy * 2 + dx) * ci + c) * co + o];
+  }
+}
+
+/* weight gradient of a 3x3 stride-2 pad-1 conv as the 2x2 stride-1 weight gradient over the space-to-depth view of x
+ * (x halo: one 5-D TMA box per tile).  x bf16 [B,H,W,C] (the twin), dy bf16 [B,H/2,W/2,N]; dw_acc f32 [16*C][N]
+ * pre-zeroed, rows ((ky*2+kx)*4 + dy*2+dx)*C + c; hb200_unpack_s2_wgrad extracts the 9 real taps. */
+extern "C" int hb200_conv_s2_wgrad_supported(int c, int n, int h, int w) {
+  return c == 32 && n == 64 && h % (2 * TH) == 0 && w % (2 * TW) == 0;
+}
+extern "C" int hb200_conv_s2_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc, int batch, int h, int w,
+                                   int c, int n, hb200_stream_t stream) {
+  HB_CHECK_ARG(x && dy && dw_acc && batch > 0, "conv_s2_wgrad: null pointer");
+  HB_CHECK_ARG(hb200_conv_s2_wgrad_supported(c, n, h, w), "conv_s2_wgrad: unsupported shape C=%d N=%d %dx%d", c, n, h, w);
+  HaloWgradArgs a;
+  a.x = (const __nv_bfloat16*)x; a.dy = (const __nv_bfloat16*)dy; a.dw = dw_acc;
+  a.B = batch; a.H = h / 2; a.W = w / 2;
+  a.ntiles = batch * (a.H / TH) * (a.W / TW);
+  return launch_halo_wgrad<128, 64, 2, 2, 1, 2>(a, (cudaStream_t)stream);
+}
+extern "C" int hb200_unpack_s2_wgrad(const float* dw_acc, float* dw_oihw, int co, int ci, hb200_stream_t stream) {
+  HB_CHECK_ARG(dw_acc && dw_oihw && co > 0 && ci > 0, "unpack_s2_wgrad: bad args");
+  unpack_s2_wgrad_kernel<<<cdiv(co * ci * 9, 256), 256, 0, (cudaStream_t)stream>>>(dw_acc, dw_oihw, co, ci);
+  HB_LAUNCH_OK();
+  count_launch(1);
+  return HB200_OK;
+}
+
 extern "C" int hb200_conv_halo_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc, int batch, int h,
                                      int w, int c, int n, int k, hb200_stream_t stream) {
   HB_CHECK_ARG(x && dy && dw_acc, "conv_halo_wgrad: null pointer");
@@ -1601,7 +1670,15 @@ extern "C" int hb200_conv_halo_wgrad(const hb200_bf16* x, const hb200_bf16* dy, 
   a.B = batch; a.H = h; a.W = w;
   a.ntiles = batch * (h / TH) * (w / TW);
   cudaStream_t st = (cudaStream_t)stream;
+  // x halo: 0 = registers (C <= 32) / cp.async, 1 = one 5-D TMA box per tile (HB200_WGRAD_XTMA / hb200_set_wgrad_xtma)
+  if (g_wgrad_xtma) {
+    if (k == 3 && c == 32) return launch_halo_wgrad<32, 32, 3, 3, 1, 1>(a, st);
+    if (k == 3 && c == 64) return launch_halo_wgrad<64, 64, 3, 3, 1, 1>(a, st);
+    return launch_halo_wgrad<16, 32, 4, 4, 2, 1>(a, st);
+  }
   if (k == 3 && c == 32) return launch_halo_wgrad<32, 32, 3, 3, 1>(a, st);
   if (k == 3 && c == 64) return launch_halo_wgrad<64, 64, 3, 3, 1>(a, st);
   return launch_halo_wgrad<16, 32, 4, 4, 2>(a, st);
 }
+extern "C" int hb200_set_wgrad_xtma(int on) { g_wgrad_xtma = on ? 1 : 0; return HB200_OK; }
+extern "C" int hb200_get_wgrad_xtma(void) { return g_wgrad_xtma; }

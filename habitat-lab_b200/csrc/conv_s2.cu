@@ -107,15 +107,6 @@ __device__ __forceinline__ void s2_gn_stats_chunk(const float (&acc)[32], int la
   }
 }
 
-__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
-        "r"(c4)
-      : "memory");
-}
-
 struct S2Args {
   const void* wimg;            // weight image (forward: fp16 [9][C/8][N][8]; dgrad: bf16 [9][N/8][C][8])
   void* ya; void* yb;          // forward outputs fp16 [B,Ho,Wo,NA] / [B,Ho,Wo,NB]; dgrad: ya = dx bf16 [B,H,W,C]

@@ -166,6 +166,14 @@ __device__ __forceinline__ void tma_load_4d(uint32_t smem_dst, const void* tmap,
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
+      : "memory");
+}
 // 2-D box load (row-major matrices: c0 = column / k index, c1 = row)
 __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
   asm volatile(

@@ -188,6 +188,19 @@ def conv_s2_fwd(x, wimg, ya, yb, batch, h, w, c, na, nb, stats_a=None, groups_a=
          int(groups_b), batch, h, w, c, na, nb)
 
 
+def conv_s2_wgrad_supported(c, n, h, w) -> bool:
+    return bool(load().hb200_conv_s2_wgrad_supported(int(c), int(n), int(h), int(w)))
+
+
+def conv_s2_wgrad(x_bf16, dy, dw_acc, batch, h, w, c, n):
+    """dw_acc f32 [16*c, n] (pre-zeroed): weight gradient of the 3x3 stride-2 conv over the space-to-depth view"""
+    call("hb200_conv_s2_wgrad", ptr(x_bf16), ptr(dy), ptr(dw_acc), batch, h, w, c, n)
+
+
+def unpack_s2_wgrad(dw_acc, dw_oihw):
+    call("hb200_unpack_s2_wgrad", ptr(dw_acc), ptr(dw_oihw), dw_oihw.shape[0], dw_oihw.shape[1])
+
+
 def conv_s2_dgrad(dya, dyb, wimg_t, dx, batch, h, w, c, na, nb, addend=None):
     call("hb200_conv_s2_dgrad", ptr(dya), ptr(dyb), ptr(wimg_t), ptr(addend), ptr(dx), batch, h, w, c, na, nb)
 

@@ -300,6 +300,7 @@ class _Conv:
         self.stem_s2d = False   # 7x7 s2 stem as a 4x4 s1 conv over the space-to-depth input
         self.s2_pair = None     # 3x3 stride-2 conv whose block's 1x1 stride-2 downsample conv shares its kernel (conv_s2.cu)
         self.s2_main = None     # ... and the downsample conv's pointer back
+        self.dw_s2 = None
         self.wh = self.wht = None
         self._wd = self._gd = None
 
@@ -321,6 +322,8 @@ class _Conv:
             self.wh = torch.empty(9 * self.ci * ntot, dtype=F16, device=dev)
             self.wht = torch.empty(9 * self.ci * ntot, dtype=BF16, device=dev)
             self._wcat = torch.zeros(ntot, self.ci, 3, 3, device=dev)
+            self.dw_s2 = (torch.empty(16 * self.ci, self.co, device=dev)
+                          if ops.conv_s2_wgrad_supported(self.ci, self.co, self.in_hw[0], self.in_hw[1]) else None)
         self.wp = torch.empty(ops.packed_weight_elems(self.co, self.ci, self.k, self.k), dtype=F16, device=dev)
         self.wt = (torch.empty(ops.packed_weight_elems(self.ci, self.co, self.k, self.k), dtype=BF16, device=dev)
                    if need_dgrad else None)
@@ -623,6 +626,10 @@ class EncoderEngine:
                 if c.stem_s2d:
                     ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.out_hw[0], c.out_hw[1], 16, c.co, 4)
                     ops.unpack_stem_wgrad(c.dw_acc, c.w.grad)
+                elif c.s2_pair is not None and c.dw_s2 is not None:   # 3x3 stride-2 conv over the space-to-depth view
+                    c.dw_s2.zero_()
+                    ops.conv_s2_wgrad(x, dy, c.dw_s2, B, c.in_hw[0], c.in_hw[1], c.ci, c.co)
+                    ops.unpack_s2_wgrad(c.dw_s2, c.grad_target())
                 else:
                     if c.halo or c.halo_w:
                         ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, 3)

@@ -227,6 +227,10 @@ int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb200_bf16* y, 
  * rows, 5 = plain TMA slabs.  All are kept parity-tested (tests/test_gpu_kernels.py::test_conv_halo_3x3). */
 int hb200_set_halo_tma(int mode);
 int hb200_get_halo_tma(void);
+/* x halo of the halo weight-gradient kernels: 0 = register staging / cp.async, 1 = one 5-D TMA box per tile (default;
+ * HB200_WGRAD_XTMA=0 in the environment selects 0 at load time) */
+int hb200_set_wgrad_xtma(int on);
+int hb200_get_wgrad_xtma(void);
 
 /* 1 if hb200_conv_halo_wgrad serves this 3x3 / stem shape: the hb200_conv_halo_supported shapes plus the small-image
  * layers (8x8 and 4x4 inputs, c % 32 == 0, n % 128 == 0: layer3 / layer4 / compression of
@@ -244,6 +248,13 @@ int hb200_conv_halo_wgrad_supported(int c, int n, int k, int h, int w);
  *            packed with mode 1 (c = NA + NB, n = C).
  * Supported: C = 32, NA = NB = 64, H % 32 == 0, W % 16 == 0 (layer2.0 of the resnet18 encoder at 256x256 input). */
 int hb200_conv_s2_supported(int c, int na, int nb, int h, int w);
+/* weight gradient of the 3x3 stride-2 branch over the same space-to-depth view (x halo = one 5-D TMA box per tile):
+ * x bf16 [B,H,W,C] (twin of the forward input), dy bf16 [B,H/2,W/2,N]; dw_acc f32 [16*C][N], pre-zeroed, rows
+ * ((ky*2+kx)*4 + dy*2+dx)*C + c; hb200_unpack_s2_wgrad writes the 9 real taps as OIHW.  C = 32, N = 64. */
+int hb200_conv_s2_wgrad_supported(int c, int n, int h, int w);
+int hb200_conv_s2_wgrad(const hb200_bf16* x, const hb200_bf16* dy, float* dw_acc, int batch, int h, int w, int c, int n,
+                        hb200_stream_t stream);
+int hb200_unpack_s2_wgrad(const float* dw_acc, float* dw_oihw, int co, int ci, hb200_stream_t stream);
 int hb200_conv_s2_fwd(const hb200_f16* x, const hb200_f16* wimg, hb200_f16* ya, hb200_f16* yb, double* stats_a,
                       int groups_a, double* stats_b, int groups_b, int batch, int h, int w, int c, int na, int nb,
                       hb200_stream_t stream);

@@ -412,6 +412,16 @@ def test_conv_s2_block_entry(hb, B, H, W):
     ops.conv_s2_dgrad(bf(nhwc(dya)), bf(nhwc(dyb)), img_t, dx, B, H, W, C, NA, NB, addend=addend)
     torch.cuda.synchronize()
     torch.testing.assert_close(nchw(dx.float()), dx_ref + nchw(addend.float()), rtol=1e-2, atol=2 * tol)
+    # weight gradient of the 3x3 branch over the same view (x halo by one 5-D TMA box per tile)
+    assert ops.conv_s2_wgrad_supported(C, NA, H, W)
+    acc = torch.zeros(16 * C, NA, device=DEV)
+    ops.conv_s2_wgrad(bf(nhwc(x)), bf(nhwc(dya)), acc, B, H, W, C, NA)
+    dw = torch.empty_like(wa)
+    ops.unpack_s2_wgrad(acc, dw)
+    torch.cuda.synchronize()
+    dw_ref = torch.nn.grad.conv2d_weight(bf(x).float(), wa.shape, bf(dya).float(), stride=2, padding=1)
+    torch.testing.assert_close(dw, dw_ref, rtol=2e-3, atol=2e-3 * dw_ref.abs().max().item())
+    # the 7 structurally-zero sub-taps of the 2x2 x 2x2 accumulator are never unpacked; the 9 real ones cover dw
 
 
 HALO_CASES = [(3, 32, 32, 32, 32), (2, 16, 16, 64, 64), (5, 16, 8, 32, 32), (600, 32, 32, 32, 32)]
@@ -430,8 +440,18 @@ def halo_loader(hb, request):
     lib.hb200_set_halo_tma(prev)
 
 
+@pytest.fixture(params=[0, 1], ids=["x_regs", "x_tma"])
+def wgrad_x(hb, request):
+    """x halo of the halo weight-gradient kernels: register staging / cp.async, or one 5-D TMA box per tile"""
+    lib = hb.load()
+    prev = lib.hb200_get_wgrad_xtma()
+    lib.hb200_set_wgrad_xtma(request.param)
+    yield request.param
+    lib.hb200_set_wgrad_xtma(prev)
+
+
 @pytest.mark.parametrize("B,H,W,C,N", HALO_CASES)
-def test_conv_halo_3x3(hb, halo_loader, B, H, W, C, N):
+def test_conv_halo_3x3(hb, halo_loader, wgrad_x, B, H, W, C, N):
     """halo kernels (one input load per tile, taps by descriptor shift) vs fp32 conv of the same rounded operands"""
     from habitat_lab_b200 import ops
 
@@ -500,7 +520,7 @@ def test_conv_halo_wgrad_small_images(hb, B, HW, C, N):
 
 
 @pytest.mark.parametrize("B,Hp,Wp", [(2, 128, 128), (3, 64, 32)])
-def test_conv_halo_stem_s2d(hb, halo_loader, B, Hp, Wp):
+def test_conv_halo_stem_s2d(hb, halo_loader, wgrad_x, B, Hp, Wp):
     """7x7 stride-2 pad-3 stem == 4x4 stride-1 conv over the space-to-depth input"""
     from habitat_lab_b200 import ops
 

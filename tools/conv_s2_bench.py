@@ -63,3 +63,9 @@ print(f"B={B}: forward  fused {timed(lambda: ops.conv_s2_fwd(x, img, ya, yb, B, 
       f"   gather (2 launches) {timed(gather_fwd):7.1f} us")
 print(f"B={B}: dgrad    fused {timed(lambda: ops.conv_s2_dgrad(dya, dyb, img_t, dx, B, H, W, C, NA, NB)):7.1f} us"
       f"   gather (2 launches) {timed(gather_dgrad):7.1f} us")
+
+xb = x.bfloat16()
+acc = torch.zeros(16 * C, NA, device=dev)
+acc_g = torch.zeros(9 * C, NA, device=dev)
+print(f"B={B}: wgrad 3x3 s2d  {timed(lambda: ops.conv_s2_wgrad(xb, dya, acc, B, H, W, C, NA)):7.1f} us"
+      f"   gather {timed(lambda: ops.conv_wgrad(xb, dya, acc_g, s_a)):7.1f} us")

@@ -47,3 +47,21 @@ for H, C in ((32, 32), (16, 64)):
         print(f"{C}ch {H}x{H} B={B} loader={mode}: fwd {tf:7.1f} us ({flop / tf / 1e6:6.1f} TF/s)  dgrad {td:7.1f} us "
               f"({flop / td / 1e6:6.1f} TF/s)")
 lib.hb200_set_halo_tma(1)
+
+# weight gradients: x halo through registers / cp.async vs one 5-D TMA box per tile
+for H, C in ((32, 32), (16, 64)):
+    x = torch.randn(B, H, H, C, device=dev).bfloat16()
+    dy = torch.randn(B, H, H, C, device=dev).bfloat16()
+    acc = torch.zeros(9 * C, C, device=dev)
+    for xt in (0, 1):
+        lib.hb200_set_wgrad_xtma(xt)
+        t = timed(lambda: ops.conv_halo_wgrad(x, dy, acc, B, H, H, C, C, 3))
+        print(f"{C}ch {H}x{H} B={B} wgrad x_tma={xt}: {t:7.1f} us")
+x = torch.randn(B, 64, 64, 16, device=dev).bfloat16()
+dy = torch.randn(B, 64, 64, 32, device=dev).bfloat16()
+acc = torch.zeros(16 * 16, 32, device=dev)
+for xt in (0, 1):
+    lib.hb200_set_wgrad_xtma(xt)
+    t = timed(lambda: ops.conv_halo_wgrad(x, dy, acc, B, 64, 64, 16, 32, 4))
+    print(f"stem 16ch(s2d) 64x64 B={B} wgrad x_tma={xt}: {t:7.1f} us")
+lib.hb200_set_wgrad_xtma(0)
