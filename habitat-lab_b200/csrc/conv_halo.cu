@@ -1374,9 +1374,16 @@ static int launch_halo_ws(const HaloArgs& a, cudaStream_t st) {
   static int grid_cache = 0;
   if (grid_cache == 0) {
     HB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 192, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    // resident CTAs per SM from the static limits (registers of 192 threads, shared memory, TMEM columns); the
+    // occupancy API reported 1 for these kernels on the B200 boxes (ncu: grid 148 where 3 CTAs per SM fit)
+    cudaFuncAttributes fa;
+    HB_CUDA(cudaFuncGetAttributes(&fa, (const void*)kern));
+    const int regs = fa.numRegs > 0 ? fa.numRegs : 128;
+    int per_sm = 65536 / (((regs + 7) / 8 * 8) * 192);
+    const int by_smem = (int)((227 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+    if (by_smem < per_sm) per_sm = by_smem;
     if (per_sm > 512 / Cfg::TMEM_COLS) per_sm = 512 / Cfg::TMEM_COLS;
+    if (per_sm < 1) per_sm = 1;
     grid_cache = kNumSMs * per_sm;
   }
   const int grid = grid_cache < a.ntiles ? grid_cache : a.ntiles;
@@ -1588,11 +1595,15 @@ extern "C" int hb200_conv_halo(const hb200_bf16* x, const hb200_bf16* wimg, hb20
   const bool use_tma = g_halo_tma != 0;
   // Loader per layer (hb200_set_halo_tma): 1 = the measured best of the variants below (tools/halo_bench.py, 4096 frames):
   //   64 channels: warp-specialised + swizzled pixel-row copies  fwd 126 -> 93 us, dgrad 99 -> 88 us
-  //   32 channels: dgrad with swizzled copies 177 -> 146 us; forward stays on the 16-byte slabs (175 us vs 182 / 209)
+  //   32 channels: warp-specialised + swizzled copies  fwd 176 -> 140 us, dgrad 177 -> 143 us
   // 2 / 3 / 4 / 5 force swizzled copies / warp-specialised slabs / warp-specialised swizzled / plain slabs everywhere.
   if (g_halo_tma == 1 && k == 3 && c == 64)
     return mode == 0 ? launch_halo_ws<64, 64, 3, 3, 1, 0, 2, true>(a, st) : launch_halo_ws<64, 64, 3, 3, 1, 1, 2, true>(a, st);
-  if (g_halo_tma == 1 && k == 3 && c == 32 && mode == 1) return launch_halo_sw<32, 32, 1>(a, st);
+  if (g_halo_tma == 1 && k == 3 && c == 32)   // fwd 176 -> 140 us, dgrad 146 -> 143 us (two CTAs per SM, 3 stages each)
+    return mode == 0 ? launch_halo_ws<32, 32, 3, 3, 1, 0, 3, true>(a, st) : launch_halo_ws<32, 32, 3, 3, 1, 1, 3, true>(a, st);
+  if (g_halo_tma == 1 && k == 4 && mode == 0) return launch_halo_ws<16, 32, 4, 4, 2, 0, 6>(a, st);   // stem 564 -> 524 us
+  if (g_halo_tma == 6 && k == 3 && c == 32)   // experiment: 2 stages, three CTAs per SM (150 / 150 us: worse)
+    return mode == 0 ? launch_halo_ws<32, 32, 3, 3, 1, 0, 2, true>(a, st) : launch_halo_ws<32, 32, 3, 3, 1, 1, 2, true>(a, st);
   if (g_halo_tma == 4 && k == 3 && c == 32)
     return mode == 0 ? launch_halo_ws<32, 32, 3, 3, 1, 0, 3, true>(a, st) : launch_halo_ws<32, 32, 3, 3, 1, 1, 3, true>(a, st);
   if (g_halo_tma == 4 && k == 3 && c == 64)

@@ -411,9 +411,17 @@ S2EncodeFn s2_encode_fn() {
 }
 
 int s2_grid(const void* kern, size_t smem, int tmem_cols, int ntiles) {
+  // resident CTAs per SM from the static limits (the occupancy API under-reports these tcgen05 kernels: see conv_halo.cu)
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-  if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;   // TMEM columns are allocated per CTA, 512 per SM
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {
+    const int regs = fa.numRegs > 0 ? fa.numRegs : 128;
+    per_sm = 65536 / (((regs + 7) / 8 * 8) * 128);
+    const int by_smem = (int)((size_t)(228 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+    if (by_smem < per_sm) per_sm = by_smem;
+    if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+    if (per_sm < 1) per_sm = 1;
+  }
   const int grid = kNumSMs * per_sm;
   return grid < ntiles ? grid : ntiles;
 }

@@ -40,12 +40,25 @@ for H, C in ((32, 32), (16, 64)):
     dx = torch.empty_like(dy)
     st = torch.zeros(B, 16, 2, device=dev, dtype=torch.float64)
     flop = 2.0 * B * H * H * C * C * 9
-    for mode in (4, 3, 1, 2, 0):
+    for mode in (6, 4, 3, 1, 2, 0, 5):
         lib.hb200_set_halo_tma(mode)
         tf = timed(lambda: ops.conv_halo(x, wh, y, B, H, H, C, C, 3, 0, gn_stats=st, gn_groups=16))
         td = timed(lambda: ops.conv_halo(dy, wt, dx, B, H, H, C, C, 3, 1))
         print(f"{C}ch {H}x{H} B={B} loader={mode}: fwd {tf:7.1f} us ({flop / tf / 1e6:6.1f} TF/s)  dgrad {td:7.1f} us "
               f"({flop / td / 1e6:6.1f} TF/s)")
+lib.hb200_set_halo_tma(1)
+
+# stem forward (7x7 s2 as 4x4 s1 over the space-to-depth input, 16 -> 32 channels @ 64x64)
+x = torch.randn(B, 64, 64, 16, device=dev).half()
+w = torch.randn(32, 4, 7, 7, device=dev) * 0.05
+wh = torch.empty(16 * 16 * 32, device=dev, dtype=torch.float16)
+ops.pack_halo_weight(w, wh, 16, 32, 4, 2)
+y = torch.empty(B, 64, 64, 32, device=dev, dtype=torch.float16)
+st = torch.zeros(B, 16, 2, device=dev, dtype=torch.float64)
+for mode in (3, 1, 0):
+    lib.hb200_set_halo_tma(mode)
+    t = timed(lambda: ops.conv_halo(x, wh, y, B, 64, 64, 16, 32, 4, 0, gn_stats=st, gn_groups=16))
+    print(f"stem 64x64 B={B} loader={mode}: fwd {t:7.1f} us")
 lib.hb200_set_halo_tma(1)
 
 # weight gradients: x halo through registers / cp.async vs one 5-D TMA box per tile
