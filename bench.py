@@ -695,7 +695,24 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
         flop = 2.0 * B * c.out_hw[0] * c.out_hw[1] * c.co * (c.ci_real // c.conv_groups) * c.k * c.k
         xin, y = inputs[id(c)], ws[f"y{i}"]
         stats = ws[f"st{i}"]
-        if c.stem_s2d:
+        fused_into = None
+        if getattr(c, "s2_pair", None) is not None:
+            # stride-2 block entry: ONE launch serves this 3x3 conv and the block's 1x1 downsample conv (conv_s2.cu);
+            # its time is booked here, the downsample row below carries only its FLOPs (and its own weight gradient)
+            d = c.s2_pair
+            kd = idx[id(d)]
+            yd, std = ws[f"y{kd}"], ws[f"st{kd}"]
+            tf = t_ms(lambda: ops.conv_s2_fwd(xin, c.wh, y, yd, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, d.co,
+                                              stats_a=stats, groups_a=c.groups, stats_b=std, groups_b=d.groups))
+            if c.dw_s2 is not None:
+                tw = t_ms(lambda: ops.conv_s2_wgrad(xin, y, c.dw_s2, B, c.in_hw[0], c.in_hw[1], c.ci, c.co))
+            else:
+                tw = t_ms(lambda: ops.conv_wgrad(xin, y, c.dw_acc, s))
+        elif getattr(c, "s2_main", None) is not None:
+            fused_into = c.s2_main
+            tf = 0.0
+            tw = t_ms(lambda: ops.conv_wgrad(xin, y, c.dw_acc, s))
+        elif c.stem_s2d:
             tf = t_ms(lambda: ops.conv_halo(xin, c.wh, y, B, c.out_hw[0], c.out_hw[1], 16, c.co, 4, 0, gn_stats=stats, gn_groups=c.groups))
             tw = t_ms(lambda: ops.conv_halo_wgrad(xin, y, c.dw_acc, B, c.out_hw[0], c.out_hw[1], 16, c.co, 4))
         elif c.halo:
@@ -712,7 +729,14 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
         td = None
         if c is not eng.stem:
             dx = ws["g0"][: xin.numel()].view_as(xin)
-            td = t_ms(lambda: eng._dgrad(c, y, dx, B))
+            if getattr(c, "s2_pair", None) is not None:
+                d = c.s2_pair
+                yd = ws[f"y{idx[id(d)]}"]
+                td = t_ms(lambda: ops.conv_s2_dgrad(y, yd, c.wht, dx, B, c.in_hw[0], c.in_hw[1], c.ci, c.co, d.co))
+            elif fused_into is not None:
+                td = 0.0
+            else:
+                td = t_ms(lambda: eng._dgrad(c, y, dx, B))
             per["dgrad"][0] += flop; per["dgrad"][1] += td
         # speed of light of each launch: max(tensor time, HBM time of reading both operands / writing the result once)
         nbytes = 2.0 * (xin.numel() + y.numel())
@@ -720,13 +744,16 @@ def kernel_roofline(hb, ops, policy, st, dev, peaks):
         bound = "tensor" if flop / (peaks["bf16"] * 1e12) > nbytes / (peaks["hbm"] * 1e9) else "hbm"
         sol[0] += t_sol * (2 if td is None else 3)
         sol[1] += tf + tw + (td or 0.0)
-        detail.append({"conv": f"{c.ci_real}->{c.co} k{c.k}s{c.stride} @{c.in_hw[0]}", "gflop": flop * 1e-9,
+        detail.append({"conv": f"{c.ci_real}->{c.co} k{c.k}s{c.stride} @{c.in_hw[0]}"
+                               + (" (fwd / dgrad fused into the 3x3 stride-2 launch)" if fused_into is not None else ""),
+                       "gflop": flop * 1e-9,
                        "mbytes": nbytes * 1e-6, "bound": bound, "sol_ms": t_sol,
                        "fwd_ms": tf, "dgrad_ms": td, "wgrad_ms": tw})
     flops = sum(v[0] for v in per.values())
     ms = sum(v[1] for v in per.values())
     achieved = flops / (ms * 1e-3) * 1e-12
-    return {"kernel": "conv_halo_kernel / conv_igemm_kernel / conv_*wgrad_kernel (tcgen05, all 21 convs of one 4096-frame minibatch pass)",
+    return {"kernel": "conv_halo_ws_kernel / conv_s2_*_kernel / conv_igemm_kernel / conv_*wgrad_kernel (tcgen05, all 21 convs of "
+                      "one 4096-frame minibatch pass, forward + dgrad + wgrad)",
             "bound": "tensor", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
             "frac": achieved / peaks["bf16"], "peak_source": peaks["src"] + " (burst: kernels timed alone)",
             "traffic": _ncu_traffic(),
