@@ -472,6 +472,14 @@ class EncoderEngine:
         if self._dev != dev:
             for c in self.convs:
                 c.alloc_weights(dev, need_dgrad=c is not self.stem)
+            # every weight-gradient accumulator in ONE arena: one memset per backward pass instead of one per conv
+            accs = [(c, nm) for c in self.convs for nm in ("dw_acc", "dw_s2") if getattr(c, nm, None) is not None]
+            self._dw_arena = torch.empty(sum(getattr(c, nm).numel() for c, nm in accs), device=dev)
+            off = 0
+            for c, nm in accs:
+                t = getattr(c, nm)
+                setattr(c, nm, self._dw_arena[off: off + t.numel()].view_as(t))
+                off += t.numel()
             self._dev, self._ws, self._packed_key = dev, {}, None
         key = (B, train)
         if key in self._ws:
@@ -537,10 +545,19 @@ class EncoderEngine:
         during a rollout) with an unchanged key reuse the packed weight images instead of re-packing every tensor per
         step; training forwards always re-pack."""
         ws = self._ensure(B, dev, train)
-        if train or wkey is None or wkey != self._packed_key:
+        packed = None
+        if train:
+            # ~40 tiny packing launches (launch-bound, 0.17 ms) ride on the side stream under the input prep, which
+            # does not read the weights
+            with self.side.after_main():
+                self.pack_weights()
+                packed = self.side.mark()
+            self._packed_key = wkey
+        elif wkey is None or wkey != self._packed_key:
             self.pack_weights()
             self._packed_key = wkey
         x0_writer(ws["x0"], ws.get("x0_b"))
+        self.side.wait(packed)
         idx = {id(c): i for i, c in enumerate(self.convs)}
         ws["st_all"].zero_()
 
@@ -622,12 +639,10 @@ class EncoderEngine:
 
         def wgrad(c, x, dy):
             with side.after_main():
-                c.dw_acc.zero_()
                 if c.stem_s2d:
                     ops.conv_halo_wgrad(x, dy, c.dw_acc, B, c.out_hw[0], c.out_hw[1], 16, c.co, 4)
                     ops.unpack_stem_wgrad(c.dw_acc, c.w.grad)
                 elif c.s2_pair is not None and c.dw_s2 is not None:   # 3x3 stride-2 conv over the space-to-depth view
-                    c.dw_s2.zero_()
                     ops.conv_s2_wgrad(x, dy, c.dw_s2, B, c.in_hw[0], c.in_hw[1], c.ci, c.co)
                     ops.unpack_s2_wgrad(c.dw_s2, c.grad_target())
                 else:
@@ -642,6 +657,8 @@ class EncoderEngine:
                 if dy.data_ptr() == dy_bufs[i].data_ptr():
                     dy_busy[i] = ev
 
+        with side.after_main():
+            self._dw_arena.zero_()   # all weight-gradient accumulators (split-K / per-tile red.add targets)
         g_bufs = [ws["g0"], ws["g1"]]
         cur = 0
         like = lambda buf, t: buf[: t.numel()].view_as(t)  # noqa: E731
