@@ -9,7 +9,8 @@ Adam).  value = world * T * N / t_step  (the reference's perf/fps definition,
 habitat-baselines/habitat_baselines/rl/ppo/ppo_trainer.py:595-598, learner part).
 
     python bench.py --gpus 1 --steps K --warmup W           # this repo's sm_100a path
-    python bench.py --impl reference ...                     # the reference's CPU learner (oracle port)
+    python bench.py --impl reference ...                     # the UNMODIFIED reference classes (baseline/_ref) on the CPU
+    python bench.py --impl torch_cuda ...                    # ... and on CUDA (TF32 cuDNN, cudnn.benchmark; DDP + NCCL at N > 1)
     torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU, NCCL
 
 Prints ONE JSON line (rank 0).
