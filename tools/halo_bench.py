@@ -58,7 +58,8 @@ st = torch.zeros(B, 16, 2, device=dev, dtype=torch.float64)
 for mode in (3, 1, 0):
     lib.hb200_set_halo_tma(mode)
     t = timed(lambda: ops.conv_halo(x, wh, y, B, 64, 64, 16, 32, 4, 0, gn_stats=st, gn_groups=16))
-    print(f"stem 64x64 B={B} loader={mode}: fwd {t:7.1f} us")
+    t0 = timed(lambda: ops.conv_halo(x, wh, y, B, 64, 64, 16, 32, 4, 0))
+    print(f"stem 64x64 B={B} loader={mode}: fwd {t:7.1f} us   (without the GroupNorm sums: {t0:7.1f} us)")
 lib.hb200_set_halo_tma(1)
 
 # weight gradients: x halo through registers / cp.async vs one 5-D TMA box per tile
