@@ -391,14 +391,20 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   constexpr int HALO_BYTES = HROWS * RP;
   constexpr int DY_BYTES = 128 * N * 2;                    // [pixel][N channels]: one swizzled row per pixel (TMA)
   constexpr int STAGE = (DY_BYTES + HALO_BYTES + 1023) / 1024 * 1024;   // dy tile first: swizzle atoms need 1024-byte alignment
+  // Ring depth.  With the x halo AND the dy tile arriving by TMA the loop is one thread: wait tile, issue MMAs; two stages
+  // exposed the ~1.5 us load latency once per tile (the MMAs of a 32-channel tile take 0.2 us): prefetch NSW-1 tiles ahead.
+  // Measured (4096 frames): 64 channels 133 -> 122 us, stride-2 view (128 virtual channels) 107 -> 99 us -- configurations
+  // that are one CTA per SM anyway (TMEM / shared memory); 32 channels 159 -> 171 us and the stem 650 -> 713 us lose more
+  // from the halved CTA count (each CTA = one MMA-issuing thread) than they gain: two stages there.
+  constexpr int NSW = (XMODE != 0 && C >= 64) ? 4 : 2;
   constexpr int NACC = KW * MT;
   constexpr int TCOLS_RAW = NACC * N;
   constexpr int TMEM_COLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
   static_assert(TCOLS_RAW <= 512, "accumulators exceed TMEM");
   static_assert(N == 32 || N == 64, "dy rows are 64 / 128 bytes: SWIZZLE_64B / SWIZZLE_128B");
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mma_bar[2];
-  __shared__ __align__(8) uint64_t dy_bar[2];
+  __shared__ __align__(8) uint64_t mma_bar[NSW];
+  __shared__ __align__(8) uint64_t dy_bar[NSW];
   __shared__ uint32_t tmem_slot;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -406,15 +412,13 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   const CUtensorMap* const tmap_xp = &tmap_x;
 
   if (tid == 0) {
-    mbar_init(&mma_bar[0], 1);
-    mbar_init(&mma_bar[1], 1);
-    mbar_init(&dy_bar[0], 1);
-    mbar_init(&dy_bar[1], 1);
+#pragma unroll
+    for (int i = 0; i < NSW; ++i) { mbar_init(&mma_bar[i], 1); mbar_init(&dy_bar[i], 1); }
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, TMEM_COLS);
   // the padding halo rows are read by the (discarded) padding M rows: keep them finite
-  for (int st = 0; st < 2; ++st)
+  for (int st = 0; st < NSW; ++st)
     for (int v = tid; v < (HROWS - HROWS_LOAD) * RP / 16; v += 128) {
       const uint32_t addr = sbase + st * STAGE + DY_BYTES + HROWS_LOAD * RP + v * 16;
       asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(0u) : "memory");
@@ -458,7 +462,7 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   };
   const int first = blockIdx.x, stride = gridDim.x;
   const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
-  if (my_n > 0) {
+  if (XMODE == 0 && my_n > 0) {
     fetch_x(first);
     commit_tile(first, 0);
   }
@@ -471,20 +475,20 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
   // A = bf16 twin of the forward activations (halo), B = output gradients (bf16); mixed fp16 x bf16 is not legal
   constexpr uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
 
-  for (int it = 0; it < my_n; ++it) {
-    const bool more = it + 1 < my_n;
-    if (more) fetch_x(first + (it + 1) * stride);                 // global loads in flight ...
-    if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);   // ... while the stage drains
-    if (more) commit_tile(first + (it + 1) * stride, (it + 1) & 1);
-    cp_async_commit();
-    cp_async_wait<1>();         // cp.async variant: this thread's copies of tile it (issued an iteration ago)
-    fence_proxy_async_smem();   // st.shared / cp.async (generic proxy) -> tcgen05 (async proxy)
-    __syncthreads();
+  if (XMODE != 0) {
+    // both operands by TMA: ONE thread runs the whole pipeline, NSW-1 tiles of loads ahead of the tensor core
     if (tid == 0) {
-      mbar_wait(&dy_bar[it & 1], (it >> 1) & 1);   // the TMA'd dy tile
-      fence_after_sync();
-      const uint32_t sd = sbase + (it & 1) * STAGE;
-      const uint32_t sh = sd + DY_BYTES;
+      for (int p = 0; p < NSW - 1 && p < my_n; ++p) commit_tile(first + p * stride, p);
+      for (int it = 0; it < my_n; ++it) {
+        const int nxt = it + NSW - 1;
+        if (nxt < my_n) {
+          if (nxt >= NSW) mbar_wait(&mma_bar[nxt % NSW], ((nxt / NSW) - 1) & 1);   // the MMAs that read this stage
+          commit_tile(first + nxt * stride, nxt % NSW);
+        }
+        mbar_wait(&dy_bar[it % NSW], (it / NSW) & 1);
+        fence_after_sync();
+        const uint32_t sd = sbase + (it % NSW) * STAGE;
+        const uint32_t sh = sd + DY_BYTES;
 #pragma unroll
       for (int s = 0; s < KW; ++s)
 #pragma unroll
@@ -497,11 +501,43 @@ conv_halo_wgrad_kernel(const HaloWgradArgs a, const __grid_constant__ CUtensorMa
             const uint64_t db = make_smem_desc(sd + ks * (16 * N * 2), 0, 8 * N * 2, N == 64 ? kSwizzle128B : kSwizzle64B);
             mma_bf16_ss(tmem_base + (uint32_t)((s * MT + mt) * N), da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
           }
-      mma_commit(&mma_bar[it & 1]);
+        mma_commit(&mma_bar[it % NSW]);
+      }
+    }
+    __syncthreads();
+  } else {
+  for (int it = 0; it < my_n; ++it) {
+      const bool more = it + 1 < my_n;
+      if (more) fetch_x(first + (it + 1) * stride);                 // global loads in flight ...
+      if (it >= 1) mbar_wait(&mma_bar[(it - 1) & 1], ((it - 1) >> 1) & 1);   // ... while the stage drains
+      if (more) commit_tile(first + (it + 1) * stride, (it + 1) & 1);
+      cp_async_commit();
+      cp_async_wait<1>();         // cp.async variant: this thread's copies of tile it (issued an iteration ago)
+      fence_proxy_async_smem();   // st.shared / cp.async (generic proxy) -> tcgen05 (async proxy)
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(&dy_bar[it & 1], (it >> 1) & 1);   // the TMA'd dy tile
+        fence_after_sync();
+        const uint32_t sd = sbase + (it & 1) * STAGE;
+        const uint32_t sh = sd + DY_BYTES;
+#pragma unroll
+        for (int s = 0; s < KW; ++s)
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < TH / 2; ++ks) {
+              // A: M = row blocks (stride P), K = 16 pixels = tile rows 2ks, 2ks+1 (stride RP)
+              const uint64_t da = make_smem_desc(sh + 2 * ks * RP + s * 16 + mt * 16 * P, RP, P, kNoSwizzle);
+              // B: MN-major swizzled rows (one pixel = N channels = 64 / 128 bytes); K16 = 2 groups of 8 rows
+              const uint64_t db = make_smem_desc(sd + ks * (16 * N * 2), 0, 8 * N * 2, N == 64 ? kSwizzle128B : kSwizzle64B);
+              mma_bf16_ss(tmem_base + (uint32_t)((s * MT + mt) * N), da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            }
+        mma_commit(&mma_bar[it & 1]);
+      }
     }
   }
   if (my_n > 0) {
-    mbar_wait(&mma_bar[(my_n - 1) & 1], ((my_n - 1) >> 1) & 1);
+    mbar_wait(&mma_bar[(my_n - 1) % NSW], ((my_n - 1) / NSW) & 1);
     fence_after_sync();
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
@@ -1433,7 +1469,8 @@ static int launch_halo_wgrad(const HaloWgradArgs& a, cudaStream_t st) {
   constexpr int CJ = C / 8, HWD = TW + KW - 1, P = HWD * 16, RP = CJ * P;
   constexpr int MT = (KH * CJ + 15) / 16, RMAX = (MT * 16 + CJ - 1) / CJ, HROWS = TH - 1 + RMAX;
   constexpr int STAGE = (128 * N * 2 + HROWS * RP + 1023) / 1024 * 1024;
-  const size_t smem = 2 * (size_t)STAGE + 1024 + 64;
+  constexpr int NSW = (XMODE != 0 && C >= 64) ? 4 : 2;   // ring depth: must match the kernel
+  const size_t smem = NSW * (size_t)STAGE + 1024 + 64;
   EncodeTiledFn enc = halo_encode_fn();
   if (!enc) {
     set_last_error("conv_halo_wgrad: cuTensorMapEncodeTiled is not available from this driver");
