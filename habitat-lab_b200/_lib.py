@@ -52,6 +52,8 @@ SIGNATURES = {
     "hb200_set_halo_tma": ("i", "i"),
     "hb200_get_halo_tma": ("i", ""),
     "hb200_conv_s2_supported": ("i", "iiiii"),
+    "hb200_set_conv_s2_ws": ("i", "i"),
+    "hb200_get_conv_s2_ws": ("i", ""),
     "hb200_conv_s2_wgrad_supported": ("i", "iiii"),
     "hb200_conv_s2_wgrad": ("i", "ppp" + "iiiii" + "p"),
     "hb200_unpack_s2_wgrad": ("i", "pp" + "ii" + "p"),

@@ -395,6 +395,207 @@ __global__ void __launch_bounds__(128) conv_s2_dgrad_kernel(const S2Args a, cons
   if (warp == 0) tmem_dealloc(tmem_base, 2 * NOUT);
 }
 
+// ---- warp-specialised variant with swizzled pixel-row copies (default) ------------------------------------------------
+// The kernels above feed the tensor core from 16-byte TMA pieces (8-channel slabs): every slab-fed kernel of this library
+// tops out near 12 B / clk / SM of TMA traffic (~3.4 TB/s).  Here a stage holds FOUR copies of the tile rows, each
+// [17 rows][8 pixels][128 B] in the 128-byte-swizzle K-major layout, one TMA box each (128-byte rows: 8x fewer pieces):
+//   forward: copy (dy, kx) = sub-row dy of the space-to-depth view, pre-shifted by kx block columns; a filter tap (r, s) reads
+//            copy (dy(r), kx(s)) shifted by ky(r) whole atoms, K offset dx(s) * 64 B inside the 128-byte (dx, c) row
+//   dgrad:   copy (t, kx) = tensor t of (dya | dyb) pre-shifted by kx; K block kk of the 128 reduction channels reads
+//            tensor kk / 4 at K offset (kk % 4) * 32 B
+// and the three phases are separate warps over an NS-deep stage ring (conv_halo_ws_kernel's structure): warp 4 producer,
+// warp 5 MMA issue, warps 0-3 epilogue.
+template <int C, int NA, int NB, int MODE, int NS>
+__global__ void __launch_bounds__(192) conv_s2_ws_kernel(const S2Args a, const __grid_constant__ CUtensorMap tmap_a,
+                                                         const __grid_constant__ CUtensorMap tmap_b) {
+  constexpr int N = NA + NB, HH = S2_TH + 1;
+  constexpr int NACC = MODE == 0 ? N : 4 * C;            // accumulator columns of one tile
+  constexpr uint32_t ATOM = 8 * 128, COPY = HH * ATOM, STAGE = 4 * COPY;
+  constexpr uint32_t W_BYTES = 9 * C * N * 2;
+  static_assert(C == 32 && NA == 64 && NB == 64, "conv_s2_ws: 128-byte rows = (dx, c) of 32 channels / 64-channel gradients");
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t s_w = sbase, s_halo = s_w + W_BYTES;   // W_BYTES = 72 KB: the stages stay 1024-byte aligned
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tfull_bar[0], 1); mbar_init(&tfull_bar[1], 1);
+    mbar_init(&tempty_bar[0], 4); mbar_init(&tempty_bar[1], 4);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 2 * NACC);
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.wimg);
+    for (int v = tid; v < (int)(W_BYTES / 16); v += 192) cp_async16(s_w + (uint32_t)v * 16, src + v, true);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+  const int tiles_x = a.Wo / S2_TW, tiles_per_img = tiles_x * (a.Ho / S2_TH);
+  const int first = blockIdx.x, stride = gridDim.x;
+  const int my_n = first < a.ntiles ? (a.ntiles - first + stride - 1) / stride : 0;
+  const CUtensorMap* const pa = &tmap_a;   // param-space addresses, taken in the kernel body
+  const CUtensorMap* const pb = &tmap_b;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int it = 0; it < my_n; ++it) {
+        const int st = it % NS;
+        if (it >= NS) mbar_wait(&empty_bar[st], ((it / NS) - 1) & 1);
+        const int tile = first + it * stride;
+        const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+        const int oh0 = (r / tiles_x) * S2_TH, ow0 = (r % tiles_x) * S2_TW;
+        const uint32_t sh = s_halo + (uint32_t)st * STAGE;
+        mbar_expect_tx(&full_bar[st], STAGE);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {   // q = (dy | tensor) * 2 + kx
+          if (MODE == 0) tma_load_5d(sh + q * COPY, pa, &full_bar[st], 0, ow0 - 1 + (q & 1), q >> 1, oh0 - 1, b);
+          else tma_load_4d(sh + q * COPY, (q >> 1) ? pb : pa, &full_bar[st], 0, ow0 + (q & 1), oh0, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    if (lane == 0) {
+      for (int it = 0; it < my_n; ++it) {
+        const int st = it % NS, acc = it & 1;
+        if (it >= 2) mbar_wait(&tempty_bar[acc], ((it >> 1) - 1) & 1);
+        mbar_wait(&full_bar[st], (it / NS) & 1);
+        fence_after_sync();
+        const uint32_t sh = s_halo + (uint32_t)st * STAGE;
+        const uint32_t tacc = tmem_base + (uint32_t)(acc * NACC);
+        if (MODE == 0) {
+          constexpr uint32_t idesc = make_idesc_f16(128, N, 0, 0, kFmtF16, kFmtF16);
+          uint32_t accum = 0;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int kk = 0; kk < C / 16; ++kk) {
+                const uint64_t da = make_smem_desc(sh + (s2_d(r) * 2 + s2_k(s)) * COPY + s2_k(r) * ATOM + s2_d(s) * 64 + kk * 32,
+                                                   16, ATOM, kSwizzle128B);
+                const uint64_t db = make_smem_desc(s_w + (r * 3 + s) * (C * N * 2) + 2 * kk * (N * 16), N * 16, 128,
+                                                   kNoSwizzle);
+                mma_bf16_ss(tacc, da, db, idesc, accum);
+                accum = 1;
+              }
+        } else {
+          constexpr uint32_t idesc = make_idesc_bf16(128, C, 0, 0);
+#pragma unroll
+          for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+              uint32_t accum = 0;
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                if (((dy + 1 - r) & 1) != 0) continue;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                  if (((dx + 1 - s) & 1) != 0) continue;
+                  const int ky = (dy + 1 - r) / 2, kx = (dx + 1 - s) / 2;
+                  const int tap = (2 - r) * 3 + (2 - s);
+#pragma unroll
+                  for (int kk = 0; kk < N / 16; ++kk) {
+                    const uint64_t da = make_smem_desc(sh + ((kk / 4) * 2 + kx) * COPY + ky * ATOM + (kk % 4) * 32, 16, ATOM,
+                                                       kSwizzle128B);
+                    const uint64_t db = make_smem_desc(s_w + tap * (C * N * 2) + 2 * kk * (C * 16), C * 16, 128, kNoSwizzle);
+                    mma_bf16_ss(tacc + (uint32_t)((dy * 2 + dx) * C), da, db, idesc, accum);
+                    accum = 1;
+                  }
+                }
+              }
+            }
+        }
+        mma_commit(&empty_bar[st]);
+        mma_commit(&tfull_bar[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int py = tid >> 3, px = tid & 7;
+    for (int it = 0; it < my_n; ++it) {
+      const int acc = it & 1;
+      const int tile = first + it * stride;
+      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+      const int oh0 = (r / tiles_x) * S2_TH, ow0 = (r % tiles_x) * S2_TW;
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * NACC);
+      uint32_t rr[NACC];
+#pragma unroll
+      for (int col0 = 0; col0 < NACC; col0 += 32) tmem_ld32(taddr + col0, *reinterpret_cast<uint32_t(*)[32]>(&rr[col0]));
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+#pragma unroll
+      for (int col0 = 0; col0 < NACC; col0 += 32) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[col0 + j]);
+        if (MODE == 0) {
+          const size_t pix = ((size_t)b * a.Ho + oh0 + py) * a.Wo + ow0 + px;
+          const bool second = col0 >= NA;
+          double* stats = second ? a.stats_b : a.stats_a;
+          if (stats != nullptr) {
+            const int groups = second ? a.groups_b : a.groups_a;
+            s2_gn_stats_chunk(v, lane, (second ? NB : NA) / groups, stats + (size_t)b * groups * 2, col0 - (second ? NA : 0));
+          }
+          __half* out = second ? reinterpret_cast<__half*>(a.yb) + pix * NB + (col0 - NA)
+                               : reinterpret_cast<__half*>(a.ya) + pix * NA + col0;
+          uint4* dst = reinterpret_cast<uint4*>(out);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_f16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            u.y = pack_f16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            u.z = pack_f16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            u.w = pack_f16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            dst[q] = u;
+          }
+        } else {
+          const int H = 2 * a.Ho, W = 2 * a.Wo;
+          const int q4 = col0 / C, c0 = col0 - q4 * C;
+          const size_t o = ((((size_t)b * H + 2 * (oh0 + py) + (q4 >> 1)) * W) + 2 * (ow0 + px) + (q4 & 1)) * C + c0;
+          if (a.addend != nullptr) {
+            const uint4* ad = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.addend) + o);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float f[8];
+              unpack8(ad[q], f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[q * 8 + e] += f[e];
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.ya) + o);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            u.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            u.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            u.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            dst[q] = u;
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 2 * NACC);
+}
+
+int g_s2_ws = getenv("HB200_NO_CONV_S2_WS") ? 0 : 1;
+
 typedef CUresult (*S2EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -430,6 +631,9 @@ int s2_grid(const void* kern, size_t smem, int tmem_cols, int ntiles) {
 
 using namespace hb200;
 
+extern "C" int hb200_set_conv_s2_ws(int on) { g_s2_ws = on ? 1 : 0; return HB200_OK; }
+extern "C" int hb200_get_conv_s2_ws(void) { return g_s2_ws; }
+
 extern "C" int hb200_conv_s2_supported(int c, int na, int nb, int h, int w) {
   return c == 32 && na == 64 && nb == 64 && h % (2 * S2_TH) == 0 && w % (2 * S2_TW) == 0;
 }
@@ -451,11 +655,14 @@ extern "C" int hb200_conv_s2_fwd(const hb200_f16* x, const hb200_f16* wimg, hb20
   const cuuint64_t dims[5] = {(cuuint64_t)2 * c, (cuuint64_t)w / 2, 2, (cuuint64_t)h / 2, (cuuint64_t)batch};
   const cuuint64_t strides[4] = {(cuuint64_t)2 * c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)2 * w * c * 2,
                                  (cuuint64_t)h * w * c * 2};
-  const cuuint32_t box[5] = {8u, (cuuint32_t)(S2_TW + 1), 1u, (cuuint32_t)(S2_TH + 1), 1u};
+  const cuuint32_t box_slab[5] = {8u, (cuuint32_t)(S2_TW + 1), 1u, (cuuint32_t)(S2_TH + 1), 1u};
+  // warp-specialised variant: whole 128-byte (dx, c) rows of 8 block columns, swizzled (one box per (dy, kx) copy)
+  const cuuint32_t box_rows[5] = {(cuuint32_t)(2 * c), (cuuint32_t)S2_TW, 1u, (cuuint32_t)(S2_TH + 1), 1u};
   const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
-  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)x, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)x, dims, strides, g_s2_ws ? box_rows : box_slab,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         g_s2_ws ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("conv_s2_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
     return HB200_ERR_CUDA;
@@ -468,6 +675,21 @@ extern "C" int hb200_conv_s2_fwd(const hb200_f16* x, const hb200_f16* wimg, hb20
   constexpr int C = 32, NA = 64, NB = 64, N = NA + NB;
   constexpr size_t slab = (size_t)(((S2_TH + 1) * (S2_TW + 1) * 16 + 127) / 128 * 128);
   const size_t smem = 9 * C * N * 2 + (4 * C / 8) * slab + 128;   // 112 KB + alignment slack: two CTAs per SM
+  if (g_s2_ws) {
+    constexpr int NS = 2;
+    const size_t smem_ws = 9 * C * N * 2 + NS * (size_t)(4 * (S2_TH + 1) * 8 * 128) + 1024;
+    auto kws = conv_s2_ws_kernel<C, NA, NB, 0, NS>;
+    static bool attr = false;
+    if (!attr) {
+      HB_CUDA(cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+      attr = true;
+    }
+    const int gws = kNumSMs < a.ntiles ? kNumSMs : a.ntiles;   // 208 KB of shared memory: one CTA per SM
+    kws<<<gws, 192, smem_ws, (cudaStream_t)stream>>>(a, tmap, tmap);
+    HB_LAUNCH_OK();
+    count_launch(1);
+    return HB200_OK;
+  }
   auto kern = conv_s2_fwd_kernel<C, NA, NB>;
   static int grid_cache = 0;
   if (grid_cache == 0) {
@@ -493,14 +715,17 @@ extern "C" int hb200_conv_s2_dgrad(const hb200_bf16* dya, const hb200_bf16* dyb,
   }
   const int ho = h / 2, wo = w / 2;
   CUtensorMap ta, tb;
-  const cuuint32_t box[4] = {8u, (cuuint32_t)(S2_TW + 1), (cuuint32_t)(S2_TH + 1), 1u};
+  const cuuint32_t box_slab[4] = {8u, (cuuint32_t)(S2_TW + 1), (cuuint32_t)(S2_TH + 1), 1u};
+  const cuuint32_t box_rows[4] = {64u, (cuuint32_t)S2_TW, (cuuint32_t)(S2_TH + 1), 1u};   // ws variant: 128-byte pixel rows
+  const cuuint32_t* box = g_s2_ws ? box_rows : box_slab;
   const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   for (int which = 0; which < 2; ++which) {
     const int n = which ? nb : na;
     const cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)wo, (cuuint64_t)ho, (cuuint64_t)batch};
     const cuuint64_t strides[3] = {(cuuint64_t)n * 2, (cuuint64_t)wo * n * 2, (cuuint64_t)ho * wo * n * 2};
     const CUresult r = enc(which ? &tb : &ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(which ? dyb : dya), dims,
-                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           g_s2_ws ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_last_error("conv_s2_dgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -515,6 +740,21 @@ extern "C" int hb200_conv_s2_dgrad(const hb200_bf16* dya, const hb200_bf16* dyb,
   constexpr int C = 32, NA = 64, NB = 64, N = NA + NB;
   constexpr size_t slab = (size_t)(((S2_TH + 1) * (S2_TW + 1) * 16 + 127) / 128 * 128);
   const size_t smem = 9 * C * N * 2 + (N / 8) * slab + 128;
+  if (g_s2_ws) {
+    constexpr int NS = 2;
+    const size_t smem_ws = 9 * C * N * 2 + NS * (size_t)(4 * (S2_TH + 1) * 8 * 128) + 1024;
+    auto kws = conv_s2_ws_kernel<C, NA, NB, 1, NS>;
+    static bool attr = false;
+    if (!attr) {
+      HB_CUDA(cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ws));
+      attr = true;
+    }
+    const int gws = kNumSMs < a.ntiles ? kNumSMs : a.ntiles;
+    kws<<<gws, 192, smem_ws, (cudaStream_t)stream>>>(a, ta, tb);
+    HB_LAUNCH_OK();
+    count_launch(1);
+    return HB200_OK;
+  }
   auto kern = conv_s2_dgrad_kernel<C, NA, NB>;
   static int grid_cache = 0;
   if (grid_cache == 0) {

@@ -248,6 +248,10 @@ int hb200_conv_halo_wgrad_supported(int c, int n, int k, int h, int w);
  *            packed with mode 1 (c = NA + NB, n = C).
  * Supported: C = 32, NA = NB = 64, H % 32 == 0, W % 16 == 0 (layer2.0 of the resnet18 encoder at 256x256 input). */
 int hb200_conv_s2_supported(int c, int na, int nb, int h, int w);
+/* forward / dgrad variant: 1 (default) = warp-specialised pipeline over swizzled 128-byte pixel-row copies, 0 = one-thread
+ * pipeline over 16-byte channel slabs (HB200_NO_CONV_S2_WS=1 in the environment selects 0 at load time) */
+int hb200_set_conv_s2_ws(int on);
+int hb200_get_conv_s2_ws(void);
 /* weight gradient of the 3x3 stride-2 branch over the same space-to-depth view (x halo = one 5-D TMA box per tile):
  * x bf16 [B,H,W,C] (twin of the forward input), dy bf16 [B,H/2,W/2,N]; dw_acc f32 [16*C][N], pre-zeroed, rows
  * ((ky*2+kx)*4 + dy*2+dx)*C + c; hb200_unpack_s2_wgrad writes the 9 real taps as OIHW.  C = 32, N = 64. */

@@ -363,8 +363,18 @@ def test_conv_fwd_dgrad_wgrad(hb, case):
                                    atol=2e-2 * max(1.0, dx_ref.abs().max().item()))
 
 
+@pytest.fixture(params=[1, 0], ids=["ws_swizzled", "slabs"])
+def s2_variant(hb, request):
+    """forward / dgrad of the stride-2 block entry: warp-specialised swizzled pixel-row copies (default) or 16-byte slabs"""
+    lib = hb.load()
+    prev = lib.hb200_get_conv_s2_ws()
+    lib.hb200_set_conv_s2_ws(request.param)
+    yield request.param
+    lib.hb200_set_conv_s2_ws(prev)
+
+
 @pytest.mark.parametrize("B,H,W", [(3, 32, 32), (2, 64, 16), (160, 32, 32)])
-def test_conv_s2_block_entry(hb, B, H, W):
+def test_conv_s2_block_entry(hb, s2_variant, B, H, W):
     """conv_s2.cu: 3x3 stride-2 conv + 1x1 stride-2 downsample conv of one input in one launch (forward with both
     GroupNorm sums, and the summed data gradient) over the TMA space-to-depth view, vs torch convolutions."""
     from habitat_lab_b200 import ops
